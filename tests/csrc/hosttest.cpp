@@ -1,0 +1,135 @@
+// Host-side test harness (tests only): runs the product's __host__ __device__ pre-tokenizer
+// rules on the CPU so they can be fuzzed against the oracle's regex engine without a GPU.
+#include <vector>
+#include <cstring>
+#include "../../splintr_b200/csrc/spl_pretok.h"
+#include "../../splintr_b200/csrc/unicode_tables.inc"
+
+struct HostText {
+    const uint8_t* p;
+    uint8_t byte(uint32_t i) const { return p[i]; }
+};
+
+extern "C" {
+
+// sequential scan of one segment [0,n): starts[i]=1 at every piece start
+int ht_scan_seq(int pattern, const uint8_t* text, uint32_t n, uint8_t* starts) {
+    HostText t{text};
+    SplScanner<HostText> sc(t, spl_ucd_stage1, spl_ucd_stage2, pattern);
+    memset(starts, 0, n + 1);
+    uint32_t p = 0;
+    while (p < n) {
+        starts[p] = 1;
+        uint32_t e = sc.next_end(p, n);
+        if (e <= p) return -1;
+        p = e;
+    }
+    return 0;
+}
+
+// emulation of the device work split: one "thread" per `chunk` bytes; a thread starts at
+// the first sync point inside its chunk and scans until the first piece start that is
+// >= chunk end AND a sync point.  `hard` marks segment starts (hard[n] must be 1).
+int ht_scan_chunked(int pattern, const uint8_t* text, uint32_t n, uint32_t chunk,
+                    const uint8_t* hard, uint8_t* starts, uint32_t* n_sync) {
+    HostText t{text};
+    SplScanner<HostText> sc(t, spl_ucd_stage1, spl_ucd_stage2, pattern);
+    memset(starts, 0, n + 1);
+    uint32_t ns = 0;
+    for (uint32_t c0 = 0; c0 < n; c0 += chunk) {
+        uint32_t c1 = c0 + chunk < n ? c0 + chunk : n;
+        // segment containing c0
+        uint32_t S = c0; while (!hard[S]) --S;
+        uint32_t E = c0 + 1; while (!hard[E]) ++E;
+        uint32_t a = c0;
+        bool found = false;
+        for (; a < c1; ++a) {
+            if (hard[a]) { S = a; E = a + 1; while (!hard[E]) ++E; found = true; break; }
+            if ((text[a] & 0xC0) == 0x80) continue;
+            if (sc.is_sync(a, S, E)) { found = true; break; }
+        }
+        if (!found) continue;
+        ++ns;
+        uint32_t p = a;
+        for (;;) {
+            if (starts[p]) return -2;          // two threads own the same piece
+            starts[p] = 1;
+            uint32_t e = sc.next_end(p, E);
+            if (e <= p || e > E) return -1;
+            p = e;
+            if (p >= n) break;
+            if (p == E) { S = E; E = S + 1; while (!hard[E]) ++E; }
+            if (p >= c1 && sc.is_sync(p, S, E)) break;
+        }
+    }
+    if (n_sync) *n_sync = ns;
+    return 0;
+}
+
+}
+
+// ---------------------------------------------------------------------------------------
+// Host emulation of the device piece encoder: same tables, same probes, same merge rule
+// (pair table keyed by symbol ids, leftmost minimum, in-place part bitmap).
+#include "../../splintr_b200/csrc/spl_host.h"
+
+static void ht_bpe_piece(const SplHostTables& T, const uint8_t* p, uint32_t n, std::vector<uint32_t>& out) {
+    uint32_t whole = spl_host_lookup_piece(T, p, n);
+    if (whole != SPL_RANK_NONE) { out.push_back(whole); return; }
+    std::vector<uint32_t> sym(n), rnk(n, SPL_RANK_NONE);
+    std::vector<uint8_t> live(n, 1);
+    for (uint32_t i = 0; i < n; ++i) sym[i] = T.byte_sym[p[i]];
+    for (uint32_t i = 0; i + 1 < n; ++i) rnk[i] = spl_host_lookup_pair(T, sym[i], sym[i + 1]);
+    for (;;) {
+        uint32_t best = SPL_RANK_NONE, bi = 0;
+        for (uint32_t i = 0; i < n; ++i) if (rnk[i] < best) { best = rnk[i]; bi = i; }
+        if (best == SPL_RANK_NONE) break;
+        uint32_t j = bi + 1; while (!live[j]) ++j;
+        sym[bi] = best; live[j] = 0; rnk[j] = SPL_RANK_NONE;
+        uint32_t k = j + 1; while (k < n && !live[k]) ++k;
+        rnk[bi] = (k < n) ? spl_host_lookup_pair(T, best, sym[k]) : SPL_RANK_NONE;
+        if (bi > 0) {
+            uint32_t h = bi - 1; while (!live[h]) --h;
+            rnk[h] = spl_host_lookup_pair(T, sym[h], best);
+        }
+    }
+    for (uint32_t i = 0; i < n; ++i) if (live[i] && sym[i] < SPL_UNK_BASE) out.push_back(sym[i]);
+}
+
+extern "C" {
+
+void* ht_create(const uint8_t* vocab, size_t vocab_len, int pattern, uint32_t flags,
+                const char* const* sp_strs, const uint32_t* sp_ids, size_t n_sp, char* err, size_t errcap) {
+    SplHostTables* t = new SplHostTables();
+    if (!spl_build_tables(*t, vocab, vocab_len, pattern, flags, sp_strs, sp_ids, n_sp)) {
+        strncpy(err, t->error.c_str(), errcap - 1); err[errcap - 1] = 0;
+        delete t; return nullptr;
+    }
+    return t;
+}
+void ht_destroy(void* h) { delete (SplHostTables*)h; }
+void ht_stats(void* h, uint64_t* out) {
+    SplHostTables* t = (SplHostTables*)h;
+    out[0] = t->encoder.size(); out[1] = t->n_pairs; out[2] = t->t8_log2; out[3] = t->t16_log2;
+    out[4] = t->tl_log2; out[5] = t->pair_log2; out[6] = t->max_key_len; out[7] = t->specials_unambiguous;
+}
+
+// encode one segment (no special handling); returns token count or -1
+long ht_encode(void* h, const uint8_t* text, uint32_t n, uint32_t* ids, size_t cap) {
+    SplHostTables* T = (SplHostTables*)h;
+    HostText t{text};
+    SplScanner<HostText> sc(t, spl_ucd_stage1, spl_ucd_stage2, T->pattern);
+    std::vector<uint32_t> out;
+    uint32_t p = 0;
+    while (p < n) {
+        uint32_t e = sc.next_end(p, n);
+        if (e <= p || e > n) return -1;
+        ht_bpe_piece(*T, text + p, e - p, out);
+        p = e;
+    }
+    if (out.size() > cap) return -2;
+    memcpy(ids, out.data(), out.size() * 4);
+    return (long)out.size();
+}
+
+}
