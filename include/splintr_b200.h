@@ -1,0 +1,126 @@
+/* splintr_b200 -- C ABI of the B200-native batch BPE encoder.
+ *
+ * This is the drop-in boundary for ONE path of ml-rust/splintr: Tokenizer::encode_batch
+ * (and encode / encode_with_special / encode_batch_with_special, which are the same path
+ * with one text / with the special-token scan).  A host (the reference's PyO3 class, or
+ * the ctypes host in splintr_b200/tokenizer.py) packs its texts into ONE contiguous UTF-8
+ * byte buffer plus n_docs+1 offsets and calls spl_encode_batch; everything between the
+ * packed bytes and the token ids runs on the GPU.  There is no CPU implementation behind
+ * these entry points: without a CUDA device spl_create fails with SPL_ERR_NO_DEVICE.
+ *
+ * Reference interfaces replaced (paths under the reference repository):
+ *   spl_create            <- Tokenizer::from_bytes / from_bytes_byte_level        src/core/tokenizer.rs:552-569
+ *                            (+ with_full_options: regex build, Aho-Corasick build  src/core/tokenizer.rs:410-456)
+ *                            Python: Tokenizer.from_pretrained / from_bytes / __new__  src/python/bindings.rs:70-187
+ *   spl_encode_batch      <- Tokenizer::encode_batch                              src/core/tokenizer.rs:932-934
+ *                            Tokenizer::encode_batch_with_special (flag)           src/core/tokenizer.rs:937-942
+ *                            Tokenizer::encode / encode_with_special (n_docs = 1)  src/core/tokenizer.rs:729-808, 842-874
+ *                            Python: bindings.rs:254-288, 337-350
+ *   spl_encode_batch_device  (same path, device-resident buffers; no reference counterpart)
+ *   spl_destroy           <- Drop for Tokenizer
+ *   spl_last_error        <- TokenizerError Display                               src/core/tokenizer.rs:19-36
+ *
+ * Conventions: every function returns SPL_OK (0) or a negative SPL_ERR_* code and never
+ * throws across the ABI.  Inputs are owned by the caller and only read during the call.
+ * Results are owned by the library (pinned host memory) until spl_result_free.  One call
+ * in flight per tokenizer handle; distinct handles may be used from distinct threads.
+ */
+#ifndef SPLINTR_B200_H
+#define SPLINTR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct spl_tokenizer spl_tokenizer;
+typedef struct spl_result spl_result;
+
+enum {
+    SPL_OK = 0,
+    SPL_ERR_INVALID_ARG = -1,   /* null pointer, bad offsets, unknown pattern id ...        */
+    SPL_ERR_VOCAB = -2,         /* vocabulary data does not parse (reference: VocabError)   */
+    SPL_ERR_CUDA = -3,          /* a CUDA runtime call or kernel failed                     */
+    SPL_ERR_OOM = -4,           /* host or device allocation failed                         */
+    SPL_ERR_UNSUPPORTED = -5,   /* valid request this implementation cannot serve exactly   */
+    SPL_ERR_NO_DEVICE = -6      /* no usable CUDA device (there is no CPU fallback)         */
+};
+
+/* pattern_id: which of the reference's split patterns the pre-tokenizer reproduces */
+#define SPL_PATTERN_CL100K      0   /* CL100K_BASE_PATTERN  src/core/tokenizer.rs:39            */
+#define SPL_PATTERN_O200K       1   /* O200K_BASE_PATTERN = LLAMA3_PATTERN  tokenizer.rs:42,45  */
+#define SPL_PATTERN_MISTRAL_V3  2   /* MISTRAL_V3_PATTERN  src/core/tokenizer.rs:64             */
+
+/* spl_create flags */
+#define SPL_CREATE_BYTE_LEVEL   1u  /* vocabulary keys are GPT-2 byte-level strings (from_bytes_byte_level) */
+
+/* spl_encode_batch flags */
+#define SPL_ENCODE_WITH_SPECIAL 1u  /* recognise special-token strings (encode_batch_with_special) */
+
+typedef struct spl_stats {
+    uint64_t n_docs;
+    uint64_t n_bytes;          /* input bytes                                   */
+    uint64_t n_tokens;         /* output ids                                    */
+    uint64_t h2d_bytes;        /* bytes copied host -> device for this call     */
+    uint64_t d2h_bytes;        /* bytes copied device -> host for this call     */
+    float kernel_ms;           /* device time of the kernels (max over devices) */
+    float total_ms;            /* device time incl. copies (max over devices)   */
+    int n_devices;
+    int n_launches;            /* kernels launched (all devices)                */
+} spl_stats;
+
+/* Build a tokenizer: parse `vocab` (tiktoken format: "base64 SP rank LF" lines), build the
+ * device tables on every listed device.  `devices` may be NULL (=> device 0 only).
+ * On failure *out is NULL and spl_last_error(NULL) describes the error. */
+int spl_create(const uint8_t* vocab, size_t vocab_len, int pattern_id, uint32_t flags,
+               const char* const* special_strs, const uint32_t* special_ids, size_t n_special,
+               const int* devices, int n_devices, spl_tokenizer** out);
+
+void spl_destroy(spl_tokenizer* tok);
+
+/* Last error message of `tok` (or of the last failed spl_create when tok is NULL). */
+const char* spl_last_error(const spl_tokenizer* tok);
+
+/* Encode n_docs documents.  `bytes` holds the concatenated UTF-8 texts, document i is
+ * bytes[offsets[i] .. offsets[i+1]); offsets has n_docs+1 entries, offsets[0] == 0.
+ * Documents are sharded over the handle's devices by cumulative bytes.  Host buffers may be
+ * pageable or pinned (spl_alloc_pinned). */
+int spl_encode_batch(spl_tokenizer* tok, const uint8_t* bytes, const uint64_t* offsets, size_t n_docs,
+                     uint32_t flags, spl_result** out);
+
+const uint32_t* spl_result_ids(const spl_result* r);       /* n_tokens ids, document order        */
+const uint64_t* spl_result_offsets(const spl_result* r);   /* n_docs+1 offsets into ids            */
+size_t spl_result_n_docs(const spl_result* r);
+size_t spl_result_n_tokens(const spl_result* r);
+void spl_result_stats(const spl_result* r, spl_stats* out);
+void spl_result_free(spl_result* r);
+
+/* Device-resident variant on the handle's device number `dev_index` (index into the
+ * `devices` list of spl_create): all four buffers are device pointers on that device;
+ * d_bytes must be 16-byte aligned and readable up to n_bytes rounded up to 16;
+ * d_ids must hold ids_capacity >= n_bytes entries (worst case: one id per byte).
+ * Work is enqueued on `cuda_stream` (a cudaStream_t, NULL = legacy default stream).
+ * If n_tokens_out is non-NULL the call synchronises the stream and stores the id count;
+ * otherwise it returns after enqueueing (d_out_offsets[n_docs] holds the count). */
+int spl_encode_batch_device(spl_tokenizer* tok, int dev_index,
+                            const uint8_t* d_bytes, size_t n_bytes,
+                            const uint64_t* d_offsets, size_t n_docs, uint32_t flags,
+                            uint32_t* d_ids, size_t ids_capacity, uint64_t* d_out_offsets,
+                            void* cuda_stream, uint64_t* n_tokens_out);
+
+/* number of kernels one spl_encode_batch_device call launches for these flags */
+int spl_launches_per_call(const spl_tokenizer* tok, uint32_t flags);
+
+/* pinned host memory helpers for callers that want full-rate PCIe copies */
+void* spl_alloc_pinned(size_t bytes);
+void spl_free_pinned(void* p);
+
+/* library / build identification, e.g. "splintr_b200 0.1.0 sm_100a" */
+const char* spl_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPLINTR_B200_H */

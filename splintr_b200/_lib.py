@@ -1,0 +1,125 @@
+"""Loader (ctypes) and in-tree build of the C-ABI shared library.
+
+The library is the product; there is no Python or CPU fallback behind it.  If it is
+missing or cannot be loaded, importing a Tokenizer fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import List, Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libsplintr_b200.so")
+SOURCES = ["spl_api.cu", "spl_kernels.cu", "spl_host.cpp"]
+HEADERS = ["spl_common.h", "spl_pretok.h", "spl_host.h", "spl_kernels.cuh", "unicode_tables.inc",
+           os.path.join("..", "..", "include", "splintr_b200.h")]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into splintr_b200/libsplintr_b200.so."""
+    if not force and not needs_build():
+        return LIB_PATH
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    if verbose:
+        print(proc.stderr)
+    return LIB_PATH
+
+
+class SplStats(ctypes.Structure):
+    _fields_ = [("n_docs", ctypes.c_uint64), ("n_bytes", ctypes.c_uint64), ("n_tokens", ctypes.c_uint64),
+                ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),
+                ("kernel_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
+                ("n_devices", ctypes.c_int), ("n_launches", ctypes.c_int)]
+
+
+# every symbol include/splintr_b200.h declares
+EXPORTS = ["spl_create", "spl_destroy", "spl_last_error", "spl_encode_batch", "spl_result_ids",
+           "spl_result_offsets", "spl_result_n_docs", "spl_result_n_tokens", "spl_result_stats",
+           "spl_result_free", "spl_encode_batch_device", "spl_launches_per_call", "spl_alloc_pinned",
+           "spl_free_pinned", "spl_version"]
+
+SPL_OK, SPL_ERR_INVALID_ARG, SPL_ERR_VOCAB, SPL_ERR_CUDA, SPL_ERR_OOM, SPL_ERR_UNSUPPORTED, SPL_ERR_NO_DEVICE = \
+    0, -1, -2, -3, -4, -5, -6
+SPL_CREATE_BYTE_LEVEL = 1
+SPL_ENCODE_WITH_SPECIAL = 1
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built "
+            "(run `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "splintr_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, u8p, u32p, u64p = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p
+    lib.spl_create.restype = ctypes.c_int
+    lib.spl_create.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32,
+                               ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_uint32), ctypes.c_size_t,
+                               ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.POINTER(vp)]
+    lib.spl_destroy.restype = None
+    lib.spl_destroy.argtypes = [vp]
+    lib.spl_last_error.restype = ctypes.c_char_p
+    lib.spl_last_error.argtypes = [vp]
+    lib.spl_encode_batch.restype = ctypes.c_int
+    lib.spl_encode_batch.argtypes = [vp, u8p, u64p, ctypes.c_size_t, ctypes.c_uint32, ctypes.POINTER(vp)]
+    lib.spl_result_ids.restype = vp
+    lib.spl_result_ids.argtypes = [vp]
+    lib.spl_result_offsets.restype = vp
+    lib.spl_result_offsets.argtypes = [vp]
+    lib.spl_result_n_docs.restype = ctypes.c_size_t
+    lib.spl_result_n_docs.argtypes = [vp]
+    lib.spl_result_n_tokens.restype = ctypes.c_size_t
+    lib.spl_result_n_tokens.argtypes = [vp]
+    lib.spl_result_stats.restype = None
+    lib.spl_result_stats.argtypes = [vp, ctypes.POINTER(SplStats)]
+    lib.spl_result_free.restype = None
+    lib.spl_result_free.argtypes = [vp]
+    lib.spl_encode_batch_device.restype = ctypes.c_int
+    lib.spl_encode_batch_device.argtypes = [vp, ctypes.c_int, u8p, ctypes.c_size_t, u64p, ctypes.c_size_t,
+                                            ctypes.c_uint32, u32p, ctypes.c_size_t, u64p, vp,
+                                            ctypes.POINTER(ctypes.c_uint64)]
+    lib.spl_launches_per_call.restype = ctypes.c_int
+    lib.spl_launches_per_call.argtypes = [vp, ctypes.c_uint32]
+    lib.spl_alloc_pinned.restype = vp
+    lib.spl_alloc_pinned.argtypes = [ctypes.c_size_t]
+    lib.spl_free_pinned.restype = None
+    lib.spl_free_pinned.argtypes = [vp]
+    lib.spl_version.restype = ctypes.c_char_p
+    lib.spl_version.argtypes = []
+    _lib = lib
+    return lib
+
+
+def last_error(handle=None) -> str:
+    msg = load().spl_last_error(handle)
+    return msg.decode("utf-8", "replace") if msg else ""

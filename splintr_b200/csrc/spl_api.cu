@@ -1,0 +1,493 @@
+// C-ABI of splintr_b200 (include/splintr_b200.h): handle lifetime, device tables,
+// per-call workspace, host<->device staging, document sharding over the handle's devices.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/splintr_b200.h"
+#include "spl_host.h"
+#include "spl_kernels.cuh"
+#include "unicode_tables.inc"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+#define CUDA_TRY(expr, errstr)                                                            \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            (errstr) = std::string(#expr) + ": " + cudaGetErrorString(_e);                \
+            return _e == cudaErrorMemoryAllocation ? SPL_ERR_OOM : SPL_ERR_CUDA;          \
+        }                                                                                 \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes, std::string& err) {
+        if (bytes <= cap) return SPL_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { err = std::string("cudaMalloc: ") + cudaGetErrorString(e); p = nullptr; return SPL_ERR_OOM; }
+        cap = want;
+        return SPL_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct DevCtx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    void* table_blob = nullptr;
+    SplTables* d_tables = nullptr;
+    DevBuf text, doc_off, hard, spec, pstart, tfd, tstate, counters, huge, ids, out_off;
+    size_t huge_words = 0;
+};
+
+struct PinnedBuf { void* p; size_t cap; };
+
+}  // namespace
+
+struct spl_tokenizer {
+    SplHostTables host;
+    std::vector<DevCtx> devs;
+    std::string err;
+    std::mutex pool_mu;
+    std::vector<PinnedBuf> pinned_pool;
+};
+
+struct spl_result {
+    spl_tokenizer* owner;
+    PinnedBuf ids_buf, off_buf;
+    size_t n_docs, n_tokens;
+    spl_stats stats;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { cudaGetDevice(&prev); }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int upload_tables(spl_tokenizer* tk, DevCtx& dc) {
+    const SplHostTables& h = tk->host;
+    struct Part { const void* src; size_t bytes; size_t off; };
+    std::vector<Part> parts;
+    size_t total = 0;
+    auto add = [&](const void* src, size_t bytes) { Part p{src, bytes, total}; total = align_up(total + std::max<size_t>(bytes, 16), 256); parts.push_back(p); return parts.size() - 1; };
+    size_t i_s1 = add(spl_ucd_stage1, sizeof(spl_ucd_stage1));
+    size_t i_s2 = add(spl_ucd_stage2, sizeof(spl_ucd_stage2));
+    size_t i_t8 = add(h.t8.data(), h.t8.size() * sizeof(SplKey8));
+    size_t i_t16 = add(h.t16.data(), h.t16.size() * sizeof(SplKey16));
+    size_t i_tl = add(h.tl.data(), h.tl.size() * sizeof(SplKeyL));
+    size_t i_tb = add(h.tok_bytes.data(), h.tok_bytes.size());
+    size_t i_to = add(h.tok_off.data(), h.tok_off.size() * 4);
+    size_t i_pair = add(h.pair.data(), h.pair.size() * 8);
+    size_t i_spb = add(h.sp_bytes.data(), h.sp_bytes.size());
+    size_t i_spo = add(h.sp_off.data(), h.sp_off.size() * 4);
+    size_t i_spi = add(h.sp_id.data(), h.sp_id.size() * 4);
+    size_t i_struct = add(nullptr, sizeof(SplTables));
+    CUDA_TRY(cudaMalloc(&dc.table_blob, total), tk->err);
+    uint8_t* base = (uint8_t*)dc.table_blob;
+    for (auto& p : parts)
+        if (p.src && p.bytes) CUDA_TRY(cudaMemcpy(base + p.off, p.src, p.bytes, cudaMemcpyHostToDevice), tk->err);
+    SplTables t;
+    memset(&t, 0, sizeof(t));
+    t.ucd_stage1 = base + parts[i_s1].off;
+    t.ucd_stage2 = base + parts[i_s2].off;
+    t.t8 = (const SplKey8*)(base + parts[i_t8].off);     t.t8_log2 = h.t8_log2;
+    t.t16 = (const SplKey16*)(base + parts[i_t16].off);  t.t16_log2 = h.t16_log2;
+    t.tl = (const SplKeyL*)(base + parts[i_tl].off);     t.tl_log2 = h.tl_log2;
+    t.tok_bytes = base + parts[i_tb].off;
+    t.tok_off = (const uint32_t*)(base + parts[i_to].off);
+    t.n_ids = h.n_ids;
+    t.max_key_len = h.max_key_len;
+    t.pair = (const uint64_t*)(base + parts[i_pair].off); t.pair_log2 = h.pair_log2;
+    memcpy(t.byte_sym, h.byte_sym, sizeof(t.byte_sym));
+    t.sp_bytes = base + parts[i_spb].off;
+    t.sp_off = (const uint32_t*)(base + parts[i_spo].off);
+    t.sp_id = (const uint32_t*)(base + parts[i_spi].off);
+    t.n_special = (uint32_t)h.sp_id.size();
+    memcpy(t.sp_first, h.sp_first, sizeof(t.sp_first));
+    t.pattern = h.pattern;
+    dc.d_tables = (SplTables*)(base + parts[i_struct].off);
+    CUDA_TRY(cudaMemcpy(dc.d_tables, &t, sizeof(t), cudaMemcpyHostToDevice), tk->err);
+    return SPL_OK;
+}
+
+void destroy_ctx(DevCtx& dc) {
+    cudaSetDevice(dc.device);
+    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.hard, &dc.spec, &dc.pstart, &dc.tfd, &dc.tstate, &dc.counters, &dc.huge, &dc.ids, &dc.out_off})
+        b->release();
+    if (dc.table_blob) cudaFree(dc.table_blob);
+    for (auto& e : dc.ev) if (e) cudaEventDestroy(e);
+    if (dc.stream) cudaStreamDestroy(dc.stream);
+}
+
+// limits of one device shard: 32-bit positions inside the kernels
+const uint64_t kMaxShardBytes = 0xFFFFFFFFull - 4ull * SPL_WIN;
+
+// Prepare the internal workspace of `dc` for N bytes / n_docs documents and fill `w`
+// (text / doc_off / ids / out_off are set by the caller).  Enqueues the zero-fills.
+int prepare_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, bool with_special,
+                 cudaStream_t st, SplWork& w) {
+    if (N > kMaxShardBytes || n_docs > 0xFFFFFFF0ull) {
+        tk->err = "a single device shard is limited to 4 GiB of text";
+        return SPL_ERR_UNSUPPORTED;
+    }
+    size_t words = (size_t)((N + SPL_WIN) / 32 + 16);
+    uint32_t n_tiles = (uint32_t)(N / SPL_TILE) + 1;
+    int rc;
+    if ((rc = dc.hard.ensure(words * 4, tk->err))) return rc;
+    if ((rc = dc.pstart.ensure(words * 4, tk->err))) return rc;
+    if (with_special && (rc = dc.spec.ensure(words * 4, tk->err))) return rc;
+    if ((rc = dc.tfd.ensure((size_t)(n_tiles + 2) * 4, tk->err))) return rc;
+    if ((rc = dc.tstate.ensure((size_t)n_tiles * 8, tk->err))) return rc;
+    if ((rc = dc.counters.ensure(64, tk->err))) return rc;
+    if (dc.huge_words == 0) dc.huge_words = (size_t)16 << 20;             // 64 MiB of scratch
+    if ((rc = dc.huge.ensure(dc.huge_words * 4, tk->err))) return rc;
+    CUDA_TRY(cudaMemsetAsync(dc.hard.p, 0, words * 4, st), tk->err);
+    CUDA_TRY(cudaMemsetAsync(dc.pstart.p, 0, words * 4, st), tk->err);
+    if (with_special) CUDA_TRY(cudaMemsetAsync(dc.spec.p, 0, words * 4, st), tk->err);
+    CUDA_TRY(cudaMemsetAsync(dc.tstate.p, 0, (size_t)n_tiles * 8, st), tk->err);
+    CUDA_TRY(cudaMemsetAsync(dc.counters.p, 0, 64, st), tk->err);
+    w.N = (uint32_t)N;
+    w.n_docs = (uint32_t)n_docs;
+    w.n_tiles = n_tiles;
+    w.hard = (uint32_t*)dc.hard.p;
+    w.spec = with_special ? (uint32_t*)dc.spec.p : nullptr;
+    w.pstart = (uint32_t*)dc.pstart.p;
+    w.bitmap_words = words;
+    w.tile_first_doc = (uint32_t*)dc.tfd.p;
+    w.tile_state = (uint64_t*)dc.tstate.p;
+    w.counters = (uint32_t*)dc.counters.p;
+    w.huge_pool = (uint32_t*)dc.huge.p;
+    w.huge_pool_words = (uint32_t)std::min<size_t>(dc.huge_words, 0xFFFFFFFFu);
+    w.T = dc.d_tables;
+    w.pattern = tk->host.pattern;
+    w.with_special = with_special;
+    return SPL_OK;
+}
+
+int check_special_support(spl_tokenizer* tk, uint32_t flags, bool& with_special) {
+    with_special = (flags & SPL_ENCODE_WITH_SPECIAL) && !tk->host.sp_id.empty();
+    if (with_special && !tk->host.specials_unambiguous) {
+        tk->err = "special-token set is ambiguous (one string contains or overlaps another); not supported on device";
+        return SPL_ERR_UNSUPPORTED;
+    }
+    return SPL_OK;
+}
+
+PinnedBuf take_pinned(spl_tokenizer* tk, size_t bytes) {
+    bytes = std::max<size_t>(bytes, 64);
+    {
+        std::lock_guard<std::mutex> g(tk->pool_mu);
+        size_t best = (size_t)-1;
+        for (size_t i = 0; i < tk->pinned_pool.size(); ++i)
+            if (tk->pinned_pool[i].cap >= bytes && (best == (size_t)-1 || tk->pinned_pool[i].cap < tk->pinned_pool[best].cap)) best = i;
+        if (best != (size_t)-1) {
+            PinnedBuf b = tk->pinned_pool[best];
+            tk->pinned_pool.erase(tk->pinned_pool.begin() + best);
+            return b;
+        }
+    }
+    PinnedBuf b{nullptr, 0};
+    size_t want = bytes + bytes / 8;
+    if (cudaHostAlloc(&b.p, want, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); b.p = nullptr; return b; }
+    b.cap = want;
+    return b;
+}
+
+void give_pinned(spl_tokenizer* tk, PinnedBuf b) {
+    if (!b.p) return;
+    std::lock_guard<std::mutex> g(tk->pool_mu);
+    if (tk->pinned_pool.size() >= 8) { cudaFreeHost(b.p); return; }
+    tk->pinned_pool.push_back(b);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* spl_version(void) { return "splintr_b200 0.1.0 sm_100a"; }
+
+int spl_create(const uint8_t* vocab, size_t vocab_len, int pattern_id, uint32_t flags,
+               const char* const* special_strs, const uint32_t* special_ids, size_t n_special,
+               const int* devices, int n_devices, spl_tokenizer** out) {
+    if (!out) return SPL_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (!vocab || (n_special && (!special_strs || !special_ids))) { g_create_error = "null argument"; return SPL_ERR_INVALID_ARG; }
+    if (pattern_id != SPL_PATTERN_CL100K && pattern_id != SPL_PATTERN_O200K && pattern_id != SPL_PATTERN_MISTRAL_V3) {
+        g_create_error = "unknown pattern id";
+        return SPL_ERR_INVALID_ARG;
+    }
+    int ndev_avail = 0;
+    if (cudaGetDeviceCount(&ndev_avail) != cudaSuccess || ndev_avail == 0) {
+        cudaGetLastError();
+        g_create_error = "no CUDA device available (splintr_b200 has no CPU fallback)";
+        return SPL_ERR_NO_DEVICE;
+    }
+    spl_tokenizer* tk = new (std::nothrow) spl_tokenizer();
+    if (!tk) return SPL_ERR_OOM;
+    uint32_t hflags = (flags & SPL_CREATE_BYTE_LEVEL) ? SPL_FLAG_BYTE_LEVEL : 0;
+    if (!spl_build_tables(tk->host, vocab, vocab_len, pattern_id, hflags, special_strs, special_ids, n_special)) {
+        g_create_error = tk->host.error;
+        bool unsupported = tk->host.error.find("byte-level vocabulary") != std::string::npos ||
+                           tk->host.error.find("not supported") != std::string::npos;
+        delete tk;
+        return unsupported ? SPL_ERR_UNSUPPORTED : SPL_ERR_VOCAB;
+    }
+    DeviceGuard guard;
+    std::vector<int> devs;
+    if (!devices || n_devices <= 0) devs.push_back(guard.prev >= 0 ? guard.prev : 0);
+    else devs.assign(devices, devices + n_devices);
+    tk->devs.resize(devs.size());
+    int rc = SPL_OK;
+    for (size_t i = 0; i < devs.size() && rc == SPL_OK; ++i) {
+        DevCtx& dc = tk->devs[i];
+        dc.device = devs[i];
+        if (dc.device < 0 || dc.device >= ndev_avail) { tk->err = "device index out of range"; rc = SPL_ERR_INVALID_ARG; break; }
+        auto init = [&]() -> int {
+            CUDA_TRY(cudaSetDevice(dc.device), tk->err);
+            CUDA_TRY(cudaDeviceGetAttribute(&dc.num_sms, cudaDevAttrMultiProcessorCount, dc.device), tk->err);
+            CUDA_TRY(cudaStreamCreateWithFlags(&dc.stream, cudaStreamNonBlocking), tk->err);
+            for (auto& e : dc.ev) CUDA_TRY(cudaEventCreate(&e), tk->err);
+            spl_kernels_init();
+            return upload_tables(tk, dc);
+        };
+        rc = init();
+    }
+    if (rc != SPL_OK) {
+        g_create_error = tk->err;
+        for (auto& dc : tk->devs) destroy_ctx(dc);
+        delete tk;
+        return rc;
+    }
+    *out = tk;
+    return SPL_OK;
+}
+
+void spl_destroy(spl_tokenizer* tk) {
+    if (!tk) return;
+    DeviceGuard guard;
+    for (auto& dc : tk->devs) destroy_ctx(dc);
+    for (auto& b : tk->pinned_pool) cudaFreeHost(b.p);
+    delete tk;
+}
+
+const char* spl_last_error(const spl_tokenizer* tk) { return tk ? tk->err.c_str() : g_create_error.c_str(); }
+
+int spl_launches_per_call(const spl_tokenizer* tk, uint32_t flags) {
+    if (!tk) return 0;
+    bool ws = (flags & SPL_ENCODE_WITH_SPECIAL) && !tk->host.sp_id.empty();
+    return ws ? 4 : 3;
+}
+
+void* spl_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, std::max<size_t>(bytes, 64), cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void spl_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+int spl_encode_batch_device(spl_tokenizer* tk, int dev_index, const uint8_t* d_bytes, size_t n_bytes,
+                            const uint64_t* d_offsets, size_t n_docs, uint32_t flags,
+                            uint32_t* d_ids, size_t ids_capacity, uint64_t* d_out_offsets,
+                            void* cuda_stream, uint64_t* n_tokens_out) {
+    if (!tk) return SPL_ERR_INVALID_ARG;
+    if (dev_index < 0 || (size_t)dev_index >= tk->devs.size() || !d_offsets || !d_out_offsets ||
+        (n_bytes && (!d_bytes || !d_ids)) || ids_capacity < n_bytes || ((uintptr_t)d_bytes & 15u)) {
+        tk->err = "invalid argument (null pointer, ids_capacity < n_bytes, or d_bytes not 16-byte aligned)";
+        return SPL_ERR_INVALID_ARG;
+    }
+    bool with_special;
+    int rc = check_special_support(tk, flags, with_special);
+    if (rc) return rc;
+    DeviceGuard guard;
+    DevCtx& dc = tk->devs[dev_index];
+    CUDA_TRY(cudaSetDevice(dc.device), tk->err);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    for (int attempt = 0;; ++attempt) {
+        SplWork w;
+        memset(&w, 0, sizeof(w));
+        if ((rc = prepare_work(tk, dc, n_bytes, n_docs, with_special, st, w))) return rc;
+        w.text = d_bytes; w.doc_off = d_offsets; w.ids = d_ids; w.out_off = d_out_offsets;
+        spl_launch_encode(w, dc.num_sms, st);
+        CUDA_TRY(cudaGetLastError(), tk->err);
+        if (!n_tokens_out) return SPL_OK;
+        uint32_t h_counters[4];
+        uint64_t total = 0;
+        CUDA_TRY(cudaMemcpyAsync(h_counters, w.counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st), tk->err);
+        CUDA_TRY(cudaMemcpyAsync(&total, d_out_offsets + n_docs, 8, cudaMemcpyDeviceToHost, st), tk->err);
+        CUDA_TRY(cudaStreamSynchronize(st), tk->err);
+        if (h_counters[1] & SPL_DEVERR_OFFSETS) { tk->err = "document offsets are not a non-decreasing sequence from 0 to n_bytes"; return SPL_ERR_INVALID_ARG; }
+        if (h_counters[1] & SPL_DEVERR_HUGE_POOL) {
+            if (attempt >= 6) { tk->err = "scratch pool for very long pieces exhausted"; return SPL_ERR_OOM; }
+            dc.huge_words = std::max<size_t>(dc.huge_words * 4, (size_t)h_counters[2] + 1024);
+            continue;
+        }
+        *n_tokens_out = total;
+        return SPL_OK;
+    }
+}
+
+int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* offsets, size_t n_docs,
+                     uint32_t flags, spl_result** out) {
+    if (!tk || !out) return SPL_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (!offsets || offsets[0] != 0) { tk->err = "offsets must start at 0"; return SPL_ERR_INVALID_ARG; }
+    const uint64_t N = offsets[n_docs];
+    if (N && !bytes) { tk->err = "null bytes"; return SPL_ERR_INVALID_ARG; }
+    for (size_t i = 0; i < n_docs; ++i)
+        if (offsets[i + 1] < offsets[i]) { tk->err = "offsets must be non-decreasing"; return SPL_ERR_INVALID_ARG; }
+    bool with_special;
+    int rc = check_special_support(tk, flags, with_special);
+    if (rc) return rc;
+
+    // ---- shard documents over devices by cumulative bytes ----------------------------------
+    const size_t G = tk->devs.size();
+    std::vector<size_t> dlo(G + 1, 0);
+    for (size_t g = 1; g < G; ++g) {
+        uint64_t target = N / G * g;
+        size_t d = std::lower_bound(offsets, offsets + n_docs + 1, target) - offsets;
+        dlo[g] = std::max(std::min(d, n_docs), dlo[g - 1]);
+    }
+    dlo[G] = n_docs;
+
+    DeviceGuard guard;
+    spl_result* r = new (std::nothrow) spl_result();
+    if (!r) return SPL_ERR_OOM;
+    memset(&r->stats, 0, sizeof(r->stats));
+    r->owner = tk; r->n_docs = n_docs; r->n_tokens = 0;
+    r->ids_buf = PinnedBuf{nullptr, 0};
+    r->off_buf = take_pinned(tk, (n_docs + 1) * 8);
+    if (!r->off_buf.p) { delete r; tk->err = "pinned host allocation failed"; return SPL_ERR_OOM; }
+    uint64_t* res_off = (uint64_t*)r->off_buf.p;
+    auto fail = [&](int code) { give_pinned(tk, r->off_buf); give_pinned(tk, r->ids_buf); delete r; return code; };
+
+    std::vector<SplWork> works(G);
+    std::vector<uint64_t> shard_tokens(G, 0);
+    std::vector<std::vector<uint32_t>> h_counters(G, std::vector<uint32_t>(4, 0));
+    int launches = 0;
+
+    for (int attempt = 0;; ++attempt) {
+        launches = 0;
+        // phase 1: copy in, run, copy offsets out -- all devices enqueued before any sync
+        for (size_t g = 0; g < G; ++g) {
+            DevCtx& dc = tk->devs[g];
+            auto run = [&]() -> int {
+                CUDA_TRY(cudaSetDevice(dc.device), tk->err);
+                const size_t nd = dlo[g + 1] - dlo[g];
+                const uint64_t b0 = offsets[dlo[g]], b1 = offsets[dlo[g + 1]], nb = b1 - b0;
+                SplWork& w = works[g];
+                memset(&w, 0, sizeof(w));
+                int rc2;
+                if ((rc2 = dc.text.ensure(nb + 64, tk->err))) return rc2;
+                if ((rc2 = dc.doc_off.ensure((nd + 1) * 8, tk->err))) return rc2;
+                if ((rc2 = dc.ids.ensure((nb + 16) * 4, tk->err))) return rc2;
+                if ((rc2 = dc.out_off.ensure((nd + 1) * 8, tk->err))) return rc2;
+                CUDA_TRY(cudaEventRecord(dc.ev[0], dc.stream), tk->err);
+                if (nb) CUDA_TRY(cudaMemcpyAsync(dc.text.p, bytes + b0, nb, cudaMemcpyHostToDevice, dc.stream), tk->err);
+                CUDA_TRY(cudaMemcpyAsync(dc.doc_off.p, offsets + dlo[g], (nd + 1) * 8, cudaMemcpyHostToDevice, dc.stream), tk->err);
+                if ((rc2 = prepare_work(tk, dc, nb, nd, with_special, dc.stream, w))) return rc2;
+                w.text = (const uint8_t*)dc.text.p;
+                w.doc_off = (const uint64_t*)dc.doc_off.p;
+                w.off_base = b0;
+                w.ids = (uint32_t*)dc.ids.p;
+                w.out_off = (uint64_t*)dc.out_off.p;
+                CUDA_TRY(cudaEventRecord(dc.ev[1], dc.stream), tk->err);
+                launches += spl_launch_encode(w, dc.num_sms, dc.stream);
+                CUDA_TRY(cudaGetLastError(), tk->err);
+                CUDA_TRY(cudaEventRecord(dc.ev[2], dc.stream), tk->err);
+                CUDA_TRY(cudaMemcpyAsync(res_off + dlo[g], dc.out_off.p, (nd + (g + 1 == G ? 1 : 0)) * 8, cudaMemcpyDeviceToHost, dc.stream), tk->err);
+                CUDA_TRY(cudaMemcpyAsync(&shard_tokens[g], (uint64_t*)dc.out_off.p + nd, 8, cudaMemcpyDeviceToHost, dc.stream), tk->err);
+                CUDA_TRY(cudaMemcpyAsync(h_counters[g].data(), dc.counters.p, 16, cudaMemcpyDeviceToHost, dc.stream), tk->err);
+                r->stats.h2d_bytes += nb + (nd + 1) * 8;
+                r->stats.d2h_bytes += (nd + 1) * 8 + 8 + 16;
+                return SPL_OK;
+            };
+            if ((rc = run())) return fail(rc);
+        }
+        bool retry = false;
+        for (size_t g = 0; g < G; ++g) {
+            DevCtx& dc = tk->devs[g];
+            cudaSetDevice(dc.device);
+            cudaError_t e = cudaStreamSynchronize(dc.stream);
+            if (e != cudaSuccess) { tk->err = std::string("encode kernels: ") + cudaGetErrorString(e); return fail(SPL_ERR_CUDA); }
+            if (h_counters[g][1] & SPL_DEVERR_OFFSETS) { tk->err = "invalid document offsets"; return fail(SPL_ERR_INVALID_ARG); }
+            if (h_counters[g][1] & SPL_DEVERR_HUGE_POOL) {
+                dc.huge_words = std::max<size_t>(dc.huge_words * 4, (size_t)h_counters[g][2] + 1024);
+                retry = true;
+            }
+        }
+        if (!retry) break;
+        if (attempt >= 6) { tk->err = "scratch pool for very long pieces exhausted"; return fail(SPL_ERR_OOM); }
+        memset(&r->stats, 0, sizeof(r->stats));
+    }
+
+    // phase 2: ids out
+    uint64_t total = 0;
+    std::vector<uint64_t> tok_base(G + 1, 0);
+    for (size_t g = 0; g < G; ++g) { tok_base[g] = total; total += shard_tokens[g]; }
+    tok_base[G] = total;
+    r->ids_buf = take_pinned(tk, (total + 16) * 4);
+    if (!r->ids_buf.p) { tk->err = "pinned host allocation failed"; return fail(SPL_ERR_OOM); }
+    for (size_t g = 0; g < G; ++g) {
+        DevCtx& dc = tk->devs[g];
+        cudaSetDevice(dc.device);
+        if (shard_tokens[g]) {
+            cudaError_t e = cudaMemcpyAsync((uint32_t*)r->ids_buf.p + tok_base[g], dc.ids.p, shard_tokens[g] * 4, cudaMemcpyDeviceToHost, dc.stream);
+            if (e != cudaSuccess) { tk->err = std::string("cudaMemcpyAsync ids: ") + cudaGetErrorString(e); return fail(SPL_ERR_CUDA); }
+        }
+        cudaEventRecord(dc.ev[3], dc.stream);
+        r->stats.d2h_bytes += shard_tokens[g] * 4;
+    }
+    float kmax = 0, tmax = 0;
+    for (size_t g = 0; g < G; ++g) {
+        DevCtx& dc = tk->devs[g];
+        cudaSetDevice(dc.device);
+        cudaError_t e = cudaStreamSynchronize(dc.stream);
+        if (e != cudaSuccess) { tk->err = std::string("copy-out: ") + cudaGetErrorString(e); return fail(SPL_ERR_CUDA); }
+        float k = 0, t = 0;
+        cudaEventElapsedTime(&k, dc.ev[1], dc.ev[2]);
+        cudaEventElapsedTime(&t, dc.ev[0], dc.ev[3]);
+        kmax = std::max(kmax, k); tmax = std::max(tmax, t);
+        if (g > 0 && tok_base[g]) {
+            for (size_t d = dlo[g]; d < dlo[g + 1] + (g + 1 == G ? 1 : 0); ++d) res_off[d] += tok_base[g];
+        }
+    }
+    r->n_tokens = total;
+    r->stats.n_docs = n_docs; r->stats.n_bytes = N; r->stats.n_tokens = total;
+    r->stats.kernel_ms = kmax; r->stats.total_ms = tmax;
+    r->stats.n_devices = (int)G; r->stats.n_launches = launches;
+    *out = r;
+    return SPL_OK;
+}
+
+const uint32_t* spl_result_ids(const spl_result* r) { return r ? (const uint32_t*)r->ids_buf.p : nullptr; }
+const uint64_t* spl_result_offsets(const spl_result* r) { return r ? (const uint64_t*)r->off_buf.p : nullptr; }
+size_t spl_result_n_docs(const spl_result* r) { return r ? r->n_docs : 0; }
+size_t spl_result_n_tokens(const spl_result* r) { return r ? r->n_tokens : 0; }
+void spl_result_stats(const spl_result* r, spl_stats* out) { if (r && out) *out = r->stats; }
+void spl_result_free(spl_result* r) {
+    if (!r) return;
+    give_pinned(r->owner, r->ids_buf);
+    give_pinned(r->owner, r->off_buf);
+    delete r;
+}
+
+}  // extern "C"

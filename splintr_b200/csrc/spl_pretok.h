@@ -25,14 +25,14 @@ SPL_HD uint32_t spl_class_of_cp(uint32_t cp, const uint8_t* s1, const uint8_t* s
 // Decode the character starting at byte i (i < E).  Malformed or truncated sequences are
 // treated as one-byte CLS_OTHER characters (the reference only ever sees valid UTF-8).
 template <class T>
-SPL_HD SplChar spl_decode(const T& t, uint32_t i, uint32_t E, const uint8_t* s1, const uint8_t* s2) {
+SPL_HD SplChar spl_decode(const T& t, uint32_t i, uint32_t E, const uint8_t* s1, const uint8_t* s2, bool* hit = nullptr) {
     uint32_t b0 = t.byte(i);
     SplChar c;
     if (b0 < 0x80u) { c.cls = spl_ascii_class(b0); c.len = 1; return c; }
     c.cls = CLS_OTHER; c.len = 1;
     if (b0 < 0xC2u || b0 > 0xF4u) return c;
     uint32_t need = b0 < 0xE0u ? 2u : (b0 < 0xF0u ? 3u : 4u);
-    if (E - i < need) return c;
+    if (E - i < need) { if (hit) *hit = true; return c; }
     uint32_t b1 = t.byte(i + 1);
     if ((b1 & 0xC0u) != 0x80u) return c;
     uint32_t cp;
@@ -70,13 +70,17 @@ SPL_HD uint32_t spl_prev_char_start(const T& t, uint32_t i, uint32_t S) {
 // (LATIN SMALL LETTER LONG S, bytes C5 BF) -> 's' (verified over all code points by
 // tools/gen_unicode_tables.py).
 template <class T>
-SPL_HD uint32_t spl_contraction(const T& t, uint32_t a, uint32_t E) {
-    if (a + 1 >= E || t.byte(a) != '\'') return 0;
+SPL_HD uint32_t spl_contraction(const T& t, uint32_t a, uint32_t E, bool* hit = nullptr) {
+    if (a >= E) { if (hit) *hit = true; return 0; }
+    if (t.byte(a) != '\'') return 0;
+    if (a + 1 >= E) { if (hit) *hit = true; return 0; }
     uint32_t b1 = t.byte(a + 1);
     uint32_t l1 = b1 | 0x20u;
     if (b1 < 0x80u) {
         if (l1 == 's' || l1 == 't' || l1 == 'm' || l1 == 'd') return 2;
-        if (a + 2 < E) {
+        if (l1 != 'r' && l1 != 'v' && l1 != 'l') return 0;
+        if (a + 2 >= E) { if (hit) *hit = true; return 0; }
+        {
             uint32_t b2 = t.byte(a + 2);
             uint32_t l2 = b2 | 0x20u;
             if (b2 < 0x80u) {
@@ -86,24 +90,37 @@ SPL_HD uint32_t spl_contraction(const T& t, uint32_t a, uint32_t E) {
         }
         return 0;
     }
-    if (b1 == 0xC5u && a + 2 < E && t.byte(a + 2) == 0xBFu) return 3;   // 'ſ
+    if (b1 == 0xC5u) {                                                    // 'ſ
+        if (a + 2 >= E) { if (hit) *hit = true; return 0; }
+        if (t.byte(a + 2) == 0xBFu) return 3;
+    }
     return 0;
 }
 
-template <class T>
+// TRACK = true: `hit` is set whenever a decision depended on the segment end E (any
+// comparison `i < E` that came out false).  A caller that only knows a provisional E
+// (its staging window ends before the real segment end) re-runs with a larger E when hit.
+template <class T, bool TRACK = false>
 struct SplScanner {
     const T& t;
     const uint8_t* s1;
     const uint8_t* s2;
     int pattern;
+    mutable bool hit;
 
-    SPL_HD SplScanner(const T& t_, const uint8_t* s1_, const uint8_t* s2_, int pat) : t(t_), s1(s1_), s2(s2_), pattern(pat) {}
+    SPL_HD SplScanner(const T& t_, const uint8_t* s1_, const uint8_t* s2_, int pat) : t(t_), s1(s1_), s2(s2_), pattern(pat), hit(false) {}
 
-    SPL_HD SplChar dec(uint32_t i, uint32_t E) const { return spl_decode(t, i, E, s1, s2); }
+    SPL_HD bool lt(uint32_t i, uint32_t E) const {
+        if (i < E) return true;
+        if (TRACK) hit = true;
+        return false;
+    }
+    SPL_HD SplChar dec(uint32_t i, uint32_t E) const { return spl_decode(t, i, E, s1, s2, TRACK ? &hit : nullptr); }
+    SPL_HD uint32_t contr(uint32_t a, uint32_t E) const { return spl_contraction(t, a, E, TRACK ? &hit : nullptr); }
 
     // end of the maximal run of chars whose class is in `set`, starting at i
     SPL_HD uint32_t run_end(uint32_t i, uint32_t E, uint32_t set) const {
-        while (i < E) {
+        while (lt(i, E)) {
             SplChar c = dec(i, E);
             if (!in_set(c.cls, set)) break;
             i += c.len;
@@ -118,7 +135,7 @@ struct SplScanner {
     SPL_HD void letters_o200k(uint32_t s, uint32_t E, uint32_t& a1, uint32_t& a2) const {
         a1 = 0; a2 = 0;
         uint32_t i = s, last_both_end = 0;
-        while (i < E) {
+        while (lt(i, E)) {
             SplChar c = dec(i, E);
             if (!in_set(c.cls, CSET_U)) break;
             i += c.len;
@@ -126,7 +143,7 @@ struct SplScanner {
         }
         uint32_t e1 = i;
         bool next_lower = false;
-        if (e1 < E) { SplChar c = dec(e1, E); next_lower = (c.cls == CLS_LOWER); }
+        if (lt(e1, E)) { SplChar c = dec(e1, E); next_lower = (c.cls == CLS_LOWER); }
         if (next_lower) { a1 = run_end(e1, E, CSET_W); if (e1 > s) a2 = a1; }
         else {
             if (last_both_end) a1 = last_both_end;
@@ -139,28 +156,28 @@ struct SplScanner {
         SplChar c = dec(p, E);
         uint32_t q = p + c.len;                       // start of the second character
         if (pattern == SPL_PAT_CL100K) {
-            uint32_t k = spl_contraction(t, p, E);                                   // alt 1
+            uint32_t k = contr(p, E);                                   // alt 1
             if (k) return p + k;
             if (in_set(c.cls, CSET_L)) return run_end(q, E, CSET_L);                 // alt 2
-            if (in_set(c.cls, CSET_PREFIX) && q < E) {
+            if (in_set(c.cls, CSET_PREFIX) && lt(q, E)) {
                 SplChar n = dec(q, E);
                 if (in_set(n.cls, CSET_L)) return run_end(q + n.len, E, CSET_L);
             }
         } else {
             uint32_t a1p = 0, a2p = 0, a10 = 0, a20 = 0;
-            bool pref_ok = in_set(c.cls, CSET_PREFIX) && q < E;
+            bool pref_ok = in_set(c.cls, CSET_PREFIX) && lt(q, E);
             if (pref_ok) letters_o200k(q, E, a1p, a2p);
             if (in_set(c.cls, CSET_U | CSET_W)) letters_o200k(p, E, a10, a20);
             uint32_t e = a1p ? a1p : (a10 ? a10 : (a2p ? a2p : a20));
             if (e) {
-                if (pattern == SPL_PAT_O200K) e += spl_contraction(t, e, E);
+                if (pattern == SPL_PAT_O200K) e += contr(e, E);
                 return e;
             }
         }
         if (c.cls == CLS_NUM) {                                                       // \p{N}{1,3}
             if (pattern == SPL_PAT_MISTRAL_V3) return q;
             uint32_t i = q;
-            for (int k = 1; k < 3 && i < E; ++k) {
+            for (int k = 1; k < 3 && lt(i, E); ++k) {
                 SplChar n = dec(i, E);
                 if (n.cls != CLS_NUM) break;
                 i += n.len;
@@ -169,7 +186,7 @@ struct SplScanner {
         }
         {                                                                             //  ?[^\s\p{L}\p{N}]+[\r\n]*
             uint32_t s = p; SplChar sc = c;
-            if (c.cls == CLS_SPACE && q < E) {
+            if (c.cls == CLS_SPACE && lt(q, E)) {
                 SplChar n = dec(q, E);
                 if (in_set(n.cls, CSET_O)) { s = q; sc = n; }
             }
@@ -181,7 +198,7 @@ struct SplScanner {
         }
         // whitespace run:  \s*[\r\n]+  |  \s+(?!\S)  |  \s+
         uint32_t i = p, last_crlf_end = 0, last_start = p, nchars = 0;
-        while (i < E) {
+        while (lt(i, E)) {
             SplChar w = dec(i, E);
             if (!in_set(w.cls, CSET_WS)) break;
             last_start = i;
@@ -191,7 +208,7 @@ struct SplScanner {
         }
         if (nchars == 0) return q;               // unreachable for classified text; guarantees progress
         if (last_crlf_end) return last_crlf_end;
-        if (i == E) return i;
+        if (i >= E) { if (TRACK) hit = true; return i; }
         if (nchars >= 2) return last_start;
         return i;
     }
@@ -209,7 +226,7 @@ struct SplScanner {
         if (pc.cls == CLS_CRLF && !cws &&                                          // after a line break
             !(pattern == SPL_PAT_MISTRAL_V3 && c.cls == CLS_SLASH)) return true;   // ([\r\n/]* tail)
         if ((c.cls == CLS_NUM) != (pc.cls == CLS_NUM)) return true;                // digit <-> non-digit
-        if (cws && c.cls != CLS_CRLF && i + c.len < E) {                           // last blank before a word
+        if (cws && c.cls != CLS_CRLF && lt(i + c.len, E)) {                           // last blank before a word
             SplChar n = dec(i + c.len, E);
             if (!in_set(n.cls, CSET_WS)) return true;
         }
@@ -217,3 +234,110 @@ struct SplScanner {
         return false;
     }
 };
+
+// ---------------------------------------------------------------------------------------
+// Work split of the piece-boundary kernel, written against an environment so the very same
+// code runs in the CUDA kernel (shared-memory window + global fallback) and in the host
+// fuzz harness.
+//
+// Env concept:
+//   uint8_t  byte(uint32_t i) const            text byte (i < N)
+//   bool     hard(uint32_t i) const            segment-boundary bit (doc start, special-span edge; bit N is set)
+//   bool     spec(uint32_t i) const            byte i lies inside a special-token span (a span starts where hard && spec)
+//   uint32_t next_hard(uint32_t from, uint32_t lim) const   first hard bit in [from, lim), else lim
+//   uint32_t win_end() const                   bits below this position are cheap to query
+//   void     mark(uint32_t p)                  record "a piece starts at p"
+struct SplSegEnd { uint32_t E; bool exact; uint32_t step; };
+
+template <class Env>
+SPL_HD void spl_seg_locate(const Env& env, uint32_t p, uint32_t N, SplSegEnd& s) {
+    uint32_t from = p + 1;
+    uint32_t W = env.win_end();
+    uint32_t lim = W < N + 1 ? W : N + 1;
+    s.step = 1024;
+    if (lim > from) {
+        uint32_t x = env.next_hard(from, lim);
+        if (x < lim) { s.E = x; s.exact = true; return; }
+        from = lim;
+    }
+    s.E = from; s.exact = false;            // every position in (p, E) is clear; E itself unknown
+}
+
+template <class Env>
+SPL_HD void spl_seg_extend(const Env& env, uint32_t N, SplSegEnd& s) {
+    uint32_t lim = (N + 1 - s.E > s.step) ? s.E + s.step : N + 1;
+    uint32_t x = env.next_hard(s.E, lim);
+    if (x < lim) { s.E = x; s.exact = true; } else { s.E = lim; }
+    if (s.step < (1u << 30)) s.step <<= 1;
+}
+
+template <class Env>
+SPL_HD uint32_t spl_prev_limit(const Env& env, uint32_t i) {
+    for (uint32_t k = 1; k <= 4 && k <= i; ++k)
+        if (env.hard(i - k)) return i - k;
+    return i >= 4 ? i - 4 : 0;
+}
+
+// One worker owns the pieces that start in [a, b): a = first sync point in its chunk
+// [c0, c1), b = first sync point at or after c1.  Workers of all chunks together mark
+// every piece start exactly once.
+template <class Env>
+SPL_HD void spl_pretok_chunk(Env& env, uint32_t c0, uint32_t c1, uint32_t N,
+                             const uint8_t* s1, const uint8_t* s2, int pattern, bool with_special) {
+    SplScanner<Env, true> sc(env, s1, s2, pattern);
+    SplSegEnd se; se.E = 0; se.exact = false; se.step = 1024;
+    bool have = false, found = false;
+    uint32_t a = c0;
+    for (; a < c1; ++a) {
+        if (env.hard(a)) { found = true; have = false; break; }
+        if (with_special && env.spec(a)) continue;                  // inside a special-token span
+        if ((env.byte(a) & 0xC0u) == 0x80u) continue;
+        if (!have) { spl_seg_locate(env, a, N, se); have = true; }
+        uint32_t S = spl_prev_limit(env, a);
+        bool r;
+        for (;;) {
+            sc.hit = false;
+            r = sc.is_sync(a, S, se.E);
+            if (!sc.hit || se.exact) break;
+            spl_seg_extend(env, N, se);
+        }
+        if (r) { found = true; break; }
+    }
+    if (!found) return;
+    uint32_t p = a;
+    if (!have) spl_seg_locate(env, p, N, se);
+    for (;;) {
+        env.mark(p);
+        uint32_t e;
+        if (with_special && env.hard(p) && env.spec(p)) {
+            while (!se.exact) spl_seg_extend(env, N, se);
+            e = se.E;
+        } else {
+            for (;;) {
+                sc.hit = false;
+                e = sc.next_end(p, se.E);
+                if (!sc.hit || se.exact) break;
+                spl_seg_extend(env, N, se);
+            }
+        }
+        p = e;
+        if (p >= N) return;
+        while (p == se.E && !se.exact) spl_seg_extend(env, N, se);
+        if (p == se.E) {                                  // segment ends here: p is a hard boundary
+            if (p >= c1) return;
+            spl_seg_locate(env, p, N, se);
+            continue;
+        }
+        if (p >= c1) {
+            uint32_t S = spl_prev_limit(env, p);
+            bool r;
+            for (;;) {
+                sc.hit = false;
+                r = sc.is_sync(p, S, se.E);
+                if (!sc.hit || se.exact) break;
+                spl_seg_extend(env, N, se);
+            }
+            if (r) return;
+        }
+    }
+}

@@ -1,0 +1,337 @@
+"""Host-side mirror of the reference's Python `Tokenizer` class
+(/root/reference/src/python/bindings.rs:57-446) over the splintr_b200 C-ABI.
+
+Same method names, argument meaning and error behaviour as the PyO3 class; the encode
+methods pack the texts into one contiguous UTF-8 buffer + offsets and hand it to
+`spl_encode_batch` -- the regex split, special-token scan, BPE merge and batch loop all run
+on the GPU.  Decode is a host table lookup (tokenizer.rs:877-911), as in the reference.
+"""
+from __future__ import annotations
+
+import base64
+import ctypes
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from . import presets as _presets
+
+
+def _byte_level_maps():
+    """byte_level.rs:46-74."""
+    direct = list(range(33, 127)) + list(range(161, 173)) + list(range(174, 256))
+    b2c = {}
+    nxt = 256
+    for b in range(256):
+        if b in direct:
+            b2c[b] = chr(b)
+        else:
+            b2c[b] = chr(nxt)
+            nxt += 1
+    return b2c, {c: b for b, c in b2c.items()}
+
+
+_BYTE_TO_CHAR, _CHAR_TO_BYTE = _byte_level_maps()
+
+
+def _parse_tiktoken(data: bytes) -> Dict[bytes, int]:
+    """vocab.rs:57-89 (host copy, used for decode tables and vocab_size only)."""
+    enc: Dict[bytes, int] = {}
+    for line in data.split(b"\n"):
+        if not line:
+            continue
+        sp = line.rfind(b" ")
+        if sp < 0:
+            raise ValueError("Invalid line format: Missing space separator")
+        try:
+            tok = base64.b64decode(line[:sp], validate=True)
+        except Exception as e:  # binascii.Error
+            raise ValueError(f"Invalid base64 encoding: {e}")
+        try:
+            rank = int(line[sp + 1:].decode("utf-8").strip())
+        except Exception:
+            raise ValueError(f"Invalid line format: Invalid rank: {line[sp + 1:]!r}")
+        enc[tok] = rank
+    return enc
+
+
+class Tokenizer:
+    """Drop-in for `splintr.Tokenizer` (bindings.rs:57-446)."""
+
+    # -- construction --------------------------------------------------------------------
+    def __init__(self, vocab_path: str, pattern: str, special_tokens: Optional[Dict[str, int]] = None):
+        # bindings.rs:70-83: file errors surface as IOError
+        try:
+            with open(vocab_path, "rb") as f:
+                data = f.read()
+        except OSError as e:
+            raise IOError(str(e))
+        try:
+            self._init(data, pattern, special_tokens or {}, byte_level=False, sentencepiece=False)
+        except ValueError as e:
+            raise IOError(str(e))
+
+    @classmethod
+    def _make(cls, data: bytes, pattern: str, special_tokens: Dict[str, int], byte_level: bool,
+              sentencepiece: bool = False, devices: Optional[Sequence[int]] = None) -> "Tokenizer":
+        self = cls.__new__(cls)
+        self._init(data, pattern, special_tokens, byte_level, sentencepiece, devices)
+        return self
+
+    def _init(self, data: bytes, pattern: str, special_tokens: Dict[str, int], byte_level: bool,
+              sentencepiece: bool, devices: Optional[Sequence[int]] = None) -> None:
+        self._handle = None
+        if sentencepiece:
+            raise ValueError("SentencePiece-mode vocabularies (mistral / mistral_v2) are not served by the "
+                             "B200 encode path (see DESIGN.md, out of scope); no CPU fallback exists")
+        if not isinstance(pattern, str):
+            raise TypeError("pattern must be str")
+        pid = _presets.PATTERN_IDS.get(pattern)
+        if pid is None:
+            raise ValueError("Regex compilation error: the device pre-tokenizer implements only the "
+                             "CL100K_BASE, O200K_BASE/LLAMA3 and MISTRAL_V3 patterns")
+        for k, v in special_tokens.items():
+            if not isinstance(k, str) or not isinstance(v, int):
+                raise TypeError("special_tokens must map str -> int")
+        self._vocab_data = bytes(data)
+        self._pattern = pattern
+        self._special_tokens = dict(special_tokens)
+        self._special_decoder = {v: k for k, v in special_tokens.items()}
+        self._byte_level = bool(byte_level)
+        self._devices = list(devices) if devices is not None else None
+        self._decoder: Optional[Dict[int, bytes]] = None
+        self._vocab_size: Optional[int] = None
+
+        lib = _lib.load()
+        sp = list(special_tokens.items())
+        n = len(sp)
+        strs = (ctypes.c_char_p * max(n, 1))(*[s.encode("utf-8") for s, _ in sp])
+        ids = (ctypes.c_uint32 * max(n, 1))(*[i for _, i in sp])
+        if self._devices:
+            devs = (ctypes.c_int * len(self._devices))(*self._devices)
+            ndev = len(self._devices)
+        else:
+            devs, ndev = None, 0
+        h = ctypes.c_void_p()
+        rc = lib.spl_create(self._vocab_data, len(self._vocab_data), pid,
+                            _lib.SPL_CREATE_BYTE_LEVEL if byte_level else 0,
+                            strs, ids, n, devs, ndev, ctypes.byref(h))
+        if rc != _lib.SPL_OK:
+            msg = _lib.last_error(None)
+            if rc == _lib.SPL_ERR_NO_DEVICE:
+                raise RuntimeError(f"splintr_b200: {msg}")
+            if rc in (_lib.SPL_ERR_CUDA, _lib.SPL_ERR_OOM):
+                raise RuntimeError(f"splintr_b200: {msg} (code {rc})")
+            raise ValueError(msg or f"spl_create failed with code {rc}")
+        self._handle = h
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h:
+            try:
+                _lib.load().spl_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+    @staticmethod
+    def from_pretrained(name: str, devices: Optional[Sequence[int]] = None) -> "Tokenizer":
+        """bindings.rs:101-166.  `devices` (extension): CUDA device indices to shard over."""
+        p = _presets.get_preset(name)
+        if p is None:
+            raise ValueError(f"Unknown pretrained model: {name}. See from_pretrained docstring for supported models.")
+        return Tokenizer._make(_presets.load_vocab_bytes(p.vocab_file), p.pattern, p.special_tokens,
+                               p.byte_level, p.sentencepiece, devices)
+
+    @staticmethod
+    def from_bytes(vocab_data: bytes, pattern: str, special_tokens: Optional[Dict[str, int]] = None,
+                   devices: Optional[Sequence[int]] = None) -> "Tokenizer":
+        """bindings.rs:174-187."""
+        return Tokenizer._make(bytes(vocab_data), pattern, special_tokens or {}, False, False, devices)
+
+    @staticmethod
+    def from_bytes_byte_level(vocab_data: bytes, pattern: str, special_tokens: Optional[Dict[str, int]] = None,
+                              devices: Optional[Sequence[int]] = None) -> "Tokenizer":
+        """tokenizer.rs:562-569 (Rust-only constructor in the reference; exposed for tests)."""
+        return Tokenizer._make(bytes(vocab_data), pattern, special_tokens or {}, True, False, devices)
+
+    def _clone(self) -> "Tokenizer":
+        return Tokenizer._make(self._vocab_data, self._pattern, self._special_tokens, self._byte_level,
+                               False, self._devices)
+
+    def pcre2(self, use_pcre2: bool = True) -> "Tokenizer":
+        """bindings.rs:207-214.  There is one pre-tokenizer (the device rules); the switch
+        is accepted and returns a new instance, like the reference."""
+        return self._clone()
+
+    def jit(self, use_jit: bool = True) -> "Tokenizer":
+        """bindings.rs:235-242 (accepted and ignored)."""
+        return self._clone()
+
+    # -- encode -----------------------------------------------------------------------------
+    @staticmethod
+    def _pack(texts: Sequence[str]) -> Tuple[bytes, np.ndarray]:
+        enc = []
+        for t in texts:
+            if not isinstance(t, str):
+                raise TypeError(f"argument 'texts': '{type(t).__name__}' object cannot be converted to 'PyString'")
+            enc.append(t.encode("utf-8"))          # lone surrogates raise UnicodeEncodeError, as in PyO3
+        offsets = np.zeros(len(enc) + 1, dtype=np.uint64)
+        if enc:
+            np.cumsum(np.fromiter((len(b) for b in enc), dtype=np.uint64, count=len(enc)), out=offsets[1:])
+        return b"".join(enc), offsets
+
+    def encode_packed(self, data, offsets: np.ndarray, with_special: bool = False, return_stats: bool = False):
+        """Zero-copy surface: `data` = concatenated UTF-8 (bytes / bytearray / uint8 array /
+        integer host address), `offsets` = uint64[n_docs+1].  Returns (ids uint32[n_tokens],
+        out_offsets uint64[n_docs+1]) as numpy arrays."""
+        lib = _lib.load()
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n_docs = offsets.shape[0] - 1
+        if n_docs < 0:
+            raise ValueError("offsets must have n_docs + 1 entries")
+        if isinstance(data, (bytes, bytearray)):
+            keep = bytes(data)
+            ptr = ctypes.cast(ctypes.c_char_p(keep), ctypes.c_void_p)
+        elif isinstance(data, np.ndarray):
+            keep = np.ascontiguousarray(data, dtype=np.uint8)
+            ptr = ctypes.c_void_p(keep.ctypes.data)
+        elif isinstance(data, int):
+            keep = None
+            ptr = ctypes.c_void_p(data)
+        else:
+            raise TypeError("data must be bytes, bytearray, numpy uint8 array or an address")
+        res = ctypes.c_void_p()
+        rc = lib.spl_encode_batch(self._handle, ptr, ctypes.c_void_p(offsets.ctypes.data), n_docs,
+                                  _lib.SPL_ENCODE_WITH_SPECIAL if with_special else 0, ctypes.byref(res))
+        del keep
+        if rc != _lib.SPL_OK:
+            msg = _lib.last_error(self._handle)
+            if rc in (_lib.SPL_ERR_INVALID_ARG, _lib.SPL_ERR_UNSUPPORTED):
+                raise ValueError(msg)
+            raise RuntimeError(f"splintr_b200: {msg} (code {rc})")
+        try:
+            n_tok = lib.spl_result_n_tokens(res)
+            ids = np.empty(n_tok, dtype=np.uint32)
+            out_off = np.empty(n_docs + 1, dtype=np.uint64)
+            if n_tok:
+                ctypes.memmove(ids.ctypes.data, lib.spl_result_ids(res), n_tok * 4)
+            ctypes.memmove(out_off.ctypes.data, lib.spl_result_offsets(res), (n_docs + 1) * 8)
+            if return_stats:
+                st = _lib.SplStats()
+                lib.spl_result_stats(res, ctypes.byref(st))
+                stats = {f: getattr(st, f) for f, _ in _lib.SplStats._fields_}
+                return ids, out_off, stats
+            return ids, out_off
+        finally:
+            lib.spl_result_free(res)
+
+    def encode_batch_packed(self, texts: Sequence[str], with_special: bool = False):
+        """list[str] -> (ids uint32, offsets uint64) without building Python lists."""
+        data, offsets = self._pack(texts)
+        return self.encode_packed(data, offsets, with_special)
+
+    def _encode_many(self, texts: Sequence[str], with_special: bool) -> List[List[int]]:
+        ids, off = self.encode_batch_packed(texts, with_special)
+        flat = ids.tolist()
+        o = off.tolist()
+        return [flat[o[i]:o[i + 1]] for i in range(len(texts))]
+
+    def encode(self, text: str) -> List[int]:
+        """bindings.rs:254-256 -> tokenizer.rs:729-808 (special strings are plain text)."""
+        return self._encode_many([text], False)[0]
+
+    def encode_rayon(self, text: str) -> List[int]:
+        """bindings.rs:273-275: same ids as encode (the device path is parallel inside a text)."""
+        return self._encode_many([text], False)[0]
+
+    def encode_with_special(self, text: str) -> List[int]:
+        """bindings.rs:286-288 -> tokenizer.rs:842-874."""
+        return self._encode_many([text], True)[0]
+
+    def encode_batch(self, texts: List[str]) -> List[List[int]]:
+        """bindings.rs:337-339 -> tokenizer.rs:932-934."""
+        return self._encode_many(list(texts), False)
+
+    def encode_batch_with_special(self, texts: List[str]) -> List[List[int]]:
+        """bindings.rs:348-350 -> tokenizer.rs:937-942."""
+        return self._encode_many(list(texts), True)
+
+    # -- decode (host table lookup, tokenizer.rs:877-958) ----------------------------------
+    def _ensure_decoder(self) -> Dict[int, bytes]:
+        if self._decoder is None:
+            enc = _parse_tiktoken(self._vocab_data)
+            dec: Dict[int, bytes] = {}
+            for k, v in enc.items():
+                if self._byte_level:
+                    # tokenizer.rs:882-887: byte-level keys decode to raw bytes, else stay as they are
+                    try:
+                        raw = bytes(_CHAR_TO_BYTE[c] for c in k.decode("utf-8"))
+                    except (UnicodeDecodeError, KeyError):
+                        raw = k
+                    dec[v] = raw
+                else:
+                    dec[v] = k
+            self._decoder = dec
+        return self._decoder
+
+    def decode_bytes(self, tokens: Iterable[int]) -> bytes:
+        dec = self._ensure_decoder()
+        out = bytearray()
+        for t in tokens:
+            b = dec.get(t)
+            if b is not None:
+                out += b
+            else:
+                s = self._special_decoder.get(t)
+                if s is not None:
+                    out += s.encode("utf-8")
+        return bytes(out)
+
+    def decode(self, tokens: Iterable[int]) -> str:
+        try:
+            return self.decode_bytes(tokens).decode("utf-8")
+        except UnicodeDecodeError:
+            raise ValueError("Decoding error: invalid UTF-8")
+
+    def decode_lossy(self, tokens: Iterable[int]) -> str:
+        return self.decode_bytes(tokens).decode("utf-8", errors="replace")
+
+    def decode_batch(self, token_lists: List[List[int]]) -> List[str]:
+        return [self.decode(t) for t in token_lists]
+
+    def decode_batch_lossy(self, token_lists: List[List[int]]) -> List[str]:
+        return [self.decode_lossy(t) for t in token_lists]
+
+    # -- misc -------------------------------------------------------------------------------
+    @property
+    def vocab_size(self) -> int:
+        """tokenizer.rs:964-972: max id over vocabulary and special tokens, plus one."""
+        if self._vocab_size is None:
+            dec = self._ensure_decoder()
+            m1 = max(dec.keys(), default=0)
+            m2 = max(self._special_tokens.values(), default=0)
+            self._vocab_size = max(m1, m2) + 1
+        return self._vocab_size
+
+    def streaming_decoder(self):
+        from .streaming import StreamingDecoder
+        return StreamingDecoder(self._raw_decoder(), dict(self._special_decoder))
+
+    def byte_level_streaming_decoder(self):
+        from .streaming import ByteLevelStreamingDecoder
+        return ByteLevelStreamingDecoder(self._raw_decoder(), dict(self._special_decoder))
+
+    def _raw_decoder(self) -> Dict[int, bytes]:
+        return {v: k for k, v in _parse_tiktoken(self._vocab_data).items()}
+
+    def clear_cache(self) -> None:
+        """bindings.rs:432-434: the device path keeps no chunk cache (it is result-transparent)."""
+
+    @property
+    def cache_len(self) -> int:
+        return 0
+
+    def __repr__(self) -> str:
+        return f"Tokenizer(vocab_size={self.vocab_size})"

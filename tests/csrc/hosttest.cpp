@@ -133,3 +133,30 @@ long ht_encode(void* h, const uint8_t* text, uint32_t n, uint32_t* ids, size_t c
 }
 
 }
+
+// ---------------------------------------------------------------------------------------
+// spl_pretok_chunk (the device kernel's per-thread routine) under a host environment with
+// an artificially small tile / window, to exercise provisional segment ends.
+struct HostEnv {
+    const uint8_t* text; const uint8_t* hardb; const uint8_t* specb; uint8_t* out; uint32_t W; int* dup;
+    uint8_t byte(uint32_t i) const { return text[i]; }
+    bool hard(uint32_t i) const { return hardb[i]; }
+    bool spec(uint32_t i) const { return specb && specb[i]; }
+    uint32_t next_hard(uint32_t from, uint32_t lim) const { while (from < lim && !hardb[from]) ++from; return from; }
+    uint32_t win_end() const { return W; }
+    void mark(uint32_t p) { if (out[p]) *dup = 1; out[p] = 1; }
+};
+
+extern "C" int ht_scan_kernel_emul(int pattern, const uint8_t* text, uint32_t n, uint32_t tile, uint32_t halo,
+                                   uint32_t chunk, const uint8_t* hard, const uint8_t* spec, uint8_t* starts) {
+    memset(starts, 0, n + 1);
+    int dup = 0;
+    for (uint32_t t0 = 0; t0 < n; t0 += tile) {
+        for (uint32_t c0 = t0; c0 < t0 + tile && c0 < n; c0 += chunk) {
+            uint32_t c1 = c0 + chunk; if (c1 > t0 + tile) c1 = t0 + tile; if (c1 > n) c1 = n;
+            HostEnv env{text, hard, spec, starts, t0 + tile + halo, &dup};
+            spl_pretok_chunk(env, c0, c1, n, spl_ucd_stage1, spl_ucd_stage2, pattern, spec != nullptr);
+        }
+    }
+    return dup ? -2 : 0;
+}
