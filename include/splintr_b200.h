@@ -113,6 +113,13 @@ int spl_encode_batch_device(spl_tokenizer* tok, int dev_index,
 /* number of kernels one spl_encode_batch_device call launches for these flags */
 int spl_launches_per_call(const spl_tokenizer* tok, uint32_t flags);
 
+/* Per-kernel device timing of spl_encode_batch_device (measurement aid, off by default): when
+ * enabled, CUDA events are recorded on the caller's stream around every kernel of the path.
+ * After the caller has synchronised that stream, spl_last_kernel_times stores up to `cap`
+ * kernel names / durations (ms) of the most recent device call and returns how many. */
+int spl_set_profiling(spl_tokenizer* tok, int enable);
+int spl_last_kernel_times(spl_tokenizer* tok, int dev_index, const char** names, float* ms, int cap);
+
 /* pinned host memory helpers for callers that want full-rate PCIe copies */
 void* spl_alloc_pinned(size_t bytes);
 void spl_free_pinned(void* p);

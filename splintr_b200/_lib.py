@@ -61,7 +61,7 @@ class SplStats(ctypes.Structure):
 EXPORTS = ["spl_create", "spl_destroy", "spl_last_error", "spl_encode_batch", "spl_result_ids",
            "spl_result_offsets", "spl_result_n_docs", "spl_result_n_tokens", "spl_result_stats",
            "spl_result_free", "spl_encode_batch_device", "spl_launches_per_call", "spl_alloc_pinned",
-           "spl_free_pinned", "spl_version"]
+           "spl_free_pinned", "spl_version", "spl_set_profiling", "spl_last_kernel_times"]
 
 SPL_OK, SPL_ERR_INVALID_ARG, SPL_ERR_VOCAB, SPL_ERR_CUDA, SPL_ERR_OOM, SPL_ERR_UNSUPPORTED, SPL_ERR_NO_DEVICE = \
     0, -1, -2, -3, -4, -5, -6
@@ -110,6 +110,11 @@ def load() -> ctypes.CDLL:
                                             ctypes.POINTER(ctypes.c_uint64)]
     lib.spl_launches_per_call.restype = ctypes.c_int
     lib.spl_launches_per_call.argtypes = [vp, ctypes.c_uint32]
+    lib.spl_set_profiling.restype = ctypes.c_int
+    lib.spl_set_profiling.argtypes = [vp, ctypes.c_int]
+    lib.spl_last_kernel_times.restype = ctypes.c_int
+    lib.spl_last_kernel_times.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p),
+                                          ctypes.POINTER(ctypes.c_float), ctypes.c_int]
     lib.spl_alloc_pinned.restype = vp
     lib.spl_alloc_pinned.argtypes = [ctypes.c_size_t]
     lib.spl_free_pinned.restype = None

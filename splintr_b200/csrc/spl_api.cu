@@ -52,6 +52,8 @@ struct DevCtx {
     SplTables* d_tables = nullptr;
     DevBuf text, doc_off, hard, spec, pstart, tfd, tstate, counters, huge, ids, out_off;
     size_t huge_words = 0;
+    SplKernelProfile prof;
+    bool prof_ready = false;
 };
 
 struct PinnedBuf { void* p; size_t cap; };
@@ -59,6 +61,7 @@ struct PinnedBuf { void* p; size_t cap; };
 }  // namespace
 
 struct spl_tokenizer {
+    bool profiling = false;
     SplHostTables host;
     std::vector<DevCtx> devs;
     std::string err;
@@ -135,6 +138,7 @@ void destroy_ctx(DevCtx& dc) {
         b->release();
     if (dc.table_blob) cudaFree(dc.table_blob);
     for (auto& e : dc.ev) if (e) cudaEventDestroy(e);
+    if (dc.prof_ready) for (auto& e : dc.prof.ev) cudaEventDestroy(e);
     if (dc.stream) cudaStreamDestroy(dc.stream);
 }
 
@@ -297,6 +301,26 @@ int spl_launches_per_call(const spl_tokenizer* tk, uint32_t flags) {
     return ws ? 4 : 3;
 }
 
+int spl_set_profiling(spl_tokenizer* tk, int enable) {
+    if (!tk) return SPL_ERR_INVALID_ARG;
+    tk->profiling = enable != 0;
+    return SPL_OK;
+}
+
+int spl_last_kernel_times(spl_tokenizer* tk, int dev_index, const char** names, float* ms, int cap) {
+    if (!tk || dev_index < 0 || (size_t)dev_index >= tk->devs.size()) return SPL_ERR_INVALID_ARG;
+    DevCtx& dc = tk->devs[dev_index];
+    if (!dc.prof_ready) return 0;
+    int n = std::min(dc.prof.n, cap);
+    for (int i = 0; i < n; ++i) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, dc.prof.ev[i], dc.prof.ev[i + 1]) != cudaSuccess) { cudaGetLastError(); t = -1.f; }
+        if (names) names[i] = dc.prof.name[i];
+        if (ms) ms[i] = t;
+    }
+    return n;
+}
+
 void* spl_alloc_pinned(size_t bytes) {
     void* p = nullptr;
     if (cudaHostAlloc(&p, std::max<size_t>(bytes, 64), cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
@@ -326,7 +350,16 @@ int spl_encode_batch_device(spl_tokenizer* tk, int dev_index, const uint8_t* d_b
         memset(&w, 0, sizeof(w));
         if ((rc = prepare_work(tk, dc, n_bytes, n_docs, with_special, st, w))) return rc;
         w.text = d_bytes; w.doc_off = d_offsets; w.ids = d_ids; w.out_off = d_out_offsets;
-        spl_launch_encode(w, dc.num_sms, st);
+        SplKernelProfile* prof = nullptr;
+        if (tk->profiling) {
+            if (!dc.prof_ready) {
+                for (auto& e : dc.prof.ev) CUDA_TRY(cudaEventCreate(&e), tk->err);
+                dc.prof.n = 0;
+                dc.prof_ready = true;
+            }
+            prof = &dc.prof;
+        }
+        spl_launch_encode(w, dc.num_sms, st, prof);
         CUDA_TRY(cudaGetLastError(), tk->err);
         if (!n_tokens_out) return SPL_OK;
         uint32_t h_counters[4];

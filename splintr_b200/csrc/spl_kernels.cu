@@ -663,28 +663,33 @@ void spl_kernels_init() {
     cudaGetLastError();
 }
 
-int spl_launch_encode(const SplWork& w, int num_sms, cudaStream_t stream) {
+int spl_launch_encode(const SplWork& w, int num_sms, cudaStream_t stream, SplKernelProfile* prof) {
     int launches = 0;
+    if (prof) { prof->n = 0; cudaEventRecord(prof->ev[0], stream); }
+    auto mark = [&](const char* name) {
+        ++launches;
+        if (prof && prof->n < SPL_PROF_MAX) { prof->name[prof->n] = name; ++prof->n; cudaEventRecord(prof->ev[prof->n], stream); }
+    };
     {
         uint32_t n = w.n_docs + 1;
         k_mark_docs<<<(n + 255) / 256, 256, 0, stream>>>(w);
-        ++launches;
+        mark("k_mark_docs");
     }
     if (w.with_special && w.N) {
         uint32_t blocks = (w.N + 255) / 256;
         uint32_t cap = (uint32_t)num_sms * 16;
         k_mark_specials<<<blocks < cap ? blocks : cap, 256, 0, stream>>>(w);
-        ++launches;
+        mark("k_mark_specials");
     }
     if (w.N) {
         k_pretok<<<(w.N + SPL_TILE - 1) / SPL_TILE, SPL_THREADS, 0, stream>>>(w);
-        ++launches;
+        mark("k_pretok");
     }
     {
         uint32_t cap = (uint32_t)num_sms * 5;
         uint32_t blocks = w.n_tiles < cap ? w.n_tiles : cap;
         k_encode<<<blocks, SPL_THREADS, 0, stream>>>(w);
-        ++launches;
+        mark("k_encode");
     }
     return launches;
 }

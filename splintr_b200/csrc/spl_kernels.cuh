@@ -35,8 +35,16 @@ struct SplWork {
 
 enum : uint32_t { SPL_DEVERR_OFFSETS = 1u, SPL_DEVERR_HUGE_POOL = 2u };
 
+// optional per-kernel device timing: ev[i] is recorded before kernel i, ev[n] after the last
+#define SPL_PROF_MAX 8
+struct SplKernelProfile {
+    cudaEvent_t ev[SPL_PROF_MAX + 1];
+    const char* name[SPL_PROF_MAX];
+    int n;
+};
+
 // Enqueue the whole encode path on `stream`.  Returns the number of kernels launched.
-int spl_launch_encode(const SplWork& w, int num_sms, cudaStream_t stream);
+int spl_launch_encode(const SplWork& w, int num_sms, cudaStream_t stream, SplKernelProfile* prof = nullptr);
 
 // Per-device one-time kernel attribute setup (shared-memory carveout).
 void spl_kernels_init();

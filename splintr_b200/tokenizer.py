@@ -227,6 +227,51 @@ class Tokenizer:
         finally:
             lib.spl_result_free(res)
 
+    def encode_device(self, d_bytes, d_offsets, with_special: bool = False, ids_out=None, out_offsets=None,
+                      dev_index: int = 0, sync: bool = True):
+        """Device-resident surface (spl_encode_batch_device): `d_bytes` = CUDA uint8 tensor whose
+        storage is 16-byte aligned and padded to a multiple of 16, `d_offsets` = CUDA int64
+        tensor [n_docs+1] (non-negative, so bit-identical to the ABI's uint64).  Work is enqueued
+        on torch's current stream.  Returns (ids int32[capacity], out_offsets int64[n_docs+1],
+        n_tokens or None when sync=False); ids[:n_tokens] are valid."""
+        import torch
+        lib = _lib.load()
+        n_bytes = int(d_bytes.numel())
+        n_docs = int(d_offsets.numel()) - 1
+        if d_bytes.dtype != torch.uint8 or d_offsets.dtype != torch.int64 or not d_bytes.is_cuda or not d_offsets.is_cuda:
+            raise TypeError("d_bytes must be a CUDA uint8 tensor and d_offsets a CUDA int64 tensor")
+        if ids_out is None:
+            ids_out = torch.empty(max(n_bytes, 1), dtype=torch.int32, device=d_bytes.device)
+        if out_offsets is None:
+            out_offsets = torch.empty(n_docs + 1, dtype=torch.int64, device=d_bytes.device)
+        n_tok = ctypes.c_uint64(0)
+        stream = torch.cuda.current_stream(d_bytes.device).cuda_stream
+        rc = lib.spl_encode_batch_device(self._handle, dev_index, ctypes.c_void_p(d_bytes.data_ptr()), n_bytes,
+                                         ctypes.c_void_p(d_offsets.data_ptr()), n_docs,
+                                         _lib.SPL_ENCODE_WITH_SPECIAL if with_special else 0,
+                                         ctypes.c_void_p(ids_out.data_ptr()), int(ids_out.numel()),
+                                         ctypes.c_void_p(out_offsets.data_ptr()), ctypes.c_void_p(stream),
+                                         ctypes.byref(n_tok) if sync else None)
+        if rc != _lib.SPL_OK:
+            msg = _lib.last_error(self._handle)
+            if rc in (_lib.SPL_ERR_INVALID_ARG, _lib.SPL_ERR_UNSUPPORTED):
+                raise ValueError(msg)
+            raise RuntimeError(f"splintr_b200: {msg} (code {rc})")
+        return ids_out, out_offsets, (int(n_tok.value) if sync else None)
+
+    def set_profiling(self, enable: bool = True) -> None:
+        _lib.load().spl_set_profiling(self._handle, int(enable))
+
+    def last_kernel_times(self, dev_index: int = 0) -> Dict[str, float]:
+        """{kernel name: ms} of the most recent encode_device call (after a stream sync)."""
+        names = (ctypes.c_char_p * 8)()
+        ms = (ctypes.c_float * 8)()
+        n = _lib.load().spl_last_kernel_times(self._handle, dev_index, names, ms, 8)
+        return {names[i].decode(): float(ms[i]) for i in range(max(n, 0))}
+
+    def launches_per_call(self, with_special: bool = False) -> int:
+        return int(_lib.load().spl_launches_per_call(self._handle, _lib.SPL_ENCODE_WITH_SPECIAL if with_special else 0))
+
     def encode_batch_packed(self, texts: Sequence[str], with_special: bool = False):
         """list[str] -> (ids uint32, offsets uint64) without building Python lists."""
         data, offsets = self._pack(texts)

@@ -1,0 +1,99 @@
+"""Builds tests/csrc/hosttest.cpp: the product's __host__ __device__ pre-tokenizer rules and
+host table builder compiled for the CPU (tests only), so the exact device logic can be
+fuzzed against the oracle without a GPU."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = [os.path.join(ROOT, "tests", "csrc", "hosttest.cpp"), os.path.join(ROOT, "splintr_b200", "csrc", "spl_host.cpp")]
+DEPS = SRC + [os.path.join(ROOT, "splintr_b200", "csrc", f) for f in ("spl_pretok.h", "spl_common.h", "spl_host.h", "unicode_tables.inc")]
+LIB = os.path.join(ROOT, "tests", "csrc", "libhosttest.so")
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in DEPS):
+        cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", LIB] + SRC
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        if p.returncode:
+            raise RuntimeError(p.stdout + p.stderr)
+    lib = ctypes.CDLL(LIB)
+    vp = ctypes.c_void_p
+    lib.ht_scan_seq.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_uint32, vp]
+    lib.ht_scan_chunked.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_uint32, vp, vp, vp]
+    lib.ht_scan_kernel_emul.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                        ctypes.c_uint32, vp, vp, vp]
+    lib.ht_create.restype = vp
+    lib.ht_create.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32,
+                              ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_uint32), ctypes.c_size_t,
+                              ctypes.c_char_p, ctypes.c_size_t]
+    lib.ht_destroy.argtypes = [vp]
+    lib.ht_stats.argtypes = [vp, vp]
+    lib.ht_encode.restype = ctypes.c_long
+    lib.ht_encode.argtypes = [vp, ctypes.c_char_p, ctypes.c_uint32, vp, ctypes.c_size_t]
+    _lib = lib
+    return lib
+
+
+def scan_seq(pattern_id, data: bytes):
+    st = np.zeros(len(data) + 1, dtype=np.uint8)
+    rc = load().ht_scan_seq(pattern_id, data, len(data), st.ctypes.data)
+    assert rc == 0, rc
+    return np.flatnonzero(st[:len(data)]).tolist()
+
+
+def scan_chunked(pattern_id, data: bytes, chunk, hard=None):
+    n = len(data)
+    h = np.zeros(n + 1, dtype=np.uint8) if hard is None else np.asarray(hard, dtype=np.uint8)
+    h[0] = 1
+    h[n] = 1
+    st = np.zeros(n + 1, dtype=np.uint8)
+    ns = ctypes.c_uint32(0)
+    rc = load().ht_scan_chunked(pattern_id, data, n, chunk, h.ctypes.data, st.ctypes.data, ctypes.addressof(ns))
+    assert rc == 0, rc
+    return np.flatnonzero(st[:n]).tolist()
+
+
+def scan_kernel_emul(pattern_id, data: bytes, tile, halo, chunk, hard, spec=None):
+    n = len(data)
+    h = np.asarray(hard, dtype=np.uint8)
+    st = np.zeros(n + 1, dtype=np.uint8)
+    sp = None if spec is None else np.asarray(spec, dtype=np.uint8)
+    rc = load().ht_scan_kernel_emul(pattern_id, data, n, tile, halo, chunk, h.ctypes.data,
+                                    None if sp is None else sp.ctypes.data, st.ctypes.data)
+    assert rc == 0, rc
+    return np.flatnonzero(st[:n]).tolist()
+
+
+class HostTables:
+    def __init__(self, vocab: bytes, pattern_id: int, byte_level: bool, specials=None):
+        sp = list((specials or {}).items())
+        n = len(sp)
+        strs = (ctypes.c_char_p * max(n, 1))(*[s.encode() for s, _ in sp])
+        ids = (ctypes.c_uint32 * max(n, 1))(*[i for _, i in sp])
+        err = ctypes.create_string_buffer(256)
+        self.h = load().ht_create(vocab, len(vocab), pattern_id, 1 if byte_level else 0, strs, ids, n, err, 256)
+        if not self.h:
+            raise ValueError(err.value.decode())
+
+    def stats(self):
+        out = np.zeros(8, dtype=np.uint64)
+        load().ht_stats(self.h, out.ctypes.data)
+        return dict(zip(["n_keys", "n_pairs", "t8_log2", "t16_log2", "tl_log2", "pair_log2", "max_key_len", "unambiguous"], out.tolist()))
+
+    def encode(self, data: bytes):
+        ids = np.zeros(len(data) + 1, dtype=np.uint32)
+        n = load().ht_encode(self.h, data, len(data), ids.ctypes.data, len(ids))
+        assert n >= 0, n
+        return ids[:n].tolist()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            load().ht_destroy(self.h)
+            self.h = None

@@ -1,0 +1,212 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI (ctypes host in
+splintr_b200/tokenizer.py), against the oracles on the same inputs.  Bit-exact ids and
+offsets are required everywhere (integer work; no tolerance).
+
+Reference behaviour under test: Tokenizer::encode / encode_with_special / encode_batch
+(/root/reference/src/core/tokenizer.rs:729-808, 842-874, 932-942), byte_pair_encode
+(src/core/bpe.rs:67-197), the split patterns (tokenizer.rs:39,42,64)."""
+import random
+
+import numpy as np
+import pytest
+
+import synth
+from conftest import VOCABS, py_oracle, c_oracle
+from fuzz_alphabet import random_text
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def toks():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from splintr_b200 import Tokenizer
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = Tokenizer.from_pretrained(name, devices=[0])
+        return cache[name]
+    return get
+
+
+def vocab_bytes(name):
+    from splintr_b200 import presets as P
+    return P.load_vocab_bytes(P.PRESETS[name].vocab_file)
+
+
+@pytest.mark.parametrize("name", VOCABS)
+def test_reference_golden_vectors(toks, name, ref_vectors):
+    t = toks(name)
+    for text, ids in ref_vectors[name]["encode"]:
+        assert t.encode(text) == ids, (name, text)
+        assert t.encode_rayon(text) == ids
+    for text, ids in ref_vectors[name]["special"]:
+        assert t.encode_with_special(text) == ids, (name, text)
+
+
+@pytest.mark.parametrize("name", VOCABS)
+def test_tiktoken_fixture(toks, name, xcheck_vectors):
+    texts = [t for t, _ in xcheck_vectors[name]]
+    assert toks(name).encode_batch(texts) == [ids for _, ids in xcheck_vectors[name]]
+
+
+@pytest.mark.parametrize("name", VOCABS)
+def test_fuzz_vs_oracles(toks, name):
+    rng = random.Random(1234 + len(name))
+    texts = [t for t in (random_text(rng, 80) for _ in range(6000)) if "᠎" not in t]
+    texts += ["".join(rng.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(rng.randint(20, 700))) for _ in range(60)]
+    got = toks(name).encode_batch(texts)
+    assert got == c_oracle(name).encode_batch(texts)
+    po = py_oracle(name)
+    for t, g in list(zip(texts, got))[:800]:
+        assert g == po.encode(t), (name, t)
+
+
+@pytest.mark.parametrize("name", VOCABS)
+def test_edge_cases(toks, name):
+    t, o = toks(name), c_oracle(name)
+    assert t.encode_batch([]) == []
+    assert t.encode("") == []
+    assert t.encode_batch(["", "", ""]) == [[], [], []]
+    cases = ["", "a", " ", "\n", "", "é", "\U0001f30d", "", "=" * 300, "-" * 77 + "\n", " " * 100 + "x", "#" * 33,
+             "ab" * 100, "a" * 257, "a" * 4095, "a" * 4096, "a" * 4097, "x" * 5000, " " * 6000, "ab" * 4000,
+             "\n" * 5000, "日本語のテキストをトークン化します。" * 9, "好" * 3000, "", "z"]
+    assert t.encode_batch(cases) == o.encode_batch(cases)
+    # ragged: documents whose boundaries fall on every offset of the 16-byte / 4096-byte tiling
+    rag = ["x" * k for k in range(0, 40)] + ["word " * k for k in (818, 819, 820)] + ["é" * k for k in (2047, 2048, 2049)]
+    assert t.encode_batch(rag) == o.encode_batch(rag)
+
+
+@pytest.mark.parametrize("name", VOCABS)
+def test_special_tokens(toks, name):
+    t, po = toks(name), py_oracle(name)
+    rng = random.Random(77)
+    sp = list(po.special_tokens)
+    texts = [s for s in sp[:12]] + [sp[0] + sp[1], "x" + sp[0], sp[0] + "y", sp[0][:-1], "<|", "a" + sp[2] + " b " + sp[3] + "\n"]
+    texts += [random_text(rng, 30) + rng.choice(sp) + random_text(rng, 30) + rng.choice(sp) for _ in range(500)]
+    texts = [x for x in texts if "᠎" not in x]
+    got = t.encode_batch_with_special(texts)
+    for x, g in zip(texts, got):
+        assert g == po.encode_with_special(x), (name, x)
+    # encode() never recognises specials (bindings.rs:246-256)
+    assert t.encode(sp[0]) == po.encode(sp[0])
+    assert t.decode(t.encode_with_special("a" + sp[0] + "b")) == "a" + sp[0] + "b"
+
+
+@pytest.mark.parametrize("name", ["cl100k_base", "o200k_base"])
+def test_batch_equals_individual_and_roundtrip(toks, name):
+    """tests/cl100k.rs:191-214 and python/tests/test_cl100k.py:545-570 (700-text batch)."""
+    t = toks(name)
+    rng = random.Random(3)
+    base = ["Hello, world!", "The quick brown fox jumps over the lazy dog.", "你好世界", "I'm sorry you're hurting—breakups suck.",
+            "def f(x):\n    return x + 1\n", '{"a": [1, 2, 3]}', "   spaces   ", "MixedCASE and 12345 numbers"]
+    texts = [rng.choice(base) + " " + str(i) for i in range(700)]
+    batch = t.encode_batch(texts)
+    assert len(batch) == 700
+    for i in range(0, 700, 37):
+        assert batch[i] == t.encode(texts[i])
+    assert t.decode_batch(batch) == texts
+
+
+def _check_packed(tok, orc, data, offsets):
+    ids, off = tok.encode_packed(data, offsets)
+    want_ids, want_off = orc.encode_packed(data, offsets)
+    assert np.array_equal(off, want_off)
+    assert np.array_equal(ids, want_ids)
+    return ids, off
+
+
+def test_cfg1_full(toks):
+    d, o = synth.cfg1(vocab_bytes("cl100k_base"))
+    _check_packed(toks("cl100k_base"), c_oracle("cl100k_base"), d, o)
+
+
+def test_cfg2_full_size_bit_exact_and_roundtrip(toks):
+    """BASELINE.json configs[1] at full size: 100 000 docs, ~100 MB."""
+    d, o = synth.cfg2(vocab_bytes("cl100k_base"))
+    tok = toks("cl100k_base")
+    ids, off = _check_packed(tok, c_oracle("cl100k_base"), d, o)
+    # size-independent property: decode(ids) reproduces the input bytes
+    dec = tok._ensure_decoder()
+    lut = [dec.get(i, b"") for i in range(max(dec) + 1)]
+    sample = np.concatenate([np.arange(0, 2000), np.arange(50_000, 52_000), np.arange(98_000, 100_000)])
+    raw = d.tobytes()
+    for k in sample:
+        got = b"".join(lut[i] for i in ids[int(off[k]):int(off[k + 1])].tolist())
+        assert got == raw[int(o[k]):int(o[k + 1])]
+
+
+def test_cfg3_mixed_o200k(toks):
+    d, o = synth.cfg3(vocab_bytes("o200k_base"), 30_000)
+    _check_packed(toks("o200k_base"), c_oracle("o200k_base"), d, o)
+
+
+def test_cfg4_long_docs_llama3(toks):
+    d, o = synth.cfg4(vocab_bytes("llama3"), 24, 1_000_000.0)
+    _check_packed(toks("llama3"), c_oracle("llama3"), d, o)
+
+
+def test_cfg5_cjk_deepseek(toks):
+    d, o = synth.cfg5(b"", 30_000)
+    _check_packed(toks("deepseek_v3"), c_oracle("deepseek_v3"), d, o)
+
+
+def test_device_resident_entry_point(toks):
+    import torch
+    tok = toks("cl100k_base")
+    d, o = synth.cfg2(vocab_bytes("cl100k_base"), 5000)
+    n = len(d)
+    buf = torch.zeros(n + ((-n) % 16), dtype=torch.uint8, device="cuda")
+    buf[:n].copy_(torch.from_numpy(d))
+    d_off = torch.from_numpy(o.astype(np.int64)).cuda()
+    ids, out_off, n_tok = tok.encode_device(buf[:n], d_off)
+    want_ids, want_off = c_oracle("cl100k_base").encode_packed(d, o)
+    assert n_tok == len(want_ids)
+    assert np.array_equal(ids[:n_tok].cpu().numpy().astype(np.uint32), want_ids)
+    assert np.array_equal(out_off.cpu().numpy().astype(np.uint64), want_off)
+    # idempotence: the same call again gives the same result (workspace is fully re-initialised)
+    ids2, out2, n2 = tok.encode_device(buf[:n], d_off)
+    assert n2 == n_tok and torch.equal(ids2[:n2], ids[:n_tok]) and torch.equal(out2, out_off)
+    tok.set_profiling(True)
+    tok.encode_device(buf[:n], d_off)
+    kt = tok.last_kernel_times()
+    tok.set_profiling(False)
+    assert "k_encode" in kt and all(v >= 0 for v in kt.values())
+
+
+def test_invalid_offsets_rejected(toks):
+    tok = toks("cl100k_base")
+    data = np.frombuffer(b"hello world", dtype=np.uint8)
+    with pytest.raises(ValueError):
+        tok.encode_packed(data, np.array([1, 11], dtype=np.uint64))
+    with pytest.raises(ValueError):
+        tok.encode_packed(data, np.array([0, 8, 4, 11], dtype=np.uint64))
+    with pytest.raises(TypeError):
+        tok.encode_batch(["ok", 5])
+
+
+def test_multi_device_handle_matches_single(toks):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from splintr_b200 import Tokenizer
+    d, o = synth.cfg2(vocab_bytes("cl100k_base"), 20_000)
+    t2 = Tokenizer.from_pretrained("cl100k_base", devices=[0, 1])
+    ids2, off2 = t2.encode_packed(d, o)
+    ids1, off1 = toks("cl100k_base").encode_packed(d, o)
+    assert np.array_equal(ids1, ids2) and np.array_equal(off1, off2)
+
+
+def test_custom_vocab_with_unknown_bytes(toks):
+    """bpe.rs:73-75,187-191: bytes that are not in the vocabulary are silently dropped."""
+    import base64
+    from splintr_b200 import Tokenizer, CL100K_BASE_PATTERN
+    from oracle.py_oracle import OracleTokenizer
+    toy = {b"a": 0, b"b": 1, b"c": 2, b"ab": 3, b"bc": 4, b"abc": 5, b" ": 6, b" a": 7}
+    vb = b"".join(base64.b64encode(k) + b" " + str(v).encode() + b"\n" for k, v in toy.items())
+    t = Tokenizer.from_bytes(vb, CL100K_BASE_PATTERN)
+    o = OracleTokenizer.from_bytes(vb, CL100K_BASE_PATTERN)
+    for s in ["a", "ab", "abc", "ac", "abcabc", "zab", "xyz", " a b", "cab abc", "aXbXc"]:
+        assert t.encode(s) == o.encode(s), s
