@@ -50,7 +50,7 @@ struct DevCtx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     void* table_blob = nullptr;
     SplTables* d_tables = nullptr;
-    DevBuf text, doc_off, hard, spec, pstart, tfd, tstate, counters, huge, ids, out_off;
+    DevBuf text, doc_off, hard, spec, pstart, tfd, tstate, counters, huge, ids, out_off, fbl;
     size_t huge_words = 0;
     SplKernelProfile prof;
     bool prof_ready = false;
@@ -134,7 +134,7 @@ int upload_tables(spl_tokenizer* tk, DevCtx& dc) {
 
 void destroy_ctx(DevCtx& dc) {
     cudaSetDevice(dc.device);
-    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.hard, &dc.spec, &dc.pstart, &dc.tfd, &dc.tstate, &dc.counters, &dc.huge, &dc.ids, &dc.out_off})
+    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.hard, &dc.spec, &dc.pstart, &dc.tfd, &dc.tstate, &dc.counters, &dc.huge, &dc.ids, &dc.out_off, &dc.fbl})
         b->release();
     if (dc.table_blob) cudaFree(dc.table_blob);
     for (auto& e : dc.ev) if (e) cudaEventDestroy(e);
@@ -162,6 +162,8 @@ int prepare_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
     if ((rc = dc.tfd.ensure((size_t)(n_tiles + 2) * 4, tk->err))) return rc;
     if ((rc = dc.tstate.ensure((size_t)n_tiles * 8, tk->err))) return rc;
     if ((rc = dc.counters.ensure(64, tk->err))) return rc;
+    uint32_t n_fast_tiles = (uint32_t)((N + SPL_FAST_PAYLOAD * 32u - 1) / (SPL_FAST_PAYLOAD * 32u));
+    if ((rc = dc.fbl.ensure((size_t)(n_fast_tiles + 1) * 4, tk->err))) return rc;
     if (dc.huge_words == 0) dc.huge_words = (size_t)16 << 20;             // 64 MiB of scratch
     if ((rc = dc.huge.ensure(dc.huge_words * 4, tk->err))) return rc;
     CUDA_TRY(cudaMemsetAsync(dc.hard.p, 0, words * 4, st), tk->err);
@@ -179,6 +181,8 @@ int prepare_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
     w.tile_first_doc = (uint32_t*)dc.tfd.p;
     w.tile_state = (uint64_t*)dc.tstate.p;
     w.counters = (uint32_t*)dc.counters.p;
+    w.fb_list = (uint32_t*)dc.fbl.p;
+    w.n_fast_tiles = n_fast_tiles;
     w.huge_pool = (uint32_t*)dc.huge.p;
     w.huge_pool_words = (uint32_t)std::min<size_t>(dc.huge_words, 0xFFFFFFFFu);
     w.T = dc.d_tables;
@@ -298,7 +302,8 @@ const char* spl_last_error(const spl_tokenizer* tk) { return tk ? tk->err.c_str(
 int spl_launches_per_call(const spl_tokenizer* tk, uint32_t flags) {
     if (!tk) return 0;
     bool ws = (flags & SPL_ENCODE_WITH_SPECIAL) && !tk->host.sp_id.empty();
-    return ws ? 4 : 3;
+    int pre = tk->host.pattern == SPL_PAT_MISTRAL_V3 ? 1 : 2;          // sequential rules | bit-parallel + fallback
+    return 2 + pre + (ws ? 1 : 0);
 }
 
 int spl_set_profiling(spl_tokenizer* tk, int enable) {

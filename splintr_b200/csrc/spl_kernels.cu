@@ -14,6 +14,7 @@
 // Integer / byte work, bounded by HBM traffic and L2 probe latency; no tensor cores.
 #include "spl_kernels.cuh"
 #include "spl_pretok.h"
+#include "spl_pretok_fast.h"
 
 #define FULL 0xFFFFFFFFu
 
@@ -183,14 +184,17 @@ struct DevEnv {
     }
 };
 
-__global__ void __launch_bounds__(SPL_THREADS) k_pretok(SplWork w) {
-    __shared__ __align__(16) uint8_t s_text[PT_LEFT + SPL_WIN];
-    __shared__ uint32_t s_hard[PT_HW];
-    __shared__ uint32_t s_spec[PT_HW];
-    __shared__ uint32_t s_ps[SPL_TILE / 32];
+struct PretokSmem {
+    __align__(16) uint8_t text[PT_LEFT + SPL_WIN];
+    uint32_t hard[PT_HW];
+    uint32_t spec[PT_HW];
+    uint32_t ps[SPL_TILE / 32];
+};
 
+// sequential rules over one SPL_TILE-byte tile (whole block); leadin: also cover the pieces that start between
+// tile0 and the tile's first sync point (needed when the tile to the left is not processed by this routine)
+__device__ void pretok_tile(const SplWork& w, PretokSmem& sm, uint32_t tile0, bool leadin) {
     const uint32_t tid = threadIdx.x;
-    const uint32_t tile0 = blockIdx.x * SPL_TILE;
     const uint32_t N = w.N;
     const uint32_t w0 = tile0 >= PT_LEFT ? tile0 - PT_LEFT : 0;       // window start (16-aligned)
     const uint32_t lead = tile0 - w0;                                  // 0 or 16
@@ -201,32 +205,146 @@ __global__ void __launch_bounds__(SPL_THREADS) k_pretok(SplWork w) {
         uint32_t g = w0 + v * 16;
         uint4 x = make_uint4(0, 0, 0, 0);
         if (g < Nup) x = __ldg(reinterpret_cast<const uint4*>(w.text + g));
-        *reinterpret_cast<uint4*>(s_text + v * 16) = x;
+        *reinterpret_cast<uint4*>(sm.text + v * 16) = x;
     }
     const uint32_t hw0 = (tile0 >> 5) - (tile0 ? 1u : 0u);
     for (uint32_t v = tid; v < PT_HW; v += SPL_THREADS) {
-        s_hard[v] = __ldg(w.hard + hw0 + v);
-        s_spec[v] = w.with_special ? __ldg(w.spec + hw0 + v) : 0u;
+        sm.hard[v] = __ldg(w.hard + hw0 + v);
+        sm.spec[v] = w.with_special ? __ldg(w.spec + hw0 + v) : 0u;
     }
-    if (tid < SPL_TILE / 32) s_ps[tid] = 0;
+    if (tid < SPL_TILE / 32) sm.ps[tid] = 0;
     __syncthreads();
 
     DevEnv env;
-    env.sm_text = s_text; env.w0 = w0; env.wlen = lead + SPL_WIN; env.g_text = w.text;
-    env.sm_hard = s_hard; env.sm_spec = s_spec; env.hw0 = hw0; env.g_hard = w.hard; env.g_spec = w.spec;
-    env.sm_ps = s_ps; env.tile0 = tile0; env.g_ps = w.pstart;
+    env.sm_text = sm.text; env.w0 = w0; env.wlen = lead + SPL_WIN; env.g_text = w.text;
+    env.sm_hard = sm.hard; env.sm_spec = sm.spec; env.hw0 = hw0; env.g_hard = w.hard; env.g_spec = w.spec;
+    env.sm_ps = sm.ps; env.tile0 = tile0; env.g_ps = w.pstart;
     env.W = tile0 + SPL_WIN;
 
+    const SplTables* T = w.T;
     uint32_t c0 = tile0 + tid * 16;
     if (c0 < N) {
         uint32_t c1 = c0 + 16 < N ? c0 + 16 : N;
-        const SplTables* T = w.T;
         spl_pretok_chunk(env, c0, c1, N, T->ucd_stage1, T->ucd_stage2, w.pattern, w.with_special);
     }
+    if (leadin && tid == SPL_THREADS - 1)
+        spl_pretok_leadin(env, tile0, N, T->ucd_stage1, T->ucd_stage2, w.pattern, w.with_special);
     __syncthreads();
     if (tid < SPL_TILE / 32) {
-        uint32_t v = s_ps[tid];
+        uint32_t v = sm.ps[tid];
         if (v) atomicOr(&w.pstart[(tile0 >> 5) + tid], v);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SPL_THREADS) k_pretok(SplWork w) {
+    __shared__ PretokSmem sm;
+    pretok_tile(w, sm, blockIdx.x * SPL_TILE, false);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_pretok_fast: the bit-parallel formulation (spl_pretok_fast.h).  One thread per 32-byte word,
+// FAST_HALO words of context on each side of FAST_PAYLOAD payload words.  A tile that cannot be
+// decided here is appended to the fallback list and left untouched.
+// ------------------------------------------------------------------------------------------
+struct FastGText {
+    const uint8_t* p;
+    __device__ __forceinline__ uint8_t byte(uint32_t i) const { return __ldg(p + i); }
+};
+
+struct FastSmem {
+    uint32_t m[FM_COUNT][SPL_FAST_THREADS];
+    uint32_t hardw[SPL_FAST_THREADS];
+    uint32_t specw[SPL_FAST_THREADS];
+    uint32_t sum[SPL_FAST_THREADS];
+};
+
+struct FastMasks {
+    const FastSmem* s; int gw0; uint32_t N;
+    __device__ __forceinline__ uint32_t get(int q, int k) const { return s->m[q][k]; }
+    __device__ __forceinline__ uint32_t hard(int k) const { return s->hardw[k]; }
+    __device__ __forceinline__ uint32_t spec(int k) const { return s->specw[k]; }
+    __device__ __forceinline__ uint32_t summary(int k) const { return s->sum[k]; }
+    __device__ __forceinline__ uint32_t valid(int k) const {
+        int gw = gw0 + k;
+        if (gw < 0) return 0u;
+        uint32_t base = (uint32_t)gw * 32u;
+        if (base >= N) return 0u;
+        return (N - base >= 32u) ? 0xFFFFFFFFu : ((1u << (N - base)) - 1u);
+    }
+};
+
+__global__ void __launch_bounds__(SPL_FAST_THREADS) k_pretok_fast(SplWork w) {
+    __shared__ FastSmem sm;
+    const int k = threadIdx.x;
+    const int gw0 = (int)(blockIdx.x * SPL_FAST_PAYLOAD) - (int)SPL_FAST_HALO;
+    const int gw = gw0 + k;
+    const uint32_t N = w.N;
+    const SplTables* T = w.T;
+    const uint32_t last_word = N >> 5;                        // the word that holds the sentinel bit N
+
+    // ---- phase A: classify my word ------------------------------------------------------------------
+    SplFastWord fw;
+#pragma unroll
+    for (int q = 0; q <= FM_BAD; ++q) fw.m[q] = 0;
+    uint32_t hw = 0, sw = 0;
+    if (gw >= 0 && (uint32_t)gw <= last_word) {
+        const uint32_t base = (uint32_t)gw * 32u;
+        hw = __ldg(w.hard + gw);
+        if (w.with_special) sw = __ldg(w.spec + gw);
+        if (base < N) {
+            uint32_t xw[8];
+            const uint4* p4 = reinterpret_cast<const uint4*>(w.text + base);
+            uint4 a = __ldg(p4);
+            uint4 b = (base + 16u < ((N + 15u) & ~15u)) ? __ldg(p4 + 1) : make_uint4(0, 0, 0, 0);
+            xw[0] = a.x; xw[1] = a.y; xw[2] = a.z; xw[3] = a.w; xw[4] = b.x; xw[5] = b.y; xw[6] = b.z; xw[7] = b.w;
+            FastGText t{w.text};
+            fw = spl_fast_classify(t, xw, base, N, T->ucd_stage1, T->ucd_stage2, w.pattern);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q <= FM_BAD; ++q) sm.m[q][k] = fw.m[q];
+    sm.hardw[k] = hw; sm.specw[k] = sw;
+    __syncthreads();
+
+    // ---- phase B: local masks, fills, summary ------------------------------------------------------------
+    FastMasks M{&sm, gw0, N};
+    SplFastLocal loc;
+    uint32_t s = spl_fast_local(M, k, SPL_FAST_THREADS, w.pattern, loc);
+    sm.sum[k] = s;
+    sm.m[FM_A2][k] = loc.A2; sm.m[FM_A3][k] = loc.A3;
+    __syncthreads();
+
+    // ---- phase C: carries, piece starts --------------------------------------------------------------------
+    bool structural = false, unknown = false;
+    uint32_t start = spl_fast_final(M, loc, k, SPL_FAST_THREADS, w.pattern, w.with_special, structural, unknown);
+    const bool payload = k >= (int)SPL_FAST_HALO && k < (int)(SPL_FAST_HALO + SPL_FAST_PAYLOAD);
+    int flag = ((s & FS_BAD) != 0) || structural || (payload && unknown);
+    flag = __syncthreads_or(flag);
+    if (flag) {
+        if (k == 0) {
+            uint32_t idx = atomicAdd(&w.counters[3], 1u);
+            w.fb_list[idx] = blockIdx.x;
+        }
+        return;
+    }
+    if (payload && (uint32_t)gw <= last_word) {
+        if ((uint32_t)gw == last_word) start |= 1u << (N & 31u);
+        w.pstart[gw] = start;
+    }
+}
+
+// tiles the fast path declined: the sequential rules, two SPL_TILE tiles per fast tile
+__global__ void __launch_bounds__(SPL_THREADS) k_pretok_fb(SplWork w) {
+    __shared__ PretokSmem sm;
+    const uint32_t n = w.counters[3];
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint32_t t0 = w.fb_list[i] * (SPL_FAST_PAYLOAD * 32u);
+#pragma unroll 1
+        for (uint32_t sub = 0; sub < SPL_FAST_PAYLOAD * 32u / SPL_TILE; ++sub) {
+            uint32_t tile0 = t0 + sub * SPL_TILE;
+            if (tile0 < w.N) pretok_tile(w, sm, tile0, sub == 0);
+        }
     }
 }
 
@@ -681,9 +799,15 @@ int spl_launch_encode(const SplWork& w, int num_sms, cudaStream_t stream, SplKer
         k_mark_specials<<<blocks < cap ? blocks : cap, 256, 0, stream>>>(w);
         mark("k_mark_specials");
     }
-    if (w.N) {
+    if (w.N && w.pattern == SPL_PAT_MISTRAL_V3) {
         k_pretok<<<(w.N + SPL_TILE - 1) / SPL_TILE, SPL_THREADS, 0, stream>>>(w);
         mark("k_pretok");
+    } else if (w.N) {
+        k_pretok_fast<<<w.n_fast_tiles, SPL_FAST_THREADS, 0, stream>>>(w);
+        mark("k_pretok_fast");
+        uint32_t cap = (uint32_t)num_sms * 4;
+        k_pretok_fb<<<w.n_fast_tiles < cap ? w.n_fast_tiles : cap, SPL_THREADS, 0, stream>>>(w);
+        mark("k_pretok_fb");
     }
     {
         uint32_t cap = (uint32_t)num_sms * 5;

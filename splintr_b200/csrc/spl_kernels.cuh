@@ -8,6 +8,10 @@
 #define SPL_HALO 256u           // bytes staged beyond a tile's end
 #define SPL_WIN  (SPL_TILE + SPL_HALO)
 #define SPL_THREADS 256
+// bit-parallel pre-tokenizer: one thread per 32-byte word, halo words of context on both sides
+#define SPL_FAST_HALO    16u
+#define SPL_FAST_PAYLOAD 256u         // words per tile = 8192 bytes = 2 * SPL_TILE
+#define SPL_FAST_THREADS (SPL_FAST_PAYLOAD + 2u * SPL_FAST_HALO)
 
 // per-call device workspace (all pointers on the current device)
 struct SplWork {
@@ -23,7 +27,9 @@ struct SplWork {
     size_t          bitmap_words;
     uint32_t*       tile_first_doc;   // [n_tiles+1]
     uint64_t*       tile_state;       // [n_tiles] decoupled look-back
-    uint32_t*       counters;         // [8]: 0 = encode ticket, 1 = error flags, 2 = huge pool bump
+    uint32_t*       counters;         // [8]: 0 = encode ticket, 1 = error flags, 2 = huge pool bump, 3 = fallback tiles
+    uint32_t*       fb_list;          // [n_fast_tiles] fast-path tiles handed to the sequential rules
+    uint32_t        n_fast_tiles;
     uint32_t*       huge_pool;        // scratch for pieces that outgrow the staging window
     uint32_t        huge_pool_words;
     uint32_t*       ids;              // [>= N]

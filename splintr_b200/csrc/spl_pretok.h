@@ -341,3 +341,32 @@ SPL_HD void spl_pretok_chunk(Env& env, uint32_t c0, uint32_t c1, uint32_t N,
         }
     }
 }
+
+// Lead-in for re-doing an isolated region [t0, ...) with the sequential rules: the pieces that start in
+// [t0, first sync point at or after t0) belong to the worker of an EARLIER chunk.  This finds the last sync
+// point before t0 (scanning backwards; a segment start always is one) and runs that worker.  Marks left of t0
+// are repeats of what the owner of that text wrote -- piece starts are a function of the text only.
+template <class Env>
+SPL_HD void spl_pretok_leadin(Env& env, uint32_t t0, uint32_t N,
+                              const uint8_t* s1, const uint8_t* s2, int pattern, bool with_special) {
+    if (t0 == 0 || t0 >= N || env.hard(t0)) return;
+    SplScanner<Env, true> sc(env, s1, s2, pattern);
+    SplSegEnd se;
+    spl_seg_locate(env, t0 - 1, N, se);
+    uint32_t a = t0 - 1;
+    for (;; --a) {
+        if (a == 0 || env.hard(a)) break;
+        if (with_special && env.spec(a)) continue;
+        if ((env.byte(a) & 0xC0u) == 0x80u) continue;
+        uint32_t S = spl_prev_limit(env, a);
+        bool r;
+        for (;;) {
+            sc.hit = false;
+            r = sc.is_sync(a, S, se.E);
+            if (!sc.hit || se.exact) break;
+            spl_seg_extend(env, N, se);
+        }
+        if (r) break;
+    }
+    spl_pretok_chunk(env, a, t0, N, s1, s2, pattern, with_special);
+}

@@ -160,3 +160,102 @@ extern "C" int ht_scan_kernel_emul(int pattern, const uint8_t* text, uint32_t n,
     }
     return dup ? -2 : 0;
 }
+
+// ---------------------------------------------------------------------------------------
+// Bit-parallel pre-tokenizer (spl_pretok_fast.h) under a host emulation of the kernel's
+// tile / window structure: `payload` words per tile, `halo` words of context on each side.
+#include "../../splintr_b200/csrc/spl_pretok_fast.h"
+
+struct HostFastText {
+    const uint8_t* p; uint32_t n;
+    uint8_t byte(uint32_t i) const { return i < n ? p[i] : 0; }
+    uint32_t load4(uint32_t i) const {
+        uint32_t v = 0;
+        for (uint32_t b = 0; b < 4; ++b) if (i + b < n) v |= (uint32_t)p[i + b] << (8 * b);
+        return v;
+    }
+};
+
+struct HostFastMasks {
+    std::vector<uint32_t> m[FM_COUNT];
+    std::vector<uint32_t> hardw, specw, validw, sum;
+    uint32_t get(int q, int k) const { return m[q][k]; }
+    uint32_t hard(int k) const { return hardw[k]; }
+    uint32_t spec(int k) const { return specw[k]; }
+    uint32_t valid(int k) const { return validw[k]; }
+    uint32_t summary(int k) const { return sum[k]; }
+};
+
+// starts[i] = 1 at piece starts found by the fast path; tile_flag[t] = 1 when tile t asked for the fallback
+extern "C" int ht_scan_fast(int pattern, const uint8_t* text, uint32_t n, uint32_t payload, uint32_t halo,
+                            const uint8_t* hard, const uint8_t* spec, uint8_t* starts, uint8_t* tile_flag) {
+    memset(starts, 0, n + 1);
+    HostFastText t{text, n};
+    const int nw = (int)(payload + 2 * halo);
+    uint32_t n_tiles = (n + payload * 32 - 1) / (payload * 32);
+    for (uint32_t tile = 0; tile < n_tiles; ++tile) {
+        long w0 = (long)tile * payload - halo;            // global word index of window word 0
+        HostFastMasks M;
+        for (auto& v : M.m) v.assign(nw, 0);
+        M.hardw.assign(nw, 0); M.specw.assign(nw, 0); M.validw.assign(nw, 0); M.sum.assign(nw, 0);
+        for (int k = 0; k < nw; ++k) {
+            long gw = w0 + k;
+            if (gw < 0) continue;
+            uint32_t base = (uint32_t)gw * 32u;
+            if (base > n) continue;
+            for (uint32_t b = 0; b < 32; ++b) {
+                uint32_t i = base + b;
+                if (i <= n && hard[i]) M.hardw[k] |= 1u << b;
+                if (i < n && spec && spec[i]) M.specw[k] |= 1u << b;
+                if (i < n) M.validw[k] |= 1u << b;
+            }
+            if (base < n) {
+                uint32_t xw[8];
+                for (int g = 0; g < 8; ++g) xw[g] = t.load4(base + 4u * g);
+                SplFastWord w = spl_fast_classify(t, xw, base, n, spl_ucd_stage1, spl_ucd_stage2, pattern);
+                for (int q = 0; q <= FM_BAD; ++q) M.m[q][k] = w.m[q];
+            }
+        }
+        std::vector<SplFastLocal> loc(nw);
+        for (int k = 0; k < nw; ++k) {
+            M.sum[k] = spl_fast_local(M, k, nw, pattern, loc[k]);
+        }
+        for (int k = 0; k < nw; ++k) { M.m[FM_A2][k] = loc[k].A2; M.m[FM_A3][k] = loc[k].A3; }
+        bool fb = false;
+        for (int k = 0; k < nw; ++k) if (M.sum[k] & FS_BAD) fb = true;
+        std::vector<uint32_t> out(payload, 0);
+        for (int k = 0; k < nw; ++k) {
+            bool st = false, un = false;
+            uint32_t v = spl_fast_final(M, loc[k], k, nw, pattern, spec != nullptr, st, un);
+            if (st) fb = true;
+            if (k >= (int)halo && k < (int)(halo + payload)) { out[k - halo] = v; if (un) fb = true; }
+        }
+        tile_flag[tile] = fb ? 1 : 0;
+        if (fb) {
+            // what k_pretok_fb does: sequential rules over the tile's 16-byte chunks plus the lead-in worker
+            int dup = 0;
+            uint32_t t0 = tile * payload * 32u, t1 = t0 + payload * 32u;
+            std::vector<uint8_t> tmp(n + 1, 0);
+            for (uint32_t c0 = t0; c0 < t1 && c0 < n; c0 += 16) {
+                uint32_t c1 = c0 + 16; if (c1 > n) c1 = n;
+                HostEnv env{text, hard, spec, tmp.data(), t1 + halo * 32u, &dup};
+                spl_pretok_chunk(env, c0, c1, n, spl_ucd_stage1, spl_ucd_stage2, pattern, spec != nullptr);
+            }
+            {
+                std::vector<uint8_t> tmp2(n + 1, 0);
+                HostEnv env{text, hard, spec, tmp2.data(), t1 + halo * 32u, &dup};
+                spl_pretok_leadin(env, t0, n, spl_ucd_stage1, spl_ucd_stage2, pattern, spec != nullptr);
+                for (uint32_t i = 0; i < n; ++i) tmp[i] |= tmp2[i];
+            }
+            for (uint32_t i = 0; i < n; ++i) if (tmp[i]) starts[i] |= 2;      // bit 1: produced by the fallback
+            continue;
+        }
+        for (uint32_t pk = 0; pk < payload; ++pk)
+            for (uint32_t b = 0; b < 32; ++b)
+                if ((out[pk] >> b) & 1u) {
+                    uint32_t i = ((uint32_t)tile * payload + pk) * 32u + b;
+                    if (i < n) starts[i] |= 1;
+                }
+    }
+    return 0;
+}

@@ -9,7 +9,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = [os.path.join(ROOT, "tests", "csrc", "hosttest.cpp"), os.path.join(ROOT, "splintr_b200", "csrc", "spl_host.cpp")]
-DEPS = SRC + [os.path.join(ROOT, "splintr_b200", "csrc", f) for f in ("spl_pretok.h", "spl_common.h", "spl_host.h", "unicode_tables.inc")]
+DEPS = SRC + [os.path.join(ROOT, "splintr_b200", "csrc", f) for f in ("spl_pretok.h", "spl_pretok_fast.h", "spl_common.h", "spl_host.h", "unicode_tables.inc")]
 LIB = os.path.join(ROOT, "tests", "csrc", "libhosttest.so")
 _lib = None
 
@@ -29,6 +29,7 @@ def load():
     lib.ht_scan_chunked.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_uint32, vp, vp, vp]
     lib.ht_scan_kernel_emul.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
                                         ctypes.c_uint32, vp, vp, vp]
+    lib.ht_scan_fast.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, vp, vp, vp, vp]
     lib.ht_create.restype = vp
     lib.ht_create.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32,
                               ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_uint32), ctypes.c_size_t,
@@ -69,6 +70,20 @@ def scan_kernel_emul(pattern_id, data: bytes, tile, halo, chunk, hard, spec=None
                                     None if sp is None else sp.ctypes.data, st.ctypes.data)
     assert rc == 0, rc
     return np.flatnonzero(st[:n]).tolist()
+
+
+def scan_fast(pattern_id, data: bytes, payload, halo, hard, spec=None):
+    """Bit-parallel path under a (payload, halo)-word tiling.  Returns (starts list, per-tile fallback flags)."""
+    n = len(data)
+    h = np.asarray(hard, dtype=np.uint8)
+    st = np.zeros(n + 1, dtype=np.uint8)
+    n_tiles = max(1, (n + payload * 32 - 1) // (payload * 32))
+    flags = np.zeros(n_tiles, dtype=np.uint8)
+    sp = None if spec is None else np.asarray(spec, dtype=np.uint8)
+    rc = load().ht_scan_fast(pattern_id, data, n, payload, halo, h.ctypes.data,
+                             None if sp is None else sp.ctypes.data, st.ctypes.data, flags.ctypes.data)
+    assert rc == 0, rc
+    return np.flatnonzero(st[:n] & 1).tolist(), flags.tolist(), np.flatnonzero(st[:n]).tolist()
 
 
 class HostTables:
