@@ -50,7 +50,7 @@ struct DevCtx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     void* table_blob = nullptr;
     SplTables* d_tables = nullptr;
-    DevBuf text, doc_off, hard, spec, pstart, tfd, tstate, counters, huge, ids, out_off, fbl;
+    DevBuf text, doc_off, hard, spec, pstart, tfd, tstate, counters, huge, ids, out_off, fbl, tcnt, tsoff, stage;
     size_t huge_words = 0;
     SplKernelProfile prof;
     bool prof_ready = false;
@@ -134,7 +134,7 @@ int upload_tables(spl_tokenizer* tk, DevCtx& dc) {
 
 void destroy_ctx(DevCtx& dc) {
     cudaSetDevice(dc.device);
-    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.hard, &dc.spec, &dc.pstart, &dc.tfd, &dc.tstate, &dc.counters, &dc.huge, &dc.ids, &dc.out_off, &dc.fbl})
+    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.hard, &dc.spec, &dc.pstart, &dc.tfd, &dc.tstate, &dc.counters, &dc.huge, &dc.ids, &dc.out_off, &dc.fbl, &dc.tcnt, &dc.tsoff, &dc.stage})
         b->release();
     if (dc.table_blob) cudaFree(dc.table_blob);
     for (auto& e : dc.ev) if (e) cudaEventDestroy(e);
@@ -161,6 +161,9 @@ int prepare_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
     if (with_special && (rc = dc.spec.ensure(words * 4, tk->err))) return rc;
     if ((rc = dc.tfd.ensure((size_t)(n_tiles + 2) * 4, tk->err))) return rc;
     if ((rc = dc.tstate.ensure((size_t)n_tiles * 8, tk->err))) return rc;
+    if ((rc = dc.tcnt.ensure((size_t)n_tiles * 4, tk->err))) return rc;
+    if ((rc = dc.tsoff.ensure((size_t)n_tiles * 8, tk->err))) return rc;
+    if ((rc = dc.stage.ensure((size_t)(N + 64) * 4, tk->err))) return rc;
     if ((rc = dc.counters.ensure(64, tk->err))) return rc;
     uint32_t n_fast_tiles = (uint32_t)((N + SPL_FAST_PAYLOAD * 32u - 1) / (SPL_FAST_PAYLOAD * 32u));
     if ((rc = dc.fbl.ensure((size_t)(n_fast_tiles + 1) * 4, tk->err))) return rc;
@@ -169,7 +172,6 @@ int prepare_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
     CUDA_TRY(cudaMemsetAsync(dc.hard.p, 0, words * 4, st), tk->err);
     CUDA_TRY(cudaMemsetAsync(dc.pstart.p, 0, words * 4, st), tk->err);
     if (with_special) CUDA_TRY(cudaMemsetAsync(dc.spec.p, 0, words * 4, st), tk->err);
-    CUDA_TRY(cudaMemsetAsync(dc.tstate.p, 0, (size_t)n_tiles * 8, st), tk->err);
     CUDA_TRY(cudaMemsetAsync(dc.counters.p, 0, 64, st), tk->err);
     w.N = (uint32_t)N;
     w.n_docs = (uint32_t)n_docs;
@@ -180,6 +182,10 @@ int prepare_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
     w.bitmap_words = words;
     w.tile_first_doc = (uint32_t*)dc.tfd.p;
     w.tile_state = (uint64_t*)dc.tstate.p;
+    w.tile_cnt = (uint32_t*)dc.tcnt.p;
+    w.tile_soff = (uint64_t*)dc.tsoff.p;
+    w.stage = (uint32_t*)dc.stage.p;
+    w.stage_bump = (uint64_t*)((uint8_t*)dc.counters.p + 32);
     w.counters = (uint32_t*)dc.counters.p;
     w.fb_list = (uint32_t*)dc.fbl.p;
     w.n_fast_tiles = n_fast_tiles;
@@ -303,7 +309,7 @@ int spl_launches_per_call(const spl_tokenizer* tk, uint32_t flags) {
     if (!tk) return 0;
     bool ws = (flags & SPL_ENCODE_WITH_SPECIAL) && !tk->host.sp_id.empty();
     int pre = tk->host.pattern == SPL_PAT_MISTRAL_V3 ? 1 : 2;          // sequential rules | bit-parallel + fallback
-    return 2 + pre + (ws ? 1 : 0);
+    return 4 + pre + (ws ? 1 : 0);                                     // mark_docs, encode, tile_scan, gather
 }
 
 int spl_set_profiling(spl_tokenizer* tk, int enable) {

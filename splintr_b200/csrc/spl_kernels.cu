@@ -358,10 +358,13 @@ struct EncSmem {
     uint32_t text[SPL_WIN / 4 + 4];   // staged bytes (+ slack for unaligned 8-byte key loads)
     uint32_t pb[EN_WORDS + 1];        // piece-start bits
     uint32_t tb[EN_WORDS + 1];        // token-start bits
-    uint32_t mb[SPL_TILE / 32];       // pieces that missed the whole-piece probe
     uint32_t tok[SPL_WIN];            // token id (or symbol during merging) at its first byte
     uint32_t rnk[SPL_WIN];            // rank of the pair (part at i, next part)
     uint32_t wpre[EN_WORDS + 1];      // exclusive token count before each bitmap word
+    uint16_t plist[SPL_TILE + 2];     // window positions of the tile's piece starts, in order (+ end of the last piece)
+    uint16_t mlist[SPL_TILE];         // pieces that missed the whole-piece probe: short ones from the bottom, long from the top
+    uint32_t wtot[EN_WARPS];
+    uint32_t n_short, n_long;
     uint32_t tile, huge_start, huge_end, huge_cnt, huge_off;
     uint64_t prefix;
     uint64_t red[SPL_THREADS];        // block reductions of the out-of-window path
@@ -581,22 +584,121 @@ __device__ uint32_t bpe_piece_block(EncSmem& sm, const SplWork& w, uint32_t gs, 
     return total;
 }
 
-#define ST_AGG  (1ull << 62)
-#define ST_INCL (2ull << 62)
-#define ST_MASK ((1ull << 62) - 1)
+// two independent pair probes issued back to back (the two re-ranks after a merge)
+__device__ __forceinline__ void pair_lookup2(const uint64_t* __restrict__ tab, uint32_t log2,
+                                             bool va, uint32_t la, uint32_t ra, bool vb, uint32_t lb, uint32_t rb,
+                                             uint32_t& outa, uint32_t& outb) {
+    const uint32_t mask = (1u << log2) - 1, symmask = (1u << SPL_SYM_BITS) - 1;
+    uint64_t ka = spl_pair_key(la, ra), kb = spl_pair_key(lb, rb);
+    uint32_t ha = spl_pair_hash(ka, log2), hb = spl_pair_hash(kb, log2);
+    uint64_t ea = va ? __ldg(tab + ha) : SPL_PAIR_EMPTY;
+    uint64_t eb = vb ? __ldg(tab + hb) : SPL_PAIR_EMPTY;
+    outa = SPL_RANK_NONE; outb = SPL_RANK_NONE;
+    while (ea != SPL_PAIR_EMPTY) {
+        if ((ea >> SPL_SYM_BITS) == ka) { outa = (uint32_t)ea & symmask; break; }
+        ha = (ha + 1) & mask; ea = __ldg(tab + ha);
+    }
+    while (eb != SPL_PAIR_EMPTY) {
+        if ((eb >> SPL_SYM_BITS) == kb) { outb = (uint32_t)eb & symmask; break; }
+        hb = (hb + 1) & mask; eb = __ldg(tab + hb);
+    }
+}
+
+// whole-piece probe of a 17..32-byte piece by one thread (long-key table, verified against the token bytes)
+__device__ uint32_t lookupL_thread(const SplTables* T, const uint32_t* text, uint32_t s, uint32_t len) {
+    if (len > T->max_key_len) return SPL_RANK_NONE;
+    uint64_t sum = 0;
+    for (uint32_t i = 0; i * 8 < len; ++i) {
+        uint64_t wv = sm_load8(text, s + i * 8);
+        uint32_t rem = len - i * 8;
+        if (rem < 8) wv &= (1ull << (8 * rem)) - 1;
+        sum += spl_hashL_word(wv, i);
+    }
+    uint64_t hv = spl_hashL_final(sum, len);
+    uint32_t mask = (1u << T->tl_log2) - 1, h = (uint32_t)(hv >> (64 - T->tl_log2));
+    for (;;) {
+        uint4 v = __ldg(reinterpret_cast<const uint4*>(T->tl + h));     // {hash lo, hash hi, id, len}
+        if (v.w == 0) return SPL_RANK_NONE;
+        if (v.w == len && v.x == (uint32_t)hv && v.y == (uint32_t)(hv >> 32)) {
+            const uint8_t* kb = T->tok_bytes + __ldg(T->tok_off + v.z);
+            bool ok = true;
+            for (uint32_t j = 0; j < len; ++j) ok &= (sm_byte(text, s + j) == __ldg(kb + j));
+            if (ok) return v.z;
+        }
+        h = (h + 1) & mask;
+    }
+}
+
+// One THREAD merges the piece at window bytes [s, s+n), 1 <= n <= 32 (bpe.rs:83-194): parts are the set bits of
+// `live` (bit i = a part starts at byte s+i), their symbols sit in sm.tok, the rank of (part, next part) in sm.rnk.
+// 32 pieces merge side by side in a warp, so the probe latency of the re-ranks overlaps across pieces.
+__device__ void bpe_piece_thread(EncSmem& sm, const SplTables* T, uint32_t s, uint32_t n) {
+    const uint64_t* __restrict__ ptab = T->pair;
+    const uint32_t plog = T->pair_log2;
+    for (uint32_t i = 0; i < n; ++i) sm.tok[s + i] = T->byte_sym[sm_byte(sm.text, s + i)];
+    for (uint32_t i = 0; i + 1 < n; i += 2) {
+        uint32_t ra, rb;
+        bool vb = i + 2 < n;
+        pair_lookup2(ptab, plog, true, sm.tok[s + i], sm.tok[s + i + 1], vb, vb ? sm.tok[s + i + 1] : 0u, vb ? sm.tok[s + i + 2] : 0u, ra, rb);
+        sm.rnk[s + i] = ra;
+        if (vb) sm.rnk[s + i + 1] = rb;
+    }
+    sm.rnk[s + n - 1] = SPL_RANK_NONE;
+    uint32_t live = n >= 32u ? 0xFFFFFFFFu : ((1u << n) - 1u);
+    for (;;) {
+        uint32_t best = SPL_RANK_NONE, bpos = 0;
+        for (uint32_t m = live; m; m &= m - 1) {
+            uint32_t i = __ffs(m) - 1;
+            uint32_t r = sm.rnk[s + i];
+            if (r < best) { best = r; bpos = i; }                 // strict <: leftmost minimum (bpe.rs:133)
+        }
+        if (best == SPL_RANK_NONE) break;
+        uint32_t above = bpos >= 31u ? 0u : (live & ~((2u << bpos) - 1u));
+        uint32_t nx = __ffs(above) - 1;                            // the absorbed part (exists: its pair has a rank)
+        uint32_t above2 = above & (above - 1);
+        uint32_t below = live & ((1u << bpos) - 1u);
+        bool has_nn = above2 != 0, has_pv = below != 0;
+        uint32_t nn = has_nn ? __ffs(above2) - 1 : 0u, pv = has_pv ? 31u - __clz(below) : 0u;
+        live &= ~(1u << nx);
+        sm.tok[s + bpos] = best;                                   // merged id == its rank
+        uint32_t r1, r0;
+        pair_lookup2(ptab, plog, has_nn, best, has_nn ? sm.tok[s + nn] : 0u, has_pv, has_pv ? sm.tok[s + pv] : 0u, best, r1, r0);
+        sm.rnk[s + bpos] = r1;
+        if (has_pv) sm.rnk[s + pv] = r0;
+    }
+    // bytes that are not in the vocabulary produce no id (bpe.rs:187-191)
+    for (uint32_t m = live; m; m &= m - 1) {
+        uint32_t i = __ffs(m) - 1;
+        if (sm.tok[s + i] >= SPL_UNK_BASE) live &= ~(1u << i);
+    }
+    // publish the parts: the piece-start bit is already set in tb
+    uint32_t w0 = s >> 5, sh = s & 31u;
+    uint32_t lo = live << sh, hi = sh ? (live >> (32u - sh)) : 0u;
+    if (lo & ~(1u << sh)) atomicOr(&sm.tb[w0], lo);
+    if (hi) atomicOr(&sm.tb[w0 + 1], hi);
+    if (!(live & 1u)) atomicAnd(&sm.tb[w0], ~(1u << sh));
+}
+
+// ------------------------------------------------------------------------------------------
+// k_encode: one tile per block iteration (ticketed).  No block waits for another one: the ids of a tile go to a
+// bump-allocated chunk of the staging buffer; k_tile_scan + k_gather put them in document order afterwards.
+// ------------------------------------------------------------------------------------------
+extern __shared__ __align__(16) uint8_t spl_dyn_smem[];
 
 __global__ void __launch_bounds__(SPL_THREADS) k_encode(SplWork w) {
-    __shared__ __align__(16) EncSmem sm;
+    EncSmem& sm = *reinterpret_cast<EncSmem*>(spl_dyn_smem);
     const SplTables* T = w.T;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t N = w.N, Nup = (N + 15u) & ~15u;
 
+    if (tid == 0) sm.tile = atomicAdd(&w.counters[0], 1u);
+    __syncthreads();
     for (;;) {
-        if (tid == 0) sm.tile = atomicAdd(&w.counters[0], 1u);
-        __syncthreads();
         const uint32_t tile = sm.tile;
         if (tile >= w.n_tiles) return;
         const uint32_t tile0 = tile * SPL_TILE;
+        __syncthreads();                                          // everybody has read sm.tile
+        if (tid == 0) sm.tile = atomicAdd(&w.counters[0], 1u);    // next ticket: its latency hides behind this tile
 
         // ---- stage the window -----------------------------------------------------------
         for (uint32_t v = tid; v < SPL_WIN / 16 + 1; v += SPL_THREADS) {
@@ -610,50 +712,75 @@ __global__ void __launch_bounds__(SPL_THREADS) k_encode(SplWork w) {
             sm.pb[v] = pbv;
             sm.tb[v] = v < SPL_TILE / 32 ? pbv : 0u;     // beyond the tile only this tile's last piece adds bits
         }
-        if (tid < SPL_TILE / 32) sm.mb[tid] = 0;
-        if (tid == 0) { sm.huge_start = SPL_RANK_NONE; sm.huge_cnt = 0; }
+        if (tid == 0) { sm.huge_start = SPL_RANK_NONE; sm.huge_cnt = 0; sm.n_short = 0; sm.n_long = 0; }
         __syncthreads();
 
-        // ---- fast path: one thread per piece start in its 16 bytes ------------------------
-        {
-            uint32_t my = (sm.pb[tid >> 1] >> ((tid & 1u) * 16u)) & 0xFFFFu;
-            const uint32_t avail = N - tile0;            // text bytes from tile0 on (>= 1 piece start only below this)
-            while (my) {
-                uint32_t b = __ffs(my) - 1;
-                my &= my - 1;
-                uint32_t s = tid * 16 + b;
-                if (s >= avail) break;                   // sentinel bit at N
-                uint32_t e = sm_next_bit(sm.pb, s + 1, SPL_WIN + 1);
-                if (e > SPL_WIN) { sm.huge_start = s; break; }    // the tile's last piece leaves the window
-                uint32_t len = e - s;
-                uint32_t id = SPL_RANK_NONE;
-                if (w.with_special && ((__ldg(w.spec + ((tile0 + s) >> 5)) >> ((tile0 + s) & 31)) & 1u)) {
-                    id = special_id(T, [&](uint32_t j) { return sm_byte(sm.text, s + j); }, len);
-                    if (id == SPL_RANK_NONE) { atomicAnd(&sm.tb[s >> 5], ~(1u << (s & 31))); continue; }
-                } else if (len <= 8) {
-                    uint64_t k0 = sm_load8(sm.text, s);
-                    if (len < 8) k0 &= (1ull << (8 * len)) - 1;
-                    id = lookup8(T->t8, T->t8_log2, k0, len);
-                } else if (len <= 16) {
-                    uint64_t k0 = sm_load8(sm.text, s), k1 = sm_load8(sm.text, s + 8);
-                    if (len < 16) k1 &= (1ull << (8 * (len - 8))) - 1;
-                    id = lookup16(T->t16, T->t16_log2, k0, k1, len);
-                }
-                if (id != SPL_RANK_NONE) sm.tok[s] = id;
-                else atomicOr(&sm.mb[s >> 5], 1u << (s & 31));
-            }
+        // ---- piece list: positions of the piece starts of this tile, in order ------------------
+        const uint32_t avail = N - tile0;                          // text bytes from tile0 on
+        uint32_t my = (sm.pb[tid >> 1] >> ((tid & 1u) * 16u)) & 0xFFFFu;
+        if (tid * 16u + 16u > avail) my &= (tid * 16u >= avail) ? 0u : ((1u << (avail - tid * 16u)) - 1u);   // sentinel bit at N
+        uint32_t cnt = __popc(my), incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= (uint32_t)o) incl += t;
+        }
+        if (lane == 31) sm.wtot[warp] = incl;
+        __syncthreads();
+        uint32_t base = incl - cnt;
+#pragma unroll
+        for (uint32_t q = 0; q < EN_WARPS; ++q) base += (q < warp) ? sm.wtot[q] : 0u;
+        uint32_t P = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < EN_WARPS; ++q) P += sm.wtot[q];
+        while (my) {
+            uint32_t b = __ffs(my) - 1;
+            my &= my - 1;
+            sm.plist[base++] = (uint16_t)(tid * 16u + b);
+        }
+        if (tid == 0) {
+            uint32_t e = sm_next_bit(sm.pb, SPL_TILE < avail ? SPL_TILE : avail, SPL_WIN + 1);
+            sm.plist[P] = (uint16_t)(e > SPL_WIN ? SPL_WIN + 1 : e);      // end of the last piece (WIN+1: it leaves the window)
         }
         __syncthreads();
 
-        // ---- slow path: one warp per missed piece --------------------------------------------
-        for (uint32_t wi = warp; wi < SPL_TILE / 32; wi += EN_WARPS) {
-            uint32_t bits = sm.mb[wi];
-            while (bits) {
-                uint32_t b = __ffs(bits) - 1;
-                bits &= bits - 1;
-                uint32_t s = wi * 32 + b;
-                uint32_t e = sm_next_bit(sm.pb, s + 1, SPL_WIN + 1);
-                bpe_piece_warp(sm, T, s, e);
+        // ---- one thread per piece: whole-piece probe (tokenizer.rs:703-705, bpe.rs:73-80) --------------
+        for (uint32_t j = tid; j < P; j += SPL_THREADS) {
+            uint32_t s = sm.plist[j], e = sm.plist[j + 1];
+            if (e > SPL_WIN) { sm.huge_start = s; continue; }
+            uint32_t len = e - s;
+            uint32_t id = SPL_RANK_NONE;
+            if (w.with_special && ((__ldg(w.spec + ((tile0 + s) >> 5)) >> ((tile0 + s) & 31)) & 1u)) {
+                id = special_id(T, [&](uint32_t q) { return sm_byte(sm.text, s + q); }, len);
+                if (id == SPL_RANK_NONE) { atomicAnd(&sm.tb[s >> 5], ~(1u << (s & 31))); continue; }
+            } else if (len <= 8) {
+                uint64_t k0 = sm_load8(sm.text, s);
+                if (len < 8) k0 &= (1ull << (8 * len)) - 1;
+                id = lookup8(T->t8, T->t8_log2, k0, len);
+            } else if (len <= 16) {
+                uint64_t k0 = sm_load8(sm.text, s), k1 = sm_load8(sm.text, s + 8);
+                if (len < 16) k1 &= (1ull << (8 * (len - 8))) - 1;
+                id = lookup16(T->t16, T->t16_log2, k0, k1, len);
+            } else if (len <= 32) {
+                id = lookupL_thread(T, sm.text, s, len);
+            }
+            if (id != SPL_RANK_NONE) sm.tok[s] = id;
+            else if (len <= 32) sm.mlist[atomicAdd(&sm.n_short, 1u)] = (uint16_t)j;
+            else sm.mlist[SPL_TILE - 1 - atomicAdd(&sm.n_long, 1u)] = (uint16_t)j;      // long pieces fill from the top
+        }
+        __syncthreads();
+
+        // ---- misses: leftmost-min-rank merge; one thread per short piece, one warp per long piece ---------
+        {
+            const uint32_t n_short = sm.n_short, n_long = sm.n_long;
+            for (uint32_t i = tid; i < n_short; i += SPL_THREADS) {
+                uint32_t j = sm.mlist[i];
+                uint32_t s = sm.plist[j];
+                bpe_piece_thread(sm, T, s, sm.plist[j + 1] - s);
+            }
+            for (uint32_t i = warp; i < n_long; i += EN_WARPS) {
+                uint32_t j = sm.mlist[SPL_TILE - 1 - i];
+                bpe_piece_warp(sm, T, sm.plist[j], sm.plist[j + 1]);
             }
         }
         __syncthreads();
@@ -682,7 +809,7 @@ __global__ void __launch_bounds__(SPL_THREADS) k_encode(SplWork w) {
             __syncthreads();
         }
 
-        // ---- count ids, word prefixes, tile prefix ------------------------------------------------
+        // ---- count ids, word prefixes, staging chunk ---------------------------------------------------
         if (warp == 0) {
             // exclusive scan of the per-word popcounts (EN_WORDS <= 160: five words per lane)
             uint32_t local[5], run = 0;
@@ -692,63 +819,46 @@ __global__ void __launch_bounds__(SPL_THREADS) k_encode(SplWork w) {
                 local[q] = v < EN_WORDS ? __popc(sm.tb[v]) : 0u;
                 run += local[q];
             }
-            uint32_t incl = run;
+            uint32_t inc2 = run;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t = __shfl_up_sync(FULL, incl, o);
-                if (lane >= (uint32_t)o) incl += t;
+                uint32_t t = __shfl_up_sync(FULL, inc2, o);
+                if (lane >= (uint32_t)o) inc2 += t;
             }
-            uint32_t base = incl - run;
+            uint32_t b2 = inc2 - run;
 #pragma unroll
             for (int q = 0; q < 5; ++q) {
                 uint32_t v = lane * 5 + q;
-                if (v <= EN_WORDS) sm.wpre[v] = base;
-                base += local[q];
+                if (v <= EN_WORDS) sm.wpre[v] = b2;
+                b2 += local[q];
             }
-            // ---- decoupled look-back over tiles ------------------------------------------------
-            uint32_t win_cnt = __shfl_sync(FULL, incl, 31);
-            uint64_t total = (uint64_t)win_cnt + huge_cnt;
-            volatile uint64_t* st = w.tile_state;
+            uint32_t win_cnt = __shfl_sync(FULL, inc2, 31);
             if (lane == 0) {
-                __threadfence();
-                st[tile] = (tile == 0 ? ST_INCL : ST_AGG) | total;
+                uint32_t total = win_cnt + huge_cnt;
+                uint64_t off = atomicAdd(reinterpret_cast<unsigned long long*>(w.stage_bump), (unsigned long long)total);
+                sm.prefix = off;
+                w.tile_cnt[tile] = total;
+                w.tile_soff[tile] = off;
             }
-            uint64_t prefix = 0;
-            if (tile > 0) {
-                int64_t look = (int64_t)tile - 1;
-                for (;;) {
-                    int64_t idx = look - lane;
-                    uint64_t v = ST_INCL;                         // lanes before tile 0 contribute an inclusive 0
-                    if (idx >= 0) { do { v = st[idx]; } while ((v >> 62) == 0); }
-                    uint32_t incl_mask = __ballot_sync(FULL, (v >> 62) == 2);
-                    uint32_t first = incl_mask ? (uint32_t)__ffs(incl_mask) - 1 : 32u;
-                    uint64_t contrib = lane <= first ? (v & ST_MASK) : 0ull;
-                    prefix += warp_sum_u64(contrib);
-                    if (incl_mask) break;
-                    look -= 32;
-                }
-                if (lane == 0) { __threadfence(); st[tile] = ST_INCL | (prefix + total); }
-            }
-            if (lane == 0) sm.prefix = prefix;
         }
         __syncthreads();
-        const uint64_t prefix = sm.prefix;
+        const uint64_t soff = sm.prefix;
 
-        // ---- ordered id output -----------------------------------------------------------------
+        // ---- ids of the tile, in order, into its staging chunk --------------------------------------------
         for (uint32_t hw = tid; hw < EN_WORDS * 2; hw += SPL_THREADS) {
             uint32_t word = sm.tb[hw >> 1], sh = (hw & 1u) * 16u;
-            uint32_t my = (word >> sh) & 0xFFFFu;
-            uint64_t o = prefix + sm.wpre[hw >> 1] + __popc(word & ((1u << sh) - 1u));
-            while (my) {
-                uint32_t b = __ffs(my) - 1;
-                my &= my - 1;
-                w.ids[o++] = sm.tok[hw * 16 + b];
+            uint32_t mine = (word >> sh) & 0xFFFFu;
+            uint64_t o = soff + sm.wpre[hw >> 1] + __popc(word & ((1u << sh) - 1u));
+            while (mine) {
+                uint32_t b = __ffs(mine) - 1;
+                mine &= mine - 1;
+                w.stage[o++] = sm.tok[hw * 16 + b];
             }
         }
         uint32_t win_total = sm.wpre[EN_WORDS];
         if (huge_cnt) {
             // block-ordered compaction of the survivors in huge_scratch[0 .. huge_len)
-            uint64_t base = prefix + win_total;
+            uint64_t hb = soff + win_total;
             uint32_t per = (huge_len + SPL_THREADS - 1) / SPL_THREADS;
             uint32_t lo = tid * per, hi = lo + per < huge_len ? lo + per : huge_len;
             uint32_t c = 0;
@@ -757,19 +867,65 @@ __global__ void __launch_bounds__(SPL_THREADS) k_encode(SplWork w) {
             __syncthreads();
             if (tid == 0) { uint64_t run = 0; for (int q = 0; q < SPL_THREADS; ++q) { uint64_t t = sm.red[q]; sm.red[q] = run; run += t; } }
             __syncthreads();
-            uint64_t o = base + sm.red[tid];
-            for (uint32_t j = lo; j < hi; ++j) { uint32_t v = huge_scratch[j]; if (v != SPL_RANK_NONE) w.ids[o++] = v; }
+            uint64_t o = hb + sm.red[tid];
+            for (uint32_t j = lo; j < hi; ++j) { uint32_t v = huge_scratch[j]; if (v != SPL_RANK_NONE) w.stage[o++] = v; }
         }
 
-        // ---- per-document output offsets -----------------------------------------------------------
+        // ---- per-document output offsets, relative to the tile (k_gather adds the tile's prefix) -----------
         {
             uint32_t d0 = __ldg(w.tile_first_doc + tile), d1 = __ldg(w.tile_first_doc + tile + 1);
             for (uint32_t d = d0 + tid; d < d1; d += SPL_THREADS) {
                 uint32_t x = (uint32_t)(w.doc_off[d] - w.off_base - tile0);
-                w.out_off[d] = prefix + sm.wpre[x >> 5] + __popc(sm.tb[x >> 5] & ((1u << (x & 31)) - 1u));
+                w.out_off[d] = sm.wpre[x >> 5] + __popc(sm.tb[x >> 5] & ((1u << (x & 31)) - 1u));
             }
         }
         __syncthreads();
+    }
+}
+
+// exclusive prefix of the per-tile id counts (one block; tiles are few: N / 4096)
+__global__ void __launch_bounds__(1024) k_tile_scan(SplWork w) {
+    __shared__ uint64_t s_w[32];
+    __shared__ uint64_t s_carry;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < w.n_tiles; b0 += 1024) {
+        uint32_t i = b0 + tid;
+        uint64_t v = i < w.n_tiles ? (uint64_t)w.tile_cnt[i] : 0ull, incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t lo = __shfl_up_sync(FULL, (uint32_t)incl, o), hi = __shfl_up_sync(FULL, (uint32_t)(incl >> 32), o);
+            if (lane >= (uint32_t)o) incl += (uint64_t)lo | ((uint64_t)hi << 32);
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint64_t x = s_w[lane], xi = x;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t lo = __shfl_up_sync(FULL, (uint32_t)xi, o), hi = __shfl_up_sync(FULL, (uint32_t)(xi >> 32), o);
+                if (lane >= (uint32_t)o) xi += (uint64_t)lo | ((uint64_t)hi << 32);
+            }
+            s_w[lane] = xi - x;
+        }
+        __syncthreads();
+        uint64_t carry = s_carry;
+        if (i < w.n_tiles) w.tile_state[i] = carry + s_w[warp] + incl - v;
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + s_w[warp] + incl;
+        __syncthreads();
+    }
+}
+
+// staging chunk of every tile -> its place in document order; tile-relative document offsets -> global
+__global__ void __launch_bounds__(256) k_gather(SplWork w) {
+    for (uint32_t tile = blockIdx.x; tile < w.n_tiles; tile += gridDim.x) {
+        const uint64_t prefix = w.tile_state[tile], soff = w.tile_soff[tile];
+        const uint32_t cnt = w.tile_cnt[tile];
+        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) w.ids[prefix + i] = w.stage[soff + i];
+        uint32_t d0 = __ldg(w.tile_first_doc + tile), d1 = __ldg(w.tile_first_doc + tile + 1);
+        for (uint32_t d = d0 + threadIdx.x; d < d1; d += blockDim.x) w.out_off[d] += prefix;
     }
 }
 
@@ -777,6 +933,7 @@ __global__ void __launch_bounds__(SPL_THREADS) k_encode(SplWork w) {
 // host launcher
 // ------------------------------------------------------------------------------------------
 void spl_kernels_init() {
+    cudaFuncSetAttribute(k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
     cudaFuncSetAttribute(k_encode, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaGetLastError();
 }
@@ -810,10 +967,15 @@ int spl_launch_encode(const SplWork& w, int num_sms, cudaStream_t stream, SplKer
         mark("k_pretok_fb");
     }
     {
-        uint32_t cap = (uint32_t)num_sms * 5;
+        uint32_t cap = (uint32_t)num_sms * 4;
         uint32_t blocks = w.n_tiles < cap ? w.n_tiles : cap;
-        k_encode<<<blocks, SPL_THREADS, 0, stream>>>(w);
+        k_encode<<<blocks, SPL_THREADS, sizeof(EncSmem), stream>>>(w);
         mark("k_encode");
+        k_tile_scan<<<1, 1024, 0, stream>>>(w);
+        mark("k_tile_scan");
+        uint32_t gcap = (uint32_t)num_sms * 16;
+        k_gather<<<w.n_tiles < gcap ? w.n_tiles : gcap, 256, 0, stream>>>(w);
+        mark("k_gather");
     }
     return launches;
 }

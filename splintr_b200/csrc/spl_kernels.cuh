@@ -26,7 +26,11 @@ struct SplWork {
     uint32_t*       pstart;      // bitmap words: piece starts (incl. sentinel bit N)
     size_t          bitmap_words;
     uint32_t*       tile_first_doc;   // [n_tiles+1]
-    uint64_t*       tile_state;       // [n_tiles] decoupled look-back
+    uint64_t*       tile_state;       // [n_tiles] exclusive prefix of tile_cnt (k_tile_scan)
+    uint32_t*       tile_cnt;         // [n_tiles] ids produced by each tile
+    uint64_t*       tile_soff;        // [n_tiles] where the tile's ids sit in `stage`
+    uint32_t*       stage;            // [>= N] ids in tile-completion order
+    uint64_t*       stage_bump;       // bump allocator of `stage` (counters + 8 bytes .. 16-byte aligned)
     uint32_t*       counters;         // [8]: 0 = encode ticket, 1 = error flags, 2 = huge pool bump, 3 = fallback tiles
     uint32_t*       fb_list;          // [n_fast_tiles] fast-path tiles handed to the sequential rules
     uint32_t        n_fast_tiles;
