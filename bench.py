@@ -308,10 +308,16 @@ def main():
         # every input byte read once, every u32 id written once, u64 doc offsets in and out
         b_alg = n_bytes + 4 * n_tok + 16 * (n_docs + 1)
         roof = None
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                traffic = json.load(f).get(dom, {}).get("bytes") if args.docs == 100_000 else None
+        except Exception:
+            traffic = None
         if dom:
             ach = b_alg / (kmean[dom] * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg,
+                    "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg,
                     "kernel_ms": kmean, "kernel_share_of_step": kmean[dom] / max(sum(kmean.values()), 1e-9)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
