@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <new>
 #include <string>
@@ -46,7 +47,9 @@ struct DevBuf {
 struct DevCtx {
     int device = 0;
     int num_sms = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;          // kernels (+ the small per-chunk results)
+    cudaStream_t s_in = nullptr, s_out = nullptr;   // host->device staging, ids device->host
+    std::vector<cudaEvent_t> pipe_ev;       // per-chunk events of spl_encode_batch, grown on demand
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     void* table_blob = nullptr;
     SplTables* d_tables = nullptr;
@@ -62,6 +65,8 @@ struct PinnedBuf { void* p; size_t cap; };
 
 struct spl_tokenizer {
     bool profiling = false;
+    bool trace = false;                     // SPL_TRACE=1: per-chunk timeline of spl_encode_batch on stderr
+    uint64_t chunk_bytes = 0;               // pipeline chunk size of spl_encode_batch (0 = automatic)
     SplHostTables host;
     std::vector<DevCtx> devs;
     std::string err;
@@ -139,18 +144,19 @@ void destroy_ctx(DevCtx& dc) {
     if (dc.table_blob) cudaFree(dc.table_blob);
     for (auto& e : dc.ev) if (e) cudaEventDestroy(e);
     if (dc.prof_ready) for (auto& e : dc.prof.ev) cudaEventDestroy(e);
+    for (auto& e : dc.pipe_ev) cudaEventDestroy(e);
     if (dc.stream) cudaStreamDestroy(dc.stream);
+    if (dc.s_in) cudaStreamDestroy(dc.s_in);
+    if (dc.s_out) cudaStreamDestroy(dc.s_out);
 }
 
 // limits of one device shard: 32-bit positions inside the kernels
 const uint64_t kMaxShardBytes = 0xFFFFFFFFull - 4ull * SPL_WIN;
 
-// Prepare the internal workspace of `dc` for N bytes / n_docs documents and fill `w`
-// (text / doc_off / ids / out_off are set by the caller).  Enqueues the zero-fills.
-int prepare_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, bool with_special,
-                 cudaStream_t st, SplWork& w) {
+// Size the internal workspace of `dc` for N bytes / n_docs documents (may reallocate: nothing may be in flight).
+int reserve_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, bool with_special) {
     if (N > kMaxShardBytes || n_docs > 0xFFFFFFF0ull) {
-        tk->err = "a single device shard is limited to 4 GiB of text";
+        tk->err = "one device pass is limited to 4 GiB of text";
         return SPL_ERR_UNSUPPORTED;
     }
     size_t words = (size_t)((N + SPL_WIN) / 32 + 16);
@@ -169,6 +175,18 @@ int prepare_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
     if ((rc = dc.fbl.ensure((size_t)(n_fast_tiles + 1) * 4, tk->err))) return rc;
     if (dc.huge_words == 0) dc.huge_words = (size_t)16 << 20;             // 64 MiB of scratch
     if ((rc = dc.huge.ensure(dc.huge_words * 4, tk->err))) return rc;
+    return SPL_OK;
+}
+
+// Prepare the internal workspace of `dc` for N bytes / n_docs documents and fill `w`
+// (text / doc_off / ids / out_off are set by the caller).  Enqueues the zero-fills.
+int prepare_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, bool with_special,
+                 cudaStream_t st, SplWork& w) {
+    int rc = reserve_work(tk, dc, N, n_docs, with_special);
+    if (rc) return rc;
+    size_t words = (size_t)((N + SPL_WIN) / 32 + 16);
+    uint32_t n_tiles = (uint32_t)(N / SPL_TILE) + 1;
+    uint32_t n_fast_tiles = (uint32_t)((N + SPL_FAST_PAYLOAD * 32u - 1) / (SPL_FAST_PAYLOAD * 32u));
     CUDA_TRY(cudaMemsetAsync(dc.hard.p, 0, words * 4, st), tk->err);
     CUDA_TRY(cudaMemsetAsync(dc.pstart.p, 0, words * 4, st), tk->err);
     if (with_special) CUDA_TRY(cudaMemsetAsync(dc.spec.p, 0, words * 4, st), tk->err);
@@ -257,6 +275,8 @@ int spl_create(const uint8_t* vocab, size_t vocab_len, int pattern_id, uint32_t 
     }
     spl_tokenizer* tk = new (std::nothrow) spl_tokenizer();
     if (!tk) return SPL_ERR_OOM;
+    if (const char* tr = getenv("SPL_TRACE")) tk->trace = tr[0] == '1';
+    if (const char* cb = getenv("SPL_CHUNK_BYTES")) tk->chunk_bytes = strtoull(cb, nullptr, 10);
     uint32_t hflags = (flags & SPL_CREATE_BYTE_LEVEL) ? SPL_FLAG_BYTE_LEVEL : 0;
     if (!spl_build_tables(tk->host, vocab, vocab_len, pattern_id, hflags, special_strs, special_ids, n_special)) {
         g_create_error = tk->host.error;
@@ -279,6 +299,8 @@ int spl_create(const uint8_t* vocab, size_t vocab_len, int pattern_id, uint32_t 
             CUDA_TRY(cudaSetDevice(dc.device), tk->err);
             CUDA_TRY(cudaDeviceGetAttribute(&dc.num_sms, cudaDevAttrMultiProcessorCount, dc.device), tk->err);
             CUDA_TRY(cudaStreamCreateWithFlags(&dc.stream, cudaStreamNonBlocking), tk->err);
+            CUDA_TRY(cudaStreamCreateWithFlags(&dc.s_in, cudaStreamNonBlocking), tk->err);
+            CUDA_TRY(cudaStreamCreateWithFlags(&dc.s_out, cudaStreamNonBlocking), tk->err);
             for (auto& e : dc.ev) CUDA_TRY(cudaEventCreate(&e), tk->err);
             spl_kernels_init();
             return upload_tables(tk, dc);
@@ -389,6 +411,19 @@ int spl_encode_batch_device(spl_tokenizer* tk, int dev_index, const uint8_t* d_b
     }
 }
 
+// One pipeline stage of spl_encode_batch: a contiguous range of documents of one device.
+struct Chunk {
+    int g;                      // device index
+    size_t d0, d1;              // documents [d0, d1)
+    uint64_t b0, b1;            // bytes [b0, b1) of the caller's buffer
+    size_t text_off;            // 16-byte aligned offset of the chunk inside the device text buffer
+    size_t ids_off;             // u32 index of the chunk's id region inside the device id buffer
+    size_t ev;                  // first of its 4 events in DevCtx::pipe_ev (copied in, kernels start, done, ids copied out)
+    volatile uint64_t* meta;    // pinned: [0] id count, [1..2] device counters
+    uint64_t n_tokens;
+    uint64_t tok_base;          // position of its ids in the result
+};
+
 int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* offsets, size_t n_docs,
                      uint32_t flags, spl_result** out) {
     if (!tk || !out) return SPL_ERR_INVALID_ARG;
@@ -402,7 +437,7 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
     int rc = check_special_support(tk, flags, with_special);
     if (rc) return rc;
 
-    // ---- shard documents over devices by cumulative bytes ----------------------------------
+    // ---- shard documents over devices by cumulative bytes, then cut every shard into pipeline chunks ----
     const size_t G = tk->devs.size();
     std::vector<size_t> dlo(G + 1, 0);
     for (size_t g = 1; g < G; ++g) {
@@ -411,6 +446,32 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
         dlo[g] = std::max(std::min(d, n_docs), dlo[g - 1]);
     }
     dlo[G] = n_docs;
+    std::vector<Chunk> chunks;
+    std::vector<size_t> text_need(G, 0), max_nb(G, 0), max_nd(G, 0);
+    for (size_t g = 0; g < G; ++g) {
+        const uint64_t s0 = offsets[dlo[g]], s1 = offsets[dlo[g + 1]], nb = s1 - s0;
+        uint64_t target = tk->chunk_bytes ? tk->chunk_bytes : std::min<uint64_t>(std::max<uint64_t>(nb / 12, 4u << 20), 256u << 20);
+        target = std::min<uint64_t>(target, kMaxShardBytes / 2);
+        size_t d = dlo[g], toff = 0;
+        do {
+            Chunk c;
+            memset(&c, 0, sizeof(c));
+            c.g = (int)g; c.d0 = d; c.b0 = offsets[d];
+            size_t e = std::upper_bound(offsets + d, offsets + dlo[g + 1] + 1, c.b0 + target) - offsets;   // first doc end beyond the target
+            e = std::min(std::max(e, d + 1), dlo[g + 1]);
+            if (offsets[dlo[g + 1]] - c.b0 <= target + target / 4) e = dlo[g + 1];                       // no runt at the end
+            if (d == dlo[g + 1]) e = d;                                                                    // shard without documents
+            c.d1 = e; c.b1 = offsets[e];
+            c.text_off = toff; c.ids_off = (size_t)(c.b0 - s0);
+            toff += align_up((size_t)(c.b1 - c.b0) + 16, 16);
+            max_nb[g] = std::max<size_t>(max_nb[g], (size_t)(c.b1 - c.b0));
+            max_nd[g] = std::max<size_t>(max_nd[g], c.d1 - c.d0);
+            chunks.push_back(c);
+            d = e;
+        } while (d < dlo[g + 1]);
+        text_need[g] = toff + 64;
+    }
+    const size_t C = chunks.size();
 
     DeviceGuard guard;
     spl_result* r = new (std::nothrow) spl_result();
@@ -419,105 +480,198 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
     r->owner = tk; r->n_docs = n_docs; r->n_tokens = 0;
     r->ids_buf = PinnedBuf{nullptr, 0};
     r->off_buf = take_pinned(tk, (n_docs + 1) * 8);
-    if (!r->off_buf.p) { delete r; tk->err = "pinned host allocation failed"; return SPL_ERR_OOM; }
+    PinnedBuf meta_buf = take_pinned(tk, C * 32);
+    auto fail = [&](int code) {
+        for (auto& dc : tk->devs) { cudaSetDevice(dc.device); cudaStreamSynchronize(dc.s_in); cudaStreamSynchronize(dc.stream); cudaStreamSynchronize(dc.s_out); }
+        cudaGetLastError();
+        give_pinned(tk, r->off_buf); give_pinned(tk, r->ids_buf); give_pinned(tk, meta_buf);
+        delete r;
+        return code;
+    };
+    if (!r->off_buf.p || !meta_buf.p) { tk->err = "pinned host allocation failed"; return fail(SPL_ERR_OOM); }
     uint64_t* res_off = (uint64_t*)r->off_buf.p;
-    auto fail = [&](int code) { give_pinned(tk, r->off_buf); give_pinned(tk, r->ids_buf); delete r; return code; };
+    for (size_t c = 0; c < C; ++c) chunks[c].meta = (volatile uint64_t*)((uint8_t*)meta_buf.p + c * 32);
 
-    std::vector<SplWork> works(G);
-    std::vector<uint64_t> shard_tokens(G, 0);
-    std::vector<std::vector<uint32_t>> h_counters(G, std::vector<uint32_t>(4, 0));
+    // ---- device buffers: whole-shard text / ids / offsets, workspace for the largest chunk ----
+    for (size_t g = 0; g < G; ++g) {
+        DevCtx& dc = tk->devs[g];
+        auto reserve = [&]() -> int {
+            CUDA_TRY(cudaSetDevice(dc.device), tk->err);
+            const size_t nd = dlo[g + 1] - dlo[g];
+            const uint64_t nb = offsets[dlo[g + 1]] - offsets[dlo[g]];
+            int rc2;
+            if ((rc2 = dc.text.ensure(text_need[g], tk->err))) return rc2;
+            if ((rc2 = dc.doc_off.ensure((nd + 1) * 8, tk->err))) return rc2;
+            if ((rc2 = dc.ids.ensure((nb + 16) * 4, tk->err))) return rc2;
+            if ((rc2 = dc.out_off.ensure((nd + 1) * 8, tk->err))) return rc2;
+            if ((rc2 = reserve_work(tk, dc, max_nb[g], max_nd[g], with_special))) return rc2;
+            size_t n_ev = 0;
+            for (auto& c : chunks) if (c.g == (int)g) { c.ev = n_ev; n_ev += 4; }
+            while (dc.pipe_ev.size() < n_ev + 1) {
+                cudaEvent_t e;
+                CUDA_TRY(cudaEventCreate(&e), tk->err);
+                dc.pipe_ev.push_back(e);
+            }
+            return SPL_OK;
+        };
+        if ((rc = reserve())) return fail(rc);
+    }
+
     int launches = 0;
-
     for (int attempt = 0;; ++attempt) {
         launches = 0;
-        // phase 1: copy in, run, copy offsets out -- all devices enqueued before any sync
-        for (size_t g = 0; g < G; ++g) {
-            DevCtx& dc = tk->devs[g];
-            auto run = [&]() -> int {
+        memset(&r->stats, 0, sizeof(r->stats));
+        bool retry = false;
+        int err_code = SPL_OK;
+        uint64_t total = 0;                 // ids of the chunks drained so far
+        size_t next_out = 0;                // chunks are drained in document order
+
+        // copy the ids of chunk c out as soon as its count is known; grows the result buffer on demand
+        auto drain = [&](size_t ci) -> int {
+            Chunk& c = chunks[ci];
+            DevCtx& dc = tk->devs[c.g];
+            const uint32_t errbits = (uint32_t)c.meta[1];
+            if (errbits & SPL_DEVERR_OFFSETS) { tk->err = "invalid document offsets"; return SPL_ERR_INVALID_ARG; }
+            if (errbits & SPL_DEVERR_HUGE_POOL) {
+                dc.huge_words = std::max<size_t>(dc.huge_words * 4, (size_t)(c.meta[1] >> 32) + 1024);
+                retry = true;
+                return SPL_OK;
+            }
+            c.n_tokens = c.meta[0];
+            c.tok_base = total;
+            total += c.n_tokens;
+            if (retry) return SPL_OK;
+            if ((total + 16) * 4 > r->ids_buf.cap) {
+                // size the result by the ids-per-byte ratio seen so far (+12 %), at least what is needed now
+                const uint64_t done_bytes = std::max<uint64_t>(c.b1, 1);
+                uint64_t est = (uint64_t)((double)total / (double)done_bytes * (double)N * 1.125) + 4096;
+                est = std::min<uint64_t>(std::max<uint64_t>(est, total + 16), N + 16);
+                PinnedBuf nb = take_pinned(tk, est * 4);
+                if (!nb.p) { tk->err = "pinned host allocation failed"; return SPL_ERR_OOM; }
+                if (r->ids_buf.p) {
+                    for (auto& d2 : tk->devs) { cudaSetDevice(d2.device); cudaStreamSynchronize(d2.s_out); }
+                    memcpy(nb.p, r->ids_buf.p, (size_t)c.tok_base * 4);
+                    give_pinned(tk, r->ids_buf);
+                }
+                r->ids_buf = nb;
+            }
+            CUDA_TRY(cudaSetDevice(dc.device), tk->err);
+            if (c.n_tokens)
+                CUDA_TRY(cudaMemcpyAsync((uint32_t*)r->ids_buf.p + c.tok_base, (uint32_t*)dc.ids.p + c.ids_off, c.n_tokens * 4,
+                                         cudaMemcpyDeviceToHost, dc.s_out), tk->err);
+            r->stats.d2h_bytes += c.n_tokens * 4;
+            if (tk->trace) cudaEventRecord(dc.pipe_ev[c.ev + 3], dc.s_out);
+            if (c.tok_base)
+                for (size_t d = c.d0; d < c.d1; ++d) res_off[d] += c.tok_base;
+            return SPL_OK;
+        };
+
+        for (size_t ci = 0; ci < C && err_code == SPL_OK; ++ci) {
+            Chunk& c = chunks[ci];
+            DevCtx& dc = tk->devs[c.g];
+            auto enqueue = [&]() -> int {
                 CUDA_TRY(cudaSetDevice(dc.device), tk->err);
-                const size_t nd = dlo[g + 1] - dlo[g];
-                const uint64_t b0 = offsets[dlo[g]], b1 = offsets[dlo[g + 1]], nb = b1 - b0;
-                SplWork& w = works[g];
+                const size_t nd = c.d1 - c.d0, g = (size_t)c.g;
+                const uint64_t nb = c.b1 - c.b0;
+                const bool first = c.d0 == dlo[g], last = c.d1 == dlo[g + 1];
+                cudaEvent_t ev_in = dc.pipe_ev[c.ev], ev_k0 = dc.pipe_ev[c.ev + 1], ev_done = dc.pipe_ev[c.ev + 2];
+                if (first) CUDA_TRY(cudaEventRecord(dc.ev[0], dc.s_in), tk->err);
+                // stage in: text to its aligned slot, document offsets (the boundary entry belongs to the earlier chunk)
+                uint8_t* d_text = (uint8_t*)dc.text.p + c.text_off;
+                uint64_t* d_doc = (uint64_t*)dc.doc_off.p + (c.d0 - dlo[g]);
+                if (nb) CUDA_TRY(cudaMemcpyAsync(d_text, bytes + c.b0, nb, cudaMemcpyHostToDevice, dc.s_in), tk->err);
+                const size_t skip = first ? 0 : 1;
+                CUDA_TRY(cudaMemcpyAsync(d_doc + skip, offsets + c.d0 + skip, (nd + 1 - skip) * 8, cudaMemcpyHostToDevice, dc.s_in), tk->err);
+                CUDA_TRY(cudaEventRecord(ev_in, dc.s_in), tk->err);
+                r->stats.h2d_bytes += nb + (nd + 1 - skip) * 8;
+                // kernels
+                CUDA_TRY(cudaStreamWaitEvent(dc.stream, ev_in, 0), tk->err);
+                CUDA_TRY(cudaEventRecord(ev_k0, dc.stream), tk->err);
+                SplWork w;
                 memset(&w, 0, sizeof(w));
                 int rc2;
-                if ((rc2 = dc.text.ensure(nb + 64, tk->err))) return rc2;
-                if ((rc2 = dc.doc_off.ensure((nd + 1) * 8, tk->err))) return rc2;
-                if ((rc2 = dc.ids.ensure((nb + 16) * 4, tk->err))) return rc2;
-                if ((rc2 = dc.out_off.ensure((nd + 1) * 8, tk->err))) return rc2;
-                CUDA_TRY(cudaEventRecord(dc.ev[0], dc.stream), tk->err);
-                if (nb) CUDA_TRY(cudaMemcpyAsync(dc.text.p, bytes + b0, nb, cudaMemcpyHostToDevice, dc.stream), tk->err);
-                CUDA_TRY(cudaMemcpyAsync(dc.doc_off.p, offsets + dlo[g], (nd + 1) * 8, cudaMemcpyHostToDevice, dc.stream), tk->err);
                 if ((rc2 = prepare_work(tk, dc, nb, nd, with_special, dc.stream, w))) return rc2;
-                w.text = (const uint8_t*)dc.text.p;
-                w.doc_off = (const uint64_t*)dc.doc_off.p;
-                w.off_base = b0;
-                w.ids = (uint32_t*)dc.ids.p;
-                w.out_off = (uint64_t*)dc.out_off.p;
-                CUDA_TRY(cudaEventRecord(dc.ev[1], dc.stream), tk->err);
+                w.text = d_text;
+                w.doc_off = d_doc;
+                w.off_base = c.b0;
+                w.ids = (uint32_t*)dc.ids.p + c.ids_off;
+                uint64_t* d_out = (uint64_t*)dc.out_off.p + (c.d0 - dlo[g]);
+                w.out_off = d_out;
                 launches += spl_launch_encode(w, dc.num_sms, dc.stream);
                 CUDA_TRY(cudaGetLastError(), tk->err);
-                CUDA_TRY(cudaEventRecord(dc.ev[2], dc.stream), tk->err);
-                CUDA_TRY(cudaMemcpyAsync(res_off + dlo[g], dc.out_off.p, (nd + (g + 1 == G ? 1 : 0)) * 8, cudaMemcpyDeviceToHost, dc.stream), tk->err);
-                CUDA_TRY(cudaMemcpyAsync(&shard_tokens[g], (uint64_t*)dc.out_off.p + nd, 8, cudaMemcpyDeviceToHost, dc.stream), tk->err);
-                CUDA_TRY(cudaMemcpyAsync(h_counters[g].data(), dc.counters.p, 16, cudaMemcpyDeviceToHost, dc.stream), tk->err);
-                r->stats.h2d_bytes += nb + (nd + 1) * 8;
-                r->stats.d2h_bytes += (nd + 1) * 8 + 8 + 16;
+                // small results on the same stream (the next chunk reuses the workspace and the boundary offset)
+                const size_t n_off = nd + ((last && g + 1 == G) ? 1 : 0);
+                if (n_off) CUDA_TRY(cudaMemcpyAsync(res_off + c.d0, d_out, n_off * 8, cudaMemcpyDeviceToHost, dc.stream), tk->err);
+                CUDA_TRY(cudaMemcpyAsync((void*)c.meta, d_out + nd, 8, cudaMemcpyDeviceToHost, dc.stream), tk->err);
+                CUDA_TRY(cudaMemcpyAsync((void*)(c.meta + 1), (uint8_t*)dc.counters.p + 4, 8, cudaMemcpyDeviceToHost, dc.stream), tk->err);
+                CUDA_TRY(cudaEventRecord(ev_done, dc.stream), tk->err);
+                r->stats.d2h_bytes += n_off * 8 + 16;
                 return SPL_OK;
             };
-            if ((rc = run())) return fail(rc);
+            err_code = enqueue();
+            // drain what has finished, without blocking
+            while (err_code == SPL_OK && next_out <= ci) {
+                Chunk& o = chunks[next_out];
+                cudaSetDevice(tk->devs[o.g].device);
+                cudaError_t q = cudaEventQuery(tk->devs[o.g].pipe_ev[o.ev + 2]);
+                if (q == cudaErrorNotReady) break;
+                if (q != cudaSuccess) { tk->err = std::string("encode kernels: ") + cudaGetErrorString(q); err_code = SPL_ERR_CUDA; break; }
+                err_code = drain(next_out++);
+            }
         }
-        bool retry = false;
+        while (err_code == SPL_OK && next_out < C) {
+            Chunk& o = chunks[next_out];
+            cudaSetDevice(tk->devs[o.g].device);
+            cudaError_t e = cudaEventSynchronize(tk->devs[o.g].pipe_ev[o.ev + 2]);
+            if (e != cudaSuccess) { tk->err = std::string("encode kernels: ") + cudaGetErrorString(e); err_code = SPL_ERR_CUDA; break; }
+            err_code = drain(next_out++);
+        }
+        if (err_code != SPL_OK) return fail(err_code);
+        float kmax = 0, tmax = 0;
         for (size_t g = 0; g < G; ++g) {
             DevCtx& dc = tk->devs[g];
             cudaSetDevice(dc.device);
-            cudaError_t e = cudaStreamSynchronize(dc.stream);
-            if (e != cudaSuccess) { tk->err = std::string("encode kernels: ") + cudaGetErrorString(e); return fail(SPL_ERR_CUDA); }
-            if (h_counters[g][1] & SPL_DEVERR_OFFSETS) { tk->err = "invalid document offsets"; return fail(SPL_ERR_INVALID_ARG); }
-            if (h_counters[g][1] & SPL_DEVERR_HUGE_POOL) {
-                dc.huge_words = std::max<size_t>(dc.huge_words * 4, (size_t)h_counters[g][2] + 1024);
-                retry = true;
+            cudaEventRecord(dc.ev[3], dc.s_out);
+            cudaError_t e = cudaStreamSynchronize(dc.s_out);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(dc.stream);
+            if (e != cudaSuccess) { tk->err = std::string("copy-out: ") + cudaGetErrorString(e); return fail(SPL_ERR_CUDA); }
+            float ksum = 0, t = 0;
+            for (auto& c : chunks)
+                if (c.g == (int)g) { float k = 0; cudaEventElapsedTime(&k, dc.pipe_ev[c.ev + 1], dc.pipe_ev[c.ev + 2]); ksum += k; }
+            cudaEventElapsedTime(&t, dc.ev[0], dc.ev[3]);
+            kmax = std::max(kmax, ksum); tmax = std::max(tmax, t);
+            if (tk->trace && !retry)
+                for (auto& c : chunks)
+                    if (c.g == (int)g) {
+                        float a = 0, b = 0, d = 0, e = 0;
+                        cudaEventElapsedTime(&a, dc.ev[0], dc.pipe_ev[c.ev]);
+                        cudaEventElapsedTime(&b, dc.ev[0], dc.pipe_ev[c.ev + 1]);
+                        cudaEventElapsedTime(&d, dc.ev[0], dc.pipe_ev[c.ev + 2]);
+                        cudaEventElapsedTime(&e, dc.ev[0], dc.pipe_ev[c.ev + 3]);
+                        fprintf(stderr, "[spl trace] dev %zu docs %zu..%zu bytes %llu: in %.3f  k0 %.3f  done %.3f  out %.3f ms\n",
+                                g, c.d0, c.d1, (unsigned long long)(c.b1 - c.b0), a, b, d, e);
+                    }
+        }
+        if (retry) {
+            if (attempt >= 6) { tk->err = "scratch pool for very long pieces exhausted"; return fail(SPL_ERR_OOM); }
+            for (size_t g = 0; g < G; ++g) {
+                cudaSetDevice(tk->devs[g].device);
+                if ((rc = reserve_work(tk, tk->devs[g], max_nb[g], max_nd[g], with_special))) return fail(rc);
             }
+            continue;
         }
-        if (!retry) break;
-        if (attempt >= 6) { tk->err = "scratch pool for very long pieces exhausted"; return fail(SPL_ERR_OOM); }
-        memset(&r->stats, 0, sizeof(r->stats));
-    }
-
-    // phase 2: ids out
-    uint64_t total = 0;
-    std::vector<uint64_t> tok_base(G + 1, 0);
-    for (size_t g = 0; g < G; ++g) { tok_base[g] = total; total += shard_tokens[g]; }
-    tok_base[G] = total;
-    r->ids_buf = take_pinned(tk, (total + 16) * 4);
-    if (!r->ids_buf.p) { tk->err = "pinned host allocation failed"; return fail(SPL_ERR_OOM); }
-    for (size_t g = 0; g < G; ++g) {
-        DevCtx& dc = tk->devs[g];
-        cudaSetDevice(dc.device);
-        if (shard_tokens[g]) {
-            cudaError_t e = cudaMemcpyAsync((uint32_t*)r->ids_buf.p + tok_base[g], dc.ids.p, shard_tokens[g] * 4, cudaMemcpyDeviceToHost, dc.stream);
-            if (e != cudaSuccess) { tk->err = std::string("cudaMemcpyAsync ids: ") + cudaGetErrorString(e); return fail(SPL_ERR_CUDA); }
+        if (!r->ids_buf.p) {
+            r->ids_buf = take_pinned(tk, 64);
+            if (!r->ids_buf.p) { tk->err = "pinned host allocation failed"; return fail(SPL_ERR_OOM); }
         }
-        cudaEventRecord(dc.ev[3], dc.stream);
-        r->stats.d2h_bytes += shard_tokens[g] * 4;
+        res_off[n_docs] = total;
+        r->n_tokens = total;
+        r->stats.n_docs = n_docs; r->stats.n_bytes = N; r->stats.n_tokens = total;
+        r->stats.kernel_ms = kmax; r->stats.total_ms = tmax;
+        r->stats.n_devices = (int)G; r->stats.n_launches = launches;
+        break;
     }
-    float kmax = 0, tmax = 0;
-    for (size_t g = 0; g < G; ++g) {
-        DevCtx& dc = tk->devs[g];
-        cudaSetDevice(dc.device);
-        cudaError_t e = cudaStreamSynchronize(dc.stream);
-        if (e != cudaSuccess) { tk->err = std::string("copy-out: ") + cudaGetErrorString(e); return fail(SPL_ERR_CUDA); }
-        float k = 0, t = 0;
-        cudaEventElapsedTime(&k, dc.ev[1], dc.ev[2]);
-        cudaEventElapsedTime(&t, dc.ev[0], dc.ev[3]);
-        kmax = std::max(kmax, k); tmax = std::max(tmax, t);
-        if (g > 0 && tok_base[g]) {
-            for (size_t d = dlo[g]; d < dlo[g + 1] + (g + 1 == G ? 1 : 0); ++d) res_off[d] += tok_base[g];
-        }
-    }
-    r->n_tokens = total;
-    r->stats.n_docs = n_docs; r->stats.n_bytes = N; r->stats.n_tokens = total;
-    r->stats.kernel_ms = kmax; r->stats.total_ms = tmax;
-    r->stats.n_devices = (int)G; r->stats.n_launches = launches;
+    give_pinned(tk, meta_buf);
     *out = r;
     return SPL_OK;
 }

@@ -210,3 +210,23 @@ def test_custom_vocab_with_unknown_bytes(toks):
     o = OracleTokenizer.from_bytes(vb, CL100K_BASE_PATTERN)
     for s in ["a", "ab", "abc", "ac", "abcabc", "zab", "xyz", " a b", "cab abc", "aXbXc"]:
         assert t.encode(s) == o.encode(s), s
+
+
+def test_pipelined_host_call_many_chunks(toks, monkeypatch):
+    """spl_encode_batch cuts a shard into pipeline chunks (H2D / kernels / D2H overlapped); force tiny chunks so
+    one call runs through dozens of them, with empty and large documents on the chunk boundaries."""
+    from splintr_b200 import Tokenizer
+    monkeypatch.setenv("SPL_CHUNK_BYTES", "20000")
+    t = Tokenizer.from_pretrained("cl100k_base", devices=[0])
+    monkeypatch.delenv("SPL_CHUNK_BYTES")
+    o = c_oracle("cl100k_base")
+    d, off = synth.cfg2(vocab_bytes("cl100k_base"), 3000)
+    _check_packed(t, o, d, off)
+    texts = synth.unpack_texts(d, off)[:400]
+    texts[3] = ""; texts[4] = ""; texts[17] = "x" * 70_000; texts[18] = ""; texts[-1] = ""
+    assert t.encode_batch(texts) == o.encode_batch(texts)
+    assert t.encode_batch(["", ""]) == [[], []]
+    sp = "<|endoftext|>"
+    texts2 = [tx[:50] + sp + tx[50:] for tx in texts[:200]]
+    po = py_oracle("cl100k_base")
+    assert t.encode_batch_with_special(texts2) == [po.encode_with_special(x) for x in texts2]
