@@ -53,7 +53,8 @@ struct DevCtx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     void* table_blob = nullptr;
     SplTables* d_tables = nullptr;
-    DevBuf text, doc_off, hard, spec, pstart, tfd, tstate, counters, huge, ids, out_off, fbl, tcnt, tsoff, stage;
+    DevBuf text, doc_off, ids, out_off;          // spl_encode_batch: the shard's buffers
+    DevBuf zero, tfd, tnp, tstate, pv, pool, mlist, fbl, huge;   // per-pass workspace (zero: everything that starts cleared)
     size_t huge_words = 0;
     SplKernelProfile prof;
     bool prof_ready = false;
@@ -139,7 +140,7 @@ int upload_tables(spl_tokenizer* tk, DevCtx& dc) {
 
 void destroy_ctx(DevCtx& dc) {
     cudaSetDevice(dc.device);
-    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.hard, &dc.spec, &dc.pstart, &dc.tfd, &dc.tstate, &dc.counters, &dc.huge, &dc.ids, &dc.out_off, &dc.fbl, &dc.tcnt, &dc.tsoff, &dc.stage})
+    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.ids, &dc.out_off, &dc.zero, &dc.tfd, &dc.tnp, &dc.tstate, &dc.pv, &dc.pool, &dc.mlist, &dc.fbl, &dc.huge})
         b->release();
     if (dc.table_blob) cudaFree(dc.table_blob);
     for (auto& e : dc.ev) if (e) cudaEventDestroy(e);
@@ -153,24 +154,45 @@ void destroy_ctx(DevCtx& dc) {
 // limits of one device shard: 32-bit positions inside the kernels
 const uint64_t kMaxShardBytes = 0xFFFFFFFFull - 4ull * SPL_WIN;
 
+// layout of the zero-initialised region: counters | tile_extra | hard | pstart | spec
+struct ZeroLayout { size_t words, n_tiles, off_extra, off_hard, off_pstart, off_spec, total; };
+ZeroLayout zero_layout(uint64_t N, bool with_special) {
+    ZeroLayout z;
+    z.words = (size_t)((N + SPL_WIN) / 32 + 16);
+    z.n_tiles = (size_t)(N / SPL_TILE) + 1;
+    z.off_extra = 256;
+    z.off_hard = align_up(z.off_extra + z.n_tiles * 4, 256);
+    z.off_pstart = align_up(z.off_hard + z.words * 4, 256);
+    z.off_spec = align_up(z.off_pstart + z.words * 4, 256);
+    z.total = with_special ? align_up(z.off_spec + z.words * 4, 256) : z.off_spec;
+    return z;
+}
+
+struct MissLayout { uint32_t r0, r1, r2; };
+MissLayout miss_layout(uint64_t N) {
+    MissLayout m;
+    m.r0 = (uint32_t)(N / 2 + 16);                                // thread + warp class: every miss has >= 2 bytes
+    m.r1 = m.r0 + (uint32_t)(N / (SPL_WARP_MAX + 1) + 16);        // big class
+    m.r2 = m.r1 + (uint32_t)(N / (SPL_BIG_MAX + 1) + 16);         // huge class
+    return m;
+}
+
 // Size the internal workspace of `dc` for N bytes / n_docs documents (may reallocate: nothing may be in flight).
 int reserve_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, bool with_special) {
     if (N > kMaxShardBytes || n_docs > 0xFFFFFFF0ull) {
         tk->err = "one device pass is limited to 4 GiB of text";
         return SPL_ERR_UNSUPPORTED;
     }
-    size_t words = (size_t)((N + SPL_WIN) / 32 + 16);
-    uint32_t n_tiles = (uint32_t)(N / SPL_TILE) + 1;
+    const ZeroLayout z = zero_layout(N, with_special);
+    const MissLayout m = miss_layout(N);
     int rc;
-    if ((rc = dc.hard.ensure(words * 4, tk->err))) return rc;
-    if ((rc = dc.pstart.ensure(words * 4, tk->err))) return rc;
-    if (with_special && (rc = dc.spec.ensure(words * 4, tk->err))) return rc;
-    if ((rc = dc.tfd.ensure((size_t)(n_tiles + 2) * 4, tk->err))) return rc;
-    if ((rc = dc.tstate.ensure((size_t)n_tiles * 8, tk->err))) return rc;
-    if ((rc = dc.tcnt.ensure((size_t)n_tiles * 4, tk->err))) return rc;
-    if ((rc = dc.tsoff.ensure((size_t)n_tiles * 8, tk->err))) return rc;
-    if ((rc = dc.stage.ensure((size_t)(N + 64) * 4, tk->err))) return rc;
-    if ((rc = dc.counters.ensure(64, tk->err))) return rc;
+    if ((rc = dc.zero.ensure(z.total, tk->err))) return rc;
+    if ((rc = dc.tfd.ensure((z.n_tiles + 2) * 4, tk->err))) return rc;
+    if ((rc = dc.tnp.ensure(z.n_tiles * 4, tk->err))) return rc;
+    if ((rc = dc.tstate.ensure(z.n_tiles * 8, tk->err))) return rc;
+    if ((rc = dc.pv.ensure(z.n_tiles * SPL_TILE * 4, tk->err))) return rc;
+    if ((rc = dc.pool.ensure((size_t)(N + 64) * 4, tk->err))) return rc;
+    if ((rc = dc.mlist.ensure((size_t)m.r2 * 8, tk->err))) return rc;
     uint32_t n_fast_tiles = (uint32_t)((N + SPL_FAST_PAYLOAD * 32u - 1) / (SPL_FAST_PAYLOAD * 32u));
     if ((rc = dc.fbl.ensure((size_t)(n_fast_tiles + 1) * 4, tk->err))) return rc;
     if (dc.huge_words == 0) dc.huge_words = (size_t)16 << 20;             // 64 MiB of scratch
@@ -179,32 +201,32 @@ int reserve_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
 }
 
 // Prepare the internal workspace of `dc` for N bytes / n_docs documents and fill `w`
-// (text / doc_off / ids / out_off are set by the caller).  Enqueues the zero-fills.
+// (text / doc_off / ids / out_off are set by the caller).  Enqueues the zero-fill.
 int prepare_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, bool with_special,
                  cudaStream_t st, SplWork& w) {
     int rc = reserve_work(tk, dc, N, n_docs, with_special);
     if (rc) return rc;
-    size_t words = (size_t)((N + SPL_WIN) / 32 + 16);
-    uint32_t n_tiles = (uint32_t)(N / SPL_TILE) + 1;
+    const ZeroLayout z = zero_layout(N, with_special);
+    const MissLayout m = miss_layout(N);
     uint32_t n_fast_tiles = (uint32_t)((N + SPL_FAST_PAYLOAD * 32u - 1) / (SPL_FAST_PAYLOAD * 32u));
-    CUDA_TRY(cudaMemsetAsync(dc.hard.p, 0, words * 4, st), tk->err);
-    CUDA_TRY(cudaMemsetAsync(dc.pstart.p, 0, words * 4, st), tk->err);
-    if (with_special) CUDA_TRY(cudaMemsetAsync(dc.spec.p, 0, words * 4, st), tk->err);
-    CUDA_TRY(cudaMemsetAsync(dc.counters.p, 0, 64, st), tk->err);
+    CUDA_TRY(cudaMemsetAsync(dc.zero.p, 0, z.total, st), tk->err);
+    uint8_t* zb = (uint8_t*)dc.zero.p;
     w.N = (uint32_t)N;
     w.n_docs = (uint32_t)n_docs;
-    w.n_tiles = n_tiles;
-    w.hard = (uint32_t*)dc.hard.p;
-    w.spec = with_special ? (uint32_t*)dc.spec.p : nullptr;
-    w.pstart = (uint32_t*)dc.pstart.p;
-    w.bitmap_words = words;
+    w.n_tiles = (uint32_t)z.n_tiles;
+    w.counters = (uint32_t*)zb;
+    w.tile_extra = (int32_t*)(zb + z.off_extra);
+    w.hard = (uint32_t*)(zb + z.off_hard);
+    w.pstart = (uint32_t*)(zb + z.off_pstart);
+    w.spec = with_special ? (uint32_t*)(zb + z.off_spec) : nullptr;
+    w.bitmap_words = z.words;
     w.tile_first_doc = (uint32_t*)dc.tfd.p;
+    w.tile_np = (uint32_t*)dc.tnp.p;
     w.tile_state = (uint64_t*)dc.tstate.p;
-    w.tile_cnt = (uint32_t*)dc.tcnt.p;
-    w.tile_soff = (uint64_t*)dc.tsoff.p;
-    w.stage = (uint32_t*)dc.stage.p;
-    w.stage_bump = (uint64_t*)((uint8_t*)dc.counters.p + 32);
-    w.counters = (uint32_t*)dc.counters.p;
+    w.pv = (uint32_t*)dc.pv.p;
+    w.pool = (uint32_t*)dc.pool.p;
+    w.mlist = (uint64_t*)dc.mlist.p;
+    w.ml_r0 = m.r0; w.ml_r1 = m.r1; w.ml_r2 = m.r2;
     w.fb_list = (uint32_t*)dc.fbl.p;
     w.n_fast_tiles = n_fast_tiles;
     w.huge_pool = (uint32_t*)dc.huge.p;
@@ -331,7 +353,7 @@ int spl_launches_per_call(const spl_tokenizer* tk, uint32_t flags) {
     if (!tk) return 0;
     bool ws = (flags & SPL_ENCODE_WITH_SPECIAL) && !tk->host.sp_id.empty();
     int pre = tk->host.pattern == SPL_PAT_MISTRAL_V3 ? 1 : 2;          // sequential rules | bit-parallel + fallback
-    return 4 + pre + (ws ? 1 : 0);                                     // mark_docs, encode, tile_scan, gather
+    return 5 + pre + (ws ? 1 : 0);                                     // mark_docs, probe, bpe, tile_scan, emit
 }
 
 int spl_set_profiling(spl_tokenizer* tk, int enable) {
@@ -603,7 +625,7 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
                 const size_t n_off = nd + ((last && g + 1 == G) ? 1 : 0);
                 if (n_off) CUDA_TRY(cudaMemcpyAsync(res_off + c.d0, d_out, n_off * 8, cudaMemcpyDeviceToHost, dc.stream), tk->err);
                 CUDA_TRY(cudaMemcpyAsync((void*)c.meta, d_out + nd, 8, cudaMemcpyDeviceToHost, dc.stream), tk->err);
-                CUDA_TRY(cudaMemcpyAsync((void*)(c.meta + 1), (uint8_t*)dc.counters.p + 4, 8, cudaMemcpyDeviceToHost, dc.stream), tk->err);
+                CUDA_TRY(cudaMemcpyAsync((void*)(c.meta + 1), (uint8_t*)dc.zero.p + 4, 8, cudaMemcpyDeviceToHost, dc.stream), tk->err);
                 CUDA_TRY(cudaEventRecord(ev_done, dc.stream), tk->err);
                 r->stats.d2h_bytes += n_off * 8 + 16;
                 return SPL_OK;

@@ -1,0 +1,736 @@
+// Device encode path, second half: piece-start bitmap -> token ids in document order.
+//
+//   k_probe      one thread per piece: whole-piece vocabulary probe (tokenizer.rs:703-705, bpe.rs:73-80); the id of a
+//                hit goes to pv[] in piece order, a miss is appended to the miss list of its length class
+//   k_bpe        the leftmost-min-rank merge loop of bpe.rs:83-194 for every listed piece -- one thread per piece up
+//                to 32 bytes, one warp up to 3968 bytes, one block beyond -- ids to pool[] at the piece's byte position
+//   k_tile_scan  exclusive prefix of the per-tile id counts
+//   k_emit       pv[] + pool[] -> ids in document order (the collect of tokenizer.rs:806 and the Rayon collect of
+//                encode_batch, tokenizer.rs:932-934) and the per-document output offsets
+//
+// No block waits for another block inside a kernel; the miss lists decouple the rare, latency-bound merge loop from
+// the streaming probe so that both run at full occupancy.  Integer / byte work; no tensor cores.
+#include "spl_device.cuh"
+
+// ------------------------------------------------------------------------------------------
+// probes that only this stage uses
+// ------------------------------------------------------------------------------------------
+
+// special-token id of the span tx[0, len) (linear search; special spans are rare)
+__device__ uint32_t special_id_g(const SplTables* T, const uint8_t* __restrict__ tx, uint32_t len) {
+    for (uint32_t k = 0; k < T->n_special; ++k) {
+        uint32_t o = T->sp_off[k];
+        if (T->sp_off[k + 1] - o != len) continue;
+        bool eq = true;
+        for (uint32_t j = 0; j < len; ++j)
+            if (__ldg(tx + j) != T->sp_bytes[o + j]) { eq = false; break; }
+        if (eq) return T->sp_id[k];
+    }
+    return SPL_RANK_NONE;
+}
+
+// whole-piece probe of a 17..128-byte piece by one thread (long-key table, verified against the token bytes)
+__device__ uint32_t lookupL_thread(const SplTables* T, const uint32_t* text, uint32_t s, uint32_t len) {
+    uint64_t sum = 0;
+    for (uint32_t i = 0; i * 8 < len; ++i) {
+        uint64_t wv = sm_load8(text, s + i * 8);
+        uint32_t rem = len - i * 8;
+        if (rem < 8) wv &= (1ull << (8 * rem)) - 1;
+        sum += spl_hashL_word(wv, i);
+    }
+    uint64_t hv = spl_hashL_final(sum, len);
+    uint32_t mask = (1u << T->tl_log2) - 1, h = (uint32_t)(hv >> (64 - T->tl_log2));
+    for (;;) {
+        uint4 v = __ldg(reinterpret_cast<const uint4*>(T->tl + h));     // {hash lo, hash hi, id, len}
+        if (v.w == 0) return SPL_RANK_NONE;
+        if (v.w == len && v.x == (uint32_t)hv && v.y == (uint32_t)(hv >> 32)) {
+            const uint8_t* kb = T->tok_bytes + __ldg(T->tok_off + v.z);
+            bool ok = true;
+            for (uint32_t j = 0; j < len; ++j) ok &= (sm_byte(text, s + j) == __ldg(kb + j));
+            if (ok) return v.z;
+        }
+        h = (h + 1) & mask;
+    }
+}
+
+// the same probe for a piece in global memory, by one warp (pieces longer than the probe halo; only vocabularies with
+// keys beyond 128 bytes get here).  Every lane returns the id or SPL_RANK_NONE.
+__device__ uint32_t lookupL_warp_g(const SplTables* T, const uint8_t* __restrict__ tx, uint32_t len) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint64_t sum = 0;
+    for (uint32_t i = lane; i * 8 < len; i += 32) {
+        uint64_t wv = 0;
+        for (uint32_t b = 0; b < 8 && i * 8 + b < len; ++b) wv |= (uint64_t)__ldg(tx + i * 8 + b) << (8 * b);
+        sum += spl_hashL_word(wv, i);
+    }
+    sum = warp_sum_u64(sum);
+    uint64_t hv = spl_hashL_final(sum, len);
+    uint32_t mask = (1u << T->tl_log2) - 1, h = (uint32_t)(hv >> (64 - T->tl_log2));
+    for (;;) {
+        uint4 v = __ldg(reinterpret_cast<const uint4*>(T->tl + h));
+        if (v.w == 0) return SPL_RANK_NONE;
+        if (v.w == len && v.x == (uint32_t)hv && v.y == (uint32_t)(hv >> 32)) {
+            const uint8_t* kb = T->tok_bytes + __ldg(T->tok_off + v.z);
+            bool ok = true;
+            for (uint32_t j = lane; j < len; j += 32) ok &= (__ldg(tx + j) == __ldg(kb + j));
+            if (__all_sync(FULL, ok)) return v.z;
+        }
+        h = (h + 1) & mask;
+    }
+}
+
+__device__ __forceinline__ uint64_t ml_entry(uint32_t gpos, uint32_t len, uint32_t j) {
+    uint32_t l = len < SPL_ML_LEN_SAT ? len : SPL_ML_LEN_SAT;
+    return (uint64_t)gpos | ((uint64_t)l << 32) | ((uint64_t)j << 52);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_probe: one tile per block
+// ------------------------------------------------------------------------------------------
+#define PB_WORDS (SPL_PROBE_WIN / 32u + 1u)          // piece-start words staged: bits 0 .. SPL_PROBE_WIN + 31
+#define PB_BITS  (PB_WORDS * 32u)
+
+struct ProbeSmem {
+    uint32_t text[SPL_PROBE_WIN / 4 + 4];     // staged bytes (+ slack for the unaligned 8-byte key loads)
+    uint32_t pb[PB_WORDS];                    // piece-start bits
+    uint32_t byte_sym[256];
+    uint16_t plist[SPL_TILE + 2];             // window positions of the tile's piece starts, in order (+ end of the last piece)
+    uint16_t mloc[SPL_TILE];                  // missed pieces: thread class from the bottom, warp class from the top
+    uint32_t wtot[SPL_THREADS / 32];
+    uint32_t n_short, n_warp, g_short, g_warp;
+    uint32_t last_end;                        // window position of the end of the tile's last piece
+};
+
+__global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
+    __shared__ ProbeSmem sm;
+    const SplTables* T = w.T;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t N = w.N, Nup = (N + 15u) & ~15u;
+    const uint32_t tile = blockIdx.x, tile0 = tile * SPL_TILE;
+
+    // ---- stage the window -----------------------------------------------------------
+    for (uint32_t v = tid; v < SPL_PROBE_WIN / 16 + 1; v += SPL_THREADS) {
+        uint32_t g = tile0 + v * 16;
+        uint4 x = make_uint4(0, 0, 0, 0);
+        if (g < Nup) x = __ldg(reinterpret_cast<const uint4*>(w.text + g));
+        reinterpret_cast<uint4*>(sm.text)[v] = x;
+    }
+    for (uint32_t v = tid; v < PB_WORDS; v += SPL_THREADS) sm.pb[v] = __ldg(w.pstart + (tile0 >> 5) + v);
+    sm.byte_sym[tid] = T->byte_sym[tid];
+    if (tid == 0) { sm.n_short = 0; sm.n_warp = 0; }
+    __syncthreads();
+
+    // ---- piece list: positions of the piece starts of this tile, in order ------------------
+    const uint32_t avail = N - tile0;                          // text bytes from tile0 on
+    uint32_t my = (sm.pb[tid >> 1] >> ((tid & 1u) * 16u)) & 0xFFFFu;
+    if (tid * 16u + 16u > avail) my &= (tid * 16u >= avail) ? 0u : ((1u << (avail - tid * 16u)) - 1u);   // sentinel bit at N
+    uint32_t cnt = __popc(my), incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+    }
+    if (lane == 31) sm.wtot[warp] = incl;
+    __syncthreads();
+    uint32_t base = incl - cnt, P = 0;
+#pragma unroll
+    for (uint32_t q = 0; q < SPL_THREADS / 32; ++q) {
+        uint32_t t = sm.wtot[q];
+        base += (q < warp) ? t : 0u;
+        P += t;
+    }
+    while (my) {
+        uint32_t b = __ffs(my) - 1;
+        my &= my - 1;
+        sm.plist[base++] = (uint16_t)(tid * 16u + b);
+    }
+    if (tid == 0) {
+        uint32_t e = sm_next_bit(sm.pb, SPL_TILE < avail ? SPL_TILE : avail, PB_BITS);
+        if (P && e >= PB_BITS) e = g_next_bit(w.pstart, tile0 + PB_BITS, N + 1) - tile0;    // the last piece leaves the staged bits
+        sm.last_end = e;
+        sm.plist[P] = (uint16_t)(e >= PB_BITS ? 0xFFFFu : e);      // 0xFFFF: see last_end
+        w.tile_np[tile] = P;
+    }
+    __syncthreads();
+
+    // ---- one thread per piece -------------------------------------------------------------
+    const uint32_t pvbase = tile * SPL_TILE;
+    for (uint32_t j0 = 0; j0 < P; j0 += SPL_THREADS) {
+        const uint32_t j = j0 + tid;
+        const bool valid = j < P;
+        uint32_t val = SPL_PV_NONE;
+        uint32_t cls = 0;                                      // 0 resolved, 1 thread class, 2 warp class, 3 big, 4 huge
+        uint32_t s = 0, len = 0;
+        if (valid) {
+            s = sm.plist[j];
+            uint32_t e = sm.plist[j + 1];
+            if (e == 0xFFFFu) e = sm.last_end;
+            len = e - s;
+            const uint32_t gpos = tile0 + s;
+            if (w.with_special && ((__ldg(w.spec + (gpos >> 5)) >> (gpos & 31)) & 1u)) {
+                val = special_id_g(T, w.text + gpos, len);
+            } else if (len == 1) {
+                uint32_t sy = sm.byte_sym[sm_byte(sm.text, s)];
+                val = sy < SPL_UNK_BASE ? sy : SPL_PV_NONE;   // unknown byte: no id (bpe.rs:73-75)
+            } else {
+                uint32_t id = SPL_RANK_NONE;
+                if (len <= 8) {
+                    uint64_t k0 = sm_load8(sm.text, s);
+                    if (len < 8) k0 &= (1ull << (8 * len)) - 1;
+                    id = lookup8(T->t8, T->t8_log2, k0, len);
+                } else if (len <= 16) {
+                    uint64_t k0 = sm_load8(sm.text, s), k1 = sm_load8(sm.text, s + 8);
+                    if (len < 16) k1 &= (1ull << (8 * (len - 8))) - 1;
+                    id = lookup16(T->t16, T->t16_log2, k0, k1, len);
+                } else if (len <= SPL_PROBE_HALO && len <= T->max_key_len) {
+                    id = lookupL_thread(T, sm.text, s, len);
+                }
+                if (id != SPL_RANK_NONE) val = id;
+                else cls = len <= SPL_SHORT_MAX ? 1u : len <= SPL_WARP_MAX ? 2u : len <= SPL_BIG_MAX ? 3u : 4u;
+            }
+            if (cls == 0) {
+                w.pv[pvbase + j] = val;
+                if (val == SPL_PV_NONE) atomicAdd(&w.tile_extra[tile], -1);
+            } else if (cls >= 3) {                             // rare: straight to the global list of its class
+                uint32_t midx = cls == 3 ? w.ml_r0 + atomicAdd(&w.counters[SPL_CTR_BIG], 1u)
+                                         : w.ml_r1 + atomicAdd(&w.counters[SPL_CTR_HUGE], 1u);
+                w.mlist[midx] = ml_entry(gpos, len, j);
+                w.pv[pvbase + j] = SPL_PV_MISS | midx;
+            }
+        }
+        // thread / warp class: collected per tile, warp-aggregated
+        {
+            uint32_t bal = __ballot_sync(FULL, cls == 1);
+            if (bal) {
+                uint32_t leader = __ffs(bal) - 1, b0 = 0;
+                if (lane == leader) b0 = atomicAdd(&sm.n_short, (uint32_t)__popc(bal));
+                b0 = __shfl_sync(FULL, b0, leader);
+                if (cls == 1) sm.mloc[b0 + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)j;
+            }
+            bal = __ballot_sync(FULL, cls == 2);
+            if (bal) {
+                uint32_t leader = __ffs(bal) - 1, b0 = 0;
+                if (lane == leader) b0 = atomicAdd(&sm.n_warp, (uint32_t)__popc(bal));
+                b0 = __shfl_sync(FULL, b0, leader);
+                if (cls == 2) sm.mloc[SPL_TILE - 1 - (b0 + __popc(bal & ((1u << lane) - 1u)))] = (uint16_t)j;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- publish the tile's misses ------------------------------------------------------------
+    const uint32_t ns = sm.n_short, nw = sm.n_warp;
+    if (ns | nw) {
+        if (tid == 0) {
+            if (ns) sm.g_short = atomicAdd(&w.counters[SPL_CTR_SHORT], ns);
+            if (nw) sm.g_warp = atomicAdd(&w.counters[SPL_CTR_WARP], nw);
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < ns; i += SPL_THREADS) {
+            uint32_t j = sm.mloc[i], s = sm.plist[j], e = sm.plist[j + 1], midx = sm.g_short + i;
+            if (e == 0xFFFFu) e = sm.last_end;
+            w.mlist[midx] = ml_entry(tile0 + s, e - s, j);
+            w.pv[pvbase + j] = SPL_PV_MISS | midx;
+        }
+        for (uint32_t i = tid; i < nw; i += SPL_THREADS) {
+            uint32_t j = sm.mloc[SPL_TILE - 1 - i], s = sm.plist[j], e = sm.plist[j + 1], midx = w.ml_r0 - 1 - (sm.g_warp + i);
+            if (e == 0xFFFFu) e = sm.last_end;
+            w.mlist[midx] = ml_entry(tile0 + s, e - s, j);
+            w.pv[pvbase + j] = SPL_PV_MISS | midx;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_bpe: the merge loop (bpe.rs:83-194) for the listed pieces
+// ------------------------------------------------------------------------------------------
+struct BpeWarpSmem {
+    uint32_t sym[SPL_WARP_MAX];
+    uint32_t rnk[SPL_WARP_MAX];
+    uint32_t tb[SPL_WARP_MAX / 32 + 1];
+};
+struct BpeBigSmem {
+    uint32_t sym[SPL_BIG_MAX];
+    uint32_t rnk[SPL_BIG_MAX];
+    uint32_t tb[SPL_BIG_MAX / 32 + 1];
+};
+union BpeSmem {
+    struct { uint32_t sym[SPL_SHORT_MAX][SPL_BPE_THREADS]; uint32_t rnk[SPL_SHORT_MAX][SPL_BPE_THREADS]; } th;
+    BpeWarpSmem wp[SPL_BPE_THREADS / 32];
+    BpeBigSmem big;
+    uint64_t red[SPL_BPE_THREADS];
+};
+
+__device__ __forceinline__ void bpe_finish(const SplWork& w, uint64_t* slot, uint32_t gpos, uint32_t cnt) {
+    *slot = (uint64_t)gpos | ((uint64_t)cnt << 32);
+    if (cnt != 1u) atomicAdd(&w.tile_extra[gpos / SPL_TILE], (int32_t)cnt - 1);
+}
+
+// One THREAD merges the piece tx[0, n), 2 <= n <= 32: parts are the set bits of `live` (bit i = a part starts at byte
+// i), their symbols in S(i), the rank of (part, next part) in R(i).  32 pieces merge side by side in a warp, so the
+// probe latency of the re-ranks overlaps across pieces.  Returns the id count; ids go to out[0 ..].
+__device__ uint32_t bpe_piece_thread(BpeSmem& sm, const SplTables* T, const uint8_t* __restrict__ tx, uint32_t n, uint32_t* __restrict__ out) {
+    const uint64_t* __restrict__ ptab = T->pair;
+    const uint32_t plog = T->pair_log2;
+    const uint32_t t = threadIdx.x;
+#define S(i) sm.th.sym[(i)][t]
+#define R(i) sm.th.rnk[(i)][t]
+    for (uint32_t i = 0; i < n; ++i) S(i) = T->byte_sym[__ldg(tx + i)];
+    for (uint32_t i = 0; i + 1 < n; i += 2) {
+        uint32_t ra, rb;
+        bool vb = i + 2 < n;
+        pair_lookup2(ptab, plog, true, S(i), S(i + 1), vb, vb ? S(i + 1) : 0u, vb ? S(i + 2) : 0u, ra, rb);
+        R(i) = ra;
+        if (vb) R(i + 1) = rb;
+    }
+    R(n - 1) = SPL_RANK_NONE;
+    uint32_t live = n >= 32u ? 0xFFFFFFFFu : ((1u << n) - 1u);
+    for (;;) {
+        uint32_t best = SPL_RANK_NONE, bpos = 0;
+        for (uint32_t m = live; m; m &= m - 1) {
+            uint32_t i = __ffs(m) - 1;
+            uint32_t r = R(i);
+            if (r < best) { best = r; bpos = i; }                 // strict <: leftmost minimum (bpe.rs:133)
+        }
+        if (best == SPL_RANK_NONE) break;
+        uint32_t above = bpos >= 31u ? 0u : (live & ~((2u << bpos) - 1u));
+        uint32_t nx = __ffs(above) - 1;                            // the absorbed part (exists: its pair has a rank)
+        uint32_t above2 = above & (above - 1);
+        uint32_t below = live & ((1u << bpos) - 1u);
+        bool has_nn = above2 != 0, has_pv = below != 0;
+        uint32_t nn = has_nn ? __ffs(above2) - 1 : 0u, pv = has_pv ? 31u - __clz(below) : 0u;
+        live &= ~(1u << nx);
+        S(bpos) = best;                                            // merged id == its rank
+        uint32_t r1, r0;
+        pair_lookup2(ptab, plog, has_nn, best, has_nn ? S(nn) : 0u, has_pv, has_pv ? S(pv) : 0u, best, r1, r0);
+        R(bpos) = r1;
+        if (has_pv) R(pv) = r0;
+    }
+    uint32_t c = 0;
+    for (uint32_t m = live; m; m &= m - 1) {
+        uint32_t sy = S(__ffs(m) - 1);
+        if (sy < SPL_UNK_BASE) out[c++] = sy;                      // bytes that are not in the vocabulary produce no id (bpe.rs:187-191)
+    }
+#undef S
+#undef R
+    return c;
+}
+
+// One WARP merges the piece tx[0, len): parts are delimited by the bits of tb, sym holds each part's symbol at its
+// first byte, rnk the rank of (part, next part).  Returns (to every lane) the id count; ids go to out[0 ..].
+__device__ uint32_t bpe_piece_warp(uint32_t* sym, uint32_t* rnk, uint32_t* tb, const SplTables* T,
+                                   const uint8_t* __restrict__ tx, uint32_t len, uint32_t* __restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t nwords = (len + 31u) >> 5;
+    if (len > SPL_PROBE_HALO && len <= T->max_key_len) {           // k_probe has already tried the shorter ones
+        uint32_t id = lookupL_warp_g(T, tx, len);
+        if (id != SPL_RANK_NONE) {
+            if (lane == 0) out[0] = id;
+            return 1u;
+        }
+    }
+    for (uint32_t j = lane; j < len; j += 32) sym[j] = T->byte_sym[__ldg(tx + j)];
+    for (uint32_t v = lane; v <= nwords; v += 32) {
+        uint32_t lo = v * 32u;
+        tb[v] = lo + 32u <= len ? FULL : (lo < len ? ((1u << (len - lo)) - 1u) : 0u);
+    }
+    __syncwarp();
+    for (uint32_t j = lane; j < len; j += 32)
+        rnk[j] = (j + 1 < len) ? pair_lookup(T->pair, T->pair_log2, sym[j], sym[j + 1]) : SPL_RANK_NONE;
+    __syncwarp();
+    for (;;) {
+        uint32_t best = SPL_RANK_NONE, bpos = SPL_RANK_NONE;
+        for (uint32_t j = lane; j < len; j += 32) {
+            uint32_t r = rnk[j];
+            if (r < best) { best = r; bpos = j; }
+        }
+        uint32_t m = __reduce_min_sync(FULL, best);
+        if (m == SPL_RANK_NONE) break;
+        uint32_t pos = __reduce_min_sync(FULL, best == m ? bpos : SPL_RANK_NONE);   // leftmost minimum (bpe.rs:133)
+        uint32_t j = sm_next_bit(tb, pos + 1, len);            // the part being absorbed
+        uint32_t k = sm_next_bit(tb, j + 1, len);              // its right neighbour (len if none)
+        uint32_t h = sm_prev_bit(tb, pos, 0);                  // left neighbour (NONE if none)
+        uint32_t symk = k < len ? sym[k] : 0u;
+        uint32_t symh = h != SPL_RANK_NONE ? sym[h] : 0u;
+        __syncwarp();
+        if (lane == 0) {
+            sym[pos] = m;                                      // merged id == its rank
+            rnk[j] = SPL_RANK_NONE;
+            tb[j >> 5] &= ~(1u << (j & 31));
+            rnk[pos] = k < len ? pair_lookup(T->pair, T->pair_log2, m, symk) : SPL_RANK_NONE;
+        } else if (lane == 1 && h != SPL_RANK_NONE) {
+            rnk[h] = pair_lookup(T->pair, T->pair_log2, symh, m);
+        }
+        __syncwarp();
+    }
+    // surviving known parts, in order
+    uint32_t run = 0;
+    for (uint32_t w0 = 0; w0 < nwords; w0 += 32) {
+        uint32_t wi = w0 + lane;
+        uint32_t bits = wi < nwords ? tb[wi] : 0u, keep = 0;
+        for (uint32_t mm = bits; mm; mm &= mm - 1) {
+            uint32_t b = __ffs(mm) - 1;
+            if (sym[wi * 32u + b] < SPL_UNK_BASE) keep |= 1u << b;     // unknown bytes produce no id (bpe.rs:187-191)
+        }
+        uint32_t c = __popc(keep), incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= (uint32_t)o) incl += t;
+        }
+        uint32_t o = run + incl - c;
+        for (uint32_t mm = keep; mm; mm &= mm - 1) out[o++] = sym[wi * 32u + __ffs(mm) - 1];
+        run += __shfl_sync(FULL, incl, 31);
+    }
+    return run;
+}
+
+// The whole block merges one piece that does not fit shared memory: text bytes tx[0, len) in global memory; the
+// sym / rnk / next / prev arrays live in the scratch pool.  Returns (to every thread) the number of ids, written in
+// order to out[0 ..].
+__device__ uint32_t bpe_piece_block(BpeSmem& sm, uint32_t* s_bcast, const SplTables* T, const uint8_t* __restrict__ tx, uint32_t len,
+                                    uint32_t* scratch, uint32_t* __restrict__ out) {
+    const uint32_t tid = threadIdx.x;
+    uint32_t* sym = scratch;
+    uint32_t* rnk = scratch + len;
+    uint32_t* nxt = scratch + 2 * (size_t)len;
+    uint32_t* prv = scratch + 3 * (size_t)len;
+
+    if (len <= T->max_key_len) {                     // only for vocabularies with very long keys
+        if (tid < 32) {
+            uint32_t id = lookupL_warp_g(T, tx, len);
+            if (tid == 0) *s_bcast = id;
+        }
+        __syncthreads();
+        uint32_t found = *s_bcast;
+        __syncthreads();
+        if (found != SPL_RANK_NONE) {
+            if (tid == 0) out[0] = found;
+            return 1u;
+        }
+    }
+    for (uint32_t j = tid; j < len; j += SPL_BPE_THREADS) {
+        sym[j] = T->byte_sym[__ldg(tx + j)];
+        nxt[j] = j + 1;                              // len == "no next"
+        prv[j] = j ? j - 1 : SPL_RANK_NONE;
+    }
+    __syncthreads();
+    for (uint32_t j = tid; j < len; j += SPL_BPE_THREADS)
+        rnk[j] = (j + 1 < len) ? pair_lookup(T->pair, T->pair_log2, sym[j], sym[j + 1]) : SPL_RANK_NONE;
+    __syncthreads();
+    for (;;) {
+        uint64_t best = ~0ull;                       // (rank << 32) | position : min = leftmost minimum
+        for (uint32_t j = tid; j < len; j += SPL_BPE_THREADS) {
+            uint64_t v = ((uint64_t)rnk[j] << 32) | j;
+            if (v < best) best = v;
+        }
+        sm.red[tid] = best;
+        __syncthreads();
+        for (uint32_t o = SPL_BPE_THREADS / 2; o; o >>= 1) {
+            if (tid < o && sm.red[tid + o] < sm.red[tid]) sm.red[tid] = sm.red[tid + o];
+            __syncthreads();
+        }
+        uint64_t mn = sm.red[0];
+        __syncthreads();
+        uint32_t m = (uint32_t)(mn >> 32), pos = (uint32_t)mn;
+        if (m == SPL_RANK_NONE) break;
+        if (tid == 0) {
+            uint32_t j = nxt[pos], k = nxt[j], h = prv[pos];
+            sym[pos] = m; sym[j] = SPL_RANK_NONE; rnk[j] = SPL_RANK_NONE;
+            nxt[pos] = k;
+            if (k < len) prv[k] = pos;
+            rnk[pos] = k < len ? pair_lookup(T->pair, T->pair_log2, m, sym[k]) : SPL_RANK_NONE;
+            if (h != SPL_RANK_NONE) rnk[h] = pair_lookup(T->pair, T->pair_log2, sym[h], m);
+        }
+        __syncthreads();
+    }
+    // ordered compaction of the surviving known symbols (unknown single bytes are dropped)
+    const uint32_t per = (len + SPL_BPE_THREADS - 1) / SPL_BPE_THREADS;
+    const uint32_t lo = tid * per < len ? tid * per : len, hi = lo + per < len ? lo + per : len;
+    uint32_t c = 0;
+    for (uint32_t j = lo; j < hi; ++j) { uint32_t sv = sym[j]; c += (sv != SPL_RANK_NONE && sv < SPL_UNK_BASE); }
+    sm.red[tid] = c;
+    __syncthreads();
+    if (tid == 0) { uint64_t run = 0; for (int q = 0; q < SPL_BPE_THREADS; ++q) { uint64_t t = sm.red[q]; sm.red[q] = run; run += t; } *s_bcast = (uint32_t)run; }
+    __syncthreads();
+    uint32_t o = (uint32_t)sm.red[tid];
+    for (uint32_t j = lo; j < hi; ++j) { uint32_t sv = sym[j]; if (sv != SPL_RANK_NONE && sv < SPL_UNK_BASE) out[o++] = sv; }
+    uint32_t total = *s_bcast;
+    __syncthreads();
+    return total;
+}
+
+__global__ void __launch_bounds__(SPL_BPE_THREADS) k_bpe(SplWork w) {
+    __shared__ BpeSmem sm;
+    __shared__ uint32_t s_bcast, s_off;
+    const SplTables* T = w.T;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+
+    // ---- thread class ------------------------------------------------------------------------
+    {
+        const uint32_t n = w.counters[SPL_CTR_SHORT];
+        for (uint32_t i = blockIdx.x * SPL_BPE_THREADS + tid; i < n; i += gridDim.x * SPL_BPE_THREADS) {
+            uint64_t e = w.mlist[i];
+            uint32_t gpos = (uint32_t)e, len = (uint32_t)(e >> 32) & SPL_ML_LEN_SAT;
+            uint32_t c = bpe_piece_thread(sm, T, w.text + gpos, len, w.pool + gpos);
+            bpe_finish(w, &w.mlist[i], gpos, c);
+        }
+    }
+    // ---- warp class --------------------------------------------------------------------------
+    {
+        const uint32_t n = w.counters[SPL_CTR_WARP];
+        if (n) {
+            __syncthreads();
+            BpeWarpSmem& ws = sm.wp[warp];
+            for (uint32_t i = blockIdx.x * (SPL_BPE_THREADS / 32) + warp; i < n; i += gridDim.x * (SPL_BPE_THREADS / 32)) {
+                uint64_t* slot = &w.mlist[w.ml_r0 - 1 - i];
+                uint64_t e = *slot;
+                uint32_t gpos = (uint32_t)e, len = (uint32_t)(e >> 32) & SPL_ML_LEN_SAT;
+                uint32_t c = bpe_piece_warp(ws.sym, ws.rnk, ws.tb, T, w.text + gpos, len, w.pool + gpos);
+                if (lane == 0) bpe_finish(w, slot, gpos, c);
+                __syncwarp();
+            }
+        }
+    }
+    // ---- big class: warp 0 with the whole block's shared memory ---------------------------------------
+    {
+        const uint32_t n = w.counters[SPL_CTR_BIG];
+        if (n) {
+            __syncthreads();
+            if (warp == 0)
+                for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+                    uint64_t* slot = &w.mlist[w.ml_r0 + i];
+                    uint64_t e = *slot;
+                    uint32_t gpos = (uint32_t)e, len = (uint32_t)(e >> 32) & SPL_ML_LEN_SAT;
+                    uint32_t c = bpe_piece_warp(sm.big.sym, sm.big.rnk, sm.big.tb, T, w.text + gpos, len, w.pool + gpos);
+                    if (lane == 0) bpe_finish(w, slot, gpos, c);
+                    __syncwarp();
+                }
+        }
+    }
+    // ---- huge class: whole block, global scratch ----------------------------------------------------
+    {
+        const uint32_t n = w.counters[SPL_CTR_HUGE];
+        if (n) {
+            __syncthreads();
+            for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+                uint64_t* slot = &w.mlist[w.ml_r1 + i];
+                uint64_t e = *slot;
+                uint32_t gpos = (uint32_t)e;
+                if (tid == 0) {
+                    uint32_t ge = g_next_bit(w.pstart, gpos + 1, w.N + 1);
+                    uint32_t need = 4u * (ge - gpos);
+                    uint32_t off = atomicAdd(&w.counters[SPL_CTR_HUGE_POOL], need);
+                    if ((uint64_t)off + need > w.huge_pool_words) { atomicOr(&w.counters[SPL_CTR_ERR], SPL_DEVERR_HUGE_POOL); off = SPL_RANK_NONE; }
+                    s_off = off; s_bcast = ge - gpos;
+                }
+                __syncthreads();
+                const uint32_t off = s_off, len = s_bcast;
+                __syncthreads();
+                uint32_t c = 0;
+                if (off != SPL_RANK_NONE) c = bpe_piece_block(sm, &s_bcast, T, w.text + gpos, len, w.huge_pool + off, w.pool + gpos);
+                if (tid == 0) bpe_finish(w, slot, gpos, c);
+                __syncthreads();
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_tile_scan: exclusive prefix of the per-tile id counts (one block; tiles are few: N / 4096)
+// ------------------------------------------------------------------------------------------
+#define TS_PER 8u                                    // tiles per thread and round
+__global__ void __launch_bounds__(1024) k_tile_scan(SplWork w) {
+    __shared__ uint32_t s_cnt[1024 * TS_PER];
+    __shared__ uint64_t s_w[32];
+    __shared__ uint64_t s_carry;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    for (uint32_t c0 = 0; c0 < w.n_tiles; c0 += 1024 * TS_PER) {
+        // coalesced, independent loads; then every thread owns TS_PER consecutive tiles
+#pragma unroll
+        for (uint32_t q = 0; q < TS_PER; ++q) {
+            uint32_t i = c0 + q * 1024 + tid;
+            s_cnt[q * 1024 + tid] = i < w.n_tiles ? (uint32_t)((int32_t)w.tile_np[i] + w.tile_extra[i]) : 0u;
+        }
+        __syncthreads();
+        uint32_t loc[TS_PER];
+        uint64_t v = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < TS_PER; ++q) { loc[q] = s_cnt[tid * TS_PER + q]; v += loc[q]; }
+        uint64_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t a = __shfl_up_sync(FULL, (uint32_t)incl, o), b = __shfl_up_sync(FULL, (uint32_t)(incl >> 32), o);
+            if (lane >= (uint32_t)o) incl += (uint64_t)a | ((uint64_t)b << 32);
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint64_t x = s_w[lane], xi = x;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t a = __shfl_up_sync(FULL, (uint32_t)xi, o), b = __shfl_up_sync(FULL, (uint32_t)(xi >> 32), o);
+                if (lane >= (uint32_t)o) xi += (uint64_t)a | ((uint64_t)b << 32);
+            }
+            s_w[lane] = xi - x;
+        }
+        __syncthreads();
+        uint64_t run = s_carry + s_w[warp] + incl - v;
+#pragma unroll
+        for (uint32_t q = 0; q < TS_PER; ++q) {
+            uint32_t i = c0 + tid * TS_PER + q;
+            if (i < w.n_tiles) w.tile_state[i] = run;
+            run += loc[q];
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = run;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_emit: one tile per block: pv[] (+ pool[] for merged pieces) -> ids in document order, output offsets
+// ------------------------------------------------------------------------------------------
+#define EM_ITERS (SPL_TILE / SPL_THREADS)            // 16 pieces per thread at most
+#define EM_WARPS (SPL_THREADS / 32)
+#define EM_INLINE 8u                                 // ids of a merged piece copied by its own thread up to this many
+#define EM_BIGCAP (SPL_TILE / (EM_INLINE + 1u) + 1u) // pieces of a tile that can have more ids than that
+
+struct EmitSmem {
+    uint32_t spos[SPL_TILE + 1];                     // ids of the tile before piece j
+    uint32_t pbw[SPL_TILE / 32];
+    uint32_t wpre[SPL_TILE / 32];
+    uint32_t wtot[EM_ITERS * EM_WARPS];
+    uint32_t bigpos[EM_BIGCAP], biggp[EM_BIGCAP], bigcnt[EM_BIGCAP];
+    uint32_t n_big;
+};
+
+__global__ void __launch_bounds__(SPL_THREADS) k_emit(SplWork w) {
+    __shared__ EmitSmem sm;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t tile = blockIdx.x, tile0 = tile * SPL_TILE;
+    const uint32_t P = w.tile_np[tile];
+    const uint64_t prefix = w.tile_state[tile];
+    const uint32_t* __restrict__ pv = w.pv + tile0;
+    uint32_t* __restrict__ out = w.ids + prefix;
+    const uint32_t d0 = __ldg(w.tile_first_doc + tile), d1 = __ldg(w.tile_first_doc + tile + 1);
+
+    if (tid == 0) sm.n_big = 0;
+    if (d1 > d0 && tid < SPL_TILE / 32) sm.pbw[tid] = __ldg(w.pstart + (tile0 >> 5) + tid);
+
+    // ---- pass 1: id count of every piece, warp-level prefixes ---------------------------------------
+    const uint32_t iters = (P + SPL_THREADS - 1) / SPL_THREADS;
+    for (uint32_t k = 0; k < iters; ++k) {
+        const uint32_t j = k * SPL_THREADS + tid;
+        uint32_t c = 0;
+        if (j < P) {
+            uint32_t v = __ldg(pv + j);
+            c = v < SPL_PV_MISS ? 1u : (v == SPL_PV_NONE ? 0u : (uint32_t)(w.mlist[v & ~SPL_PV_MISS] >> 32));
+        }
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= (uint32_t)o) incl += t;
+        }
+        if (j < P) sm.spos[j] = incl - c;
+        if (lane == 31) sm.wtot[k * EM_WARPS + warp] = incl;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // exclusive scan of the iters * EM_WARPS (<= 128) warp totals, four per lane; word prefixes of the piece bits
+        uint32_t loc[4], run = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t idx = lane * 4 + q;
+            loc[q] = idx < iters * EM_WARPS ? sm.wtot[idx] : 0u;
+            run += loc[q];
+        }
+        uint32_t incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= (uint32_t)o) incl += t;
+        }
+        uint32_t b = incl - run;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t idx = lane * 4 + q;
+            if (idx < iters * EM_WARPS) sm.wtot[idx] = b;
+            b += loc[q];
+        }
+        if (lane == 31) sm.spos[P] = incl;                     // ids of the whole tile
+        if (d1 > d0) {
+            run = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { loc[q] = __popc(sm.pbw[lane * 4 + q]); run += loc[q]; }
+            incl = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= (uint32_t)o) incl += t;
+            }
+            b = incl - run;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { sm.wpre[lane * 4 + q] = b; b += loc[q]; }
+        }
+    }
+    __syncthreads();
+
+    // ---- pass 2: ids to their place ----------------------------------------------------------------------
+    for (uint32_t k = 0; k < iters; ++k) {
+        const uint32_t j = k * SPL_THREADS + tid;
+        if (j < P) {
+            const uint32_t pos = sm.spos[j] + sm.wtot[k * EM_WARPS + warp];
+            sm.spos[j] = pos;
+            const uint32_t v = __ldg(pv + j);
+            if (v < SPL_PV_MISS) out[pos] = v;
+            else if (v != SPL_PV_NONE) {
+                const uint64_t e = w.mlist[v & ~SPL_PV_MISS];
+                const uint32_t gp = (uint32_t)e, c = (uint32_t)(e >> 32);
+                if (c <= EM_INLINE) {
+                    for (uint32_t q = 0; q < c; ++q) out[pos + q] = w.pool[gp + q];
+                } else {
+                    uint32_t b = atomicAdd(&sm.n_big, 1u);
+                    sm.bigpos[b] = pos; sm.biggp[b] = gp; sm.bigcnt[b] = c;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const uint32_t nb = sm.n_big;
+        for (uint32_t b = 0; b < nb; ++b) {
+            const uint32_t pos = sm.bigpos[b], gp = sm.biggp[b], c = sm.bigcnt[b];
+            for (uint32_t q = tid; q < c; q += SPL_THREADS) out[pos + q] = w.pool[gp + q];
+        }
+    }
+
+    // ---- output offset of every document that starts in this tile ----------------------------------------
+    for (uint32_t d = d0 + tid; d < d1; d += SPL_THREADS) {
+        uint32_t x = (uint32_t)(w.doc_off[d] - w.off_base - tile0);
+        uint32_t pi = sm.wpre[x >> 5] + __popc(sm.pbw[x >> 5] & ((1u << (x & 31)) - 1u));
+        w.out_off[d] = prefix + sm.spos[pi];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+void spl_encode_init() {
+    cudaFuncSetAttribute(k_probe, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
+    cudaFuncSetAttribute(k_emit, cudaFuncAttributePreferredSharedMemoryCarveout, 75);
+    cudaGetLastError();
+}
+
+void spl_launch_encode_stage(const SplWork& w, int num_sms, cudaStream_t stream, SplMarkFn mark, void* ctx) {
+    k_probe<<<w.n_tiles, SPL_THREADS, 0, stream>>>(w);
+    mark(ctx, "k_probe");
+    k_bpe<<<(uint32_t)num_sms * 6u, SPL_BPE_THREADS, 0, stream>>>(w);
+    mark(ctx, "k_bpe");
+    k_tile_scan<<<1, 1024, 0, stream>>>(w);
+    mark(ctx, "k_tile_scan");
+    k_emit<<<w.n_tiles, SPL_THREADS, 0, stream>>>(w);
+    mark(ctx, "k_emit");
+}

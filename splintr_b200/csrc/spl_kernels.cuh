@@ -13,6 +13,21 @@
 #define SPL_FAST_PAYLOAD 256u         // words per tile = 8192 bytes = 2 * SPL_TILE
 #define SPL_FAST_THREADS (SPL_FAST_PAYLOAD + 2u * SPL_FAST_HALO)
 
+// encode stage (spl_encode.cu)
+#define SPL_PROBE_HALO  128u          // bytes staged beyond a tile for the whole-piece probe (bundled keys are <= 128 B)
+#define SPL_PROBE_WIN   (SPL_TILE + SPL_PROBE_HALO)
+#define SPL_BPE_THREADS 128           // k_bpe block size
+#define SPL_SHORT_MAX   32u           // piece bytes merged by one thread
+#define SPL_WARP_MAX    256u          // ... by one warp, four pieces per block
+#define SPL_BIG_MAX     3968u         // ... by one warp that owns the block's shared memory; longer: whole block, global scratch
+
+// values of SplWork::pv (one per piece, in text order)
+#define SPL_PV_MISS  0x80000000u      // | index of the piece's entry in `mlist`
+#define SPL_PV_NONE  0xFFFFFFFFu      // the piece produces no id (byte unknown to the vocabulary)
+// miss-list entry before k_bpe:  gpos:32 | len:20 (saturating) | piece index in its tile:12
+// miss-list entry after  k_bpe:  gpos:32 | id count:32         (ids at pool[gpos ..])
+#define SPL_ML_LEN_SAT 0xFFFFFu
+
 // per-call device workspace (all pointers on the current device)
 struct SplWork {
     const uint8_t*  text;        // [N], 16-byte aligned, readable up to N rounded up to 16
@@ -26,15 +41,17 @@ struct SplWork {
     uint32_t*       pstart;      // bitmap words: piece starts (incl. sentinel bit N)
     size_t          bitmap_words;
     uint32_t*       tile_first_doc;   // [n_tiles+1]
-    uint64_t*       tile_state;       // [n_tiles] exclusive prefix of tile_cnt (k_tile_scan)
-    uint32_t*       tile_cnt;         // [n_tiles] ids produced by each tile
-    uint64_t*       tile_soff;        // [n_tiles] where the tile's ids sit in `stage`
-    uint32_t*       stage;            // [>= N] ids in tile-completion order
-    uint64_t*       stage_bump;       // bump allocator of `stage` (counters + 8 bytes .. 16-byte aligned)
-    uint32_t*       counters;         // [8]: 0 = encode ticket, 1 = error flags, 2 = huge pool bump, 3 = fallback tiles
+    uint32_t*       tile_np;          // [n_tiles] pieces that start in the tile (k_probe)
+    int32_t*        tile_extra;       // [n_tiles] ids minus pieces (k_probe: dropped bytes, k_bpe: merged pieces)
+    uint64_t*       tile_state;       // [n_tiles] exclusive prefix of the tiles' id counts (k_tile_scan)
+    uint32_t*       pv;               // [n_tiles * SPL_TILE] per-piece value, tile t at pv[t * SPL_TILE ..]
+    uint32_t*       pool;             // [N] ids of the pieces that went through the merge loop, at the piece's byte position
+    uint64_t*       mlist;            // miss list: [0, ml_r0) short pieces bottom-up / warp pieces top-down,
+    uint32_t        ml_r0, ml_r1, ml_r2;   // [ml_r0, ml_r1) big pieces, [ml_r1, ml_r2) huge pieces
+    uint32_t*       counters;         // [16]: see SPL_CTR_*
     uint32_t*       fb_list;          // [n_fast_tiles] fast-path tiles handed to the sequential rules
     uint32_t        n_fast_tiles;
-    uint32_t*       huge_pool;        // scratch for pieces that outgrow the staging window
+    uint32_t*       huge_pool;        // scratch for pieces that outgrow shared memory
     uint32_t        huge_pool_words;
     uint32_t*       ids;              // [>= N]
     uint64_t*       out_off;          // [n_docs+1]
@@ -43,10 +60,15 @@ struct SplWork {
     bool            with_special;
 };
 
+// SplWork::counters
+enum : uint32_t { SPL_CTR_SHORT = 0, SPL_CTR_ERR = 1, SPL_CTR_HUGE_POOL = 2, SPL_CTR_FB = 3,
+                  SPL_CTR_WARP = 4, SPL_CTR_BIG = 5, SPL_CTR_HUGE = 6, SPL_CTR_TICKET_S = 8, SPL_CTR_TICKET_W = 9,
+                  SPL_CTR_TICKET_B = 10, SPL_CTR_TICKET_H = 11, SPL_CTR_WORDS = 16 };
+
 enum : uint32_t { SPL_DEVERR_OFFSETS = 1u, SPL_DEVERR_HUGE_POOL = 2u };
 
 // optional per-kernel device timing: ev[i] is recorded before kernel i, ev[n] after the last
-#define SPL_PROF_MAX 8
+#define SPL_PROF_MAX 12
 struct SplKernelProfile {
     cudaEvent_t ev[SPL_PROF_MAX + 1];
     const char* name[SPL_PROF_MAX];
@@ -58,3 +80,8 @@ int spl_launch_encode(const SplWork& w, int num_sms, cudaStream_t stream, SplKer
 
 // Per-device one-time kernel attribute setup (shared-memory carveout).
 void spl_kernels_init();
+
+// spl_encode.cu: the encode stage behind the pre-tokenizer (k_probe, k_bpe, k_tile_scan, k_emit)
+typedef void (*SplMarkFn)(void* ctx, const char* name);
+void spl_encode_init();
+void spl_launch_encode_stage(const SplWork& w, int num_sms, cudaStream_t stream, SplMarkFn mark, void* ctx);

@@ -173,7 +173,7 @@ def test_device_resident_entry_point(toks):
     tok.encode_device(buf[:n], d_off)
     kt = tok.last_kernel_times()
     tok.set_profiling(False)
-    assert "k_encode" in kt and all(v >= 0 for v in kt.values())
+    assert "k_probe" in kt and "k_emit" in kt and all(v >= 0 for v in kt.values())
 
 
 def test_invalid_offsets_rejected(toks):
