@@ -154,13 +154,14 @@ void destroy_ctx(DevCtx& dc) {
 // limits of one device shard: 32-bit positions inside the kernels
 const uint64_t kMaxShardBytes = 0xFFFFFFFFull - 4ull * SPL_WIN;
 
-// layout of the zero-initialised region: counters | tile_extra | hard | pstart | spec
-struct ZeroLayout { size_t words, n_tiles, off_extra, off_hard, off_pstart, off_spec, total; };
+// layout of the zero-initialised region: counters | chunk_cnt | tile_extra | hard | pstart | spec
+struct ZeroLayout { size_t words, n_tiles, off_chunk, off_extra, off_hard, off_pstart, off_spec, total; };
 ZeroLayout zero_layout(uint64_t N, bool with_special) {
     ZeroLayout z;
     z.words = (size_t)((N + SPL_WIN) / 32 + 16);
     z.n_tiles = (size_t)(N / SPL_TILE) + 1;
-    z.off_extra = 256;
+    z.off_chunk = 256;
+    z.off_extra = align_up(z.off_chunk + (z.n_tiles / SPL_CHUNK_TILES + 2) * 4, 256);
     z.off_hard = align_up(z.off_extra + z.n_tiles * 4, 256);
     z.off_pstart = align_up(z.off_hard + z.words * 4, 256);
     z.off_spec = align_up(z.off_pstart + z.words * 4, 256);
@@ -189,7 +190,7 @@ int reserve_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
     if ((rc = dc.zero.ensure(z.total, tk->err))) return rc;
     if ((rc = dc.tfd.ensure((z.n_tiles + 2) * 4, tk->err))) return rc;
     if ((rc = dc.tnp.ensure(z.n_tiles * 4, tk->err))) return rc;
-    if ((rc = dc.tstate.ensure(z.n_tiles * 8, tk->err))) return rc;
+    if ((rc = dc.tstate.ensure((z.n_tiles / SPL_CHUNK_TILES + 2) * 8, tk->err))) return rc;
     if ((rc = dc.pv.ensure(z.n_tiles * SPL_TILE * 4, tk->err))) return rc;
     if ((rc = dc.pool.ensure((size_t)(N + 64) * 4, tk->err))) return rc;
     if ((rc = dc.mlist.ensure((size_t)m.r2 * 8, tk->err))) return rc;
@@ -215,6 +216,7 @@ int prepare_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
     w.n_docs = (uint32_t)n_docs;
     w.n_tiles = (uint32_t)z.n_tiles;
     w.counters = (uint32_t*)zb;
+    w.chunk_cnt = (int32_t*)(zb + z.off_chunk);
     w.tile_extra = (int32_t*)(zb + z.off_extra);
     w.hard = (uint32_t*)(zb + z.off_hard);
     w.pstart = (uint32_t*)(zb + z.off_pstart);
@@ -222,7 +224,7 @@ int prepare_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
     w.bitmap_words = z.words;
     w.tile_first_doc = (uint32_t*)dc.tfd.p;
     w.tile_np = (uint32_t*)dc.tnp.p;
-    w.tile_state = (uint64_t*)dc.tstate.p;
+    w.chunk_state = (uint64_t*)dc.tstate.p;
     w.pv = (uint32_t*)dc.pv.p;
     w.pool = (uint32_t*)dc.pool.p;
     w.mlist = (uint64_t*)dc.mlist.p;
@@ -353,7 +355,7 @@ int spl_launches_per_call(const spl_tokenizer* tk, uint32_t flags) {
     if (!tk) return 0;
     bool ws = (flags & SPL_ENCODE_WITH_SPECIAL) && !tk->host.sp_id.empty();
     int pre = tk->host.pattern == SPL_PAT_MISTRAL_V3 ? 1 : 2;          // sequential rules | bit-parallel + fallback
-    return 5 + pre + (ws ? 1 : 0);                                     // mark_docs, probe, bpe, tile_scan, emit
+    return 5 + pre + (ws ? 1 : 0);                                     // mark_docs, probe, bpe, chunk_scan, emit
 }
 
 int spl_set_profiling(spl_tokenizer* tk, int enable) {

@@ -58,7 +58,11 @@ SPL_HD uint64_t spl_mix64(uint64_t x) {
     return x;
 }
 
-// pair table: open addressing, 8-byte entries  (left:21 | right:21 | merged:21), bit 63 = 0
+// pair table: 8-byte entries (left:21 | right:21 | merged:21), bit 63 = 0, in buckets of SPL_PAIR_WAYS entries
+// (one 32-byte sector per probe).  A bucket fills front to back; a key lives in the first bucket from its home
+// bucket on that was not full when it was inserted, so a probe ends at the first bucket whose last slot is empty.
+// `log2size` counts BUCKETS.
+#define SPL_PAIR_WAYS 4
 SPL_HD uint64_t spl_pair_key(uint32_t l, uint32_t r) { return ((uint64_t)l << SPL_SYM_BITS) | r; }
 SPL_HD uint64_t spl_pair_entry(uint32_t l, uint32_t r, uint32_t m) { return (spl_pair_key(l, r) << SPL_SYM_BITS) | m; }
 SPL_HD uint32_t spl_pair_hash(uint64_t key, uint32_t log2size) {
@@ -67,15 +71,20 @@ SPL_HD uint32_t spl_pair_hash(uint64_t key, uint32_t log2size) {
 
 // whole-piece tables.  Keys are the piece bytes packed little-endian into u64 words,
 // zero padded; `len` disambiguates padding from NUL bytes.  len == 0 marks an empty slot.
+// T8 is bucketed like the pair table: SPL_T8_WAYS entries (one 32-byte sector) per bucket, t8_log2 counts buckets,
+// keys are inserted in id order so that the frequent (low-rank) tokens sit in their home bucket.
 struct SplKey8  { uint64_t k0; uint32_t id; uint32_t len; };                       // len 1..8
 struct SplKey16 { uint64_t k0; uint64_t k1; uint32_t id; uint32_t len; uint64_t pad; };   // len 9..16
 struct SplKeyL  { uint64_t hash; uint32_t id; uint32_t len; };                    // len 17..max, verified against token bytes
 
-SPL_HD uint32_t spl_hash8(uint64_t k0, uint32_t len, uint32_t log2size) {
-    uint64_t h = (k0 + len) * 0x9E3779B97F4A7C15ull;
-    h ^= h >> 29;
-    h *= 0xBF58476D1CE4E5B9ull;
-    return (uint32_t)(h >> (64 - log2size));
+#define SPL_T8_WAYS 2
+SPL_HD uint32_t spl_hash8(uint32_t lo, uint32_t hi, uint32_t len, uint32_t log2size) {
+    uint32_t x = lo * 0x9E3779B1u + hi * 0x85EBCA77u + len * 0xC2B2AE3Du;
+    x ^= x >> 15;
+    x *= 0x2C1B3C6Du;
+    x ^= x >> 13;
+    x *= 0x297A2D39u;
+    return x >> (32 - log2size);
 }
 SPL_HD uint32_t spl_hash16(uint64_t k0, uint64_t k1, uint32_t len, uint32_t log2size) {
     uint64_t h = (k0 + len) * 0x9E3779B97F4A7C15ull;

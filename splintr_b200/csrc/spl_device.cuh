@@ -42,24 +42,48 @@ __device__ __forceinline__ uint32_t g_next_bit(const uint32_t* __restrict__ w, u
     }
 }
 
+// one bucket of the pair table: SPL_PAIR_WAYS entries = one 32-byte sector
+struct PairBucket { ulonglong2 lo, hi; };
+__device__ __forceinline__ PairBucket pair_bucket_load(const uint64_t* __restrict__ tab, uint32_t b) {
+    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(tab + (size_t)b * SPL_PAIR_WAYS);
+    PairBucket r;
+    r.lo = __ldg(p); r.hi = __ldg(p + 1);
+    return r;
+}
+// 0: key absent (bucket not full), 1: found (out set), 2: bucket full, go on with the next one
+__device__ __forceinline__ int pair_bucket_match(const PairBucket& k, uint64_t key, uint32_t& out) {
+    const uint32_t symmask = (1u << SPL_SYM_BITS) - 1;
+    if ((k.lo.x >> SPL_SYM_BITS) == key) { out = (uint32_t)k.lo.x & symmask; return 1; }
+    if ((k.lo.y >> SPL_SYM_BITS) == key) { out = (uint32_t)k.lo.y & symmask; return 1; }
+    if ((k.hi.x >> SPL_SYM_BITS) == key) { out = (uint32_t)k.hi.x & symmask; return 1; }
+    if ((k.hi.y >> SPL_SYM_BITS) == key) { out = (uint32_t)k.hi.y & symmask; return 1; }
+    return k.hi.y == SPL_PAIR_EMPTY ? 0 : 2;
+}
+
 __device__ __forceinline__ uint32_t pair_lookup(const uint64_t* __restrict__ tab, uint32_t log2, uint32_t l, uint32_t r) {
-    uint64_t key = spl_pair_key(l, r);
-    uint32_t mask = (1u << log2) - 1, h = spl_pair_hash(key, log2);
+    const uint64_t key = spl_pair_key(l, r);
+    const uint32_t mask = (1u << log2) - 1;
+    uint32_t b = spl_pair_hash(key, log2), out = SPL_RANK_NONE;
     for (;;) {
-        uint64_t e = __ldg(tab + h);
-        if ((e >> SPL_SYM_BITS) == key) return (uint32_t)e & ((1u << SPL_SYM_BITS) - 1);
-        if (e == SPL_PAIR_EMPTY) return SPL_RANK_NONE;
-        h = (h + 1) & mask;
+        PairBucket k = pair_bucket_load(tab, b);
+        int m = pair_bucket_match(k, key, out);
+        if (m != 2) return out;
+        b = (b + 1) & mask;
     }
 }
 
+// whole-piece probe, 1..8 bytes: buckets of SPL_T8_WAYS entries (one sector)
 __device__ __forceinline__ uint32_t lookup8(const SplKey8* __restrict__ t, uint32_t log2, uint64_t k0, uint32_t len) {
-    uint32_t mask = (1u << log2) - 1, h = spl_hash8(k0, len, log2);
+    const uint32_t lo = (uint32_t)k0, hi = (uint32_t)(k0 >> 32);
+    const uint32_t mask = (1u << log2) - 1;
+    uint32_t b = spl_hash8(lo, hi, len, log2);
     for (;;) {
-        uint4 v = __ldg(reinterpret_cast<const uint4*>(t + h));
-        if (v.w == 0) return SPL_RANK_NONE;
-        if (v.w == len && v.x == (uint32_t)k0 && v.y == (uint32_t)(k0 >> 32)) return v.z;
-        h = (h + 1) & mask;
+        const uint4* p = reinterpret_cast<const uint4*>(t + (size_t)b * SPL_T8_WAYS);
+        uint4 v0 = __ldg(p), v1 = __ldg(p + 1);               // {k0 lo, k0 hi, id, len}
+        if (v0.w == len && v0.x == lo && v0.y == hi) return v0.z;
+        if (v1.w == len && v1.x == lo && v1.y == hi) return v1.z;
+        if (v1.w == 0) return SPL_RANK_NONE;
+        b = (b + 1) & mask;
     }
 }
 
@@ -101,18 +125,17 @@ __device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
 __device__ __forceinline__ void pair_lookup2(const uint64_t* __restrict__ tab, uint32_t log2,
                                              bool va, uint32_t la, uint32_t ra, bool vb, uint32_t lb, uint32_t rb,
                                              uint32_t& outa, uint32_t& outb) {
-    const uint32_t mask = (1u << log2) - 1, symmask = (1u << SPL_SYM_BITS) - 1;
-    uint64_t ka = spl_pair_key(la, ra), kb = spl_pair_key(lb, rb);
-    uint32_t ha = spl_pair_hash(ka, log2), hb = spl_pair_hash(kb, log2);
-    uint64_t ea = va ? __ldg(tab + ha) : SPL_PAIR_EMPTY;
-    uint64_t eb = vb ? __ldg(tab + hb) : SPL_PAIR_EMPTY;
+    const uint32_t mask = (1u << log2) - 1;
+    const uint64_t ka = spl_pair_key(la, ra), kb = spl_pair_key(lb, rb);
+    uint32_t ba = spl_pair_hash(ka, log2), bb = spl_pair_hash(kb, log2);
+    PairBucket xa, xb;
+    xa.lo = xa.hi = make_ulonglong2(SPL_PAIR_EMPTY, SPL_PAIR_EMPTY);
+    xb = xa;
+    if (va) xa = pair_bucket_load(tab, ba);
+    if (vb) xb = pair_bucket_load(tab, bb);
     outa = SPL_RANK_NONE; outb = SPL_RANK_NONE;
-    while (ea != SPL_PAIR_EMPTY) {
-        if ((ea >> SPL_SYM_BITS) == ka) { outa = (uint32_t)ea & symmask; break; }
-        ha = (ha + 1) & mask; ea = __ldg(tab + ha);
-    }
-    while (eb != SPL_PAIR_EMPTY) {
-        if ((eb >> SPL_SYM_BITS) == kb) { outb = (uint32_t)eb & symmask; break; }
-        hb = (hb + 1) & mask; eb = __ldg(tab + hb);
-    }
+    if (va)
+        while (pair_bucket_match(xa, ka, outa) == 2) { ba = (ba + 1) & mask; xa = pair_bucket_load(tab, ba); }
+    if (vb)
+        while (pair_bucket_match(xb, kb, outb) == 2) { bb = (bb + 1) & mask; xb = pair_bucket_load(tab, bb); }
 }

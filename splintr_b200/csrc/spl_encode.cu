@@ -4,7 +4,7 @@
 //                hit goes to pv[] in piece order, a miss is appended to the miss list of its length class
 //   k_bpe        the leftmost-min-rank merge loop of bpe.rs:83-194 for every listed piece -- one thread per piece up
 //                to 32 bytes, one warp up to 3968 bytes, one block beyond -- ids to pool[] at the piece's byte position
-//   k_tile_scan  exclusive prefix of the per-tile id counts
+//   k_chunk_scan exclusive prefix of the id counts of 32-tile chunks (k_emit adds the tiles inside its chunk)
 //   k_emit       pv[] + pool[] -> ids in document order (the collect of tokenizer.rs:806 and the Rayon collect of
 //                encode_batch, tokenizer.rs:932-934) and the per-document output offsets
 //
@@ -93,13 +93,29 @@ __device__ __forceinline__ uint64_t ml_entry(uint32_t gpos, uint32_t len, uint32
 struct ProbeSmem {
     uint32_t text[SPL_PROBE_WIN / 4 + 4];     // staged bytes (+ slack for the unaligned 8-byte key loads)
     uint32_t pb[PB_WORDS];                    // piece-start bits
-    uint32_t byte_sym[256];
+    uint32_t spw[SPL_TILE / 32];              // special-span bits of the tile (with_special)
     uint16_t plist[SPL_TILE + 2];             // window positions of the tile's piece starts, in order (+ end of the last piece)
+    uint16_t slow[SPL_TILE];                  // pieces the one-sector probe did not settle
     uint16_t mloc[SPL_TILE];                  // missed pieces: thread class from the bottom, warp class from the top
     uint32_t wtot[SPL_THREADS / 32];
-    uint32_t n_short, n_warp, g_short, g_warp;
+    uint32_t n_slow, n_short, n_warp, g_short, g_warp;
     uint32_t last_end;                        // window position of the end of the tile's last piece
 };
+
+// append j to a shared list, one shared atomic per warp.  Every lane of the warp must call it.
+__device__ __forceinline__ void warp_push(bool pred, uint32_t* counter, uint16_t* list, uint32_t j, bool top_down) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t bal = __ballot_sync(FULL, pred);
+    if (bal) {
+        uint32_t leader = __ffs(bal) - 1, b0 = 0;
+        if (lane == leader) b0 = atomicAdd(counter, (uint32_t)__popc(bal));
+        b0 = __shfl_sync(FULL, b0, leader);
+        if (pred) {
+            uint32_t k = b0 + __popc(bal & ((1u << lane) - 1u));
+            list[top_down ? SPL_TILE - 1 - k : k] = (uint16_t)j;
+        }
+    }
+}
 
 __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
     __shared__ ProbeSmem sm;
@@ -107,6 +123,8 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t N = w.N, Nup = (N + 15u) & ~15u;
     const uint32_t tile = blockIdx.x, tile0 = tile * SPL_TILE;
+    const SplKey8* __restrict__ t8 = T->t8;
+    const uint32_t t8_log2 = T->t8_log2;
 
     // ---- stage the window -----------------------------------------------------------
     for (uint32_t v = tid; v < SPL_PROBE_WIN / 16 + 1; v += SPL_THREADS) {
@@ -116,8 +134,8 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
         reinterpret_cast<uint4*>(sm.text)[v] = x;
     }
     for (uint32_t v = tid; v < PB_WORDS; v += SPL_THREADS) sm.pb[v] = __ldg(w.pstart + (tile0 >> 5) + v);
-    sm.byte_sym[tid] = T->byte_sym[tid];
-    if (tid == 0) { sm.n_short = 0; sm.n_warp = 0; }
+    if (w.with_special && tid < SPL_TILE / 32) sm.spw[tid] = __ldg(w.spec + (tile0 >> 5) + tid);
+    if (tid == 0) { sm.n_slow = 0; sm.n_short = 0; sm.n_warp = 0; }
     __syncthreads();
 
     // ---- piece list: positions of the piece starts of this tile, in order ------------------
@@ -150,34 +168,61 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
         sm.last_end = e;
         sm.plist[P] = (uint16_t)(e >= PB_BITS ? 0xFFFFu : e);      // 0xFFFF: see last_end
         w.tile_np[tile] = P;
+        if (P) atomicAdd(&w.chunk_cnt[tile / SPL_CHUNK_TILES], (int32_t)P);
     }
     __syncthreads();
 
-    // ---- one thread per piece -------------------------------------------------------------
+    // ---- hot loop, one thread per piece: pieces of up to 8 bytes, one sector of the bucketed table -------------
     const uint32_t pvbase = tile * SPL_TILE;
     for (uint32_t j0 = 0; j0 < P; j0 += SPL_THREADS) {
         const uint32_t j = j0 + tid;
         const bool valid = j < P;
-        uint32_t val = SPL_PV_NONE;
-        uint32_t cls = 0;                                      // 0 resolved, 1 thread class, 2 warp class, 3 big, 4 huge
         uint32_t s = 0, len = 0;
-        if (valid) {
-            s = sm.plist[j];
+        if (valid) { s = sm.plist[j]; len = sm.plist[j + 1] - s; }      // end 0xFFFF: len is large, not probed here
+        bool fast = valid && len <= 8;
+        if (w.with_special && ((sm.spw[s >> 5] >> (s & 31)) & 1u)) fast = false;
+        bool found = false;
+        if (fast) {
+            const uint32_t wi = s >> 2, sh = (s & 3u) * 8u;
+            const uint32_t a = sm.text[wi], b = sm.text[wi + 1], c = sm.text[wi + 2];
+            uint32_t lo = __funnelshift_r(a, b, sh), hi = __funnelshift_r(b, c, sh);
+            const uint32_t nb = len * 8u;
+            lo &= nb >= 32u ? FULL : ((1u << nb) - 1u);
+            hi &= nb <= 32u ? 0u : (nb >= 64u ? FULL : ((1u << (nb - 32u)) - 1u));
+            const uint4* p = reinterpret_cast<const uint4*>(t8 + (size_t)spl_hash8(lo, hi, len, t8_log2) * SPL_T8_WAYS);
+            const uint4 v0 = __ldg(p), v1 = __ldg(p + 1);       // {k0 lo, k0 hi, id, len}
+            const bool h0 = v0.w == len && v0.x == lo && v0.y == hi;
+            const bool h1 = v1.w == len && v1.x == lo && v1.y == hi;
+            found = h0 || h1;
+            if (found) w.pv[pvbase + j] = h0 ? v0.z : v1.z;
+        }
+        warp_push(valid && !found, &sm.n_slow, sm.slow, j, false);
+    }
+    __syncthreads();
+
+    // ---- the rest: specials, longer pieces, second buckets, misses ------------------------------------------
+    const uint32_t n_slow = sm.n_slow;
+    for (uint32_t i0 = 0; i0 < n_slow; i0 += SPL_THREADS) {
+        const uint32_t i = i0 + tid;
+        uint32_t cls = 0, j = 0;                               // 0 settled, 1 thread class, 2 warp class, 3 big, 4 huge
+        if (i < n_slow) {
+            j = sm.slow[i];
+            const uint32_t s = sm.plist[j];
             uint32_t e = sm.plist[j + 1];
             if (e == 0xFFFFu) e = sm.last_end;
-            len = e - s;
-            const uint32_t gpos = tile0 + s;
-            if (w.with_special && ((__ldg(w.spec + (gpos >> 5)) >> (gpos & 31)) & 1u)) {
+            const uint32_t len = e - s, gpos = tile0 + s;
+            uint32_t val = SPL_PV_NONE;
+            if (w.with_special && ((sm.spw[s >> 5] >> (s & 31)) & 1u)) {
                 val = special_id_g(T, w.text + gpos, len);
             } else if (len == 1) {
-                uint32_t sy = sm.byte_sym[sm_byte(sm.text, s)];
+                uint32_t sy = T->byte_sym[sm_byte(sm.text, s)];
                 val = sy < SPL_UNK_BASE ? sy : SPL_PV_NONE;   // unknown byte: no id (bpe.rs:73-75)
             } else {
                 uint32_t id = SPL_RANK_NONE;
                 if (len <= 8) {
                     uint64_t k0 = sm_load8(sm.text, s);
                     if (len < 8) k0 &= (1ull << (8 * len)) - 1;
-                    id = lookup8(T->t8, T->t8_log2, k0, len);
+                    id = lookup8(t8, t8_log2, k0, len);
                 } else if (len <= 16) {
                     uint64_t k0 = sm_load8(sm.text, s), k1 = sm_load8(sm.text, s + 8);
                     if (len < 16) k1 &= (1ull << (8 * (len - 8))) - 1;
@@ -190,7 +235,7 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
             }
             if (cls == 0) {
                 w.pv[pvbase + j] = val;
-                if (val == SPL_PV_NONE) atomicAdd(&w.tile_extra[tile], -1);
+                if (val == SPL_PV_NONE) { atomicAdd(&w.tile_extra[tile], -1); atomicAdd(&w.chunk_cnt[tile / SPL_CHUNK_TILES], -1); }
             } else if (cls >= 3) {                             // rare: straight to the global list of its class
                 uint32_t midx = cls == 3 ? w.ml_r0 + atomicAdd(&w.counters[SPL_CTR_BIG], 1u)
                                          : w.ml_r1 + atomicAdd(&w.counters[SPL_CTR_HUGE], 1u);
@@ -198,23 +243,8 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
                 w.pv[pvbase + j] = SPL_PV_MISS | midx;
             }
         }
-        // thread / warp class: collected per tile, warp-aggregated
-        {
-            uint32_t bal = __ballot_sync(FULL, cls == 1);
-            if (bal) {
-                uint32_t leader = __ffs(bal) - 1, b0 = 0;
-                if (lane == leader) b0 = atomicAdd(&sm.n_short, (uint32_t)__popc(bal));
-                b0 = __shfl_sync(FULL, b0, leader);
-                if (cls == 1) sm.mloc[b0 + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)j;
-            }
-            bal = __ballot_sync(FULL, cls == 2);
-            if (bal) {
-                uint32_t leader = __ffs(bal) - 1, b0 = 0;
-                if (lane == leader) b0 = atomicAdd(&sm.n_warp, (uint32_t)__popc(bal));
-                b0 = __shfl_sync(FULL, b0, leader);
-                if (cls == 2) sm.mloc[SPL_TILE - 1 - (b0 + __popc(bal & ((1u << lane) - 1u)))] = (uint16_t)j;
-            }
-        }
+        warp_push(cls == 1, &sm.n_short, sm.mloc, j, false);
+        warp_push(cls == 2, &sm.n_warp, sm.mloc, j, true);
     }
     __syncthreads();
 
@@ -263,7 +293,10 @@ union BpeSmem {
 
 __device__ __forceinline__ void bpe_finish(const SplWork& w, uint64_t* slot, uint32_t gpos, uint32_t cnt) {
     *slot = (uint64_t)gpos | ((uint64_t)cnt << 32);
-    if (cnt != 1u) atomicAdd(&w.tile_extra[gpos / SPL_TILE], (int32_t)cnt - 1);
+    if (cnt != 1u) {
+        atomicAdd(&w.tile_extra[gpos / SPL_TILE], (int32_t)cnt - 1);
+        atomicAdd(&w.chunk_cnt[gpos / (SPL_TILE * SPL_CHUNK_TILES)], (int32_t)cnt - 1);
+    }
 }
 
 // One THREAD merges the piece tx[0, n), 2 <= n <= 32: parts are the set bits of `live` (bit i = a part starts at byte
@@ -275,13 +308,31 @@ __device__ uint32_t bpe_piece_thread(BpeSmem& sm, const SplTables* T, const uint
     const uint32_t t = threadIdx.x;
 #define S(i) sm.th.sym[(i)][t]
 #define R(i) sm.th.rnk[(i)][t]
-    for (uint32_t i = 0; i < n; ++i) S(i) = T->byte_sym[__ldg(tx + i)];
-    for (uint32_t i = 0; i + 1 < n; i += 2) {
-        uint32_t ra, rb;
-        bool vb = i + 2 < n;
-        pair_lookup2(ptab, plog, true, S(i), S(i + 1), vb, vb ? S(i + 1) : 0u, vb ? S(i + 2) : 0u, ra, rb);
-        R(i) = ra;
-        if (vb) R(i + 1) = rb;
+#pragma unroll 4
+    for (uint32_t i = 0; i < n; ++i) S(i) = __ldg(tx + i);
+#pragma unroll 4
+    for (uint32_t i = 0; i < n; ++i) S(i) = T->byte_sym[S(i)];
+    {
+        const uint32_t pmask = (1u << plog) - 1;
+        for (uint32_t i = 0; i + 1 < n; i += 4) {                  // four independent probes in flight
+            PairBucket bk[4];
+            uint64_t key[4];
+            uint32_t bb[4];
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q)
+                if (i + q + 1 < n) {
+                    key[q] = spl_pair_key(S(i + q), S(i + q + 1));
+                    bb[q] = spl_pair_hash(key[q], plog);
+                    bk[q] = pair_bucket_load(ptab, bb[q]);
+                }
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q)
+                if (i + q + 1 < n) {
+                    uint32_t r = SPL_RANK_NONE;
+                    while (pair_bucket_match(bk[q], key[q], r) == 2) { bb[q] = (bb[q] + 1) & pmask; bk[q] = pair_bucket_load(ptab, bb[q]); }
+                    R(i + q) = r;
+                }
+        }
     }
     R(n - 1) = SPL_RANK_NONE;
     uint32_t live = n >= 32u ? 0xFFFFFFFFu : ((1u << n) - 1u);
@@ -537,21 +588,23 @@ __global__ void __launch_bounds__(SPL_BPE_THREADS) k_bpe(SplWork w) {
 }
 
 // ------------------------------------------------------------------------------------------
-// k_tile_scan: exclusive prefix of the per-tile id counts (one block; tiles are few: N / 4096)
+// k_chunk_scan: exclusive prefix of the id counts of the chunks (SPL_CHUNK_TILES tiles each; k_probe and k_bpe keep
+// the chunk totals up to date).  One block: chunks are few (N / 128 KiB); k_emit adds the tiles inside a chunk itself.
 // ------------------------------------------------------------------------------------------
-#define TS_PER 8u                                    // tiles per thread and round
-__global__ void __launch_bounds__(1024) k_tile_scan(SplWork w) {
+#define TS_PER 4u                                    // chunks per thread and round
+__global__ void __launch_bounds__(1024) k_chunk_scan(SplWork w) {
     __shared__ uint32_t s_cnt[1024 * TS_PER];
     __shared__ uint64_t s_w[32];
     __shared__ uint64_t s_carry;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t n = (w.n_tiles + SPL_CHUNK_TILES - 1) / SPL_CHUNK_TILES;
     if (tid == 0) s_carry = 0;
-    for (uint32_t c0 = 0; c0 < w.n_tiles; c0 += 1024 * TS_PER) {
-        // coalesced, independent loads; then every thread owns TS_PER consecutive tiles
+    for (uint32_t c0 = 0; c0 < n; c0 += 1024 * TS_PER) {
+        // coalesced, independent loads; then every thread owns TS_PER consecutive chunks
 #pragma unroll
         for (uint32_t q = 0; q < TS_PER; ++q) {
             uint32_t i = c0 + q * 1024 + tid;
-            s_cnt[q * 1024 + tid] = i < w.n_tiles ? (uint32_t)((int32_t)w.tile_np[i] + w.tile_extra[i]) : 0u;
+            s_cnt[q * 1024 + tid] = i < n ? (uint32_t)w.chunk_cnt[i] : 0u;
         }
         __syncthreads();
         uint32_t loc[TS_PER];
@@ -580,7 +633,7 @@ __global__ void __launch_bounds__(1024) k_tile_scan(SplWork w) {
 #pragma unroll
         for (uint32_t q = 0; q < TS_PER; ++q) {
             uint32_t i = c0 + tid * TS_PER + q;
-            if (i < w.n_tiles) w.tile_state[i] = run;
+            if (i < n) w.chunk_state[i] = run;
             run += loc[q];
         }
         __syncthreads();
@@ -590,79 +643,85 @@ __global__ void __launch_bounds__(1024) k_tile_scan(SplWork w) {
 }
 
 // ------------------------------------------------------------------------------------------
-// k_emit: one tile per block: pv[] (+ pool[] for merged pieces) -> ids in document order, output offsets
+// k_emit: one tile per block: pv[] (+ pool[] for merged pieces) -> ids in document order, output offsets.
+// Four pieces per thread and round (one 16-byte load of pv), so a warp owns 128 consecutive pieces.
 // ------------------------------------------------------------------------------------------
-#define EM_ITERS (SPL_TILE / SPL_THREADS)            // 16 pieces per thread at most
+#define EM_ROUNDS (SPL_TILE / (SPL_THREADS * 4))     // 4 rounds cover the 4096 pieces a tile can have
 #define EM_WARPS (SPL_THREADS / 32)
 #define EM_INLINE 8u                                 // ids of a merged piece copied by its own thread up to this many
 #define EM_BIGCAP (SPL_TILE / (EM_INLINE + 1u) + 1u) // pieces of a tile that can have more ids than that
 
 struct EmitSmem {
-    uint32_t spos[SPL_TILE + 1];                     // ids of the tile before piece j
+    uint32_t spos[SPL_TILE + 4];                     // ids of the tile before piece j; spos[P] = ids of the tile
     uint32_t pbw[SPL_TILE / 32];
     uint32_t wpre[SPL_TILE / 32];
-    uint32_t wtot[EM_ITERS * EM_WARPS];
+    uint32_t wtot[EM_ROUNDS * EM_WARPS];
     uint32_t bigpos[EM_BIGCAP], biggp[EM_BIGCAP], bigcnt[EM_BIGCAP];
     uint32_t n_big;
+    uint64_t prefix;
 };
+
+__device__ __forceinline__ uint32_t emit_count(const SplWork& w, uint32_t v, bool valid) {
+    if (!valid) return 0u;
+    if (v < SPL_PV_MISS) return 1u;
+    if (v == SPL_PV_NONE) return 0u;
+    return (uint32_t)(w.mlist[v & ~SPL_PV_MISS] >> 32);
+}
 
 __global__ void __launch_bounds__(SPL_THREADS) k_emit(SplWork w) {
     __shared__ EmitSmem sm;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t tile = blockIdx.x, tile0 = tile * SPL_TILE;
     const uint32_t P = w.tile_np[tile];
-    const uint64_t prefix = w.tile_state[tile];
     const uint32_t* __restrict__ pv = w.pv + tile0;
-    uint32_t* __restrict__ out = w.ids + prefix;
     const uint32_t d0 = __ldg(w.tile_first_doc + tile), d1 = __ldg(w.tile_first_doc + tile + 1);
+    const uint32_t rounds = (P + SPL_THREADS * 4 - 1) / (SPL_THREADS * 4);
 
     if (tid == 0) sm.n_big = 0;
     if (d1 > d0 && tid < SPL_TILE / 32) sm.pbw[tid] = __ldg(w.pstart + (tile0 >> 5) + tid);
+    if (warp == EM_WARPS - 1) {
+        // ids before this tile: the chunk's prefix plus the tiles of the chunk in front of this one
+        const uint32_t t = (tile & ~(SPL_CHUNK_TILES - 1u)) + lane;
+        uint32_t c = t < tile ? (uint32_t)((int32_t)w.tile_np[t] + w.tile_extra[t]) : 0u;
+        c = __reduce_add_sync(FULL, c);
+        if (lane == 0) sm.prefix = w.chunk_state[tile / SPL_CHUNK_TILES] + c;
+    }
 
     // ---- pass 1: id count of every piece, warp-level prefixes ---------------------------------------
-    const uint32_t iters = (P + SPL_THREADS - 1) / SPL_THREADS;
-    for (uint32_t k = 0; k < iters; ++k) {
-        const uint32_t j = k * SPL_THREADS + tid;
-        uint32_t c = 0;
-        if (j < P) {
-            uint32_t v = __ldg(pv + j);
-            c = v < SPL_PV_MISS ? 1u : (v == SPL_PV_NONE ? 0u : (uint32_t)(w.mlist[v & ~SPL_PV_MISS] >> 32));
-        }
-        uint32_t incl = c;
+    uint4 vals[EM_ROUNDS];
+    uint32_t ex[EM_ROUNDS];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(FULL, incl, o);
-            if (lane >= (uint32_t)o) incl += t;
+    for (uint32_t k = 0; k < EM_ROUNDS; ++k) {
+        if (k < rounds) {
+            const uint32_t j4 = (k * SPL_THREADS + tid) * 4u;
+            uint4 v = make_uint4(SPL_PV_NONE, SPL_PV_NONE, SPL_PV_NONE, SPL_PV_NONE);
+            if (j4 < P) v = __ldg(reinterpret_cast<const uint4*>(pv + j4));
+            vals[k] = v;
+            const uint32_t c = emit_count(w, v.x, j4 < P) + emit_count(w, v.y, j4 + 1 < P) +
+                               emit_count(w, v.z, j4 + 2 < P) + emit_count(w, v.w, j4 + 3 < P);
+            uint32_t incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= (uint32_t)o) incl += t;
+            }
+            ex[k] = incl - c;
+            if (lane == 31) sm.wtot[k * EM_WARPS + warp] = incl;
         }
-        if (j < P) sm.spos[j] = incl - c;
-        if (lane == 31) sm.wtot[k * EM_WARPS + warp] = incl;
     }
     __syncthreads();
     if (warp == 0) {
-        // exclusive scan of the iters * EM_WARPS (<= 128) warp totals, four per lane; word prefixes of the piece bits
-        uint32_t loc[4], run = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint32_t idx = lane * 4 + q;
-            loc[q] = idx < iters * EM_WARPS ? sm.wtot[idx] : 0u;
-            run += loc[q];
-        }
-        uint32_t incl = run;
+        // exclusive scan of the rounds * EM_WARPS (<= 32) warp totals; word prefixes of the piece bits
+        uint32_t x = lane < rounds * EM_WARPS ? sm.wtot[lane] : 0u, incl = x;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t t = __shfl_up_sync(FULL, incl, o);
             if (lane >= (uint32_t)o) incl += t;
         }
-        uint32_t b = incl - run;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint32_t idx = lane * 4 + q;
-            if (idx < iters * EM_WARPS) sm.wtot[idx] = b;
-            b += loc[q];
-        }
+        sm.wtot[lane] = incl - x;
         if (lane == 31) sm.spos[P] = incl;                     // ids of the whole tile
         if (d1 > d0) {
-            run = 0;
+            uint32_t loc[4], run = 0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) { loc[q] = __popc(sm.pbw[lane * 4 + q]); run += loc[q]; }
             incl = run;
@@ -671,7 +730,7 @@ __global__ void __launch_bounds__(SPL_THREADS) k_emit(SplWork w) {
                 uint32_t t = __shfl_up_sync(FULL, incl, o);
                 if (lane >= (uint32_t)o) incl += t;
             }
-            b = incl - run;
+            uint32_t b = incl - run;
 #pragma unroll
             for (int q = 0; q < 4; ++q) { sm.wpre[lane * 4 + q] = b; b += loc[q]; }
         }
@@ -679,21 +738,31 @@ __global__ void __launch_bounds__(SPL_THREADS) k_emit(SplWork w) {
     __syncthreads();
 
     // ---- pass 2: ids to their place ----------------------------------------------------------------------
-    for (uint32_t k = 0; k < iters; ++k) {
-        const uint32_t j = k * SPL_THREADS + tid;
-        if (j < P) {
-            const uint32_t pos = sm.spos[j] + sm.wtot[k * EM_WARPS + warp];
-            sm.spos[j] = pos;
-            const uint32_t v = __ldg(pv + j);
-            if (v < SPL_PV_MISS) out[pos] = v;
-            else if (v != SPL_PV_NONE) {
-                const uint64_t e = w.mlist[v & ~SPL_PV_MISS];
-                const uint32_t gp = (uint32_t)e, c = (uint32_t)(e >> 32);
-                if (c <= EM_INLINE) {
-                    for (uint32_t q = 0; q < c; ++q) out[pos + q] = w.pool[gp + q];
-                } else {
-                    uint32_t b = atomicAdd(&sm.n_big, 1u);
-                    sm.bigpos[b] = pos; sm.biggp[b] = gp; sm.bigcnt[b] = c;
+    const uint64_t prefix = sm.prefix;
+    uint32_t* __restrict__ out = w.ids + prefix;
+#pragma unroll
+    for (uint32_t k = 0; k < EM_ROUNDS; ++k) {
+        if (k < rounds) {
+            const uint32_t j4 = (k * SPL_THREADS + tid) * 4u;
+            uint32_t pos = ex[k] + sm.wtot[k * EM_WARPS + warp];
+            const uint32_t vv[4] = {vals[k].x, vals[k].y, vals[k].z, vals[k].w};
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q) {
+                if (j4 + q < P) {
+                    const uint32_t v = vv[q];
+                    sm.spos[j4 + q] = pos;
+                    if (v < SPL_PV_MISS) out[pos++] = v;
+                    else if (v != SPL_PV_NONE) {
+                        const uint64_t e = w.mlist[v & ~SPL_PV_MISS];
+                        const uint32_t gp = (uint32_t)e, c = (uint32_t)(e >> 32);
+                        if (c <= EM_INLINE) {
+                            for (uint32_t r = 0; r < c; ++r) out[pos + r] = w.pool[gp + r];
+                        } else {
+                            uint32_t b = atomicAdd(&sm.n_big, 1u);
+                            sm.bigpos[b] = pos; sm.biggp[b] = gp; sm.bigcnt[b] = c;
+                        }
+                        pos += c;
+                    }
                 }
             }
         }
@@ -729,8 +798,8 @@ void spl_launch_encode_stage(const SplWork& w, int num_sms, cudaStream_t stream,
     mark(ctx, "k_probe");
     k_bpe<<<(uint32_t)num_sms * 6u, SPL_BPE_THREADS, 0, stream>>>(w);
     mark(ctx, "k_bpe");
-    k_tile_scan<<<1, 1024, 0, stream>>>(w);
-    mark(ctx, "k_tile_scan");
+    k_chunk_scan<<<1, 1024, 0, stream>>>(w);
+    mark(ctx, "k_chunk_scan");
     k_emit<<<w.n_tiles, SPL_THREADS, 0, stream>>>(w);
     mark(ctx, "k_emit");
 }

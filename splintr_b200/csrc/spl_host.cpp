@@ -130,12 +130,13 @@ uint64_t spl_host_hashL(const uint8_t* p, uint32_t len) {
 uint32_t spl_host_lookup_pair(const SplHostTables& t, uint32_t l, uint32_t r) {
     uint64_t key = spl_pair_key(l, r);
     uint32_t mask = (1u << t.pair_log2) - 1;
-    uint32_t h = spl_pair_hash(key, t.pair_log2);
+    uint32_t b = spl_pair_hash(key, t.pair_log2);
     for (;;) {
-        uint64_t e = t.pair[h];
-        if (e == SPL_PAIR_EMPTY) return SPL_RANK_NONE;
-        if ((e >> SPL_SYM_BITS) == key) return (uint32_t)(e & ((1u << SPL_SYM_BITS) - 1));
-        h = (h + 1) & mask;
+        const uint64_t* e = &t.pair[(size_t)b * SPL_PAIR_WAYS];
+        for (int k = 0; k < SPL_PAIR_WAYS; ++k)
+            if (e[k] != SPL_PAIR_EMPTY && (e[k] >> SPL_SYM_BITS) == key) return (uint32_t)(e[k] & ((1u << SPL_SYM_BITS) - 1));
+        if (e[SPL_PAIR_WAYS - 1] == SPL_PAIR_EMPTY) return SPL_RANK_NONE;
+        b = (b + 1) & mask;
     }
 }
 
@@ -143,12 +144,13 @@ uint32_t spl_host_lookup_piece(const SplHostTables& t, const uint8_t* p, uint32_
     if (len == 0) return SPL_RANK_NONE;
     if (len <= 8) {
         uint64_t k0 = load_le(p, len);
-        uint32_t mask = (1u << t.t8_log2) - 1, h = spl_hash8(k0, len, t.t8_log2);
+        uint32_t mask = (1u << t.t8_log2) - 1, b = spl_hash8((uint32_t)k0, (uint32_t)(k0 >> 32), len, t.t8_log2);
         for (;;) {
-            const SplKey8& e = t.t8[h];
-            if (e.len == 0) return SPL_RANK_NONE;
-            if (e.k0 == k0 && e.len == len) return e.id;
-            h = (h + 1) & mask;
+            const SplKey8* e = &t.t8[(size_t)b * SPL_T8_WAYS];
+            for (int k = 0; k < SPL_T8_WAYS; ++k)
+                if (e[k].len == len && e[k].k0 == k0) return e[k].id;
+            if (e[SPL_T8_WAYS - 1].len == 0) return SPL_RANK_NONE;
+            b = (b + 1) & mask;
         }
     }
     if (len <= 16) {
@@ -275,18 +277,32 @@ bool spl_build_tables(SplHostTables& t, const uint8_t* vocab, size_t vocab_len, 
         size_t n = kv.first.size();
         if (n <= 8) ++n8; else if (n <= 16) ++n16; else ++nl;
     }
-    t.t8_log2 = log2_for(n8);   t.t8.assign((size_t)1 << t.t8_log2, SplKey8{0, 0, 0});
+    t.t8_log2 = log2_for(n8) - 1;                       // buckets of two: as many slots as before
+    t.t8.assign(((size_t)1 << t.t8_log2) * SPL_T8_WAYS, SplKey8{0, 0, 0});
     t.t16_log2 = log2_for(n16); t.t16.assign((size_t)1 << t.t16_log2, SplKey16{0, 0, 0, 0, 0});
     t.tl_log2 = log2_for(nl);   t.tl.assign((size_t)1 << t.tl_log2, SplKeyL{0, 0, 0});
-    for (auto& kv : t.encoder) {
+    // in id order: the low-rank (frequent) tokens take the home buckets
+    std::vector<const std::pair<const std::string, uint32_t>*> by_rank;
+    by_rank.reserve(t.encoder.size());
+    for (auto& kv : t.encoder) by_rank.push_back(&kv);
+    std::sort(by_rank.begin(), by_rank.end(), [](auto* a, auto* b) { return a->second != b->second ? a->second < b->second : a->first < b->first; });
+    t.t8_displaced = 0;
+    for (auto* kvp : by_rank) {
+        auto& kv = *kvp;
         const uint8_t* p = (const uint8_t*)kv.first.data();
         uint32_t n = (uint32_t)kv.first.size();
         // two keys can map to one id only if ids collide in the file; tok_off then holds one of them
         if (n <= 8) {
             uint64_t k0 = load_le(p, n);
-            uint32_t mask = (1u << t.t8_log2) - 1, h = spl_hash8(k0, n, t.t8_log2);
-            while (t.t8[h].len) h = (h + 1) & mask;
-            t.t8[h] = SplKey8{k0, kv.second, n};
+            uint32_t mask = (1u << t.t8_log2) - 1, b = spl_hash8((uint32_t)k0, (uint32_t)(k0 >> 32), n, t.t8_log2);
+            bool home = true;
+            for (;; b = (b + 1) & mask, home = false) {
+                SplKey8* e = &t.t8[(size_t)b * SPL_T8_WAYS];
+                int k = 0;
+                while (k < SPL_T8_WAYS && e[k].len) ++k;
+                if (k < SPL_T8_WAYS) { e[k] = SplKey8{k0, kv.second, n}; break; }
+            }
+            if (!home) ++t.t8_displaced;
         } else if (n <= 16) {
             uint64_t k0 = load_le(p, 8), k1 = load_le(p + 8, n - 8);
             uint32_t mask = (1u << t.t16_log2) - 1, h = spl_hash16(k0, k1, n, t.t16_log2);
@@ -334,13 +350,25 @@ bool spl_build_tables(SplHostTables& t, const uint8_t* vocab, size_t vocab_len, 
             }
         }
         t.n_pairs = ents.size();
-        t.pair_log2 = log2_for(ents.size());
-        t.pair.assign((size_t)1 << t.pair_log2, SPL_PAIR_EMPTY);
+        t.pair_log2 = log2_for(ents.size()) - 1;          // buckets of four at load <= 0.25: a probe rarely leaves its home bucket
+        t.pair.assign(((size_t)1 << t.pair_log2) * SPL_PAIR_WAYS, SPL_PAIR_EMPTY);
         uint32_t mask = (1u << t.pair_log2) - 1;
+        // low merged rank first: the pairs the merge loop asks for most sit in their home bucket
+        std::sort(ents.begin(), ents.end(), [](uint64_t a, uint64_t b) {
+            uint64_t ma = a & ((1u << SPL_SYM_BITS) - 1), mb = b & ((1u << SPL_SYM_BITS) - 1);
+            return ma != mb ? ma < mb : a < b;
+        });
+        t.pair_displaced = 0;
         for (uint64_t e : ents) {
-            uint32_t h = spl_pair_hash(e >> SPL_SYM_BITS, t.pair_log2);
-            while (t.pair[h] != SPL_PAIR_EMPTY) h = (h + 1) & mask;
-            t.pair[h] = e;
+            uint32_t b = spl_pair_hash(e >> SPL_SYM_BITS, t.pair_log2);
+            bool home = true;
+            for (;; b = (b + 1) & mask, home = false) {
+                uint64_t* s = &t.pair[(size_t)b * SPL_PAIR_WAYS];
+                int k = 0;
+                while (k < SPL_PAIR_WAYS && s[k] != SPL_PAIR_EMPTY) ++k;
+                if (k < SPL_PAIR_WAYS) { s[k] = e; break; }
+            }
+            if (!home) ++t.pair_displaced;
         }
     }
 

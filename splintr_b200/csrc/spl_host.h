@@ -25,6 +25,7 @@ struct SplHostTables {
     std::vector<uint32_t> tok_off;
     uint32_t n_ids = 0, max_key_len = 0;
     std::vector<uint64_t> pair; uint32_t pair_log2 = 0; size_t n_pairs = 0;
+    size_t t8_displaced = 0, pair_displaced = 0;         // keys that are not in their home bucket
     uint32_t byte_sym[256];
     std::vector<uint8_t>  sp_bytes;
     std::vector<uint32_t> sp_off, sp_id;

@@ -16,6 +16,7 @@
 // encode stage (spl_encode.cu)
 #define SPL_PROBE_HALO  128u          // bytes staged beyond a tile for the whole-piece probe (bundled keys are <= 128 B)
 #define SPL_PROBE_WIN   (SPL_TILE + SPL_PROBE_HALO)
+#define SPL_CHUNK_TILES 32u           // tiles per chunk of the two-level id-count prefix
 #define SPL_BPE_THREADS 128           // k_bpe block size
 #define SPL_SHORT_MAX   32u           // piece bytes merged by one thread
 #define SPL_WARP_MAX    256u          // ... by one warp, four pieces per block
@@ -43,7 +44,8 @@ struct SplWork {
     uint32_t*       tile_first_doc;   // [n_tiles+1]
     uint32_t*       tile_np;          // [n_tiles] pieces that start in the tile (k_probe)
     int32_t*        tile_extra;       // [n_tiles] ids minus pieces (k_probe: dropped bytes, k_bpe: merged pieces)
-    uint64_t*       tile_state;       // [n_tiles] exclusive prefix of the tiles' id counts (k_tile_scan)
+    int32_t*        chunk_cnt;        // [n_tiles / SPL_CHUNK_TILES + 1] ids of the chunk's tiles (kept by k_probe and k_bpe)
+    uint64_t*       chunk_state;      // [n_tiles / SPL_CHUNK_TILES + 1] exclusive prefix of chunk_cnt (k_chunk_scan)
     uint32_t*       pv;               // [n_tiles * SPL_TILE] per-piece value, tile t at pv[t * SPL_TILE ..]
     uint32_t*       pool;             // [N] ids of the pieces that went through the merge loop, at the piece's byte position
     uint64_t*       mlist;            // miss list: [0, ml_r0) short pieces bottom-up / warp pieces top-down,

@@ -112,6 +112,7 @@ void ht_stats(void* h, uint64_t* out) {
     SplHostTables* t = (SplHostTables*)h;
     out[0] = t->encoder.size(); out[1] = t->n_pairs; out[2] = t->t8_log2; out[3] = t->t16_log2;
     out[4] = t->tl_log2; out[5] = t->pair_log2; out[6] = t->max_key_len; out[7] = t->specials_unambiguous;
+    out[8] = t->t8_displaced; out[9] = t->pair_displaced;
 }
 
 // encode one segment (no special handling); returns token count or -1

@@ -98,9 +98,10 @@ class HostTables:
             raise ValueError(err.value.decode())
 
     def stats(self):
-        out = np.zeros(8, dtype=np.uint64)
+        out = np.zeros(10, dtype=np.uint64)
         load().ht_stats(self.h, out.ctypes.data)
-        return dict(zip(["n_keys", "n_pairs", "t8_log2", "t16_log2", "tl_log2", "pair_log2", "max_key_len", "unambiguous"], out.tolist()))
+        return dict(zip(["n_keys", "n_pairs", "t8_log2", "t16_log2", "tl_log2", "pair_log2", "max_key_len", "unambiguous",
+                         "t8_displaced", "pair_displaced"], out.tolist()))
 
     def encode(self, data: bytes):
         ids = np.zeros(len(data) + 1, dtype=np.uint32)
