@@ -54,7 +54,7 @@ struct DevCtx {
     void* table_blob = nullptr;
     SplTables* d_tables = nullptr;
     DevBuf text, doc_off, ids, out_off;          // spl_encode_batch: the shard's buffers
-    DevBuf zero, tfd, tnp, tstate, pv, pool, mlist, fbl, huge;   // per-pass workspace (zero: everything that starts cleared)
+    DevBuf zero, tstate, pv, pool, mlist, fbl, huge;   // per-pass workspace (zero: everything that starts cleared)
     size_t huge_words = 0;
     SplKernelProfile prof;
     bool prof_ready = false;
@@ -140,7 +140,7 @@ int upload_tables(spl_tokenizer* tk, DevCtx& dc) {
 
 void destroy_ctx(DevCtx& dc) {
     cudaSetDevice(dc.device);
-    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.ids, &dc.out_off, &dc.zero, &dc.tfd, &dc.tnp, &dc.tstate, &dc.pv, &dc.pool, &dc.mlist, &dc.fbl, &dc.huge})
+    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.ids, &dc.out_off, &dc.zero, &dc.tstate, &dc.pv, &dc.pool, &dc.mlist, &dc.fbl, &dc.huge})
         b->release();
     if (dc.table_blob) cudaFree(dc.table_blob);
     for (auto& e : dc.ev) if (e) cudaEventDestroy(e);
@@ -154,7 +154,7 @@ void destroy_ctx(DevCtx& dc) {
 // limits of one device shard: 32-bit positions inside the kernels
 const uint64_t kMaxShardBytes = 0xFFFFFFFFull - 4ull * SPL_WIN;
 
-// layout of the zero-initialised region: counters | chunk_cnt | tile_extra | hard | pstart | spec
+// layout of the zero-initialised region: counters | chunk_cnt | tinfo | hard | pstart | spec
 struct ZeroLayout { size_t words, n_tiles, off_chunk, off_extra, off_hard, off_pstart, off_spec, total; };
 ZeroLayout zero_layout(uint64_t N, bool with_special) {
     ZeroLayout z;
@@ -162,7 +162,7 @@ ZeroLayout zero_layout(uint64_t N, bool with_special) {
     z.n_tiles = (size_t)(N / SPL_TILE) + 1;
     z.off_chunk = 256;
     z.off_extra = align_up(z.off_chunk + (z.n_tiles / SPL_CHUNK_TILES + 2) * 4, 256);
-    z.off_hard = align_up(z.off_extra + z.n_tiles * 4, 256);
+    z.off_hard = align_up(z.off_extra + (z.n_tiles + 2) * sizeof(SplTileInfo), 256);
     z.off_pstart = align_up(z.off_hard + z.words * 4, 256);
     z.off_spec = align_up(z.off_pstart + z.words * 4, 256);
     z.total = with_special ? align_up(z.off_spec + z.words * 4, 256) : z.off_spec;
@@ -188,8 +188,6 @@ int reserve_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
     const MissLayout m = miss_layout(N);
     int rc;
     if ((rc = dc.zero.ensure(z.total, tk->err))) return rc;
-    if ((rc = dc.tfd.ensure((z.n_tiles + 2) * 4, tk->err))) return rc;
-    if ((rc = dc.tnp.ensure(z.n_tiles * 4, tk->err))) return rc;
     if ((rc = dc.tstate.ensure((z.n_tiles / SPL_CHUNK_TILES + 2) * 8, tk->err))) return rc;
     if ((rc = dc.pv.ensure(z.n_tiles * SPL_TILE * 4, tk->err))) return rc;
     if ((rc = dc.pool.ensure((size_t)(N + 64) * 4, tk->err))) return rc;
@@ -217,13 +215,11 @@ int prepare_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
     w.n_tiles = (uint32_t)z.n_tiles;
     w.counters = (uint32_t*)zb;
     w.chunk_cnt = (int32_t*)(zb + z.off_chunk);
-    w.tile_extra = (int32_t*)(zb + z.off_extra);
+    w.tinfo = (SplTileInfo*)(zb + z.off_extra);
     w.hard = (uint32_t*)(zb + z.off_hard);
     w.pstart = (uint32_t*)(zb + z.off_pstart);
     w.spec = with_special ? (uint32_t*)(zb + z.off_spec) : nullptr;
     w.bitmap_words = z.words;
-    w.tile_first_doc = (uint32_t*)dc.tfd.p;
-    w.tile_np = (uint32_t*)dc.tnp.p;
     w.chunk_state = (uint64_t*)dc.tstate.p;
     w.pv = (uint32_t*)dc.pv.p;
     w.pool = (uint32_t*)dc.pool.p;

@@ -95,32 +95,17 @@ struct ProbeSmem {
     uint32_t pb[PB_WORDS];                    // piece-start bits
     uint32_t spw[SPL_TILE / 32];              // special-span bits of the tile (with_special)
     uint16_t plist[SPL_TILE + 2];             // window positions of the tile's piece starts, in order (+ end of the last piece)
-    uint16_t slow[SPL_TILE];                  // pieces the one-sector probe did not settle
-    uint16_t mloc[SPL_TILE];                  // missed pieces: thread class from the bottom, warp class from the top
+    uint16_t slow[SPL_TILE];                  // pieces the one-sector probe did not settle (each warp: its own range)
+    uint16_t mloc[SPL_TILE];                  // missed pieces: thread class from the bottom of the warp's range, warp class from its top
     uint32_t wtot[SPL_THREADS / 32];
-    uint32_t n_slow, n_short, n_warp, g_short, g_warp;
     uint32_t last_end;                        // window position of the end of the tile's last piece
 };
-
-// append j to a shared list, one shared atomic per warp.  Every lane of the warp must call it.
-__device__ __forceinline__ void warp_push(bool pred, uint32_t* counter, uint16_t* list, uint32_t j, bool top_down) {
-    const uint32_t lane = threadIdx.x & 31u;
-    uint32_t bal = __ballot_sync(FULL, pred);
-    if (bal) {
-        uint32_t leader = __ffs(bal) - 1, b0 = 0;
-        if (lane == leader) b0 = atomicAdd(counter, (uint32_t)__popc(bal));
-        b0 = __shfl_sync(FULL, b0, leader);
-        if (pred) {
-            uint32_t k = b0 + __popc(bal & ((1u << lane) - 1u));
-            list[top_down ? SPL_TILE - 1 - k : k] = (uint16_t)j;
-        }
-    }
-}
 
 __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
     __shared__ ProbeSmem sm;
     const SplTables* T = w.T;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t N = w.N, Nup = (N + 15u) & ~15u;
     const uint32_t tile = blockIdx.x, tile0 = tile * SPL_TILE;
     const SplKey8* __restrict__ t8 = T->t8;
@@ -135,7 +120,6 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
     }
     for (uint32_t v = tid; v < PB_WORDS; v += SPL_THREADS) sm.pb[v] = __ldg(w.pstart + (tile0 >> 5) + v);
     if (w.with_special && tid < SPL_TILE / 32) sm.spw[tid] = __ldg(w.spec + (tile0 >> 5) + tid);
-    if (tid == 0) { sm.n_slow = 0; sm.n_short = 0; sm.n_warp = 0; }
     __syncthreads();
 
     // ---- piece list: positions of the piece starts of this tile, in order ------------------
@@ -167,16 +151,22 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
         if (P && e >= PB_BITS) e = g_next_bit(w.pstart, tile0 + PB_BITS, N + 1) - tile0;    // the last piece leaves the staged bits
         sm.last_end = e;
         sm.plist[P] = (uint16_t)(e >= PB_BITS ? 0xFFFFu : e);      // 0xFFFF: see last_end
-        w.tile_np[tile] = P;
+        w.tinfo[tile].np = P;
         if (P) atomicAdd(&w.chunk_cnt[tile / SPL_CHUNK_TILES], (int32_t)P);
     }
     __syncthreads();
 
-    // ---- hot loop, one thread per piece: pieces of up to 8 bytes, one sector of the bucketed table -------------
+    // From here on every warp works alone on its own range of pieces [jlo, jhi): no block barrier, a warp with
+    // slow pieces does not hold the others back.
+    const uint32_t per = (((P + SPL_THREADS / 32 - 1) / (SPL_THREADS / 32)) + 31u) & ~31u;
+    const uint32_t jlo = warp * per < P ? warp * per : P, jhi = jlo + per < P ? jlo + per : P;
     const uint32_t pvbase = tile * SPL_TILE;
-    for (uint32_t j0 = 0; j0 < P; j0 += SPL_THREADS) {
-        const uint32_t j = j0 + tid;
-        const bool valid = j < P;
+
+    // ---- hot loop, one thread per piece: pieces of up to 8 bytes, one sector of the bucketed table -------------
+    uint32_t n_slow = 0;
+    for (uint32_t j0 = jlo; j0 < jhi; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        const bool valid = j < jhi;
         uint32_t s = 0, len = 0;
         if (valid) { s = sm.plist[j]; len = sm.plist[j + 1] - s; }      // end 0xFFFF: len is large, not probed here
         bool fast = valid && len <= 8;
@@ -196,17 +186,20 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
             found = h0 || h1;
             if (found) w.pv[pvbase + j] = h0 ? v0.z : v1.z;
         }
-        warp_push(valid && !found, &sm.n_slow, sm.slow, j, false);
+        const bool sl = valid && !found;
+        const uint32_t bal = __ballot_sync(FULL, sl);
+        if (sl) sm.slow[jlo + n_slow + __popc(bal & lt_mask)] = (uint16_t)j;
+        n_slow += __popc(bal);
     }
-    __syncthreads();
+    __syncwarp();
 
     // ---- the rest: specials, longer pieces, second buckets, misses ------------------------------------------
-    const uint32_t n_slow = sm.n_slow;
-    for (uint32_t i0 = 0; i0 < n_slow; i0 += SPL_THREADS) {
-        const uint32_t i = i0 + tid;
+    uint32_t n_short = 0, n_warp = 0;
+    for (uint32_t i0 = 0; i0 < n_slow; i0 += 32) {
+        const uint32_t i = i0 + lane;
         uint32_t cls = 0, j = 0;                               // 0 settled, 1 thread class, 2 warp class, 3 big, 4 huge
         if (i < n_slow) {
-            j = sm.slow[i];
+            j = sm.slow[jlo + i];
             const uint32_t s = sm.plist[j];
             uint32_t e = sm.plist[j + 1];
             if (e == 0xFFFFu) e = sm.last_end;
@@ -235,7 +228,7 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
             }
             if (cls == 0) {
                 w.pv[pvbase + j] = val;
-                if (val == SPL_PV_NONE) { atomicAdd(&w.tile_extra[tile], -1); atomicAdd(&w.chunk_cnt[tile / SPL_CHUNK_TILES], -1); }
+                if (val == SPL_PV_NONE) { atomicAdd(&w.tinfo[tile].extra, -1); atomicAdd(&w.chunk_cnt[tile / SPL_CHUNK_TILES], -1); }
             } else if (cls >= 3) {                             // rare: straight to the global list of its class
                 uint32_t midx = cls == 3 ? w.ml_r0 + atomicAdd(&w.counters[SPL_CTR_BIG], 1u)
                                          : w.ml_r1 + atomicAdd(&w.counters[SPL_CTR_HUGE], 1u);
@@ -243,27 +236,32 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
                 w.pv[pvbase + j] = SPL_PV_MISS | midx;
             }
         }
-        warp_push(cls == 1, &sm.n_short, sm.mloc, j, false);
-        warp_push(cls == 2, &sm.n_warp, sm.mloc, j, true);
+        uint32_t bal = __ballot_sync(FULL, cls == 1);
+        if (cls == 1) sm.mloc[jlo + n_short + __popc(bal & lt_mask)] = (uint16_t)j;
+        n_short += __popc(bal);
+        bal = __ballot_sync(FULL, cls == 2);
+        if (cls == 2) sm.mloc[jhi - 1 - (n_warp + __popc(bal & lt_mask))] = (uint16_t)j;
+        n_warp += __popc(bal);
     }
-    __syncthreads();
+    __syncwarp();
 
-    // ---- publish the tile's misses ------------------------------------------------------------
-    const uint32_t ns = sm.n_short, nw = sm.n_warp;
-    if (ns | nw) {
-        if (tid == 0) {
-            if (ns) sm.g_short = atomicAdd(&w.counters[SPL_CTR_SHORT], ns);
-            if (nw) sm.g_warp = atomicAdd(&w.counters[SPL_CTR_WARP], nw);
+    // ---- publish the warp's misses ------------------------------------------------------------
+    if (n_short | n_warp) {
+        uint32_t g_short = 0, g_warp = 0;
+        if (lane == 0) {
+            if (n_short) g_short = atomicAdd(&w.counters[SPL_CTR_SHORT], n_short);
+            if (n_warp) g_warp = atomicAdd(&w.counters[SPL_CTR_WARP], n_warp);
         }
-        __syncthreads();
-        for (uint32_t i = tid; i < ns; i += SPL_THREADS) {
-            uint32_t j = sm.mloc[i], s = sm.plist[j], e = sm.plist[j + 1], midx = sm.g_short + i;
+        g_short = __shfl_sync(FULL, g_short, 0);
+        g_warp = __shfl_sync(FULL, g_warp, 0);
+        for (uint32_t i = lane; i < n_short; i += 32) {
+            uint32_t j = sm.mloc[jlo + i], s = sm.plist[j], e = sm.plist[j + 1], midx = g_short + i;
             if (e == 0xFFFFu) e = sm.last_end;
             w.mlist[midx] = ml_entry(tile0 + s, e - s, j);
             w.pv[pvbase + j] = SPL_PV_MISS | midx;
         }
-        for (uint32_t i = tid; i < nw; i += SPL_THREADS) {
-            uint32_t j = sm.mloc[SPL_TILE - 1 - i], s = sm.plist[j], e = sm.plist[j + 1], midx = w.ml_r0 - 1 - (sm.g_warp + i);
+        for (uint32_t i = lane; i < n_warp; i += 32) {
+            uint32_t j = sm.mloc[jhi - 1 - i], s = sm.plist[j], e = sm.plist[j + 1], midx = w.ml_r0 - 1 - (g_warp + i);
             if (e == 0xFFFFu) e = sm.last_end;
             w.mlist[midx] = ml_entry(tile0 + s, e - s, j);
             w.pv[pvbase + j] = SPL_PV_MISS | midx;
@@ -294,7 +292,7 @@ union BpeSmem {
 __device__ __forceinline__ void bpe_finish(const SplWork& w, uint64_t* slot, uint32_t gpos, uint32_t cnt) {
     *slot = (uint64_t)gpos | ((uint64_t)cnt << 32);
     if (cnt != 1u) {
-        atomicAdd(&w.tile_extra[gpos / SPL_TILE], (int32_t)cnt - 1);
+        atomicAdd(&w.tinfo[gpos / SPL_TILE].extra, (int32_t)cnt - 1);
         atomicAdd(&w.chunk_cnt[gpos / (SPL_TILE * SPL_CHUNK_TILES)], (int32_t)cnt - 1);
     }
 }
@@ -652,12 +650,12 @@ __global__ void __launch_bounds__(1024) k_chunk_scan(SplWork w) {
 #define EM_BIGCAP (SPL_TILE / (EM_INLINE + 1u) + 1u) // pieces of a tile that can have more ids than that
 
 struct EmitSmem {
-    uint32_t spos[SPL_TILE + 4];                     // ids of the tile before piece j; spos[P] = ids of the tile
+    __align__(16) uint32_t spos[SPL_TILE + 4];       // ids of the warp's round before piece j (see wtot)
     uint32_t pbw[SPL_TILE / 32];
     uint32_t wpre[SPL_TILE / 32];
-    uint32_t wtot[EM_ROUNDS * EM_WARPS];
+    uint32_t wtot[EM_ROUNDS * EM_WARPS];             // ids of the tile before each (round, warp)
     uint32_t bigpos[EM_BIGCAP], biggp[EM_BIGCAP], bigcnt[EM_BIGCAP];
-    uint32_t n_big;
+    uint32_t n_big, total;
     uint64_t prefix;
 };
 
@@ -668,46 +666,48 @@ __device__ __forceinline__ uint32_t emit_count(const SplWork& w, uint32_t v, boo
     return (uint32_t)(w.mlist[v & ~SPL_PV_MISS] >> 32);
 }
 
-__global__ void __launch_bounds__(SPL_THREADS) k_emit(SplWork w) {
+__global__ void __launch_bounds__(SPL_THREADS, 8) k_emit(SplWork w) {
     __shared__ EmitSmem sm;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t tile = blockIdx.x, tile0 = tile * SPL_TILE;
-    const uint32_t P = w.tile_np[tile];
     const uint32_t* __restrict__ pv = w.pv + tile0;
-    const uint32_t d0 = __ldg(w.tile_first_doc + tile), d1 = __ldg(w.tile_first_doc + tile + 1);
-    const uint32_t rounds = (P + SPL_THREADS * 4 - 1) / (SPL_THREADS * 4);
 
-    if (tid == 0) sm.n_big = 0;
-    if (d1 > d0 && tid < SPL_TILE / 32) sm.pbw[tid] = __ldg(w.pstart + (tile0 >> 5) + tid);
+    // everything the block needs to know comes from one round of independent loads
+    const uint4 ti = __ldg(reinterpret_cast<const uint4*>(w.tinfo + tile));          // {np, extra, first_doc, -}
+    const uint32_t d1 = __ldg(&w.tinfo[tile + 1].first_doc);
+    uint4 v_first = make_uint4(SPL_PV_NONE, SPL_PV_NONE, SPL_PV_NONE, SPL_PV_NONE);
+    if (tid < 128) v_first = __ldg(reinterpret_cast<const uint4*>(pv + tid * 4u));   // the first 512 pieces: every ordinary tile has them
+    const uint32_t pbw_mine = tid < SPL_TILE / 32 ? __ldg(w.pstart + (tile0 >> 5) + tid) : 0u;
     if (warp == EM_WARPS - 1) {
         // ids before this tile: the chunk's prefix plus the tiles of the chunk in front of this one
         const uint32_t t = (tile & ~(SPL_CHUNK_TILES - 1u)) + lane;
-        uint32_t c = t < tile ? (uint32_t)((int32_t)w.tile_np[t] + w.tile_extra[t]) : 0u;
+        uint32_t c = 0;
+        if (t < tile) { const uint4 x = __ldg(reinterpret_cast<const uint4*>(w.tinfo + t)); c = x.x + x.y; }
         c = __reduce_add_sync(FULL, c);
         if (lane == 0) sm.prefix = w.chunk_state[tile / SPL_CHUNK_TILES] + c;
     }
+    const uint32_t P = ti.x, d0 = ti.z;
+    const uint32_t rounds = (P + SPL_THREADS * 4 - 1) / (SPL_THREADS * 4);
+    if (tid == 0) sm.n_big = 0;
+    if (tid < SPL_TILE / 32) sm.pbw[tid] = pbw_mine;
 
     // ---- pass 1: id count of every piece, warp-level prefixes ---------------------------------------
-    uint4 vals[EM_ROUNDS];
-    uint32_t ex[EM_ROUNDS];
+    for (uint32_t k = 0; k < rounds; ++k) {
+        const uint32_t j4 = (k * SPL_THREADS + tid) * 4u;
+        uint4 v = v_first;
+        if ((k > 0 || tid >= 128) && j4 < P) v = __ldg(reinterpret_cast<const uint4*>(pv + j4));
+        const uint32_t c0 = emit_count(w, v.x, j4 < P), c1 = emit_count(w, v.y, j4 + 1 < P),
+                       c2 = emit_count(w, v.z, j4 + 2 < P), c3 = emit_count(w, v.w, j4 + 3 < P);
+        const uint32_t c = c0 + c1 + c2 + c3;
+        uint32_t incl = c;
 #pragma unroll
-    for (uint32_t k = 0; k < EM_ROUNDS; ++k) {
-        if (k < rounds) {
-            const uint32_t j4 = (k * SPL_THREADS + tid) * 4u;
-            uint4 v = make_uint4(SPL_PV_NONE, SPL_PV_NONE, SPL_PV_NONE, SPL_PV_NONE);
-            if (j4 < P) v = __ldg(reinterpret_cast<const uint4*>(pv + j4));
-            vals[k] = v;
-            const uint32_t c = emit_count(w, v.x, j4 < P) + emit_count(w, v.y, j4 + 1 < P) +
-                               emit_count(w, v.z, j4 + 2 < P) + emit_count(w, v.w, j4 + 3 < P);
-            uint32_t incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t = __shfl_up_sync(FULL, incl, o);
-                if (lane >= (uint32_t)o) incl += t;
-            }
-            ex[k] = incl - c;
-            if (lane == 31) sm.wtot[k * EM_WARPS + warp] = incl;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= (uint32_t)o) incl += t;
         }
+        const uint32_t ex = incl - c;
+        *reinterpret_cast<uint4*>(&sm.spos[j4]) = make_uint4(ex, ex + c0, ex + c0 + c1, ex + c0 + c1 + c2);
+        if (lane == 31) sm.wtot[k * EM_WARPS + warp] = incl;
     }
     __syncthreads();
     if (warp == 0) {
@@ -719,7 +719,7 @@ __global__ void __launch_bounds__(SPL_THREADS) k_emit(SplWork w) {
             if (lane >= (uint32_t)o) incl += t;
         }
         sm.wtot[lane] = incl - x;
-        if (lane == 31) sm.spos[P] = incl;                     // ids of the whole tile
+        if (lane == 31) sm.total = incl;                       // ids of the whole tile
         if (d1 > d0) {
             uint32_t loc[4], run = 0;
 #pragma unroll
@@ -740,20 +740,20 @@ __global__ void __launch_bounds__(SPL_THREADS) k_emit(SplWork w) {
     // ---- pass 2: ids to their place ----------------------------------------------------------------------
     const uint64_t prefix = sm.prefix;
     uint32_t* __restrict__ out = w.ids + prefix;
-#pragma unroll
-    for (uint32_t k = 0; k < EM_ROUNDS; ++k) {
-        if (k < rounds) {
-            const uint32_t j4 = (k * SPL_THREADS + tid) * 4u;
-            uint32_t pos = ex[k] + sm.wtot[k * EM_WARPS + warp];
-            const uint32_t vv[4] = {vals[k].x, vals[k].y, vals[k].z, vals[k].w};
+    for (uint32_t k = 0; k < rounds; ++k) {
+        const uint32_t j4 = (k * SPL_THREADS + tid) * 4u;
+        if (j4 < P) {
+            uint4 v = v_first;
+            if (k > 0 || tid >= 128) v = __ldg(reinterpret_cast<const uint4*>(pv + j4));
+            uint32_t pos = sm.spos[j4] + sm.wtot[k * EM_WARPS + warp];
+            const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (uint32_t q = 0; q < 4; ++q) {
                 if (j4 + q < P) {
-                    const uint32_t v = vv[q];
-                    sm.spos[j4 + q] = pos;
-                    if (v < SPL_PV_MISS) out[pos++] = v;
-                    else if (v != SPL_PV_NONE) {
-                        const uint64_t e = w.mlist[v & ~SPL_PV_MISS];
+                    const uint32_t x = vv[q];
+                    if (x < SPL_PV_MISS) out[pos++] = x;
+                    else if (x != SPL_PV_NONE) {
+                        const uint64_t e = w.mlist[x & ~SPL_PV_MISS];
                         const uint32_t gp = (uint32_t)e, c = (uint32_t)(e >> 32);
                         if (c <= EM_INLINE) {
                             for (uint32_t r = 0; r < c; ++r) out[pos + r] = w.pool[gp + r];
@@ -767,7 +767,7 @@ __global__ void __launch_bounds__(SPL_THREADS) k_emit(SplWork w) {
             }
         }
     }
-    __syncthreads();
+    if (d1 > d0 || P > 0) __syncthreads();
     {
         const uint32_t nb = sm.n_big;
         for (uint32_t b = 0; b < nb; ++b) {
@@ -778,9 +778,10 @@ __global__ void __launch_bounds__(SPL_THREADS) k_emit(SplWork w) {
 
     // ---- output offset of every document that starts in this tile ----------------------------------------
     for (uint32_t d = d0 + tid; d < d1; d += SPL_THREADS) {
-        uint32_t x = (uint32_t)(w.doc_off[d] - w.off_base - tile0);
-        uint32_t pi = sm.wpre[x >> 5] + __popc(sm.pbw[x >> 5] & ((1u << (x & 31)) - 1u));
-        w.out_off[d] = prefix + sm.spos[pi];
+        const uint32_t x = (uint32_t)(w.doc_off[d] - w.off_base - tile0);
+        const uint32_t pi = sm.wpre[x >> 5] + __popc(sm.pbw[x >> 5] & ((1u << (x & 31)) - 1u));
+        const uint32_t rel = pi >= P ? sm.total : sm.spos[pi] + sm.wtot[(pi / (SPL_THREADS * 4u)) * EM_WARPS + ((pi / 128u) & (EM_WARPS - 1u))];
+        w.out_off[d] = prefix + rel;
     }
 }
 

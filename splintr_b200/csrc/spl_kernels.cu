@@ -26,9 +26,9 @@ __global__ void k_mark_docs(SplWork w) {
     uint32_t p = (uint32_t)s;
     atomicOr(&w.hard[p >> 5], 1u << (p & 31));
     uint32_t t_lo = d ? (uint32_t)(prev / SPL_TILE) + 1 : 0, t_hi = p / SPL_TILE;
-    for (uint32_t t = t_lo; t <= t_hi; ++t) w.tile_first_doc[t] = d;
+    for (uint32_t t = t_lo; t <= t_hi; ++t) w.tinfo[t].first_doc = d;
     if (d == w.n_docs) {
-        w.tile_first_doc[w.n_tiles] = w.n_docs + 1;
+        w.tinfo[w.n_tiles].first_doc = w.n_docs + 1;
         atomicOr(&w.pstart[p >> 5], 1u << (p & 31));            // sentinel piece start at N
     }
 }

@@ -29,6 +29,14 @@
 // miss-list entry after  k_bpe:  gpos:32 | id count:32         (ids at pool[gpos ..])
 #define SPL_ML_LEN_SAT 0xFFFFFu
 
+// one record per tile, so that k_emit learns everything about its tile (and its chunk) from one line
+struct SplTileInfo {
+    uint32_t np;          // pieces that start in the tile (k_probe)
+    int32_t  extra;       // ids minus pieces (k_probe: dropped bytes, k_bpe: merged pieces)
+    uint32_t first_doc;   // first document that starts at or after the tile (k_mark_docs); [n_tiles] = n_docs + 1
+    uint32_t pad;
+};
+
 // per-call device workspace (all pointers on the current device)
 struct SplWork {
     const uint8_t*  text;        // [N], 16-byte aligned, readable up to N rounded up to 16
@@ -41,9 +49,7 @@ struct SplWork {
     uint32_t*       spec;        // bitmap words: bytes inside special-token spans (with_special only)
     uint32_t*       pstart;      // bitmap words: piece starts (incl. sentinel bit N)
     size_t          bitmap_words;
-    uint32_t*       tile_first_doc;   // [n_tiles+1]
-    uint32_t*       tile_np;          // [n_tiles] pieces that start in the tile (k_probe)
-    int32_t*        tile_extra;       // [n_tiles] ids minus pieces (k_probe: dropped bytes, k_bpe: merged pieces)
+    SplTileInfo*    tinfo;            // [n_tiles+1] per-tile record (zero-initialised)
     int32_t*        chunk_cnt;        // [n_tiles / SPL_CHUNK_TILES + 1] ids of the chunk's tiles (kept by k_probe and k_bpe)
     uint64_t*       chunk_state;      // [n_tiles / SPL_CHUNK_TILES + 1] exclusive prefix of chunk_cnt (k_chunk_scan)
     uint32_t*       pv;               // [n_tiles * SPL_TILE] per-piece value, tile t at pv[t * SPL_TILE ..]
