@@ -220,8 +220,10 @@ def main():
         if world > 1:                                                       # the path's only exchange step
             dist.all_gather_into_tensor(counts, d_out[n_docs:n_docs + 1])
 
+    no_flush = os.environ.get("SPL_BENCH_NO_FLUSH") == "1"     # diagnostics only: the reported runs always flush
     for _ in range(args.warmup):
-        flush.zero_()
+        if not no_flush:
+            flush.zero_()
         step_device()
     barrier()
     tok.set_profiling(True)
@@ -232,7 +234,8 @@ def main():
     ktimes = {}
     barrier()
     for i in range(args.steps):
-        flush.zero_()
+        if not no_flush:
+            flush.zero_()
         ev[i][0].record()
         step_device()
         ev[i][1].record()
@@ -323,7 +326,7 @@ def main():
                 "ms_per_step": dev_ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8/u32 integer", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "docs_per_gpu": n_docs, "bytes_per_gpu": n_bytes, "tokens_per_gpu": n_tok,
-                           "parallelism": f"doc-sharded dp{world}", "l2": "flushed between steps (512 MiB memset)",
+                           "parallelism": f"doc-sharded dp{world}", "l2": "NOT flushed (diagnostic run)" if no_flush else "flushed between steps (512 MiB memset)",
                            "timing": "per-step CUDA events on the launching stream, max over ranks"},
                 "roofline": roof, "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_stats["h2d"], "d2h_bytes_per_step": e2e_stats["d2h"],

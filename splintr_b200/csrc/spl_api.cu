@@ -2,6 +2,7 @@
 // per-call workspace, host<->device staging, document sharding over the handle's devices.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -259,7 +260,7 @@ PinnedBuf take_pinned(spl_tokenizer* tk, size_t bytes) {
     }
     PinnedBuf b{nullptr, 0};
     size_t want = bytes + bytes / 8;
-    if (cudaHostAlloc(&b.p, want, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); b.p = nullptr; return b; }
+    if (cudaHostAlloc(&b.p, want, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); b.p = nullptr; return b; }
     b.cap = want;
     return b;
 }
@@ -439,7 +440,8 @@ struct Chunk {
     size_t text_off;            // 16-byte aligned offset of the chunk inside the device text buffer
     size_t ids_off;             // u32 index of the chunk's id region inside the device id buffer
     size_t ev;                  // first of its 4 events in DevCtx::pipe_ev (copied in, kernels start, done, ids copied out)
-    volatile uint64_t* meta;    // pinned: [0] id count, [1..2] device counters
+    volatile uint64_t* meta;    // pinned, mapped: [0] id count, [1] error flags | huge-pool need << 32
+    uint64_t* d_meta;           // the same memory as the device sees it
     uint64_t n_tokens;
     uint64_t tok_base;          // position of its ids in the result
 };
@@ -448,6 +450,9 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
                      uint32_t flags, spl_result** out) {
     if (!tk || !out) return SPL_ERR_INVALID_ARG;
     *out = nullptr;
+    const auto h_t0 = std::chrono::steady_clock::now();
+    auto h_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h_t0).count(); };
+    double h_plan = 0, h_reserved = 0, h_enq = 0, h_drained = 0, h_synced = 0;
     if (!offsets || offsets[0] != 0) { tk->err = "offsets must start at 0"; return SPL_ERR_INVALID_ARG; }
     const uint64_t N = offsets[n_docs];
     if (N && !bytes) { tk->err = "null bytes"; return SPL_ERR_INVALID_ARG; }
@@ -470,7 +475,7 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
     std::vector<size_t> text_need(G, 0), max_nb(G, 0), max_nd(G, 0);
     for (size_t g = 0; g < G; ++g) {
         const uint64_t s0 = offsets[dlo[g]], s1 = offsets[dlo[g + 1]], nb = s1 - s0;
-        uint64_t target = tk->chunk_bytes ? tk->chunk_bytes : std::min<uint64_t>(std::max<uint64_t>(nb / 12, 4u << 20), 256u << 20);
+        uint64_t target = tk->chunk_bytes ? tk->chunk_bytes : std::min<uint64_t>(std::max<uint64_t>(nb / 8, 4u << 20), 256u << 20);
         target = std::min<uint64_t>(target, kMaxShardBytes / 2);
         size_t d = dlo[g], toff = 0;
         do {
@@ -492,6 +497,7 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
         text_need[g] = toff + 64;
     }
     const size_t C = chunks.size();
+    h_plan = h_ms();
 
     DeviceGuard guard;
     spl_result* r = new (std::nothrow) spl_result();
@@ -510,7 +516,14 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
     };
     if (!r->off_buf.p || !meta_buf.p) { tk->err = "pinned host allocation failed"; return fail(SPL_ERR_OOM); }
     uint64_t* res_off = (uint64_t*)r->off_buf.p;
-    for (size_t c = 0; c < C; ++c) chunks[c].meta = (volatile uint64_t*)((uint8_t*)meta_buf.p + c * 32);
+    {
+        void* d_meta_base = nullptr;
+        if (cudaHostGetDevicePointer(&d_meta_base, meta_buf.p, 0) != cudaSuccess) { cudaGetLastError(); tk->err = "pinned host memory is not mapped"; return fail(SPL_ERR_CUDA); }
+        for (size_t c = 0; c < C; ++c) {
+            chunks[c].meta = (volatile uint64_t*)((uint8_t*)meta_buf.p + c * 32);
+            chunks[c].d_meta = (uint64_t*)((uint8_t*)d_meta_base + c * 32);
+        }
+    }
 
     // ---- device buffers: whole-shard text / ids / offsets, workspace for the largest chunk ----
     for (size_t g = 0; g < G; ++g) {
@@ -537,6 +550,7 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
         if ((rc = reserve())) return fail(rc);
     }
 
+    h_reserved = h_ms();
     int launches = 0;
     for (int attempt = 0;; ++attempt) {
         launches = 0;
@@ -576,13 +590,20 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
                 r->ids_buf = nb;
             }
             CUDA_TRY(cudaSetDevice(dc.device), tk->err);
+            {
+                // per-document offsets of the chunk (chunk-relative; rebased below once they have landed)
+                const size_t g = (size_t)c.g, nd = c.d1 - c.d0;
+                const size_t n_off = nd + ((c.d1 == dlo[g + 1] && g + 1 == G) ? 1 : 0);
+                if (n_off)
+                    CUDA_TRY(cudaMemcpyAsync(res_off + c.d0, (uint64_t*)dc.out_off.p + (c.d0 - dlo[g]), n_off * 8,
+                                             cudaMemcpyDeviceToHost, dc.s_out), tk->err);
+                r->stats.d2h_bytes += n_off * 8;
+            }
             if (c.n_tokens)
                 CUDA_TRY(cudaMemcpyAsync((uint32_t*)r->ids_buf.p + c.tok_base, (uint32_t*)dc.ids.p + c.ids_off, c.n_tokens * 4,
                                          cudaMemcpyDeviceToHost, dc.s_out), tk->err);
             r->stats.d2h_bytes += c.n_tokens * 4;
             if (tk->trace) cudaEventRecord(dc.pipe_ev[c.ev + 3], dc.s_out);
-            if (c.tok_base)
-                for (size_t d = c.d0; d < c.d1; ++d) res_off[d] += c.tok_base;
             return SPL_OK;
         };
 
@@ -617,15 +638,13 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
                 w.ids = (uint32_t*)dc.ids.p + c.ids_off;
                 uint64_t* d_out = (uint64_t*)dc.out_off.p + (c.d0 - dlo[g]);
                 w.out_off = d_out;
+                w.host_meta = c.d_meta;
                 launches += spl_launch_encode(w, dc.num_sms, dc.stream);
                 CUDA_TRY(cudaGetLastError(), tk->err);
-                // small results on the same stream (the next chunk reuses the workspace and the boundary offset)
-                const size_t n_off = nd + ((last && g + 1 == G) ? 1 : 0);
-                if (n_off) CUDA_TRY(cudaMemcpyAsync(res_off + c.d0, d_out, n_off * 8, cudaMemcpyDeviceToHost, dc.stream), tk->err);
-                CUDA_TRY(cudaMemcpyAsync((void*)c.meta, d_out + nd, 8, cudaMemcpyDeviceToHost, dc.stream), tk->err);
-                CUDA_TRY(cudaMemcpyAsync((void*)(c.meta + 1), (uint8_t*)dc.zero.p + 4, 8, cudaMemcpyDeviceToHost, dc.stream), tk->err);
+                // the chunk's id count and error flags arrive in mapped host memory (written by k_emit): no copy on the
+                // kernel stream, which would queue behind the previous chunk's ids on the device-to-host engine
                 CUDA_TRY(cudaEventRecord(ev_done, dc.stream), tk->err);
-                r->stats.d2h_bytes += n_off * 8 + 16;
+                r->stats.d2h_bytes += 16;
                 return SPL_OK;
             };
             err_code = enqueue();
@@ -639,6 +658,7 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
                 err_code = drain(next_out++);
             }
         }
+        h_enq = h_ms();
         while (err_code == SPL_OK && next_out < C) {
             Chunk& o = chunks[next_out];
             cudaSetDevice(tk->devs[o.g].device);
@@ -647,6 +667,7 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
             err_code = drain(next_out++);
         }
         if (err_code != SPL_OK) return fail(err_code);
+        h_drained = h_ms();
         float kmax = 0, tmax = 0;
         for (size_t g = 0; g < G; ++g) {
             DevCtx& dc = tk->devs[g];
@@ -672,6 +693,7 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
                                 g, c.d0, c.d1, (unsigned long long)(c.b1 - c.b0), a, b, d, e);
                     }
         }
+        h_synced = h_ms();
         if (retry) {
             if (attempt >= 6) { tk->err = "scratch pool for very long pieces exhausted"; return fail(SPL_ERR_OOM); }
             for (size_t g = 0; g < G; ++g) {
@@ -684,6 +706,10 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
             r->ids_buf = take_pinned(tk, 64);
             if (!r->ids_buf.p) { tk->err = "pinned host allocation failed"; return fail(SPL_ERR_OOM); }
         }
+        // the per-document offsets came back chunk-relative: rebase (all copies have completed)
+        for (auto& c : chunks)
+            if (c.tok_base)
+                for (size_t d = c.d0; d < c.d1; ++d) res_off[d] += c.tok_base;
         res_off[n_docs] = total;
         r->n_tokens = total;
         r->stats.n_docs = n_docs; r->stats.n_bytes = N; r->stats.n_tokens = total;
@@ -693,6 +719,9 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
     }
     give_pinned(tk, meta_buf);
     *out = r;
+    if (tk->trace)
+        fprintf(stderr, "[spl trace] host ms: plan %.3f  reserved %.3f  enqueued %.3f  drained %.3f  synced %.3f  end %.3f  (%zu chunks)\n",
+                h_plan, h_reserved, h_enq, h_drained, h_synced, h_ms(), C);
     return SPL_OK;
 }
 

@@ -782,6 +782,10 @@ __global__ void __launch_bounds__(SPL_THREADS, 8) k_emit(SplWork w) {
         const uint32_t pi = sm.wpre[x >> 5] + __popc(sm.pbw[x >> 5] & ((1u << (x & 31)) - 1u));
         const uint32_t rel = pi >= P ? sm.total : sm.spos[pi] + sm.wtot[(pi / (SPL_THREADS * 4u)) * EM_WARPS + ((pi / 128u) & (EM_WARPS - 1u))];
         w.out_off[d] = prefix + rel;
+        if (d == w.n_docs && w.host_meta) {                    // the call's summary, straight to the host (no copy on this stream)
+            w.host_meta[0] = prefix + rel;
+            w.host_meta[1] = (uint64_t)w.counters[SPL_CTR_ERR] | ((uint64_t)w.counters[SPL_CTR_HUGE_POOL] << 32);
+        }
     }
 }
 

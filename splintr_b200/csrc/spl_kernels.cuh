@@ -63,6 +63,7 @@ struct SplWork {
     uint32_t        huge_pool_words;
     uint32_t*       ids;              // [>= N]
     uint64_t*       out_off;          // [n_docs+1]
+    uint64_t*       host_meta;        // optional, mapped pinned host memory: [0] id count, [1] error flags | huge-pool need << 32
     const SplTables* T;               // device copy of the tables
     int             pattern;
     bool            with_special;
