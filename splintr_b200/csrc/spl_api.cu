@@ -170,12 +170,12 @@ ZeroLayout zero_layout(uint64_t N, bool with_special) {
     return z;
 }
 
-struct MissLayout { uint32_t r0, r1, r2; };
+struct MissLayout { uint32_t base[SPL_NCLS + 1]; };
 MissLayout miss_layout(uint64_t N) {
     MissLayout m;
-    m.r0 = (uint32_t)(N / 2 + 16);                                // thread + warp class: every miss has >= 2 bytes
-    m.r1 = m.r0 + (uint32_t)(N / (SPL_WARP_MAX + 1) + 16);        // big class
-    m.r2 = m.r1 + (uint32_t)(N / (SPL_BIG_MAX + 1) + 16);         // huge class
+    m.base[0] = 0;
+    for (uint32_t c = 0; c < SPL_NCLS; ++c)                       // pieces are disjoint: at most N / minlen of a class
+        m.base[c + 1] = m.base[c] + (uint32_t)(N / spl_class_minlen(c) + 16);
     return m;
 }
 
@@ -192,7 +192,7 @@ int reserve_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
     if ((rc = dc.tstate.ensure((z.n_tiles / SPL_CHUNK_TILES + 2) * 8, tk->err))) return rc;
     if ((rc = dc.pv.ensure(z.n_tiles * SPL_TILE * 4, tk->err))) return rc;
     if ((rc = dc.pool.ensure((size_t)(N + 64) * 4, tk->err))) return rc;
-    if ((rc = dc.mlist.ensure((size_t)m.r2 * 8, tk->err))) return rc;
+    if ((rc = dc.mlist.ensure((size_t)m.base[SPL_NCLS] * 8, tk->err))) return rc;
     uint32_t n_fast_tiles = (uint32_t)((N + SPL_FAST_PAYLOAD * 32u - 1) / (SPL_FAST_PAYLOAD * 32u));
     if ((rc = dc.fbl.ensure((size_t)(n_fast_tiles + 1) * 4, tk->err))) return rc;
     if (dc.huge_words == 0) dc.huge_words = (size_t)16 << 20;             // 64 MiB of scratch
@@ -225,7 +225,7 @@ int prepare_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
     w.pv = (uint32_t*)dc.pv.p;
     w.pool = (uint32_t*)dc.pool.p;
     w.mlist = (uint64_t*)dc.mlist.p;
-    w.ml_r0 = m.r0; w.ml_r1 = m.r1; w.ml_r2 = m.r2;
+    for (uint32_t c = 0; c <= SPL_NCLS; ++c) w.ml_base[c] = m.base[c];
     w.fb_list = (uint32_t*)dc.fbl.p;
     w.n_fast_tiles = n_fast_tiles;
     w.huge_pool = (uint32_t*)dc.huge.p;

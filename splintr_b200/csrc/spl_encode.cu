@@ -2,8 +2,8 @@
 //
 //   k_probe      one thread per piece: whole-piece vocabulary probe (tokenizer.rs:703-705, bpe.rs:73-80); the id of a
 //                hit goes to pv[] in piece order, a miss is appended to the miss list of its length class
-//   k_bpe        the leftmost-min-rank merge loop of bpe.rs:83-194 for every listed piece -- one thread per piece up
-//                to 32 bytes, one warp up to 3968 bytes, one block beyond -- ids to pool[] at the piece's byte position
+//   k_bpe        the leftmost-min-rank merge loop of bpe.rs:83-194 for every listed piece -- a group of 1..32 lanes per
+//                piece by length class, 32 / group pieces side by side in a warp -- ids to pool[] at the piece's byte position
 //   k_chunk_scan exclusive prefix of the id counts of 32-tile chunks (k_emit adds the tiles inside its chunk)
 //   k_emit       pv[] + pool[] -> ids in document order (the collect of tokenizer.rs:806 and the Rayon collect of
 //                encode_batch, tokenizer.rs:932-934) and the per-document output offsets
@@ -96,7 +96,7 @@ struct ProbeSmem {
     uint32_t spw[SPL_TILE / 32];              // special-span bits of the tile (with_special)
     uint16_t plist[SPL_TILE + 2];             // window positions of the tile's piece starts, in order (+ end of the last piece)
     uint16_t slow[SPL_TILE];                  // pieces the one-sector probe did not settle (each warp: its own range)
-    uint16_t mloc[SPL_TILE];                  // missed pieces: thread class from the bottom of the warp's range, warp class from its top
+    uint16_t mloc[SPL_TILE];                  // missed pieces: class 0 from the bottom of the warp's range, class 1 from its top
     uint32_t wtot[SPL_THREADS / 32];
     uint32_t last_end;                        // window position of the end of the tile's last piece
 };
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
     uint32_t n_short = 0, n_warp = 0;
     for (uint32_t i0 = 0; i0 < n_slow; i0 += 32) {
         const uint32_t i = i0 + lane;
-        uint32_t cls = 0, j = 0;                               // 0 settled, 1 thread class, 2 warp class, 3 big, 4 huge
+        uint32_t cls = 0, j = 0, mlen = 0, mpos = 0;           // cls: 0 settled, else 1 + length class of the miss
         if (i < n_slow) {
             j = sm.slow[jlo + i];
             const uint32_t s = sm.plist[j];
@@ -224,24 +224,36 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
                     id = lookupL_thread(T, sm.text, s, len);
                 }
                 if (id != SPL_RANK_NONE) val = id;
-                else cls = len <= SPL_SHORT_MAX ? 1u : len <= SPL_WARP_MAX ? 2u : len <= SPL_BIG_MAX ? 3u : 4u;
+                else cls = 1u + spl_len_class(len);
             }
             if (cls == 0) {
                 w.pv[pvbase + j] = val;
                 if (val == SPL_PV_NONE) { atomicAdd(&w.tinfo[tile].extra, -1); atomicAdd(&w.chunk_cnt[tile / SPL_CHUNK_TILES], -1); }
-            } else if (cls >= 3) {                             // rare: straight to the global list of its class
-                uint32_t midx = cls == 3 ? w.ml_r0 + atomicAdd(&w.counters[SPL_CTR_BIG], 1u)
-                                         : w.ml_r1 + atomicAdd(&w.counters[SPL_CTR_HUGE], 1u);
-                w.mlist[midx] = ml_entry(gpos, len, j);
-                w.pv[pvbase + j] = SPL_PV_MISS | midx;
             }
+            mlen = len; mpos = gpos;
         }
+        // classes 0 and 1 (up to 64 bytes) are collected per warp and published below with one atomic each
         uint32_t bal = __ballot_sync(FULL, cls == 1);
         if (cls == 1) sm.mloc[jlo + n_short + __popc(bal & lt_mask)] = (uint16_t)j;
         n_short += __popc(bal);
         bal = __ballot_sync(FULL, cls == 2);
         if (cls == 2) sm.mloc[jhi - 1 - (n_warp + __popc(bal & lt_mask))] = (uint16_t)j;
         n_warp += __popc(bal);
+        // longer pieces: straight to the list of their class, one atomic per warp and class
+        if (__any_sync(FULL, cls > 2)) {
+            for (uint32_t c = 2; c < SPL_NCLS; ++c) {
+                bal = __ballot_sync(FULL, cls == c + 1);
+                if (!bal) continue;
+                uint32_t leader = __ffs(bal) - 1, b0 = 0;
+                if (lane == leader) b0 = atomicAdd(&w.counters[SPL_CTR_CLS + c], (uint32_t)__popc(bal));
+                b0 = __shfl_sync(FULL, b0, leader);
+                if (cls == c + 1) {
+                    const uint32_t midx = w.ml_base[c] + b0 + __popc(bal & lt_mask);
+                    w.mlist[midx] = ml_entry(mpos, mlen, j);
+                    w.pv[pvbase + j] = SPL_PV_MISS | midx;
+                }
+            }
+        }
     }
     __syncwarp();
 
@@ -249,19 +261,19 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
     if (n_short | n_warp) {
         uint32_t g_short = 0, g_warp = 0;
         if (lane == 0) {
-            if (n_short) g_short = atomicAdd(&w.counters[SPL_CTR_SHORT], n_short);
-            if (n_warp) g_warp = atomicAdd(&w.counters[SPL_CTR_WARP], n_warp);
+            if (n_short) g_short = atomicAdd(&w.counters[SPL_CTR_CLS + 0], n_short);
+            if (n_warp) g_warp = atomicAdd(&w.counters[SPL_CTR_CLS + 1], n_warp);
         }
         g_short = __shfl_sync(FULL, g_short, 0);
         g_warp = __shfl_sync(FULL, g_warp, 0);
         for (uint32_t i = lane; i < n_short; i += 32) {
-            uint32_t j = sm.mloc[jlo + i], s = sm.plist[j], e = sm.plist[j + 1], midx = g_short + i;
+            uint32_t j = sm.mloc[jlo + i], s = sm.plist[j], e = sm.plist[j + 1], midx = w.ml_base[0] + g_short + i;
             if (e == 0xFFFFu) e = sm.last_end;
             w.mlist[midx] = ml_entry(tile0 + s, e - s, j);
             w.pv[pvbase + j] = SPL_PV_MISS | midx;
         }
         for (uint32_t i = lane; i < n_warp; i += 32) {
-            uint32_t j = sm.mloc[jhi - 1 - i], s = sm.plist[j], e = sm.plist[j + 1], midx = w.ml_r0 - 1 - (g_warp + i);
+            uint32_t j = sm.mloc[jhi - 1 - i], s = sm.plist[j], e = sm.plist[j + 1], midx = w.ml_base[1] + g_warp + i;
             if (e == 0xFFFFu) e = sm.last_end;
             w.mlist[midx] = ml_entry(tile0 + s, e - s, j);
             w.pv[pvbase + j] = SPL_PV_MISS | midx;
@@ -271,23 +283,41 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
 
 // ------------------------------------------------------------------------------------------
 // k_bpe: the merge loop (bpe.rs:83-194) for the listed pieces
+//
+// A piece of length class c is merged by a GROUP of G = 2^log2group(c) lanes, 64 parts per lane, so a warp merges
+// 32 / G pieces side by side and every lane has work in every step (32 parts per lane).  The parts of a piece form a doubly linked
+// list (bpe.rs:42-54) packed into two words per part, in the warp's 8 KiB of shared memory:
+//     A[e] = symbol:21 | next:11        B[e] = rank of (part e, next part):21 | prev:11
+// Element e of the piece of group p sits at word (e / G) * 32 + p * G + e % G, so the strided scan of a group is
+// conflict free.  One merge = strided min-scan of the ranks (leftmost minimum, bpe.rs:133), a shuffle reduction
+// inside the group, the splice and the two re-ranks (bpe.rs:146-166), done by lanes 0 and 1 of the group.
 // ------------------------------------------------------------------------------------------
-struct BpeWarpSmem {
-    uint32_t sym[SPL_WARP_MAX];
-    uint32_t rnk[SPL_WARP_MAX];
-    uint32_t tb[SPL_WARP_MAX / 32 + 1];
-};
-struct BpeBigSmem {
-    uint32_t sym[SPL_BIG_MAX];
-    uint32_t rnk[SPL_BIG_MAX];
-    uint32_t tb[SPL_BIG_MAX / 32 + 1];
-};
-union BpeSmem {
-    struct { uint32_t sym[SPL_SHORT_MAX][SPL_BPE_THREADS]; uint32_t rnk[SPL_SHORT_MAX][SPL_BPE_THREADS]; } th;
-    BpeWarpSmem wp[SPL_BPE_THREADS / 32];
-    BpeBigSmem big;
-    uint64_t red[SPL_BPE_THREADS];
-};
+#define BG_RANK_NONE 0x1FFFFFu
+#define BG_LINK_NONE 0x7FFu
+#define BG_WORDS     2048u                              // words per warp: A[1024] + B[1024] (32 parts per lane)
+
+// whole-piece probe of a piece in global memory by ONE thread (vocabularies with keys beyond 128 bytes only)
+__device__ uint32_t lookupL_serial_g(const SplTables* T, const uint8_t* __restrict__ tx, uint32_t len) {
+    uint64_t sum = 0;
+    for (uint32_t i = 0; i * 8 < len; ++i) {
+        uint64_t wv = 0;
+        for (uint32_t b = 0; b < 8 && i * 8 + b < len; ++b) wv |= (uint64_t)__ldg(tx + i * 8 + b) << (8 * b);
+        sum += spl_hashL_word(wv, i);
+    }
+    uint64_t hv = spl_hashL_final(sum, len);
+    uint32_t mask = (1u << T->tl_log2) - 1, h = (uint32_t)(hv >> (64 - T->tl_log2));
+    for (;;) {
+        uint4 v = __ldg(reinterpret_cast<const uint4*>(T->tl + h));
+        if (v.w == 0) return SPL_RANK_NONE;
+        if (v.w == len && v.x == (uint32_t)hv && v.y == (uint32_t)(hv >> 32)) {
+            const uint8_t* kb = T->tok_bytes + __ldg(T->tok_off + v.z);
+            bool ok = true;
+            for (uint32_t j = 0; j < len && ok; ++j) ok = (__ldg(tx + j) == __ldg(kb + j));
+            if (ok) return v.z;
+        }
+        h = (h + 1) & mask;
+    }
+}
 
 __device__ __forceinline__ void bpe_finish(const SplWork& w, uint64_t* slot, uint32_t gpos, uint32_t cnt) {
     *slot = (uint64_t)gpos | ((uint64_t)cnt << 32);
@@ -297,147 +327,137 @@ __device__ __forceinline__ void bpe_finish(const SplWork& w, uint64_t* slot, uin
     }
 }
 
-// One THREAD merges the piece tx[0, n), 2 <= n <= 32: parts are the set bits of `live` (bit i = a part starts at byte
-// i), their symbols in S(i), the rank of (part, next part) in R(i).  32 pieces merge side by side in a warp, so the
-// probe latency of the re-ranks overlaps across pieces.  Returns the id count; ids go to out[0 ..].
-__device__ uint32_t bpe_piece_thread(BpeSmem& sm, const SplTables* T, const uint8_t* __restrict__ tx, uint32_t n, uint32_t* __restrict__ out) {
+// All 32 lanes call this; lane = p * G + g works on piece p of the warp's task (valid: the piece exists), G = 1 << LG.
+// Returns the id count in lane g == 0 of every group; ids go to out[0 ..] in order.
+template <uint32_t LG>
+__device__ uint32_t bpe_group(uint32_t* reg, const bool valid, const SplTables* T,
+                              const uint8_t* __restrict__ tx, const uint32_t n, uint32_t* __restrict__ out) {
+    constexpr uint32_t G = 1u << LG;
+    const uint32_t lane = threadIdx.x & 31u, p = lane >> LG, g = lane & (G - 1u);
+    uint32_t* A = reg;
+    uint32_t* B = reg + BG_WORDS / 2;
     const uint64_t* __restrict__ ptab = T->pair;
-    const uint32_t plog = T->pair_log2;
-    const uint32_t t = threadIdx.x;
-#define S(i) sm.th.sym[(i)][t]
-#define R(i) sm.th.rnk[(i)][t]
-#pragma unroll 4
-    for (uint32_t i = 0; i < n; ++i) S(i) = __ldg(tx + i);
-#pragma unroll 4
-    for (uint32_t i = 0; i < n; ++i) S(i) = T->byte_sym[S(i)];
+    const uint32_t plog = T->pair_log2, pmask = (1u << plog) - 1u;
+#define IDX(e) ((((e) >> LG) << 5) + (p << LG) + ((e) & (G - 1u)))
+    bool act = valid;
     {
-        const uint32_t pmask = (1u << plog) - 1;
-        for (uint32_t i = 0; i + 1 < n; i += 4) {                  // four independent probes in flight
-            PairBucket bk[4];
-            uint64_t key[4];
-            uint32_t bb[4];
+        // whole-piece probe of pieces beyond the probe halo (k_probe has already tried the shorter ones)
+        const bool tryw = act && n > SPL_PROBE_HALO && n <= T->max_key_len;
+        if (__any_sync(FULL, tryw)) {
+            uint32_t id = SPL_RANK_NONE;
+            if (tryw && g == 0) id = lookupL_serial_g(T, tx, n);
+            id = __shfl_sync(FULL, id, p << LG);
+            if (tryw && id != SPL_RANK_NONE) { if (g == 0) out[0] = id; act = false; }
+        }
+    }
+    const bool whole = valid && !act;
+    const uint32_t rows = act ? (n + G - 1u - g) >> LG : 0u;      // parts of this lane: e = g + it * G, at word it * 32 + lane
+    // ---- every byte becomes a part ------------------------------------------------------------------
+    for (uint32_t it = 0, e = g; it < rows; ++it, e += G)
+        A[it * 32u + lane] = (T->byte_sym[__ldg(tx + e)] << 11) | (e + 1 < n ? e + 1 : BG_LINK_NONE);
+    __syncwarp();
+    // ---- ranks of the adjacent pairs, two independent probes in flight per lane ----------------------
+    for (uint32_t it = 0; it < rows; it += 2) {
+        PairBucket bk[2];
+        uint64_t key[2];
+        uint32_t bb[2];
 #pragma unroll
-            for (uint32_t q = 0; q < 4; ++q)
-                if (i + q + 1 < n) {
-                    key[q] = spl_pair_key(S(i + q), S(i + q + 1));
-                    bb[q] = spl_pair_hash(key[q], plog);
-                    bk[q] = pair_bucket_load(ptab, bb[q]);
-                }
+        for (uint32_t q = 0; q < 2; ++q) {
+            const uint32_t e = g + (it + q) * G;
+            if (e + 1 < n) {
+                key[q] = spl_pair_key(A[(it + q) * 32u + lane] >> 11, A[IDX(e + 1)] >> 11);
+                bb[q] = spl_pair_hash(key[q], plog);
+                bk[q] = pair_bucket_load(ptab, bb[q]);
+            }
+        }
 #pragma unroll
-            for (uint32_t q = 0; q < 4; ++q)
-                if (i + q + 1 < n) {
-                    uint32_t r = SPL_RANK_NONE;
+        for (uint32_t q = 0; q < 2; ++q) {
+            const uint32_t e = g + (it + q) * G;
+            if (e < n) {
+                uint32_t r = SPL_RANK_NONE;
+                if (e + 1 < n)
                     while (pair_bucket_match(bk[q], key[q], r) == 2) { bb[q] = (bb[q] + 1) & pmask; bk[q] = pair_bucket_load(ptab, bb[q]); }
-                    R(i + q) = r;
-                }
+                B[(it + q) * 32u + lane] = ((r & BG_RANK_NONE) << 11) | (e ? e - 1 : BG_LINK_NONE);
+            }
         }
     }
-    R(n - 1) = SPL_RANK_NONE;
-    uint32_t live = n >= 32u ? 0xFFFFFFFFu : ((1u << n) - 1u);
+    __syncwarp();
+    // ---- merge loop --------------------------------------------------------------------------------------
     for (;;) {
-        uint32_t best = SPL_RANK_NONE, bpos = 0;
-        for (uint32_t m = live; m; m &= m - 1) {
-            uint32_t i = __ffs(m) - 1;
-            uint32_t r = R(i);
-            if (r < best) { best = r; bpos = i; }                 // strict <: leftmost minimum (bpe.rs:133)
+        uint32_t best = BG_RANK_NONE, bit = 0;
+        if (act)
+            for (uint32_t it = 0; it < rows; ++it) {
+                const uint32_t r = B[it * 32u + lane] >> 11;
+                if (r < best) { best = r; bit = it; }              // strict <: leftmost minimum of this lane's parts
+            }
+        uint32_t bpos = g + (bit << LG);
+#pragma unroll
+        for (uint32_t o = G >> 1; o; o >>= 1) {
+            const uint32_t ob = __shfl_xor_sync(FULL, best, o), op = __shfl_xor_sync(FULL, bpos, o);
+            if (ob < best || (ob == best && op < bpos)) { best = ob; bpos = op; }     // leftmost minimum (bpe.rs:133)
         }
-        if (best == SPL_RANK_NONE) break;
-        uint32_t above = bpos >= 31u ? 0u : (live & ~((2u << bpos) - 1u));
-        uint32_t nx = __ffs(above) - 1;                            // the absorbed part (exists: its pair has a rank)
-        uint32_t above2 = above & (above - 1);
-        uint32_t below = live & ((1u << bpos) - 1u);
-        bool has_nn = above2 != 0, has_pv = below != 0;
-        uint32_t nn = has_nn ? __ffs(above2) - 1 : 0u, pv = has_pv ? 31u - __clz(below) : 0u;
-        live &= ~(1u << nx);
-        S(bpos) = best;                                            // merged id == its rank
-        uint32_t r1, r0;
-        pair_lookup2(ptab, plog, has_nn, best, has_nn ? S(nn) : 0u, has_pv, has_pv ? S(pv) : 0u, best, r1, r0);
-        R(bpos) = r1;
-        if (has_pv) R(pv) = r0;
+        const bool go = act && best != BG_RANK_NONE;
+        if (!__any_sync(FULL, go)) break;
+        act = go;                                                  // a finished group idles until the warp is done
+        uint32_t j = 0, k = 0, h = 0, symk = 0, symh = 0;
+        bool has_k = false, has_h = false;
+        if (go) {
+            j = A[IDX(bpos)] & BG_LINK_NONE;                       // the part being absorbed (exists: its pair has a rank)
+            k = A[IDX(j)] & BG_LINK_NONE;                          // its right neighbour
+            h = B[IDX(bpos)] & BG_LINK_NONE;                       // left neighbour
+            has_k = k != BG_LINK_NONE; has_h = h != BG_LINK_NONE;
+            if (has_k) symk = A[IDX(k)] >> 11;
+            if (has_h) symh = A[IDX(h)] >> 11;
+        }
+        __syncwarp();
+        if (go) {
+            const bool do_a = g == 0, do_b = g == (G > 1u ? 1u : 0u);
+            uint32_t ra, rb;
+            pair_lookup2(ptab, plog, do_a && has_k, best, symk, do_b && has_h, symh, best, ra, rb);
+            if (do_a) {
+                A[IDX(bpos)] = (best << 11) | k;                   // merged id == its rank
+                B[IDX(bpos)] = ((ra & BG_RANK_NONE) << 11) | h;
+                B[IDX(j)] = (BG_RANK_NONE << 11) | BG_LINK_NONE;   // unlinked
+                if (has_k) B[IDX(k)] = (B[IDX(k)] & ~BG_LINK_NONE) | bpos;
+            }
+            if (do_b && has_h) B[IDX(h)] = ((rb & BG_RANK_NONE) << 11) | (B[IDX(h)] & BG_LINK_NONE);
+        }
+        __syncwarp();
     }
-    uint32_t c = 0;
-    for (uint32_t m = live; m; m &= m - 1) {
-        uint32_t sy = S(__ffs(m) - 1);
-        if (sy < SPL_UNK_BASE) out[c++] = sy;                      // bytes that are not in the vocabulary produce no id (bpe.rs:187-191)
-    }
-#undef S
-#undef R
+    // ---- surviving known parts, in order (part 0 is never absorbed: it heads the list) --------------------
+    uint32_t c = whole ? 1u : 0u;
+    if (valid && !whole && g == 0)
+        for (uint32_t e = 0; e != BG_LINK_NONE;) {
+            const uint32_t a = A[IDX(e)], sy = a >> 11;
+            if (sy < SPL_UNK_BASE) out[c++] = sy;                  // unknown bytes produce no id (bpe.rs:187-191)
+            e = a & BG_LINK_NONE;
+        }
+#undef IDX
     return c;
 }
 
-// One WARP merges the piece tx[0, len): parts are delimited by the bits of tb, sym holds each part's symbol at its
-// first byte, rnk the rank of (part, next part).  Returns (to every lane) the id count; ids go to out[0 ..].
-__device__ uint32_t bpe_piece_warp(uint32_t* sym, uint32_t* rnk, uint32_t* tb, const SplTables* T,
-                                   const uint8_t* __restrict__ tx, uint32_t len, uint32_t* __restrict__ out) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t nwords = (len + 31u) >> 5;
-    if (len > SPL_PROBE_HALO && len <= T->max_key_len) {           // k_probe has already tried the shorter ones
-        uint32_t id = lookupL_warp_g(T, tx, len);
-        if (id != SPL_RANK_NONE) {
-            if (lane == 0) out[0] = id;
-            return 1u;
-        }
-    }
-    for (uint32_t j = lane; j < len; j += 32) sym[j] = T->byte_sym[__ldg(tx + j)];
-    for (uint32_t v = lane; v <= nwords; v += 32) {
-        uint32_t lo = v * 32u;
-        tb[v] = lo + 32u <= len ? FULL : (lo < len ? ((1u << (len - lo)) - 1u) : 0u);
-    }
-    __syncwarp();
-    for (uint32_t j = lane; j < len; j += 32)
-        rnk[j] = (j + 1 < len) ? pair_lookup(T->pair, T->pair_log2, sym[j], sym[j + 1]) : SPL_RANK_NONE;
-    __syncwarp();
-    for (;;) {
-        uint32_t best = SPL_RANK_NONE, bpos = SPL_RANK_NONE;
-        for (uint32_t j = lane; j < len; j += 32) {
-            uint32_t r = rnk[j];
-            if (r < best) { best = r; bpos = j; }
-        }
-        uint32_t m = __reduce_min_sync(FULL, best);
-        if (m == SPL_RANK_NONE) break;
-        uint32_t pos = __reduce_min_sync(FULL, best == m ? bpos : SPL_RANK_NONE);   // leftmost minimum (bpe.rs:133)
-        uint32_t j = sm_next_bit(tb, pos + 1, len);            // the part being absorbed
-        uint32_t k = sm_next_bit(tb, j + 1, len);              // its right neighbour (len if none)
-        uint32_t h = sm_prev_bit(tb, pos, 0);                  // left neighbour (NONE if none)
-        uint32_t symk = k < len ? sym[k] : 0u;
-        uint32_t symh = h != SPL_RANK_NONE ? sym[h] : 0u;
-        __syncwarp();
-        if (lane == 0) {
-            sym[pos] = m;                                      // merged id == its rank
-            rnk[j] = SPL_RANK_NONE;
-            tb[j >> 5] &= ~(1u << (j & 31));
-            rnk[pos] = k < len ? pair_lookup(T->pair, T->pair_log2, m, symk) : SPL_RANK_NONE;
-        } else if (lane == 1 && h != SPL_RANK_NONE) {
-            rnk[h] = pair_lookup(T->pair, T->pair_log2, symh, m);
-        }
+template <uint32_t LG>
+__device__ void bpe_class(const SplWork& w, uint32_t c, uint32_t* reg, uint32_t gwarp, uint32_t nwarps) {
+    const uint32_t n = w.counters[SPL_CTR_CLS + c];
+    if (!n) return;
+    const uint32_t lane = threadIdx.x & 31u, ppw = 32u >> LG;                 // pieces per warp task
+    const uint32_t tasks = (n + ppw - 1) / ppw;
+    for (uint32_t t = gwarp; t < tasks; t += nwarps) {
+        const uint32_t pi = t * ppw + (lane >> LG);
+        const bool valid = pi < n;
+        uint64_t* slot = &w.mlist[w.ml_base[c] + (valid ? pi : 0u)];
+        const uint64_t e = *slot;
+        const uint32_t gpos = (uint32_t)e, len = (uint32_t)(e >> 32) & SPL_ML_LEN_SAT;
+        const uint32_t cnt = bpe_group<LG>(reg, valid, w.T, w.text + gpos, len, w.pool + gpos);
+        if (valid && (lane & ((1u << LG) - 1u)) == 0) bpe_finish(w, slot, gpos, cnt);
         __syncwarp();
     }
-    // surviving known parts, in order
-    uint32_t run = 0;
-    for (uint32_t w0 = 0; w0 < nwords; w0 += 32) {
-        uint32_t wi = w0 + lane;
-        uint32_t bits = wi < nwords ? tb[wi] : 0u, keep = 0;
-        for (uint32_t mm = bits; mm; mm &= mm - 1) {
-            uint32_t b = __ffs(mm) - 1;
-            if (sym[wi * 32u + b] < SPL_UNK_BASE) keep |= 1u << b;     // unknown bytes produce no id (bpe.rs:187-191)
-        }
-        uint32_t c = __popc(keep), incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(FULL, incl, o);
-            if (lane >= (uint32_t)o) incl += t;
-        }
-        uint32_t o = run + incl - c;
-        for (uint32_t mm = keep; mm; mm &= mm - 1) out[o++] = sym[wi * 32u + __ffs(mm) - 1];
-        run += __shfl_sync(FULL, incl, 31);
-    }
-    return run;
 }
 
 // The whole block merges one piece that does not fit shared memory: text bytes tx[0, len) in global memory; the
 // sym / rnk / next / prev arrays live in the scratch pool.  Returns (to every thread) the number of ids, written in
 // order to out[0 ..].
-__device__ uint32_t bpe_piece_block(BpeSmem& sm, uint32_t* s_bcast, const SplTables* T, const uint8_t* __restrict__ tx, uint32_t len,
+__device__ uint32_t bpe_piece_block(uint64_t* red, uint32_t* s_bcast, const SplTables* T, const uint8_t* __restrict__ tx, uint32_t len,
                                     uint32_t* scratch, uint32_t* __restrict__ out) {
     const uint32_t tid = threadIdx.x;
     uint32_t* sym = scratch;
@@ -473,13 +493,13 @@ __device__ uint32_t bpe_piece_block(BpeSmem& sm, uint32_t* s_bcast, const SplTab
             uint64_t v = ((uint64_t)rnk[j] << 32) | j;
             if (v < best) best = v;
         }
-        sm.red[tid] = best;
+        red[tid] = best;
         __syncthreads();
         for (uint32_t o = SPL_BPE_THREADS / 2; o; o >>= 1) {
-            if (tid < o && sm.red[tid + o] < sm.red[tid]) sm.red[tid] = sm.red[tid + o];
+            if (tid < o && red[tid + o] < red[tid]) red[tid] = red[tid + o];
             __syncthreads();
         }
-        uint64_t mn = sm.red[0];
+        uint64_t mn = red[0];
         __syncthreads();
         uint32_t m = (uint32_t)(mn >> 32), pos = (uint32_t)mn;
         if (m == SPL_RANK_NONE) break;
@@ -498,72 +518,43 @@ __device__ uint32_t bpe_piece_block(BpeSmem& sm, uint32_t* s_bcast, const SplTab
     const uint32_t lo = tid * per < len ? tid * per : len, hi = lo + per < len ? lo + per : len;
     uint32_t c = 0;
     for (uint32_t j = lo; j < hi; ++j) { uint32_t sv = sym[j]; c += (sv != SPL_RANK_NONE && sv < SPL_UNK_BASE); }
-    sm.red[tid] = c;
+    red[tid] = c;
     __syncthreads();
-    if (tid == 0) { uint64_t run = 0; for (int q = 0; q < SPL_BPE_THREADS; ++q) { uint64_t t = sm.red[q]; sm.red[q] = run; run += t; } *s_bcast = (uint32_t)run; }
+    if (tid == 0) { uint64_t run = 0; for (int q = 0; q < SPL_BPE_THREADS; ++q) { uint64_t t = red[q]; red[q] = run; run += t; } *s_bcast = (uint32_t)run; }
     __syncthreads();
-    uint32_t o = (uint32_t)sm.red[tid];
+    uint32_t o = (uint32_t)red[tid];
     for (uint32_t j = lo; j < hi; ++j) { uint32_t sv = sym[j]; if (sv != SPL_RANK_NONE && sv < SPL_UNK_BASE) out[o++] = sv; }
     uint32_t total = *s_bcast;
     __syncthreads();
     return total;
 }
 
-__global__ void __launch_bounds__(SPL_BPE_THREADS) k_bpe(SplWork w) {
-    __shared__ BpeSmem sm;
+#define BPE_SMEM_BYTES ((SPL_BPE_THREADS / 32) * BG_WORDS * 4)
+
+__global__ void __launch_bounds__(SPL_BPE_THREADS, 6) k_bpe(SplWork w) {
+    extern __shared__ __align__(16) uint32_t bpe_smem[];
     __shared__ uint32_t s_bcast, s_off;
     const SplTables* T = w.T;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t gwarp = blockIdx.x * (SPL_BPE_THREADS / 32) + warp, nwarps = gridDim.x * (SPL_BPE_THREADS / 32);
+    uint32_t* reg = bpe_smem + warp * BG_WORDS;
 
-    // ---- thread class ------------------------------------------------------------------------
-    {
-        const uint32_t n = w.counters[SPL_CTR_SHORT];
-        for (uint32_t i = blockIdx.x * SPL_BPE_THREADS + tid; i < n; i += gridDim.x * SPL_BPE_THREADS) {
-            uint64_t e = w.mlist[i];
-            uint32_t gpos = (uint32_t)e, len = (uint32_t)(e >> 32) & SPL_ML_LEN_SAT;
-            uint32_t c = bpe_piece_thread(sm, T, w.text + gpos, len, w.pool + gpos);
-            bpe_finish(w, &w.mlist[i], gpos, c);
-        }
-    }
-    // ---- warp class --------------------------------------------------------------------------
-    {
-        const uint32_t n = w.counters[SPL_CTR_WARP];
-        if (n) {
-            __syncthreads();
-            BpeWarpSmem& ws = sm.wp[warp];
-            for (uint32_t i = blockIdx.x * (SPL_BPE_THREADS / 32) + warp; i < n; i += gridDim.x * (SPL_BPE_THREADS / 32)) {
-                uint64_t* slot = &w.mlist[w.ml_r0 - 1 - i];
-                uint64_t e = *slot;
-                uint32_t gpos = (uint32_t)e, len = (uint32_t)(e >> 32) & SPL_ML_LEN_SAT;
-                uint32_t c = bpe_piece_warp(ws.sym, ws.rnk, ws.tb, T, w.text + gpos, len, w.pool + gpos);
-                if (lane == 0) bpe_finish(w, slot, gpos, c);
-                __syncwarp();
-            }
-        }
-    }
-    // ---- big class: warp 0 with the whole block's shared memory ---------------------------------------
-    {
-        const uint32_t n = w.counters[SPL_CTR_BIG];
-        if (n) {
-            __syncthreads();
-            if (warp == 0)
-                for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
-                    uint64_t* slot = &w.mlist[w.ml_r0 + i];
-                    uint64_t e = *slot;
-                    uint32_t gpos = (uint32_t)e, len = (uint32_t)(e >> 32) & SPL_ML_LEN_SAT;
-                    uint32_t c = bpe_piece_warp(sm.big.sym, sm.big.rnk, sm.big.tb, T, w.text + gpos, len, w.pool + gpos);
-                    if (lane == 0) bpe_finish(w, slot, gpos, c);
-                    __syncwarp();
-                }
-        }
-    }
+    // ---- classes merged by lane groups: the longest pieces first, so that the tail of the kernel is short work ------
+    bpe_class<5>(w, 6, reg, gwarp, nwarps);
+    bpe_class<4>(w, 5, reg, gwarp, nwarps);
+    bpe_class<3>(w, 4, reg, gwarp, nwarps);
+    bpe_class<2>(w, 3, reg, gwarp, nwarps);
+    bpe_class<1>(w, 2, reg, gwarp, nwarps);
+    bpe_class<0>(w, 1, reg, gwarp, nwarps);
+    bpe_class<0>(w, 0, reg, gwarp, nwarps);
     // ---- huge class: whole block, global scratch ----------------------------------------------------
     {
-        const uint32_t n = w.counters[SPL_CTR_HUGE];
+        const uint32_t n = w.counters[SPL_CTR_CLS + SPL_NCLS - 1];
         if (n) {
             __syncthreads();
+            uint64_t* red = reinterpret_cast<uint64_t*>(bpe_smem);
             for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
-                uint64_t* slot = &w.mlist[w.ml_r1 + i];
+                uint64_t* slot = &w.mlist[w.ml_base[SPL_NCLS - 1] + i];
                 uint64_t e = *slot;
                 uint32_t gpos = (uint32_t)e;
                 if (tid == 0) {
@@ -577,7 +568,7 @@ __global__ void __launch_bounds__(SPL_BPE_THREADS) k_bpe(SplWork w) {
                 const uint32_t off = s_off, len = s_bcast;
                 __syncthreads();
                 uint32_t c = 0;
-                if (off != SPL_RANK_NONE) c = bpe_piece_block(sm, &s_bcast, T, w.text + gpos, len, w.huge_pool + off, w.pool + gpos);
+                if (off != SPL_RANK_NONE) c = bpe_piece_block(red, &s_bcast, T, w.text + gpos, len, w.huge_pool + off, w.pool + gpos);
                 if (tid == 0) bpe_finish(w, slot, gpos, c);
                 __syncthreads();
             }
@@ -646,7 +637,7 @@ __global__ void __launch_bounds__(1024) k_chunk_scan(SplWork w) {
 // ------------------------------------------------------------------------------------------
 #define EM_ROUNDS (SPL_TILE / (SPL_THREADS * 4))     // 4 rounds cover the 4096 pieces a tile can have
 #define EM_WARPS (SPL_THREADS / 32)
-#define EM_INLINE 8u                                 // ids of a merged piece copied by its own thread up to this many
+#define EM_INLINE 5u                                 // ids of a merged piece copied by its own thread up to this many
 #define EM_BIGCAP (SPL_TILE / (EM_INLINE + 1u) + 1u) // pieces of a tile that can have more ids than that
 
 struct EmitSmem {
@@ -769,10 +760,10 @@ __global__ void __launch_bounds__(SPL_THREADS, 8) k_emit(SplWork w) {
     }
     if (d1 > d0 || P > 0) __syncthreads();
     {
-        const uint32_t nb = sm.n_big;
-        for (uint32_t b = 0; b < nb; ++b) {
+        const uint32_t nb = sm.n_big;                          // one warp per long piece
+        for (uint32_t b = warp; b < nb; b += EM_WARPS) {
             const uint32_t pos = sm.bigpos[b], gp = sm.biggp[b], c = sm.bigcnt[b];
-            for (uint32_t q = tid; q < c; q += SPL_THREADS) out[pos + q] = w.pool[gp + q];
+            for (uint32_t q = lane; q < c; q += 32) out[pos + q] = w.pool[gp + q];
         }
     }
 
@@ -793,6 +784,7 @@ __global__ void __launch_bounds__(SPL_THREADS, 8) k_emit(SplWork w) {
 // host side
 // ------------------------------------------------------------------------------------------
 void spl_encode_init() {
+    cudaFuncSetAttribute(k_bpe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BPE_SMEM_BYTES);
     cudaFuncSetAttribute(k_probe, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
     cudaFuncSetAttribute(k_emit, cudaFuncAttributePreferredSharedMemoryCarveout, 75);
     cudaGetLastError();
@@ -801,7 +793,7 @@ void spl_encode_init() {
 void spl_launch_encode_stage(const SplWork& w, int num_sms, cudaStream_t stream, SplMarkFn mark, void* ctx) {
     k_probe<<<w.n_tiles, SPL_THREADS, 0, stream>>>(w);
     mark(ctx, "k_probe");
-    k_bpe<<<(uint32_t)num_sms * 6u, SPL_BPE_THREADS, 0, stream>>>(w);
+    k_bpe<<<(uint32_t)num_sms * 6u, SPL_BPE_THREADS, BPE_SMEM_BYTES, stream>>>(w);
     mark(ctx, "k_bpe");
     k_chunk_scan<<<1, 1024, 0, stream>>>(w);
     mark(ctx, "k_chunk_scan");

@@ -18,9 +18,21 @@
 #define SPL_PROBE_WIN   (SPL_TILE + SPL_PROBE_HALO)
 #define SPL_CHUNK_TILES 32u           // tiles per chunk of the two-level id-count prefix
 #define SPL_BPE_THREADS 128           // k_bpe block size
-#define SPL_SHORT_MAX   32u           // piece bytes merged by one thread
-#define SPL_WARP_MAX    256u          // ... by one warp, four pieces per block
-#define SPL_BIG_MAX     3968u         // ... by one warp that owns the block's shared memory; longer: whole block, global scratch
+// Length classes of the pieces that go through the merge loop.  A piece of class c is merged by a group of
+// 2^spl_class_log2group(c) lanes (32 parts per lane), so a warp always works on 32 / group pieces side by side:
+//   class  0      1       2       3        4         5          6           7
+//   bytes  2..16  17..32  33..64  65..128  129..256  257..512   513..1024   1025.. (whole block, global scratch)
+//   group  1      1       2       4        8         16         32          -
+#define SPL_NCLS 8
+#define SPL_GROUP_MAXLEN 1024u
+__host__ __device__ inline uint32_t spl_len_class(uint32_t len) {
+    return len <= 16u ? 0u : len <= 32u ? 1u : len <= 64u ? 2u : len <= 128u ? 3u : len <= 256u ? 4u :
+           len <= 512u ? 5u : len <= SPL_GROUP_MAXLEN ? 6u : 7u;
+}
+__host__ __device__ inline uint32_t spl_class_minlen(uint32_t c) {
+    return c == 0 ? 2u : c == 7 ? SPL_GROUP_MAXLEN + 1u : (16u << (c - 1)) + 1u;
+}
+__host__ __device__ inline uint32_t spl_class_log2group(uint32_t c) { return c <= 1u ? 0u : c - 1u; }
 
 // values of SplWork::pv (one per piece, in text order)
 #define SPL_PV_MISS  0x80000000u      // | index of the piece's entry in `mlist`
@@ -54,9 +66,9 @@ struct SplWork {
     uint64_t*       chunk_state;      // [n_tiles / SPL_CHUNK_TILES + 1] exclusive prefix of chunk_cnt (k_chunk_scan)
     uint32_t*       pv;               // [n_tiles * SPL_TILE] per-piece value, tile t at pv[t * SPL_TILE ..]
     uint32_t*       pool;             // [N] ids of the pieces that went through the merge loop, at the piece's byte position
-    uint64_t*       mlist;            // miss list: [0, ml_r0) short pieces bottom-up / warp pieces top-down,
-    uint32_t        ml_r0, ml_r1, ml_r2;   // [ml_r0, ml_r1) big pieces, [ml_r1, ml_r2) huge pieces
-    uint32_t*       counters;         // [16]: see SPL_CTR_*
+    uint64_t*       mlist;            // miss lists, one region per length class
+    uint32_t        ml_base[SPL_NCLS + 1];   // class c owns mlist[ml_base[c] .. ml_base[c+1])
+    uint32_t*       counters;         // [SPL_CTR_WORDS]: see SPL_CTR_*
     uint32_t*       fb_list;          // [n_fast_tiles] fast-path tiles handed to the sequential rules
     uint32_t        n_fast_tiles;
     uint32_t*       huge_pool;        // scratch for pieces that outgrow shared memory
@@ -70,9 +82,9 @@ struct SplWork {
 };
 
 // SplWork::counters
-enum : uint32_t { SPL_CTR_SHORT = 0, SPL_CTR_ERR = 1, SPL_CTR_HUGE_POOL = 2, SPL_CTR_FB = 3,
-                  SPL_CTR_WARP = 4, SPL_CTR_BIG = 5, SPL_CTR_HUGE = 6, SPL_CTR_TICKET_S = 8, SPL_CTR_TICKET_W = 9,
-                  SPL_CTR_TICKET_B = 10, SPL_CTR_TICKET_H = 11, SPL_CTR_WORDS = 16 };
+enum : uint32_t { SPL_CTR_ERR = 1, SPL_CTR_HUGE_POOL = 2, SPL_CTR_FB = 3,
+                  SPL_CTR_CLS = 8,            // [8 .. 8 + SPL_NCLS): entries in the miss list of each class
+                  SPL_CTR_WORDS = 32 };
 
 enum : uint32_t { SPL_DEVERR_OFFSETS = 1u, SPL_DEVERR_HUGE_POOL = 2u };
 

@@ -264,9 +264,9 @@ class Tokenizer:
 
     def last_kernel_times(self, dev_index: int = 0) -> Dict[str, float]:
         """{kernel name: ms} of the most recent encode_device call (after a stream sync)."""
-        names = (ctypes.c_char_p * 8)()
-        ms = (ctypes.c_float * 8)()
-        n = _lib.load().spl_last_kernel_times(self._handle, dev_index, names, ms, 8)
+        names = (ctypes.c_char_p * 12)()
+        ms = (ctypes.c_float * 12)()
+        n = _lib.load().spl_last_kernel_times(self._handle, dev_index, names, ms, 12)
         return {names[i].decode(): float(ms[i]) for i in range(max(n, 0))}
 
     def launches_per_call(self, with_special: bool = False) -> int:
