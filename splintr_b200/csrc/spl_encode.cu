@@ -286,15 +286,16 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
 //
 // A piece of length class c is merged by a GROUP of G = 2^log2group(c) lanes, 64 parts per lane, so a warp merges
 // 32 / G pieces side by side and every lane has work in every step (32 parts per lane).  The parts of a piece form a doubly linked
-// list (bpe.rs:42-54) packed into two words per part, in the warp's 8 KiB of shared memory:
-//     A[e] = symbol:21 | next:11        B[e] = rank of (part e, next part):21 | prev:11
+// list (bpe.rs:42-54) packed into ten bytes per part, in the warp's 10 KiB of shared memory:
+//     A[e] = symbol:21 | next:11     R[e] = rank of (part e, next part):21 | e:11     P[e] = prev (u16)
+// R doubles as the scan key: the minimum over R is the lowest rank at the leftmost position.
 // Element e of the piece of group p sits at word (e / G) * 32 + p * G + e % G, so the strided scan of a group is
 // conflict free.  One merge = strided min-scan of the ranks (leftmost minimum, bpe.rs:133), a shuffle reduction
 // inside the group, the splice and the two re-ranks (bpe.rs:146-166), done by lanes 0 and 1 of the group.
 // ------------------------------------------------------------------------------------------
 #define BG_RANK_NONE 0x1FFFFFu
 #define BG_LINK_NONE 0x7FFu
-#define BG_WORDS     2048u                              // words per warp: A[1024] + B[1024] (32 parts per lane)
+#define BG_WORDS     2560u                              // words per warp: A[1024] + R[1024] + P[1024 x u16] (32 parts per lane)
 
 // whole-piece probe of a piece in global memory by ONE thread (vocabularies with keys beyond 128 bytes only)
 __device__ uint32_t lookupL_serial_g(const SplTables* T, const uint8_t* __restrict__ tx, uint32_t len) {
@@ -334,8 +335,9 @@ __device__ uint32_t bpe_group(uint32_t* reg, const bool valid, const SplTables* 
                               const uint8_t* __restrict__ tx, const uint32_t n, uint32_t* __restrict__ out) {
     constexpr uint32_t G = 1u << LG;
     const uint32_t lane = threadIdx.x & 31u, p = lane >> LG, g = lane & (G - 1u);
-    uint32_t* A = reg;
-    uint32_t* B = reg + BG_WORDS / 2;
+    uint32_t* A = reg;                                             // symbol:21 | next:11
+    uint32_t* R = reg + 1024;                                      // rank:21 | own position:11  (the scan key)
+    uint16_t* P = reinterpret_cast<uint16_t*>(reg + 2048);         // prev
     const uint64_t* __restrict__ ptab = T->pair;
     const uint32_t plog = T->pair_log2, pmask = (1u << plog) - 1u;
 #define IDX(e) ((((e) >> LG) << 5) + (p << LG) + ((e) & (G - 1u)))
@@ -352,9 +354,11 @@ __device__ uint32_t bpe_group(uint32_t* reg, const bool valid, const SplTables* 
     }
     const bool whole = valid && !act;
     const uint32_t rows = act ? (n + G - 1u - g) >> LG : 0u;      // parts of this lane: e = g + it * G, at word it * 32 + lane
+    const uint32_t rows4 = (rows + 3u) & ~3u;                      // the scan runs four rows at a time
     // ---- every byte becomes a part ------------------------------------------------------------------
     for (uint32_t it = 0, e = g; it < rows; ++it, e += G)
         A[it * 32u + lane] = (T->byte_sym[__ldg(tx + e)] << 11) | (e + 1 < n ? e + 1 : BG_LINK_NONE);
+    for (uint32_t it = rows; it < rows4; ++it) R[it * 32u + lane] = BG_RANK_NONE << 11;
     __syncwarp();
     // ---- ranks of the adjacent pairs, two independent probes in flight per lane ----------------------
     for (uint32_t it = 0; it < rows; it += 2) {
@@ -377,34 +381,31 @@ __device__ uint32_t bpe_group(uint32_t* reg, const bool valid, const SplTables* 
                 uint32_t r = SPL_RANK_NONE;
                 if (e + 1 < n)
                     while (pair_bucket_match(bk[q], key[q], r) == 2) { bb[q] = (bb[q] + 1) & pmask; bk[q] = pair_bucket_load(ptab, bb[q]); }
-                B[(it + q) * 32u + lane] = ((r & BG_RANK_NONE) << 11) | (e ? e - 1 : BG_LINK_NONE);
+                R[(it + q) * 32u + lane] = ((r & BG_RANK_NONE) << 11) | e;
+                P[(it + q) * 32u + lane] = (uint16_t)(e ? e - 1 : BG_LINK_NONE);
             }
         }
     }
     __syncwarp();
     // ---- merge loop --------------------------------------------------------------------------------------
     for (;;) {
-        uint32_t best = BG_RANK_NONE, bit = 0;
-        if (act)
-            for (uint32_t it = 0; it < rows; ++it) {
-                const uint32_t r = B[it * 32u + lane] >> 11;
-                if (r < best) { best = r; bit = it; }              // strict <: leftmost minimum of this lane's parts
-            }
-        uint32_t bpos = g + (bit << LG);
-#pragma unroll
-        for (uint32_t o = G >> 1; o; o >>= 1) {
-            const uint32_t ob = __shfl_xor_sync(FULL, best, o), op = __shfl_xor_sync(FULL, bpos, o);
-            if (ob < best || (ob == best && op < bpos)) { best = ob; bpos = op; }     // leftmost minimum (bpe.rs:133)
+        // leftmost minimum (bpe.rs:133): the key orders by rank, then by position
+        uint32_t key = 0xFFFFFFFFu;
+        for (uint32_t it = 0; it < rows4; it += 4) {
+            const uint32_t* r4 = R + it * 32u + lane;
+            key = min(min(key, r4[0]), min(r4[32], min(r4[64], r4[96])));
         }
+#pragma unroll
+        for (uint32_t o = G >> 1; o; o >>= 1) key = min(key, __shfl_xor_sync(FULL, key, o));
+        const uint32_t best = key >> 11, bpos = key & BG_LINK_NONE;
         const bool go = act && best != BG_RANK_NONE;
         if (!__any_sync(FULL, go)) break;
-        act = go;                                                  // a finished group idles until the warp is done
         uint32_t j = 0, k = 0, h = 0, symk = 0, symh = 0;
         bool has_k = false, has_h = false;
         if (go) {
             j = A[IDX(bpos)] & BG_LINK_NONE;                       // the part being absorbed (exists: its pair has a rank)
             k = A[IDX(j)] & BG_LINK_NONE;                          // its right neighbour
-            h = B[IDX(bpos)] & BG_LINK_NONE;                       // left neighbour
+            h = P[IDX(bpos)];                                      // left neighbour
             has_k = k != BG_LINK_NONE; has_h = h != BG_LINK_NONE;
             if (has_k) symk = A[IDX(k)] >> 11;
             if (has_h) symh = A[IDX(h)] >> 11;
@@ -416,11 +417,11 @@ __device__ uint32_t bpe_group(uint32_t* reg, const bool valid, const SplTables* 
             pair_lookup2(ptab, plog, do_a && has_k, best, symk, do_b && has_h, symh, best, ra, rb);
             if (do_a) {
                 A[IDX(bpos)] = (best << 11) | k;                   // merged id == its rank
-                B[IDX(bpos)] = ((ra & BG_RANK_NONE) << 11) | h;
-                B[IDX(j)] = (BG_RANK_NONE << 11) | BG_LINK_NONE;   // unlinked
-                if (has_k) B[IDX(k)] = (B[IDX(k)] & ~BG_LINK_NONE) | bpos;
+                R[IDX(bpos)] = ((ra & BG_RANK_NONE) << 11) | bpos;
+                R[IDX(j)] = (BG_RANK_NONE << 11) | j;              // unlinked
+                if (has_k) P[IDX(k)] = (uint16_t)bpos;
             }
-            if (do_b && has_h) B[IDX(h)] = ((rb & BG_RANK_NONE) << 11) | (B[IDX(h)] & BG_LINK_NONE);
+            if (do_b && has_h) R[IDX(h)] = ((rb & BG_RANK_NONE) << 11) | h;
         }
         __syncwarp();
     }
@@ -531,7 +532,7 @@ __device__ uint32_t bpe_piece_block(uint64_t* red, uint32_t* s_bcast, const SplT
 
 #define BPE_SMEM_BYTES ((SPL_BPE_THREADS / 32) * BG_WORDS * 4)
 
-__global__ void __launch_bounds__(SPL_BPE_THREADS, 6) k_bpe(SplWork w) {
+__global__ void __launch_bounds__(SPL_BPE_THREADS, 5) k_bpe(SplWork w) {
     extern __shared__ __align__(16) uint32_t bpe_smem[];
     __shared__ uint32_t s_bcast, s_off;
     const SplTables* T = w.T;
@@ -793,7 +794,7 @@ void spl_encode_init() {
 void spl_launch_encode_stage(const SplWork& w, int num_sms, cudaStream_t stream, SplMarkFn mark, void* ctx) {
     k_probe<<<w.n_tiles, SPL_THREADS, 0, stream>>>(w);
     mark(ctx, "k_probe");
-    k_bpe<<<(uint32_t)num_sms * 6u, SPL_BPE_THREADS, BPE_SMEM_BYTES, stream>>>(w);
+    k_bpe<<<(uint32_t)num_sms * 5u, SPL_BPE_THREADS, BPE_SMEM_BYTES, stream>>>(w);
     mark(ctx, "k_bpe");
     k_chunk_scan<<<1, 1024, 0, stream>>>(w);
     mark(ctx, "k_chunk_scan");
