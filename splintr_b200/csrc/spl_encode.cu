@@ -356,8 +356,14 @@ __device__ uint32_t bpe_group(uint32_t* reg, const bool valid, const SplTables* 
     const uint32_t rows = act ? (n + G - 1u - g) >> LG : 0u;      // parts of this lane: e = g + it * G, at word it * 32 + lane
     const uint32_t rows4 = (rows + 3u) & ~3u;                      // the scan runs four rows at a time
     // ---- every byte becomes a part ------------------------------------------------------------------
-    for (uint32_t it = 0, e = g; it < rows; ++it, e += G)
-        A[it * 32u + lane] = (T->byte_sym[__ldg(tx + e)] << 11) | (e + 1 < n ? e + 1 : BG_LINK_NONE);
+    // (two passes, each unrolled, so that the loads of several parts are in flight together)
+#pragma unroll 4
+    for (uint32_t it = 0; it < rows; ++it) A[it * 32u + lane] = __ldg(tx + g + (it << LG));
+#pragma unroll 4
+    for (uint32_t it = 0; it < rows; ++it) {
+        const uint32_t e = g + (it << LG);
+        A[it * 32u + lane] = (T->byte_sym[A[it * 32u + lane]] << 11) | (e + 1 < n ? e + 1 : BG_LINK_NONE);
+    }
     for (uint32_t it = rows; it < rows4; ++it) R[it * 32u + lane] = BG_RANK_NONE << 11;
     __syncwarp();
     // ---- ranks of the adjacent pairs, two independent probes in flight per lane ----------------------
@@ -686,6 +692,10 @@ __global__ void __launch_bounds__(SPL_THREADS, 8) k_emit(SplWork w) {
     // ---- pass 1: id count of every piece, warp-level prefixes ---------------------------------------
     for (uint32_t k = 0; k < rounds; ++k) {
         const uint32_t j4 = (k * SPL_THREADS + tid) * 4u;
+        if ((k * SPL_THREADS + warp * 32u) * 4u >= P) {            // the whole warp is past the last piece (warp-uniform)
+            if (lane == 31) sm.wtot[k * EM_WARPS + warp] = 0u;
+            continue;
+        }
         uint4 v = v_first;
         if ((k > 0 || tid >= 128) && j4 < P) v = __ldg(reinterpret_cast<const uint4*>(pv + j4));
         const uint32_t c0 = emit_count(w, v.x, j4 < P), c1 = emit_count(w, v.y, j4 + 1 < P),

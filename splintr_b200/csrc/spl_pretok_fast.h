@@ -81,6 +81,26 @@ SPL_HD uint32_t spl_smear(uint32_t f, uint32_t cont) {
     return f;
 }
 
+// 8x8 bit-matrix transpose of 8 bytes held in a u64 (byte r of the result collects bit r of every input byte):
+// with bit index 8 * row + column the three masked swaps exchange (row, column) with (column, row).
+SPL_HD uint64_t spl_transpose8(uint64_t x) {
+    uint64_t t;
+    t = (x ^ (x >> 7)) & 0x00AA00AA00AA00AAull;  x = x ^ t ^ (t << 7);
+    t = (x ^ (x >> 14)) & 0x0000CCCC0000CCCCull; x = x ^ t ^ (t << 14);
+    t = (x ^ (x >> 28)) & 0x00000000F0F0F0F0ull; x = x ^ t ^ (t << 28);
+    return x;
+}
+// xw[0..7] = 32 bytes as little-endian u32  ->  plane[q] bit i = bit q of byte i
+SPL_HD void spl_bitplanes(const uint32_t* xw, uint32_t* plane) {
+    uint64_t t[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t[k] = spl_transpose8((uint64_t)xw[2 * k] | ((uint64_t)xw[2 * k + 1] << 32));
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        plane[q] = (uint32_t)((t[0] >> (8 * q)) & 0xFFu) | ((uint32_t)((t[1] >> (8 * q)) & 0xFFu) << 8) |
+                   ((uint32_t)((t[2] >> (8 * q)) & 0xFFu) << 16) | ((uint32_t)((t[3] >> (8 * q)) & 0xFFu) << 24);
+}
+
 // ---- phase A: classify one word -------------------------------------------------------------------
 // xw[0..7] = the word's 32 bytes as little-endian u32 (bytes at or beyond N may hold anything: they are masked).
 // Text concept: uint8_t byte(uint32_t i) const  (any i < N) -- used only for non-ASCII characters and contractions.
@@ -92,24 +112,24 @@ SPL_HD SplFastWord spl_fast_classify(const Text& t, const uint32_t* xw, uint32_t
     for (int q = 0; q <= FM_BAD; ++q) w.m[q] = 0;
     if (base >= N) return w;
     const uint32_t valid = (N - base >= 32u) ? 0xFFFFFFFFu : ((1u << (N - base)) - 1u);
-    uint32_t m_lo = 0, m_up = 0, m_num = 0, m_sp = 0, m_ctl = 0, m_cr = 0, m_ap = 0, m_hi = 0;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-        uint32_t x = xw[g];
-        uint32_t hi = x & 0x80808080u, a = x & 0x7F7F7F7Fu;
-        uint32_t al = a | 0x20202020u;              // folds A-Z onto a-z (and @[\]^_ onto `{|}~ DEL, outside a-z)
-        uint32_t y_let = SPL_RNG(al, 0x61u, 0x7Au);
-        uint32_t y_cas = a & 0x20202020u;           // set for lower-case letters
-        uint32_t y_lo = y_let & (y_cas << 2), y_up = y_let & ~(y_cas << 2);
-        uint32_t y_num = SPL_RNG(a, 0x30u, 0x39u), y_ctl = SPL_RNG(a, 9u, 13u);
-        uint32_t y_sp = SPL_EQ(a, 0x20u), y_ap = SPL_EQ(a, 0x27u);
-        uint32_t y_cr = SPL_EQ(a, 0x0Au) | SPL_EQ(a, 0x0Du);
-        uint32_t keep = ~hi;
-        m_lo |= spl_nib(y_lo & keep) << (4 * g);  m_up |= spl_nib(y_up & keep) << (4 * g);
-        m_num |= spl_nib(y_num & keep) << (4 * g); m_ctl |= spl_nib(y_ctl & keep) << (4 * g);
-        m_sp |= spl_nib(y_sp & keep) << (4 * g);  m_ap |= spl_nib(y_ap & keep) << (4 * g);
-        m_cr |= spl_nib(y_cr & keep) << (4 * g);  m_hi |= spl_nib(hi) << (4 * g);
-    }
+    // ASCII classes by bit slicing: transpose the 32 bytes into 8 bit planes (plane q, bit i = bit q of byte i), then
+    // every class is a few boolean operations on whole planes.
+    uint32_t b[8];
+    spl_bitplanes(xw, b);
+    const uint32_t asc = ~b[7], n6 = asc & ~b[6];
+    const uint32_t hn0 = n6 & ~b[5] & ~b[4];                                   // 0x00..0x0F
+    const uint32_t hn2 = n6 & b[5] & ~b[4];                                    // 0x20..0x2F
+    const uint32_t low5_nz = b[4] | b[3] | b[2] | b[1] | b[0];
+    const uint32_t low5_gt26 = b[4] & b[3] & (b[2] | (b[1] & b[0]));
+    const uint32_t let = asc & b[6] & low5_nz & ~low5_gt26;                    // A-Z a-z
+    const uint32_t m_lo = let & b[5], m_up = let & ~b[5];
+    const uint32_t m_num = n6 & b[5] & b[4] & ~(b[3] & (b[2] | b[1]));         // 0-9
+    const uint32_t z30 = ~b[3] & ~b[2] & ~b[1] & ~b[0];
+    const uint32_t m_sp = hn2 & z30;                                           // 0x20
+    const uint32_t m_ap = hn2 & ~b[3] & b[2] & b[1] & b[0];                    // 0x27
+    const uint32_t m_ctl = hn0 & b[3] & ((~b[2] & (b[1] | b[0])) | (b[2] & ~b[1]));   // 0x09..0x0D
+    const uint32_t m_cr = hn0 & b[3] & ((~b[2] & b[1] & ~b[0]) | (b[2] & ~b[1] & b[0]));   // 0x0A 0x0D
+    uint32_t m_hi = b[7];
     m_hi &= valid;
     uint32_t lead = valid & ~m_hi;
     uint32_t up = m_up & valid, lo = m_lo & valid, bo = 0, num = m_num & valid, sp = m_sp & valid;

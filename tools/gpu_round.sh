@@ -14,6 +14,6 @@ cat gpurun_out/bench_${TAG}.json
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_${TAG}.json 2>> gpurun_out/bench_${TAG}.err
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches_${TAG}.log 2>&1
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_encode|k_pretok' -s 6 -c 2 -f -o gpurun_out/prof_${TAG} \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_probe|k_emit|k_pretok_fast|k_bpe' -s 12 -c 4 -f -o gpurun_out/prof_${TAG} \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_${TAG}.log 2>&1
 ls -la gpurun_out
