@@ -125,19 +125,20 @@ def run_cpu(vb, data, offsets, budget_s: float, steps: int = 1, warmup: int = 0)
     from splintr_b200 import presets as P
     p = P.PRESETS["cl100k_base"]
     orc = COracle(vb, p.pattern, p.special_tokens, False)
-    cores = max_threads()
+    # every host core this process may run on (torchrun exports OMP_NUM_THREADS=1: do not inherit that for the baseline)
+    cores = max(len(os.sched_getaffinity(0)), 1) if hasattr(os, "sched_getaffinity") else max(os.cpu_count() or 1, 1)
     nd0 = cpu_sample_docs(offsets, 4 << 20)
     t0 = time.perf_counter()
-    orc.encode_packed(data[:int(offsets[nd0])], offsets[:nd0 + 1])
+    orc.encode_packed(data[:int(offsets[nd0])], offsets[:nd0 + 1], n_threads=cores)
     rate = int(offsets[nd0]) / max(time.perf_counter() - t0, 1e-6)
     nd = cpu_sample_docs(offsets, min(rate * budget_s, float(offsets[-1])))
     sb, so = data[:int(offsets[nd])], offsets[:nd + 1]
     for _ in range(warmup):
-        orc.encode_packed(sb, so)
+        orc.encode_packed(sb, so, n_threads=cores)
     times = []
     for _ in range(max(steps, 1)):
         t0 = time.perf_counter()
-        ids, off = orc.encode_packed(sb, so)
+        ids, off = orc.encode_packed(sb, so, n_threads=cores)
         times.append(time.perf_counter() - t0)
     gbs = len(sb) / (sum(times) / len(times)) / 1e9
     sample = f"first {nd} docs ({len(sb) / 1e6:.1f} MB) of the workload, {cores} OpenMP threads, PCRE2-JIT, LRU omitted"

@@ -644,7 +644,7 @@ __global__ void __launch_bounds__(1024) k_chunk_scan(SplWork w) {
 // ------------------------------------------------------------------------------------------
 #define EM_ROUNDS (SPL_TILE / (SPL_THREADS * 4))     // 4 rounds cover the 4096 pieces a tile can have
 #define EM_WARPS (SPL_THREADS / 32)
-#define EM_INLINE 5u                                 // ids of a merged piece copied by its own thread up to this many
+#define EM_INLINE 8u                                 // ids of a merged piece copied by its own thread up to this many
 #define EM_BIGCAP (SPL_TILE / (EM_INLINE + 1u) + 1u) // pieces of a tile that can have more ids than that
 
 struct EmitSmem {
