@@ -162,7 +162,10 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
     const uint32_t jlo = warp * per < P ? warp * per : P, jhi = jlo + per < P ? jlo + per : P;
     const uint32_t pvbase = tile * SPL_TILE;
 
-    // ---- hot loop, one thread per piece: pieces of up to 8 bytes, one sector of the bucketed table -------------
+    // ---- hot loop, one thread per piece: pieces of up to 8 bytes against the FIRST slot of their home bucket ------
+    // A scattered 16-byte load costs one L1 wavefront per lane, and that is what bounds this loop, so only one load
+    // is spent here: keys were inserted in rank order, the frequent tokens sit in the first slot.  Everything else
+    // (second slot, next buckets, longer pieces, specials) goes to the slow list.
     uint32_t n_slow = 0;
     for (uint32_t j0 = jlo; j0 < jhi; j0 += 32) {
         const uint32_t j = j0 + lane;
@@ -179,12 +182,9 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
             const uint32_t nb = len * 8u;
             lo &= nb >= 32u ? FULL : ((1u << nb) - 1u);
             hi &= nb <= 32u ? 0u : (nb >= 64u ? FULL : ((1u << (nb - 32u)) - 1u));
-            const uint4* p = reinterpret_cast<const uint4*>(t8 + (size_t)spl_hash8(lo, hi, len, t8_log2) * SPL_T8_WAYS);
-            const uint4 v0 = __ldg(p), v1 = __ldg(p + 1);       // {k0 lo, k0 hi, id, len}
-            const bool h0 = v0.w == len && v0.x == lo && v0.y == hi;
-            const bool h1 = v1.w == len && v1.x == lo && v1.y == hi;
-            found = h0 || h1;
-            if (found) w.pv[pvbase + j] = h0 ? v0.z : v1.z;
+            const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(t8 + (size_t)spl_hash8(lo, hi, len, t8_log2) * SPL_T8_WAYS));
+            found = v0.w == len && v0.x == lo && v0.y == hi;            // {k0 lo, k0 hi, id, len}
+            if (found) w.pv[pvbase + j] = v0.z;
         }
         const bool sl = valid && !found;
         const uint32_t bal = __ballot_sync(FULL, sl);

@@ -1,0 +1,26 @@
+#!/bin/bash
+# compute-sanitizer (memcheck, then racecheck + initcheck) over a small mixed workload through the C-ABI.
+mkdir -p gpurun_out
+cat > /tmp/san_driver.py <<'PY'
+import os, sys, random
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tools")); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+import numpy as np, synth
+from splintr_b200 import Tokenizer, presets as P
+from fuzz_alphabet import random_text
+rng = random.Random(11)
+texts = [random_text(rng, 60) for _ in range(300)] + ["", "a", "x" * 3000, " " * 2500, "ab" * 700, "日本語のテキスト" * 40, "Hello <|endoftext|> world"]
+texts += ["".join(rng.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(rng.randint(20, 900))) for _ in range(20)]
+for name in ("cl100k_base", "llama3", "deepseek_v3"):
+    tok = Tokenizer.from_pretrained(name, devices=[0])
+    a = tok.encode_batch(texts)
+    b = tok.encode_batch_with_special(texts)
+    vb = P.load_vocab_bytes(P.PRESETS[name].vocab_file)
+    d, o = synth.cfg2(vb, 300) if name == "cl100k_base" else (synth.cfg4(vb, 1, 300000.0) if name == "llama3" else synth.cfg5(vb, 300))
+    ids, off = tok.encode_packed(d, o)
+    print(name, sum(len(x) for x in a), sum(len(x) for x in b), len(ids), flush=True)
+PY
+for tool in memcheck racecheck; do
+  timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python /tmp/san_driver.py > gpurun_out/sanitizer_$tool.log 2>&1
+  echo "$tool exit $?" >> gpurun_out/sanitizer_$tool.log
+  tail -6 gpurun_out/sanitizer_$tool.log
+done
