@@ -447,11 +447,15 @@ template <uint32_t LG>
 __device__ void bpe_class(const SplWork& w, uint32_t c, uint32_t* reg, uint32_t gwarp, uint32_t nwarps) {
     const uint32_t n = w.counters[SPL_CTR_CLS + c];
     if (!n) return;
-    const uint32_t lane = threadIdx.x & 31u, ppw = 32u >> LG;                 // pieces per warp task
+    const uint32_t lane = threadIdx.x & 31u;
+    // pieces per warp task: all 32 / G groups when there is plenty of work; fewer when the list is short, so that the
+    // pieces spread over all warps of the grid and a warp's merge rounds are the maximum over fewer pieces
+    uint32_t ppw = 32u >> LG;
+    while (ppw > 1u && (size_t)n * 2u <= (size_t)nwarps * ppw) ppw >>= 1;
     const uint32_t tasks = (n + ppw - 1) / ppw;
     for (uint32_t t = gwarp; t < tasks; t += nwarps) {
         const uint32_t pi = t * ppw + (lane >> LG);
-        const bool valid = pi < n;
+        const bool valid = (lane >> LG) < ppw && pi < n;
         uint64_t* slot = &w.mlist[w.ml_base[c] + (valid ? pi : 0u)];
         const uint64_t e = *slot;
         const uint32_t gpos = (uint32_t)e, len = (uint32_t)(e >> 32) & SPL_ML_LEN_SAT;
@@ -651,9 +655,10 @@ struct EmitSmem {
     __align__(16) uint32_t spos[SPL_TILE + 4];       // ids of the warp's round before piece j (see wtot)
     uint32_t pbw[SPL_TILE / 32];
     uint32_t wpre[SPL_TILE / 32];
-    uint32_t wtot[EM_ROUNDS * EM_WARPS];             // ids of the tile before each (round, warp)
+    uint32_t wtot[EM_ROUNDS * EM_WARPS];             // ids of each (round, warp)
+    uint32_t wexc[EM_ROUNDS * EM_WARPS];             // ids of the tile before each (round, warp)
     uint32_t bigpos[EM_BIGCAP], biggp[EM_BIGCAP], bigcnt[EM_BIGCAP];
-    uint32_t n_big, total;
+    uint32_t n_big;
     uint64_t prefix;
 };
 
@@ -712,21 +717,23 @@ __global__ void __launch_bounds__(SPL_THREADS, 8) k_emit(SplWork w) {
         if (lane == 31) sm.wtot[k * EM_WARPS + warp] = incl;
     }
     __syncthreads();
-    if (warp == 0) {
-        // exclusive scan of the rounds * EM_WARPS (<= 32) warp totals; word prefixes of the piece bits
-        uint32_t x = lane < rounds * EM_WARPS ? sm.wtot[lane] : 0u, incl = x;
+    // every warp turns the (<= 32) warp totals into exclusive offsets for itself: no serial scan, no second barrier
+    uint32_t my_tot = lane < rounds * EM_WARPS ? sm.wtot[lane] : 0u, my_incl = my_tot;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(FULL, incl, o);
-            if (lane >= (uint32_t)o) incl += t;
-        }
-        sm.wtot[lane] = incl - x;
-        if (lane == 31) sm.total = incl;                       // ids of the whole tile
-        if (d1 > d0) {
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(FULL, my_incl, o);
+        if (lane >= (uint32_t)o) my_incl += t;
+    }
+    const uint32_t my_excl = my_incl - my_tot;                   // lane l: ids before (round, warp) pair l
+    const uint32_t tile_total = __shfl_sync(FULL, my_incl, 31);
+    if (d1 > d0) {                                               // for the document offsets at the end (after the next barrier)
+        if (warp == 0) sm.wexc[lane] = my_excl;
+        if (warp == 1) {
+            // word prefixes of the piece bits (document start -> piece index)
             uint32_t loc[4], run = 0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) { loc[q] = __popc(sm.pbw[lane * 4 + q]); run += loc[q]; }
-            incl = run;
+            uint32_t incl = run;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 uint32_t t = __shfl_up_sync(FULL, incl, o);
@@ -737,17 +744,17 @@ __global__ void __launch_bounds__(SPL_THREADS, 8) k_emit(SplWork w) {
             for (int q = 0; q < 4; ++q) { sm.wpre[lane * 4 + q] = b; b += loc[q]; }
         }
     }
-    __syncthreads();
 
     // ---- pass 2: ids to their place ----------------------------------------------------------------------
     const uint64_t prefix = sm.prefix;
     uint32_t* __restrict__ out = w.ids + prefix;
     for (uint32_t k = 0; k < rounds; ++k) {
         const uint32_t j4 = (k * SPL_THREADS + tid) * 4u;
+        const uint32_t base_k = __shfl_sync(FULL, my_excl, k * EM_WARPS + warp);
         if (j4 < P) {
             uint4 v = v_first;
             if (k > 0 || tid >= 128) v = __ldg(reinterpret_cast<const uint4*>(pv + j4));
-            uint32_t pos = sm.spos[j4] + sm.wtot[k * EM_WARPS + warp];
+            uint32_t pos = sm.spos[j4] + base_k;
             const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (uint32_t q = 0; q < 4; ++q) {
@@ -769,7 +776,7 @@ __global__ void __launch_bounds__(SPL_THREADS, 8) k_emit(SplWork w) {
             }
         }
     }
-    if (d1 > d0 || P > 0) __syncthreads();
+    __syncthreads();
     {
         const uint32_t nb = sm.n_big;                          // one warp per long piece
         for (uint32_t b = warp; b < nb; b += EM_WARPS) {
@@ -782,7 +789,7 @@ __global__ void __launch_bounds__(SPL_THREADS, 8) k_emit(SplWork w) {
     for (uint32_t d = d0 + tid; d < d1; d += SPL_THREADS) {
         const uint32_t x = (uint32_t)(w.doc_off[d] - w.off_base - tile0);
         const uint32_t pi = sm.wpre[x >> 5] + __popc(sm.pbw[x >> 5] & ((1u << (x & 31)) - 1u));
-        const uint32_t rel = pi >= P ? sm.total : sm.spos[pi] + sm.wtot[(pi / (SPL_THREADS * 4u)) * EM_WARPS + ((pi / 128u) & (EM_WARPS - 1u))];
+        const uint32_t rel = pi >= P ? tile_total : sm.spos[pi] + sm.wexc[(pi / (SPL_THREADS * 4u)) * EM_WARPS + ((pi / 128u) & (EM_WARPS - 1u))];
         w.out_off[d] = prefix + rel;
         if (d == w.n_docs && w.host_meta) {                    // the call's summary, straight to the host (no copy on this stream)
             w.host_meta[0] = prefix + rel;
