@@ -230,3 +230,45 @@ def test_pipelined_host_call_many_chunks(toks, monkeypatch):
     texts2 = [tx[:50] + sp + tx[50:] for tx in texts[:200]]
     po = py_oracle("cl100k_base")
     assert t.encode_batch_with_special(texts2) == [po.encode_with_special(x) for x in texts2]
+
+
+def test_large_shard_beyond_2gib_tiling_property(toks):
+    """One device pass over more than 2^31 bytes (positions, tile indices and list indices are 32-bit inside the
+    kernels; the limit is 4 GiB): the batch is cfg2 (100 MB, checked bit-exact above) repeated 22 times, so the ids
+    must be the 100 MB result repeated and the offsets the same ramp shifted -- a size-independent property."""
+    import torch
+    tok = toks("cl100k_base")
+    d, o = synth.cfg2(vocab_bytes("cl100k_base"))
+    n1, nd1, reps = len(d), len(o) - 1, 22
+    base = torch.from_numpy(d).cuda()
+    n = n1 * reps
+    assert n > (1 << 31)
+    buf = torch.empty(n + ((-n) % 16), dtype=torch.uint8, device="cuda")
+    buf[:n].view(reps, n1).copy_(base.unsqueeze(0).expand(reps, n1))
+    o1 = torch.from_numpy(o.astype(np.int64)).cuda()
+    d_off = torch.cat([o1[:-1] + r * n1 for r in range(reps)] + [torch.tensor([n], dtype=torch.int64, device="cuda")])
+    b1 = torch.zeros(n1 + ((-n1) % 16), dtype=torch.uint8, device="cuda")
+    b1[:n1].copy_(base)
+    ids1, off1, nt1 = tok.encode_device(b1[:n1], o1)
+    ids1 = ids1[:nt1].clone(); off1 = off1.clone()
+    ids, off, nt = tok.encode_device(buf[:n], d_off)
+    assert nt == nt1 * reps
+    assert torch.equal(ids[:nt].view(reps, nt1), ids1.unsqueeze(0).expand(reps, nt1))
+    want_off = torch.cat([off1[:-1] + r * nt1 for r in range(reps)] + [torch.tensor([nt], dtype=torch.int64, device="cuda")])
+    assert torch.equal(off, want_off)
+
+
+def test_cfg3_large_host_call_equals_parts(toks):
+    """cfg3 (o200k_base, mixed prose / code / JSON) at 150 000 documents (~300 MB) through the pipelined host call:
+    bit-exact against the C oracle, and identical to encoding the batch in three separate calls."""
+    tok = toks("o200k_base")
+    d, o = synth.cfg3(vocab_bytes("o200k_base"), 150_000)
+    ids, off = _check_packed(tok, c_oracle("o200k_base"), d, o)
+    cuts = [0, 50_000, 100_000, 150_000]
+    parts_ids, parts_off = [], [np.zeros(1, dtype=np.uint64)]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        pi, po = tok.encode_packed(d[int(o[a]):int(o[b])], o[a:b + 1] - o[a])
+        parts_ids.append(pi)
+        parts_off.append(po[1:] + parts_off[-1][-1])
+    assert np.array_equal(np.concatenate(parts_ids), ids)
+    assert np.array_equal(np.concatenate(parts_off), off)
