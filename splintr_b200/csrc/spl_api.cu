@@ -477,14 +477,26 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
         const uint64_t s0 = offsets[dlo[g]], s1 = offsets[dlo[g + 1]], nb = s1 - s0;
         uint64_t target = tk->chunk_bytes ? tk->chunk_bytes : std::min<uint64_t>(std::max<uint64_t>(nb / 8, 4u << 20), 256u << 20);
         target = std::min<uint64_t>(target, kMaxShardBytes / 2);
-        size_t d = dlo[g], toff = 0;
+        // the pipeline fills with the first chunk's copy-in and drains with the last chunk's copy-out: ramp the chunk
+        // size up at the start and down at the end (quarter, half, full ... full, half, quarter) unless it was pinned
+        const bool ramp = !tk->chunk_bytes && nb >= 4 * target;
+        size_t d = dlo[g], toff = 0, k = 0;
         do {
             Chunk c;
             memset(&c, 0, sizeof(c));
             c.g = (int)g; c.d0 = d; c.b0 = offsets[d];
-            size_t e = std::upper_bound(offsets + d, offsets + dlo[g + 1] + 1, c.b0 + target) - offsets;   // first doc end beyond the target
+            uint64_t want = target;
+            const uint64_t rem = s1 - c.b0;
+            if (ramp) {
+                if (k == 0) want = target / 4; else if (k == 1) want = target / 2;
+                if (rem <= target / 4 + target / 8) want = rem;                      // last: about a quarter
+                else if (rem <= target) want = rem - target / 4;                     // second to last
+            }
+            ++k;
+            size_t e = std::upper_bound(offsets + d, offsets + dlo[g + 1] + 1, c.b0 + want) - offsets;   // first doc end beyond the target
             e = std::min(std::max(e, d + 1), dlo[g + 1]);
-            if (offsets[dlo[g + 1]] - c.b0 <= target + target / 4) e = dlo[g + 1];                       // no runt at the end
+            if (!ramp && rem <= target + target / 4) e = dlo[g + 1];                                      // no runt at the end
+            if (ramp && rem <= want + want / 8) e = dlo[g + 1];
             if (d == dlo[g + 1]) e = d;                                                                    // shard without documents
             c.d1 = e; c.b1 = offsets[e];
             c.text_off = toff; c.ids_off = (size_t)(c.b0 - s0);
