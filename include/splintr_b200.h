@@ -110,6 +110,25 @@ int spl_encode_batch_device(spl_tokenizer* tok, int dev_index,
                             uint32_t* d_ids, size_t ids_capacity, uint64_t* d_out_offsets,
                             void* cuda_stream, uint64_t* n_tokens_out);
 
+/* ---- decode (the step on the other side of the path) ------------------------------
+ * Replaces, for batches, Tokenizer::decode_bytes / decode_batch (src/core/tokenizer.rs:877-897, 945-958;
+ * Python: bindings.rs:300-379): every id is looked up in the vocabulary (byte-level keys are returned as raw
+ * bytes, tokenizer.rs:882-887), then among the special tokens; unknown ids contribute nothing.  UTF-8
+ * validation of the result (decode vs decode_lossy) stays with the caller.
+ * `ids` holds the concatenated token ids, document i is ids[offsets[i] .. offsets[i+1]).  The result carries
+ * the concatenated bytes (spl_result_bytes / spl_result_n_bytes) and n_docs+1 byte offsets (spl_result_offsets). */
+int spl_decode_batch(spl_tokenizer* tok, const uint32_t* ids, const uint64_t* offsets, size_t n_docs, spl_result** out);
+const uint8_t* spl_result_bytes(const spl_result* r);
+size_t spl_result_n_bytes(const spl_result* r);
+
+/* Device-resident variant: all buffers are device pointers on the handle's device `dev_index`.  The call
+ * synchronises `cuda_stream`; *n_bytes_out receives the decoded size.  If that exceeds bytes_capacity nothing
+ * is written and SPL_ERR_INVALID_ARG is returned (retry with a buffer of *n_bytes_out bytes). */
+int spl_decode_batch_device(spl_tokenizer* tok, int dev_index, const uint32_t* d_ids, size_t n_tokens,
+                            const uint64_t* d_tok_offsets, size_t n_docs,
+                            uint8_t* d_bytes_out, size_t bytes_capacity, uint64_t* d_out_offsets,
+                            void* cuda_stream, uint64_t* n_bytes_out);
+
 /* number of kernels one spl_encode_batch_device call launches for these flags */
 int spl_launches_per_call(const spl_tokenizer* tok, uint32_t flags);
 

@@ -13,7 +13,7 @@ from typing import List, Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libsplintr_b200.so")
-SOURCES = ["spl_api.cu", "spl_kernels.cu", "spl_encode.cu", "spl_host.cpp"]
+SOURCES = ["spl_api.cu", "spl_kernels.cu", "spl_encode.cu", "spl_decode.cu", "spl_host.cpp"]
 HEADERS = ["spl_common.h", "spl_pretok.h", "spl_pretok_fast.h", "spl_host.h", "spl_kernels.cuh", "spl_device.cuh", "unicode_tables.inc",
            os.path.join("..", "..", "include", "splintr_b200.h")]
 
@@ -61,7 +61,8 @@ class SplStats(ctypes.Structure):
 EXPORTS = ["spl_create", "spl_destroy", "spl_last_error", "spl_encode_batch", "spl_result_ids",
            "spl_result_offsets", "spl_result_n_docs", "spl_result_n_tokens", "spl_result_stats",
            "spl_result_free", "spl_encode_batch_device", "spl_launches_per_call", "spl_alloc_pinned",
-           "spl_free_pinned", "spl_version", "spl_set_profiling", "spl_last_kernel_times"]
+           "spl_free_pinned", "spl_version", "spl_set_profiling", "spl_last_kernel_times",
+           "spl_decode_batch", "spl_decode_batch_device", "spl_result_bytes", "spl_result_n_bytes"]
 
 SPL_OK, SPL_ERR_INVALID_ARG, SPL_ERR_VOCAB, SPL_ERR_CUDA, SPL_ERR_OOM, SPL_ERR_UNSUPPORTED, SPL_ERR_NO_DEVICE = \
     0, -1, -2, -3, -4, -5, -6
@@ -108,6 +109,15 @@ def load() -> ctypes.CDLL:
     lib.spl_encode_batch_device.argtypes = [vp, ctypes.c_int, u8p, ctypes.c_size_t, u64p, ctypes.c_size_t,
                                             ctypes.c_uint32, u32p, ctypes.c_size_t, u64p, vp,
                                             ctypes.POINTER(ctypes.c_uint64)]
+    lib.spl_decode_batch.restype = ctypes.c_int
+    lib.spl_decode_batch.argtypes = [vp, u32p, u64p, ctypes.c_size_t, ctypes.POINTER(vp)]
+    lib.spl_result_bytes.restype = vp
+    lib.spl_result_bytes.argtypes = [vp]
+    lib.spl_result_n_bytes.restype = ctypes.c_size_t
+    lib.spl_result_n_bytes.argtypes = [vp]
+    lib.spl_decode_batch_device.restype = ctypes.c_int
+    lib.spl_decode_batch_device.argtypes = [vp, ctypes.c_int, u32p, ctypes.c_size_t, u64p, ctypes.c_size_t,
+                                            u8p, ctypes.c_size_t, u64p, vp, ctypes.POINTER(ctypes.c_uint64)]
     lib.spl_launches_per_call.restype = ctypes.c_int
     lib.spl_launches_per_call.argtypes = [vp, ctypes.c_uint32]
     lib.spl_set_profiling.restype = ctypes.c_int

@@ -55,7 +55,8 @@ struct DevCtx {
     void* table_blob = nullptr;
     SplTables* d_tables = nullptr;
     DevBuf text, doc_off, ids, out_off;          // spl_encode_batch: the shard's buffers
-    DevBuf zero, tstate, pv, pool, mlist, fbl, huge;   // per-pass workspace (zero: everything that starts cleared)
+    DevBuf zero, tstate, pv, pool, mlist, fbl, huge;
+    DevBuf dec_ids, dec_off, dec_ws, dec_out, dec_out_off;       // spl_decode_batch   // per-pass workspace (zero: everything that starts cleared)
     size_t huge_words = 0;
     SplKernelProfile prof;
     bool prof_ready = false;
@@ -80,6 +81,7 @@ struct spl_result {
     spl_tokenizer* owner;
     PinnedBuf ids_buf, off_buf;
     size_t n_docs, n_tokens;
+    size_t n_bytes = 0;         // spl_decode_batch: ids_buf holds this many bytes
     spl_stats stats;
 };
 
@@ -107,6 +109,8 @@ int upload_tables(spl_tokenizer* tk, DevCtx& dc) {
     size_t i_tb = add(h.tok_bytes.data(), h.tok_bytes.size());
     size_t i_to = add(h.tok_off.data(), h.tok_off.size() * 4);
     size_t i_pair = add(h.pair.data(), h.pair.size() * 8);
+    size_t i_decb = add(h.dec_bytes.data(), h.dec_bytes.size());
+    size_t i_deco = add(h.dec_off.data(), h.dec_off.size() * 4);
     size_t i_spb = add(h.sp_bytes.data(), h.sp_bytes.size());
     size_t i_spo = add(h.sp_off.data(), h.sp_off.size() * 4);
     size_t i_spi = add(h.sp_id.data(), h.sp_id.size() * 4);
@@ -128,6 +132,9 @@ int upload_tables(spl_tokenizer* tk, DevCtx& dc) {
     t.max_key_len = h.max_key_len;
     t.pair = (const uint64_t*)(base + parts[i_pair].off); t.pair_log2 = h.pair_log2;
     memcpy(t.byte_sym, h.byte_sym, sizeof(t.byte_sym));
+    t.dec_bytes = base + parts[i_decb].off;
+    t.dec_off = (const uint32_t*)(base + parts[i_deco].off);
+    t.n_dec = h.dec_off.empty() ? 0u : (uint32_t)h.dec_off.size() - 1u;
     t.sp_bytes = base + parts[i_spb].off;
     t.sp_off = (const uint32_t*)(base + parts[i_spo].off);
     t.sp_id = (const uint32_t*)(base + parts[i_spi].off);
@@ -141,7 +148,7 @@ int upload_tables(spl_tokenizer* tk, DevCtx& dc) {
 
 void destroy_ctx(DevCtx& dc) {
     cudaSetDevice(dc.device);
-    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.ids, &dc.out_off, &dc.zero, &dc.tstate, &dc.pv, &dc.pool, &dc.mlist, &dc.fbl, &dc.huge})
+    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.ids, &dc.out_off, &dc.dec_ids, &dc.dec_off, &dc.dec_ws, &dc.dec_out, &dc.dec_out_off, &dc.zero, &dc.tstate, &dc.pv, &dc.pool, &dc.mlist, &dc.fbl, &dc.huge})
         b->release();
     if (dc.table_blob) cudaFree(dc.table_blob);
     for (auto& e : dc.ev) if (e) cudaEventDestroy(e);
@@ -736,6 +743,111 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
                 h_plan, h_reserved, h_enq, h_drained, h_synced, h_ms(), C);
     return SPL_OK;
 }
+
+
+// ---- decode (row N2): ids -> bytes --------------------------------------------------------------------
+
+int spl_decode_batch_device(spl_tokenizer* tk, int dev_index, const uint32_t* d_ids, size_t n_tokens,
+                            const uint64_t* d_tok_offsets, size_t n_docs,
+                            uint8_t* d_bytes_out, size_t bytes_capacity, uint64_t* d_out_offsets,
+                            void* cuda_stream, uint64_t* n_bytes_out) {
+    if (!tk) return SPL_ERR_INVALID_ARG;
+    if (dev_index < 0 || (size_t)dev_index >= tk->devs.size() || !d_tok_offsets || !d_out_offsets || !n_bytes_out ||
+        (n_tokens && !d_ids)) {
+        tk->err = "invalid argument (null pointer)";
+        return SPL_ERR_INVALID_ARG;
+    }
+    DeviceGuard guard;
+    DevCtx& dc = tk->devs[dev_index];
+    CUDA_TRY(cudaSetDevice(dc.device), tk->err);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    SplDecLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.ids = d_ids; L.n_tok = n_tokens; L.tok_off = d_tok_offsets; L.n_docs = n_docs;
+    L.n_tiles = (uint32_t)(n_tokens / SPL_DEC_TILE) + 1;
+    if (n_tokens / SPL_DEC_TILE >= 0xFFFFFFF0ull) { tk->err = "too many ids for one device pass"; return SPL_ERR_UNSUPPORTED; }
+    int rc;
+    const size_t ws_sum = align_up((size_t)L.n_tiles * 4, 256);
+    if ((rc = dc.dec_ws.ensure(ws_sum + ((size_t)L.n_tiles + 1) * 8, tk->err))) return rc;
+    L.tile_sum = (uint32_t*)dc.dec_ws.p;
+    L.tile_pref = (uint64_t*)((uint8_t*)dc.dec_ws.p + ws_sum);
+    L.out = d_bytes_out; L.capacity = bytes_capacity; L.out_off = d_out_offsets; L.T = dc.d_tables;
+    spl_launch_decode_count(L, st);
+    uint64_t total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, L.tile_pref + L.n_tiles, 8, cudaMemcpyDeviceToHost, st), tk->err);
+    CUDA_TRY(cudaStreamSynchronize(st), tk->err);
+    *n_bytes_out = total;
+    if (total > bytes_capacity || (total && !d_bytes_out)) {
+        tk->err = "output capacity too small for the decoded bytes (needed size returned in n_bytes_out)";
+        return SPL_ERR_INVALID_ARG;
+    }
+    spl_launch_decode_emit(L, st);
+    CUDA_TRY(cudaGetLastError(), tk->err);
+    CUDA_TRY(cudaStreamSynchronize(st), tk->err);
+    return SPL_OK;
+}
+
+int spl_decode_batch(spl_tokenizer* tk, const uint32_t* ids, const uint64_t* offsets, size_t n_docs, spl_result** out) {
+    if (!tk || !out) return SPL_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (!offsets || offsets[0] != 0) { tk->err = "offsets must start at 0"; return SPL_ERR_INVALID_ARG; }
+    for (size_t i = 0; i < n_docs; ++i)
+        if (offsets[i + 1] < offsets[i]) { tk->err = "offsets must be non-decreasing"; return SPL_ERR_INVALID_ARG; }
+    const uint64_t n_tok = offsets[n_docs];
+    if (n_tok && !ids) { tk->err = "null ids"; return SPL_ERR_INVALID_ARG; }
+    DeviceGuard guard;
+    DevCtx& dc = tk->devs[0];
+    CUDA_TRY(cudaSetDevice(dc.device), tk->err);
+    int rc;
+    if ((rc = dc.dec_ids.ensure((size_t)(n_tok + 16) * 4, tk->err))) return rc;
+    if ((rc = dc.dec_off.ensure((n_docs + 1) * 8, tk->err))) return rc;
+    if ((rc = dc.dec_out_off.ensure((n_docs + 1) * 8, tk->err))) return rc;
+    cudaStream_t st = dc.stream;
+    cudaEvent_t e0 = dc.ev[0], e1 = dc.ev[1];
+    CUDA_TRY(cudaEventRecord(e0, st), tk->err);
+    if (n_tok) CUDA_TRY(cudaMemcpyAsync(dc.dec_ids.p, ids, n_tok * 4, cudaMemcpyHostToDevice, st), tk->err);
+    CUDA_TRY(cudaMemcpyAsync(dc.dec_off.p, offsets, (n_docs + 1) * 8, cudaMemcpyHostToDevice, st), tk->err);
+    // first attempt with the capacity of the previous call (at least 4 bytes per id), retry once with the exact size
+    uint64_t total = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        size_t cap = std::max<size_t>(dc.dec_out.cap, (size_t)n_tok * 4 + 256);
+        if ((rc = dc.dec_out.ensure(std::max<size_t>(cap, (size_t)total + 256), tk->err))) return rc;
+        rc = spl_decode_batch_device(tk, 0, (const uint32_t*)dc.dec_ids.p, (size_t)n_tok, (const uint64_t*)dc.dec_off.p, n_docs,
+                                     (uint8_t*)dc.dec_out.p, dc.dec_out.cap, (uint64_t*)dc.dec_out_off.p, st, &total);
+        if (rc == SPL_OK) break;
+        if (rc != SPL_ERR_INVALID_ARG || total <= dc.dec_out.cap || attempt == 1) return rc;
+    }
+    spl_result* r = new (std::nothrow) spl_result();
+    if (!r) return SPL_ERR_OOM;
+    memset(&r->stats, 0, sizeof(r->stats));
+    r->owner = tk; r->n_docs = n_docs; r->n_tokens = (size_t)n_tok; r->n_bytes = (size_t)total;
+    r->ids_buf = take_pinned(tk, (size_t)total + 64);
+    r->off_buf = take_pinned(tk, (n_docs + 1) * 8);
+    if (!r->ids_buf.p || !r->off_buf.p) {
+        give_pinned(tk, r->ids_buf); give_pinned(tk, r->off_buf);
+        delete r;
+        tk->err = "pinned host allocation failed";
+        return SPL_ERR_OOM;
+    }
+    auto finish = [&]() -> int {
+        if (total) CUDA_TRY(cudaMemcpyAsync(r->ids_buf.p, dc.dec_out.p, (size_t)total, cudaMemcpyDeviceToHost, st), tk->err);
+        CUDA_TRY(cudaMemcpyAsync(r->off_buf.p, dc.dec_out_off.p, (n_docs + 1) * 8, cudaMemcpyDeviceToHost, st), tk->err);
+        CUDA_TRY(cudaEventRecord(e1, st), tk->err);
+        CUDA_TRY(cudaStreamSynchronize(st), tk->err);
+        return SPL_OK;
+    };
+    if ((rc = finish())) { give_pinned(tk, r->ids_buf); give_pinned(tk, r->off_buf); delete r; return rc; }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    r->stats.n_docs = n_docs; r->stats.n_tokens = n_tok; r->stats.n_bytes = total;
+    r->stats.h2d_bytes = n_tok * 4 + (n_docs + 1) * 8; r->stats.d2h_bytes = total + (n_docs + 1) * 8;
+    r->stats.total_ms = ms; r->stats.n_devices = 1; r->stats.n_launches = 3;
+    *out = r;
+    return SPL_OK;
+}
+
+const uint8_t* spl_result_bytes(const spl_result* r) { return r ? (const uint8_t*)r->ids_buf.p : nullptr; }
+size_t spl_result_n_bytes(const spl_result* r) { return r ? r->n_bytes : 0; }
 
 const uint32_t* spl_result_ids(const spl_result* r) { return r ? (const uint32_t*)r->ids_buf.p : nullptr; }
 const uint64_t* spl_result_offsets(const spl_result* r) { return r ? (const uint64_t*)r->off_buf.p : nullptr; }

@@ -119,6 +119,10 @@ struct SplTables {
     // BPE
     const uint64_t* pair;  uint32_t pair_log2;
     uint32_t byte_sym[256];        // symbol of each single byte
+    // decode: id -> bytes
+    const uint8_t*  dec_bytes;
+    const uint32_t* dec_off;       // [n_dec + 1]
+    uint32_t n_dec;
     // special tokens (encode_with_special)
     const uint8_t*  sp_bytes;      // concatenated special strings
     const uint32_t* sp_off;        // [n_special+1]

@@ -241,6 +241,56 @@ bool spl_build_tables(SplHostTables& t, const uint8_t* vocab, size_t vocab_len, 
         for (auto& e : entries) t.encoder[e.first] = e.second;
     }
 
+    // ---- decode table (build_decoder vocab.rs:146-148 + decode_bytes tokenizer.rs:877-897) ----------------
+    {
+        std::unordered_map<std::string, uint32_t> final_rank;              // later duplicates overwrite (vocab.rs:85)
+        final_rank.reserve(entries.size() * 2);
+        for (auto& e : entries) final_rank[e.first] = e.second;
+        uint32_t cp_of_byte[256];
+        byte_to_cp_table(cp_of_byte);
+        std::unordered_map<uint32_t, uint8_t> byte_of_cp;
+        for (int b = 0; b < 256; ++b) byte_of_cp[cp_of_byte[b]] = (uint8_t)b;
+        uint32_t max_dec = 0;
+        bool any = false;
+        for (auto& e : entries) { max_dec = std::max(max_dec, e.second); any = true; }
+        for (size_t i = 0; i < n_special; ++i) { max_dec = std::max(max_dec, special_ids[i]); any = true; }
+        if (any && max_dec > 0x3FFFFFFu) { t.error = "token ids above 2^26 are not supported"; return false; }
+        std::vector<std::string> dec(any ? (size_t)max_dec + 1 : 0);
+        std::vector<uint8_t> has(dec.size(), 0);
+        for (auto& e : entries) {
+            if (final_rank[e.first] != e.second) continue;                  // an overwritten duplicate
+            std::string raw = e.first;
+            if (flags & SPL_FLAG_BYTE_LEVEL) {
+                // byte_level_decode_bytes, falling back to the key itself (tokenizer.rs:883-887)
+                const uint8_t* p = (const uint8_t*)e.first.data();
+                size_t n = e.first.size(), i = 0;
+                std::string tr;
+                bool ok = true;
+                while (i < n) {
+                    uint32_t cp;
+                    int l = utf8_next(p + i, n - i, cp);
+                    if (l == 0) { ok = false; break; }
+                    auto it = byte_of_cp.find(cp);
+                    if (it == byte_of_cp.end()) { ok = false; break; }
+                    tr.push_back((char)it->second);
+                    i += l;
+                }
+                if (ok) raw = tr;
+            }
+            dec[e.second] = raw; has[e.second] = 1;
+        }
+        for (size_t i = 0; i < n_special; ++i)
+            if (!has[special_ids[i]]) { dec[special_ids[i]] = special_strs[i]; has[special_ids[i]] = 1; }
+        t.dec_off.assign(dec.size() + 1, 0);
+        t.dec_bytes.clear();
+        for (size_t i = 0; i < dec.size(); ++i) {
+            t.dec_off[i] = (uint32_t)t.dec_bytes.size();
+            t.dec_bytes.insert(t.dec_bytes.end(), dec[i].begin(), dec[i].end());
+        }
+        t.dec_off[dec.size()] = (uint32_t)t.dec_bytes.size();
+        t.dec_bytes.resize(t.dec_bytes.size() + 16, 0);
+    }
+
     // ---- id space ---------------------------------------------------------------------
     uint32_t max_id = 0;
     t.max_key_len = 0;

@@ -27,6 +27,10 @@ struct SplHostTables {
     std::vector<uint64_t> pair; uint32_t pair_log2 = 0; size_t n_pairs = 0;
     size_t t8_displaced = 0, pair_displaced = 0;         // keys that are not in their home bucket
     uint32_t byte_sym[256];
+    // decode (tokenizer.rs:877-897): id -> bytes for every vocabulary id (byte-level keys translated back to raw
+    // bytes, untranslatable ones kept as they are) and, where the vocabulary has no entry, the special-token string
+    std::vector<uint8_t>  dec_bytes;
+    std::vector<uint32_t> dec_off;                        // [n_dec + 1]
     std::vector<uint8_t>  sp_bytes;
     std::vector<uint32_t> sp_off, sp_id;
     uint32_t sp_first[8] = {0, 0, 0, 0, 0, 0, 0, 0};

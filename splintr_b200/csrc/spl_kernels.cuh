@@ -102,6 +102,19 @@ int spl_launch_encode(const SplWork& w, int num_sms, cudaStream_t stream, SplKer
 // Per-device one-time kernel attribute setup (shared-memory carveout).
 void spl_kernels_init();
 
+// spl_decode.cu: ids -> bytes (row N2)
+#define SPL_DEC_TILE 2048u            // ids per tile
+struct SplDecLaunch {
+    const uint32_t* ids; uint64_t n_tok;
+    const uint64_t* tok_off; uint64_t n_docs;
+    uint32_t n_tiles;                  // n_tok / SPL_DEC_TILE + 1
+    uint32_t* tile_sum; uint64_t* tile_pref;    // [n_tiles], [n_tiles + 1] (last = total bytes)
+    uint8_t* out; uint64_t capacity; uint64_t* out_off;
+    const SplTables* T;
+};
+void spl_launch_decode_count(const SplDecLaunch& L, cudaStream_t stream);   // k_dec_len + k_dec_scan
+void spl_launch_decode_emit(const SplDecLaunch& L, cudaStream_t stream);    // k_dec_emit (no-op on the device if capacity is too small)
+
 // spl_encode.cu: the encode stage behind the pre-tokenizer (k_probe, k_bpe, k_tile_scan, k_emit)
 typedef void (*SplMarkFn)(void* ctx, const char* name);
 void spl_encode_init();

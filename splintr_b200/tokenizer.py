@@ -343,11 +343,97 @@ class Tokenizer:
     def decode_lossy(self, tokens: Iterable[int]) -> str:
         return self.decode_bytes(tokens).decode("utf-8", errors="replace")
 
+    def decode_packed(self, ids, offsets, return_stats: bool = False):
+        """Batch decode on the device (spl_decode_batch; tokenizer.rs:877-897, 945-958): `ids` = concatenated
+        token ids (uint32), `offsets` = uint64[n_docs+1] token offsets.  Returns (bytes uint8[n_bytes],
+        byte_offsets uint64[n_docs+1]); UTF-8 validation is the caller's (decode_batch below does it)."""
+        lib = _lib.load()
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n_docs = offsets.shape[0] - 1
+        if n_docs < 0:
+            raise ValueError("offsets must have n_docs + 1 entries")
+        if int(offsets[-1]) != ids.shape[0]:
+            raise ValueError("offsets[-1] must equal the number of ids")
+        res = ctypes.c_void_p()
+        rc = lib.spl_decode_batch(self._handle, ctypes.c_void_p(ids.ctypes.data), ctypes.c_void_p(offsets.ctypes.data),
+                                  n_docs, ctypes.byref(res))
+        if rc != _lib.SPL_OK:
+            msg = _lib.last_error(self._handle)
+            if rc in (_lib.SPL_ERR_INVALID_ARG, _lib.SPL_ERR_UNSUPPORTED):
+                raise ValueError(msg)
+            raise RuntimeError(f"splintr_b200: {msg} (code {rc})")
+        try:
+            nb = lib.spl_result_n_bytes(res)
+            out = np.empty(nb, dtype=np.uint8)
+            out_off = np.empty(n_docs + 1, dtype=np.uint64)
+            if nb:
+                ctypes.memmove(out.ctypes.data, lib.spl_result_bytes(res), nb)
+            ctypes.memmove(out_off.ctypes.data, lib.spl_result_offsets(res), (n_docs + 1) * 8)
+            if return_stats:
+                st = _lib.SplStats()
+                lib.spl_result_stats(res, ctypes.byref(st))
+                return out, out_off, {f: getattr(st, f) for f, _ in _lib.SplStats._fields_}
+            return out, out_off
+        finally:
+            lib.spl_result_free(res)
+
+    def decode_device(self, d_ids, d_tok_offsets, dev_index: int = 0):
+        """Device-resident decode (spl_decode_batch_device): CUDA int32/uint32 ids tensor and CUDA int64 token
+        offsets [n_docs+1] -> (bytes uint8 tensor[n_bytes], byte offsets int64[n_docs+1]) on the same device."""
+        import torch
+        lib = _lib.load()
+        n_tok = int(d_ids.numel())
+        n_docs = int(d_tok_offsets.numel()) - 1
+        if d_ids.dtype not in (torch.int32, torch.uint32) or d_tok_offsets.dtype != torch.int64 or not d_tok_offsets.is_cuda:
+            raise TypeError("d_ids must be a CUDA int32 tensor and d_tok_offsets a CUDA int64 tensor")
+        out_off = torch.empty(n_docs + 1, dtype=torch.int64, device=d_tok_offsets.device)
+        stream = torch.cuda.current_stream(d_tok_offsets.device).cuda_stream
+        cap = max(n_tok * 4, 16)
+        for _ in range(2):
+            out = torch.empty(cap, dtype=torch.uint8, device=d_tok_offsets.device)
+            nb = ctypes.c_uint64(0)
+            rc = lib.spl_decode_batch_device(self._handle, dev_index, ctypes.c_void_p(d_ids.data_ptr()), n_tok,
+                                             ctypes.c_void_p(d_tok_offsets.data_ptr()), n_docs,
+                                             ctypes.c_void_p(out.data_ptr()), cap, ctypes.c_void_p(out_off.data_ptr()),
+                                             ctypes.c_void_p(stream), ctypes.byref(nb))
+            if rc == _lib.SPL_OK:
+                return out[:int(nb.value)], out_off
+            if rc == _lib.SPL_ERR_INVALID_ARG and int(nb.value) > cap:
+                cap = int(nb.value)
+                continue
+            raise RuntimeError(f"splintr_b200: {_lib.last_error(self._handle)} (code {rc})")
+        raise RuntimeError("splintr_b200: decode capacity retry failed")
+
+    def _decode_many(self, token_lists, errors: str) -> List[str]:
+        n = len(token_lists)
+        offsets = np.zeros(n + 1, dtype=np.uint64)
+        if n:
+            np.cumsum(np.fromiter((len(t) for t in token_lists), dtype=np.uint64, count=n), out=offsets[1:])
+        total = int(offsets[-1])
+        ids = np.fromiter((x for t in token_lists for x in t), dtype=np.int64, count=total)
+        if total and (ids.min() < 0 or ids.max() > 0xFFFFFFFF):
+            raise OverflowError("token ids must fit in u32")
+        data, off = self.decode_packed(ids.astype(np.uint32), offsets)
+        raw = data.tobytes()
+        out = []
+        for i in range(n):
+            b = raw[int(off[i]):int(off[i + 1])]
+            if errors == "strict":
+                try:
+                    out.append(b.decode("utf-8"))
+                except UnicodeDecodeError:
+                    raise ValueError("Decoding error: invalid UTF-8")
+            else:
+                out.append(b.decode("utf-8", errors="replace"))
+        return out
+
     def decode_batch(self, token_lists: List[List[int]]) -> List[str]:
-        return [self.decode(t) for t in token_lists]
+        """bindings.rs:364-370 -> tokenizer.rs:945-950: on the device (one call for the whole batch)."""
+        return self._decode_many(token_lists, "strict")
 
     def decode_batch_lossy(self, token_lists: List[List[int]]) -> List[str]:
-        return [self.decode_lossy(t) for t in token_lists]
+        return self._decode_many(token_lists, "replace")
 
     # -- misc -------------------------------------------------------------------------------
     @property

@@ -272,3 +272,49 @@ def test_cfg3_large_host_call_equals_parts(toks):
         parts_off.append(po[1:] + parts_off[-1][-1])
     assert np.array_equal(np.concatenate(parts_ids), ids)
     assert np.array_equal(np.concatenate(parts_off), off)
+
+
+# ---- decode on the device ---------------------------------------------------------
+@pytest.mark.parametrize("name", VOCABS)
+def test_decode_batch_matches_host_decode(toks, name):
+    """spl_decode_batch against the host table lookup (mirror of tokenizer.rs:877-897) on ordinary ids, special
+    ids, ids outside the vocabulary (skipped) and, for the byte-level vocabulary, the untranslatable keys."""
+    t = toks(name)
+    rng = random.Random(99)
+    vs = t.vocab_size
+    sp = list(t._special_tokens.values())
+    lists = [[], [0], [1, 2, 3], [vs - 1], [vs + 5, 7, 2 ** 31 + 3], sp[:5], [sp[0], 11, sp[1]]]
+    lists += [[rng.randrange(vs) for _ in range(rng.randint(0, 300))] for _ in range(400)]
+    lists += [[rng.randrange(vs) for _ in range(5000)]]
+    off = np.cumsum([0] + [len(x) for x in lists]).astype(np.uint64)
+    ids = np.array([x for l in lists for x in l], dtype=np.uint32)
+    data, boff = t.decode_packed(ids, off)
+    raw = data.tobytes()
+    for i, l in enumerate(lists):
+        assert raw[int(boff[i]):int(boff[i + 1])] == t.decode_bytes(l), (name, i)
+    assert t.decode_batch_lossy(lists[:50]) == [t.decode_lossy(l) for l in lists[:50]]
+
+
+def test_decode_roundtrip_cfg2_full_and_device_entry(toks):
+    """encode -> decode over the whole cfg2 batch reproduces the input bytes and document boundaries exactly
+    (size-independent property), through the host call and through the device-resident entry point."""
+    import torch
+    tok = toks("cl100k_base")
+    d, o = synth.cfg2(vocab_bytes("cl100k_base"))
+    ids, off = tok.encode_packed(d, o)
+    data, boff = tok.decode_packed(ids, off)
+    assert np.array_equal(boff, o) and np.array_equal(data, d)
+    d_ids = torch.from_numpy(ids.astype(np.int64)).to(torch.int32).cuda()
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    out, out_off = tok.decode_device(d_ids, d_off)
+    assert torch.equal(out.cpu(), torch.from_numpy(d)) and np.array_equal(out_off.cpu().numpy().astype(np.uint64), o)
+    bad = next(i for i in range(1000) if tok.decode_bytes([i]).decode("utf-8", errors="replace") != tok.decode_bytes([i]).decode("latin-1")
+               and b"\xef\xbf\xbd" not in tok.decode_bytes([i]))
+    with pytest.raises(ValueError):                            # a lone byte >= 0x80 is not valid UTF-8 (bindings.rs:300-304)
+        tok.decode_batch([[bad]])
+
+
+def test_decode_batch_strings_roundtrip(toks):
+    t = toks("deepseek_v3")
+    texts = ["Hello 你好 World 世界!", "", " hello world ", "日本語のテキスト" * 50, "émoji 🌍 ok"]
+    assert t.decode_batch(t.encode_batch(texts)) == texts
