@@ -52,9 +52,16 @@ enum {
 #define SPL_PATTERN_CL100K      0   /* CL100K_BASE_PATTERN  src/core/tokenizer.rs:39            */
 #define SPL_PATTERN_O200K       1   /* O200K_BASE_PATTERN = LLAMA3_PATTERN  tokenizer.rs:42,45  */
 #define SPL_PATTERN_MISTRAL_V3  2   /* MISTRAL_V3_PATTERN  src/core/tokenizer.rs:64             */
+#define SPL_PATTERN_SENTENCEPIECE 3 /* SENTENCEPIECE_PATTERN tokenizer.rs:56, with SPL_CREATE_SENTENCEPIECE */
 
 /* spl_create flags */
 #define SPL_CREATE_BYTE_LEVEL   1u  /* vocabulary keys are GPT-2 byte-level strings (from_bytes_byte_level) */
+#define SPL_CREATE_SENTENCEPIECE 2u /* SentencePiece mode (Tokenizer::from_bytes_sentencepiece, tokenizer.rs:589-640):
+                                     * spaces become U+2581 prefixes of the following word, other ASCII whitespace is
+                                     * encoded byte by byte (the encode branch at tokenizer.rs:737-795); of duplicated
+                                     * vocabulary keys the FIRST id encodes and every id decodes (vocab.rs:101-143).
+                                     * Requires SPL_PATTERN_SENTENCEPIECE.  decode returns the raw bytes; turning
+                                     * U+2581 back into a space (tokenizer.rs:923-930) is string-level work of the host. */
 
 /* spl_encode_batch flags */
 #define SPL_ENCODE_WITH_SPECIAL 1u  /* recognise special-token strings (encode_batch_with_special) */
@@ -100,7 +107,8 @@ void spl_result_free(spl_result* r);
 /* Device-resident variant on the handle's device number `dev_index` (index into the
  * `devices` list of spl_create): all four buffers are device pointers on that device;
  * d_bytes must be 16-byte aligned and readable up to n_bytes rounded up to 16;
- * d_ids must hold ids_capacity >= n_bytes entries (worst case: one id per byte).
+ * d_ids must hold ids_capacity >= n_bytes entries (worst case: one id per byte; for a SentencePiece-mode
+ * handle n_bytes + 2 * (number of spaces) <= 3 * n_bytes, because a space becomes the three bytes of U+2581).
  * Work is enqueued on `cuda_stream` (a cudaStream_t, NULL = legacy default stream).
  * If n_tokens_out is non-NULL the call synchronises the stream and stores the id count;
  * otherwise it returns after enqueueing (d_out_offsets[n_docs] holds the count). */

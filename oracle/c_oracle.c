@@ -14,7 +14,9 @@
  *   src/core/bpe.rs:67-197         byte_pair_encode             -> byte_pair_encode()
  *   src/core/tokenizer.rs:693-724  encode_chunk_with_position   -> encode_chunk()  (LRU omitted:
  *                                  result-transparent, tokenizer.rs:667-690)
- *   src/core/tokenizer.rs:729-808  encode (non-SentencePiece)   -> encode_text()
+ *   src/core/tokenizer.rs:729-808  encode                       -> encode_text() (regex branch :796-807),
+ *                                                                  encode_text_sp() (SentencePiece branch :737-795)
+ *   src/core/vocab.rs:101-143      load_tiktoken_bpe_with_decoder -> parse_vocab(first_wins = 1)
  *   src/core/tokenizer.rs:842-874  encode_with_special          -> encode_text_special()
  *   src/core/tokenizer.rs:932-942  encode_batch (Rayon par_iter)-> orc_encode_batch() (OpenMP,
  *                                  schedule(dynamic) over documents)
@@ -114,7 +116,8 @@ static uint32_t bmap_get(const bmap* m, const uint8_t* p, size_t n) {
     }
 }
 
-static int bmap_put(bmap* m, const uint8_t* p, size_t n, uint32_t rank) {   /* insert overwrites (vocab.rs:85) */
+/* insert overwrites (vocab.rs:85) unless first_wins (SentencePiece vocabularies, vocab.rs:139) */
+static int bmap_put(bmap* m, const uint8_t* p, size_t n, uint32_t rank, int first_wins) {
     uint32_t h = (uint32_t)hash_bytes(p, n) & m->mask;
     for (;;) {
         slot* s = &m->slots[h];
@@ -130,7 +133,7 @@ static int bmap_put(bmap* m, const uint8_t* p, size_t n, uint32_t rank) {   /* i
             m->pool_len += n;
             return 0;
         }
-        if (s->len == n && memcmp(m->pool + s->off, p, n) == 0) { s->rank = rank; return 0; }
+        if (s->len == n && memcmp(m->pool + s->off, p, n) == 0) { if (!first_wins) s->rank = rank; return 0; }
         h = (h + 1) & m->mask;
     }
 }
@@ -139,7 +142,7 @@ static int bmap_put(bmap* m, const uint8_t* p, size_t n, uint32_t rank) {   /* i
 typedef struct {
     bmap enc;
     pcre2_code* re;
-    int byte_level;
+    int byte_level, sentencepiece;
     uint8_t bl_utf8[256][2]; uint8_t bl_len[256];
     uint8_t** sp_str; uint32_t* sp_len; uint32_t* sp_id; uint32_t n_sp;
     uint8_t sp_last[256];
@@ -203,7 +206,7 @@ static int parse_vocab(orc* t, const uint8_t* data, size_t len) {
                 if (line[i] < '0' || line[i] > '9') { snprintf(t->err, sizeof t->err, "Invalid line format: Invalid rank"); free(tmp); return -1; }
                 r = r * 10 + (line[i] - '0');
             }
-            if (bmap_put(&t->enc, tmp, (size_t)tl, (uint32_t)r)) { free(tmp); return -1; }
+            if (bmap_put(&t->enc, tmp, (size_t)tl, (uint32_t)r, t->sentencepiece)) { free(tmp); return -1; }
         }
         pos = eol + 1;
     }
@@ -310,8 +313,27 @@ static int encode_chunk(const orc* t, scratch* sc, const uint8_t* piece, size_t 
     return byte_pair_encode(t, sc, piece, n, out);
 }
 
+/* tokenizer.rs:666-690 (LRU skipped) */
+static int encode_bytes(const orc* t, scratch* sc, const uint8_t* b, size_t n, u32vec* out) {
+    uint32_t r = n ? bmap_get(&t->enc, b, n) : RANK_NONE;
+    if (r != RANK_NONE) return push(out, r);
+    return byte_pair_encode(t, sc, b, n, out);
+}
+
+/* k copies of U+2581 (E2 96 81) followed by tail[0, m), through encode_bytes */
+static int encode_underscores(const orc* t, scratch* sc, size_t k, const uint8_t* tail, size_t m, u32vec* out) {
+    size_t need = 3 * k + m;
+    if (sc->blcap < need + 2) { free(sc->bl); sc->blcap = 2 * need + 64; sc->bl = (uint8_t*)malloc(sc->blcap); if (!sc->bl) return -1; }
+    for (size_t i = 0; i < k; ++i) { sc->bl[3 * i] = 0xE2; sc->bl[3 * i + 1] = 0x96; sc->bl[3 * i + 2] = 0x81; }
+    if (m) memcpy(sc->bl + 3 * k, tail, m);
+    return encode_bytes(t, sc, sc->bl, need, out);
+}
+
+static int encode_text_sp(const orc* t, scratch* sc, const uint8_t* text, size_t n, u32vec* out);
+
 /* tokenizer.rs:729-808, regex find_iter :244-257 */
 static int encode_text(const orc* t, scratch* sc, const uint8_t* text, size_t n, u32vec* out) {
+    if (t->sentencepiece) return encode_text_sp(t, sc, text, n, out);
     size_t pos = 0;
     while (pos < n) {
         int rc = P.match(t->re, text, n, pos, PCRE2_NO_UTF_CHECK, sc->md, sc->mc);
@@ -325,6 +347,34 @@ static int encode_text(const orc* t, scratch* sc, const uint8_t* text, size_t n,
         if (encode_chunk(t, sc, text + s, e - s, out)) return -1;
         pos = e;
     }
+    return 0;
+}
+
+/* tokenizer.rs:737-795: the SentencePiece branch of encode */
+static int encode_text_sp(const orc* t, scratch* sc, const uint8_t* text, size_t n, u32vec* out) {
+    size_t pos = 0, pending = 0;                                       /* U+2581 to prepend to the next word */
+    while (pos < n) {
+        int rc = P.match(t->re, text, n, pos, PCRE2_NO_UTF_CHECK, sc->md, sc->mc);
+        if (rc == -46 || rc == -47) rc = P.match(t->re, text, n, pos, PCRE2_NO_UTF_CHECK | PCRE2_NO_JIT, sc->md, sc->mc);
+        if (rc == -1) break;
+        if (rc < 0) return -2;
+        size_t* ov = P.ovector(sc->md);
+        size_t s = ov[0], e = ov[1];
+        if (e <= s) { pos = s + 1; continue; }
+        uint8_t b0 = text[s];
+        if (b0 == ' ' || b0 == '\t' || b0 == '\n' || b0 == 0x0C || b0 == '\r') {      /* u8::is_ascii_whitespace, :750 */
+            for (size_t i = s; i < e; ++i) {                                           /* byte by byte, :752 */
+                if (text[i] == ' ') { ++pending; continue; }
+                if (pending) { if (encode_underscores(t, sc, pending, NULL, 0, out)) return -1; pending = 0; }
+                if (encode_bytes(t, sc, text + i, 1, out)) return -1;
+            }
+        } else if (pending) {
+            if (encode_underscores(t, sc, pending, text + s, e - s, out)) return -1;
+            pending = 0;
+        } else if (encode_bytes(t, sc, text + s, e - s, out)) return -1;
+        pos = e;
+    }
+    if (pending && encode_underscores(t, sc, pending, NULL, 0, out)) return -1;        /* :787-790 */
     return 0;
 }
 
@@ -372,7 +422,8 @@ void* orc_create(const uint8_t* vocab, size_t vocab_len, const char* pattern, in
     if (load_pcre2(err, errcap)) return NULL;
     orc* t = (orc*)calloc(1, sizeof(orc));
     if (!t) return NULL;
-    t->byte_level = byte_level;
+    t->sentencepiece = (byte_level & 2) != 0;      /* `byte_level` carries the mode flags: 1 byte-level, 2 SentencePiece */
+    t->byte_level = (byte_level & 1) != 0;
     build_byte_level(t);
     if (parse_vocab(t, vocab, vocab_len)) { snprintf(err, errcap, "%s", t->err[0] ? t->err : "out of memory"); orc_destroy(t); return NULL; }
     int ec = 0; size_t eo = 0;

@@ -59,14 +59,16 @@ class COracle:
     """C restatement of core::Tokenizer's encode path (PCRE2 backend, linked-list BPE)."""
 
     def __init__(self, vocab_data: bytes, pattern: str, special_tokens: Optional[Dict[str, int]] = None,
-                 byte_level: bool = False):
+                 byte_level: bool = False, sentencepiece: bool = False):
         lib = _load()
+        self._cap_mul = 3 if sentencepiece else 1          # a space becomes the 3 bytes of U+2581
         sp = list((special_tokens or {}).items())
         n = len(sp)
         strs = (ctypes.c_char_p * max(n, 1))(*[s.encode("utf-8") for s, _ in sp])
         ids = (ctypes.c_uint32 * max(n, 1))(*[i for _, i in sp])
         err = ctypes.create_string_buffer(256)
-        self._h = lib.orc_create(vocab_data, len(vocab_data), pattern.encode("utf-8"), int(byte_level),
+        self._h = lib.orc_create(vocab_data, len(vocab_data), pattern.encode("utf-8"),
+                                 int(bool(byte_level)) | (2 if sentencepiece else 0),
                                  strs, ids, n, err, 256)
         if not self._h:
             raise ValueError(err.value.decode("utf-8", "replace"))
@@ -82,7 +84,7 @@ class COracle:
         data = np.ascontiguousarray(data, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         n_docs = len(offsets) - 1
-        cap = int(offsets[-1]) + 16 if n_docs >= 0 else 16
+        cap = self._cap_mul * int(offsets[-1]) + 16 if n_docs >= 0 else 16
         ids = np.empty(cap, dtype=np.uint32)
         out_off = np.zeros(n_docs + 1, dtype=np.uint64)
         n = _load().orc_encode_batch(self._h, data.ctypes.data, offsets.ctypes.data, n_docs, int(with_special),

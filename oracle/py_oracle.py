@@ -11,7 +11,11 @@ Restated from (all paths under /root/reference):
   * src/core/bpe.rs:67-197         byte_pair_encode       -> byte_pair_encode()
   * src/core/tokenizer.rs:693-724  encode_chunk_with_position (LRU omitted: it is
                                    result-transparent)    -> OracleTokenizer._encode_chunk()
-  * src/core/tokenizer.rs:729-808  encode (non-SentencePiece branch :796-807)
+  * src/core/tokenizer.rs:729-808  encode (non-SentencePiece branch :796-807; SentencePiece
+                                   branch :737-795 -> OracleTokenizer._encode_sentencepiece())
+  * src/core/vocab.rs:101-143      load_tiktoken_bpe_with_decoder (SentencePiece vocabularies:
+                                   the FIRST id of a duplicated byte string encodes, every id decodes)
+  * src/core/tokenizer.rs:923-930  postprocess_decode (U+2581 -> space)
   * src/core/tokenizer.rs:842-874  encode_with_special
   * src/core/tokenizer.rs:932-942  encode_batch / encode_batch_with_special
   * src/core/tokenizer.rs:877-911  decode_bytes / decode / decode_lossy
@@ -63,6 +67,29 @@ def load_tiktoken_bpe(data: bytes) -> Dict[bytes, int]:
         tok = base64.b64decode(line[:sp], validate=True)
         enc[tok] = int(line[sp + 1:].decode("utf-8").strip())
     return enc
+
+
+def load_tiktoken_bpe_with_decoder(data: bytes) -> Tuple[Dict[bytes, int], Dict[int, bytes]]:
+    """vocab.rs:101-143 -- the encoder keeps the FIRST occurrence of a byte string
+    (`entry().or_insert`, :139), the decoder keeps every id (:135)."""
+    enc: Dict[bytes, int] = {}
+    dec: Dict[int, bytes] = {}
+    for line in data.split(b"\n"):
+        if not line:
+            continue
+        sp = line.rfind(b" ")
+        if sp < 0:
+            raise ValueError("Invalid line format: Missing space separator")
+        tok = base64.b64decode(line[:sp], validate=True)
+        rank = int(line[sp + 1:].decode("utf-8").strip())
+        dec[rank] = tok
+        enc.setdefault(tok, rank)
+    return enc, dec
+
+
+SENTENCEPIECE_PATTERN = r"[^\s]+|\s+"          # tokenizer.rs:56
+_SP_UNDERSCORE = "\u2581".encode("utf-8")     # E2 96 81
+_ASCII_WS = frozenset(b" \t\n\x0c\r")          # u8::is_ascii_whitespace (no VT)
 
 
 def _build_byte_to_char() -> List[str]:
@@ -176,12 +203,17 @@ def byte_pair_encode(piece: bytes, encoder: Dict[bytes, int]) -> List[int]:
 
 
 class OracleTokenizer:
-    """Restatement of core::Tokenizer for the non-SentencePiece encode path."""
+    """Restatement of core::Tokenizer (encode / decode paths, both modes)."""
 
     def __init__(self, encoder: Dict[bytes, int], special_tokens: Dict[str, int],
-                 pattern: str, byte_level: bool = False):
+                 pattern: str, byte_level: bool = False, sentencepiece: bool = False,
+                 decoder: Optional[Dict[int, bytes]] = None):
         self.encoder = encoder
-        self.decoder = {v: k for k, v in encoder.items()}          # vocab.rs:146-148
+        self.decoder = decoder if decoder is not None else {v: k for k, v in encoder.items()}   # vocab.rs:146-148
+        self.sentencepiece = sentencepiece
+        if sentencepiece:                                           # tokenizer.rs:597-600
+            for s_, i_ in special_tokens.items():
+                self.decoder[i_] = s_.encode("utf-8")
         self.special_tokens = dict(special_tokens)
         self.special_tokens_decoder = {v: k for k, v in special_tokens.items()}
         self.pattern = pattern
@@ -191,7 +223,11 @@ class OracleTokenizer:
 
     @classmethod
     def from_bytes(cls, vocab_data: bytes, pattern: str,
-                   special_tokens: Optional[Dict[str, int]] = None, byte_level: bool = False):
+                   special_tokens: Optional[Dict[str, int]] = None, byte_level: bool = False,
+                   sentencepiece: bool = False):
+        if sentencepiece:                                           # tokenizer.rs:589-640
+            enc, dec = load_tiktoken_bpe_with_decoder(vocab_data)
+            return cls(enc, special_tokens or {}, pattern, False, True, dec)
         return cls(load_tiktoken_bpe(vocab_data), special_tokens or {}, pattern, byte_level)
 
     # -- tokenizer.rs:244-257 ------------------------------------------------------
@@ -212,9 +248,52 @@ class OracleTokenizer:
 
     # -- tokenizer.rs:729-808 ----------------------------------------------------------
     def encode(self, text: str) -> List[int]:
+        if self.sentencepiece:
+            return self._encode_sentencepiece(text)
         out: List[int] = []
         for s, e in self.find_iter(text):
             out.extend(self._encode_chunk(text[s:e].encode("utf-8")))
+        return out
+
+    # -- tokenizer.rs:666-690 (LRU skipped) --------------------------------------------
+    def _encode_bytes(self, b: bytes) -> List[int]:
+        r = self.encoder.get(b)
+        if r is not None:
+            return [r]
+        return byte_pair_encode(b, self.encoder)
+
+    # -- tokenizer.rs:737-795 ----------------------------------------------------------
+    def sentencepiece_pieces(self, text: str) -> List[bytes]:
+        """The byte strings the SentencePiece branch hands to encode_bytes_with_cache, in order."""
+        out: List[bytes] = []
+        pending = 0                                   # count of U+2581 to prepend to the next word
+        for s, e in self.find_iter(text):
+            sl = text[s:e].encode("utf-8")
+            if not sl:
+                continue
+            if sl[0] in _ASCII_WS:                    # :750 -- decided by the FIRST BYTE only
+                for b in sl:                          # :752 -- byte by byte
+                    if b == 0x20:
+                        pending += 1
+                    else:
+                        if pending:
+                            out.append(_SP_UNDERSCORE * pending)
+                            pending = 0
+                        out.append(bytes([b]))
+            else:
+                if pending:
+                    out.append(_SP_UNDERSCORE * pending + sl)
+                    pending = 0
+                else:
+                    out.append(sl)
+        if pending:                                   # :787-790 trailing spaces
+            out.append(_SP_UNDERSCORE * pending)
+        return out
+
+    def _encode_sentencepiece(self, text: str) -> List[int]:
+        out: List[int] = []
+        for piece in self.sentencepiece_pieces(text):
+            out.extend(self._encode_bytes(piece))
         return out
 
     # -- aho-corasick Standard, non-overlapping ---------------------------------------
@@ -281,14 +360,17 @@ class OracleTokenizer:
                     out += s.encode("utf-8")
         return bytes(out)
 
+    def _postprocess(self, text: str) -> str:                       # tokenizer.rs:923-930
+        return text.replace("\u2581", " ") if self.sentencepiece else text
+
     def decode(self, tokens: List[int]) -> str:
         try:
-            return self.decode_bytes(tokens).decode("utf-8")
+            return self._postprocess(self.decode_bytes(tokens).decode("utf-8"))
         except UnicodeDecodeError:
             raise ValueError("Decoding error: invalid UTF-8")
 
     def decode_lossy(self, tokens: List[int]) -> str:
-        return self.decode_bytes(tokens).decode("utf-8", errors="replace")
+        return self._postprocess(self.decode_bytes(tokens).decode("utf-8", errors="replace"))
 
     @property
     def vocab_size(self) -> int:                 # tokenizer.rs:964-972

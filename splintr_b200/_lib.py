@@ -13,8 +13,8 @@ from typing import List, Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libsplintr_b200.so")
-SOURCES = ["spl_api.cu", "spl_kernels.cu", "spl_encode.cu", "spl_decode.cu", "spl_host.cpp"]
-HEADERS = ["spl_common.h", "spl_pretok.h", "spl_pretok_fast.h", "spl_host.h", "spl_kernels.cuh", "spl_device.cuh", "unicode_tables.inc",
+SOURCES = ["spl_api.cu", "spl_kernels.cu", "spl_encode.cu", "spl_decode.cu", "spl_sentencepiece.cu", "spl_host.cpp"]
+HEADERS = ["spl_common.h", "spl_pretok.h", "spl_pretok_fast.h", "spl_sentencepiece.h", "spl_host.h", "spl_kernels.cuh", "spl_device.cuh", "unicode_tables.inc",
            os.path.join("..", "..", "include", "splintr_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -67,6 +67,7 @@ EXPORTS = ["spl_create", "spl_destroy", "spl_last_error", "spl_encode_batch", "s
 SPL_OK, SPL_ERR_INVALID_ARG, SPL_ERR_VOCAB, SPL_ERR_CUDA, SPL_ERR_OOM, SPL_ERR_UNSUPPORTED, SPL_ERR_NO_DEVICE = \
     0, -1, -2, -3, -4, -5, -6
 SPL_CREATE_BYTE_LEVEL = 1
+SPL_CREATE_SENTENCEPIECE = 2
 SPL_ENCODE_WITH_SPECIAL = 1
 
 _lib: Optional[ctypes.CDLL] = None

@@ -57,6 +57,7 @@ struct DevCtx {
     DevBuf text, doc_off, ids, out_off;          // spl_encode_batch: the shard's buffers
     DevBuf zero, tstate, pv, pool, mlist, fbl, huge;
     DevBuf dec_ids, dec_off, dec_ws, dec_out, dec_out_off;       // spl_decode_batch   // per-pass workspace (zero: everything that starts cleared)
+    DevBuf sp_zero, sp_tiles, sp_text, sp_doc;                   // SentencePiece mode: bitmaps over T, tile counts, T', offsets in T'
     size_t huge_words = 0;
     SplKernelProfile prof;
     bool prof_ready = false;
@@ -148,7 +149,7 @@ int upload_tables(spl_tokenizer* tk, DevCtx& dc) {
 
 void destroy_ctx(DevCtx& dc) {
     cudaSetDevice(dc.device);
-    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.ids, &dc.out_off, &dc.dec_ids, &dc.dec_off, &dc.dec_ws, &dc.dec_out, &dc.dec_out_off, &dc.zero, &dc.tstate, &dc.pv, &dc.pool, &dc.mlist, &dc.fbl, &dc.huge})
+    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.ids, &dc.out_off, &dc.dec_ids, &dc.dec_off, &dc.dec_ws, &dc.dec_out, &dc.dec_out_off, &dc.sp_zero, &dc.sp_tiles, &dc.sp_text, &dc.sp_doc, &dc.zero, &dc.tstate, &dc.pv, &dc.pool, &dc.mlist, &dc.fbl, &dc.huge})
         b->release();
     if (dc.table_blob) cudaFree(dc.table_blob);
     for (auto& e : dc.ev) if (e) cudaEventDestroy(e);
@@ -252,6 +253,87 @@ int check_special_support(spl_tokenizer* tk, uint32_t flags, bool& with_special)
     return SPL_OK;
 }
 
+bool is_sentencepiece(const spl_tokenizer* tk) { return tk->host.pattern == SPL_PAT_SENTENCEPIECE; }
+
+// ids an input of n bytes can produce at most: one per byte, except that SentencePiece mode turns a space into the
+// three bytes of U+2581, which can stay three byte tokens
+uint64_t ids_bound(const spl_tokenizer* tk, uint64_t n_bytes) { return is_sentencepiece(tk) ? 3 * n_bytes : n_bytes; }
+
+struct EncodeArgs {
+    const uint8_t* text; uint64_t N;
+    const uint64_t* doc_off; uint64_t off_base; uint64_t n_docs;
+    uint32_t* ids; uint64_t ids_cap; uint64_t* out_off; uint64_t* host_meta;
+};
+
+// Enqueue the encode path for one device pass on `st`; `w` is the workspace view the pass uses (its counters are what
+// the caller reads back).  SentencePiece mode (tokenizer.rs:737-795) first builds the transformed text T' -- that needs
+// the size of T' on the host, i.e. one stream synchronisation in the middle -- and then runs the ordinary encode stage
+// over T'.
+int enqueue_encode(spl_tokenizer* tk, DevCtx& dc, cudaStream_t st, const EncodeArgs& a, bool with_special,
+                   SplKernelProfile* prof, SplWork& w, int& launches) {
+    int rc;
+    memset(&w, 0, sizeof(w));
+    if (!is_sentencepiece(tk)) {
+        if ((rc = prepare_work(tk, dc, a.N, a.n_docs, with_special, st, w))) return rc;
+        w.text = a.text; w.doc_off = a.doc_off; w.off_base = a.off_base;
+        w.ids = a.ids; w.out_off = a.out_off; w.host_meta = a.host_meta;
+        launches += spl_launch_encode(w, dc.num_sms, st, prof);
+        return SPL_OK;
+    }
+    if (3 * a.N > kMaxShardBytes || a.n_docs > 0xFFFFFFF0ull) {
+        tk->err = "one SentencePiece-mode device pass is limited to 4/3 GiB of text";
+        return SPL_ERR_UNSUPPORTED;
+    }
+    // ---- bitmaps over T: counters | tinfo | hard | spec | w0 | a | rs (one memset) ----
+    const size_t words = (size_t)((a.N + SPL_WIN) / 32 + 16), n_tiles = (size_t)(a.N / SPL_TILE) + 1;
+    const size_t off_tinfo = 256, off_hard = align_up(off_tinfo + (n_tiles + 2) * sizeof(SplTileInfo), 256);
+    const size_t bm = align_up(words * 4, 256);
+    const size_t off_spec = off_hard + bm, off_w0 = off_spec + (with_special ? bm : 0), off_a = off_w0 + bm, off_rs = off_a + bm;
+    if ((rc = dc.sp_zero.ensure(off_rs + bm, tk->err))) return rc;
+    if ((rc = dc.sp_tiles.ensure((2 * n_tiles + 2) * 4, tk->err))) return rc;
+    if ((rc = dc.sp_doc.ensure((a.n_docs + 1) * 8, tk->err))) return rc;
+    CUDA_TRY(cudaMemsetAsync(dc.sp_zero.p, 0, off_rs + bm, st), tk->err);
+    uint8_t* zb = (uint8_t*)dc.sp_zero.p;
+    SplWork v;
+    memset(&v, 0, sizeof(v));
+    v.text = a.text; v.N = (uint32_t)a.N; v.doc_off = a.doc_off; v.off_base = a.off_base; v.n_docs = (uint32_t)a.n_docs;
+    v.n_tiles = (uint32_t)n_tiles;
+    v.counters = (uint32_t*)zb; v.tinfo = (SplTileInfo*)(zb + off_tinfo);
+    v.hard = (uint32_t*)(zb + off_hard); v.pstart = v.hard;            // the sentinel bit N is a hard bit as well
+    v.spec = with_special ? (uint32_t*)(zb + off_spec) : nullptr;
+    v.T = dc.d_tables; v.pattern = tk->host.pattern; v.with_special = with_special;
+    launches += spl_launch_mark(v, dc.num_sms, st);
+    SplSpWork s;
+    memset(&s, 0, sizeof(s));
+    s.text = a.text; s.N = v.N; s.doc_off = a.doc_off; s.off_base = a.off_base; s.n_docs = v.n_docs; s.n_tiles = v.n_tiles;
+    s.hard = v.hard; s.spec = v.spec; s.tinfo = v.tinfo;
+    s.w0 = (uint32_t*)(zb + off_w0); s.a = (uint32_t*)(zb + off_a); s.rs = (uint32_t*)(zb + off_rs);
+    s.tile_cnt = (uint32_t*)dc.sp_tiles.p; s.tile_pref = s.tile_cnt + n_tiles;
+    s.counters = v.counters; s.T = dc.d_tables;
+    launches += spl_launch_sp_scan(s, st);
+    uint32_t h_ctr[8];
+    CUDA_TRY(cudaMemcpyAsync(h_ctr, v.counters, sizeof(h_ctr), cudaMemcpyDeviceToHost, st), tk->err);
+    CUDA_TRY(cudaStreamSynchronize(st), tk->err);
+    if (h_ctr[SPL_CTR_ERR] & SPL_DEVERR_OFFSETS) {
+        tk->err = "document offsets are not a non-decreasing sequence from 0 to n_bytes";
+        return SPL_ERR_INVALID_ARG;
+    }
+    const uint64_t N2 = a.N + 2ull * h_ctr[SPL_SPCTR_CONV];
+    if (a.ids_cap < N2) {
+        tk->err = "ids_capacity too small (SentencePiece mode: up to three ids per input byte)";
+        return SPL_ERR_INVALID_ARG;
+    }
+    if ((rc = dc.sp_text.ensure((size_t)N2 + 64, tk->err))) return rc;
+    if ((rc = prepare_work(tk, dc, N2, a.n_docs, with_special, st, w))) return rc;
+    w.text = (const uint8_t*)dc.sp_text.p; w.doc_off = (const uint64_t*)dc.sp_doc.p; w.off_base = 0;
+    w.ids = a.ids; w.out_off = a.out_off; w.host_meta = a.host_meta;
+    w.pretok_done = true;
+    s.text2 = (uint8_t*)dc.sp_text.p; s.pstart2 = w.pstart; s.spec2 = w.spec; s.doc_off2 = (uint64_t*)dc.sp_doc.p;
+    launches += spl_launch_sp_emit(s, st);
+    launches += spl_launch_encode(w, dc.num_sms, st, prof);
+    return SPL_OK;
+}
+
 PinnedBuf take_pinned(spl_tokenizer* tk, size_t bytes) {
     bytes = std::max<size_t>(bytes, 64);
     {
@@ -291,8 +373,14 @@ int spl_create(const uint8_t* vocab, size_t vocab_len, int pattern_id, uint32_t 
     if (!out) return SPL_ERR_INVALID_ARG;
     *out = nullptr;
     if (!vocab || (n_special && (!special_strs || !special_ids))) { g_create_error = "null argument"; return SPL_ERR_INVALID_ARG; }
-    if (pattern_id != SPL_PATTERN_CL100K && pattern_id != SPL_PATTERN_O200K && pattern_id != SPL_PATTERN_MISTRAL_V3) {
+    if (pattern_id != SPL_PATTERN_CL100K && pattern_id != SPL_PATTERN_O200K && pattern_id != SPL_PATTERN_MISTRAL_V3 &&
+        pattern_id != SPL_PATTERN_SENTENCEPIECE) {
         g_create_error = "unknown pattern id";
+        return SPL_ERR_INVALID_ARG;
+    }
+    if (((flags & SPL_CREATE_SENTENCEPIECE) != 0) != (pattern_id == SPL_PATTERN_SENTENCEPIECE) ||
+        ((flags & SPL_CREATE_SENTENCEPIECE) && (flags & SPL_CREATE_BYTE_LEVEL))) {
+        g_create_error = "SPL_CREATE_SENTENCEPIECE goes with SPL_PATTERN_SENTENCEPIECE (and not with SPL_CREATE_BYTE_LEVEL)";
         return SPL_ERR_INVALID_ARG;
     }
     int ndev_avail = 0;
@@ -305,7 +393,8 @@ int spl_create(const uint8_t* vocab, size_t vocab_len, int pattern_id, uint32_t 
     if (!tk) return SPL_ERR_OOM;
     if (const char* tr = getenv("SPL_TRACE")) tk->trace = tr[0] == '1';
     if (const char* cb = getenv("SPL_CHUNK_BYTES")) tk->chunk_bytes = strtoull(cb, nullptr, 10);
-    uint32_t hflags = (flags & SPL_CREATE_BYTE_LEVEL) ? SPL_FLAG_BYTE_LEVEL : 0;
+    uint32_t hflags = ((flags & SPL_CREATE_BYTE_LEVEL) ? SPL_FLAG_BYTE_LEVEL : 0) |
+                      ((flags & SPL_CREATE_SENTENCEPIECE) ? SPL_FLAG_SENTENCEPIECE : 0);
     if (!spl_build_tables(tk->host, vocab, vocab_len, pattern_id, hflags, special_strs, special_ids, n_special)) {
         g_create_error = tk->host.error;
         bool unsupported = tk->host.error.find("byte-level vocabulary") != std::string::npos ||
@@ -358,6 +447,7 @@ const char* spl_last_error(const spl_tokenizer* tk) { return tk ? tk->err.c_str(
 int spl_launches_per_call(const spl_tokenizer* tk, uint32_t flags) {
     if (!tk) return 0;
     bool ws = (flags & SPL_ENCODE_WITH_SPECIAL) && !tk->host.sp_id.empty();
+    if (is_sentencepiece(tk)) return 11 + (ws ? 1 : 0);                // mark (T), 4 x scan, sp_emit, mark (T'), probe, bpe, chunk_scan, emit
     int pre = tk->host.pattern == SPL_PAT_MISTRAL_V3 ? 1 : 2;          // sequential rules | bit-parallel + fallback
     return 5 + pre + (ws ? 1 : 0);                                     // mark_docs, probe, bpe, chunk_scan, emit
 }
@@ -395,7 +485,7 @@ int spl_encode_batch_device(spl_tokenizer* tk, int dev_index, const uint8_t* d_b
                             void* cuda_stream, uint64_t* n_tokens_out) {
     if (!tk) return SPL_ERR_INVALID_ARG;
     if (dev_index < 0 || (size_t)dev_index >= tk->devs.size() || !d_offsets || !d_out_offsets ||
-        (n_bytes && (!d_bytes || !d_ids)) || ids_capacity < n_bytes || ((uintptr_t)d_bytes & 15u)) {
+        (n_bytes && (!d_bytes || !d_ids)) || (!is_sentencepiece(tk) && ids_capacity < n_bytes) || ((uintptr_t)d_bytes & 15u)) {
         tk->err = "invalid argument (null pointer, ids_capacity < n_bytes, or d_bytes not 16-byte aligned)";
         return SPL_ERR_INVALID_ARG;
     }
@@ -408,9 +498,6 @@ int spl_encode_batch_device(spl_tokenizer* tk, int dev_index, const uint8_t* d_b
     cudaStream_t st = (cudaStream_t)cuda_stream;
     for (int attempt = 0;; ++attempt) {
         SplWork w;
-        memset(&w, 0, sizeof(w));
-        if ((rc = prepare_work(tk, dc, n_bytes, n_docs, with_special, st, w))) return rc;
-        w.text = d_bytes; w.doc_off = d_offsets; w.ids = d_ids; w.out_off = d_out_offsets;
         SplKernelProfile* prof = nullptr;
         if (tk->profiling) {
             if (!dc.prof_ready) {
@@ -420,7 +507,9 @@ int spl_encode_batch_device(spl_tokenizer* tk, int dev_index, const uint8_t* d_b
             }
             prof = &dc.prof;
         }
-        spl_launch_encode(w, dc.num_sms, st, prof);
+        int launches = 0;
+        EncodeArgs ea{d_bytes, n_bytes, d_offsets, 0, n_docs, d_ids, ids_capacity, d_out_offsets, nullptr};
+        if ((rc = enqueue_encode(tk, dc, st, ea, with_special, prof, w, launches))) return rc;
         CUDA_TRY(cudaGetLastError(), tk->err);
         if (!n_tokens_out) return SPL_OK;
         uint32_t h_counters[4];
@@ -483,7 +572,7 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
     for (size_t g = 0; g < G; ++g) {
         const uint64_t s0 = offsets[dlo[g]], s1 = offsets[dlo[g + 1]], nb = s1 - s0;
         uint64_t target = tk->chunk_bytes ? tk->chunk_bytes : std::min<uint64_t>(std::max<uint64_t>(nb / 8, 4u << 20), 256u << 20);
-        target = std::min<uint64_t>(target, kMaxShardBytes / 2);
+        target = std::min<uint64_t>(target, kMaxShardBytes / (is_sentencepiece(tk) ? 6 : 2));
         // the pipeline fills with the first chunk's copy-in and drains with the last chunk's copy-out: ramp the chunk
         // size up at the start and down at the end (quarter, half, full ... full, half, quarter) unless it was pinned
         const bool ramp = !tk->chunk_bytes && nb >= 4 * target;
@@ -506,7 +595,7 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
             if (ramp && rem <= want + want / 8) e = dlo[g + 1];
             if (d == dlo[g + 1]) e = d;                                                                    // shard without documents
             c.d1 = e; c.b1 = offsets[e];
-            c.text_off = toff; c.ids_off = (size_t)(c.b0 - s0);
+            c.text_off = toff; c.ids_off = (size_t)ids_bound(tk, c.b0 - s0);
             toff += align_up((size_t)(c.b1 - c.b0) + 16, 16);
             max_nb[g] = std::max<size_t>(max_nb[g], (size_t)(c.b1 - c.b0));
             max_nd[g] = std::max<size_t>(max_nd[g], c.d1 - c.d0);
@@ -554,9 +643,9 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
             int rc2;
             if ((rc2 = dc.text.ensure(text_need[g], tk->err))) return rc2;
             if ((rc2 = dc.doc_off.ensure((nd + 1) * 8, tk->err))) return rc2;
-            if ((rc2 = dc.ids.ensure((nb + 16) * 4, tk->err))) return rc2;
+            if ((rc2 = dc.ids.ensure((ids_bound(tk, nb) + 16) * 4, tk->err))) return rc2;
             if ((rc2 = dc.out_off.ensure((nd + 1) * 8, tk->err))) return rc2;
-            if ((rc2 = reserve_work(tk, dc, max_nb[g], max_nd[g], with_special))) return rc2;
+            if ((rc2 = reserve_work(tk, dc, ids_bound(tk, max_nb[g]), max_nd[g], with_special))) return rc2;
             size_t n_ev = 0;
             for (auto& c : chunks) if (c.g == (int)g) { c.ev = n_ev; n_ev += 4; }
             while (dc.pipe_ev.size() < n_ev + 1) {
@@ -598,7 +687,7 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
                 // size the result by the ids-per-byte ratio seen so far (+12 %), at least what is needed now
                 const uint64_t done_bytes = std::max<uint64_t>(c.b1, 1);
                 uint64_t est = (uint64_t)((double)total / (double)done_bytes * (double)N * 1.125) + 4096;
-                est = std::min<uint64_t>(std::max<uint64_t>(est, total + 16), N + 16);
+                est = std::min<uint64_t>(std::max<uint64_t>(est, total + 16), ids_bound(tk, N) + 16);
                 PinnedBuf nb = take_pinned(tk, est * 4);
                 if (!nb.p) { tk->err = "pinned host allocation failed"; return SPL_ERR_OOM; }
                 if (r->ids_buf.p) {
@@ -648,17 +737,10 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
                 CUDA_TRY(cudaStreamWaitEvent(dc.stream, ev_in, 0), tk->err);
                 CUDA_TRY(cudaEventRecord(ev_k0, dc.stream), tk->err);
                 SplWork w;
-                memset(&w, 0, sizeof(w));
                 int rc2;
-                if ((rc2 = prepare_work(tk, dc, nb, nd, with_special, dc.stream, w))) return rc2;
-                w.text = d_text;
-                w.doc_off = d_doc;
-                w.off_base = c.b0;
-                w.ids = (uint32_t*)dc.ids.p + c.ids_off;
                 uint64_t* d_out = (uint64_t*)dc.out_off.p + (c.d0 - dlo[g]);
-                w.out_off = d_out;
-                w.host_meta = c.d_meta;
-                launches += spl_launch_encode(w, dc.num_sms, dc.stream);
+                EncodeArgs ea{d_text, nb, d_doc, c.b0, nd, (uint32_t*)dc.ids.p + c.ids_off, ids_bound(tk, nb), d_out, c.d_meta};
+                if ((rc2 = enqueue_encode(tk, dc, dc.stream, ea, with_special, nullptr, w, launches))) return rc2;
                 CUDA_TRY(cudaGetLastError(), tk->err);
                 // the chunk's id count and error flags arrive in mapped host memory (written by k_emit): no copy on the
                 // kernel stream, which would queue behind the previous chunk's ids on the device-to-host engine
@@ -717,7 +799,7 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
             if (attempt >= 6) { tk->err = "scratch pool for very long pieces exhausted"; return fail(SPL_ERR_OOM); }
             for (size_t g = 0; g < G; ++g) {
                 cudaSetDevice(tk->devs[g].device);
-                if ((rc = reserve_work(tk, tk->devs[g], max_nb[g], max_nd[g], with_special))) return fail(rc);
+                if ((rc = reserve_work(tk, tk->devs[g], ids_bound(tk, max_nb[g]), max_nd[g], with_special))) return fail(rc);
             }
             continue;
         }

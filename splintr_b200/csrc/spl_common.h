@@ -40,7 +40,8 @@ enum : uint8_t {
 SPL_HD bool in_set(uint32_t cls, uint32_t set) { return (set >> cls) & 1u; }
 
 // ---- split patterns (C-ABI ids) ------------------------------------------------------
-enum : int { SPL_PAT_CL100K = 0, SPL_PAT_O200K = 1, SPL_PAT_MISTRAL_V3 = 2 };
+enum : int { SPL_PAT_CL100K = 0, SPL_PAT_O200K = 1, SPL_PAT_MISTRAL_V3 = 2,
+             SPL_PAT_SENTENCEPIECE = 3 };   // `[^\s]+|\s+` (tokenizer.rs:56) + the U+2581 walk of tokenizer.rs:737-795
 
 // ---- symbols ---------------------------------------------------------------------------
 // A "symbol" is a token id (= merge rank) or, for a single byte that is not in the

@@ -178,7 +178,8 @@ bool spl_build_tables(SplHostTables& t, const uint8_t* vocab, size_t vocab_len, 
                       const char* const* special_strs, const uint32_t* special_ids, size_t n_special) {
     t.pattern = pattern;
     t.flags = flags;
-    if (pattern != SPL_PAT_CL100K && pattern != SPL_PAT_O200K && pattern != SPL_PAT_MISTRAL_V3) {
+    if (pattern != SPL_PAT_CL100K && pattern != SPL_PAT_O200K && pattern != SPL_PAT_MISTRAL_V3 &&
+        pattern != SPL_PAT_SENTENCEPIECE) {
         t.error = "unsupported split pattern id";
         return false;
     }
@@ -237,6 +238,8 @@ bool spl_build_tables(SplHostTables& t, const uint8_t* vocab, size_t vocab_len, 
             }
             t.encoder[tr.raw] = tr.rank;
         }
+    } else if (flags & SPL_FLAG_SENTENCEPIECE) {
+        for (auto& e : entries) t.encoder.emplace(e.first, e.second);       // the FIRST occurrence encodes (vocab.rs:139)
     } else {
         for (auto& e : entries) t.encoder[e.first] = e.second;
     }
@@ -257,8 +260,11 @@ bool spl_build_tables(SplHostTables& t, const uint8_t* vocab, size_t vocab_len, 
         if (any && max_dec > 0x3FFFFFFu) { t.error = "token ids above 2^26 are not supported"; return false; }
         std::vector<std::string> dec(any ? (size_t)max_dec + 1 : 0);
         std::vector<uint8_t> has(dec.size(), 0);
+        const bool spm = (flags & SPL_FLAG_SENTENCEPIECE) != 0;
         for (auto& e : entries) {
-            if (final_rank[e.first] != e.second) continue;                  // an overwritten duplicate
+            // SentencePiece vocabularies decode EVERY id (vocab.rs:135); otherwise the decoder is the inverse of the
+            // encoder map, which has lost the overwritten duplicates
+            if (!spm && final_rank[e.first] != e.second) continue;
             std::string raw = e.first;
             if (flags & SPL_FLAG_BYTE_LEVEL) {
                 // byte_level_decode_bytes, falling back to the key itself (tokenizer.rs:883-887)
@@ -279,8 +285,8 @@ bool spl_build_tables(SplHostTables& t, const uint8_t* vocab, size_t vocab_len, 
             }
             dec[e.second] = raw; has[e.second] = 1;
         }
-        for (size_t i = 0; i < n_special; ++i)
-            if (!has[special_ids[i]]) { dec[special_ids[i]] = special_strs[i]; has[special_ids[i]] = 1; }
+        for (size_t i = 0; i < n_special; ++i)       // from_bytes_sentencepiece inserts the specials INTO the decoder (tokenizer.rs:597-600)
+            if (spm || !has[special_ids[i]]) { dec[special_ids[i]] = special_strs[i]; has[special_ids[i]] = 1; }
         t.dec_off.assign(dec.size() + 1, 0);
         t.dec_bytes.clear();
         for (size_t i = 0; i < dec.size(); ++i) {

@@ -12,7 +12,8 @@
 #include <unordered_map>
 #include "spl_common.h"
 
-enum : uint32_t { SPL_FLAG_BYTE_LEVEL = 1u };
+enum : uint32_t { SPL_FLAG_BYTE_LEVEL = 1u,
+                  SPL_FLAG_SENTENCEPIECE = 2u };   // vocab.rs:101-143: first id of a duplicated key encodes, every id decodes
 
 struct SplHostTables {
     int pattern = 0;

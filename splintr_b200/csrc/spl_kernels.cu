@@ -285,6 +285,16 @@ void mark_cb(void* p, const char* name) {
 }
 }  // namespace
 
+int spl_launch_mark(const SplWork& w, int num_sms, cudaStream_t stream) {
+    uint32_t n = w.n_docs + 1;
+    k_mark_docs<<<(n + 255) / 256, 256, 0, stream>>>(w);
+    if (!(w.with_special && w.N)) return 1;
+    uint32_t blocks = (w.N + 255) / 256;
+    uint32_t cap = (uint32_t)num_sms * 16;
+    k_mark_specials<<<blocks < cap ? blocks : cap, 256, 0, stream>>>(w);
+    return 2;
+}
+
 int spl_launch_encode(const SplWork& w, int num_sms, cudaStream_t stream, SplKernelProfile* prof) {
     MarkCtx mc{prof, stream, 0};
     if (prof) { prof->n = 0; cudaEventRecord(prof->ev[0], stream); }
@@ -294,13 +304,15 @@ int spl_launch_encode(const SplWork& w, int num_sms, cudaStream_t stream, SplKer
         k_mark_docs<<<(n + 255) / 256, 256, 0, stream>>>(w);
         mark("k_mark_docs");
     }
-    if (w.with_special && w.N) {
+    if (w.with_special && w.N && !w.pretok_done) {
         uint32_t blocks = (w.N + 255) / 256;
         uint32_t cap = (uint32_t)num_sms * 16;
         k_mark_specials<<<blocks < cap ? blocks : cap, 256, 0, stream>>>(w);
         mark("k_mark_specials");
     }
-    if (w.N && w.pattern == SPL_PAT_MISTRAL_V3) {
+    if (w.pretok_done) {
+        // SentencePiece mode: k_sp_emit has written the piece starts of the transformed text
+    } else if (w.N && w.pattern == SPL_PAT_MISTRAL_V3) {
         k_pretok<<<(w.N + SPL_TILE - 1) / SPL_TILE, SPL_THREADS, 0, stream>>>(w);
         mark("k_pretok");
     } else if (w.N) {

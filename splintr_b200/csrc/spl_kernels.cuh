@@ -79,6 +79,7 @@ struct SplWork {
     const SplTables* T;               // device copy of the tables
     int             pattern;
     bool            with_special;
+    bool            pretok_done;      // pstart / spec are already filled in (SentencePiece mode: written by k_sp_emit)
 };
 
 // SplWork::counters
@@ -89,7 +90,7 @@ enum : uint32_t { SPL_CTR_ERR = 1, SPL_CTR_HUGE_POOL = 2, SPL_CTR_FB = 3,
 enum : uint32_t { SPL_DEVERR_OFFSETS = 1u, SPL_DEVERR_HUGE_POOL = 2u };
 
 // optional per-kernel device timing: ev[i] is recorded before kernel i, ev[n] after the last
-#define SPL_PROF_MAX 12
+#define SPL_PROF_MAX 16
 struct SplKernelProfile {
     cudaEvent_t ev[SPL_PROF_MAX + 1];
     const char* name[SPL_PROF_MAX];
@@ -101,6 +102,28 @@ int spl_launch_encode(const SplWork& w, int num_sms, cudaStream_t stream, SplKer
 
 // Per-device one-time kernel attribute setup (shared-memory carveout).
 void spl_kernels_init();
+
+// spl_sentencepiece.cu: SentencePiece mode (tokenizer.rs:737-795).  Text T -> transformed text T' + its bitmaps.
+// All bitmaps are over T (zero-initialised by the caller); hard / spec / tinfo are filled by k_mark_docs /
+// k_mark_specials run on a view of T before spl_launch_sp_scan.
+#define SPL_SPCTR_CONV 4u             // counters[]: number of converted spaces (N' = N + 2 * that)
+struct SplSpWork {
+    const uint8_t*  text; uint32_t N;
+    const uint64_t* doc_off; uint64_t off_base; uint32_t n_docs;
+    uint32_t        n_tiles;                    // N / SPL_TILE + 1
+    const uint32_t* hard; const uint32_t* spec; // spec == nullptr without special tokens
+    const SplTileInfo* tinfo;                   // first_doc per tile
+    uint32_t *w0, *a, *rs;                      // bitmaps, see spl_sentencepiece.h
+    uint32_t *tile_cnt, *tile_pref;             // [n_tiles], [n_tiles + 1]
+    uint32_t* counters;
+    const SplTables* T;
+    // outputs (spl_launch_sp_emit)
+    uint8_t*  text2; uint32_t* pstart2; uint32_t* spec2; uint64_t* doc_off2;
+};
+int spl_launch_sp_scan(const SplSpWork& s, cudaStream_t stream);    // classify, raw runs, count, scan
+int spl_launch_sp_emit(const SplSpWork& s, cudaStream_t stream);
+// k_mark_docs (+ k_mark_specials) only: the segment bitmaps of a text (SentencePiece mode runs them over T)
+int spl_launch_mark(const SplWork& w, int num_sms, cudaStream_t stream);
 
 // spl_decode.cu: ids -> bytes (row N2)
 #define SPL_DEC_TILE 2048u            // ids per tile

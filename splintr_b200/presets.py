@@ -23,6 +23,7 @@ PATTERN_IDS = {
     O200K_BASE_PATTERN: 1,
     MISTRAL_V3_PATTERN: 2,
 }
+SPL_PATTERN_SENTENCEPIECE = 3      # SENTENCEPIECE_PATTERN, only together with SentencePiece mode
 
 # --- agent tokens (pretrained.rs:402-476): 54 names, ids base+0 .. base+53 -----------
 _AGENT_NAMES = [

@@ -56,6 +56,20 @@ def _parse_tiktoken(data: bytes) -> Dict[bytes, int]:
     return enc
 
 
+def _parse_tiktoken_decoder(data: bytes) -> Dict[int, bytes]:
+    """vocab.rs:101-143, decoder half: EVERY id of a SentencePiece vocabulary decodes (duplicated byte strings
+    keep all their ids; the encoder half -- first id wins -- lives in the C++ table builder)."""
+    dec: Dict[int, bytes] = {}
+    for line in data.split(b"\n"):
+        if not line:
+            continue
+        sp = line.rfind(b" ")
+        if sp < 0:
+            raise ValueError("Invalid line format: Missing space separator")
+        dec[int(line[sp + 1:].decode("utf-8").strip())] = base64.b64decode(line[:sp], validate=True)
+    return dec
+
+
 class Tokenizer:
     """Drop-in for `splintr.Tokenizer` (bindings.rs:57-446)."""
 
@@ -82,15 +96,18 @@ class Tokenizer:
     def _init(self, data: bytes, pattern: str, special_tokens: Dict[str, int], byte_level: bool,
               sentencepiece: bool, devices: Optional[Sequence[int]] = None) -> None:
         self._handle = None
-        if sentencepiece:
-            raise ValueError("SentencePiece-mode vocabularies (mistral / mistral_v2) are not served by the "
-                             "B200 encode path (see DESIGN.md, out of scope); no CPU fallback exists")
         if not isinstance(pattern, str):
             raise TypeError("pattern must be str")
-        pid = _presets.PATTERN_IDS.get(pattern)
+        if sentencepiece:
+            # tokenizer.rs:589-640 + the encode branch :737-795; the device implements that walk for the split
+            # the reference's presets use it with (`[^\s]+|\s+`, tokenizer.rs:56)
+            pid = _presets.SPL_PATTERN_SENTENCEPIECE if pattern == _presets.SENTENCEPIECE_PATTERN else None
+        else:
+            pid = _presets.PATTERN_IDS.get(pattern)
         if pid is None:
             raise ValueError("Regex compilation error: the device pre-tokenizer implements only the "
-                             "CL100K_BASE, O200K_BASE/LLAMA3 and MISTRAL_V3 patterns")
+                             "CL100K_BASE, O200K_BASE/LLAMA3 and MISTRAL_V3 patterns, and SENTENCEPIECE_PATTERN "
+                             "in SentencePiece mode")
         for k, v in special_tokens.items():
             if not isinstance(k, str) or not isinstance(v, int):
                 raise TypeError("special_tokens must map str -> int")
@@ -99,6 +116,7 @@ class Tokenizer:
         self._special_tokens = dict(special_tokens)
         self._special_decoder = {v: k for k, v in special_tokens.items()}
         self._byte_level = bool(byte_level)
+        self._sentencepiece = bool(sentencepiece)
         self._devices = list(devices) if devices is not None else None
         self._decoder: Optional[Dict[int, bytes]] = None
         self._vocab_size: Optional[int] = None
@@ -115,7 +133,8 @@ class Tokenizer:
             devs, ndev = None, 0
         h = ctypes.c_void_p()
         rc = lib.spl_create(self._vocab_data, len(self._vocab_data), pid,
-                            _lib.SPL_CREATE_BYTE_LEVEL if byte_level else 0,
+                            (_lib.SPL_CREATE_BYTE_LEVEL if byte_level else 0) |
+                            (_lib.SPL_CREATE_SENTENCEPIECE if sentencepiece else 0),
                             strs, ids, n, devs, ndev, ctypes.byref(h))
         if rc != _lib.SPL_OK:
             msg = _lib.last_error(None)
@@ -156,9 +175,15 @@ class Tokenizer:
         """tokenizer.rs:562-569 (Rust-only constructor in the reference; exposed for tests)."""
         return Tokenizer._make(bytes(vocab_data), pattern, special_tokens or {}, True, False, devices)
 
+    @staticmethod
+    def from_bytes_sentencepiece(vocab_data: bytes, pattern: str, special_tokens: Optional[Dict[str, int]] = None,
+                                 devices: Optional[Sequence[int]] = None) -> "Tokenizer":
+        """tokenizer.rs:589-640 (Rust-only constructor in the reference; what from_pretrained("mistral") uses)."""
+        return Tokenizer._make(bytes(vocab_data), pattern, special_tokens or {}, False, True, devices)
+
     def _clone(self) -> "Tokenizer":
         return Tokenizer._make(self._vocab_data, self._pattern, self._special_tokens, self._byte_level,
-                               False, self._devices)
+                               self._sentencepiece, self._devices)
 
     def pcre2(self, use_pcre2: bool = True) -> "Tokenizer":
         """bindings.rs:207-214.  There is one pre-tokenizer (the device rules); the switch
@@ -240,8 +265,9 @@ class Tokenizer:
         n_docs = int(d_offsets.numel()) - 1
         if d_bytes.dtype != torch.uint8 or d_offsets.dtype != torch.int64 or not d_bytes.is_cuda or not d_offsets.is_cuda:
             raise TypeError("d_bytes must be a CUDA uint8 tensor and d_offsets a CUDA int64 tensor")
-        if ids_out is None:
-            ids_out = torch.empty(max(n_bytes, 1), dtype=torch.int32, device=d_bytes.device)
+        if ids_out is None:                        # SentencePiece mode: a space becomes the three bytes of U+2581
+            ids_out = torch.empty(max(n_bytes * (3 if self._sentencepiece else 1), 1), dtype=torch.int32,
+                                  device=d_bytes.device)
         if out_offsets is None:
             out_offsets = torch.empty(n_docs + 1, dtype=torch.int64, device=d_bytes.device)
         n_tok = ctypes.c_uint64(0)
@@ -264,9 +290,9 @@ class Tokenizer:
 
     def last_kernel_times(self, dev_index: int = 0) -> Dict[str, float]:
         """{kernel name: ms} of the most recent encode_device call (after a stream sync)."""
-        names = (ctypes.c_char_p * 12)()
-        ms = (ctypes.c_float * 12)()
-        n = _lib.load().spl_last_kernel_times(self._handle, dev_index, names, ms, 12)
+        names = (ctypes.c_char_p * 16)()
+        ms = (ctypes.c_float * 16)()
+        n = _lib.load().spl_last_kernel_times(self._handle, dev_index, names, ms, 16)
         return {names[i].decode(): float(ms[i]) for i in range(max(n, 0))}
 
     def launches_per_call(self, with_special: bool = False) -> int:
@@ -305,6 +331,11 @@ class Tokenizer:
 
     # -- decode (host table lookup, tokenizer.rs:877-958) ----------------------------------
     def _ensure_decoder(self) -> Dict[int, bytes]:
+        if self._decoder is None and self._sentencepiece:
+            dec = _parse_tiktoken_decoder(self._vocab_data)          # vocab.rs:135
+            for k, v in self._special_tokens.items():                # tokenizer.rs:597-600
+                dec[v] = k.encode("utf-8")
+            self._decoder = dec
         if self._decoder is None:
             enc = _parse_tiktoken(self._vocab_data)
             dec: Dict[int, bytes] = {}
@@ -334,14 +365,18 @@ class Tokenizer:
                     out += s.encode("utf-8")
         return bytes(out)
 
+    def _postprocess(self, text: str) -> str:
+        """tokenizer.rs:923-930: SentencePiece mode turns U+2581 back into a space (string level, after UTF-8)."""
+        return text.replace("\u2581", " ") if self._sentencepiece else text
+
     def decode(self, tokens: Iterable[int]) -> str:
         try:
-            return self.decode_bytes(tokens).decode("utf-8")
+            return self._postprocess(self.decode_bytes(tokens).decode("utf-8"))
         except UnicodeDecodeError:
             raise ValueError("Decoding error: invalid UTF-8")
 
     def decode_lossy(self, tokens: Iterable[int]) -> str:
-        return self.decode_bytes(tokens).decode("utf-8", errors="replace")
+        return self._postprocess(self.decode_bytes(tokens).decode("utf-8", errors="replace"))
 
     def decode_packed(self, ids, offsets, return_stats: bool = False):
         """Batch decode on the device (spl_decode_batch; tokenizer.rs:877-897, 945-958): `ids` = concatenated
@@ -421,11 +456,11 @@ class Tokenizer:
             b = raw[int(off[i]):int(off[i + 1])]
             if errors == "strict":
                 try:
-                    out.append(b.decode("utf-8"))
+                    out.append(self._postprocess(b.decode("utf-8")))
                 except UnicodeDecodeError:
                     raise ValueError("Decoding error: invalid UTF-8")
             else:
-                out.append(b.decode("utf-8", errors="replace"))
+                out.append(self._postprocess(b.decode("utf-8", errors="replace")))
         return out
 
     def decode_batch(self, token_lists: List[List[int]]) -> List[str]:
@@ -455,6 +490,8 @@ class Tokenizer:
         return ByteLevelStreamingDecoder(self._raw_decoder(), dict(self._special_decoder))
 
     def _raw_decoder(self) -> Dict[int, bytes]:
+        if self._sentencepiece:
+            return _parse_tiktoken_decoder(self._vocab_data)
         return {v: k for k, v in _parse_tiktoken(self._vocab_data).items()}
 
     def clear_cache(self) -> None:

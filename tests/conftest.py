@@ -10,6 +10,8 @@ for p in (ROOT, os.path.join(ROOT, "tools"), os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 VOCABS = ["cl100k_base", "o200k_base", "llama3", "deepseek_v3", "mistral_v3"]
+SP_VOCABS = ["mistral_v1", "mistral_v2"]                # SentencePiece mode (tokenizer.rs:737-795)
+ALL_VOCABS = VOCABS + SP_VOCABS
 
 
 def pytest_configure(config):
@@ -40,7 +42,8 @@ def py_oracle(name):
     from splintr_b200 import presets as P
     if name not in _ORACLES:
         p = P.PRESETS[name]
-        _ORACLES[name] = OracleTokenizer.from_bytes(P.load_vocab_bytes(p.vocab_file), p.pattern, p.special_tokens, p.byte_level)
+        _ORACLES[name] = OracleTokenizer.from_bytes(P.load_vocab_bytes(p.vocab_file), p.pattern, p.special_tokens, p.byte_level,
+                                                     p.sentencepiece)
     return _ORACLES[name]
 
 
@@ -52,5 +55,5 @@ def c_oracle(name):
     from splintr_b200 import presets as P
     if name not in _CORACLES:
         p = P.PRESETS[name]
-        _CORACLES[name] = COracle(P.load_vocab_bytes(p.vocab_file), p.pattern, p.special_tokens, p.byte_level)
+        _CORACLES[name] = COracle(P.load_vocab_bytes(p.vocab_file), p.pattern, p.special_tokens, p.byte_level, p.sentencepiece)
     return _CORACLES[name]

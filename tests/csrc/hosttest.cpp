@@ -260,3 +260,71 @@ extern "C" int ht_scan_fast(int pattern, const uint8_t* text, uint32_t n, uint32
     }
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------
+// SentencePiece mode: the five kernels of spl_sentencepiece.cu replayed sequentially with the SAME
+// __host__ __device__ rules (spl_sentencepiece.h), word by word and tile by tile like the device does.
+#include "../../splintr_b200/csrc/spl_sentencepiece.h"
+
+// hardb[i] = 1 at segment starts (hardb[n] must be 1), specb (optional) = bytes of special spans.
+// out_text must hold 3 * n bytes, out_ps / out_spec 3 * n + 1 flags.  Returns the length of T'.
+extern "C" long ht_sp_transform(const uint8_t* text, uint32_t n, const uint8_t* hardb, const uint8_t* specb,
+                                uint8_t* out_text, uint8_t* out_ps, uint8_t* out_spec) {
+    HostText t{text};
+    std::vector<uint8_t> w0(n + 1, 0), a(n + 1, 0), rs(n + 1, 0);
+    // k_sp_classify (one "thread" per 32-byte word; prev_w0 of the word's first byte is recomputed, as on the device)
+    for (uint32_t base = 0; base < n; base += 32) {
+        bool prev_w0 = false;
+        if (base > 0 && !(specb && specb[base - 1])) prev_w0 = spl_sp_ws_byte(t, base - 1, n, spl_ucd_stage1, spl_ucd_stage2);
+        for (uint32_t i = base; i < n && i < base + 32; ++i) {
+            uint32_t b = text[i];
+            bool sp = specb && specb[i];
+            bool ws = !sp && spl_sp_ws_byte(t, i, n, spl_ucd_stage1, spl_ucd_stage2);
+            if (ws) {
+                w0[i] = 1; a[i] = 1;
+                bool char_start = (b & 0xC0u) != 0x80u;
+                if (char_start && (hardb[i] || i == 0 || !prev_w0) && !spl_sp_ascii_ws(b)) rs[i] = 1;
+            }
+            prev_w0 = ws;
+        }
+    }
+    // k_sp_rawruns
+    for (uint32_t st = 0; st < n; ++st)
+        if (rs[st])
+            for (uint32_t i = st; i < n && w0[i] && (i == st || !hardb[i]); ++i) a[i] = 0;
+    // k_sp_count / k_sp_scan / k_sp_emit
+    memset(out_ps, 0, 3 * (size_t)n + 1);
+    memset(out_spec, 0, 3 * (size_t)n + 1);
+    uint32_t o = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        SplSpPos p;
+        p.w0 = w0[i]; p.a = a[i]; p.rs = rs[i]; p.s = hardb[i]; p.b = text[i];
+        p.w0_prev = i ? w0[i - 1] : false; p.a_prev = i ? a[i - 1] : false; p.b_prev = i ? text[i - 1] : 0;
+        if (spl_sp_piece_start(p)) out_ps[o] = 1;
+        if (specb && specb[i]) out_spec[o] = 1;
+        if (spl_sp_conv(p)) { out_text[o] = 0xE2; out_text[o + 1] = 0x96; out_text[o + 2] = 0x81; o += 3; }
+        else out_text[o++] = text[i];
+    }
+    out_ps[o] = 1;
+    return (long)o;
+}
+
+// encode one segment in SentencePiece mode: transform, then every piece of T' through the device-equivalent piece
+// encoder.  ids needs room for 3 * n entries.
+extern "C" long ht_encode_sp(void* h, const uint8_t* text, uint32_t n, uint32_t* ids, size_t cap) {
+    SplHostTables* T = (SplHostTables*)h;
+    std::vector<uint8_t> hard(n + 1, 0), t2(3 * (size_t)n + 4), ps(3 * (size_t)n + 1), sp(3 * (size_t)n + 1);
+    hard[0] = 1; hard[n] = 1;
+    long n2 = ht_sp_transform(text, n, hard.data(), nullptr, t2.data(), ps.data(), sp.data());
+    std::vector<uint32_t> out;
+    long p = 0;
+    while (p < n2) {
+        long e = p + 1;
+        while (!ps[e]) ++e;
+        ht_bpe_piece(*T, t2.data() + p, (uint32_t)(e - p), out);
+        p = e;
+    }
+    if (out.size() > cap) return -2;
+    memcpy(ids, out.data(), out.size() * 4);
+    return (long)out.size();
+}

@@ -9,7 +9,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = [os.path.join(ROOT, "tests", "csrc", "hosttest.cpp"), os.path.join(ROOT, "splintr_b200", "csrc", "spl_host.cpp")]
-DEPS = SRC + [os.path.join(ROOT, "splintr_b200", "csrc", f) for f in ("spl_pretok.h", "spl_pretok_fast.h", "spl_common.h", "spl_host.h", "unicode_tables.inc")]
+DEPS = SRC + [os.path.join(ROOT, "splintr_b200", "csrc", f) for f in ("spl_pretok.h", "spl_pretok_fast.h", "spl_sentencepiece.h", "spl_common.h", "spl_host.h", "unicode_tables.inc")]
 LIB = os.path.join(ROOT, "tests", "csrc", "libhosttest.so")
 _lib = None
 
@@ -38,8 +38,28 @@ def load():
     lib.ht_stats.argtypes = [vp, vp]
     lib.ht_encode.restype = ctypes.c_long
     lib.ht_encode.argtypes = [vp, ctypes.c_char_p, ctypes.c_uint32, vp, ctypes.c_size_t]
+    lib.ht_sp_transform.restype = ctypes.c_long
+    lib.ht_sp_transform.argtypes = [ctypes.c_char_p, ctypes.c_uint32, vp, vp, vp, vp, vp]
+    lib.ht_encode_sp.restype = ctypes.c_long
+    lib.ht_encode_sp.argtypes = [vp, ctypes.c_char_p, ctypes.c_uint32, vp, ctypes.c_size_t]
     _lib = lib
     return lib
+
+
+def sp_transform(data: bytes, hard=None, spec=None):
+    """SentencePiece-mode transform (spl_sentencepiece.h rules): returns (T' bytes, piece starts in T', special-span
+    starts in T')."""
+    n = len(data)
+    h = np.zeros(n + 1, dtype=np.uint8) if hard is None else np.asarray(hard, dtype=np.uint8).copy()
+    h[0] = 1
+    h[n] = 1
+    sp = None if spec is None else np.asarray(spec, dtype=np.uint8)
+    t2 = np.zeros(3 * n + 4, dtype=np.uint8)
+    ps = np.zeros(3 * n + 1, dtype=np.uint8)
+    s2 = np.zeros(3 * n + 1, dtype=np.uint8)
+    n2 = load().ht_sp_transform(data, n, h.ctypes.data, None if sp is None else sp.ctypes.data,
+                                t2.ctypes.data, ps.ctypes.data, s2.ctypes.data)
+    return t2[:n2].tobytes(), np.flatnonzero(ps[:n2]).tolist(), np.flatnonzero(s2[:n2]).tolist()
 
 
 def scan_seq(pattern_id, data: bytes):
@@ -87,13 +107,13 @@ def scan_fast(pattern_id, data: bytes, payload, halo, hard, spec=None):
 
 
 class HostTables:
-    def __init__(self, vocab: bytes, pattern_id: int, byte_level: bool, specials=None):
+    def __init__(self, vocab: bytes, pattern_id: int, byte_level: bool, specials=None, sentencepiece: bool = False):
         sp = list((specials or {}).items())
         n = len(sp)
         strs = (ctypes.c_char_p * max(n, 1))(*[s.encode() for s, _ in sp])
         ids = (ctypes.c_uint32 * max(n, 1))(*[i for _, i in sp])
         err = ctypes.create_string_buffer(256)
-        self.h = load().ht_create(vocab, len(vocab), pattern_id, 1 if byte_level else 0, strs, ids, n, err, 256)
+        self.h = load().ht_create(vocab, len(vocab), pattern_id, (1 if byte_level else 0) | (2 if sentencepiece else 0), strs, ids, n, err, 256)
         if not self.h:
             raise ValueError(err.value.decode())
 
@@ -106,6 +126,12 @@ class HostTables:
     def encode(self, data: bytes):
         ids = np.zeros(len(data) + 1, dtype=np.uint32)
         n = load().ht_encode(self.h, data, len(data), ids.ctypes.data, len(ids))
+        assert n >= 0, n
+        return ids[:n].tolist()
+
+    def encode_sp(self, data: bytes):
+        ids = np.zeros(3 * len(data) + 1, dtype=np.uint32)
+        n = load().ht_encode_sp(self.h, data, len(data), ids.ctypes.data, len(ids))
         assert n >= 0, n
         return ids[:n].tolist()
 

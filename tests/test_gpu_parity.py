@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 import synth
-from conftest import VOCABS, py_oracle, c_oracle
+from conftest import VOCABS, SP_VOCABS, py_oracle, c_oracle
 from fuzz_alphabet import random_text
 
 pytestmark = pytest.mark.gpu
@@ -275,7 +275,7 @@ def test_cfg3_large_host_call_equals_parts(toks):
 
 
 # ---- decode on the device ---------------------------------------------------------
-@pytest.mark.parametrize("name", VOCABS)
+@pytest.mark.parametrize("name", VOCABS + SP_VOCABS)
 def test_decode_batch_matches_host_decode(toks, name):
     """spl_decode_batch against the host table lookup (mirror of tokenizer.rs:877-897) on ordinary ids, special
     ids, ids outside the vocabulary (skipped) and, for the byte-level vocabulary, the untranslatable keys."""
@@ -318,3 +318,95 @@ def test_decode_batch_strings_roundtrip(toks):
     t = toks("deepseek_v3")
     texts = ["Hello 你好 World 世界!", "", " hello world ", "日本語のテキスト" * 50, "émoji 🌍 ok"]
     assert t.decode_batch(t.encode_batch(texts)) == texts
+
+
+# ---- SentencePiece mode on the device (mistral_v1 / mistral_v2; tokenizer.rs:737-795) -----------
+def _sp_texts(seed, n, maxlen):
+    rng = random.Random(seed)
+    ws = [" ", " ", " ", "  ", "\n", "\t", "\x0b", "\x0c", "\r", "\xa0", "　", " ", "\x85", "\x1c"]
+    out = []
+    for _ in range(n):
+        if rng.random() < 0.5:
+            t = random_text(rng, maxlen)
+        else:
+            t = "".join(rng.choice(ws) if rng.random() < 0.45 else rng.choice("ab,Zé中🙂") for _ in range(rng.randint(0, maxlen)))
+        if "᠎" not in t:
+            out.append(t)
+    return out
+
+
+@pytest.mark.parametrize("name", SP_VOCABS)
+def test_sentencepiece_golden_and_edges(toks, name, ref_vectors):
+    t, o = toks(name), c_oracle(name)
+    for text, ids in ref_vectors[name]["encode"]:
+        assert t.encode(text) == ids, (name, text)
+    for text, ids in ref_vectors[name]["special"]:
+        assert t.encode_with_special(text) == ids, (name, text)
+    assert t.vocab_size == {"mistral_v1": 32054, "mistral_v2": 32822}[name]        # tests/mistral_v2.rs:116
+    assert t.encode_batch([]) == [] and t.encode_batch(["", ""]) == [[], []]
+    cases = ["", " ", "  ", "a", "a ", " a", "a b", "a  b", "\n", " \n ", "\n\n  x", "a\tb", "a \t b", "　 a", "a 　 b",
+             "x\x0b y", "\x0b", " \x0b ", "a \x85 b", "\xa0 x", "       x", "x       ", "a\r\n b", "Hello world", " world!",
+             "Hello 🌍 World!", "def f():\n    return 1\n\n\nx = 2  # c\n", " " * 100, "\n" * 50, " " * 9000 + "y",
+             "x\x0b" + " " * 9000 + "y", "a" * 4095 + " b", "a" * 4096 + " b", ("word " * 820), "é " * 2049, "好 " * 3000,
+             "a" * 300, "ab " * 4000, ""]
+    assert t.encode_batch(cases) == o.encode_batch(cases)
+    # ids can outnumber the input bytes here: each of the 7 spaces is three byte tokens (E2 96 81)
+    assert len(t.encode("       x")) == 22
+    rag = [" " * k + "x" * (40 - k) for k in range(0, 41)] + ["x " * k for k in (2047, 2048, 2049)]
+    assert t.encode_batch(rag) == o.encode_batch(rag)
+
+
+@pytest.mark.parametrize("name", SP_VOCABS)
+def test_sentencepiece_fuzz_and_special(toks, name):
+    t, o, po = toks(name), c_oracle(name), py_oracle(name)
+    texts = _sp_texts(31, 6000, 90)
+    got = t.encode_batch(texts)
+    assert got == o.encode_batch(texts)
+    for x, g in list(zip(texts, got))[:600]:
+        assert g == po.encode(x), (name, x)
+    rng = random.Random(5)
+    sp = list(po.special_tokens)
+    st = [s for s in sp[:10]] + [sp[0] + sp[1], " " + sp[0] + " ", "a  " + sp[2] + "  b", sp[0][:-1]]
+    st += [x + rng.choice(sp) + y + rng.choice(sp) + " " for x, y in zip(_sp_texts(7, 400, 30), _sp_texts(8, 400, 30))]
+    gs = t.encode_batch_with_special(st)
+    for x, g in zip(st, gs):
+        assert g == po.encode_with_special(x), (name, x)
+
+
+@pytest.mark.parametrize("name", SP_VOCABS)
+def test_sentencepiece_roundtrip_and_batch(toks, name):
+    """python/tests/test_mistral_v1.py:68-109,176-190: decode(encode(x)) == x (U+2581 -> space, tokenizer.rs:923-930),
+    batch == individual; plus a 20 MB English batch against the C oracle, through the host call (many pipeline chunks,
+    one mid-pipeline size read-back each) and through the device entry point."""
+    import torch
+    t, o = toks(name), c_oracle(name)
+    texts = ["Hello, world!", "The quick brown fox jumps over the lazy dog.", "1234567890", " world!",
+             "Unicode: こんにちは 世界 🦀", "Mixed: Hello 你好 🌍 World!", "Multi-line\ntext\nwith\nnewlines",
+             'def hello_world():\n    print("Hello, World!")\n\nif __name__ == "__main__":\n    hello_world()\n']
+    batch = t.encode_batch(texts)
+    assert batch == [t.encode(x) for x in texts]
+    assert t.decode_batch(batch) == texts and [t.decode(b) for b in batch] == texts
+    d, off = synth.cfg2(vocab_bytes("cl100k_base"), 20_000)
+    ids, out_off = _check_packed(t, o, d, off)
+    n = len(d)
+    buf = torch.zeros(n + ((-n) % 16), dtype=torch.uint8, device="cuda")
+    buf[:n].copy_(torch.from_numpy(d))
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    dids, dout, n_tok = t.encode_device(buf[:n], d_off)
+    assert n_tok == len(ids)
+    assert np.array_equal(dids[:n_tok].cpu().numpy().astype(np.uint32), ids)
+    assert np.array_equal(dout.cpu().numpy().astype(np.uint64), out_off)
+    with pytest.raises(ValueError):                     # the id buffer must cover the transformed text
+        t.encode_device(buf[:n], d_off, ids_out=torch.empty(n // 2, dtype=torch.int32, device="cuda"))
+
+
+def test_sentencepiece_pipelined_small_chunks(toks, monkeypatch):
+    from splintr_b200 import Tokenizer
+    monkeypatch.setenv("SPL_CHUNK_BYTES", "20000")
+    t = Tokenizer.from_pretrained("mistral_v2", devices=[0])
+    monkeypatch.delenv("SPL_CHUNK_BYTES")
+    o = c_oracle("mistral_v2")
+    texts = _sp_texts(41, 3000, 200)
+    texts[3] = ""; texts[17] = " " * 50_000; texts[18] = ""; texts[-1] = ""
+    assert t.encode_batch(texts) == o.encode_batch(texts)
+    assert t.pcre2().encode("a  b") == o.encode("a  b")           # clones keep the mode

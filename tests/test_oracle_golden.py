@@ -5,11 +5,11 @@ import random
 
 import pytest
 
-from conftest import VOCABS, py_oracle, c_oracle
+from conftest import VOCABS, ALL_VOCABS, py_oracle, c_oracle
 from fuzz_alphabet import random_text
 
 
-@pytest.mark.parametrize("name", VOCABS)
+@pytest.mark.parametrize("name", ALL_VOCABS)
 def test_py_oracle_reference_vectors(name, ref_vectors):
     o = py_oracle(name)
     for text, ids in ref_vectors[name]["encode"]:
@@ -18,7 +18,7 @@ def test_py_oracle_reference_vectors(name, ref_vectors):
         assert o.encode_with_special(text) == ids, (name, text)
 
 
-@pytest.mark.parametrize("name", VOCABS)
+@pytest.mark.parametrize("name", ALL_VOCABS)
 def test_c_oracle_reference_vectors(name, ref_vectors):
     o = c_oracle(name)
     for text, ids in ref_vectors[name]["encode"]:
@@ -37,7 +37,7 @@ def test_oracles_match_tiktoken_fixture(name, xcheck_vectors):
         assert po.encode(t) == ids, (name, t)
 
 
-@pytest.mark.parametrize("name", VOCABS)
+@pytest.mark.parametrize("name", ALL_VOCABS)
 def test_c_oracle_equals_py_oracle_fuzz(name):
     rng = random.Random(hash(name) & 0xFFFF)
     texts = [t for t in (random_text(rng, 60) for _ in range(1500)) if "᠎" not in t]
@@ -70,3 +70,20 @@ def test_byte_level_map():
     assert byte_level_encode(b" ").decode() == "Ġ"
     assert byte_level_encode("你好".encode()).decode() == "ä½łå¥½"
     assert byte_level_decode_bytes(byte_level_encode(bytes(range(256)))) == bytes(range(256))
+
+
+@pytest.mark.parametrize("name", ["mistral_v1", "mistral_v2"])
+def test_sentencepiece_mode_properties(name):
+    """SentencePiece branch (tokenizer.rs:737-795): round trips of the reference's own corpora
+    (python/tests/test_mistral_v1.py:68-109), vocab sizes (tests/mistral_v2.rs:116), the first-byte rule."""
+    o = py_oracle(name)
+    for text in ["Hello, world!", "The quick brown fox jumps over the lazy dog.", "1234567890", " world!",
+                 "Special characters: !@#$%^&*()", "Unicode: こんにちは 世界 🦀", "Mixed: Hello 你好 🌍 World!",
+                 "Multi-line\ntext\nwith\nnewlines",
+                 'def hello_world():\n    print("Hello, World!")\n\nif __name__ == "__main__":\n    hello_world()\n']:
+        assert o.decode(o.encode(text)) == text
+    assert o.vocab_size == {"mistral_v1": 32054, "mistral_v2": 32822}[name]
+    us = o.encoder["\u2581".encode()]
+    assert o.encode(" ") == [us] and o.encode("a ") == o.encode("a") + [us]
+    # a whitespace chunk that starts with a non-ASCII space is encoded as a word: its spaces stay 0x20
+    assert o.encode("\u3000 a")[-2:] == [o.encoder[b" "], o.encoder[b"a"]]
