@@ -50,13 +50,16 @@ struct DevCtx {
     int num_sms = 0;
     cudaStream_t stream = nullptr;          // kernels (+ the small per-chunk results)
     cudaStream_t s_in = nullptr, s_out = nullptr;   // host->device staging, ids device->host
-    std::vector<cudaEvent_t> pipe_ev;       // per-chunk events of spl_encode_batch, grown on demand
+    std::vector<cudaEvent_t> pipe_ev;       // per-chunk timing events of spl_encode_batch, grown on demand
+    std::vector<cudaEvent_t> sync_ev;       // per-chunk ordering events (cudaEventDisableTiming: a timing event on a copy
+                                            // stream makes the copy engine drain before the next transfer starts)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     void* table_blob = nullptr;
     SplTables* d_tables = nullptr;
     DevBuf text, doc_off, ids, out_off;          // spl_encode_batch: the shard's buffers
     DevBuf zero, tstate, pv, pool, mlist, fbl, huge;
     DevBuf dec_ids, dec_off, dec_ws, dec_out, dec_out_off;       // spl_decode_batch   // per-pass workspace (zero: everything that starts cleared)
+    DevBuf run_tot;                                              // spl_encode_batch: cumulative id count after each pipeline chunk
     DevBuf sp_zero, sp_tiles, sp_text, sp_doc;                   // SentencePiece mode: bitmaps over T, tile counts, T', offsets in T'
     size_t huge_words = 0;
     SplKernelProfile prof;
@@ -70,6 +73,7 @@ struct PinnedBuf { void* p; size_t cap; };
 struct spl_tokenizer {
     bool profiling = false;
     bool trace = false;                     // SPL_TRACE=1: per-chunk timeline of spl_encode_batch on stderr
+    int trace_chunk = -1;                   // SPL_TRACE_CHUNK=k: with SPL_TRACE, per-kernel times of the k-th chunk
     uint64_t chunk_bytes = 0;               // pipeline chunk size of spl_encode_batch (0 = automatic)
     SplHostTables host;
     std::vector<DevCtx> devs;
@@ -149,12 +153,13 @@ int upload_tables(spl_tokenizer* tk, DevCtx& dc) {
 
 void destroy_ctx(DevCtx& dc) {
     cudaSetDevice(dc.device);
-    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.ids, &dc.out_off, &dc.dec_ids, &dc.dec_off, &dc.dec_ws, &dc.dec_out, &dc.dec_out_off, &dc.sp_zero, &dc.sp_tiles, &dc.sp_text, &dc.sp_doc, &dc.zero, &dc.tstate, &dc.pv, &dc.pool, &dc.mlist, &dc.fbl, &dc.huge})
+    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.ids, &dc.out_off, &dc.dec_ids, &dc.dec_off, &dc.dec_ws, &dc.dec_out, &dc.dec_out_off, &dc.run_tot, &dc.sp_zero, &dc.sp_tiles, &dc.sp_text, &dc.sp_doc, &dc.zero, &dc.tstate, &dc.pv, &dc.pool, &dc.mlist, &dc.fbl, &dc.huge})
         b->release();
     if (dc.table_blob) cudaFree(dc.table_blob);
     for (auto& e : dc.ev) if (e) cudaEventDestroy(e);
     if (dc.prof_ready) for (auto& e : dc.prof.ev) cudaEventDestroy(e);
     for (auto& e : dc.pipe_ev) cudaEventDestroy(e);
+    for (auto& e : dc.sync_ev) cudaEventDestroy(e);
     if (dc.stream) cudaStreamDestroy(dc.stream);
     if (dc.s_in) cudaStreamDestroy(dc.s_in);
     if (dc.s_out) cudaStreamDestroy(dc.s_out);
@@ -263,6 +268,7 @@ struct EncodeArgs {
     const uint8_t* text; uint64_t N;
     const uint64_t* doc_off; uint64_t off_base; uint64_t n_docs;
     uint32_t* ids; uint64_t ids_cap; uint64_t* out_off; uint64_t* host_meta;
+    const uint64_t* tok_base_in; uint64_t* tok_total_out;
 };
 
 // Enqueue the encode path for one device pass on `st`; `w` is the workspace view the pass uses (its counters are what
@@ -277,6 +283,7 @@ int enqueue_encode(spl_tokenizer* tk, DevCtx& dc, cudaStream_t st, const EncodeA
         if ((rc = prepare_work(tk, dc, a.N, a.n_docs, with_special, st, w))) return rc;
         w.text = a.text; w.doc_off = a.doc_off; w.off_base = a.off_base;
         w.ids = a.ids; w.out_off = a.out_off; w.host_meta = a.host_meta;
+        w.tok_base_in = a.tok_base_in; w.tok_total_out = a.tok_total_out;
         launches += spl_launch_encode(w, dc.num_sms, st, prof);
         return SPL_OK;
     }
@@ -327,6 +334,7 @@ int enqueue_encode(spl_tokenizer* tk, DevCtx& dc, cudaStream_t st, const EncodeA
     if ((rc = prepare_work(tk, dc, N2, a.n_docs, with_special, st, w))) return rc;
     w.text = (const uint8_t*)dc.sp_text.p; w.doc_off = (const uint64_t*)dc.sp_doc.p; w.off_base = 0;
     w.ids = a.ids; w.out_off = a.out_off; w.host_meta = a.host_meta;
+    w.tok_base_in = a.tok_base_in; w.tok_total_out = a.tok_total_out;
     w.pretok_done = true;
     s.text2 = (uint8_t*)dc.sp_text.p; s.pstart2 = w.pstart; s.spec2 = w.spec; s.doc_off2 = (uint64_t*)dc.sp_doc.p;
     launches += spl_launch_sp_emit(s, st);
@@ -392,6 +400,7 @@ int spl_create(const uint8_t* vocab, size_t vocab_len, int pattern_id, uint32_t 
     spl_tokenizer* tk = new (std::nothrow) spl_tokenizer();
     if (!tk) return SPL_ERR_OOM;
     if (const char* tr = getenv("SPL_TRACE")) tk->trace = tr[0] == '1';
+    if (const char* tc = getenv("SPL_TRACE_CHUNK")) tk->trace_chunk = atoi(tc);
     if (const char* cb = getenv("SPL_CHUNK_BYTES")) tk->chunk_bytes = strtoull(cb, nullptr, 10);
     uint32_t hflags = ((flags & SPL_CREATE_BYTE_LEVEL) ? SPL_FLAG_BYTE_LEVEL : 0) |
                       ((flags & SPL_CREATE_SENTENCEPIECE) ? SPL_FLAG_SENTENCEPIECE : 0);
@@ -508,7 +517,7 @@ int spl_encode_batch_device(spl_tokenizer* tk, int dev_index, const uint8_t* d_b
             prof = &dc.prof;
         }
         int launches = 0;
-        EncodeArgs ea{d_bytes, n_bytes, d_offsets, 0, n_docs, d_ids, ids_capacity, d_out_offsets, nullptr};
+        EncodeArgs ea{d_bytes, n_bytes, d_offsets, 0, n_docs, d_ids, ids_capacity, d_out_offsets, nullptr, nullptr, nullptr};
         if ((rc = enqueue_encode(tk, dc, st, ea, with_special, prof, w, launches))) return rc;
         CUDA_TRY(cudaGetLastError(), tk->err);
         if (!n_tokens_out) return SPL_OK;
@@ -535,7 +544,9 @@ struct Chunk {
     uint64_t b0, b1;            // bytes [b0, b1) of the caller's buffer
     size_t text_off;            // 16-byte aligned offset of the chunk inside the device text buffer
     size_t ids_off;             // u32 index of the chunk's id region inside the device id buffer
-    size_t ev;                  // first of its 4 events in DevCtx::pipe_ev (copied in, kernels start, done, ids copied out)
+    size_t ev;                  // first of its 4 timing events in DevCtx::pipe_ev (copied in*, kernels start, kernels end,
+                                // ids copied out*; * = trace only); its 2 ordering events are sync_ev[ev / 2 ..] (in, done)
+    size_t slot;                // index of the chunk within its device's shard (running-total slot)
     volatile uint64_t* meta;    // pinned, mapped: [0] id count, [1] error flags | huge-pool need << 32
     uint64_t* d_meta;           // the same memory as the device sees it
     uint64_t n_tokens;
@@ -646,13 +657,19 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
             if ((rc2 = dc.ids.ensure((ids_bound(tk, nb) + 16) * 4, tk->err))) return rc2;
             if ((rc2 = dc.out_off.ensure((nd + 1) * 8, tk->err))) return rc2;
             if ((rc2 = reserve_work(tk, dc, ids_bound(tk, max_nb[g]), max_nd[g], with_special))) return rc2;
-            size_t n_ev = 0;
-            for (auto& c : chunks) if (c.g == (int)g) { c.ev = n_ev; n_ev += 4; }
+            size_t n_ev = 0, n_slot = 0;
+            for (auto& c : chunks) if (c.g == (int)g) { c.ev = n_ev; n_ev += 4; c.slot = n_slot++; }
             while (dc.pipe_ev.size() < n_ev + 1) {
                 cudaEvent_t e;
                 CUDA_TRY(cudaEventCreate(&e), tk->err);
                 dc.pipe_ev.push_back(e);
             }
+            while (dc.sync_ev.size() < n_ev / 2 + 1) {
+                cudaEvent_t e;
+                CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), tk->err);
+                dc.sync_ev.push_back(e);
+            }
+            if ((rc2 = dc.run_tot.ensure((n_slot + 2) * 8, tk->err))) return rc2;
             return SPL_OK;
         };
         if ((rc = reserve())) return fail(rc);
@@ -698,20 +715,21 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
                 r->ids_buf = nb;
             }
             CUDA_TRY(cudaSetDevice(dc.device), tk->err);
-            {
-                // per-document offsets of the chunk (chunk-relative; rebased below once they have landed)
-                const size_t g = (size_t)c.g, nd = c.d1 - c.d0;
-                const size_t n_off = nd + ((c.d1 == dlo[g + 1] && g + 1 == G) ? 1 : 0);
-                if (n_off)
-                    CUDA_TRY(cudaMemcpyAsync(res_off + c.d0, (uint64_t*)dc.out_off.p + (c.d0 - dlo[g]), n_off * 8,
-                                             cudaMemcpyDeviceToHost, dc.s_out), tk->err);
-                r->stats.d2h_bytes += n_off * 8;
-            }
             if (c.n_tokens)
                 CUDA_TRY(cudaMemcpyAsync((uint32_t*)r->ids_buf.p + c.tok_base, (uint32_t*)dc.ids.p + c.ids_off, c.n_tokens * 4,
                                          cudaMemcpyDeviceToHost, dc.s_out), tk->err);
             r->stats.d2h_bytes += c.n_tokens * 4;
             if (tk->trace) cudaEventRecord(dc.pipe_ev[c.ev + 3], dc.s_out);
+            const size_t g = (size_t)c.g;
+            if (c.d1 == dlo[g + 1]) {
+                // last chunk of the shard: the per-document offsets of the whole shard in one copy.  They are
+                // shard-relative (every chunk's k_emit adds the ids of the chunks before it, kept on the device); one
+                // small copy per chunk would cost the copy engine more than it moves.
+                const size_t n_off = dlo[g + 1] - dlo[g] + (g + 1 == G ? 1 : 0);
+                if (n_off)
+                    CUDA_TRY(cudaMemcpyAsync(res_off + dlo[g], dc.out_off.p, n_off * 8, cudaMemcpyDeviceToHost, dc.s_out), tk->err);
+                r->stats.d2h_bytes += n_off * 8;
+            }
             return SPL_OK;
         };
 
@@ -723,25 +741,44 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
                 const size_t nd = c.d1 - c.d0, g = (size_t)c.g;
                 const uint64_t nb = c.b1 - c.b0;
                 const bool first = c.d0 == dlo[g], last = c.d1 == dlo[g + 1];
-                cudaEvent_t ev_in = dc.pipe_ev[c.ev], ev_k0 = dc.pipe_ev[c.ev + 1], ev_done = dc.pipe_ev[c.ev + 2];
-                if (first) CUDA_TRY(cudaEventRecord(dc.ev[0], dc.s_in), tk->err);
-                // stage in: text to its aligned slot, document offsets (the boundary entry belongs to the earlier chunk)
+                cudaEvent_t ev_in = dc.sync_ev[c.ev / 2], ev_done = dc.sync_ev[c.ev / 2 + 1];
+                cudaEvent_t ev_k0 = dc.pipe_ev[c.ev + 1], ev_k1 = dc.pipe_ev[c.ev + 2];
+                uint64_t* run_tot = (uint64_t*)dc.run_tot.p;
+                if (first) {
+                    CUDA_TRY(cudaEventRecord(dc.ev[0], dc.s_in), tk->err);
+                    // the document offsets of the whole shard go in with one copy, ahead of the text
+                    const size_t nds = dlo[g + 1] - dlo[g];
+                    CUDA_TRY(cudaMemcpyAsync(dc.doc_off.p, offsets + dlo[g], (nds + 1) * 8, cudaMemcpyHostToDevice, dc.s_in), tk->err);
+                    CUDA_TRY(cudaMemsetAsync(run_tot, 0, 8, dc.s_in), tk->err);
+                    r->stats.h2d_bytes += (nds + 1) * 8;
+                }
+                // stage in: text to its aligned slot
                 uint8_t* d_text = (uint8_t*)dc.text.p + c.text_off;
                 uint64_t* d_doc = (uint64_t*)dc.doc_off.p + (c.d0 - dlo[g]);
                 if (nb) CUDA_TRY(cudaMemcpyAsync(d_text, bytes + c.b0, nb, cudaMemcpyHostToDevice, dc.s_in), tk->err);
-                const size_t skip = first ? 0 : 1;
-                CUDA_TRY(cudaMemcpyAsync(d_doc + skip, offsets + c.d0 + skip, (nd + 1 - skip) * 8, cudaMemcpyHostToDevice, dc.s_in), tk->err);
+                if (tk->trace) CUDA_TRY(cudaEventRecord(dc.pipe_ev[c.ev], dc.s_in), tk->err);
                 CUDA_TRY(cudaEventRecord(ev_in, dc.s_in), tk->err);
-                r->stats.h2d_bytes += nb + (nd + 1 - skip) * 8;
+                r->stats.h2d_bytes += nb;
                 // kernels
                 CUDA_TRY(cudaStreamWaitEvent(dc.stream, ev_in, 0), tk->err);
                 CUDA_TRY(cudaEventRecord(ev_k0, dc.stream), tk->err);
                 SplWork w;
                 int rc2;
                 uint64_t* d_out = (uint64_t*)dc.out_off.p + (c.d0 - dlo[g]);
-                EncodeArgs ea{d_text, nb, d_doc, c.b0, nd, (uint32_t*)dc.ids.p + c.ids_off, ids_bound(tk, nb), d_out, c.d_meta};
-                if ((rc2 = enqueue_encode(tk, dc, dc.stream, ea, with_special, nullptr, w, launches))) return rc2;
+                EncodeArgs ea{d_text, nb, d_doc, c.b0, nd, (uint32_t*)dc.ids.p + c.ids_off, ids_bound(tk, nb), d_out, c.d_meta,
+                              run_tot + c.slot, run_tot + c.slot + 1};
+                SplKernelProfile* prof = nullptr;
+                if (tk->trace && (int)c.slot == tk->trace_chunk) {        // SPL_TRACE_CHUNK=k: per-kernel times of chunk k
+                    if (!dc.prof_ready) {
+                        for (auto& e : dc.prof.ev) CUDA_TRY(cudaEventCreate(&e), tk->err);
+                        dc.prof.n = 0;
+                        dc.prof_ready = true;
+                    }
+                    prof = &dc.prof;
+                }
+                if ((rc2 = enqueue_encode(tk, dc, dc.stream, ea, with_special, prof, w, launches))) return rc2;
                 CUDA_TRY(cudaGetLastError(), tk->err);
+                CUDA_TRY(cudaEventRecord(ev_k1, dc.stream), tk->err);
                 // the chunk's id count and error flags arrive in mapped host memory (written by k_emit): no copy on the
                 // kernel stream, which would queue behind the previous chunk's ids on the device-to-host engine
                 CUDA_TRY(cudaEventRecord(ev_done, dc.stream), tk->err);
@@ -753,7 +790,7 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
             while (err_code == SPL_OK && next_out <= ci) {
                 Chunk& o = chunks[next_out];
                 cudaSetDevice(tk->devs[o.g].device);
-                cudaError_t q = cudaEventQuery(tk->devs[o.g].pipe_ev[o.ev + 2]);
+                cudaError_t q = cudaEventQuery(tk->devs[o.g].sync_ev[o.ev / 2 + 1]);
                 if (q == cudaErrorNotReady) break;
                 if (q != cudaSuccess) { tk->err = std::string("encode kernels: ") + cudaGetErrorString(q); err_code = SPL_ERR_CUDA; break; }
                 err_code = drain(next_out++);
@@ -763,7 +800,7 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
         while (err_code == SPL_OK && next_out < C) {
             Chunk& o = chunks[next_out];
             cudaSetDevice(tk->devs[o.g].device);
-            cudaError_t e = cudaEventSynchronize(tk->devs[o.g].pipe_ev[o.ev + 2]);
+            cudaError_t e = cudaEventSynchronize(tk->devs[o.g].sync_ev[o.ev / 2 + 1]);
             if (e != cudaSuccess) { tk->err = std::string("encode kernels: ") + cudaGetErrorString(e); err_code = SPL_ERR_CUDA; break; }
             err_code = drain(next_out++);
         }
@@ -792,6 +829,17 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
                         cudaEventElapsedTime(&e, dc.ev[0], dc.pipe_ev[c.ev + 3]);
                         fprintf(stderr, "[spl trace] dev %zu docs %zu..%zu bytes %llu: in %.3f  k0 %.3f  done %.3f  out %.3f ms\n",
                                 g, c.d0, c.d1, (unsigned long long)(c.b1 - c.b0), a, b, d, e);
+                        if ((int)c.slot == tk->trace_chunk && dc.prof_ready) {
+                            fprintf(stderr, "[spl trace]   kernels of this chunk (us):");
+                            for (int i = 0; i < dc.prof.n; ++i) {
+                                float t2 = 0;
+                                cudaEventElapsedTime(&t2, dc.prof.ev[i], dc.prof.ev[i + 1]);
+                                fprintf(stderr, " %s %.0f", dc.prof.name[i], t2 * 1000.f);
+                            }
+                            float t0 = 0;
+                            cudaEventElapsedTime(&t0, dc.pipe_ev[c.ev + 1], dc.prof.ev[0]);
+                            fprintf(stderr, " | k0 -> first kernel %.0f\n", t0 * 1000.f);
+                        }
                     }
         }
         h_synced = h_ms();
@@ -807,10 +855,12 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
             r->ids_buf = take_pinned(tk, 64);
             if (!r->ids_buf.p) { tk->err = "pinned host allocation failed"; return fail(SPL_ERR_OOM); }
         }
-        // the per-document offsets came back chunk-relative: rebase (all copies have completed)
-        for (auto& c : chunks)
-            if (c.tok_base)
-                for (size_t d = c.d0; d < c.d1; ++d) res_off[d] += c.tok_base;
+        // the per-document offsets came back shard-relative: shards after the first are rebased (all copies have completed)
+        for (size_t g = 1; g < G; ++g) {
+            uint64_t sbase = 0;
+            for (auto& c : chunks) if (c.g == (int)g && c.d0 == dlo[g]) sbase = c.tok_base;
+            if (sbase) for (size_t d = dlo[g]; d < dlo[g + 1]; ++d) res_off[d] += sbase;
+        }
         res_off[n_docs] = total;
         r->n_tokens = total;
         r->stats.n_docs = n_docs; r->stats.n_bytes = N; r->stats.n_tokens = total;

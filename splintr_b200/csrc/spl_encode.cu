@@ -790,10 +790,16 @@ __global__ void __launch_bounds__(SPL_THREADS, 8) k_emit(SplWork w) {
         const uint32_t x = (uint32_t)(w.doc_off[d] - w.off_base - tile0);
         const uint32_t pi = sm.wpre[x >> 5] + __popc(sm.pbw[x >> 5] & ((1u << (x & 31)) - 1u));
         const uint32_t rel = pi >= P ? tile_total : sm.spos[pi] + sm.wexc[(pi / (SPL_THREADS * 4u)) * EM_WARPS + ((pi / 128u) & (EM_WARPS - 1u))];
-        w.out_off[d] = prefix + rel;
-        if (d == w.n_docs && w.host_meta) {                    // the call's summary, straight to the host (no copy on this stream)
-            w.host_meta[0] = prefix + rel;
-            w.host_meta[1] = (uint64_t)w.counters[SPL_CTR_ERR] | ((uint64_t)w.counters[SPL_CTR_HUGE_POOL] << 32);
+        // pipelined host call: the ids of the shard's earlier chunks (kept on the device, so that the host gets
+        // shard-relative offsets in one copy at the end instead of one small copy and a rebase per chunk)
+        const uint64_t base = w.tok_base_in ? *w.tok_base_in : 0ull;
+        w.out_off[d] = base + prefix + rel;
+        if (d == w.n_docs) {
+            if (w.tok_total_out) *w.tok_total_out = base + prefix + rel;
+            if (w.host_meta) {                                 // the call's summary, straight to the host (no copy on this stream)
+                w.host_meta[0] = prefix + rel;
+                w.host_meta[1] = (uint64_t)w.counters[SPL_CTR_ERR] | ((uint64_t)w.counters[SPL_CTR_HUGE_POOL] << 32);
+            }
         }
     }
 }

@@ -76,6 +76,8 @@ struct SplWork {
     uint32_t*       ids;              // [>= N]
     uint64_t*       out_off;          // [n_docs+1]
     uint64_t*       host_meta;        // optional, mapped pinned host memory: [0] id count, [1] error flags | huge-pool need << 32
+    const uint64_t* tok_base_in;      // optional: ids of the shard's earlier chunks, added to out_off (not to the id positions)
+    uint64_t*       tok_total_out;    // optional: receives *tok_base_in + this pass's id count
     const SplTables* T;               // device copy of the tables
     int             pattern;
     bool            with_special;
