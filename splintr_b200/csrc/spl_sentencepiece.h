@@ -8,7 +8,7 @@
 //   * a whitespace chunk whose FIRST BYTE is ASCII whitespace (u8::is_ascii_whitespace: 09 0A 0C 0D 20, not 0B) is
 //     walked BYTE by byte: a space adds one pending U+2581; any other byte first flushes the pending run as one piece
 //     and is then encoded as a one-byte piece (so the bytes of U+3000 inside such a chunk are three pieces);
-//   * every other chunk (a word, or a whitespace chunk led by 0B / 1C-1F-free non-ASCII space such as U+00A0) is one
+//   * every other chunk (a word, or a whitespace chunk led by 0B or a non-ASCII space such as U+00A0) is one
 //     piece, prefixed with the pending U+2581 run; its own bytes stay as they are (its spaces stay 0x20);
 //   * the pending run left at the end of the text is one piece.
 // So the ids are those of the non-SentencePiece path over a TRANSFORMED text T' in which every "converted" space is
