@@ -13,6 +13,8 @@ value      device-resident: packed bytes + offsets already in HBM, ids + offsets
            every step timed with CUDA events on the launching stream, L2 flushed between steps.
 e2e        the same batch through the C-ABI host call spl_encode_batch from pinned host
            buffers: H2D copy, kernels, D2H of ids + offsets inside the timed region.
+python_api the Python methods on a 10 000-document sample: Tokenizer.encode_batch (list[str] ->
+           list[list[int]], the reference's signature) and encode_batch_packed (numpy arrays out).
 roofline   dominant kernel: algorithmic bytes per launch / its CUDA-event duration, against the
            measured HBM copy bandwidth (MEASURED_PEAKS.json, else the profiling guide's fallback).
 cpu_baseline  oracle/c_oracle.c (C restatement of the reference algorithm, PCRE2-JIT regex,
@@ -294,6 +296,20 @@ def main():
     e2e_value = float(tot_bytes.item()) * args.steps / float(e2e_s.item()) / 1e9
     assert e2e_stats["tokens"] == n_tok, "host and device entry points disagree on the id count"
 
+    # ---- the Python surface (SURVEY 8d "T3"): list[str] in, list[list[int]] / packed arrays out; rank 0, N=1 ----
+    py_api = None
+    if rank == 0 and world == 1:
+        import synth
+        nd_s = min(n_docs, 10_000)
+        texts = synth.unpack_texts(data[:int(offsets[nd_s])], offsets[:nd_s + 1])
+        nb_s = int(offsets[nd_s])
+        best = {"list": 1e9, "packed": 1e9}
+        for _ in range(3):
+            t1 = time.perf_counter(); tok.encode_batch(texts); best["list"] = min(best["list"], time.perf_counter() - t1)
+            t1 = time.perf_counter(); tok.encode_batch_packed(texts); best["packed"] = min(best["packed"], time.perf_counter() - t1)
+        py_api = {"encode_batch_list_of_lists": nb_s / best["list"] / 1e9, "encode_batch_packed": nb_s / best["packed"] / 1e9,
+                  "unit": UNIT, "sample": f"first {nd_s} docs ({nb_s / 1e6:.1f} MB), best of 3, str packing and result objects included"}
+
     # ---- CPU baseline + parity spot check (rank 0, N=1) ------------------------------------
     cpu = None
     parity = None
@@ -333,6 +349,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_stats["h2d"], "d2h_bytes_per_step": e2e_stats["d2h"],
                         "timing": "host wall clock around spl_encode_batch, barrier + synchronize both sides, max over ranks",
                         "device_ms_per_step": e2e_stats["dev_ms"]},
+                "python_api": py_api,
                 "gpu_launches": args.steps * tok.launches_per_call(False), "clocks": clocks,
                 "ids_match_cpu_baseline": parity}
         print(json.dumps(line), flush=True)

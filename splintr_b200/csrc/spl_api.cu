@@ -57,7 +57,7 @@ struct DevCtx {
     void* table_blob = nullptr;
     SplTables* d_tables = nullptr;
     DevBuf text, doc_off, ids, out_off;          // spl_encode_batch: the shard's buffers
-    DevBuf zero, tstate, pv, pool, mlist, fbl, huge;
+    DevBuf zero, tstate, pv, pool, mlist, fbl, huge, defer;
     DevBuf dec_ids, dec_off, dec_ws, dec_out, dec_out_off;       // spl_decode_batch   // per-pass workspace (zero: everything that starts cleared)
     DevBuf run_tot;                                              // spl_encode_batch: cumulative id count after each pipeline chunk
     DevBuf sp_zero, sp_tiles, sp_text, sp_doc;                   // SentencePiece mode: bitmaps over T, tile counts, T', offsets in T'
@@ -73,6 +73,7 @@ struct PinnedBuf { void* p; size_t cap; };
 struct spl_tokenizer {
     bool profiling = false;
     bool trace = false;                     // SPL_TRACE=1: per-chunk timeline of spl_encode_batch on stderr
+    bool fused = true;                      // SPL_FUSED=0: separate k_pretok_fast / k_probe kernels (A/B switch)
     int trace_chunk = -1;                   // SPL_TRACE_CHUNK=k: with SPL_TRACE, per-kernel times of the k-th chunk
     uint64_t chunk_bytes = 0;               // pipeline chunk size of spl_encode_batch (0 = automatic)
     SplHostTables host;
@@ -153,7 +154,7 @@ int upload_tables(spl_tokenizer* tk, DevCtx& dc) {
 
 void destroy_ctx(DevCtx& dc) {
     cudaSetDevice(dc.device);
-    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.ids, &dc.out_off, &dc.dec_ids, &dc.dec_off, &dc.dec_ws, &dc.dec_out, &dc.dec_out_off, &dc.run_tot, &dc.sp_zero, &dc.sp_tiles, &dc.sp_text, &dc.sp_doc, &dc.zero, &dc.tstate, &dc.pv, &dc.pool, &dc.mlist, &dc.fbl, &dc.huge})
+    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.ids, &dc.out_off, &dc.dec_ids, &dc.dec_off, &dc.dec_ws, &dc.dec_out, &dc.dec_out_off, &dc.run_tot, &dc.sp_zero, &dc.sp_tiles, &dc.sp_text, &dc.sp_doc, &dc.zero, &dc.tstate, &dc.pv, &dc.pool, &dc.mlist, &dc.fbl, &dc.huge, &dc.defer})
         b->release();
     if (dc.table_blob) cudaFree(dc.table_blob);
     for (auto& e : dc.ev) if (e) cudaEventDestroy(e);
@@ -208,6 +209,7 @@ int reserve_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
     if ((rc = dc.mlist.ensure((size_t)m.base[SPL_NCLS] * 8, tk->err))) return rc;
     uint32_t n_fast_tiles = (uint32_t)((N + SPL_FAST_PAYLOAD * 32u - 1) / (SPL_FAST_PAYLOAD * 32u));
     if ((rc = dc.fbl.ensure((size_t)(n_fast_tiles + 1) * 4, tk->err))) return rc;
+    if ((rc = dc.defer.ensure((z.n_tiles + 1) * 8, tk->err))) return rc;
     if (dc.huge_words == 0) dc.huge_words = (size_t)16 << 20;             // 64 MiB of scratch
     if ((rc = dc.huge.ensure(dc.huge_words * 4, tk->err))) return rc;
     return SPL_OK;
@@ -240,6 +242,8 @@ int prepare_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
     w.mlist = (uint64_t*)dc.mlist.p;
     for (uint32_t c = 0; c <= SPL_NCLS; ++c) w.ml_base[c] = m.base[c];
     w.fb_list = (uint32_t*)dc.fbl.p;
+    w.defer_list = (uint64_t*)dc.defer.p;
+    w.fused = tk->fused;
     w.n_fast_tiles = n_fast_tiles;
     w.huge_pool = (uint32_t*)dc.huge.p;
     w.huge_pool_words = (uint32_t)std::min<size_t>(dc.huge_words, 0xFFFFFFFFu);
@@ -401,6 +405,7 @@ int spl_create(const uint8_t* vocab, size_t vocab_len, int pattern_id, uint32_t 
     if (!tk) return SPL_ERR_OOM;
     if (const char* tr = getenv("SPL_TRACE")) tk->trace = tr[0] == '1';
     if (const char* tc = getenv("SPL_TRACE_CHUNK")) tk->trace_chunk = atoi(tc);
+    if (const char* fu = getenv("SPL_FUSED")) tk->fused = fu[0] != '0';
     if (const char* cb = getenv("SPL_CHUNK_BYTES")) tk->chunk_bytes = strtoull(cb, nullptr, 10);
     uint32_t hflags = ((flags & SPL_CREATE_BYTE_LEVEL) ? SPL_FLAG_BYTE_LEVEL : 0) |
                       ((flags & SPL_CREATE_SENTENCEPIECE) ? SPL_FLAG_SENTENCEPIECE : 0);

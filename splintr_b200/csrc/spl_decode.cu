@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(1024) k_dec_scan(SplDecWork w) {
 struct DecSmem {
     __align__(16) uint8_t stage[DEC_STAGE + 16];
     uint32_t pos[SPL_DEC_TILE + 1];                    // byte offset of every id inside the tile; [TILE] = tile bytes
-    uint32_t wtot[DEC_THREADS / 32];
+    __align__(16) uint32_t wtot[DEC_THREADS / 32];     // aligned: the compiler reads it with LDS.128, which must not cover pos[TILE]
     uint64_t d0, d1;
 };
 

@@ -11,6 +11,7 @@
 // No block waits for another block inside a kernel; the miss lists decouple the rare, latency-bound merge loop from
 // the streaming probe so that both run at full occupancy.  Integer / byte work; no tensor cores.
 #include "spl_device.cuh"
+#include "spl_fast_dev.cuh"
 
 // ------------------------------------------------------------------------------------------
 // probes that only this stage uses
@@ -85,46 +86,33 @@ __device__ __forceinline__ uint64_t ml_entry(uint32_t gpos, uint32_t len, uint32
 }
 
 // ------------------------------------------------------------------------------------------
-// k_probe: one tile per block
+// probe_tile: the whole-piece probe of one 4 KiB tile whose text and piece-start bits are staged in shared memory.
+// Called by all threads of the block (barriers inside); threads beyond SPL_THREADS only take part in the barriers.
+//   k_probe         stages one tile from global memory (text + the piece-start bitmap another kernel wrote)
+//   k_pretok_probe  (spl_kernels.cu) computes the piece starts of two tiles itself and stages both from registers:
+//                   DEFER = true, because the piece starts beyond its own words are not in global memory yet
 // ------------------------------------------------------------------------------------------
 #define PB_WORDS (SPL_PROBE_WIN / 32u + 1u)          // piece-start words staged: bits 0 .. SPL_PROBE_WIN + 31
 #define PB_BITS  (PB_WORDS * 32u)
+#define PROBE_WARPS (SPL_THREADS / 32)
 
-struct ProbeSmem {
-    uint32_t text[SPL_PROBE_WIN / 4 + 4];     // staged bytes (+ slack for the unaligned 8-byte key loads)
-    uint32_t pb[PB_WORDS];                    // piece-start bits
-    uint32_t spw[SPL_TILE / 32];              // special-span bits of the tile (with_special)
-    uint16_t plist[SPL_TILE + 2];             // window positions of the tile's piece starts, in order (+ end of the last piece)
-    uint16_t slow[SPL_TILE];                  // pieces the one-sector probe did not settle (each warp: its own range)
-    uint16_t mloc[SPL_TILE];                  // missed pieces: class 0 from the bottom of the warp's range, class 1 from its top
-    uint32_t wtot[SPL_THREADS / 32];
-    uint32_t last_end;                        // window position of the end of the tile's last piece
-};
-
-__global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
-    __shared__ ProbeSmem sm;
+template <bool DEFER>
+__device__ __forceinline__ void probe_tile(const SplWork& w, SplProbeScratch& sm, const uint32_t* text, const uint32_t* pb,
+                                           const uint32_t tile) {
     const SplTables* T = w.T;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const bool worker = tid < SPL_THREADS;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t N = w.N, Nup = (N + 15u) & ~15u;
-    const uint32_t tile = blockIdx.x, tile0 = tile * SPL_TILE;
+    const uint32_t N = w.N;
+    const uint32_t tile0 = tile * SPL_TILE;
     const SplKey8* __restrict__ t8 = T->t8;
     const uint32_t t8_log2 = T->t8_log2;
 
-    // ---- stage the window -----------------------------------------------------------
-    for (uint32_t v = tid; v < SPL_PROBE_WIN / 16 + 1; v += SPL_THREADS) {
-        uint32_t g = tile0 + v * 16;
-        uint4 x = make_uint4(0, 0, 0, 0);
-        if (g < Nup) x = __ldg(reinterpret_cast<const uint4*>(w.text + g));
-        reinterpret_cast<uint4*>(sm.text)[v] = x;
-    }
-    for (uint32_t v = tid; v < PB_WORDS; v += SPL_THREADS) sm.pb[v] = __ldg(w.pstart + (tile0 >> 5) + v);
     if (w.with_special && tid < SPL_TILE / 32) sm.spw[tid] = __ldg(w.spec + (tile0 >> 5) + tid);
-    __syncthreads();
 
     // ---- piece list: positions of the piece starts of this tile, in order ------------------
     const uint32_t avail = N - tile0;                          // text bytes from tile0 on
-    uint32_t my = (sm.pb[tid >> 1] >> ((tid & 1u) * 16u)) & 0xFFFFu;
+    uint32_t my = worker ? (pb[tid >> 1] >> ((tid & 1u) * 16u)) & 0xFFFFu : 0u;
     if (tid * 16u + 16u > avail) my &= (tid * 16u >= avail) ? 0u : ((1u << (avail - tid * 16u)) - 1u);   // sentinel bit at N
     uint32_t cnt = __popc(my), incl = cnt;
 #pragma unroll
@@ -132,11 +120,11 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
         uint32_t t = __shfl_up_sync(FULL, incl, o);
         if (lane >= (uint32_t)o) incl += t;
     }
-    if (lane == 31) sm.wtot[warp] = incl;
+    if (lane == 31 && worker) sm.wtot[warp] = incl;
     __syncthreads();
     uint32_t base = incl - cnt, P = 0;
 #pragma unroll
-    for (uint32_t q = 0; q < SPL_THREADS / 32; ++q) {
+    for (uint32_t q = 0; q < PROBE_WARPS; ++q) {
         uint32_t t = sm.wtot[q];
         base += (q < warp) ? t : 0u;
         P += t;
@@ -147,8 +135,11 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
         sm.plist[base++] = (uint16_t)(tid * 16u + b);
     }
     if (tid == 0) {
-        uint32_t e = sm_next_bit(sm.pb, SPL_TILE < avail ? SPL_TILE : avail, PB_BITS);
-        if (P && e >= PB_BITS) e = g_next_bit(w.pstart, tile0 + PB_BITS, N + 1) - tile0;    // the last piece leaves the staged bits
+        uint32_t e = sm_next_bit(pb, SPL_TILE < avail ? SPL_TILE : avail, PB_BITS);
+        if (P && e >= PB_BITS) {                                   // the last piece leaves the staged bits
+            if (DEFER) e = SPL_RANK_NONE;                          // its end is some other block's business: see k_probe_rest
+            else e = g_next_bit(w.pstart, tile0 + PB_BITS, N + 1) - tile0;
+        }
         sm.last_end = e;
         sm.plist[P] = (uint16_t)(e >= PB_BITS ? 0xFFFFu : e);      // 0xFFFF: see last_end
         w.tinfo[tile].np = P;
@@ -158,7 +149,7 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
 
     // From here on every warp works alone on its own range of pieces [jlo, jhi): no block barrier, a warp with
     // slow pieces does not hold the others back.
-    const uint32_t per = (((P + SPL_THREADS / 32 - 1) / (SPL_THREADS / 32)) + 31u) & ~31u;
+    const uint32_t per = (((P + PROBE_WARPS - 1) / PROBE_WARPS) + 31u) & ~31u;
     const uint32_t jlo = warp * per < P ? warp * per : P, jhi = jlo + per < P ? jlo + per : P;
     const uint32_t pvbase = tile * SPL_TILE;
 
@@ -177,7 +168,7 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
         bool found = false;
         if (fast) {
             const uint32_t wi = s >> 2, sh = (s & 3u) * 8u;
-            const uint32_t a = sm.text[wi], b = sm.text[wi + 1], c = sm.text[wi + 2];
+            const uint32_t a = text[wi], b = text[wi + 1], c = text[wi + 2];
             uint32_t lo = __funnelshift_r(a, b, sh), hi = __funnelshift_r(b, c, sh);
             const uint32_t nb = len * 8u;
             lo &= nb >= 32u ? FULL : ((1u << nb) - 1u);
@@ -205,23 +196,29 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
             if (e == 0xFFFFu) e = sm.last_end;
             const uint32_t len = e - s, gpos = tile0 + s;
             uint32_t val = SPL_PV_NONE;
-            if (w.with_special && ((sm.spw[s >> 5] >> (s & 31)) & 1u)) {
+            if (DEFER && e == SPL_RANK_NONE) {
+                // the end of this piece (the tile's last, longer than the staged bits) is not known yet: k_probe_rest
+                // looks it up once every piece start is in global memory and files the piece in its length class
+                const uint32_t di = atomicAdd(&w.counters[SPL_CTR_DEFER], 1u);
+                w.defer_list[di] = (uint64_t)gpos | ((uint64_t)j << 32);
+                val = SPL_PV_NONE - 1u;                            // placeholder (overwritten by k_probe_rest)
+            } else if (w.with_special && ((sm.spw[s >> 5] >> (s & 31)) & 1u)) {
                 val = special_id_g(T, w.text + gpos, len);
             } else if (len == 1) {
-                uint32_t sy = T->byte_sym[sm_byte(sm.text, s)];
+                uint32_t sy = T->byte_sym[sm_byte(text, s)];
                 val = sy < SPL_UNK_BASE ? sy : SPL_PV_NONE;   // unknown byte: no id (bpe.rs:73-75)
             } else {
                 uint32_t id = SPL_RANK_NONE;
                 if (len <= 8) {
-                    uint64_t k0 = sm_load8(sm.text, s);
+                    uint64_t k0 = sm_load8(text, s);
                     if (len < 8) k0 &= (1ull << (8 * len)) - 1;
                     id = lookup8(t8, t8_log2, k0, len);
                 } else if (len <= 16) {
-                    uint64_t k0 = sm_load8(sm.text, s), k1 = sm_load8(sm.text, s + 8);
+                    uint64_t k0 = sm_load8(text, s), k1 = sm_load8(text, s + 8);
                     if (len < 16) k1 &= (1ull << (8 * (len - 8))) - 1;
                     id = lookup16(T->t16, T->t16_log2, k0, k1, len);
                 } else if (len <= SPL_PROBE_HALO && len <= T->max_key_len) {
-                    id = lookupL_thread(T, sm.text, s, len);
+                    id = lookupL_thread(T, text, s, len);
                 }
                 if (id != SPL_RANK_NONE) val = id;
                 else cls = 1u + spl_len_class(len);
@@ -278,6 +275,161 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
             w.mlist[midx] = ml_entry(tile0 + s, e - s, j);
             w.pv[pvbase + j] = SPL_PV_MISS | midx;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_pretok_probe: the bit-parallel pre-tokenizer (k_pretok_fast, spl_kernels.cu: same three phases) and the probe of
+// the two tiles it has just decided, in one kernel.  The 32 text bytes every thread classified are still in its
+// registers and so is its word of piece starts: both go to shared memory directly, the text is not read a second
+// time and the probe does not wait for a bitmap round trip through global memory.  Blocks in the (integer-pipe bound)
+// classification phases and blocks in the (L1-wavefront bound) probe phase share an SM.
+// The probe needs the piece starts of SPL_PROBE_HALO + 32 bits beyond its tile: the first FUSE_EXT halo words, which
+// this block computes anyway; they are trusted under the same rule as the payload (no carry from outside the window).
+// A block that cannot decide its words appends its tile to the fallback list exactly like k_pretok_fast and probes
+// nothing; k_pretok_fb and k_probe_rest finish those tiles.
+// ------------------------------------------------------------------------------------------
+#define FUSE_EXT 5u                                   // halo words whose piece starts the probe of the second tile reads
+#define FUSE_TILES (SPL_FAST_PAYLOAD * 32u / SPL_TILE)
+
+struct FusedProbeSmem {
+    uint32_t text[(SPL_FAST_PAYLOAD + FUSE_EXT) * 8u + 8u];     // payload + ext words (+ slack for the unaligned key loads)
+    uint32_t pb[SPL_FAST_PAYLOAD + FUSE_EXT + 1u];
+    SplProbeScratch ps;
+};
+union FusedSmem {
+    FastSmem fast;                                    // phases A-C
+    FusedProbeSmem probe;                             // afterwards
+};
+
+__global__ void __launch_bounds__(SPL_FAST_THREADS, 4) k_pretok_probe(SplWork w) {
+    __shared__ FusedSmem sm;
+    const int k = threadIdx.x;
+    const int gw0 = (int)(blockIdx.x * SPL_FAST_PAYLOAD) - (int)SPL_FAST_HALO;
+    const int gw = gw0 + k;
+    const uint32_t N = w.N;
+    const SplTables* T = w.T;
+    const uint32_t last_word = N >> 5;                        // the word that holds the sentinel bit N
+
+    // ---- phase A: classify my word ------------------------------------------------------------------
+    SplFastWord fw;
+#pragma unroll
+    for (int q = 0; q <= FM_BAD; ++q) fw.m[q] = 0;
+    uint32_t hw = 0, sw = 0;
+    uint32_t xw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (gw >= 0 && (uint32_t)gw <= last_word) {
+        const uint32_t base = (uint32_t)gw * 32u;
+        hw = __ldg(w.hard + gw);
+        if (w.with_special) sw = __ldg(w.spec + gw);
+        if (base < N) {
+            const uint4* p4 = reinterpret_cast<const uint4*>(w.text + base);
+            uint4 a = __ldg(p4);
+            uint4 b = (base + 16u < ((N + 15u) & ~15u)) ? __ldg(p4 + 1) : make_uint4(0, 0, 0, 0);
+            xw[0] = a.x; xw[1] = a.y; xw[2] = a.z; xw[3] = a.w; xw[4] = b.x; xw[5] = b.y; xw[6] = b.z; xw[7] = b.w;
+            FastGText t{w.text};
+            fw = spl_fast_classify(t, xw, base, N, T->ucd_stage1, T->ucd_stage2, w.pattern);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q <= FM_BAD; ++q) sm.fast.m[q][k] = fw.m[q];
+    sm.fast.hardw[k] = hw; sm.fast.specw[k] = sw;
+    __syncthreads();
+
+    // ---- phase B: local masks, fills, summary ------------------------------------------------------------
+    FastMasks M{&sm.fast, gw0, N};
+    SplFastLocal loc;
+    uint32_t s = spl_fast_local(M, k, SPL_FAST_THREADS, w.pattern, loc);
+    sm.fast.sum[k] = s;
+    sm.fast.m[FM_A2][k] = loc.A2; sm.fast.m[FM_A3][k] = loc.A3;
+    __syncthreads();
+
+    // ---- phase C: carries, piece starts --------------------------------------------------------------------
+    bool structural = false, unknown = false;
+    uint32_t start = spl_fast_final(M, loc, k, SPL_FAST_THREADS, w.pattern, w.with_special, structural, unknown);
+    const bool payload = k >= (int)SPL_FAST_HALO && k < (int)(SPL_FAST_HALO + SPL_FAST_PAYLOAD);
+    const bool staged = k >= (int)SPL_FAST_HALO && k < (int)(SPL_FAST_HALO + SPL_FAST_PAYLOAD + FUSE_EXT);
+    int flag = ((s & FS_BAD) != 0) || structural || (staged && unknown);
+    flag = __syncthreads_or(flag);                 // (also: nobody reads sm.fast any more)
+    if (flag) {
+        if (k == 0) {
+            uint32_t idx = atomicAdd(&w.counters[SPL_CTR_FB], 1u);
+            w.fb_list[idx] = blockIdx.x;
+        }
+        return;
+    }
+    if ((uint32_t)gw == last_word) start |= 1u << (N & 31u);
+    if (payload && (uint32_t)gw <= last_word) w.pstart[gw] = start;
+
+    // ---- stage text and piece starts for the probe, from registers ----------------------------------------
+    if (staged) {
+        const uint32_t pk = (uint32_t)k - SPL_FAST_HALO;
+        uint4* dst = reinterpret_cast<uint4*>(sm.probe.text + pk * 8u);
+        dst[0] = make_uint4(xw[0], xw[1], xw[2], xw[3]);
+        dst[1] = make_uint4(xw[4], xw[5], xw[6], xw[7]);
+        sm.probe.pb[pk] = ((uint32_t)gw <= last_word) ? start : 0u;
+    }
+    if (k < 8) sm.probe.text[(SPL_FAST_PAYLOAD + FUSE_EXT) * 8u + k] = 0u;
+    if (k == 8) sm.probe.pb[SPL_FAST_PAYLOAD + FUSE_EXT] = 0u;
+    __syncthreads();
+#pragma unroll 1
+    for (uint32_t sub = 0; sub < FUSE_TILES; ++sub) {
+        const uint32_t tile = blockIdx.x * FUSE_TILES + sub;
+        if (tile >= w.n_tiles) break;
+        if (sub) __syncthreads();                  // the scratch of the previous tile is free
+        probe_tile<true>(w, sm.probe.ps, sm.probe.text + sub * (SPL_TILE / 4u), sm.probe.pb + sub * (SPL_TILE / 32u), tile);
+    }
+}
+
+struct ProbeSmem {
+    uint32_t text[SPL_PROBE_WIN / 4 + 4];     // staged bytes (+ slack for the unaligned 8-byte key loads)
+    uint32_t pb[PB_WORDS];                    // piece-start bits
+    SplProbeScratch ps;
+};
+
+// stage one tile (text window + piece-start bits) from global memory
+__device__ __forceinline__ void probe_stage(const SplWork& w, ProbeSmem& sm, const uint32_t tile) {
+    const uint32_t tid = threadIdx.x, tile0 = tile * SPL_TILE, Nup = (w.N + 15u) & ~15u;
+    for (uint32_t v = tid; v < SPL_PROBE_WIN / 16 + 1; v += blockDim.x) {
+        uint32_t g = tile0 + v * 16;
+        uint4 x = make_uint4(0, 0, 0, 0);
+        if (g < Nup) x = __ldg(reinterpret_cast<const uint4*>(w.text + g));
+        reinterpret_cast<uint4*>(sm.text)[v] = x;
+    }
+    for (uint32_t v = tid; v < PB_WORDS; v += blockDim.x) sm.pb[v] = __ldg(w.pstart + (tile0 >> 5) + v);
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
+    __shared__ ProbeSmem sm;
+    probe_stage(w, sm, blockIdx.x);
+    probe_tile<false>(w, sm.ps, sm.text, sm.pb, blockIdx.x);
+}
+
+// After k_pretok_probe + k_pretok_fb: (1) the tiles the bit-parallel pre-tokenizer handed to the sequential rules are
+// probed here, now that their piece starts exist; (2) every deferred piece (see probe_tile) gets its end, its length
+// class and its miss-list entry.
+__global__ void __launch_bounds__(SPL_THREADS) k_probe_rest(SplWork w) {
+    __shared__ ProbeSmem sm;
+    const uint32_t n_fb = w.counters[SPL_CTR_FB];
+    for (uint32_t i = blockIdx.x; i < n_fb; i += gridDim.x) {
+#pragma unroll 1
+        for (uint32_t sub = 0; sub < SPL_FAST_PAYLOAD * 32u / SPL_TILE; ++sub) {
+            const uint32_t tile = w.fb_list[i] * (SPL_FAST_PAYLOAD * 32u / SPL_TILE) + sub;
+            if (tile >= w.n_tiles) break;
+            __syncthreads();
+            probe_stage(w, sm, tile);
+            probe_tile<false>(w, sm.ps, sm.text, sm.pb, tile);
+        }
+    }
+    const uint32_t n_def = w.counters[SPL_CTR_DEFER];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_def; i += gridDim.x * blockDim.x) {
+        const uint64_t d = w.defer_list[i];
+        const uint32_t gpos = (uint32_t)d, j = (uint32_t)(d >> 32);
+        const uint32_t len = g_next_bit(w.pstart, gpos + 1, w.N + 1) - gpos;     // > SPL_PROBE_HALO: k_bpe tries the whole piece
+        const uint32_t c = spl_len_class(len);
+        const uint32_t midx = w.ml_base[c] + atomicAdd(&w.counters[SPL_CTR_CLS + c], 1u);
+        w.mlist[midx] = ml_entry(gpos, len, j);
+        w.pv[(gpos / SPL_TILE) * SPL_TILE + j] = SPL_PV_MISS | midx;
     }
 }
 
@@ -810,13 +962,25 @@ __global__ void __launch_bounds__(SPL_THREADS, 8) k_emit(SplWork w) {
 void spl_encode_init() {
     cudaFuncSetAttribute(k_bpe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BPE_SMEM_BYTES);
     cudaFuncSetAttribute(k_probe, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
+    cudaFuncSetAttribute(k_probe_rest, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
+    cudaFuncSetAttribute(k_pretok_probe, cudaFuncAttributePreferredSharedMemoryCarveout, 75);
     cudaFuncSetAttribute(k_emit, cudaFuncAttributePreferredSharedMemoryCarveout, 75);
     cudaGetLastError();
 }
 
-void spl_launch_encode_stage(const SplWork& w, int num_sms, cudaStream_t stream, SplMarkFn mark, void* ctx) {
-    k_probe<<<w.n_tiles, SPL_THREADS, 0, stream>>>(w);
-    mark(ctx, "k_probe");
+void spl_launch_pretok_probe(const SplWork& w, cudaStream_t stream) {
+    k_pretok_probe<<<w.n_fast_tiles, SPL_FAST_THREADS, 0, stream>>>(w);
+}
+
+void spl_launch_encode_stage(const SplWork& w, int num_sms, cudaStream_t stream, SplMarkFn mark, void* ctx, bool probed) {
+    if (probed) {
+        // k_pretok_probe has probed every tile the bit-parallel pre-tokenizer decided; the rest + deferred pieces here
+        k_probe_rest<<<(uint32_t)num_sms * 2u, SPL_THREADS, 0, stream>>>(w);
+        mark(ctx, "k_probe_rest");
+    } else {
+        k_probe<<<w.n_tiles, SPL_THREADS, 0, stream>>>(w);
+        mark(ctx, "k_probe");
+    }
     k_bpe<<<(uint32_t)num_sms * 5u, SPL_BPE_THREADS, BPE_SMEM_BYTES, stream>>>(w);
     mark(ctx, "k_bpe");
     k_chunk_scan<<<1, 1024, 0, stream>>>(w);

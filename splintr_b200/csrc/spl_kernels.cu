@@ -12,6 +12,7 @@
 #include "spl_device.cuh"
 #include "spl_pretok.h"
 #include "spl_pretok_fast.h"
+#include "spl_fast_dev.cuh"
 
 // ------------------------------------------------------------------------------------------
 // k_mark_docs
@@ -167,33 +168,6 @@ __global__ void __launch_bounds__(SPL_THREADS) k_pretok(SplWork w) {
 // FAST_HALO words of context on each side of FAST_PAYLOAD payload words.  A tile that cannot be
 // decided here is appended to the fallback list and left untouched.
 // ------------------------------------------------------------------------------------------
-struct FastGText {
-    const uint8_t* p;
-    __device__ __forceinline__ uint8_t byte(uint32_t i) const { return __ldg(p + i); }
-};
-
-struct FastSmem {
-    uint32_t m[FM_COUNT][SPL_FAST_THREADS];
-    uint32_t hardw[SPL_FAST_THREADS];
-    uint32_t specw[SPL_FAST_THREADS];
-    uint32_t sum[SPL_FAST_THREADS];
-};
-
-struct FastMasks {
-    const FastSmem* s; int gw0; uint32_t N;
-    __device__ __forceinline__ uint32_t get(int q, int k) const { return s->m[q][k]; }
-    __device__ __forceinline__ uint32_t hard(int k) const { return s->hardw[k]; }
-    __device__ __forceinline__ uint32_t spec(int k) const { return s->specw[k]; }
-    __device__ __forceinline__ uint32_t summary(int k) const { return s->sum[k]; }
-    __device__ __forceinline__ uint32_t valid(int k) const {
-        int gw = gw0 + k;
-        if (gw < 0) return 0u;
-        uint32_t base = (uint32_t)gw * 32u;
-        if (base >= N) return 0u;
-        return (N - base >= 32u) ? 0xFFFFFFFFu : ((1u << (N - base)) - 1u);
-    }
-};
-
 __global__ void __launch_bounds__(SPL_FAST_THREADS) k_pretok_fast(SplWork w) {
     __shared__ FastSmem sm;
     const int k = threadIdx.x;
@@ -299,6 +273,7 @@ int spl_launch_encode(const SplWork& w, int num_sms, cudaStream_t stream, SplKer
     MarkCtx mc{prof, stream, 0};
     if (prof) { prof->n = 0; cudaEventRecord(prof->ev[0], stream); }
     auto mark = [&](const char* name) { mark_cb(&mc, name); };
+    bool probed = false;
     {
         uint32_t n = w.n_docs + 1;
         k_mark_docs<<<(n + 255) / 256, 256, 0, stream>>>(w);
@@ -315,6 +290,13 @@ int spl_launch_encode(const SplWork& w, int num_sms, cudaStream_t stream, SplKer
     } else if (w.N && w.pattern == SPL_PAT_MISTRAL_V3) {
         k_pretok<<<(w.N + SPL_TILE - 1) / SPL_TILE, SPL_THREADS, 0, stream>>>(w);
         mark("k_pretok");
+    } else if (w.N && w.fused) {
+        spl_launch_pretok_probe(w, stream);
+        mark("k_pretok_probe");
+        uint32_t cap = (uint32_t)num_sms * 4;
+        k_pretok_fb<<<w.n_fast_tiles < cap ? w.n_fast_tiles : cap, SPL_THREADS, 0, stream>>>(w);
+        mark("k_pretok_fb");
+        probed = true;
     } else if (w.N) {
         k_pretok_fast<<<w.n_fast_tiles, SPL_FAST_THREADS, 0, stream>>>(w);
         mark("k_pretok_fast");
@@ -322,6 +304,6 @@ int spl_launch_encode(const SplWork& w, int num_sms, cudaStream_t stream, SplKer
         k_pretok_fb<<<w.n_fast_tiles < cap ? w.n_fast_tiles : cap, SPL_THREADS, 0, stream>>>(w);
         mark("k_pretok_fb");
     }
-    spl_launch_encode_stage(w, num_sms, stream, mark_cb, &mc);
+    spl_launch_encode_stage(w, num_sms, stream, mark_cb, &mc, probed);
     return mc.launches;
 }

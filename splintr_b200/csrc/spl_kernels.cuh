@@ -70,6 +70,8 @@ struct SplWork {
     uint32_t        ml_base[SPL_NCLS + 1];   // class c owns mlist[ml_base[c] .. ml_base[c+1])
     uint32_t*       counters;         // [SPL_CTR_WORDS]: see SPL_CTR_*
     uint32_t*       fb_list;          // [n_fast_tiles] fast-path tiles handed to the sequential rules
+    uint64_t*       defer_list;       // [n_tiles] fused front end: pieces whose end lies beyond the staged bits (gpos | piece index << 32)
+    bool            fused;            // front end = k_pretok_probe (pre-tokenizer + probe in one kernel)
     uint32_t        n_fast_tiles;
     uint32_t*       huge_pool;        // scratch for pieces that outgrow shared memory
     uint32_t        huge_pool_words;
@@ -85,7 +87,7 @@ struct SplWork {
 };
 
 // SplWork::counters
-enum : uint32_t { SPL_CTR_ERR = 1, SPL_CTR_HUGE_POOL = 2, SPL_CTR_FB = 3,
+enum : uint32_t { SPL_CTR_ERR = 1, SPL_CTR_HUGE_POOL = 2, SPL_CTR_FB = 3, SPL_CTR_DEFER = 5,
                   SPL_CTR_CLS = 8,            // [8 .. 8 + SPL_NCLS): entries in the miss list of each class
                   SPL_CTR_WORDS = 32 };
 
@@ -143,4 +145,16 @@ void spl_launch_decode_emit(const SplDecLaunch& L, cudaStream_t stream);    // k
 // spl_encode.cu: the encode stage behind the pre-tokenizer (k_probe, k_bpe, k_tile_scan, k_emit)
 typedef void (*SplMarkFn)(void* ctx, const char* name);
 void spl_encode_init();
-void spl_launch_encode_stage(const SplWork& w, int num_sms, cudaStream_t stream, SplMarkFn mark, void* ctx);
+// probed: the front end was k_pretok_probe, which has already probed the tiles it decided
+void spl_launch_encode_stage(const SplWork& w, int num_sms, cudaStream_t stream, SplMarkFn mark, void* ctx, bool probed);
+void spl_launch_pretok_probe(const SplWork& w, cudaStream_t stream);   // k_pretok_probe (bit-parallel pre-tokenizer + probe)
+
+// per-tile scratch of the whole-piece probe (spl_encode.cu: probe_tile)
+struct SplProbeScratch {
+    uint32_t spw[SPL_TILE / 32];              // special-span bits of the tile (with_special)
+    uint16_t plist[SPL_TILE + 2];             // window positions of the tile's piece starts, in order (+ end of the last piece)
+    uint16_t slow[SPL_TILE];                  // pieces the one-sector probe did not settle (each warp: its own range)
+    uint16_t mloc[SPL_TILE];                  // missed pieces: class 0 from the bottom of the warp's range, class 1 from its top
+    uint32_t wtot[SPL_THREADS / 32];
+    uint32_t last_end;                        // window position of the end of the tile's last piece
+};

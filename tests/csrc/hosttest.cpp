@@ -187,6 +187,13 @@ struct HostFastMasks {
     uint32_t summary(int k) const { return sum[k]; }
 };
 
+// The fused kernel (k_pretok_probe) also trusts the first `ht_fast_ext` words of the right halo of a tile that did
+// not fall back.  With ht_fast_ext > 0 a carry that enters one of those words from outside the window also sends the
+// tile to the fallback, and for the other tiles bit 2 (value 4) of starts[i] marks the piece starts those words
+// report, bit 3 (value 8) the bytes they cover.
+static int ht_fast_ext = 0;
+extern "C" void ht_set_fast_ext(int e) { ht_fast_ext = e; }
+
 // starts[i] = 1 at piece starts found by the fast path; tile_flag[t] = 1 when tile t asked for the fallback
 extern "C" int ht_scan_fast(int pattern, const uint8_t* text, uint32_t n, uint32_t payload, uint32_t halo,
                             const uint8_t* hard, const uint8_t* spec, uint8_t* starts, uint8_t* tile_flag) {
@@ -224,12 +231,12 @@ extern "C" int ht_scan_fast(int pattern, const uint8_t* text, uint32_t n, uint32
         for (int k = 0; k < nw; ++k) { M.m[FM_A2][k] = loc[k].A2; M.m[FM_A3][k] = loc[k].A3; }
         bool fb = false;
         for (int k = 0; k < nw; ++k) if (M.sum[k] & FS_BAD) fb = true;
-        std::vector<uint32_t> out(payload, 0);
+        std::vector<uint32_t> out(payload + ht_fast_ext, 0);
         for (int k = 0; k < nw; ++k) {
             bool st = false, un = false;
             uint32_t v = spl_fast_final(M, loc[k], k, nw, pattern, spec != nullptr, st, un);
             if (st) fb = true;
-            if (k >= (int)halo && k < (int)(halo + payload)) { out[k - halo] = v; if (un) fb = true; }
+            if (k >= (int)halo && k < (int)(halo + payload + ht_fast_ext)) { out[k - halo] = v; if (un) fb = true; }
         }
         tile_flag[tile] = fb ? 1 : 0;
         if (fb) {
@@ -257,6 +264,13 @@ extern "C" int ht_scan_fast(int pattern, const uint8_t* text, uint32_t n, uint32
                     uint32_t i = ((uint32_t)tile * payload + pk) * 32u + b;
                     if (i < n) starts[i] |= 1;
                 }
+        for (uint32_t pk = payload; pk < payload + (uint32_t)ht_fast_ext; ++pk)
+            for (uint32_t b = 0; b < 32; ++b) {
+                uint32_t i = ((uint32_t)tile * payload + pk) * 32u + b;
+                if (i >= n) continue;
+                starts[i] |= 8;
+                if ((out[pk] >> b) & 1u) starts[i] |= 4;
+            }
     }
     return 0;
 }

@@ -92,6 +92,27 @@ def scan_kernel_emul(pattern_id, data: bytes, tile, halo, chunk, hard, spec=None
     return np.flatnonzero(st[:n]).tolist()
 
 
+def scan_fast_ext(pattern_id, data: bytes, payload, halo, ext, hard, spec=None):
+    """The fused kernel's use of the bit-parallel path: the first `ext` right-halo words of a decided tile are trusted
+    too.  Returns (raw flag array: 1 fast start, 2 fallback start, 4 start reported by an ext word, 8 covered by an
+    ext word; per-tile fallback flags)."""
+    n = len(data)
+    h = np.asarray(hard, dtype=np.uint8)
+    st = np.zeros(n + 1, dtype=np.uint8)
+    n_tiles = max(1, (n + payload * 32 - 1) // (payload * 32))
+    flags = np.zeros(n_tiles, dtype=np.uint8)
+    sp = None if spec is None else np.asarray(spec, dtype=np.uint8)
+    lib = load()
+    lib.ht_set_fast_ext(ext)
+    try:
+        rc = lib.ht_scan_fast(pattern_id, data, n, payload, halo, h.ctypes.data,
+                              None if sp is None else sp.ctypes.data, st.ctypes.data, flags.ctypes.data)
+    finally:
+        lib.ht_set_fast_ext(0)
+    assert rc == 0, rc
+    return st[:n], flags.tolist()
+
+
 def scan_fast(pattern_id, data: bytes, payload, halo, hard, spec=None):
     """Bit-parallel path under a (payload, halo)-word tiling.  Returns (starts list, per-tile fallback flags)."""
     n = len(data)

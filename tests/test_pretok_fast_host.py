@@ -134,3 +134,38 @@ def test_survey_examples():
     for name, pid in PATS:
         for e in ex:
             check_batch(name, pid, [e], ((1, 1), (8, 16)))
+
+
+@pytest.mark.parametrize("name,pid", PATS[:2])
+def test_fused_kernel_trusts_the_first_halo_words(name, pid):
+    """k_pretok_probe (pre-tokenizer + probe in one kernel) reads the piece starts of the first words of its right halo
+    from its own computation instead of from global memory.  Under the same rule as for the payload (no carry enters
+    the word from outside the window) those bits must equal the reference split, for every tiling."""
+    rng = random.Random(31 + pid)
+    checked = 0
+    for it in range(1500):
+        if it % 3 == 0:
+            docs = [runs_text(rng) for _ in range(rng.randint(1, 3))]
+        elif it % 3 == 1:
+            docs = ["".join(rng.choice(NATURAL) for _ in range(rng.randint(1, rng.choice([30, 120, 400])))) for _ in range(rng.randint(1, 4))]
+        else:
+            docs = ["".join(rng.choice(ALPHABET) for _ in range(rng.randint(1, 90))) for _ in range(rng.randint(1, 4))]
+            docs = [d for d in docs if "᠎" not in d] or ["a"]
+        enc = [d.encode() for d in docs]
+        data = b"".join(enc)
+        if not data:
+            continue
+        hard = np.zeros(len(data) + 1, dtype=np.uint8)
+        want, off = set(), 0
+        for d, e in zip(docs, enc):
+            hard[off] = 1
+            want |= {off + s for s in oracle_starts(name, d)}
+            off += len(e)
+        hard[len(data)] = 1
+        for payload, halo, ext in ((1, 2, 1), (2, 3, 2), (2, 8, 5), (4, 16, 5)):
+            st, flags = hostlib.scan_fast_ext(pid, data, payload, halo, ext, hard)
+            cov = np.flatnonzero(st & 8)
+            for i in cov.tolist():
+                assert bool(st[i] & 4) == (i in want), (name, payload, halo, ext, i, docs)
+            checked += len(cov)
+    assert checked > 20000

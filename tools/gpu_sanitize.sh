@@ -17,7 +17,18 @@ for name in ("cl100k_base", "llama3", "deepseek_v3"):
     vb = P.load_vocab_bytes(P.PRESETS[name].vocab_file)
     d, o = synth.cfg2(vb, 300) if name == "cl100k_base" else (synth.cfg4(vb, 1, 300000.0) if name == "llama3" else synth.cfg5(vb, 300))
     ids, off = tok.encode_packed(d, o)
+    data, boff = tok.decode_packed(ids, off)                       # decode kernels (row N2)
+    assert np.array_equal(data, d) and np.array_equal(boff, o)
     print(name, sum(len(x) for x in a), sum(len(x) for x in b), len(ids), flush=True)
+# SentencePiece mode (row N3): transform kernels + encode stage over the transformed text, with specials
+ws = [" ", "  ", "\n", "\t", "\x0b", "\xa0", "\u3000"]
+sp_texts = texts + ["".join(rng.choice(ws) if rng.random() < 0.4 else rng.choice("ab,Z\u00e9\u4e2d") for _ in range(rng.randint(0, 300))) for _ in range(200)]
+sp_texts += [" " * 5000 + "y", "x\x0b" + " " * 5000, "a [INST] b [/INST]  <|think|> "]
+tok = Tokenizer.from_pretrained("mistral_v2", devices=[0])
+a = tok.encode_batch(sp_texts)
+b = tok.encode_batch_with_special(sp_texts)
+assert tok.decode_batch(a[:50]) == sp_texts[:50]
+print("mistral_v2", sum(len(x) for x in a), sum(len(x) for x in b), flush=True)
 PY
 for tool in memcheck racecheck; do
   timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python /tmp/san_driver.py > gpurun_out/sanitizer_$tool.log 2>&1
