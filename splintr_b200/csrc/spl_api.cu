@@ -73,7 +73,7 @@ struct PinnedBuf { void* p; size_t cap; };
 struct spl_tokenizer {
     bool profiling = false;
     bool trace = false;                     // SPL_TRACE=1: per-chunk timeline of spl_encode_batch on stderr
-    bool fused = true;                      // SPL_FUSED=0: separate k_pretok_fast / k_probe kernels (A/B switch)
+    bool fused = false;                     // SPL_FUSED=1: k_pretok_probe instead of k_pretok_fast + k_probe (experiment)
     int trace_chunk = -1;                   // SPL_TRACE_CHUNK=k: with SPL_TRACE, per-kernel times of the k-th chunk
     uint64_t chunk_bytes = 0;               // pipeline chunk size of spl_encode_batch (0 = automatic)
     SplHostTables host;

@@ -108,8 +108,7 @@ __device__ __forceinline__ void probe_tile(const SplWork& w, SplProbeScratch& sm
     const SplKey8* __restrict__ t8 = T->t8;
     const uint32_t t8_log2 = T->t8_log2;
 
-    if (w.with_special && tid < SPL_TILE / 32) sm.spw[tid] = __ldg(w.spec + (tile0 >> 5) + tid);
-
+    // (sm.spw, the special-span bits of the tile, is filled by the caller together with text and pb)
     // ---- piece list: positions of the piece starts of this tile, in order ------------------
     const uint32_t avail = N - tile0;                          // text bytes from tile0 on
     uint32_t my = worker ? (pb[tid >> 1] >> ((tid & 1u) * 16u)) & 0xFFFFu : 0u;
@@ -376,6 +375,7 @@ __global__ void __launch_bounds__(SPL_FAST_THREADS, 4) k_pretok_probe(SplWork w)
         const uint32_t tile = blockIdx.x * FUSE_TILES + sub;
         if (tile >= w.n_tiles) break;
         if (sub) __syncthreads();                  // the scratch of the previous tile is free
+        if (w.with_special && k < (int)(SPL_TILE / 32)) sm.probe.ps.spw[k] = __ldg(w.spec + tile * (SPL_TILE / 32u) + k);
         probe_tile<true>(w, sm.probe.ps, sm.probe.text + sub * (SPL_TILE / 4u), sm.probe.pb + sub * (SPL_TILE / 32u), tile);
     }
 }
@@ -389,13 +389,14 @@ struct ProbeSmem {
 // stage one tile (text window + piece-start bits) from global memory
 __device__ __forceinline__ void probe_stage(const SplWork& w, ProbeSmem& sm, const uint32_t tile) {
     const uint32_t tid = threadIdx.x, tile0 = tile * SPL_TILE, Nup = (w.N + 15u) & ~15u;
-    for (uint32_t v = tid; v < SPL_PROBE_WIN / 16 + 1; v += blockDim.x) {
+    for (uint32_t v = tid; v < SPL_PROBE_WIN / 16 + 1; v += SPL_THREADS) {
         uint32_t g = tile0 + v * 16;
         uint4 x = make_uint4(0, 0, 0, 0);
         if (g < Nup) x = __ldg(reinterpret_cast<const uint4*>(w.text + g));
         reinterpret_cast<uint4*>(sm.text)[v] = x;
     }
-    for (uint32_t v = tid; v < PB_WORDS; v += blockDim.x) sm.pb[v] = __ldg(w.pstart + (tile0 >> 5) + v);
+    for (uint32_t v = tid; v < PB_WORDS; v += SPL_THREADS) sm.pb[v] = __ldg(w.pstart + (tile0 >> 5) + v);
+    if (w.with_special && tid < SPL_TILE / 32) sm.ps.spw[tid] = __ldg(w.spec + (tile0 >> 5) + tid);
     __syncthreads();
 }
 
