@@ -410,3 +410,28 @@ def test_sentencepiece_pipelined_small_chunks(toks, monkeypatch):
     texts[3] = ""; texts[17] = " " * 50_000; texts[18] = ""; texts[-1] = ""
     assert t.encode_batch(texts) == o.encode_batch(texts)
     assert t.pcre2().encode("a  b") == o.encode("a  b")           # clones keep the mode
+
+
+def test_fused_front_end_is_bit_exact(monkeypatch):
+    """SPL_FUSED=1 selects k_pretok_probe (pre-tokenizer + probe in one kernel, deferred list for pieces that leave the
+    staged bits, k_probe_rest for the tiles the bit-parallel path declines) -- not the default (no faster),
+    but kept working: fuzz, long pieces across tile ends, specials, cfg3 / cfg4 samples against the C oracle."""
+    from splintr_b200 import Tokenizer
+    monkeypatch.setenv("SPL_FUSED", "1")
+    toks_f = {n: Tokenizer.from_pretrained(n, devices=[0]) for n in ("cl100k_base", "o200k_base", "llama3")}
+    monkeypatch.delenv("SPL_FUSED")
+    rng = random.Random(321)
+    texts = [t for t in (random_text(rng, 80) for _ in range(3000)) if "᠎" not in t]
+    texts += ["a" * k for k in (4000, 4096, 4097, 8100, 8192, 8193, 8350, 20000)] + [" " * 9000, "x" * 8000 + " " + "y" * 300, "=" * 8400]
+    texts += ["".join(rng.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(rng.randint(100, 900))) + " " for _ in range(200)]
+    for name, t in toks_f.items():
+        o = c_oracle(name)
+        assert t.encode_batch(texts) == o.encode_batch(texts), name
+        assert t.launches_per_call() == 7
+    sp = "<|endoftext|>"
+    st = [x[:40] + sp + x[40:] for x in texts[:300]]
+    assert toks_f["cl100k_base"].encode_batch_with_special(st) == c_oracle("cl100k_base").encode_batch(st, with_special=True)
+    d, off = synth.cfg3(vocab_bytes("o200k_base"), 8000)
+    _check_packed(toks_f["o200k_base"], c_oracle("o200k_base"), d, off)
+    d, off = synth.cfg4(vocab_bytes("llama3"), 6, 1_000_000.0)
+    _check_packed(toks_f["llama3"], c_oracle("llama3"), d, off)
