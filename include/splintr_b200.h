@@ -137,6 +137,30 @@ int spl_decode_batch_device(spl_tokenizer* tok, int dev_index, const uint32_t* d
                             uint8_t* d_bytes_out, size_t bytes_capacity, uint64_t* d_out_offsets,
                             void* cuda_stream, uint64_t* n_bytes_out);
 
+/* ---- ingestion: JSON Lines -> packed text + offsets, on the device ------------------
+ * Not a reference function: it replaces the loop a splintr user runs in front of Tokenizer.encode_batch
+ * (python/splintr/__init__.py documents `encode_batch(texts)` over a list the user built),
+ *     texts = [json.loads(line)[field] for line in open(path) if line.strip()]
+ * and the packing of `texts`.  d_jsonl = the file's bytes on the device (16-byte aligned, readable up to n_bytes
+ * rounded up to 16).  Every non-blank line is one JSON object and yields one document: the unescaped string value of
+ * its LAST top-level member named `field` (1..64 bytes); a line without it, with a non-string there, or that does not
+ * parse yields an empty document and is counted in the stats.  Outputs (device memory of the caller): d_text_out
+ * (text_capacity >= n_bytes always suffices; 16-byte aligned and padded if it is to be fed to
+ * spl_encode_batch_device) and d_offsets_out (offsets_capacity entries; n_docs + 1 are written; the number of '\n'
+ * bytes + 2 always suffices).  Too small a capacity: SPL_ERR_INVALID_ARG with the needed sizes in *stats (either
+ * output pointer may be NULL to ask for the sizes only).  Synchronises the stream twice. */
+typedef struct spl_ingest_stats {
+    uint64_t n_lines;          /* '\n'-separated lines, blank ones included                 */
+    uint64_t n_docs;           /* non-blank lines = documents                                */
+    uint64_t n_text_bytes;     /* bytes of packed text                                       */
+    uint64_t n_missing;        /* documents left empty: member absent or not a string        */
+    uint64_t n_bad;            /* documents left empty: the line is not a JSON object        */
+    int n_launches;
+} spl_ingest_stats;
+int spl_ingest_jsonl_device(spl_tokenizer* tok, int dev_index, const uint8_t* d_jsonl, size_t n_bytes, const char* field,
+                            uint8_t* d_text_out, size_t text_capacity, uint64_t* d_offsets_out, size_t offsets_capacity,
+                            void* cuda_stream, spl_ingest_stats* stats);
+
 /* number of kernels one spl_encode_batch_device call launches for these flags */
 int spl_launches_per_call(const spl_tokenizer* tok, uint32_t flags);
 

@@ -13,8 +13,8 @@ from typing import List, Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libsplintr_b200.so")
-SOURCES = ["spl_api.cu", "spl_kernels.cu", "spl_encode.cu", "spl_decode.cu", "spl_sentencepiece.cu", "spl_host.cpp"]
-HEADERS = ["spl_common.h", "spl_pretok.h", "spl_pretok_fast.h", "spl_sentencepiece.h", "spl_host.h", "spl_kernels.cuh", "spl_device.cuh", "spl_fast_dev.cuh", "unicode_tables.inc",
+SOURCES = ["spl_api.cu", "spl_kernels.cu", "spl_encode.cu", "spl_decode.cu", "spl_sentencepiece.cu", "spl_ingest.cu", "spl_host.cpp"]
+HEADERS = ["spl_common.h", "spl_pretok.h", "spl_pretok_fast.h", "spl_sentencepiece.h", "spl_ingest.h", "spl_host.h", "spl_kernels.cuh", "spl_device.cuh", "spl_fast_dev.cuh", "unicode_tables.inc",
            os.path.join("..", "..", "include", "splintr_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -57,12 +57,18 @@ class SplStats(ctypes.Structure):
                 ("n_devices", ctypes.c_int), ("n_launches", ctypes.c_int)]
 
 
+class SplIngestStats(ctypes.Structure):
+    _fields_ = [("n_lines", ctypes.c_uint64), ("n_docs", ctypes.c_uint64), ("n_text_bytes", ctypes.c_uint64),
+                ("n_missing", ctypes.c_uint64), ("n_bad", ctypes.c_uint64), ("n_launches", ctypes.c_int)]
+
+
 # every symbol include/splintr_b200.h declares
 EXPORTS = ["spl_create", "spl_destroy", "spl_last_error", "spl_encode_batch", "spl_result_ids",
            "spl_result_offsets", "spl_result_n_docs", "spl_result_n_tokens", "spl_result_stats",
            "spl_result_free", "spl_encode_batch_device", "spl_launches_per_call", "spl_alloc_pinned",
            "spl_free_pinned", "spl_version", "spl_set_profiling", "spl_last_kernel_times",
-           "spl_decode_batch", "spl_decode_batch_device", "spl_result_bytes", "spl_result_n_bytes"]
+           "spl_decode_batch", "spl_decode_batch_device", "spl_result_bytes", "spl_result_n_bytes",
+           "spl_ingest_jsonl_device"]
 
 SPL_OK, SPL_ERR_INVALID_ARG, SPL_ERR_VOCAB, SPL_ERR_CUDA, SPL_ERR_OOM, SPL_ERR_UNSUPPORTED, SPL_ERR_NO_DEVICE = \
     0, -1, -2, -3, -4, -5, -6
@@ -119,6 +125,9 @@ def load() -> ctypes.CDLL:
     lib.spl_decode_batch_device.restype = ctypes.c_int
     lib.spl_decode_batch_device.argtypes = [vp, ctypes.c_int, u32p, ctypes.c_size_t, u64p, ctypes.c_size_t,
                                             u8p, ctypes.c_size_t, u64p, vp, ctypes.POINTER(ctypes.c_uint64)]
+    lib.spl_ingest_jsonl_device.restype = ctypes.c_int
+    lib.spl_ingest_jsonl_device.argtypes = [vp, ctypes.c_int, u8p, ctypes.c_size_t, ctypes.c_char_p, u8p, ctypes.c_size_t,
+                                            u64p, ctypes.c_size_t, vp, ctypes.POINTER(SplIngestStats)]
     lib.spl_launches_per_call.restype = ctypes.c_int
     lib.spl_launches_per_call.argtypes = [vp, ctypes.c_uint32]
     lib.spl_set_profiling.restype = ctypes.c_int

@@ -59,6 +59,7 @@ struct DevCtx {
     DevBuf text, doc_off, ids, out_off;          // spl_encode_batch: the shard's buffers
     DevBuf zero, tstate, pv, pool, mlist, fbl, huge, defer;
     DevBuf dec_ids, dec_off, dec_ws, dec_out, dec_out_off;       // spl_decode_batch   // per-pass workspace (zero: everything that starts cleared)
+    DevBuf jl_tiles, jl_lines;                                   // spl_ingest_jsonl_device: tile counts, per-line arrays
     DevBuf run_tot;                                              // spl_encode_batch: cumulative id count after each pipeline chunk
     DevBuf sp_zero, sp_tiles, sp_text, sp_doc;                   // SentencePiece mode: bitmaps over T, tile counts, T', offsets in T'
     size_t huge_words = 0;
@@ -154,7 +155,7 @@ int upload_tables(spl_tokenizer* tk, DevCtx& dc) {
 
 void destroy_ctx(DevCtx& dc) {
     cudaSetDevice(dc.device);
-    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.ids, &dc.out_off, &dc.dec_ids, &dc.dec_off, &dc.dec_ws, &dc.dec_out, &dc.dec_out_off, &dc.run_tot, &dc.sp_zero, &dc.sp_tiles, &dc.sp_text, &dc.sp_doc, &dc.zero, &dc.tstate, &dc.pv, &dc.pool, &dc.mlist, &dc.fbl, &dc.huge, &dc.defer})
+    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.ids, &dc.out_off, &dc.dec_ids, &dc.dec_off, &dc.dec_ws, &dc.dec_out, &dc.dec_out_off, &dc.jl_tiles, &dc.jl_lines, &dc.run_tot, &dc.sp_zero, &dc.sp_tiles, &dc.sp_text, &dc.sp_doc, &dc.zero, &dc.tstate, &dc.pv, &dc.pool, &dc.mlist, &dc.fbl, &dc.huge, &dc.defer})
         b->release();
     if (dc.table_blob) cudaFree(dc.table_blob);
     for (auto& e : dc.ev) if (e) cudaEventDestroy(e);
@@ -980,6 +981,62 @@ int spl_decode_batch(spl_tokenizer* tk, const uint32_t* ids, const uint64_t* off
     r->stats.h2d_bytes = n_tok * 4 + (n_docs + 1) * 8; r->stats.d2h_bytes = total + (n_docs + 1) * 8;
     r->stats.total_ms = ms; r->stats.n_devices = 1; r->stats.n_launches = 3;
     *out = r;
+    return SPL_OK;
+}
+
+// ---- ingestion (row N4): JSON Lines -> packed text + offsets ------------------------------------------------
+
+int spl_ingest_jsonl_device(spl_tokenizer* tk, int dev_index, const uint8_t* d_jsonl, size_t n_bytes, const char* field,
+                            uint8_t* d_text_out, size_t text_capacity, uint64_t* d_offsets_out, size_t offsets_capacity,
+                            void* cuda_stream, spl_ingest_stats* stats) {
+    if (!tk) return SPL_ERR_INVALID_ARG;
+    const size_t flen = field ? strlen(field) : 0;
+    if (dev_index < 0 || (size_t)dev_index >= tk->devs.size() || !stats || !field || flen == 0 || flen > 64 ||
+        (n_bytes && !d_jsonl) || ((uintptr_t)d_jsonl & 15u)) {
+        tk->err = "invalid argument (null pointer, member name of 0 or more than 64 bytes, or d_jsonl not 16-byte aligned)";
+        return SPL_ERR_INVALID_ARG;
+    }
+    if (n_bytes > kMaxShardBytes) { tk->err = "one device pass is limited to 4 GiB"; return SPL_ERR_UNSUPPORTED; }
+    memset(stats, 0, sizeof(*stats));
+    DeviceGuard guard;
+    DevCtx& dc = tk->devs[dev_index];
+    CUDA_TRY(cudaSetDevice(dc.device), tk->err);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    SplJlWork w;
+    memset(&w, 0, sizeof(w));
+    w.text = d_jsonl; w.N = (uint32_t)n_bytes; w.n_tiles = (uint32_t)(n_bytes / SPL_TILE) + 1;
+    memcpy(w.field, field, flen); w.flen = (uint32_t)flen;
+    int rc;
+    const size_t tiles_bytes = align_up(256 + (2 * (size_t)w.n_tiles + 2) * 4, 256);
+    if ((rc = dc.jl_tiles.ensure(tiles_bytes, tk->err))) return rc;
+    CUDA_TRY(cudaMemsetAsync(dc.jl_tiles.p, 0, 256, st), tk->err);
+    w.counters = (uint32_t*)dc.jl_tiles.p;
+    w.tile_cnt = w.counters + 64; w.tile_pref = w.tile_cnt + w.n_tiles;
+    spl_launch_jsonl_count(w, st);
+    uint32_t h_ctr[8];
+    CUDA_TRY(cudaMemcpyAsync(h_ctr, w.counters, sizeof(h_ctr), cudaMemcpyDeviceToHost, st), tk->err);
+    CUDA_TRY(cudaStreamSynchronize(st), tk->err);
+    const size_t n_lines = (size_t)h_ctr[SPL_JLCTR_NEWLINES] + 1;
+    w.n_lines = (uint32_t)n_lines;
+    // per-line arrays: line_start | doc_idx | text_off (n_lines + 1 each) | is_doc | out_len (n_lines each) | span
+    const size_t a1 = align_up((n_lines + 1) * 4, 16), a0 = align_up(n_lines * 4, 16);
+    if ((rc = dc.jl_lines.ensure(3 * a1 + 2 * a0 + n_lines * 16 + 64, tk->err))) return rc;
+    uint8_t* lb = (uint8_t*)dc.jl_lines.p;
+    w.line_start = (uint32_t*)lb; w.doc_idx = (uint32_t*)(lb + a1); w.text_off = (uint32_t*)(lb + 2 * a1);
+    w.is_doc = (uint32_t*)(lb + 3 * a1); w.out_len = (uint32_t*)(lb + 3 * a1 + a0);
+    w.span = (SplJlSpan*)(lb + 3 * a1 + 2 * a0);
+    w.out_text = d_text_out; w.text_capacity = d_text_out ? text_capacity : 0;
+    w.out_off = d_offsets_out; w.off_capacity = d_offsets_out ? offsets_capacity : 0;
+    spl_launch_jsonl_extract(w, st);
+    CUDA_TRY(cudaGetLastError(), tk->err);
+    CUDA_TRY(cudaMemcpyAsync(h_ctr, w.counters, sizeof(h_ctr), cudaMemcpyDeviceToHost, st), tk->err);
+    CUDA_TRY(cudaStreamSynchronize(st), tk->err);
+    stats->n_lines = n_lines; stats->n_docs = h_ctr[SPL_JLCTR_DOCS]; stats->n_text_bytes = h_ctr[SPL_JLCTR_TEXT];
+    stats->n_missing = h_ctr[SPL_JLCTR_MISSING]; stats->n_bad = h_ctr[SPL_JLCTR_BAD]; stats->n_launches = 6;
+    if (stats->n_docs + 1 > w.off_capacity || stats->n_text_bytes > w.text_capacity) {
+        tk->err = "output capacity too small (needed sizes returned in the stats: n_docs + 1 offsets, n_text_bytes bytes)";
+        return SPL_ERR_INVALID_ARG;
+    }
     return SPL_OK;
 }
 

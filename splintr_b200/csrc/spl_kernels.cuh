@@ -129,6 +129,26 @@ int spl_launch_sp_emit(const SplSpWork& s, cudaStream_t stream);
 // k_mark_docs (+ k_mark_specials) only: the segment bitmaps of a text (SentencePiece mode runs them over T)
 int spl_launch_mark(const SplWork& w, int num_sms, cudaStream_t stream);
 
+// spl_ingest.cu: JSON Lines -> packed text + offsets (row N4; contract in spl_ingest.h)
+enum : uint32_t { SPL_JLCTR_NEWLINES = 0, SPL_JLCTR_DOCS = 1, SPL_JLCTR_MISSING = 2, SPL_JLCTR_BAD = 3, SPL_JLCTR_TEXT = 4 };
+struct SplJlSpan;
+struct SplJlWork {
+    const uint8_t* text; uint32_t N;              // file bytes, 16-byte aligned, readable up to N rounded up to 16
+    uint32_t n_tiles;                             // N / SPL_TILE + 1
+    uint32_t* tile_cnt; uint32_t* tile_pref;      // newlines per tile, exclusive prefix [n_tiles + 1]
+    uint32_t n_lines;                             // newlines + 1 (known after spl_launch_jsonl_count)
+    uint32_t* line_start;                         // [n_lines + 1]
+    SplJlSpan* span;                              // [n_lines]
+    uint32_t *is_doc, *out_len;                   // [n_lines]
+    uint32_t *doc_idx, *text_off;                 // [n_lines + 1] exclusive prefixes
+    uint32_t* counters;                           // SPL_JLCTR_* (zero-initialised)
+    uint8_t field[64]; uint32_t flen;
+    uint8_t* out_text; uint64_t text_capacity;
+    uint64_t* out_off; uint64_t off_capacity;     // entries
+};
+int spl_launch_jsonl_count(const SplJlWork& w, cudaStream_t stream);     // k_jl_count, k_jl_scan
+int spl_launch_jsonl_extract(const SplJlWork& w, cudaStream_t stream);   // k_jl_lines, k_jl_parse, k_jl_scan2, k_jl_emit
+
 // spl_decode.cu: ids -> bytes (row N2)
 #define SPL_DEC_TILE 2048u            // ids per tile
 struct SplDecLaunch {

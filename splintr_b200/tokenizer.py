@@ -285,6 +285,49 @@ class Tokenizer:
             raise RuntimeError(f"splintr_b200: {msg} (code {rc})")
         return ids_out, out_offsets, (int(n_tok.value) if sync else None)
 
+    # -- ingestion: JSON Lines -> packed text + offsets on the device ---------------
+    def ingest_jsonl_device(self, d_jsonl, field: str = "text", dev_index: int = 0):
+        """spl_ingest_jsonl_device: `d_jsonl` = the bytes of a JSON Lines file as a CUDA uint8 tensor (16-byte aligned
+        storage, padded to a multiple of 16).  Returns (text uint8[n_text_bytes] -- a view of a 16-byte padded buffer,
+        ready for encode_device --, offsets int64[n_docs + 1], stats dict).  One document per non-blank line: the
+        string value of its last top-level member `field`; see include/splintr_b200.h for the full contract."""
+        import torch
+        lib = _lib.load()
+        if d_jsonl.dtype != torch.uint8 or not d_jsonl.is_cuda:
+            raise TypeError("d_jsonl must be a CUDA uint8 tensor")
+        n = int(d_jsonl.numel())
+        n_lines_max = int((d_jsonl == 10).sum().item()) + 2 if n else 2
+        text = torch.empty(n + ((-n) % 16) + 16, dtype=torch.uint8, device=d_jsonl.device)
+        offs = torch.empty(n_lines_max, dtype=torch.int64, device=d_jsonl.device)
+        st = _lib.SplIngestStats()
+        stream = torch.cuda.current_stream(d_jsonl.device).cuda_stream
+        rc = lib.spl_ingest_jsonl_device(self._handle, dev_index, ctypes.c_void_p(d_jsonl.data_ptr()), n, field.encode("utf-8"),
+                                         ctypes.c_void_p(text.data_ptr()), n, ctypes.c_void_p(offs.data_ptr()), n_lines_max,
+                                         ctypes.c_void_p(stream), ctypes.byref(st))
+        if rc != _lib.SPL_OK:
+            msg = _lib.last_error(self._handle)
+            if rc in (_lib.SPL_ERR_INVALID_ARG, _lib.SPL_ERR_UNSUPPORTED):
+                raise ValueError(msg)
+            raise RuntimeError(f"splintr_b200: {msg} (code {rc})")
+        stats = {f: getattr(st, f) for f, _ in _lib.SplIngestStats._fields_}
+        return text[:int(st.n_text_bytes)], offs[:int(st.n_docs) + 1], stats
+
+    def encode_jsonl(self, data, field: str = "text", with_special: bool = False, return_stats: bool = False):
+        """File bytes of a JSON Lines dataset (bytes / bytearray / numpy uint8) -> (ids uint32, offsets uint64): one
+        host-to-device copy of the raw file, member extraction + unescaping, encode and the copy of the ids back --
+        the `[json.loads(l)[field] for l in f]` loop and the packing of its result never run on the host."""
+        import torch
+        raw = np.frombuffer(bytes(data), dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data, dtype=np.uint8)
+        n = int(raw.shape[0])
+        dev = torch.device("cuda", self._devices[0] if self._devices else torch.cuda.current_device())
+        buf = torch.zeros(n + ((-n) % 16) + 16, dtype=torch.uint8, device=dev)
+        if n:
+            buf[:n].copy_(torch.from_numpy(raw))
+        text, offs, stats = self.ingest_jsonl_device(buf[:n], field)
+        ids, out_off, n_tok = self.encode_device(text, offs, with_special=with_special)
+        res = (ids[:n_tok].cpu().numpy().astype(np.uint32), out_off.cpu().numpy().astype(np.uint64))
+        return res + (stats,) if return_stats else res
+
     def set_profiling(self, enable: bool = True) -> None:
         _lib.load().spl_set_profiling(self._handle, int(enable))
 

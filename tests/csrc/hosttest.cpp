@@ -342,3 +342,33 @@ extern "C" long ht_encode_sp(void* h, const uint8_t* text, uint32_t n, uint32_t*
     memcpy(ids, out.data(), out.size() * 4);
     return (long)out.size();
 }
+
+// ---------------------------------------------------------------------------------------
+// JSON Lines ingestion (row N4): the per-line parser of spl_ingest.h over a whole buffer, line by line, as the
+// device kernels apply it.  out_text needs n bytes, out_off n + 2 entries.  counts = {docs, text bytes, missing, bad}.
+#include "../../splintr_b200/csrc/spl_ingest.h"
+extern "C" int ht_jsonl(const uint8_t* text, uint32_t n, const char* field, uint8_t* out_text, uint64_t* out_off, uint64_t* counts) {
+    HostText t{text};
+    uint32_t flen = (uint32_t)strlen(field);
+    uint64_t docs = 0, bytes = 0, missing = 0, bad = 0;
+    uint32_t s = 0;
+    for (;;) {
+        uint32_t e = s;
+        while (e < n && text[e] != '\n') ++e;
+        SplJlSpan sp = spl_jl_parse_line(t, s, e, (const uint8_t*)field, flen);
+        if (sp.flags & SPL_JL_DOC) {
+            out_off[docs++] = bytes;
+            if (sp.flags & SPL_JL_FOUND) {
+                uint32_t j = sp.vs, len = 0;
+                while (j < sp.ve) { uint8_t ch[4]; uint32_t k; j = spl_jl_char(t, j, sp.ve, ch, k); for (uint32_t q = 0; q < k; ++q) out_text[bytes + len + q] = ch[q]; len += k; }
+                if (len != sp.out_len) return -1;
+                bytes += len;
+            } else if (sp.flags & SPL_JL_BAD) ++bad; else ++missing;
+        }
+        if (e >= n) break;
+        s = e + 1;
+    }
+    out_off[docs] = bytes;
+    counts[0] = docs; counts[1] = bytes; counts[2] = missing; counts[3] = bad;
+    return 0;
+}

@@ -9,7 +9,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = [os.path.join(ROOT, "tests", "csrc", "hosttest.cpp"), os.path.join(ROOT, "splintr_b200", "csrc", "spl_host.cpp")]
-DEPS = SRC + [os.path.join(ROOT, "splintr_b200", "csrc", f) for f in ("spl_pretok.h", "spl_pretok_fast.h", "spl_sentencepiece.h", "spl_common.h", "spl_host.h", "unicode_tables.inc")]
+DEPS = SRC + [os.path.join(ROOT, "splintr_b200", "csrc", f) for f in ("spl_pretok.h", "spl_pretok_fast.h", "spl_sentencepiece.h", "spl_ingest.h", "spl_common.h", "spl_host.h", "unicode_tables.inc")]
 LIB = os.path.join(ROOT, "tests", "csrc", "libhosttest.so")
 _lib = None
 
@@ -38,12 +38,29 @@ def load():
     lib.ht_stats.argtypes = [vp, vp]
     lib.ht_encode.restype = ctypes.c_long
     lib.ht_encode.argtypes = [vp, ctypes.c_char_p, ctypes.c_uint32, vp, ctypes.c_size_t]
+    lib.ht_jsonl.restype = ctypes.c_int
+    lib.ht_jsonl.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, vp, vp, vp]
+    lib.ht_set_fast_ext.argtypes = [ctypes.c_int]
     lib.ht_sp_transform.restype = ctypes.c_long
     lib.ht_sp_transform.argtypes = [ctypes.c_char_p, ctypes.c_uint32, vp, vp, vp, vp, vp]
     lib.ht_encode_sp.restype = ctypes.c_long
     lib.ht_encode_sp.argtypes = [vp, ctypes.c_char_p, ctypes.c_uint32, vp, ctypes.c_size_t]
     _lib = lib
     return lib
+
+
+def jsonl(data: bytes, field: str = "text"):
+    """spl_ingest.h line parser over a whole JSON Lines buffer -> (list of document bytes, missing, bad)."""
+    n = len(data)
+    out = np.zeros(n + 16, dtype=np.uint8)
+    off = np.zeros(n + 2, dtype=np.uint64)
+    cnt = np.zeros(4, dtype=np.uint64)
+    rc = load().ht_jsonl(data, n, field.encode(), out.ctypes.data, off.ctypes.data, cnt.ctypes.data)
+    assert rc == 0, rc
+    nd = int(cnt[0])
+    raw = out[:int(cnt[1])].tobytes()
+    o = off[:nd + 1].tolist()
+    return [raw[o[i]:o[i + 1]] for i in range(nd)], int(cnt[2]), int(cnt[3])
 
 
 def sp_transform(data: bytes, hard=None, spec=None):

@@ -435,3 +435,56 @@ def test_fused_front_end_is_bit_exact(monkeypatch):
     _check_packed(toks_f["o200k_base"], c_oracle("o200k_base"), d, off)
     d, off = synth.cfg4(vocab_bytes("llama3"), 6, 1_000_000.0)
     _check_packed(toks_f["llama3"], c_oracle("llama3"), d, off)
+
+
+# ---- JSON Lines ingestion on the device ---------------------------------------------
+def test_ingest_jsonl_matches_json_module(toks):
+    """spl_ingest_jsonl_device against Python's json module: documents = [json.loads(l)["text"] for non-blank l]
+    (missing / non-string members -> empty documents), then encode_jsonl == encode_batch of those documents."""
+    import json
+    import torch
+    from jsonl_cases import make_lines, join_lines
+    tok = toks("cl100k_base")
+    for seed, n, final_nl in ((1, 400, True), (2, 3000, False), (3, 1, True), (4, 20000, True)):
+        lines, want = make_lines(seed, n)
+        data = join_lines(lines, final_nl)
+        buf = torch.zeros(len(data) + ((-len(data)) % 16) + 16, dtype=torch.uint8, device="cuda")
+        buf[:len(data)].copy_(torch.frombuffer(bytearray(data), dtype=torch.uint8))
+        text, offs, st = tok.ingest_jsonl_device(buf[:len(data)])
+        raw = text.cpu().numpy().tobytes()
+        o = offs.cpu().tolist()
+        assert st["n_docs"] == len(want) and st["n_bad"] == 0
+        assert [raw[o[i]:o[i + 1]].decode("utf-8") for i in range(len(want))] == want, seed
+        assert st["n_missing"] == sum(1 for l in lines if l.strip(" \t\r") and not isinstance(json.loads(l).get("text"), str))
+        ids, ioff = tok.encode_jsonl(data)
+        exp = tok.encode_batch(want)
+        flat = ids.tolist()
+        io = ioff.tolist()
+        assert [flat[io[i]:io[i + 1]] for i in range(len(want))] == exp
+    # empty input, blank-only input, another member name, capacity query
+    assert tok.encode_jsonl(b"")[1].tolist() == [0]
+    assert tok.encode_jsonl(b"\n \n\t\n")[1].tolist() == [0]
+    ids, ioff = tok.encode_jsonl(b'{"body":"Hello world","text":"no"}\n', field="body")
+    assert ids.tolist() == [9906, 1917]
+    with pytest.raises(ValueError):
+        tok.ingest_jsonl_device(torch.zeros(16, dtype=torch.uint8, device="cuda")[:3], field="")
+
+
+def test_ingest_jsonl_cfg2_roundtrip(toks):
+    """cfg2 (100 000 documents) written as JSON Lines with json.dumps and ingested on the device reproduces the packed
+    batch byte for byte, and its ids equal the ids of the packed batch."""
+    import json
+    import torch
+    tok = toks("cl100k_base")
+    d, o = synth.cfg2(vocab_bytes("cl100k_base"), 100_000)
+    texts = synth.unpack_texts(d, o)
+    data = ("\n".join(json.dumps({"id": i, "text": t, "meta": {"text": "x"}}) for i, t in enumerate(texts)) + "\n").encode()
+    n = len(data)
+    buf = torch.zeros(n + ((-n) % 16) + 16, dtype=torch.uint8, device="cuda")
+    buf[:n].copy_(torch.frombuffer(bytearray(data), dtype=torch.uint8))
+    text, offs, st = tok.ingest_jsonl_device(buf[:n])
+    assert st["n_docs"] == 100_000 and st["n_missing"] == 0 and st["n_bad"] == 0
+    assert np.array_equal(text.cpu().numpy(), d) and np.array_equal(offs.cpu().numpy().astype(np.uint64), o)
+    ids, ioff = tok.encode_jsonl(data)
+    want_ids, want_off = tok.encode_packed(d, o)
+    assert np.array_equal(ids, want_ids) and np.array_equal(ioff, want_off)
