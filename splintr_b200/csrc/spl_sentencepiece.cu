@@ -30,20 +30,45 @@ __global__ void __launch_bounds__(256) k_sp_classify(SplSpWork s) {
     const SplTables* T = s.T;
     const GText t{s.text};
     const uint32_t hw = __ldg(s.hard + gw), sw = s.spec ? __ldg(s.spec + gw) : 0u;
-    bool prev_w0 = false;
-    if (base > 0 && !(s.spec && bit_at(s.spec, base - 1))) prev_w0 = spl_sp_ws_byte(t, base - 1, s.N, T->ucd_stage1, T->ucd_stage2);
-    uint32_t w0 = 0, rs = 0;
     const uint32_t n = s.N - base < 32u ? s.N - base : 32u;
-    for (uint32_t k = 0; k < n; ++k) {
-        const uint32_t i = base + k, b = t.byte(i);
-        const bool sp = (sw >> k) & 1u;
-        const bool ws = !sp && spl_sp_ws_byte(t, i, s.N, T->ucd_stage1, T->ucd_stage2);
-        if (ws) {
-            w0 |= 1u << k;
-            const bool char_start = (b & 0xC0u) != 0x80u;
-            if (char_start && (((hw >> k) & 1u) || i == 0 || !prev_w0) && !spl_sp_ascii_ws(b)) rs |= 1u << k;
+    uint32_t x[8];
+    {
+        const uint32_t Nup = (s.N + 15u) & ~15u;
+        const uint4* p4 = reinterpret_cast<const uint4*>(s.text + base);
+        const uint4 a = __ldg(p4), b = (base + 16u < Nup) ? __ldg(p4 + 1) : make_uint4(0, 0, 0, 0);
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    }
+    const uint32_t pb = base ? t.byte(base - 1) : 0u;                          // the byte in front of the word
+    const uint32_t any_hi = (x[0] | x[1] | x[2] | x[3] | x[4] | x[5] | x[6] | x[7] | pb) & 0x80808080u;
+    uint32_t w0 = 0, rs = 0;
+    if (!any_hi) {
+        // ASCII only (the usual word): whitespace = 09..0D, 20; of those only 0B is not u8::is_ascii_whitespace
+        bool prev_w0 = base && !(s.spec && bit_at(s.spec, base - 1)) && (pb == 0x20u || pb - 9u <= 4u);
+        const uint8_t* xb = reinterpret_cast<const uint8_t*>(x);
+#pragma unroll 8
+        for (uint32_t k = 0; k < 32u; ++k) {
+            const uint32_t b = xb[k];
+            const bool ws = k < n && !((sw >> k) & 1u) && (b == 0x20u || b - 9u <= 4u);
+            if (ws) {
+                w0 |= 1u << k;
+                if (b == 0x0Bu && (((hw >> k) & 1u) || base + k == 0 || !prev_w0)) rs |= 1u << k;
+            }
+            prev_w0 = ws;
         }
-        prev_w0 = ws;
+    } else {
+        bool prev_w0 = false;
+        if (base > 0 && !(s.spec && bit_at(s.spec, base - 1))) prev_w0 = spl_sp_ws_byte(t, base - 1, s.N, T->ucd_stage1, T->ucd_stage2);
+        for (uint32_t k = 0; k < n; ++k) {
+            const uint32_t i = base + k, b = t.byte(i);
+            const bool sp = (sw >> k) & 1u;
+            const bool ws = !sp && spl_sp_ws_byte(t, i, s.N, T->ucd_stage1, T->ucd_stage2);
+            if (ws) {
+                w0 |= 1u << k;
+                const bool char_start = (b & 0xC0u) != 0x80u;
+                if (char_start && (((hw >> k) & 1u) || i == 0 || !prev_w0) && !spl_sp_ascii_ws(b)) rs |= 1u << k;
+            }
+            prev_w0 = ws;
+        }
     }
     s.w0[gw] = w0; s.a[gw] = w0; s.rs[gw] = rs;
 }
@@ -129,8 +154,18 @@ __global__ void __launch_bounds__(1024) k_sp_scan(SplSpWork s) {
     if (tid == 0) { s.tile_pref[s.n_tiles] = carry; s.counters[SPL_SPCTR_CONV] = carry; }
 }
 
+// bytes and bits of a tile's image in T' are staged in shared memory and leave as coalesced stores: the image of tile t
+// is the contiguous range [tile0 + 2 * before, ... + SPL_TILE + 2 * conv(t)) and no other tile writes into it
+#define SP_OUT_MAX (3u * SPL_TILE)
+#define SP_BM_WORDS (SP_OUT_MAX / 32u + 2u)
+struct SpEmitSmem {
+    uint8_t out[SP_OUT_MAX];
+    uint32_t ps[SP_BM_WORDS], sp[SP_BM_WORDS];       // bit r <-> output position (obase_tile & ~31) + r
+    uint32_t excl[SP_TW], conv[SP_TW], wsum[SP_TW / 32];
+};
+
 __global__ void __launch_bounds__(SP_TW) k_sp_emit(SplSpWork s) {
-    __shared__ uint32_t s_excl[SP_TW], s_conv[SP_TW], wsum[SP_TW / 32];
+    __shared__ SpEmitSmem sm;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t tile = blockIdx.x, tile0 = tile * SPL_TILE, gw = tile * SP_TW + tid, base = gw * 32u;
     uint32_t x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -142,47 +177,61 @@ __global__ void __launch_bounds__(SP_TW) k_sp_emit(SplSpWork s) {
         if (s.spec) sw = __ldg(s.spec + gw);
         conv = a & eq20_mask(x) & valid;
     }
+    for (uint32_t v = tid; v < SP_BM_WORDS; v += SP_TW) { sm.ps[v] = 0; sm.sp[v] = 0; }
     // exclusive count of converted spaces in front of my word, inside the tile
     const uint32_t c = __popc(conv);
     uint32_t incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += u; }
-    if (lane == 31) wsum[warp] = incl;
+    if (lane == 31) sm.wsum[warp] = incl;
     __syncthreads();
-    uint32_t excl = incl - c;
-    for (uint32_t q = 0; q < warp; ++q) excl += wsum[q];
-    s_excl[tid] = excl; s_conv[tid] = conv;
+    uint32_t excl = incl - c, tile_conv = 0;
+    for (uint32_t q = 0; q < SP_TW / 32; ++q) { const uint32_t t = sm.wsum[q]; excl += q < warp ? t : 0u; tile_conv += t; }
+    sm.excl[tid] = excl; sm.conv[tid] = conv;
     const uint32_t before = s.tile_pref[tile];
+    const uint32_t obase_tile = tile0 + 2u * before;                    // first output position of the tile
+    const uint32_t bit0 = obase_tile & ~31u;
+    const uint32_t tile_in = s.N > tile0 ? (s.N - tile0 < SPL_TILE ? s.N - tile0 : SPL_TILE) : 0u;
+    const uint32_t tile_out = tile_in + 2u * tile_conv;
     if (base < s.N) {
-        // left neighbour of my first byte
         bool w0_prev = false, a_prev = false;
         uint32_t b_prev = 0;
         if (base > 0) {
             w0_prev = (s.w0[gw - 1] >> 31) & 1u; a_prev = (s.a[gw - 1] >> 31) & 1u;
             b_prev = __ldg(s.text + base - 1);
         }
-        const uint32_t obase = base + 2u * (before + excl);
+        uint32_t lo = tid * 32u + 2u * excl;                            // tile-relative output position of my first byte
         const uint8_t* xb = reinterpret_cast<const uint8_t*>(x);
         const uint32_t n = s.N - base < 32u ? s.N - base : 32u;
         for (uint32_t k = 0; k < n; ++k) {
             SplSpPos p;
             p.w0 = (w0 >> k) & 1u; p.a = (a >> k) & 1u; p.rs = (rs >> k) & 1u; p.s = (hw >> k) & 1u; p.b = xb[k];
             p.w0_prev = w0_prev; p.a_prev = a_prev; p.b_prev = b_prev;
-            const uint32_t o = obase + k + 2u * __popc(conv & ((1u << k) - 1u));
-            if ((conv >> k) & 1u) { s.text2[o] = 0xE2u; s.text2[o + 1] = 0x96u; s.text2[o + 2] = 0x81u; }
-            else s.text2[o] = (uint8_t)p.b;
-            if (spl_sp_piece_start(p)) atomicOr(&s.pstart2[o >> 5], 1u << (o & 31));
-            if ((sw >> k) & 1u) atomicOr(&s.spec2[o >> 5], 1u << (o & 31));
+            const uint32_t r = obase_tile + lo - bit0;                  // bit index in the staged bitmaps
+            if (spl_sp_piece_start(p)) atomicOr(&sm.ps[r >> 5], 1u << (r & 31));
+            if ((sw >> k) & 1u) atomicOr(&sm.sp[r >> 5], 1u << (r & 31));
+            if ((conv >> k) & 1u) { sm.out[lo] = 0xE2u; sm.out[lo + 1] = 0x96u; sm.out[lo + 2] = 0x81u; lo += 3; }
+            else sm.out[lo++] = (uint8_t)p.b;
             w0_prev = p.w0; a_prev = p.a; b_prev = p.b;
         }
     }
     __syncthreads();
+    // bytes: consecutive threads store consecutive bytes
+    uint8_t* __restrict__ dst = s.text2 + obase_tile;
+    for (uint32_t i = tid; i < tile_out; i += SP_TW) dst[i] = sm.out[i];
+    // bits: the first and the last word of the range can be shared with the neighbouring tiles
+    const uint32_t nbw = tile_out ? ((obase_tile + tile_out - 1u) >> 5) - (bit0 >> 5) + 1u : 0u;
+    for (uint32_t v = tid; v < nbw; v += SP_TW) {
+        const uint32_t pv = sm.ps[v], sv = sm.sp[v];
+        if (pv) atomicOr(&s.pstart2[(bit0 >> 5) + v], pv);
+        if (sv) atomicOr(&s.spec2[(bit0 >> 5) + v], sv);
+    }
     // document starts of this tile -> positions in T'
     const uint32_t d0 = s.tinfo[tile].first_doc, d1 = s.tinfo[tile + 1].first_doc;
     for (uint32_t d = d0 + tid; d < d1 && d <= s.n_docs; d += SP_TW) {
         const uint32_t xo = (uint32_t)(s.doc_off[d] - s.off_base) - tile0;
         const uint32_t wq = xo >> 5;
-        const uint32_t cnt = before + s_excl[wq] + __popc(s_conv[wq] & ((1u << (xo & 31)) - 1u));
+        const uint32_t cnt = before + sm.excl[wq] + __popc(sm.conv[wq] & ((1u << (xo & 31)) - 1u));
         s.doc_off2[d] = (uint64_t)tile0 + xo + 2ull * cnt;
     }
 }
