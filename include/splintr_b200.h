@@ -161,6 +161,13 @@ int spl_ingest_jsonl_device(spl_tokenizer* tok, int dev_index, const uint8_t* d_
                             uint8_t* d_text_out, size_t text_capacity, uint64_t* d_offsets_out, size_t offsets_capacity,
                             void* cuda_stream, spl_ingest_stats* stats);
 
+/* spl_encode_batch for a JSON Lines file held in host memory (pinned memory makes the copies asynchronous): the
+ * file is cut into chunks at line ends; each chunk is copied in as it is, ingested and encoded on the handle's first
+ * device, and its ids are copied out while the next chunk is worked on.  The result is the same object
+ * spl_encode_batch returns (one document per non-blank line); `ingest_stats` (optional) receives the totals. */
+int spl_encode_jsonl(spl_tokenizer* tok, const uint8_t* bytes, size_t n_bytes, const char* field, uint32_t flags,
+                     spl_result** out, spl_ingest_stats* ingest_stats);
+
 /* number of kernels one spl_encode_batch_device call launches for these flags */
 int spl_launches_per_call(const spl_tokenizer* tok, uint32_t flags);
 

@@ -68,7 +68,7 @@ EXPORTS = ["spl_create", "spl_destroy", "spl_last_error", "spl_encode_batch", "s
            "spl_result_free", "spl_encode_batch_device", "spl_launches_per_call", "spl_alloc_pinned",
            "spl_free_pinned", "spl_version", "spl_set_profiling", "spl_last_kernel_times",
            "spl_decode_batch", "spl_decode_batch_device", "spl_result_bytes", "spl_result_n_bytes",
-           "spl_ingest_jsonl_device"]
+           "spl_ingest_jsonl_device", "spl_encode_jsonl"]
 
 SPL_OK, SPL_ERR_INVALID_ARG, SPL_ERR_VOCAB, SPL_ERR_CUDA, SPL_ERR_OOM, SPL_ERR_UNSUPPORTED, SPL_ERR_NO_DEVICE = \
     0, -1, -2, -3, -4, -5, -6
@@ -128,6 +128,9 @@ def load() -> ctypes.CDLL:
     lib.spl_ingest_jsonl_device.restype = ctypes.c_int
     lib.spl_ingest_jsonl_device.argtypes = [vp, ctypes.c_int, u8p, ctypes.c_size_t, ctypes.c_char_p, u8p, ctypes.c_size_t,
                                             u64p, ctypes.c_size_t, vp, ctypes.POINTER(SplIngestStats)]
+    lib.spl_encode_jsonl.restype = ctypes.c_int
+    lib.spl_encode_jsonl.argtypes = [vp, u8p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_uint32, ctypes.POINTER(vp),
+                                     ctypes.POINTER(SplIngestStats)]
     lib.spl_launches_per_call.restype = ctypes.c_int
     lib.spl_launches_per_call.argtypes = [vp, ctypes.c_uint32]
     lib.spl_set_profiling.restype = ctypes.c_int

@@ -60,6 +60,7 @@ struct DevCtx {
     DevBuf zero, tstate, pv, pool, mlist, fbl, huge, defer;
     DevBuf dec_ids, dec_off, dec_ws, dec_out, dec_out_off;       // spl_decode_batch   // per-pass workspace (zero: everything that starts cleared)
     DevBuf jl_tiles, jl_lines;                                   // spl_ingest_jsonl_device: tile counts, per-line arrays
+    DevBuf jl_text, jl_off, jl_out_off[2];                       // spl_encode_jsonl: ingested text + offsets, output offsets (alternating)
     DevBuf run_tot;                                              // spl_encode_batch: cumulative id count after each pipeline chunk
     DevBuf sp_zero, sp_tiles, sp_text, sp_doc;                   // SentencePiece mode: bitmaps over T, tile counts, T', offsets in T'
     size_t huge_words = 0;
@@ -155,7 +156,7 @@ int upload_tables(spl_tokenizer* tk, DevCtx& dc) {
 
 void destroy_ctx(DevCtx& dc) {
     cudaSetDevice(dc.device);
-    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.ids, &dc.out_off, &dc.dec_ids, &dc.dec_off, &dc.dec_ws, &dc.dec_out, &dc.dec_out_off, &dc.jl_tiles, &dc.jl_lines, &dc.run_tot, &dc.sp_zero, &dc.sp_tiles, &dc.sp_text, &dc.sp_doc, &dc.zero, &dc.tstate, &dc.pv, &dc.pool, &dc.mlist, &dc.fbl, &dc.huge, &dc.defer})
+    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.ids, &dc.out_off, &dc.dec_ids, &dc.dec_off, &dc.dec_ws, &dc.dec_out, &dc.dec_out_off, &dc.jl_tiles, &dc.jl_lines, &dc.jl_text, &dc.jl_off, &dc.jl_out_off[0], &dc.jl_out_off[1], &dc.run_tot, &dc.sp_zero, &dc.sp_tiles, &dc.sp_text, &dc.sp_doc, &dc.zero, &dc.tstate, &dc.pv, &dc.pool, &dc.mlist, &dc.fbl, &dc.huge, &dc.defer})
         b->release();
     if (dc.table_blob) cudaFree(dc.table_blob);
     for (auto& e : dc.ev) if (e) cudaEventDestroy(e);
@@ -344,6 +345,55 @@ int enqueue_encode(spl_tokenizer* tk, DevCtx& dc, cudaStream_t st, const EncodeA
     s.text2 = (uint8_t*)dc.sp_text.p; s.pstart2 = w.pstart; s.spec2 = w.spec; s.doc_off2 = (uint64_t*)dc.sp_doc.p;
     launches += spl_launch_sp_emit(s, st);
     launches += spl_launch_encode(w, dc.num_sms, st, prof);
+    return SPL_OK;
+}
+
+struct JlOut { uint8_t* text; size_t text_cap; uint64_t* off; size_t off_cap; };
+
+// JSON Lines -> packed text + offsets for one device pass on `st` (two synchronisations).  `outputs(n_lines, o)` is
+// called once the line count is known and names the buffers.
+template <class OutFn>
+int ingest_jsonl_core(spl_tokenizer* tk, DevCtx& dc, cudaStream_t st, const uint8_t* d_jsonl, size_t n_bytes,
+                      const char* field, size_t flen, OutFn outputs, spl_ingest_stats* stats) {
+    if (n_bytes > kMaxShardBytes) { tk->err = "one device pass is limited to 4 GiB"; return SPL_ERR_UNSUPPORTED; }
+    memset(stats, 0, sizeof(*stats));
+    SplJlWork w;
+    memset(&w, 0, sizeof(w));
+    w.text = d_jsonl; w.N = (uint32_t)n_bytes; w.n_tiles = (uint32_t)(n_bytes / SPL_TILE) + 1;
+    memcpy(w.field, field, flen); w.flen = (uint32_t)flen;
+    int rc;
+    const size_t tiles_bytes = align_up(256 + (2 * (size_t)w.n_tiles + 2) * 4, 256);
+    if ((rc = dc.jl_tiles.ensure(tiles_bytes, tk->err))) return rc;
+    CUDA_TRY(cudaMemsetAsync(dc.jl_tiles.p, 0, 256, st), tk->err);
+    w.counters = (uint32_t*)dc.jl_tiles.p;
+    w.tile_cnt = w.counters + 64; w.tile_pref = w.tile_cnt + w.n_tiles;
+    spl_launch_jsonl_count(w, st);
+    uint32_t h_ctr[8];
+    CUDA_TRY(cudaMemcpyAsync(h_ctr, w.counters, sizeof(h_ctr), cudaMemcpyDeviceToHost, st), tk->err);
+    CUDA_TRY(cudaStreamSynchronize(st), tk->err);
+    const size_t n_lines = (size_t)h_ctr[SPL_JLCTR_NEWLINES] + 1;
+    w.n_lines = (uint32_t)n_lines;
+    // per-line arrays: line_start | doc_idx | text_off (n_lines + 1 each) | is_doc | out_len (n_lines each) | span
+    const size_t a1 = align_up((n_lines + 1) * 4, 16), a0 = align_up(n_lines * 4, 16);
+    if ((rc = dc.jl_lines.ensure(3 * a1 + 2 * a0 + n_lines * 16 + 64, tk->err))) return rc;
+    uint8_t* lb = (uint8_t*)dc.jl_lines.p;
+    w.line_start = (uint32_t*)lb; w.doc_idx = (uint32_t*)(lb + a1); w.text_off = (uint32_t*)(lb + 2 * a1);
+    w.is_doc = (uint32_t*)(lb + 3 * a1); w.out_len = (uint32_t*)(lb + 3 * a1 + a0);
+    w.span = (SplJlSpan*)(lb + 3 * a1 + 2 * a0);
+    JlOut o{nullptr, 0, nullptr, 0};
+    if ((rc = outputs(n_lines, o))) return rc;
+    w.out_text = o.text; w.text_capacity = o.text ? o.text_cap : 0;
+    w.out_off = o.off; w.off_capacity = o.off ? o.off_cap : 0;
+    spl_launch_jsonl_extract(w, st);
+    CUDA_TRY(cudaGetLastError(), tk->err);
+    CUDA_TRY(cudaMemcpyAsync(h_ctr, w.counters, sizeof(h_ctr), cudaMemcpyDeviceToHost, st), tk->err);
+    CUDA_TRY(cudaStreamSynchronize(st), tk->err);
+    stats->n_lines = n_lines; stats->n_docs = h_ctr[SPL_JLCTR_DOCS]; stats->n_text_bytes = h_ctr[SPL_JLCTR_TEXT];
+    stats->n_missing = h_ctr[SPL_JLCTR_MISSING]; stats->n_bad = h_ctr[SPL_JLCTR_BAD]; stats->n_launches = 6;
+    if (stats->n_docs + 1 > w.off_capacity || stats->n_text_bytes > w.text_capacity) {
+        tk->err = "output capacity too small (needed sizes returned in the stats: n_docs + 1 offsets, n_text_bytes bytes)";
+        return SPL_ERR_INVALID_ARG;
+    }
     return SPL_OK;
 }
 
@@ -996,47 +1046,206 @@ int spl_ingest_jsonl_device(spl_tokenizer* tk, int dev_index, const uint8_t* d_j
         tk->err = "invalid argument (null pointer, member name of 0 or more than 64 bytes, or d_jsonl not 16-byte aligned)";
         return SPL_ERR_INVALID_ARG;
     }
-    if (n_bytes > kMaxShardBytes) { tk->err = "one device pass is limited to 4 GiB"; return SPL_ERR_UNSUPPORTED; }
-    memset(stats, 0, sizeof(*stats));
     DeviceGuard guard;
     DevCtx& dc = tk->devs[dev_index];
     CUDA_TRY(cudaSetDevice(dc.device), tk->err);
-    cudaStream_t st = (cudaStream_t)cuda_stream;
-    SplJlWork w;
-    memset(&w, 0, sizeof(w));
-    w.text = d_jsonl; w.N = (uint32_t)n_bytes; w.n_tiles = (uint32_t)(n_bytes / SPL_TILE) + 1;
-    memcpy(w.field, field, flen); w.flen = (uint32_t)flen;
-    int rc;
-    const size_t tiles_bytes = align_up(256 + (2 * (size_t)w.n_tiles + 2) * 4, 256);
-    if ((rc = dc.jl_tiles.ensure(tiles_bytes, tk->err))) return rc;
-    CUDA_TRY(cudaMemsetAsync(dc.jl_tiles.p, 0, 256, st), tk->err);
-    w.counters = (uint32_t*)dc.jl_tiles.p;
-    w.tile_cnt = w.counters + 64; w.tile_pref = w.tile_cnt + w.n_tiles;
-    spl_launch_jsonl_count(w, st);
-    uint32_t h_ctr[8];
-    CUDA_TRY(cudaMemcpyAsync(h_ctr, w.counters, sizeof(h_ctr), cudaMemcpyDeviceToHost, st), tk->err);
-    CUDA_TRY(cudaStreamSynchronize(st), tk->err);
-    const size_t n_lines = (size_t)h_ctr[SPL_JLCTR_NEWLINES] + 1;
-    w.n_lines = (uint32_t)n_lines;
-    // per-line arrays: line_start | doc_idx | text_off (n_lines + 1 each) | is_doc | out_len (n_lines each) | span
-    const size_t a1 = align_up((n_lines + 1) * 4, 16), a0 = align_up(n_lines * 4, 16);
-    if ((rc = dc.jl_lines.ensure(3 * a1 + 2 * a0 + n_lines * 16 + 64, tk->err))) return rc;
-    uint8_t* lb = (uint8_t*)dc.jl_lines.p;
-    w.line_start = (uint32_t*)lb; w.doc_idx = (uint32_t*)(lb + a1); w.text_off = (uint32_t*)(lb + 2 * a1);
-    w.is_doc = (uint32_t*)(lb + 3 * a1); w.out_len = (uint32_t*)(lb + 3 * a1 + a0);
-    w.span = (SplJlSpan*)(lb + 3 * a1 + 2 * a0);
-    w.out_text = d_text_out; w.text_capacity = d_text_out ? text_capacity : 0;
-    w.out_off = d_offsets_out; w.off_capacity = d_offsets_out ? offsets_capacity : 0;
-    spl_launch_jsonl_extract(w, st);
-    CUDA_TRY(cudaGetLastError(), tk->err);
-    CUDA_TRY(cudaMemcpyAsync(h_ctr, w.counters, sizeof(h_ctr), cudaMemcpyDeviceToHost, st), tk->err);
-    CUDA_TRY(cudaStreamSynchronize(st), tk->err);
-    stats->n_lines = n_lines; stats->n_docs = h_ctr[SPL_JLCTR_DOCS]; stats->n_text_bytes = h_ctr[SPL_JLCTR_TEXT];
-    stats->n_missing = h_ctr[SPL_JLCTR_MISSING]; stats->n_bad = h_ctr[SPL_JLCTR_BAD]; stats->n_launches = 6;
-    if (stats->n_docs + 1 > w.off_capacity || stats->n_text_bytes > w.text_capacity) {
-        tk->err = "output capacity too small (needed sizes returned in the stats: n_docs + 1 offsets, n_text_bytes bytes)";
-        return SPL_ERR_INVALID_ARG;
+    JlOut o{d_text_out, d_text_out ? text_capacity : 0, d_offsets_out, d_offsets_out ? offsets_capacity : 0};
+    return ingest_jsonl_core(tk, dc, (cudaStream_t)cuda_stream, d_jsonl, n_bytes, field, flen,
+                             [&](size_t, JlOut& out) { out = o; return SPL_OK; }, stats);
+}
+
+// File bytes in host memory -> ids in host memory: spl_encode_batch for a JSON Lines file.  Chunks end at line ends;
+// every chunk is copied in as it is, ingested (spl_ingest.h) and encoded on the device, its ids copied out while the
+// next chunk is being worked on.  One device (the handle's first).
+int spl_encode_jsonl(spl_tokenizer* tk, const uint8_t* bytes, size_t n_bytes, const char* field, uint32_t flags,
+                     spl_result** out, spl_ingest_stats* ingest_stats) {
+    if (!tk || !out) return SPL_ERR_INVALID_ARG;
+    *out = nullptr;
+    const size_t flen = field ? strlen(field) : 0;
+    if ((n_bytes && !bytes) || flen == 0 || flen > 64) { tk->err = "invalid argument (null bytes, member name of 0 or more than 64 bytes)"; return SPL_ERR_INVALID_ARG; }
+    bool with_special;
+    int rc = check_special_support(tk, flags, with_special);
+    if (rc) return rc;
+    // ---- chunks that end right behind a '\n' -------------------------------------------------------------------
+    struct JChunk { size_t b0, b1, text_off; uint64_t n_docs, doc_base, n_tokens, tok_base; volatile uint64_t* meta; uint64_t* d_meta; int obuf; };
+    std::vector<JChunk> chunks;
+    {
+        uint64_t target = tk->chunk_bytes ? tk->chunk_bytes : std::min<uint64_t>(std::max<uint64_t>(n_bytes / 8, 4u << 20), 256u << 20);
+        target = std::min<uint64_t>(target, kMaxShardBytes / (is_sentencepiece(tk) ? 6 : 2));
+        size_t b = 0, toff = 0;
+        while (b < n_bytes) {
+            size_t e = n_bytes;
+            if (n_bytes - b > target + target / 4) {
+                const void* nl = memchr(bytes + b + target, '\n', n_bytes - (b + target));
+                e = nl ? (size_t)((const uint8_t*)nl - bytes) + 1 : n_bytes;
+            }
+            JChunk c;
+            memset(&c, 0, sizeof(c));
+            c.b0 = b; c.b1 = e; c.text_off = toff; c.obuf = (int)(chunks.size() & 1);
+            toff += align_up(e - b + 16, 16);
+            chunks.push_back(c);
+            b = e;
+        }
     }
+    const size_t C = chunks.size();
+    size_t max_nb = 0;
+    for (auto& c : chunks) max_nb = std::max(max_nb, c.b1 - c.b0);
+    if (max_nb > kMaxShardBytes / (is_sentencepiece(tk) ? 3 : 1)) { tk->err = "a single line exceeds what one device pass can hold"; return SPL_ERR_UNSUPPORTED; }
+
+    DeviceGuard guard;
+    DevCtx& dc = tk->devs[0];
+    CUDA_TRY(cudaSetDevice(dc.device), tk->err);
+    spl_result* r = new (std::nothrow) spl_result();
+    if (!r) return SPL_ERR_OOM;
+    memset(&r->stats, 0, sizeof(r->stats));
+    r->owner = tk; r->n_docs = 0; r->n_tokens = 0;
+    r->ids_buf = PinnedBuf{nullptr, 0};
+    r->off_buf = take_pinned(tk, 4096 * 8);
+    PinnedBuf meta_buf = take_pinned(tk, (C + 1) * 32);
+    spl_ingest_stats tot;
+    memset(&tot, 0, sizeof(tot));
+    auto fail = [&](int code) {
+        cudaStreamSynchronize(dc.s_in); cudaStreamSynchronize(dc.stream); cudaStreamSynchronize(dc.s_out);
+        cudaGetLastError();
+        give_pinned(tk, r->off_buf); give_pinned(tk, r->ids_buf); give_pinned(tk, meta_buf);
+        delete r;
+        return code;
+    };
+    if (!r->off_buf.p || !meta_buf.p) { tk->err = "pinned host allocation failed"; return fail(SPL_ERR_OOM); }
+    void* d_meta_base = nullptr;
+    if (cudaHostGetDevicePointer(&d_meta_base, meta_buf.p, 0) != cudaSuccess) { cudaGetLastError(); tk->err = "pinned host memory is not mapped"; return fail(SPL_ERR_CUDA); }
+    auto setup = [&]() -> int {
+        int rc2;
+        size_t raw_need = 64;
+        for (auto& c : chunks) raw_need = std::max(raw_need, c.text_off + (c.b1 - c.b0) + 64);
+        if ((rc2 = dc.text.ensure(raw_need, tk->err))) return rc2;
+        if ((rc2 = dc.jl_text.ensure(max_nb + 64, tk->err))) return rc2;
+        if ((rc2 = dc.ids.ensure((ids_bound(tk, n_bytes) + 16) * 4, tk->err))) return rc2;
+        if ((rc2 = reserve_work(tk, dc, ids_bound(tk, max_nb), max_nb / 2 + 2, with_special))) return rc2;
+        if ((rc2 = dc.run_tot.ensure((C + 2) * 8, tk->err))) return rc2;
+        while (dc.sync_ev.size() < 2 * C + 2) {
+            cudaEvent_t e;
+            CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), tk->err);
+            dc.sync_ev.push_back(e);
+        }
+        return SPL_OK;
+    };
+    if ((rc = setup())) return fail(rc);
+    uint64_t* run_tot = (uint64_t*)dc.run_tot.p;
+    // every chunk of the file goes in right away, one copy each (they do not depend on anything)
+    auto copy_in = [&]() -> int {
+        CUDA_TRY(cudaEventRecord(dc.ev[0], dc.s_in), tk->err);
+        CUDA_TRY(cudaMemsetAsync(run_tot, 0, 8, dc.s_in), tk->err);
+        for (size_t k = 0; k < C; ++k) {
+            JChunk& c = chunks[k];
+            c.meta = (volatile uint64_t*)((uint8_t*)meta_buf.p + k * 32);
+            c.d_meta = (uint64_t*)((uint8_t*)d_meta_base + k * 32);
+            CUDA_TRY(cudaMemcpyAsync((uint8_t*)dc.text.p + c.text_off, bytes + c.b0, c.b1 - c.b0, cudaMemcpyHostToDevice, dc.s_in), tk->err);
+            CUDA_TRY(cudaEventRecord(dc.sync_ev[2 * k], dc.s_in), tk->err);
+            r->stats.h2d_bytes += c.b1 - c.b0;
+        }
+        return SPL_OK;
+    };
+    if ((rc = copy_in())) return fail(rc);
+
+    uint64_t total = 0, docs = 0;
+    int launches = 0;
+    uint64_t* res_off = (uint64_t*)r->off_buf.p;
+    // ids and offsets of chunk k to the host (its kernels have finished)
+    auto drain = [&](size_t k) -> int {
+        JChunk& c = chunks[k];
+        const uint32_t errbits = (uint32_t)c.meta[1];
+        if (errbits & SPL_DEVERR_HUGE_POOL) { tk->err = "scratch pool for very long pieces exhausted (spl_encode_jsonl does not retry)"; return SPL_ERR_OOM; }
+        if (errbits) { tk->err = "device error flags set by the encode kernels"; return SPL_ERR_CUDA; }
+        c.n_tokens = c.meta[0];
+        c.tok_base = total;
+        total += c.n_tokens;
+        if ((total + 16) * 4 > r->ids_buf.cap) {
+            uint64_t est = (uint64_t)((double)total / (double)std::max<size_t>(c.b1, 1) * (double)n_bytes * 1.125) + 4096;
+            est = std::min<uint64_t>(std::max<uint64_t>(est, total + 16), ids_bound(tk, n_bytes) + 16);
+            PinnedBuf nb = take_pinned(tk, est * 4);
+            if (!nb.p) { tk->err = "pinned host allocation failed"; return SPL_ERR_OOM; }
+            if (r->ids_buf.p) { cudaStreamSynchronize(dc.s_out); memcpy(nb.p, r->ids_buf.p, (size_t)c.tok_base * 4); give_pinned(tk, r->ids_buf); }
+            r->ids_buf = nb;
+        }
+        if ((c.doc_base + c.n_docs + 2) * 8 > r->off_buf.cap) {
+            uint64_t est = (uint64_t)((double)(c.doc_base + c.n_docs) / (double)std::max<size_t>(c.b1, 1) * (double)n_bytes * 1.25) + 4096;
+            PinnedBuf nb = take_pinned(tk, std::max<uint64_t>(est, c.doc_base + c.n_docs + 2) * 8);
+            if (!nb.p) { tk->err = "pinned host allocation failed"; return SPL_ERR_OOM; }
+            cudaStreamSynchronize(dc.s_out);
+            memcpy(nb.p, r->off_buf.p, (size_t)c.doc_base * 8);
+            give_pinned(tk, r->off_buf);
+            r->off_buf = nb;
+            res_off = (uint64_t*)nb.p;
+        }
+        if (c.n_tokens)
+            CUDA_TRY(cudaMemcpyAsync((uint32_t*)r->ids_buf.p + c.tok_base, (uint32_t*)dc.ids.p + ids_bound(tk, c.b0), c.n_tokens * 4,
+                                     cudaMemcpyDeviceToHost, dc.s_out), tk->err);
+        CUDA_TRY(cudaMemcpyAsync(res_off + c.doc_base, dc.jl_out_off[c.obuf].p, (c.n_docs + 1) * 8, cudaMemcpyDeviceToHost, dc.s_out), tk->err);
+        CUDA_TRY(cudaEventRecord(dc.sync_ev[2 * k + 1], dc.s_out), tk->err);
+        r->stats.d2h_bytes += c.n_tokens * 4 + (c.n_docs + 1) * 8 + 16;
+        return SPL_OK;
+    };
+    for (size_t k = 0; k < C; ++k) {
+        JChunk& c = chunks[k];
+        auto work = [&]() -> int {
+            CUDA_TRY(cudaStreamWaitEvent(dc.stream, dc.sync_ev[2 * k], 0), tk->err);
+            spl_ingest_stats st;
+            int rc2 = ingest_jsonl_core(tk, dc, dc.stream, (const uint8_t*)dc.text.p + c.text_off, c.b1 - c.b0, field, flen,
+                                        [&](size_t n_lines, JlOut& o) {
+                                            int e = dc.jl_off.ensure((n_lines + 2) * 8, tk->err);
+                                            o = JlOut{(uint8_t*)dc.jl_text.p, dc.jl_text.cap, (uint64_t*)dc.jl_off.p, n_lines + 1};
+                                            return e;
+                                        }, &st);
+            if (rc2) return rc2;
+            launches += st.n_launches;
+            tot.n_lines += st.n_lines; tot.n_docs += st.n_docs; tot.n_text_bytes += st.n_text_bytes;
+            tot.n_missing += st.n_missing; tot.n_bad += st.n_bad;
+            c.n_docs = st.n_docs; c.doc_base = docs;
+            docs += st.n_docs;
+            // the stream is idle here (ingest_jsonl_core has synchronised it): the previous chunk can leave
+            if (k > 0 && (rc2 = drain(k - 1))) return rc2;
+            DevBuf& ob = dc.jl_out_off[c.obuf];
+            if ((c.n_docs + 2) * 8 > ob.cap) {                 // may reallocate: the copy that read this buffer two chunks ago must be done
+                if (k >= 2) CUDA_TRY(cudaEventSynchronize(dc.sync_ev[2 * (k - 2) + 1]), tk->err);
+                if ((rc2 = ob.ensure((c.n_docs + 2) * 8, tk->err))) return rc2;
+            } else if (k >= 2) {
+                CUDA_TRY(cudaStreamWaitEvent(dc.stream, dc.sync_ev[2 * (k - 2) + 1], 0), tk->err);
+            }
+            SplWork w;
+            EncodeArgs ea{(const uint8_t*)dc.jl_text.p, st.n_text_bytes, (const uint64_t*)dc.jl_off.p, 0, st.n_docs,
+                          (uint32_t*)dc.ids.p + ids_bound(tk, c.b0), ids_bound(tk, c.b1 - c.b0), (uint64_t*)ob.p, c.d_meta,
+                          run_tot + k, run_tot + k + 1};
+            if ((rc2 = enqueue_encode(tk, dc, dc.stream, ea, with_special, nullptr, w, launches))) return rc2;
+            CUDA_TRY(cudaGetLastError(), tk->err);
+            return SPL_OK;
+        };
+        if ((rc = work())) return fail(rc);
+    }
+    auto finish = [&]() -> int {
+        if (C) {
+            CUDA_TRY(cudaStreamSynchronize(dc.stream), tk->err);
+            int rc2 = drain(C - 1);
+            if (rc2) return rc2;
+        }
+        CUDA_TRY(cudaEventRecord(dc.ev[3], dc.s_out), tk->err);
+        CUDA_TRY(cudaStreamSynchronize(dc.s_out), tk->err);
+        return SPL_OK;
+    };
+    if ((rc = finish())) return fail(rc);
+    if (!r->ids_buf.p) {
+        r->ids_buf = take_pinned(tk, 64);
+        if (!r->ids_buf.p) { tk->err = "pinned host allocation failed"; return fail(SPL_ERR_OOM); }
+    }
+    res_off[docs] = total;
+    float t = 0;
+    cudaEventElapsedTime(&t, dc.ev[0], dc.ev[3]);
+    r->n_docs = (size_t)docs; r->n_tokens = (size_t)total;
+    r->stats.n_docs = docs; r->stats.n_bytes = n_bytes; r->stats.n_tokens = total;
+    r->stats.total_ms = t; r->stats.n_devices = 1; r->stats.n_launches = launches;
+    if (ingest_stats) *ingest_stats = tot;
+    give_pinned(tk, meta_buf);
+    *out = r;
     return SPL_OK;
 }
 

@@ -313,20 +313,48 @@ class Tokenizer:
         return text[:int(st.n_text_bytes)], offs[:int(st.n_docs) + 1], stats
 
     def encode_jsonl(self, data, field: str = "text", with_special: bool = False, return_stats: bool = False):
-        """File bytes of a JSON Lines dataset (bytes / bytearray / numpy uint8) -> (ids uint32, offsets uint64): one
-        host-to-device copy of the raw file, member extraction + unescaping, encode and the copy of the ids back --
+        """spl_encode_jsonl: the bytes of a JSON Lines file (bytes / bytearray / numpy uint8 / integer host address
+        with `nbytes=` folded into a (address, nbytes) tuple) -> (ids uint32, offsets uint64): chunks of the raw file
+        are copied to the device, member extraction + unescaping and the encode run there, ids come back --
         the `[json.loads(l)[field] for l in f]` loop and the packing of its result never run on the host."""
-        import torch
-        raw = np.frombuffer(bytes(data), dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data, dtype=np.uint8)
-        n = int(raw.shape[0])
-        dev = torch.device("cuda", self._devices[0] if self._devices else torch.cuda.current_device())
-        buf = torch.zeros(n + ((-n) % 16) + 16, dtype=torch.uint8, device=dev)
-        if n:
-            buf[:n].copy_(torch.from_numpy(raw))
-        text, offs, stats = self.ingest_jsonl_device(buf[:n], field)
-        ids, out_off, n_tok = self.encode_device(text, offs, with_special=with_special)
-        res = (ids[:n_tok].cpu().numpy().astype(np.uint32), out_off.cpu().numpy().astype(np.uint64))
-        return res + (stats,) if return_stats else res
+        lib = _lib.load()
+        if isinstance(data, tuple):
+            keep, (addr, n) = None, data
+            ptr = ctypes.c_void_p(addr)
+        elif isinstance(data, (bytes, bytearray)):
+            keep = bytes(data)
+            n = len(keep)
+            ptr = ctypes.cast(ctypes.c_char_p(keep), ctypes.c_void_p)
+        else:
+            keep = np.ascontiguousarray(data, dtype=np.uint8)
+            n = int(keep.shape[0])
+            ptr = ctypes.c_void_p(keep.ctypes.data)
+        res = ctypes.c_void_p()
+        ist = _lib.SplIngestStats()
+        rc = lib.spl_encode_jsonl(self._handle, ptr, n, field.encode("utf-8"),
+                                  _lib.SPL_ENCODE_WITH_SPECIAL if with_special else 0, ctypes.byref(res), ctypes.byref(ist))
+        del keep
+        if rc != _lib.SPL_OK:
+            msg = _lib.last_error(self._handle)
+            if rc in (_lib.SPL_ERR_INVALID_ARG, _lib.SPL_ERR_UNSUPPORTED):
+                raise ValueError(msg)
+            raise RuntimeError(f"splintr_b200: {msg} (code {rc})")
+        try:
+            n_tok, n_docs = lib.spl_result_n_tokens(res), lib.spl_result_n_docs(res)
+            ids = np.empty(n_tok, dtype=np.uint32)
+            out_off = np.empty(n_docs + 1, dtype=np.uint64)
+            if n_tok:
+                ctypes.memmove(ids.ctypes.data, lib.spl_result_ids(res), n_tok * 4)
+            ctypes.memmove(out_off.ctypes.data, lib.spl_result_offsets(res), (n_docs + 1) * 8)
+            if return_stats:
+                st = _lib.SplStats()
+                lib.spl_result_stats(res, ctypes.byref(st))
+                stats = {f: getattr(st, f) for f, _ in _lib.SplStats._fields_}
+                stats.update({f: getattr(ist, f) for f, _ in _lib.SplIngestStats._fields_ if f != "n_launches"})
+                return ids, out_off, stats
+            return ids, out_off
+        finally:
+            lib.spl_result_free(res)
 
     def set_profiling(self, enable: bool = True) -> None:
         _lib.load().spl_set_profiling(self._handle, int(enable))

@@ -470,6 +470,35 @@ def test_ingest_jsonl_matches_json_module(toks):
         tok.ingest_jsonl_device(torch.zeros(16, dtype=torch.uint8, device="cuda")[:3], field="")
 
 
+def test_encode_jsonl_many_chunks(toks, monkeypatch):
+    """spl_encode_jsonl cuts the file at line ends into pipeline chunks; force small chunks so one call runs through
+    dozens of them (blank lines, empty documents and a huge line on the boundaries), also in SentencePiece mode."""
+    import json
+    from splintr_b200 import Tokenizer
+    from jsonl_cases import make_lines, join_lines
+    monkeypatch.setenv("SPL_CHUNK_BYTES", "30000")
+    t1 = Tokenizer.from_pretrained("cl100k_base", devices=[0])
+    t2 = Tokenizer.from_pretrained("mistral_v2", devices=[0])
+    monkeypatch.delenv("SPL_CHUNK_BYTES")
+    lines, want = make_lines(77, 6000)
+    lines[10] = json.dumps({"text": "x " * 40000}); want_big = "x " * 40000
+    want = []
+    for l in lines:
+        if l.strip(" \t\r"):
+            v = json.loads(l).get("text")
+            want.append(v if isinstance(v, str) else "")
+    assert want_big in want
+    data = join_lines(lines)
+    for t in (t1, t2):
+        ids, off, st = t.encode_jsonl(data, return_stats=True)
+        assert st["n_docs"] == len(want) and st["n_bad"] == 0
+        flat, o = ids.tolist(), off.tolist()
+        assert [flat[o[i]:o[i + 1]] for i in range(len(want))] == t.encode_batch(want)
+    ids_s, off_s = t1.encode_jsonl(data, with_special=True)
+    flat, o = ids_s.tolist(), off_s.tolist()
+    assert [flat[o[i]:o[i + 1]] for i in range(len(want))] == t1.encode_batch_with_special(want)
+
+
 def test_ingest_jsonl_cfg2_roundtrip(toks):
     """cfg2 (100 000 documents) written as JSON Lines with json.dumps and ingested on the device reproduces the packed
     batch byte for byte, and its ids equal the ids of the packed batch."""

@@ -13,7 +13,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --cs
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches_${TAG}.log 2>&1
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_probe|k_emit|k_pretok_fast|k_bpe' -s 12 -c 4 -f -o gpurun_out/prof_${TAG} \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_${TAG}.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_dec_|k_sp_' -c 16 -f -o gpurun_out/prof_aux_${TAG} \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_dec_|k_sp_|k_jl_' -c 40 -f -o gpurun_out/prof_aux_${TAG} \
     python tools/gpu_aux_kernels.py > gpurun_out/ncu_aux_${TAG}.log 2>&1
 bash tools/gpu_sanitize.sh > gpurun_out/sanitize_${TAG}.log 2>&1
 tail -4 gpurun_out/sanitize_${TAG}.log

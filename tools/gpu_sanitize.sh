@@ -29,6 +29,14 @@ a = tok.encode_batch(sp_texts)
 b = tok.encode_batch_with_special(sp_texts)
 assert tok.decode_batch(a[:50]) == sp_texts[:50]
 print("mistral_v2", sum(len(x) for x in a), sum(len(x) for x in b), flush=True)
+# JSON Lines ingestion (row N4)
+import json
+from jsonl_cases import make_lines, join_lines
+lines, want = make_lines(5, 800)
+tok = Tokenizer.from_pretrained("cl100k_base", devices=[0])
+ids, off = tok.encode_jsonl(join_lines(lines))
+assert len(off) == len(want) + 1
+print("jsonl", len(want), len(ids), flush=True)
 PY
 for tool in memcheck racecheck; do
   timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python /tmp/san_driver.py > gpurun_out/sanitizer_$tool.log 2>&1
