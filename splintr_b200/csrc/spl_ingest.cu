@@ -13,9 +13,30 @@
 
 namespace {
 
+// Text accessor of the per-line walks: a 16-byte window in registers.  A thread reads its line front to back with
+// short look-aheads, so one 16-byte load serves ~16 byte() calls; without it every byte is its own sector request and
+// the walk is a chain of ~1 000 dependent L2 round trips per line.
 struct GText {
     const uint8_t* p;
-    __device__ __forceinline__ uint8_t byte(uint32_t i) const { return __ldg(p + i); }
+    mutable uint32_t blk;
+    mutable uint64_t lo, hi;
+    __device__ __forceinline__ explicit GText(const uint8_t* p_) : p(p_), blk(0xFFFFFFFFu), lo(0), hi(0) {}
+    __device__ __forceinline__ uint8_t byte(uint32_t i) const {
+        const uint32_t b = i >> 4;
+        if (b != blk) {
+            const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(p) + b);     // p is 16-byte aligned and padded
+            lo = v.x; hi = v.y; blk = b;
+        }
+        const uint64_t w = (i & 8u) ? hi : lo;
+        return (uint8_t)(w >> ((i & 7u) * 8u));
+    }
+    // the eight bytes from i on (two aligned loads; the walk is sequential, so the second one is the next call's first)
+    __device__ __forceinline__ uint64_t word8(uint32_t i) const {
+        const uint64_t* q = reinterpret_cast<const uint64_t*>(p + (i & ~7u));
+        const uint64_t a = __ldg(q), b = __ldg(q + 1);
+        const uint32_t sh = (i & 7u) * 8u;
+        return sh ? (a >> sh) | (b << (64u - sh)) : a;
+    }
 };
 
 #define JL_THREADS 256
@@ -101,7 +122,7 @@ __global__ void __launch_bounds__(JL_THREADS) k_jl_lines(SplJlWork w) {
 __global__ void __launch_bounds__(JL_THREADS) k_jl_parse(SplJlWork w) {
     const uint32_t k = blockIdx.x * JL_THREADS + threadIdx.x;
     if (k >= w.n_lines) return;
-    const GText t{w.text};
+    const GText t(w.text);
     const SplJlSpan sp = spl_jl_parse_line(t, w.line_start[k], w.line_start[k + 1] - 1, w.field, w.flen);
     w.span[k] = sp;
     w.is_doc[k] = sp.flags & SPL_JL_DOC;
@@ -134,9 +155,24 @@ __global__ void __launch_bounds__(JL_THREADS) k_jl_emit(SplJlWork w) {
     uint32_t o = w.text_off[k];
     w.out_off[d] = o;
     if (!(sp.flags & SPL_JL_FOUND) || (uint64_t)w.text_off[w.n_lines] > w.text_capacity) return;
-    const GText t{w.text};
+    const GText t(w.text);
     uint32_t j = sp.vs;
     while (j < sp.ve) {
+        if (j + 16u <= sp.ve) {
+            const uint64_t x = t.word8(j);
+            if (!spl_jl_has(x, '\\')) {                          // eight bytes without an escape: copied as they are,
+                const uint32_t mis = o & 7u;                     // with one 8-byte store once the destination is aligned
+                if (mis == 0) {
+                    *reinterpret_cast<uint64_t*>(w.out_text + o) = x;
+                    o += 8; j += 8;
+                } else {
+                    const uint32_t k = 8u - mis;
+                    for (uint32_t q = 0; q < k; ++q) w.out_text[o + q] = (uint8_t)(x >> (8u * q));
+                    o += k; j += k;
+                }
+                continue;
+            }
+        }
         uint8_t ch[4];
         uint32_t n;
         j = spl_jl_char(t, j, sp.ve, ch, n);

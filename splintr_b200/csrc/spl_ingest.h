@@ -79,86 +79,105 @@ SPL_HD uint32_t spl_jl_char(const T& t, uint32_t i, uint32_t e, uint8_t* out, ui
     return next;
 }
 
-// position of the closing quote of the string whose body starts at i, or e
-template <class T>
-SPL_HD uint32_t spl_jl_string_end(const T& t, uint32_t i, uint32_t e) {
-    while (i < e) {
-        uint32_t b = t.byte(i);
-        if (b == '"') return i;
-        i += (b == '\\') ? 2u : 1u;
-    }
-    return e;
+// bytes of `w` (eight text bytes, little endian) equal to c, flagged in bit 7 of their byte
+SPL_HD uint64_t spl_jl_has(uint64_t w, uint32_t c) {
+    const uint64_t x = w ^ (0x0101010101010101ull * c);
+    return (x - 0x0101010101010101ull) & ~x & 0x8080808080808080ull;
 }
 
 // Parse the line [s, e) (no '\n' inside).  field[0..flen) = the member name wanted.
+//
+// Written as ONE loop over the line with an explicit state, not as nested scanning loops: on the device one thread
+// parses one line, and the 32 lines of a warp are at different places of their objects; with nested loops the lanes
+// never reconverge and the warp executes them one after the other (measured: 3.3 of 32 lanes active).  Here every
+// lane goes round the same loop and the divergence is confined to the body of one iteration.  Inside strings the
+// loop advances eight bytes at a time while they hold no quote and no escape (T::word8(i) = the eight bytes from i
+// on; only called with i + 16 <= e).
 template <class T>
 SPL_HD SplJlSpan spl_jl_parse_line(const T& t, uint32_t s, uint32_t e, const uint8_t* field, uint32_t flen) {
+    enum : uint32_t { ST_START, ST_MEMBER, ST_KEY, ST_COLON, ST_VALUE, ST_VSTR, ST_SCALAR, ST_NESTED, ST_NSTR, ST_AFTER, ST_DONE, ST_BAD };
     SplJlSpan r;
     r.vs = r.ve = r.out_len = r.flags = 0;
-    uint32_t i = s;
-    while (i < e && spl_jl_blank(t.byte(i))) ++i;
-    if (i >= e) return r;                                    // blank line: no document
-    r.flags = SPL_JL_DOC;
-    if (t.byte(i) != '{') { r.flags |= SPL_JL_BAD; return r; }
-    ++i;
-    bool found = false;
-    for (;;) {
-        while (i < e && spl_jl_blank(t.byte(i))) ++i;
-        if (i >= e) { r.flags |= SPL_JL_BAD; break; }
-        if (t.byte(i) == '}') break;
-        if (t.byte(i) != '"') { r.flags |= SPL_JL_BAD; break; }
-        // ---- member name: compared unescaped --------------------------------------------------------
-        const uint32_t kend = spl_jl_string_end(t, i + 1, e);
-        if (kend >= e) { r.flags |= SPL_JL_BAD; break; }
-        bool match = true;
-        {
-            uint32_t j = i + 1, f = 0;
-            while (j < kend && match) {
-                uint8_t ch[4]; uint32_t n;
-                j = spl_jl_char(t, j, kend, ch, n);
-                for (uint32_t q = 0; q < n; ++q) { if (f >= flen || field[f] != ch[q]) { match = false; break; } ++f; }
-            }
-            if (f != flen) match = false;
-        }
-        i = kend + 1;
-        while (i < e && spl_jl_blank(t.byte(i))) ++i;
-        if (i >= e || t.byte(i) != ':') { r.flags |= SPL_JL_BAD; break; }
-        ++i;
-        while (i < e && spl_jl_blank(t.byte(i))) ++i;
-        if (i >= e) { r.flags |= SPL_JL_BAD; break; }
-        // ---- value -------------------------------------------------------------------------------------
-        uint32_t b = t.byte(i);
-        if (b == '"') {
-            const uint32_t vend = spl_jl_string_end(t, i + 1, e);
-            if (vend >= e) { r.flags |= SPL_JL_BAD; break; }
-            if (match) { r.vs = i + 1; r.ve = vend; found = true; }
-            i = vend + 1;
-        } else {
-            if (match) found = false;                        // the last member of that name wins, and it is not a string
-            if (b == '{' || b == '[') {
-                uint32_t depth = 0;
-                while (i < e) {
-                    uint32_t c = t.byte(i);
-                    if (c == '"') { i = spl_jl_string_end(t, i + 1, e); if (i >= e) break; }
-                    else if (c == '{' || c == '[') ++depth;
-                    else if (c == '}' || c == ']') { if (--depth == 0) { ++i; break; } }
-                    ++i;
+    uint32_t st = ST_START, i = s, f = 0, depth = 0, vstart = 0;
+    bool doc = false, kmatch = true, match = false, found = false;
+    while (i < e && st < ST_DONE) {
+        const uint32_t b = t.byte(i);
+        switch (st) {
+            case ST_START:                                   // blanks, then the opening brace
+                if (spl_jl_blank(b)) { ++i; break; }
+                doc = true;
+                if (b == '{') { st = ST_MEMBER; ++i; } else st = ST_BAD;
+                break;
+            case ST_MEMBER:                                  // a member name, or the closing brace
+                if (spl_jl_blank(b)) { ++i; break; }
+                if (b == '}') { st = ST_DONE; break; }
+                if (b == '"') { st = ST_KEY; f = 0; kmatch = true; ++i; } else st = ST_BAD;
+                break;
+            case ST_KEY: {                                   // member name: compared unescaped
+                if (b == '"') { match = kmatch && f == flen; st = ST_COLON; ++i; break; }
+                uint8_t ch[4];
+                uint32_t n = 1, ni = i + 1;
+                ch[0] = (uint8_t)b;
+                if (b == '\\') ni = spl_jl_char(t, i, e, ch, n);
+                for (uint32_t q = 0; q < n; ++q) {
+                    if (kmatch && f < flen && field[f] == ch[q]) ++f; else kmatch = false;
                 }
-                if (depth != 0) { r.flags |= SPL_JL_BAD; break; }
-            } else {
-                while (i < e) { uint32_t c = t.byte(i); if (c == ',' || c == '}' || spl_jl_blank(c)) break; ++i; }
+                i = ni;
+                break;
             }
+            case ST_COLON:
+                if (spl_jl_blank(b)) { ++i; break; }
+                if (b == ':') { st = ST_VALUE; ++i; } else st = ST_BAD;
+                break;
+            case ST_VALUE:                                   // first character of the value decides
+                if (spl_jl_blank(b)) { ++i; break; }
+                if (b == '"') { st = ST_VSTR; vstart = i + 1; ++i; break; }
+                if (match) found = false;                    // the last member of that name wins, and it is not a string
+                if (b == '{' || b == '[') { depth = 1; st = ST_NESTED; ++i; } else st = ST_SCALAR;
+                break;
+            case ST_VSTR:
+            case ST_NSTR:                                    // inside a string (a value / somewhere in a nested value)
+                if (i + 16u <= e) {
+                    const uint64_t w = t.word8(i);
+                    if (!(spl_jl_has(w, '"') | spl_jl_has(w, '\\'))) { i += 8u; break; }
+                }
+                if (b == '"') {
+                    if (st == ST_VSTR) { if (match) { r.vs = vstart; r.ve = i; found = true; } st = ST_AFTER; }
+                    else st = ST_NESTED;
+                    ++i;
+                } else {
+                    i += (b == '\\') ? 2u : 1u;
+                }
+                break;
+            case ST_SCALAR:                                  // number / true / false / null: up to , } or a blank
+                if (b == ',' || b == '}' || spl_jl_blank(b)) st = ST_AFTER; else ++i;
+                break;
+            case ST_NESTED:                                  // object or array value: skipped with a depth count
+                if (b == '"') st = ST_NSTR;
+                else if (b == '{' || b == '[') ++depth;
+                else if (b == '}' || b == ']') { if (--depth == 0) st = ST_AFTER; }
+                ++i;
+                break;
+            default:                                         // ST_AFTER: a comma or the closing brace
+                if (spl_jl_blank(b)) { ++i; break; }
+                if (b == ',') { st = ST_MEMBER; ++i; }
+                else if (b == '}') st = ST_DONE;
+                else st = ST_BAD;
+                break;
         }
-        while (i < e && spl_jl_blank(t.byte(i))) ++i;
-        if (i < e && t.byte(i) == ',') { ++i; continue; }
-        if (i < e && t.byte(i) == '}') break;
-        r.flags |= SPL_JL_BAD;
-        break;
     }
+    if (!doc) return r;                                      // blank line: no document
+    r.flags = SPL_JL_DOC;
+    if (st != ST_DONE) r.flags |= SPL_JL_BAD;                // ran into the end of the line, or saw something unexpected
     if (found && !(r.flags & SPL_JL_BAD)) {
         r.flags |= SPL_JL_FOUND;
         uint32_t j = r.vs, len = 0;
-        while (j < r.ve) { uint8_t ch[4]; uint32_t n; j = spl_jl_char(t, j, r.ve, ch, n); len += n; }
+        while (j < r.ve) {
+            if (j + 16u <= r.ve && !spl_jl_has(t.word8(j), '\\')) { j += 8u; len += 8u; continue; }   // no escape: as it is
+            uint8_t ch[4]; uint32_t n;
+            j = spl_jl_char(t, j, r.ve, ch, n);
+            len += n;
+        }
         r.out_len = len;
     } else {
         r.vs = r.ve = 0;
