@@ -121,6 +121,29 @@ __device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
     return v;
 }
 
+// three independent pair probes issued back to back (the ranks a merge window needs per candidate, k_bpe)
+__device__ __forceinline__ void pair_lookup3(const uint64_t* __restrict__ tab, uint32_t log2,
+                                             bool va, uint32_t la, uint32_t ra, bool vb, uint32_t lb, uint32_t rb,
+                                             bool vc, uint32_t lc, uint32_t rc,
+                                             uint32_t& outa, uint32_t& outb, uint32_t& outc) {
+    const uint32_t mask = (1u << log2) - 1;
+    const uint64_t ka = spl_pair_key(la, ra), kb = spl_pair_key(lb, rb), kc = spl_pair_key(lc, rc);
+    uint32_t ba = spl_pair_hash(ka, log2), bb = spl_pair_hash(kb, log2), bc = spl_pair_hash(kc, log2);
+    PairBucket xa, xb, xc;
+    xa.lo = xa.hi = make_ulonglong2(SPL_PAIR_EMPTY, SPL_PAIR_EMPTY);
+    xb = xa; xc = xa;
+    if (va) xa = pair_bucket_load(tab, ba);
+    if (vb) xb = pair_bucket_load(tab, bb);
+    if (vc) xc = pair_bucket_load(tab, bc);
+    outa = SPL_RANK_NONE; outb = SPL_RANK_NONE; outc = SPL_RANK_NONE;
+    if (va)
+        while (pair_bucket_match(xa, ka, outa) == 2) { ba = (ba + 1) & mask; xa = pair_bucket_load(tab, ba); }
+    if (vb)
+        while (pair_bucket_match(xb, kb, outb) == 2) { bb = (bb + 1) & mask; xb = pair_bucket_load(tab, bb); }
+    if (vc)
+        while (pair_bucket_match(xc, kc, outc) == 2) { bc = (bc + 1) & mask; xc = pair_bucket_load(tab, bc); }
+}
+
 // two independent pair probes issued back to back (the two re-ranks after a merge)
 __device__ __forceinline__ void pair_lookup2(const uint64_t* __restrict__ tab, uint32_t log2,
                                              bool va, uint32_t la, uint32_t ra, bool vb, uint32_t lb, uint32_t rb,

@@ -437,18 +437,30 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe_rest(SplWork w) {
 // ------------------------------------------------------------------------------------------
 // k_bpe: the merge loop (bpe.rs:83-194) for the listed pieces
 //
-// A piece of length class c is merged by a GROUP of G = 2^log2group(c) lanes, 64 parts per lane, so a warp merges
-// 32 / G pieces side by side and every lane has work in every step (32 parts per lane).  The parts of a piece form a doubly linked
-// list (bpe.rs:42-54) packed into ten bytes per part, in the warp's 10 KiB of shared memory:
-//     A[e] = symbol:21 | next:11     R[e] = rank of (part e, next part):21 | e:11     P[e] = prev (u16)
-// R doubles as the scan key: the minimum over R is the lowest rank at the leftmost position.
-// Element e of the piece of group p sits at word (e / G) * 32 + p * G + e % G, so the strided scan of a group is
-// conflict free.  One merge = strided min-scan of the ranks (leftmost minimum, bpe.rs:133), a shuffle reduction
-// inside the group, the splice and the two re-ranks (bpe.rs:146-166), done by lanes 0 and 1 of the group.
+// A piece of length class c is merged by a GROUP of G = 2^log2group(c) lanes, up to 32 parts per lane, so a warp
+// merges 32 / G pieces side by side.  The live parts of a piece are an ARRAY (compacted after every round) in the
+// warp's 12 KiB of shared memory:
+//     S[i] = symbol of part i     K[i] = rank of the pair (part i, part i+1), BG_RANK_NONE if none     X[i] = scratch
+// Part i sits at word (i / G) * 32 + p * G + i % G (p = the group's index in the warp), so row r of a group is G
+// consecutive parts in G consecutive lanes and a ballot over a row is a bitmap of G consecutive parts.
+//
+// The reference merges one pair per step: the lowest rank, leftmost on ties (bpe.rs:121-138).  Here one ROUND
+// performs every merge of a whole window of that sequence at once; the result is the same list of parts:
+//   order pairs by key = (rank, position).  If no pair created in the window had a rank below the window's end,
+//   the sequential loop would visit the existing pairs in key order and merge pair i unless a neighbour merged
+//   first (its part is gone then):  m(i) = !(m(i-1) && key(i-1) < key(i)) && !(m(i+1) && key(i+1) < key(i)).
+//   A pair below both neighbours merges; along a slope m alternates with the distance from the valley (the parity
+//   comes from the row bitmaps); a pair above both neighbours merges iff neither does.
+//   Every pair with m = 1 looks up the ranks its merge can create: (left part, T), (T, right part) and, when the
+//   pair two to the right has m = 1 too, (T, T').  theta = the minimum of all of them.  No created pair ranks below
+//   theta, so up to theta the sequential loop does exactly the m = 1 merges: the round commits those with
+//   rank < theta (and always the global minimum, which bpe.rs merges first whatever follows).
+//   The three looked-up ranks are also the K values of the new neighbours, so a round needs no second probe pass.
+// tools/bpe_batch_sim.py is the same round in Python, checked against the oracle; random letter strings of
+// 32..512 bytes take ~3 rounds instead of ~80 merges steps, runs of one character ~6 instead of ~120.
 // ------------------------------------------------------------------------------------------
 #define BG_RANK_NONE 0x1FFFFFu
-#define BG_LINK_NONE 0x7FFu
-#define BG_WORDS     2560u                              // words per warp: A[1024] + R[1024] + P[1024 x u16] (32 parts per lane)
+#define BG_WORDS     3424u                              // words per warp: S[1024] + K[1024] + X[1024] + worklist (256) + 3 x 32
 
 // whole-piece probe of a piece in global memory by ONE thread (vocabularies with keys beyond 128 bytes only)
 __device__ uint32_t lookupL_serial_g(const SplTables* T, const uint8_t* __restrict__ tx, uint32_t len) {
@@ -481,12 +493,16 @@ __device__ __forceinline__ void bpe_finish(const SplWork& w, uint64_t* slot, uin
     }
 }
 
-// All 32 lanes call this; lane = p * G + g works on piece p of the warp's task (valid: the piece exists), G = 1 << LG.
-// Returns the id count in lane g == 0 of every group; ids go to out[0 ..] in order.
-template <uint32_t LG>
-__device__ uint32_t bpe_group(uint32_t* reg, const bool valid, const SplTables* T,
+// Short pieces (<= 32 bytes, classes 0 and 1): ONE lane per piece runs the loop of bpe.rs:119-167 as it stands -- a
+// piece of a few parts takes fewer instructions that way than a round of the windowed form below costs.
+// The parts form a doubly linked list (bpe.rs:42-54) in the lane's column of the warp's shared memory:
+//     A[e] = symbol:21 | next:11     R[e] = rank of (part e, next part):21 | e:11     P[e] = prev (u16)
+// R doubles as the scan key: the minimum over R is the lowest rank at the leftmost position (bpe.rs:133).
+// All 32 lanes call this (valid: the lane has a piece).  Returns the id count; ids go to out[0 ..] in order.
+#define BG_LINK_NONE 0x7FFu
+__device__ uint32_t bpe_lane(uint32_t* reg, const bool valid, const SplTables* T,
                               const uint8_t* __restrict__ tx, const uint32_t n, uint32_t* __restrict__ out) {
-    constexpr uint32_t G = 1u << LG;
+    constexpr uint32_t LG = 0u, G = 1u;
     const uint32_t lane = threadIdx.x & 31u, p = lane >> LG, g = lane & (G - 1u);
     uint32_t* A = reg;                                             // symbol:21 | next:11
     uint32_t* R = reg + 1024;                                      // rank:21 | own position:11  (the scan key)
@@ -596,6 +612,212 @@ __device__ uint32_t bpe_group(uint32_t* reg, const bool valid, const SplTables* 
     return c;
 }
 
+// All 32 lanes call this; lane = p * G + g works on piece p of the warp's task (valid: the piece exists), G = 1 << LG.
+// Returns the id count in every lane of the group; ids go to out[0 ..] in order.
+template <uint32_t LG>
+__device__ uint32_t bpe_group(uint32_t* reg, const bool valid, const SplTables* T,
+                              const uint8_t* __restrict__ tx, const uint32_t n, uint32_t* __restrict__ out) {
+    constexpr uint32_t G = 1u << LG;
+    constexpr uint32_t GM = G == 32u ? 0xFFFFFFFFu : (1u << G) - 1u;
+    constexpr uint32_t NONE = BG_RANK_NONE;
+    const uint32_t lane = threadIdx.x & 31u, g = lane & (G - 1u), gsh = lane & ~(G - 1u);
+    uint32_t* S = reg;                                             // symbols of the live parts
+    uint32_t* K = reg + 1024;                                      // rank of (part i, part i + 1)
+    uint32_t* X = reg + 2048;                                      // ranks looked up in the current round
+    uint16_t* WL = reinterpret_cast<uint16_t*>(reg + 3072);        // worklist of the round: word index of every m-pair (<= 512)
+    uint32_t* MW = reg + 3328;                                     // per lane: its m mask, its piece's part count, theta of its group
+    uint32_t* LW = reg + 3360;
+    uint32_t* TH = reg + 3392;
+    const uint64_t* __restrict__ ptab = T->pair;
+    const uint32_t plog = T->pair_log2, pmask = (1u << plog) - 1u;
+#define IDX(e) ((((e) >> LG) << 5) + gsh + ((e) & (G - 1u)))
+    // bit r of a lane's mask = its part of row r; the same mask of part i + d sits d lanes on (wrapping into the next row)
+#define NEXT_MASK(v, d) (__shfl_sync(FULL, (v), gsh + ((g + (d)) & (G - 1u))) >> ((g + (d)) >> LG))
+#define PREV_MASK(v)    (__shfl_sync(FULL, (v), gsh + ((g + G - 1u) & (G - 1u))) << (g ? 0u : 1u))
+    bool act = valid;
+    {
+        // whole-piece probe of pieces beyond the probe halo (k_probe has already tried the shorter ones)
+        const bool tryw = act && n > SPL_PROBE_HALO && n <= T->max_key_len;
+        if (__any_sync(FULL, tryw)) {
+            uint32_t id = SPL_RANK_NONE;
+            if (tryw && g == 0) id = lookupL_serial_g(T, tx, n);
+            id = __shfl_sync(FULL, id, gsh);
+            if (tryw && id != SPL_RANK_NONE) { if (g == 0) out[0] = id; act = false; }
+        }
+    }
+    const bool whole = valid && !act;
+    uint32_t L = act ? n : 0u;                                     // live parts (uniform in the group)
+    {
+        const uint32_t rows = (L + G - 1u - g) >> LG;             // parts of this lane: i = g + it * G, at word it * 32 + lane
+        // ---- every byte becomes a part (two passes, each unrolled, so that several loads are in flight together)
+#pragma unroll 4
+        for (uint32_t it = 0; it < rows; ++it) S[it * 32u + lane] = __ldg(tx + g + (it << LG));
+#pragma unroll 4
+        for (uint32_t it = 0; it < rows; ++it) S[it * 32u + lane] = T->byte_sym[S[it * 32u + lane]];
+        __syncwarp();
+        // ---- ranks of the adjacent pairs, two independent probes in flight per lane
+        for (uint32_t it = 0; it < rows; it += 2) {
+            PairBucket bk[2];
+            uint64_t key[2];
+            uint32_t bb[2];
+#pragma unroll
+            for (uint32_t q = 0; q < 2; ++q) {
+                const uint32_t e = g + ((it + q) << LG);
+                if (e + 1 < L) {
+                    key[q] = spl_pair_key(S[(it + q) * 32u + lane], S[IDX(e + 1)]);
+                    bb[q] = spl_pair_hash(key[q], plog);
+                    bk[q] = pair_bucket_load(ptab, bb[q]);
+                }
+            }
+#pragma unroll
+            for (uint32_t q = 0; q < 2; ++q) {
+                const uint32_t e = g + ((it + q) << LG);
+                if (e < L) {
+                    uint32_t r = SPL_RANK_NONE;
+                    if (e + 1 < L)
+                        while (pair_bucket_match(bk[q], key[q], r) == 2) { bb[q] = (bb[q] + 1) & pmask; bk[q] = pair_bucket_load(ptab, bb[q]); }
+                    K[(it + q) * 32u + lane] = r & NONE;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    // ---- merge rounds ------------------------------------------------------------------------------------
+    for (;;) {
+        const uint32_t rowsW = __reduce_max_sync(FULL, (L + G - 1u) >> LG);        // rows of the longest piece of the warp
+        // (1) every pair against its neighbours: valley / slope to the left / slope to the right / peak
+        uint32_t fV = 0, fDL = 0, fDR = 0, fPK = 0, gmin = 0xFFFFFFFFu;
+        for (uint32_t r = 0; r < rowsW; ++r) {
+            const uint32_t i = (r << LG) + g;
+            if (i + 1 < L) {
+                const uint32_t kc = K[r * 32u + lane];
+                if (kc != NONE) {
+                    const uint32_t kl = i ? K[IDX(i - 1)] : NONE, kr = i + 2 < L ? K[IDX(i + 1)] : NONE;
+                    const bool lt = kl <= kc, rt = kr < kc;                         // the neighbour merges first (left wins ties)
+                    const uint32_t bit = 1u << r;
+                    if (lt) { if (rt) fPK |= bit; else fDL |= bit; } else { if (rt) fDR |= bit; else fV |= bit; }
+                    gmin = min(gmin, (kc << 11) | i);
+                }
+            }
+        }
+#pragma unroll
+        for (uint32_t o = G >> 1; o; o >>= 1) gmin = min(gmin, __shfl_xor_sync(FULL, gmin, o));
+        if (!__any_sync(FULL, gmin != 0xFFFFFFFFu)) break;                          // no pair with a rank anywhere in the warp
+        // (2) m: valleys merge; along a slope m alternates with the distance from its valley
+        uint32_t m = fV;
+        if (__any_sync(FULL, fDL != 0u)) {
+            uint32_t carry = 0;                                                     // m of the last part of the row before
+            for (uint32_t r = 0; r < rowsW; ++r) {
+                const uint32_t bit = 1u << r;
+                const uint32_t bDL = (__ballot_sync(FULL, (fDL & bit) != 0u) >> gsh) & GM;
+                if (fDL & bit) {
+                    const uint32_t below = ~bDL & ((1u << g) - 1u);                 // nearest part to the left that is not on the slope: its valley
+                    const uint32_t mv = below ? ((g - (31u - __clz(below))) & 1u) ^ 1u : carry ^ ((g + 1u) & 1u);
+                    if (mv) m |= bit;
+                }
+                carry = (__shfl_sync(FULL, m, gsh + G - 1u) >> r) & 1u;
+            }
+        }
+        if (__any_sync(FULL, fDR != 0u)) {
+            uint32_t carry = 0;                                                     // m of the first part of the row after
+            for (uint32_t r = rowsW; r-- > 0;) {
+                const uint32_t bit = 1u << r;
+                const uint32_t bDR = (__ballot_sync(FULL, (fDR & bit) != 0u) >> gsh) & GM;
+                if (fDR & bit) {
+                    const uint32_t above = ~bDR & GM & ~((2u << g) - 1u);
+                    const uint32_t mv = above ? (((uint32_t)__ffs(above) - 1u - g) & 1u) ^ 1u : carry ^ ((G - g) & 1u);
+                    if (mv) m |= bit;
+                }
+                carry = (__shfl_sync(FULL, m, gsh) >> r) & 1u;
+            }
+        }
+        {
+            const uint32_t mL = PREV_MASK(m), mR = NEXT_MASK(m, 1u);
+            m |= fPK & ~mL & ~mR;                                                   // a peak merges iff neither neighbour does
+        }
+        // (3) the ranks the merges can create; theta = their minimum.  The m-pairs of the whole warp go through a
+        // worklist so that all 32 lanes probe (a lane holds anything from 0 to rows / 2 m-pairs of its own).
+        {
+            const uint32_t cntm = __popc(m);
+            uint32_t off = cntm;
+#pragma unroll
+            for (uint32_t o = 1; o < 32u; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, off, o); if (lane >= o) off += t; }
+            const uint32_t total = __shfl_sync(FULL, off, 31);
+            off -= cntm;
+            for (uint32_t mm = m; mm; mm &= mm - 1u) WL[off++] = (uint16_t)((((uint32_t)__ffs(mm) - 1u) << 5) | lane);
+            MW[lane] = m; LW[lane] = L; TH[lane] = NONE;
+            __syncwarp();
+            for (uint32_t q = lane; q < total; q += 32u) {
+                const uint32_t wv = WL[q], r = wv >> 5, ln = wv & 31u, g2 = ln & (G - 1u), gs2 = ln & ~(G - 1u);
+                const uint32_t i = (r << LG) + g2, L2 = LW[ln];
+#define IDX2(e) ((((e) >> LG) << 5) + gs2 + ((e) & (G - 1u)))
+                const uint32_t tm = K[wv];                                          // merged id == its rank
+                const bool hasL = i > 0u, hasR = i + 2u < L2;
+                const bool hasC = hasR && ((MW[gs2 + ((g2 + 2u) & (G - 1u))] >> (r + ((g2 + 2u) >> LG))) & 1u);
+                const uint32_t sl = hasL ? S[IDX2(i - 1u)] : 0u, sr = hasR ? S[IDX2(i + 2u)] : 0u, tc = hasC ? K[IDX2(i + 2u)] : 0u;
+                uint32_t ra, rb, rc;
+                pair_lookup3(ptab, plog, hasL, sl, tm, hasR, tm, sr, hasC, tm, tc, ra, rb, rc);
+                ra &= NONE; rb &= NONE; rc &= NONE;
+                atomicMin(&TH[gs2], min(ra, min(rb, rc)));
+                X[wv] = ra | (rc << 21);                                            // rc: low 11 bits here, high 10 bits in the next word
+                X[IDX2(i + 1u)] = rb | ((rc >> 11) << 21);
+#undef IDX2
+            }
+            __syncwarp();
+        }
+        const uint32_t theta = TH[gsh];
+        // (4) commit: m-pairs below theta, and the global minimum in any case
+        uint32_t cm = 0;
+        for (uint32_t mm = m; mm; mm &= mm - 1u) {
+            const uint32_t r = (uint32_t)__ffs(mm) - 1u, kc = K[r * 32u + lane];
+            if (kc < theta || ((kc << 11) | ((r << LG) + g)) == gmin) cm |= 1u << r;
+        }
+        __syncwarp();
+        // (5) compact the parts in place, row by row (a part moves to an index <= its own)
+        const uint32_t cmL = PREV_MASK(cm), cmR1 = NEXT_MASK(cm, 1u), cmR2 = NEXT_MASK(cm, 2u);
+        uint32_t base = 0;
+        for (uint32_t r = 0; r < rowsW; ++r) {
+            const uint32_t i = (r << LG) + g;
+            const bool surv = i < L && !((cmL >> r) & 1u);                          // the right part of a committed pair is absorbed
+            uint32_t s_new = 0, k_new = NONE;
+            if (surv) {
+                if ((cm >> r) & 1u) {
+                    const uint32_t x0 = X[r * 32u + lane], x1 = X[IDX(i + 1u)];
+                    s_new = K[r * 32u + lane];
+                    k_new = ((cmR2 >> r) & 1u) ? ((x0 >> 21) | ((x1 >> 21) << 11)) : (x1 & NONE);
+                } else {
+                    s_new = S[r * 32u + lane];
+                    k_new = ((cmR1 >> r) & 1u) ? (X[IDX(i + 1u)] & NONE) : (i + 1u < L ? K[r * 32u + lane] : NONE);
+                }
+            }
+            const uint32_t b = (__ballot_sync(FULL, surv) >> gsh) & GM;
+            const uint32_t pos = base + __popc(b & ((1u << g) - 1u));
+            base += __popc(b);
+            __syncwarp();
+            if (surv) { S[IDX(pos)] = s_new; K[IDX(pos)] = k_new; }
+        }
+        L = base;
+        __syncwarp();
+    }
+    // ---- surviving known parts, in order -------------------------------------------------------------------
+    uint32_t c = whole ? 1u : 0u;
+    {
+        const uint32_t rowsW = __reduce_max_sync(FULL, (L + G - 1u) >> LG);
+        for (uint32_t r = 0; r < rowsW; ++r) {
+            const uint32_t i = (r << LG) + g;
+            const uint32_t sy = i < L ? S[r * 32u + lane] : SPL_UNK_BASE;
+            const bool keep = sy < SPL_UNK_BASE;                                    // unknown bytes produce no id (bpe.rs:187-191)
+            const uint32_t b = (__ballot_sync(FULL, keep) >> gsh) & GM;
+            if (keep) out[c + __popc(b & ((1u << g) - 1u))] = sy;
+            c += __popc(b);
+        }
+    }
+#undef IDX
+#undef NEXT_MASK
+#undef PREV_MASK
+    return c;
+}
+
 template <uint32_t LG>
 __device__ void bpe_class(const SplWork& w, uint32_t c, uint32_t* reg, uint32_t gwarp, uint32_t nwarps) {
     const uint32_t n = w.counters[SPL_CTR_CLS + c];
@@ -612,7 +834,9 @@ __device__ void bpe_class(const SplWork& w, uint32_t c, uint32_t* reg, uint32_t 
         uint64_t* slot = &w.mlist[w.ml_base[c] + (valid ? pi : 0u)];
         const uint64_t e = *slot;
         const uint32_t gpos = (uint32_t)e, len = (uint32_t)(e >> 32) & SPL_ML_LEN_SAT;
-        const uint32_t cnt = bpe_group<LG>(reg, valid, w.T, w.text + gpos, len, w.pool + gpos);
+        uint32_t cnt;
+        if constexpr (LG == 0u) cnt = bpe_lane(reg, valid, w.T, w.text + gpos, len, w.pool + gpos);
+        else cnt = bpe_group<LG>(reg, valid, w.T, w.text + gpos, len, w.pool + gpos);
         if (valid && (lane & ((1u << LG) - 1u)) == 0) bpe_finish(w, slot, gpos, cnt);
         __syncwarp();
     }
@@ -695,7 +919,7 @@ __device__ uint32_t bpe_piece_block(uint64_t* red, uint32_t* s_bcast, const SplT
 
 #define BPE_SMEM_BYTES ((SPL_BPE_THREADS / 32) * BG_WORDS * 4)
 
-__global__ void __launch_bounds__(SPL_BPE_THREADS, 5) k_bpe(SplWork w) {
+__global__ void __launch_bounds__(SPL_BPE_THREADS, 4) k_bpe(SplWork w) {
     extern __shared__ __align__(16) uint32_t bpe_smem[];
     __shared__ uint32_t s_bcast, s_off;
     const SplTables* T = w.T;
@@ -982,7 +1206,7 @@ void spl_launch_encode_stage(const SplWork& w, int num_sms, cudaStream_t stream,
         k_probe<<<w.n_tiles, SPL_THREADS, 0, stream>>>(w);
         mark(ctx, "k_probe");
     }
-    k_bpe<<<(uint32_t)num_sms * 5u, SPL_BPE_THREADS, BPE_SMEM_BYTES, stream>>>(w);
+    k_bpe<<<(uint32_t)num_sms * 4u, SPL_BPE_THREADS, BPE_SMEM_BYTES, stream>>>(w);
     mark(ctx, "k_bpe");
     k_chunk_scan<<<1, 1024, 0, stream>>>(w);
     mark(ctx, "k_chunk_scan");
