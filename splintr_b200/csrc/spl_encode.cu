@@ -460,7 +460,8 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe_rest(SplWork w) {
 // 32..512 bytes take ~3 rounds instead of ~80 merges steps, runs of one character ~6 instead of ~120.
 // ------------------------------------------------------------------------------------------
 #define BG_RANK_NONE 0x1FFFFFu
-#define BG_WORDS     3424u                              // words per warp: S[1024] + K[1024] + X[1024] + worklist (256) + 3 x 32
+#define BG_ARR       1056u                              // words per array: 1024 parts + one pad word per 32
+#define BG_WORDS     (3u * BG_ARR + 256u + 64u)         // words per warp: S + K + X + worklist (512 x u16) + 2 x 32
 
 // whole-piece probe of a piece in global memory by ONE thread (vocabularies with keys beyond 128 bytes only)
 __device__ uint32_t lookupL_serial_g(const SplTables* T, const uint8_t* __restrict__ tx, uint32_t len) {
@@ -612,28 +613,39 @@ __device__ uint32_t bpe_lane(uint32_t* reg, const bool valid, const SplTables* T
     return c;
 }
 
+// Bit tricks of a round.  A lane's masks hold its B consecutive parts, bit j = part e0 + j.
+// runs_above(D, st): the runs of D that start right above the bits of st (the addition ripples through exactly those).
+__device__ __forceinline__ uint32_t runs_above(uint32_t D, uint32_t st) { return D & ~(D + (st << 1)); }
+// m along upward slopes: D = slope bits, V = valleys (m = 1); a run that starts at bit 0 continues the slope of the
+// lane before, whose last part has m = cin.  m alternates with the distance from the valley.
+__device__ __forceinline__ uint32_t slope_m(uint32_t D, uint32_t V, uint32_t cin, uint32_t first /* bit where a foreign run starts */) {
+    const uint32_t E = 0x55555555u;
+    const uint32_t run0 = D & ~(D + first);                                        // run from `first` upwards (empty if D lacks that bit)
+    const uint32_t P = (first & E) ? ~E : E;                                       // positions at an even distance from the part below `first`
+    return (runs_above(D, V & E) & E) | (runs_above(D, V & ~E) & ~E) | (run0 & (cin ? P : ~P));
+}
+
 // All 32 lanes call this; lane = p * G + g works on piece p of the warp's task (valid: the piece exists), G = 1 << LG.
 // Returns the id count in every lane of the group; ids go to out[0 ..] in order.
 template <uint32_t LG>
 __device__ uint32_t bpe_group(uint32_t* reg, const bool valid, const SplTables* T,
                               const uint8_t* __restrict__ tx, const uint32_t n, uint32_t* __restrict__ out) {
     constexpr uint32_t G = 1u << LG;
-    constexpr uint32_t GM = G == 32u ? 0xFFFFFFFFu : (1u << G) - 1u;
     constexpr uint32_t NONE = BG_RANK_NONE;
     const uint32_t lane = threadIdx.x & 31u, g = lane & (G - 1u), gsh = lane & ~(G - 1u);
     uint32_t* S = reg;                                             // symbols of the live parts
-    uint32_t* K = reg + 1024;                                      // rank of (part i, part i + 1)
-    uint32_t* X = reg + 2048;                                      // ranks looked up in the current round
-    uint16_t* WL = reinterpret_cast<uint16_t*>(reg + 3072);        // worklist of the round: word index of every m-pair (<= 512)
-    uint32_t* MW = reg + 3328;                                     // per lane: its m mask, its piece's part count, theta of its group
-    uint32_t* LW = reg + 3360;
-    uint32_t* TH = reg + 3392;
+    uint32_t* K = reg + BG_ARR;                                    // rank of (part e, part e + 1)
+    uint32_t* X = reg + 2u * BG_ARR;                               // ranks looked up in the current round
+    uint16_t* WL = reinterpret_cast<uint16_t*>(reg + 3u * BG_ARR); // worklist of the round: every m-pair of the warp (<= 512)
+    uint32_t* LW = reg + 3u * BG_ARR + 256u;                       // per lane: part count of its piece | B << 16
+    uint32_t* TH = LW + 32u;                                       // per group (at its first lane): theta
     const uint64_t* __restrict__ ptab = T->pair;
     const uint32_t plog = T->pair_log2, pmask = (1u << plog) - 1u;
-#define IDX(e) ((((e) >> LG) << 5) + gsh + ((e) & (G - 1u)))
-    // bit r of a lane's mask = its part of row r; the same mask of part i + d sits d lanes on (wrapping into the next row)
-#define NEXT_MASK(v, d) (__shfl_sync(FULL, (v), gsh + ((g + (d)) & (G - 1u))) >> ((g + (d)) >> LG))
-#define PREV_MASK(v)    (__shfl_sync(FULL, (v), gsh + ((g + G - 1u) & (G - 1u))) << (g ? 0u : 1u))
+    // part e of the group that starts at lane gs: one pad word per 32 parts, so lanes that walk their blocks in step hit 32 banks
+#define ADR(gs, e) ((gs) * 33u + (e) + ((e) >> 5))
+#define AD(e) ADR(gsh, e)
+    // inclusive sum over the lanes of the group
+#define GROUP_SCAN(v) _Pragma("unroll") for (uint32_t o_ = 1; o_ < G; o_ <<= 1) { const uint32_t t_ = __shfl_up_sync(FULL, (v), o_); if (g >= o_) (v) += t_; }
     bool act = valid;
     {
         // whole-piece probe of pieces beyond the probe halo (k_probe has already tried the shorter ones)
@@ -647,36 +659,37 @@ __device__ uint32_t bpe_group(uint32_t* reg, const bool valid, const SplTables* 
     }
     const bool whole = valid && !act;
     uint32_t L = act ? n : 0u;                                     // live parts (uniform in the group)
+    uint32_t B = max(2u, (L + G - 1u) >> LG);                      // parts per lane: lane g owns [g * B, g * B + B)
     {
-        const uint32_t rows = (L + G - 1u - g) >> LG;             // parts of this lane: i = g + it * G, at word it * 32 + lane
-        // ---- every byte becomes a part (two passes, each unrolled, so that several loads are in flight together)
+        const uint32_t e0 = g * B, nv = e0 < L ? min(B, L - e0) : 0u;
+        // ---- every byte becomes a part
 #pragma unroll 4
-        for (uint32_t it = 0; it < rows; ++it) S[it * 32u + lane] = __ldg(tx + g + (it << LG));
+        for (uint32_t j = 0; j < nv; ++j) S[AD(e0 + j)] = __ldg(tx + e0 + j);
 #pragma unroll 4
-        for (uint32_t it = 0; it < rows; ++it) S[it * 32u + lane] = T->byte_sym[S[it * 32u + lane]];
+        for (uint32_t j = 0; j < nv; ++j) S[AD(e0 + j)] = T->byte_sym[S[AD(e0 + j)]];
         __syncwarp();
         // ---- ranks of the adjacent pairs, two independent probes in flight per lane
-        for (uint32_t it = 0; it < rows; it += 2) {
+        for (uint32_t j = 0; j < nv; j += 2) {
             PairBucket bk[2];
             uint64_t key[2];
             uint32_t bb[2];
 #pragma unroll
             for (uint32_t q = 0; q < 2; ++q) {
-                const uint32_t e = g + ((it + q) << LG);
-                if (e + 1 < L) {
-                    key[q] = spl_pair_key(S[(it + q) * 32u + lane], S[IDX(e + 1)]);
+                const uint32_t e = e0 + j + q;
+                if (j + q < nv && e + 1 < L) {
+                    key[q] = spl_pair_key(S[AD(e)], S[AD(e + 1)]);
                     bb[q] = spl_pair_hash(key[q], plog);
                     bk[q] = pair_bucket_load(ptab, bb[q]);
                 }
             }
 #pragma unroll
             for (uint32_t q = 0; q < 2; ++q) {
-                const uint32_t e = g + ((it + q) << LG);
-                if (e < L) {
+                const uint32_t e = e0 + j + q;
+                if (j + q < nv) {
                     uint32_t r = SPL_RANK_NONE;
                     if (e + 1 < L)
                         while (pair_bucket_match(bk[q], key[q], r) == 2) { bb[q] = (bb[q] + 1) & pmask; bk[q] = pair_bucket_load(ptab, bb[q]); }
-                    K[(it + q) * 32u + lane] = r & NONE;
+                    K[AD(e)] = r & NONE;
                 }
             }
         }
@@ -684,137 +697,134 @@ __device__ uint32_t bpe_group(uint32_t* reg, const bool valid, const SplTables* 
     }
     // ---- merge rounds ------------------------------------------------------------------------------------
     for (;;) {
-        const uint32_t rowsW = __reduce_max_sync(FULL, (L + G - 1u) >> LG);        // rows of the longest piece of the warp
-        // (1) every pair against its neighbours: valley / slope to the left / slope to the right / peak
-        uint32_t fV = 0, fDL = 0, fDR = 0, fPK = 0, gmin = 0xFFFFFFFFu;
-        for (uint32_t r = 0; r < rowsW; ++r) {
-            const uint32_t i = (r << LG) + g;
-            if (i + 1 < L) {
-                const uint32_t kc = K[r * 32u + lane];
-                if (kc != NONE) {
-                    const uint32_t kl = i ? K[IDX(i - 1)] : NONE, kr = i + 2 < L ? K[IDX(i + 1)] : NONE;
-                    const bool lt = kl <= kc, rt = kr < kc;                         // the neighbour merges first (left wins ties)
-                    const uint32_t bit = 1u << r;
-                    if (lt) { if (rt) fPK |= bit; else fDL |= bit; } else { if (rt) fDR |= bit; else fV |= bit; }
-                    gmin = min(gmin, (kc << 11) | i);
+        const uint32_t e0 = g * B, nv = e0 < L ? min(B, L - e0) : 0u;
+        // (1) every pair of the lane's block against its neighbours
+        uint32_t LV = 0, LT = 0, RT = 0, gmin = 0xFFFFFFFFu;
+        {
+            uint32_t prev = (e0 && e0 < L) ? K[AD(e0 - 1u)] : NONE, cur = e0 + 1u < L ? K[AD(e0)] : NONE;
+            for (uint32_t j = 0; j < nv; ++j) {
+                const uint32_t e = e0 + j, nxt = e + 2u < L ? K[AD(e + 1u)] : NONE;
+                if (cur != NONE) {
+                    const uint32_t bit = 1u << j;
+                    LV |= bit;
+                    if (prev <= cur) LT |= bit;                                      // the left neighbour merges first (it wins ties)
+                    if (nxt < cur) RT |= bit;
+                    gmin = min(gmin, (cur << 11) | e);
                 }
+                prev = cur; cur = nxt;
             }
         }
 #pragma unroll
         for (uint32_t o = G >> 1; o; o >>= 1) gmin = min(gmin, __shfl_xor_sync(FULL, gmin, o));
         if (!__any_sync(FULL, gmin != 0xFFFFFFFFu)) break;                          // no pair with a rank anywhere in the warp
-        // (2) m: valleys merge; along a slope m alternates with the distance from its valley
-        uint32_t m = fV;
-        if (__any_sync(FULL, fDL != 0u)) {
-            uint32_t carry = 0;                                                     // m of the last part of the row before
-            for (uint32_t r = 0; r < rowsW; ++r) {
-                const uint32_t bit = 1u << r;
-                const uint32_t bDL = (__ballot_sync(FULL, (fDL & bit) != 0u) >> gsh) & GM;
-                if (fDL & bit) {
-                    const uint32_t below = ~bDL & ((1u << g) - 1u);                 // nearest part to the left that is not on the slope: its valley
-                    const uint32_t mv = below ? ((g - (31u - __clz(below))) & 1u) ^ 1u : carry ^ ((g + 1u) & 1u);
-                    if (mv) m |= bit;
-                }
-                carry = (__shfl_sync(FULL, m, gsh + G - 1u) >> r) & 1u;
-            }
-        }
-        if (__any_sync(FULL, fDR != 0u)) {
-            uint32_t carry = 0;                                                     // m of the first part of the row after
-            for (uint32_t r = rowsW; r-- > 0;) {
-                const uint32_t bit = 1u << r;
-                const uint32_t bDR = (__ballot_sync(FULL, (fDR & bit) != 0u) >> gsh) & GM;
-                if (fDR & bit) {
-                    const uint32_t above = ~bDR & GM & ~((2u << g) - 1u);
-                    const uint32_t mv = above ? (((uint32_t)__ffs(above) - 1u - g) & 1u) ^ 1u : carry ^ ((G - g) & 1u);
-                    if (mv) m |= bit;
-                }
-                carry = (__shfl_sync(FULL, m, gsh) >> r) & 1u;
-            }
-        }
+        const uint32_t fV = LV & ~LT & ~RT, fDL = LV & LT & ~RT, fDR = LV & RT & ~LT, fPK = LV & LT & RT;
+        // (2) m: valleys merge; along a slope m alternates with the distance from its valley; slopes that cross into the
+        // next lane's block take that lane's boundary bit, until nothing changes (one extra pass per lane a slope spans)
+        uint32_t m, cin = 0, cin2 = 0;
         {
-            const uint32_t mL = PREV_MASK(m), mR = NEXT_MASK(m, 1u);
-            m |= fPK & ~mL & ~mR;                                                   // a peak merges iff neither neighbour does
+            const uint32_t rDR = __brev(fDR), rV = __brev(fV), firstR = 1u << (32u - B);
+            for (;;) {
+                m = fV | slope_m(fDL, fV, cin, 1u) | __brev(slope_m(rDR, rV, cin2, firstR));
+                const uint32_t up = __shfl_up_sync(FULL, m, 1), dn = __shfl_down_sync(FULL, m, 1);
+                const uint32_t ncin = g ? (up >> (B - 1u)) & 1u : 0u, ncin2 = g + 1u < G ? dn & 1u : 0u;
+                const bool ch = (ncin != cin && (fDL & 1u)) || (ncin2 != cin2 && ((fDR >> (B - 1u)) & 1u));
+                cin = ncin; cin2 = ncin2;
+                if (!__any_sync(FULL, ch)) break;
+            }
+            m |= fPK & ~((m << 1) | cin) & ~((m >> 1) | (cin2 << (B - 1u)));      // a peak merges iff neither neighbour does
         }
         // (3) the ranks the merges can create; theta = their minimum.  The m-pairs of the whole warp go through a
-        // worklist so that all 32 lanes probe (a lane holds anything from 0 to rows / 2 m-pairs of its own).
+        // worklist so that all 32 lanes probe.
         {
+            const uint32_t dn = __shfl_down_sync(FULL, m, 1);
+            const uint32_t m2 = (uint32_t)(((uint64_t)m | ((uint64_t)(g + 1u < G ? dn : 0u) << B)) >> 2);   // m of the pair two to the right
             const uint32_t cntm = __popc(m);
             uint32_t off = cntm;
 #pragma unroll
             for (uint32_t o = 1; o < 32u; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, off, o); if (lane >= o) off += t; }
             const uint32_t total = __shfl_sync(FULL, off, 31);
             off -= cntm;
-            for (uint32_t mm = m; mm; mm &= mm - 1u) WL[off++] = (uint16_t)((((uint32_t)__ffs(mm) - 1u) << 5) | lane);
-            MW[lane] = m; LW[lane] = L; TH[lane] = NONE;
+            for (uint32_t mm = m; mm; mm &= mm - 1u) {
+                const uint32_t j = (uint32_t)__ffs(mm) - 1u;
+                WL[off++] = (uint16_t)(j | (lane << 5) | (((m2 >> j) & 1u) << 10));
+            }
+            LW[lane] = L | (B << 16);
+            TH[lane] = NONE;
             __syncwarp();
             for (uint32_t q = lane; q < total; q += 32u) {
-                const uint32_t wv = WL[q], r = wv >> 5, ln = wv & 31u, g2 = ln & (G - 1u), gs2 = ln & ~(G - 1u);
-                const uint32_t i = (r << LG) + g2, L2 = LW[ln];
-#define IDX2(e) ((((e) >> LG) << 5) + gs2 + ((e) & (G - 1u)))
-                const uint32_t tm = K[wv];                                          // merged id == its rank
-                const bool hasL = i > 0u, hasR = i + 2u < L2;
-                const bool hasC = hasR && ((MW[gs2 + ((g2 + 2u) & (G - 1u))] >> (r + ((g2 + 2u) >> LG))) & 1u);
-                const uint32_t sl = hasL ? S[IDX2(i - 1u)] : 0u, sr = hasR ? S[IDX2(i + 2u)] : 0u, tc = hasC ? K[IDX2(i + 2u)] : 0u;
+                const uint32_t wv = WL[q], ln = (wv >> 5) & 31u, g2 = ln & (G - 1u), gs2 = ln & ~(G - 1u), info = LW[ln];
+                const uint32_t L2 = info & 0xFFFFu, e = g2 * (info >> 16) + (wv & 31u);
+                const uint32_t tm = K[ADR(gs2, e)];                                 // merged id == its rank
+                const bool hasL = e > 0u, hasR = e + 2u < L2, hasC = (wv >> 10) & 1u;
+                const uint32_t sl = hasL ? S[ADR(gs2, e - 1u)] : 0u, sr = hasR ? S[ADR(gs2, e + 2u)] : 0u, tc = hasC ? K[ADR(gs2, e + 2u)] : 0u;
                 uint32_t ra, rb, rc;
                 pair_lookup3(ptab, plog, hasL, sl, tm, hasR, tm, sr, hasC, tm, tc, ra, rb, rc);
                 ra &= NONE; rb &= NONE; rc &= NONE;
                 atomicMin(&TH[gs2], min(ra, min(rb, rc)));
-                X[wv] = ra | (rc << 21);                                            // rc: low 11 bits here, high 10 bits in the next word
-                X[IDX2(i + 1u)] = rb | ((rc >> 11) << 21);
-#undef IDX2
+                X[ADR(gs2, e)] = ra | (rc << 21);                                   // rc: low 11 bits here, high 10 bits in the next word
+                X[ADR(gs2, e + 1u)] = rb | ((rc >> 11) << 21);
             }
             __syncwarp();
         }
-        const uint32_t theta = TH[gsh];
         // (4) commit: m-pairs below theta, and the global minimum in any case
+        const uint32_t theta = TH[gsh];
         uint32_t cm = 0;
         for (uint32_t mm = m; mm; mm &= mm - 1u) {
-            const uint32_t r = (uint32_t)__ffs(mm) - 1u, kc = K[r * 32u + lane];
-            if (kc < theta || ((kc << 11) | ((r << LG) + g)) == gmin) cm |= 1u << r;
+            const uint32_t j = (uint32_t)__ffs(mm) - 1u, kc = K[AD(e0 + j)];
+            if (kc < theta || ((kc << 11) | (e0 + j)) == gmin) cm |= 1u << j;
         }
-        __syncwarp();
-        // (5) compact the parts in place, row by row (a part moves to an index <= its own)
-        const uint32_t cmL = PREV_MASK(cm), cmR1 = NEXT_MASK(cm, 1u), cmR2 = NEXT_MASK(cm, 2u);
-        uint32_t base = 0;
-        for (uint32_t r = 0; r < rowsW; ++r) {
-            const uint32_t i = (r << LG) + g;
-            const bool surv = i < L && !((cmL >> r) & 1u);                          // the right part of a committed pair is absorbed
-            uint32_t s_new = 0, k_new = NONE;
-            if (surv) {
-                if ((cm >> r) & 1u) {
-                    const uint32_t x0 = X[r * 32u + lane], x1 = X[IDX(i + 1u)];
-                    s_new = K[r * 32u + lane];
-                    k_new = ((cmR2 >> r) & 1u) ? ((x0 >> 21) | ((x1 >> 21) << 11)) : (x1 & NONE);
+        // (5) new symbol and rank of every surviving part, in place; then the parts move to their new index through
+        // the free array (the three arrays swap roles)
+        uint32_t surv;
+        {
+            const uint32_t up = __shfl_up_sync(FULL, cm, 1), dn = __shfl_down_sync(FULL, cm, 1);
+            const uint64_t cw = (uint64_t)cm | ((uint64_t)(g + 1u < G ? dn : 0u) << B);
+            const uint32_t cm1 = (uint32_t)(cw >> 1), cm2 = (uint32_t)(cw >> 2);
+            const uint32_t ex = nv >= 32u ? 0xFFFFFFFFu : (1u << nv) - 1u;
+            surv = ex & ~((cm << 1) | (g ? (up >> (B - 1u)) & 1u : 0u));            // the right part of a committed pair is absorbed
+            for (uint32_t mm = surv & (cm | cm1); mm; mm &= mm - 1u) {
+                const uint32_t j = (uint32_t)__ffs(mm) - 1u, e = e0 + j, x1 = X[AD(e + 1u)];
+                if ((cm >> j) & 1u) {
+                    const uint32_t x0 = X[AD(e)];
+                    S[AD(e)] = K[AD(e)];
+                    K[AD(e)] = ((cm2 >> j) & 1u) ? ((x0 >> 21) | ((x1 >> 21) << 11)) : (x1 & NONE);
                 } else {
-                    s_new = S[r * 32u + lane];
-                    k_new = ((cmR1 >> r) & 1u) ? (X[IDX(i + 1u)] & NONE) : (i + 1u < L ? K[r * 32u + lane] : NONE);
+                    K[AD(e)] = x1 & NONE;
                 }
             }
-            const uint32_t b = (__ballot_sync(FULL, surv) >> gsh) & GM;
-            const uint32_t pos = base + __popc(b & ((1u << g) - 1u));
-            base += __popc(b);
-            __syncwarp();
-            if (surv) { S[IDX(pos)] = s_new; K[IDX(pos)] = k_new; }
         }
-        L = base;
         __syncwarp();
+        uint32_t lb = __popc(surv);
+        GROUP_SCAN(lb);
+        const uint32_t newL = __shfl_sync(FULL, lb, gsh + G - 1u);
+        lb -= __popc(surv);
+        {
+            uint32_t d = lb;
+            for (uint32_t mm = surv; mm; mm &= mm - 1u, ++d) X[AD(d)] = S[AD(e0 + (uint32_t)__ffs(mm) - 1u)];
+            __syncwarp();
+            d = lb;
+            for (uint32_t mm = surv; mm; mm &= mm - 1u, ++d) S[AD(d)] = K[AD(e0 + (uint32_t)__ffs(mm) - 1u)];
+            __syncwarp();
+            uint32_t* t = K; K = S; S = X; X = t;
+        }
+        L = newL;
+        B = max(2u, (L + G - 1u) >> LG);
     }
     // ---- surviving known parts, in order -------------------------------------------------------------------
     uint32_t c = whole ? 1u : 0u;
     {
-        const uint32_t rowsW = __reduce_max_sync(FULL, (L + G - 1u) >> LG);
-        for (uint32_t r = 0; r < rowsW; ++r) {
-            const uint32_t i = (r << LG) + g;
-            const uint32_t sy = i < L ? S[r * 32u + lane] : SPL_UNK_BASE;
-            const bool keep = sy < SPL_UNK_BASE;                                    // unknown bytes produce no id (bpe.rs:187-191)
-            const uint32_t b = (__ballot_sync(FULL, keep) >> gsh) & GM;
-            if (keep) out[c + __popc(b & ((1u << g) - 1u))] = sy;
-            c += __popc(b);
-        }
+        const uint32_t e0 = g * B, nv = e0 < L ? min(B, L - e0) : 0u;
+        uint32_t keep = 0;
+        for (uint32_t j = 0; j < nv; ++j) keep |= (S[AD(e0 + j)] < SPL_UNK_BASE ? 1u : 0u) << j;   // unknown bytes produce no id (bpe.rs:187-191)
+        uint32_t lb = __popc(keep);
+        GROUP_SCAN(lb);
+        c += __shfl_sync(FULL, lb, gsh + G - 1u);
+        uint32_t d = lb - __popc(keep) + (whole ? 1u : 0u);
+        for (uint32_t mm = keep; mm; mm &= mm - 1u, ++d) out[d] = S[AD(e0 + (uint32_t)__ffs(mm) - 1u)];
     }
-#undef IDX
-#undef NEXT_MASK
-#undef PREV_MASK
+#undef ADR
+#undef AD
+#undef GROUP_SCAN
     return c;
 }
 
