@@ -460,6 +460,7 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe_rest(SplWork w) {
 // 32..512 bytes take ~3 rounds instead of ~80 merges steps, runs of one character ~6 instead of ~120.
 // ------------------------------------------------------------------------------------------
 #define BG_RANK_NONE 0x1FFFFFu
+#define SPL_BPE_WIN_CLS 3u                             // pieces beyond 64 bytes: windowed rounds (measured: cfg4 2.3 ms at 3, 2.6 at 4, 3.9 at 5)
 #define BG_ARR       1056u                              // words per array: 1024 parts + one pad word per 32
 #define BG_WORDS     (3u * BG_ARR + 256u + 64u)         // words per warp: S + K + X + worklist (512 x u16) + 2 x 32
 
@@ -494,16 +495,21 @@ __device__ __forceinline__ void bpe_finish(const SplWork& w, uint64_t* slot, uin
     }
 }
 
-// Short pieces (<= 32 bytes, classes 0 and 1): ONE lane per piece runs the loop of bpe.rs:119-167 as it stands -- a
-// piece of a few parts takes fewer instructions that way than a round of the windowed form below costs.
-// The parts form a doubly linked list (bpe.rs:42-54) in the lane's column of the warp's shared memory:
+// Short pieces (classes below SplBpeCfg's window class): the loop of bpe.rs:119-167 as it stands, one merge per step,
+// by a group of G = 2^LG lanes (one lane up to 32 bytes) -- a piece of a few dozen parts takes fewer instructions that
+// way than the rounds of the windowed form below cost.
+// The parts form a doubly linked list (bpe.rs:42-54) in the warp's shared memory:
 //     A[e] = symbol:21 | next:11     R[e] = rank of (part e, next part):21 | e:11     P[e] = prev (u16)
 // R doubles as the scan key: the minimum over R is the lowest rank at the leftmost position (bpe.rs:133).
-// All 32 lanes call this (valid: the lane has a piece).  Returns the id count; ids go to out[0 ..] in order.
+// Part e of the piece of group p sits at word (e / G) * 32 + p * G + e % G, so the strided scan of a group is conflict free.
+// One merge = strided min-scan of the ranks, a shuffle reduction inside the group, the splice and the two re-ranks
+// (bpe.rs:146-166), done by lanes 0 and 1 of the group.
+// All 32 lanes call this (valid: the group has a piece).  Returns the id count in lane g == 0; ids go to out[0 ..] in order.
 #define BG_LINK_NONE 0x7FFu
-__device__ uint32_t bpe_lane(uint32_t* reg, const bool valid, const SplTables* T,
-                              const uint8_t* __restrict__ tx, const uint32_t n, uint32_t* __restrict__ out) {
-    constexpr uint32_t LG = 0u, G = 1u;
+template <uint32_t LG>
+__device__ uint32_t bpe_seq(uint32_t* reg, const bool valid, const SplTables* T,
+                            const uint8_t* __restrict__ tx, const uint32_t n, uint32_t* __restrict__ out) {
+    constexpr uint32_t G = 1u << LG;
     const uint32_t lane = threadIdx.x & 31u, p = lane >> LG, g = lane & (G - 1u);
     uint32_t* A = reg;                                             // symbol:21 | next:11
     uint32_t* R = reg + 1024;                                      // rank:21 | own position:11  (the scan key)
@@ -701,9 +707,10 @@ __device__ uint32_t bpe_group(uint32_t* reg, const bool valid, const SplTables* 
         // (1) every pair of the lane's block against its neighbours
         uint32_t LV = 0, LT = 0, RT = 0, gmin = 0xFFFFFFFFu;
         {
-            uint32_t prev = (e0 && e0 < L) ? K[AD(e0 - 1u)] : NONE, cur = e0 + 1u < L ? K[AD(e0)] : NONE;
+            // (K[L - 1] is BG_RANK_NONE at all times, so the walk needs no bound checks: what lies beyond is never used)
+            uint32_t prev = (e0 && e0 < L) ? K[AD(e0 - 1u)] : NONE, cur = e0 < L ? K[AD(e0)] : NONE;
             for (uint32_t j = 0; j < nv; ++j) {
-                const uint32_t e = e0 + j, nxt = e + 2u < L ? K[AD(e + 1u)] : NONE;
+                const uint32_t e = e0 + j, nxt = K[AD(e + 1u)];
                 if (cur != NONE) {
                     const uint32_t bit = 1u << j;
                     LV |= bit;
@@ -828,7 +835,7 @@ __device__ uint32_t bpe_group(uint32_t* reg, const bool valid, const SplTables* 
     return c;
 }
 
-template <uint32_t LG>
+template <uint32_t LG, bool WINDOWED>
 __device__ void bpe_class(const SplWork& w, uint32_t c, uint32_t* reg, uint32_t gwarp, uint32_t nwarps) {
     const uint32_t n = w.counters[SPL_CTR_CLS + c];
     if (!n) return;
@@ -845,8 +852,8 @@ __device__ void bpe_class(const SplWork& w, uint32_t c, uint32_t* reg, uint32_t 
         const uint64_t e = *slot;
         const uint32_t gpos = (uint32_t)e, len = (uint32_t)(e >> 32) & SPL_ML_LEN_SAT;
         uint32_t cnt;
-        if constexpr (LG == 0u) cnt = bpe_lane(reg, valid, w.T, w.text + gpos, len, w.pool + gpos);
-        else cnt = bpe_group<LG>(reg, valid, w.T, w.text + gpos, len, w.pool + gpos);
+        if constexpr (WINDOWED) cnt = bpe_group<LG>(reg, valid, w.T, w.text + gpos, len, w.pool + gpos);
+        else cnt = bpe_seq<LG>(reg, valid, w.T, w.text + gpos, len, w.pool + gpos);
         if (valid && (lane & ((1u << LG) - 1u)) == 0) bpe_finish(w, slot, gpos, cnt);
         __syncwarp();
     }
@@ -929,22 +936,37 @@ __device__ uint32_t bpe_piece_block(uint64_t* red, uint32_t* s_bcast, const SplT
 
 #define BPE_SMEM_BYTES ((SPL_BPE_THREADS / 32) * BG_WORDS * 4)
 
-__global__ void __launch_bounds__(SPL_BPE_THREADS, 4) k_bpe(SplWork w) {
+// k_bpe_long: the classes from win_cls up by windowed rounds (13.6 KiB of shared memory per warp), then the huge class.
+// k_bpe: the classes below win_cls, one merge per step (10 KiB per warp: five blocks per SM -- those pieces wait on
+// dependent table probes, so resident warps are what counts).
+#define BPE_SEQ_WORDS 2560u                            // A[1024] + R[1024] + P[1024 x u16]
+#define BPE_SEQ_SMEM_BYTES ((SPL_BPE_THREADS / 32) * BPE_SEQ_WORDS * 4)
+__global__ void __launch_bounds__(SPL_BPE_THREADS, 5) k_bpe(SplWork w, const uint32_t win_cls) {
+    extern __shared__ __align__(16) uint32_t bpe_smem[];
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t gwarp = blockIdx.x * (SPL_BPE_THREADS / 32) + warp, nwarps = gridDim.x * (SPL_BPE_THREADS / 32);
+    uint32_t* reg = bpe_smem + warp * BPE_SEQ_WORDS;
+    // the longest pieces first, so that the tail of the kernel is short work
+    if (win_cls > 5u) bpe_class<4, false>(w, 5, reg, gwarp, nwarps);
+    if (win_cls > 4u) bpe_class<3, false>(w, 4, reg, gwarp, nwarps);
+    if (win_cls > 3u) bpe_class<2, false>(w, 3, reg, gwarp, nwarps);
+    if (win_cls > 2u) bpe_class<1, false>(w, 2, reg, gwarp, nwarps);
+    bpe_class<0, false>(w, 1, reg, gwarp, nwarps);
+    bpe_class<0, false>(w, 0, reg, gwarp, nwarps);
+}
+
+__global__ void __launch_bounds__(SPL_BPE_THREADS, 4) k_bpe_long(SplWork w, const uint32_t win_cls) {
     extern __shared__ __align__(16) uint32_t bpe_smem[];
     __shared__ uint32_t s_bcast, s_off;
     const SplTables* T = w.T;
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     const uint32_t gwarp = blockIdx.x * (SPL_BPE_THREADS / 32) + warp, nwarps = gridDim.x * (SPL_BPE_THREADS / 32);
     uint32_t* reg = bpe_smem + warp * BG_WORDS;
-
-    // ---- classes merged by lane groups: the longest pieces first, so that the tail of the kernel is short work ------
-    bpe_class<5>(w, 6, reg, gwarp, nwarps);
-    bpe_class<4>(w, 5, reg, gwarp, nwarps);
-    bpe_class<3>(w, 4, reg, gwarp, nwarps);
-    bpe_class<2>(w, 3, reg, gwarp, nwarps);
-    bpe_class<1>(w, 2, reg, gwarp, nwarps);
-    bpe_class<0>(w, 1, reg, gwarp, nwarps);
-    bpe_class<0>(w, 0, reg, gwarp, nwarps);
+    bpe_class<5, true>(w, 6, reg, gwarp, nwarps);
+    if (win_cls <= 5u) bpe_class<4, true>(w, 5, reg, gwarp, nwarps);
+    if (win_cls <= 4u) bpe_class<3, true>(w, 4, reg, gwarp, nwarps);
+    if (win_cls <= 3u) bpe_class<2, true>(w, 3, reg, gwarp, nwarps);
+    if (win_cls <= 2u) bpe_class<1, true>(w, 2, reg, gwarp, nwarps);
     // ---- huge class: whole block, global scratch ----------------------------------------------------
     {
         const uint32_t n = w.counters[SPL_CTR_CLS + SPL_NCLS - 1];
@@ -1195,7 +1217,8 @@ __global__ void __launch_bounds__(SPL_THREADS, 8) k_emit(SplWork w) {
 // host side
 // ------------------------------------------------------------------------------------------
 void spl_encode_init() {
-    cudaFuncSetAttribute(k_bpe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BPE_SMEM_BYTES);
+    cudaFuncSetAttribute(k_bpe_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BPE_SMEM_BYTES);
+    cudaFuncSetAttribute(k_bpe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BPE_SEQ_SMEM_BYTES);
     cudaFuncSetAttribute(k_probe, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
     cudaFuncSetAttribute(k_probe_rest, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
     cudaFuncSetAttribute(k_pretok_probe, cudaFuncAttributePreferredSharedMemoryCarveout, 75);
@@ -1216,7 +1239,11 @@ void spl_launch_encode_stage(const SplWork& w, int num_sms, cudaStream_t stream,
         k_probe<<<w.n_tiles, SPL_THREADS, 0, stream>>>(w);
         mark(ctx, "k_probe");
     }
-    k_bpe<<<(uint32_t)num_sms * 4u, SPL_BPE_THREADS, BPE_SMEM_BYTES, stream>>>(w);
+    // first length class merged by windowed rounds (measured crossover; SPL_BPE_WIN_CLS overrides it for experiments)
+    static const uint32_t win_cls = [] { const char* e = getenv("SPL_BPE_WIN_CLS"); return e ? (uint32_t)atoi(e) : SPL_BPE_WIN_CLS; }();
+    k_bpe_long<<<(uint32_t)num_sms * 4u, SPL_BPE_THREADS, BPE_SMEM_BYTES, stream>>>(w, win_cls);
+    mark(ctx, "k_bpe_long");
+    k_bpe<<<(uint32_t)num_sms * 5u, SPL_BPE_THREADS, BPE_SEQ_SMEM_BYTES, stream>>>(w, win_cls);
     mark(ctx, "k_bpe");
     k_chunk_scan<<<1, 1024, 0, stream>>>(w);
     mark(ctx, "k_chunk_scan");
