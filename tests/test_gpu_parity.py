@@ -153,6 +153,26 @@ def test_cfg5_cjk_deepseek(toks):
     _check_packed(toks("deepseek_v3"), c_oracle("deepseek_v3"), d, o)
 
 
+@pytest.mark.parametrize("name", ["cl100k_base", "o200k_base", "llama3", "deepseek_v3"])
+def test_merge_rounds_long_pieces(toks, name, monkeypatch):
+    """k_bpe_long (windowed rounds, spl_encode.cu bpe_group) against the sequential loop of bpe.rs:119-167 in the C
+    oracle: pieces of every length class; runs of one character (one slope across all lanes of a group), two-letter
+    alphabets (long ties), random letters, CJK runs; lengths around the class and lane-block boundaries."""
+    rng = random.Random(77)
+    texts = []
+    for ch in "=-#a \n.":
+        texts += [ch * k for k in (33, 63, 64, 65, 66, 95, 127, 128, 129, 130, 191, 255, 256, 257, 300, 511, 512, 513, 700, 1023, 1024, 1025, 1500)]
+    for alpha in ("ab", "abc", "etaoin", "abcdefghijklmnopqrstuvwxyz", "aeiou0123456789", "xyzXYZ_"):
+        texts += ["".join(rng.choice(alpha) for _ in range(rng.randint(33, 1100))) for _ in range(150)]
+    texts += ["".join(chr(rng.randint(0x4E00, 0x9FA5)) for _ in range(rng.randint(12, 330))) for _ in range(150)]
+    texts += [" " + "".join(rng.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(2 ** k - 1)) for k in range(5, 11)]
+    rng.shuffle(texts)
+    t, o = toks(name), c_oracle(name)
+    assert t.encode_batch(texts) == o.encode_batch(texts)
+    docs = ["\n".join(texts[i:i + 20]) for i in range(0, len(texts), 20)]     # many long pieces per warp task
+    assert t.encode_batch(docs) == o.encode_batch(docs)
+
+
 def test_device_resident_entry_point(toks):
     import torch
     tok = toks("cl100k_base")
