@@ -668,11 +668,9 @@ __device__ uint32_t bpe_group(uint32_t* reg, const bool valid, const SplTables* 
     uint32_t B = max(2u, (L + G - 1u) >> LG);                      // parts per lane: lane g owns [g * B, g * B + B)
     {
         const uint32_t e0 = g * B, nv = e0 < L ? min(B, L - e0) : 0u;
-        // ---- every byte becomes a part
+        // ---- every byte becomes a part (the lanes of the group read consecutive bytes)
 #pragma unroll 4
-        for (uint32_t j = 0; j < nv; ++j) S[AD(e0 + j)] = __ldg(tx + e0 + j);
-#pragma unroll 4
-        for (uint32_t j = 0; j < nv; ++j) S[AD(e0 + j)] = T->byte_sym[S[AD(e0 + j)]];
+        for (uint32_t i = g; i < L; i += G) S[AD(i)] = T->byte_sym[__ldg(tx + i)];
         __syncwarp();
         // ---- ranks of the adjacent pairs, two independent probes in flight per lane
         for (uint32_t j = 0; j < nv; j += 2) {
