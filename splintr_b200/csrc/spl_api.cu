@@ -512,9 +512,9 @@ const char* spl_last_error(const spl_tokenizer* tk) { return tk ? tk->err.c_str(
 int spl_launches_per_call(const spl_tokenizer* tk, uint32_t flags) {
     if (!tk) return 0;
     bool ws = (flags & SPL_ENCODE_WITH_SPECIAL) && !tk->host.sp_id.empty();
-    if (is_sentencepiece(tk)) return 12 + (ws ? 1 : 0);                // mark (T), 4 x scan, sp_emit, mark (T'), probe, bpe_long, bpe, chunk_scan, emit
+    if (is_sentencepiece(tk)) return 11 + (ws ? 1 : 0);                // mark (T), 4 x scan, sp_emit, mark (T'), probe, bpe, bpe_long (+ chunk scan), emit
     int pre = tk->host.pattern == SPL_PAT_MISTRAL_V3 ? 1 : 2;          // sequential rules | bit-parallel + fallback
-    return 6 + pre + (ws ? 1 : 0);                                     // mark_docs, probe, bpe_long, bpe, chunk_scan, emit
+    return 5 + pre + (ws ? 1 : 0);                                     // mark_docs, probe, bpe, bpe_long (+ chunk scan), emit
 }
 
 int spl_set_profiling(spl_tokenizer* tk, int enable) {

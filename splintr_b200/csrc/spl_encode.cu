@@ -4,7 +4,8 @@
 //                hit goes to pv[] in piece order, a miss is appended to the miss list of its length class
 //   k_bpe        the leftmost-min-rank merge loop of bpe.rs:83-194 for every listed piece -- a group of 1..32 lanes per
 //                piece by length class, 32 / group pieces side by side in a warp -- ids to pool[] at the piece's byte position
-//   k_chunk_scan exclusive prefix of the id counts of 32-tile chunks (k_emit adds the tiles inside its chunk)
+//   (chunk scan) exclusive prefix of the id counts of 32-tile chunks, by the last block of k_bpe_long (k_emit adds the
+//                tiles inside its chunk)
 //   k_emit       pv[] + pool[] -> ids in document order (the collect of tokenizer.rs:806 and the Rayon collect of
 //                encode_batch, tokenizer.rs:932-934) and the per-document output offsets
 //
@@ -934,6 +935,54 @@ __device__ uint32_t bpe_piece_block(uint64_t* red, uint32_t* s_bcast, const SplT
 
 #define BPE_SMEM_BYTES ((SPL_BPE_THREADS / 32) * BG_WORDS * 4)
 
+// Exclusive prefix of the id counts of the chunks (SPL_CHUNK_TILES tiles each; k_probe and the merge kernels keep the
+// chunk totals up to date with atomics) -> chunk_state; k_emit adds the tiles inside a chunk itself.  Run by ONE block
+// of SPL_BPE_THREADS threads: the block of k_bpe_long that finishes last (chunks are few, N / 128 KiB).
+// smem: CS_TILE + CS_TILE / 32 + 2 * SPL_BPE_THREADS + 2 words.
+#define CS_PER  32u                                  // chunks per thread and round
+#define CS_TILE (SPL_BPE_THREADS * CS_PER)
+__device__ void chunk_scan_block(const SplWork& w, uint32_t* smem) {
+    uint32_t* cnt = smem;                            // one pad word per 32: a thread's CS_PER chunks start in its own bank
+    uint64_t* part = reinterpret_cast<uint64_t*>(smem + CS_TILE + CS_TILE / 32u);
+    uint64_t* s_carry = part + SPL_BPE_THREADS;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t n = (w.n_tiles + SPL_CHUNK_TILES - 1) / SPL_CHUNK_TILES;
+    if (tid == 0) *s_carry = 0;
+    for (uint32_t c0 = 0; c0 < n; c0 += CS_TILE) {
+        // coalesced, independent loads (past the L1: other blocks' atomics wrote these words)
+#pragma unroll 8
+        for (uint32_t i = tid; i < CS_TILE; i += SPL_BPE_THREADS)
+            cnt[i + (i >> 5)] = c0 + i < n ? (uint32_t)__ldcg(w.chunk_cnt + c0 + i) : 0u;
+        __syncthreads();
+        const uint32_t lo = tid * CS_PER;
+        uint64_t sum = 0;
+#pragma unroll 8
+        for (uint32_t q = 0; q < CS_PER; ++q) sum += cnt[lo + q + tid];               // (lo + q) + ((lo + q) >> 5)
+        part[tid] = sum;
+        __syncthreads();
+        if (tid < 32) {                              // one warp turns the per-thread sums into exclusive offsets
+            uint64_t carry = *s_carry;
+            for (uint32_t q0 = 0; q0 < SPL_BPE_THREADS; q0 += 32) {
+                const uint64_t x = part[q0 + tid];
+                uint64_t incl = x;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t a = __shfl_up_sync(FULL, (uint32_t)incl, o), b = __shfl_up_sync(FULL, (uint32_t)(incl >> 32), o);
+                    if (tid >= (uint32_t)o) incl += (uint64_t)a | ((uint64_t)b << 32);
+                }
+                part[q0 + tid] = carry + incl - x;
+                const uint32_t ta = __shfl_sync(FULL, (uint32_t)incl, 31), tb = __shfl_sync(FULL, (uint32_t)(incl >> 32), 31);
+                carry += (uint64_t)ta | ((uint64_t)tb << 32);
+            }
+            if (tid == 0) *s_carry = carry;
+        }
+        __syncthreads();
+        uint64_t run = part[tid];
+        for (uint32_t q = 0; q < CS_PER && c0 + lo + q < n; ++q) { w.chunk_state[c0 + lo + q] = run; run += cnt[lo + q + tid]; }
+        __syncthreads();
+    }
+}
+
 // k_bpe_long: the classes from win_cls up by windowed rounds (13.6 KiB of shared memory per warp), then the huge class.
 // k_bpe: the classes below win_cls, one merge per step (10 KiB per warp: five blocks per SM -- those pieces wait on
 // dependent table probes, so resident warps are what counts).
@@ -992,60 +1041,16 @@ __global__ void __launch_bounds__(SPL_BPE_THREADS, 4) k_bpe_long(SplWork w, cons
             }
         }
     }
-}
-
-// ------------------------------------------------------------------------------------------
-// k_chunk_scan: exclusive prefix of the id counts of the chunks (SPL_CHUNK_TILES tiles each; k_probe and k_bpe keep
-// the chunk totals up to date).  One block: chunks are few (N / 128 KiB); k_emit adds the tiles inside a chunk itself.
-// ------------------------------------------------------------------------------------------
-#define TS_PER 4u                                    // chunks per thread and round
-__global__ void __launch_bounds__(1024) k_chunk_scan(SplWork w) {
-    __shared__ uint32_t s_cnt[1024 * TS_PER];
-    __shared__ uint64_t s_w[32];
-    __shared__ uint64_t s_carry;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t n = (w.n_tiles + SPL_CHUNK_TILES - 1) / SPL_CHUNK_TILES;
-    if (tid == 0) s_carry = 0;
-    for (uint32_t c0 = 0; c0 < n; c0 += 1024 * TS_PER) {
-        // coalesced, independent loads; then every thread owns TS_PER consecutive chunks
-#pragma unroll
-        for (uint32_t q = 0; q < TS_PER; ++q) {
-            uint32_t i = c0 + q * 1024 + tid;
-            s_cnt[q * 1024 + tid] = i < n ? (uint32_t)w.chunk_cnt[i] : 0u;
-        }
-        __syncthreads();
-        uint32_t loc[TS_PER];
-        uint64_t v = 0;
-#pragma unroll
-        for (uint32_t q = 0; q < TS_PER; ++q) { loc[q] = s_cnt[tid * TS_PER + q]; v += loc[q]; }
-        uint64_t incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t a = __shfl_up_sync(FULL, (uint32_t)incl, o), b = __shfl_up_sync(FULL, (uint32_t)(incl >> 32), o);
-            if (lane >= (uint32_t)o) incl += (uint64_t)a | ((uint64_t)b << 32);
-        }
-        if (lane == 31) s_w[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            uint64_t x = s_w[lane], xi = x;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t a = __shfl_up_sync(FULL, (uint32_t)xi, o), b = __shfl_up_sync(FULL, (uint32_t)(xi >> 32), o);
-                if (lane >= (uint32_t)o) xi += (uint64_t)a | ((uint64_t)b << 32);
-            }
-            s_w[lane] = xi - x;
-        }
-        __syncthreads();
-        uint64_t run = s_carry + s_w[warp] + incl - v;
-#pragma unroll
-        for (uint32_t q = 0; q < TS_PER; ++q) {
-            uint32_t i = c0 + tid * TS_PER + q;
-            if (i < n) w.chunk_state[i] = run;
-            run += loc[q];
-        }
-        __syncthreads();
-        if (tid == 1023) s_carry = run;
-        __syncthreads();
+    // ---- the block that finishes last (k_bpe ran before this kernel) scans the chunk totals for k_emit --------------
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        s_bcast = atomicAdd(&w.counters[SPL_CTR_TICKET], 1u) == gridDim.x - 1u;
+    }
+    __syncthreads();
+    if (s_bcast) {
+        __threadfence();
+        chunk_scan_block(w, bpe_smem);
     }
 }
 
@@ -1239,12 +1244,10 @@ void spl_launch_encode_stage(const SplWork& w, int num_sms, cudaStream_t stream,
     }
     // first length class merged by windowed rounds (measured crossover; SPL_BPE_WIN_CLS overrides it for experiments)
     static const uint32_t win_cls = [] { const char* e = getenv("SPL_BPE_WIN_CLS"); return e ? (uint32_t)atoi(e) : SPL_BPE_WIN_CLS; }();
-    k_bpe_long<<<(uint32_t)num_sms * 4u, SPL_BPE_THREADS, BPE_SMEM_BYTES, stream>>>(w, win_cls);
-    mark(ctx, "k_bpe_long");
     k_bpe<<<(uint32_t)num_sms * 5u, SPL_BPE_THREADS, BPE_SEQ_SMEM_BYTES, stream>>>(w, win_cls);
     mark(ctx, "k_bpe");
-    k_chunk_scan<<<1, 1024, 0, stream>>>(w);
-    mark(ctx, "k_chunk_scan");
+    k_bpe_long<<<(uint32_t)num_sms * 4u, SPL_BPE_THREADS, BPE_SMEM_BYTES, stream>>>(w, win_cls);   // + the chunk scan, by its last block
+    mark(ctx, "k_bpe_long");
     k_emit<<<w.n_tiles, SPL_THREADS, 0, stream>>>(w);
     mark(ctx, "k_emit");
 }

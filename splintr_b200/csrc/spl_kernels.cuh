@@ -63,7 +63,7 @@ struct SplWork {
     size_t          bitmap_words;
     SplTileInfo*    tinfo;            // [n_tiles+1] per-tile record (zero-initialised)
     int32_t*        chunk_cnt;        // [n_tiles / SPL_CHUNK_TILES + 1] ids of the chunk's tiles (kept by k_probe and k_bpe)
-    uint64_t*       chunk_state;      // [n_tiles / SPL_CHUNK_TILES + 1] exclusive prefix of chunk_cnt (k_chunk_scan)
+    uint64_t*       chunk_state;      // [n_tiles / SPL_CHUNK_TILES + 1] exclusive prefix of chunk_cnt (chunk_scan_block, last block of k_bpe_long)
     uint32_t*       pv;               // [n_tiles * SPL_TILE] per-piece value, tile t at pv[t * SPL_TILE ..]
     uint32_t*       pool;             // [N] ids of the pieces that went through the merge loop, at the piece's byte position
     uint64_t*       mlist;            // miss lists, one region per length class
@@ -89,6 +89,7 @@ struct SplWork {
 // SplWork::counters
 enum : uint32_t { SPL_CTR_ERR = 1, SPL_CTR_HUGE_POOL = 2, SPL_CTR_FB = 3, SPL_CTR_DEFER = 5,
                   SPL_CTR_CLS = 8,            // [8 .. 8 + SPL_NCLS): entries in the miss list of each class
+                  SPL_CTR_TICKET = 16,        // blocks of k_bpe_long that are done (the last one scans the chunk totals)
                   SPL_CTR_WORDS = 32 };
 
 enum : uint32_t { SPL_DEVERR_OFFSETS = 1u, SPL_DEVERR_HUGE_POOL = 2u };
