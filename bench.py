@@ -190,6 +190,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner / debug lines: not on stdout (one JSON line there)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     def barrier():

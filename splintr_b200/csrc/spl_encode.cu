@@ -13,6 +13,7 @@
 // the streaming probe so that both run at full occupancy.  Integer / byte work; no tensor cores.
 #include "spl_device.cuh"
 #include "spl_fast_dev.cuh"
+#include "spl_bpe_bits.h"
 
 // ------------------------------------------------------------------------------------------
 // probes that only this stage uses
@@ -620,18 +621,6 @@ __device__ uint32_t bpe_seq(uint32_t* reg, const bool valid, const SplTables* T,
     return c;
 }
 
-// Bit tricks of a round.  A lane's masks hold its B consecutive parts, bit j = part e0 + j.
-// runs_above(D, st): the runs of D that start right above the bits of st (the addition ripples through exactly those).
-__device__ __forceinline__ uint32_t runs_above(uint32_t D, uint32_t st) { return D & ~(D + (st << 1)); }
-// m along upward slopes: D = slope bits, V = valleys (m = 1); a run that starts at bit 0 continues the slope of the
-// lane before, whose last part has m = cin.  m alternates with the distance from the valley.
-__device__ __forceinline__ uint32_t slope_m(uint32_t D, uint32_t V, uint32_t cin, uint32_t first /* bit where a foreign run starts */) {
-    const uint32_t E = 0x55555555u;
-    const uint32_t run0 = D & ~(D + first);                                        // run from `first` upwards (empty if D lacks that bit)
-    const uint32_t P = (first & E) ? ~E : E;                                       // positions at an even distance from the part below `first`
-    return (runs_above(D, V & E) & E) | (runs_above(D, V & ~E) & ~E) | (run0 & (cin ? P : ~P));
-}
-
 // All 32 lanes call this; lane = p * G + g works on piece p of the warp's task (valid: the piece exists), G = 1 << LG.
 // Returns the id count in every lane of the group; ids go to out[0 ..] in order.
 template <uint32_t LG>
@@ -728,16 +717,15 @@ __device__ uint32_t bpe_group(uint32_t* reg, const bool valid, const SplTables* 
         // next lane's block take that lane's boundary bit, until nothing changes (one extra pass per lane a slope spans)
         uint32_t m, cin = 0, cin2 = 0;
         {
-            const uint32_t rDR = __brev(fDR), rV = __brev(fV), firstR = 1u << (32u - B);
             for (;;) {
-                m = fV | slope_m(fDL, fV, cin, 1u) | __brev(slope_m(rDR, rV, cin2, firstR));
+                m = spl_window_slopes(fV, fDL, fDR, cin, cin2, B);
                 const uint32_t up = __shfl_up_sync(FULL, m, 1), dn = __shfl_down_sync(FULL, m, 1);
                 const uint32_t ncin = g ? (up >> (B - 1u)) & 1u : 0u, ncin2 = g + 1u < G ? dn & 1u : 0u;
                 const bool ch = (ncin != cin && (fDL & 1u)) || (ncin2 != cin2 && ((fDR >> (B - 1u)) & 1u));
                 cin = ncin; cin2 = ncin2;
                 if (!__any_sync(FULL, ch)) break;
             }
-            m |= fPK & ~((m << 1) | cin) & ~((m >> 1) | (cin2 << (B - 1u)));      // a peak merges iff neither neighbour does
+            m = spl_window_peaks(m, fPK, cin, cin2, B);
         }
         // (3) the ranks the merges can create; theta = their minimum.  The m-pairs of the whole warp go through a
         // worklist so that all 32 lanes probe.

@@ -383,3 +383,44 @@ extern "C" int ht_jsonl(const uint8_t* text, uint32_t n, const char* field, uint
     counts[0] = docs; counts[1] = bytes; counts[2] = missing; counts[3] = bad;
     return 0;
 }
+
+// ---- windowed merge rounds (spl_bpe_bits.h): the m masks of one group of G lanes, B parts per lane ----------------
+// K[0 .. n_pairs): rank of every pair (0x1FFFFF = none).  Builds the lanes' LT / RT masks the way bpe_group does, then
+// runs the kernel's boundary-bit iteration (the shuffles become array reads) and the peak step.  m_out[g] = lane g's mask.
+#include "../../splintr_b200/csrc/spl_bpe_bits.h"
+extern "C" int ht_bpe_window_m(const uint32_t* K, uint32_t n_pairs, uint32_t G, uint32_t B, uint32_t* m_out) {
+    const uint32_t NONE = 0x1FFFFFu, L = n_pairs + 1;
+    if (B < 2 || B > 32 || (uint64_t)G * B < L || G > 32) return -1;
+    uint32_t fV[32], fDL[32], fDR[32], fPK[32], m[32], cin[32] = {0}, cin2[32] = {0};
+    auto rank = [&](uint32_t e) { return e + 1 < L ? K[e] : NONE; };
+    for (uint32_t g = 0; g < G; ++g) {
+        const uint32_t e0 = g * B, nv = e0 < L ? (B < L - e0 ? B : L - e0) : 0u;
+        uint32_t LV = 0, LT = 0, RT = 0;
+        uint32_t prev = (e0 && e0 < L) ? rank(e0 - 1) : NONE, cur = e0 < L ? rank(e0) : NONE;
+        for (uint32_t j = 0; j < nv; ++j) {
+            const uint32_t nxt = rank(e0 + j + 1);
+            if (cur != NONE) {
+                LV |= 1u << j;
+                if (prev <= cur) LT |= 1u << j;
+                if (nxt < cur) RT |= 1u << j;
+            }
+            prev = cur; cur = nxt;
+        }
+        fV[g] = LV & ~LT & ~RT; fDL[g] = LV & LT & ~RT; fDR[g] = LV & RT & ~LT; fPK[g] = LV & LT & RT;
+    }
+    int passes = 0;
+    for (;;) {
+        ++passes;
+        for (uint32_t g = 0; g < G; ++g) m[g] = spl_window_slopes(fV[g], fDL[g], fDR[g], cin[g], cin2[g], B);
+        bool ch = false;
+        for (uint32_t g = 0; g < G; ++g) {
+            const uint32_t ncin = g ? (m[g - 1] >> (B - 1u)) & 1u : 0u, ncin2 = g + 1u < G ? m[g + 1] & 1u : 0u;
+            ch |= (ncin != cin[g] && (fDL[g] & 1u)) || (ncin2 != cin2[g] && ((fDR[g] >> (B - 1u)) & 1u));
+            cin[g] = ncin; cin2[g] = ncin2;
+        }
+        if (!ch) break;
+        if (passes > 64) return -2;
+    }
+    for (uint32_t g = 0; g < G; ++g) m_out[g] = spl_window_peaks(m[g], fPK[g], cin[g], cin2[g], B);
+    return passes;
+}

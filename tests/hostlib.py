@@ -9,7 +9,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = [os.path.join(ROOT, "tests", "csrc", "hosttest.cpp"), os.path.join(ROOT, "splintr_b200", "csrc", "spl_host.cpp")]
-DEPS = SRC + [os.path.join(ROOT, "splintr_b200", "csrc", f) for f in ("spl_pretok.h", "spl_pretok_fast.h", "spl_sentencepiece.h", "spl_ingest.h", "spl_common.h", "spl_host.h", "unicode_tables.inc")]
+DEPS = SRC + [os.path.join(ROOT, "splintr_b200", "csrc", f) for f in ("spl_pretok.h", "spl_pretok_fast.h", "spl_sentencepiece.h", "spl_ingest.h", "spl_bpe_bits.h", "spl_common.h", "spl_host.h", "unicode_tables.inc")]
 LIB = os.path.join(ROOT, "tests", "csrc", "libhosttest.so")
 _lib = None
 
@@ -45,8 +45,19 @@ def load():
     lib.ht_sp_transform.argtypes = [ctypes.c_char_p, ctypes.c_uint32, vp, vp, vp, vp, vp]
     lib.ht_encode_sp.restype = ctypes.c_long
     lib.ht_encode_sp.argtypes = [vp, ctypes.c_char_p, ctypes.c_uint32, vp, ctypes.c_size_t]
+    lib.ht_bpe_window_m.restype = ctypes.c_int
+    lib.ht_bpe_window_m.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, vp]
     _lib = lib
     return lib
+
+
+def bpe_window_m(ranks, G: int, B: int):
+    """spl_bpe_bits.h over one group: ranks of the pairs (0x1FFFFF = none) -> (m flag per pair, boundary passes)."""
+    k = np.ascontiguousarray(ranks, dtype=np.uint32)
+    m = np.zeros(32, dtype=np.uint32)
+    rc = load().ht_bpe_window_m(k.ctypes.data, len(k), G, B, m.ctypes.data)
+    assert rc > 0, rc
+    return [bool((int(m[e // B]) >> (e % B)) & 1) for e in range(len(k))], rc
 
 
 def jsonl(data: bytes, field: str = "text"):

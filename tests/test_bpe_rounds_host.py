@@ -59,3 +59,44 @@ def test_lane_model_bitmaps_equal_sequential_loop():
                 continue
             got, _ = bpe_lane_model.group_bpe(piece, enc, dec, LG)
             assert got == byte_pair_encode(piece, enc), (LG, piece)
+
+
+def _m_by_definition(ranks):
+    """m(i) = !(m(i-1) and key(i-1) < key(i)) and !(m(i+1) and key(i+1) < key(i)), pairs visited in key order."""
+    NONE = 0x1FFFFF
+    n = len(ranks)
+    m = [False] * n
+    for i in sorted((i for i in range(n) if ranks[i] != NONE), key=lambda i: (ranks[i], i)):
+        m[i] = not (i > 0 and m[i - 1]) and not (i + 1 < n and m[i + 1])      # a neighbour with m set was visited before: its key is lower
+    return m
+
+
+def test_kernel_bit_tricks_equal_the_definition_of_m():
+    """spl_bpe_bits.h (the code k_bpe_long runs: carry-ripple run masks, bit reversal, boundary bits between lanes)
+    compiled for the host, against m evaluated pair by pair in key order."""
+    import hostlib
+    NONE = 0x1FFFFF
+    rng = random.Random(5)
+    worst = 0
+    for trial in range(6000):
+        G = 1 << rng.randrange(6)
+        B = rng.randint(2, 32)
+        n = rng.randint(1, G * B - 1)                               # pairs; parts = n + 1 <= G * B
+        B = max(2, (n + 1 + G - 1) // G)                            # the kernel's block size for that many parts
+        kind = rng.randrange(5)
+        if kind == 0:
+            ranks = [rng.randrange(300, 5000) for _ in range(n)]
+        elif kind == 1:
+            ranks = [777] * n                                       # one character repeated: a single slope over all lanes
+        elif kind == 2:
+            ranks = [rng.choice((400, 401)) for _ in range(n)]      # long ties
+        elif kind == 3:
+            ranks = sorted(rng.randrange(300, 900) for _ in range(n))
+            if rng.random() < 0.5:
+                ranks.reverse()                                     # monotone: one slope, to either side
+        else:
+            ranks = [rng.choice((NONE, 300, 301, 5000)) for _ in range(n)]
+        got, passes = hostlib.bpe_window_m(ranks, G, B)
+        assert got == _m_by_definition(ranks), (G, B, ranks)
+        worst = max(worst, passes)
+    assert worst <= 33
