@@ -50,6 +50,46 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+# ---- host side of the Python boundary: CPython extension (packing list[str], building list[list[int]]) -------------
+PYHOST_SRC = os.path.join(CSRC, "spl_pyhost.c")
+_pyhost = None
+
+
+def _pyhost_path() -> str:
+    import sysconfig
+    return os.path.join(_HERE, "_pyhost" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_pyhost(force: bool = False) -> str:
+    """gcc -shared spl_pyhost.c against this interpreter's headers -> splintr_b200/_pyhost.<abi>.so"""
+    import sysconfig
+    out = _pyhost_path()
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(PYHOST_SRC):
+        return out
+    cmd = ["gcc", "-O2", "-shared", "-fPIC", "-I" + sysconfig.get_paths()["include"], "-o", out, PYHOST_SRC]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("gcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    return out
+
+
+def pyhost():
+    """The extension module, built on first use.  None when it cannot be built (no compiler / headers): the callers
+    then run the same steps in Python (tests/test_pyhost.py holds the two against each other) -- host-side packing
+    only; the encode path itself has no fallback."""
+    global _pyhost
+    if _pyhost is None:
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("splintr_b200._pyhost", build_pyhost())
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            _pyhost = mod
+        except Exception:                                   # noqa: BLE001
+            _pyhost = False
+    return _pyhost or None
+
+
 class SplStats(ctypes.Structure):
     _fields_ = [("n_docs", ctypes.c_uint64), ("n_bytes", ctypes.c_uint64), ("n_tokens", ctypes.c_uint64),
                 ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),

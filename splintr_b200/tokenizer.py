@@ -196,7 +196,7 @@ class Tokenizer:
 
     # -- encode -----------------------------------------------------------------------------
     @staticmethod
-    def _pack(texts: Sequence[str]) -> Tuple[bytes, np.ndarray]:
+    def _pack_py(texts: Sequence[str]) -> Tuple[bytes, np.ndarray]:
         enc = []
         for t in texts:
             if not isinstance(t, str):
@@ -206,6 +206,21 @@ class Tokenizer:
         if enc:
             np.cumsum(np.fromiter((len(b) for b in enc), dtype=np.uint64, count=len(enc)), out=offsets[1:])
         return b"".join(enc), offsets
+
+    @staticmethod
+    def _pack(texts: Sequence[str]):
+        """list[str] -> (concatenated UTF-8, uint64 offsets[n + 1]): what PyO3 does for bindings.rs:337 when it
+        extracts Vec<String>.  csrc/spl_pyhost.c copies every text once, straight into one array."""
+        ph = _lib.pyhost()
+        if ph is None:
+            return Tokenizer._pack_py(texts)
+        if not isinstance(texts, list):
+            texts = list(texts)
+        offsets = np.empty(len(texts) + 1, dtype=np.uint64)
+        total = ph.pack_sizes(texts, offsets.ctypes.data)
+        data = np.empty(total + 16, dtype=np.uint8)
+        ph.pack_copy(texts, data.ctypes.data)
+        return data[:total], offsets
 
     def encode_packed(self, data, offsets: np.ndarray, with_special: bool = False, return_stats: bool = False):
         """Zero-copy surface: `data` = concatenated UTF-8 (bytes / bytearray / uint8 array /
@@ -376,6 +391,9 @@ class Tokenizer:
 
     def _encode_many(self, texts: Sequence[str], with_special: bool) -> List[List[int]]:
         ids, off = self.encode_batch_packed(texts, with_special)
+        ph = _lib.pyhost()
+        if ph is not None:
+            return ph.ids_to_lists(ids.ctypes.data, off.ctypes.data, len(texts))
         flat = ids.tolist()
         o = off.tolist()
         return [flat[o[i]:o[i + 1]] for i in range(len(texts))]
