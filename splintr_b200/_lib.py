@@ -66,10 +66,12 @@ def build_pyhost(force: bool = False) -> str:
     out = _pyhost_path()
     if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(PYHOST_SRC):
         return out
-    cmd = ["gcc", "-O2", "-shared", "-fPIC", "-I" + sysconfig.get_paths()["include"], "-o", out, PYHOST_SRC]
+    tmp = f"{out}.{os.getpid()}.tmp"                         # ranks of one job may get here together: build aside, rename
+    cmd = ["gcc", "-O2", "-shared", "-fPIC", "-I" + sysconfig.get_paths()["include"], "-o", tmp, PYHOST_SRC]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("gcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    os.replace(tmp, out)
     return out
 
 
