@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(SPL_THREADS) k_probe_rest(SplWork w) {
 //   theta, so up to theta the sequential loop does exactly the m = 1 merges: the round commits those with
 //   rank < theta (and always the global minimum, which bpe.rs merges first whatever follows).
 //   The three looked-up ranks are also the K values of the new neighbours, so a round needs no second probe pass.
-// tools/bpe_batch_sim.py is the same round in Python, checked against the oracle; random letter strings of
+// tests/bpe_batch_sim.py is the same round in Python, checked against the oracle; random letter strings of
 // 32..512 bytes take ~3 rounds instead of ~80 merges steps, runs of one character ~6 instead of ~120.
 // ------------------------------------------------------------------------------------------
 #define BG_RANK_NONE 0x1FFFFFu

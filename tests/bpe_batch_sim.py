@@ -9,7 +9,7 @@ A round, on the current part list with pair keys key[e] = (rank(e, next e), e):
   3. commit the m-true pairs with rank < theta (the global minimum always).  Re-rank around them.
 The sequential loop performs exactly these merges before any other (no pair created in the window ranks below theta).
 
-Usage: python tools/bpe_batch_sim.py [vocab] [n_pieces]
+Usage: python tests/bpe_batch_sim.py [vocab] [n_pieces]
 """
 import sys, os, random
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

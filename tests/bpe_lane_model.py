@@ -1,7 +1,7 @@
 """Lane-level model of one k_bpe_long group (spl_encode.cu, bpe_group<LG>): the same per-lane bitmasks over consecutive
 parts, carry-ripple run masks (runs_above / slope_m, bit reversal for the right-hand slopes), boundary bits between
 lanes, packed probe results and compaction as the kernel, checked against the oracle's sequential loop.
-Usage: python tools/bpe_lane_model.py [vocab] [pieces per kind]"""
+Usage: python tests/bpe_lane_model.py [vocab] [pieces per kind]"""
 import sys, os, random
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle.py_oracle import byte_pair_encode, load_tiktoken_bpe

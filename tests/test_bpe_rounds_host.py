@@ -1,15 +1,13 @@
 """The windowed merge rounds of k_bpe_long (splintr_b200/csrc/spl_encode.cu, bpe_group) restated in Python and held
 against the oracle's sequential loop (byte_pair_encode = bpe.rs:67-197):
-tools/bpe_batch_sim.py is the round as an algorithm (m, theta, commit), tools/bpe_lane_model.py a lane-level model
-with row bitmaps and shuffled masks.  CPU only; the kernel itself is covered by tests/test_gpu_parity.py."""
+tests/bpe_batch_sim.py is the round as an algorithm (m, theta, commit), tests/bpe_lane_model.py a lane-level model
+with the per-lane bitmasks of the kernel.  CPU only; the kernel itself is covered by tests/test_gpu_parity.py."""
 import os
 import random
 import sys
 
 import pytest
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 from conftest import py_oracle                                   # noqa: E402
 from oracle.py_oracle import byte_pair_encode                    # noqa: E402
