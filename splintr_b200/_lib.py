@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libsplintr_b200.so")
 SOURCES = ["spl_api.cu", "spl_kernels.cu", "spl_encode.cu", "spl_decode.cu", "spl_sentencepiece.cu", "spl_ingest.cu", "spl_host.cpp"]
-HEADERS = ["spl_common.h", "spl_pretok.h", "spl_pretok_fast.h", "spl_sentencepiece.h", "spl_ingest.h", "spl_host.h", "spl_kernels.cuh", "spl_device.cuh", "spl_fast_dev.cuh", "spl_bpe_bits.h", "unicode_tables.inc",
+HEADERS = ["spl_common.h", "spl_segment.h", "spl_pretok.h", "spl_pretok_fast.h", "spl_sentencepiece.h", "spl_ingest.h", "spl_host.h", "spl_kernels.cuh", "spl_device.cuh", "spl_fast_dev.cuh", "spl_bpe_bits.h", "unicode_tables.inc",
            os.path.join("..", "..", "include", "splintr_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

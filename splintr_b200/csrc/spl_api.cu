@@ -57,7 +57,7 @@ struct DevCtx {
     void* table_blob = nullptr;
     SplTables* d_tables = nullptr;
     DevBuf text, doc_off, ids, out_off;          // spl_encode_batch: the shard's buffers
-    DevBuf zero, tstate, pv, pool, mlist, fbl, huge, defer;
+    DevBuf zero, tstate, pv, pool, mlist, fbl, huge;
     DevBuf dec_ids, dec_off, dec_ws, dec_out, dec_out_off;       // spl_decode_batch   // per-pass workspace (zero: everything that starts cleared)
     DevBuf jl_tiles, jl_lines;                                   // spl_ingest_jsonl_device: tile counts, per-line arrays
     DevBuf jl_text, jl_off, jl_out_off[2];                       // spl_encode_jsonl: ingested text + offsets, output offsets (alternating)
@@ -75,7 +75,6 @@ struct PinnedBuf { void* p; size_t cap; };
 struct spl_tokenizer {
     bool profiling = false;
     bool trace = false;                     // SPL_TRACE=1: per-chunk timeline of spl_encode_batch on stderr
-    bool fused = false;                     // SPL_FUSED=1: k_pretok_probe instead of k_pretok_fast + k_probe (experiment)
     int trace_chunk = -1;                   // SPL_TRACE_CHUNK=k: with SPL_TRACE, per-kernel times of the k-th chunk
     uint64_t chunk_bytes = 0;               // pipeline chunk size of spl_encode_batch (0 = automatic)
     SplHostTables host;
@@ -116,7 +115,11 @@ int upload_tables(spl_tokenizer* tk, DevCtx& dc) {
     size_t i_tl = add(h.tl.data(), h.tl.size() * sizeof(SplKeyL));
     size_t i_tb = add(h.tok_bytes.data(), h.tok_bytes.size());
     size_t i_to = add(h.tok_off.data(), h.tok_off.size() * 4);
-    size_t i_pair = add(h.pair.data(), h.pair.size() * 8);
+    size_t i_pair = add(h.pair.data(), h.pair.size() * 4);
+    size_t i_bpair = add(h.bpair.data(), h.bpair.size() * 4);
+    size_t i_irr = add(h.seg_irr.data(), h.seg_irr.size() * 4);
+    size_t i_h2 = add(h.seg_h2.data(), h.seg_h2.size() * 4);
+    size_t i_ctok = add(h.char_tok.data(), h.char_tok.size() * 4);
     size_t i_decb = add(h.dec_bytes.data(), h.dec_bytes.size());
     size_t i_deco = add(h.dec_off.data(), h.dec_off.size() * 4);
     size_t i_spb = add(h.sp_bytes.data(), h.sp_bytes.size());
@@ -138,7 +141,11 @@ int upload_tables(spl_tokenizer* tk, DevCtx& dc) {
     t.tok_off = (const uint32_t*)(base + parts[i_to].off);
     t.n_ids = h.n_ids;
     t.max_key_len = h.max_key_len;
-    t.pair = (const uint64_t*)(base + parts[i_pair].off); t.pair_log2 = h.pair_log2;
+    t.pair = (const uint32_t*)(base + parts[i_pair].off); t.pair_log2 = h.pair_log2;
+    t.bpair = (const uint32_t*)(base + parts[i_bpair].off);
+    t.seg_irr = (const uint32_t*)(base + parts[i_irr].off);
+    t.seg_h2 = (const uint32_t*)(base + parts[i_h2].off); t.seg_h2_log2 = h.seg_h2_log2;
+    t.char_tok = (const uint32_t*)(base + parts[i_ctok].off);
     memcpy(t.byte_sym, h.byte_sym, sizeof(t.byte_sym));
     t.dec_bytes = base + parts[i_decb].off;
     t.dec_off = (const uint32_t*)(base + parts[i_deco].off);
@@ -156,7 +163,7 @@ int upload_tables(spl_tokenizer* tk, DevCtx& dc) {
 
 void destroy_ctx(DevCtx& dc) {
     cudaSetDevice(dc.device);
-    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.ids, &dc.out_off, &dc.dec_ids, &dc.dec_off, &dc.dec_ws, &dc.dec_out, &dc.dec_out_off, &dc.jl_tiles, &dc.jl_lines, &dc.jl_text, &dc.jl_off, &dc.jl_out_off[0], &dc.jl_out_off[1], &dc.run_tot, &dc.sp_zero, &dc.sp_tiles, &dc.sp_text, &dc.sp_doc, &dc.zero, &dc.tstate, &dc.pv, &dc.pool, &dc.mlist, &dc.fbl, &dc.huge, &dc.defer})
+    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.ids, &dc.out_off, &dc.dec_ids, &dc.dec_off, &dc.dec_ws, &dc.dec_out, &dc.dec_out_off, &dc.jl_tiles, &dc.jl_lines, &dc.jl_text, &dc.jl_off, &dc.jl_out_off[0], &dc.jl_out_off[1], &dc.run_tot, &dc.sp_zero, &dc.sp_tiles, &dc.sp_text, &dc.sp_doc, &dc.zero, &dc.tstate, &dc.pv, &dc.pool, &dc.mlist, &dc.fbl, &dc.huge})
         b->release();
     if (dc.table_blob) cudaFree(dc.table_blob);
     for (auto& e : dc.ev) if (e) cudaEventDestroy(e);
@@ -211,7 +218,6 @@ int reserve_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
     if ((rc = dc.mlist.ensure((size_t)m.base[SPL_NCLS] * 8, tk->err))) return rc;
     uint32_t n_fast_tiles = (uint32_t)((N + SPL_FAST_PAYLOAD * 32u - 1) / (SPL_FAST_PAYLOAD * 32u));
     if ((rc = dc.fbl.ensure((size_t)(n_fast_tiles + 1) * 4, tk->err))) return rc;
-    if ((rc = dc.defer.ensure((z.n_tiles + 1) * 8, tk->err))) return rc;
     if (dc.huge_words == 0) dc.huge_words = (size_t)16 << 20;             // 64 MiB of scratch
     if ((rc = dc.huge.ensure(dc.huge_words * 4, tk->err))) return rc;
     return SPL_OK;
@@ -244,8 +250,6 @@ int prepare_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
     w.mlist = (uint64_t*)dc.mlist.p;
     for (uint32_t c = 0; c <= SPL_NCLS; ++c) w.ml_base[c] = m.base[c];
     w.fb_list = (uint32_t*)dc.fbl.p;
-    w.defer_list = (uint64_t*)dc.defer.p;
-    w.fused = tk->fused;
     w.n_fast_tiles = n_fast_tiles;
     w.huge_pool = (uint32_t*)dc.huge.p;
     w.huge_pool_words = (uint32_t)std::min<size_t>(dc.huge_words, 0xFFFFFFFFu);
@@ -456,7 +460,6 @@ int spl_create(const uint8_t* vocab, size_t vocab_len, int pattern_id, uint32_t 
     if (!tk) return SPL_ERR_OOM;
     if (const char* tr = getenv("SPL_TRACE")) tk->trace = tr[0] == '1';
     if (const char* tc = getenv("SPL_TRACE_CHUNK")) tk->trace_chunk = atoi(tc);
-    if (const char* fu = getenv("SPL_FUSED")) tk->fused = fu[0] != '0';
     if (const char* cb = getenv("SPL_CHUNK_BYTES")) tk->chunk_bytes = strtoull(cb, nullptr, 10);
     uint32_t hflags = ((flags & SPL_CREATE_BYTE_LEVEL) ? SPL_FLAG_BYTE_LEVEL : 0) |
                       ((flags & SPL_CREATE_SENTENCEPIECE) ? SPL_FLAG_SENTENCEPIECE : 0);

@@ -50,7 +50,6 @@ enum : int { SPL_PAT_CL100K = 0, SPL_PAT_O200K = 1, SPL_PAT_MISTRAL_V3 = 2,
 #define SPL_SYM_BITS   21
 #define SPL_UNK_BASE   ((1u << SPL_SYM_BITS) - 256u)
 #define SPL_RANK_NONE  0xFFFFFFFFu
-#define SPL_PAIR_EMPTY 0xFFFFFFFFFFFFFFFFull
 
 SPL_HD uint64_t spl_mix64(uint64_t x) {
     x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull;
@@ -59,15 +58,24 @@ SPL_HD uint64_t spl_mix64(uint64_t x) {
     return x;
 }
 
-// pair table: 8-byte entries (left:21 | right:21 | merged:21), bit 63 = 0, in buckets of SPL_PAIR_WAYS entries
-// (one 32-byte sector per probe).  A bucket fills front to back; a key lives in the first bucket from its home
-// bucket on that was not full when it was inserted, so a probe ends at the first bucket whose last slot is empty.
-// `log2size` counts BUCKETS.
+// pair table: (left symbol, right symbol) -> merged symbol, in buckets of SPL_PAIR_WAYS entries = one 32-byte sector:
+// four 32-bit TAGS followed by four 32-bit VALUES, so that the device reads a bucket with ONE 256-bit load
+// (LDG.E.256, sm_100) and finds a key with four 32-bit compares:
+//     tag   = right:21 | (left & 0x7FF) << 21
+//     value = merged:21 | (left >> 11) << 21          (bit 31 clear; an empty slot is tag = value = 0xFFFFFFFF)
+// A bucket fills front to back; a key lives in the first bucket from its home bucket on that was not full when it
+// was inserted, so a probe ends at the first bucket whose last slot is empty.  `log2size` counts BUCKETS.
 #define SPL_PAIR_WAYS 4
-SPL_HD uint64_t spl_pair_key(uint32_t l, uint32_t r) { return ((uint64_t)l << SPL_SYM_BITS) | r; }
-SPL_HD uint64_t spl_pair_entry(uint32_t l, uint32_t r, uint32_t m) { return (spl_pair_key(l, r) << SPL_SYM_BITS) | m; }
-SPL_HD uint32_t spl_pair_hash(uint64_t key, uint32_t log2size) {
-    return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> (64 - log2size));
+#define SPL_PAIR_WORDS (2 * SPL_PAIR_WAYS)
+#define SPL_PAIR_EMPTY 0xFFFFFFFFu
+#define SPL_SYM_MASK ((1u << SPL_SYM_BITS) - 1u)
+SPL_HD uint32_t spl_pair_tag(uint32_t l, uint32_t r) { return r | (l << SPL_SYM_BITS); }
+SPL_HD uint32_t spl_pair_hi(uint32_t l) { return (l >> (32 - SPL_SYM_BITS)) << SPL_SYM_BITS; }        // the value's key bits
+SPL_HD uint32_t spl_pair_hash(uint32_t l, uint32_t r, uint32_t log2size) {
+    uint32_t x = l * 0x9E3779B1u + r * 0x85EBCA77u;
+    x ^= x >> 16;
+    x *= 0x2C1B3C6Du;
+    return x >> (32 - log2size);
 }
 
 // whole-piece tables.  Keys are the piece bytes packed little-endian into u64 words,
@@ -118,8 +126,13 @@ struct SplTables {
     uint32_t n_ids;                // max mergeable id + 1
     uint32_t max_key_len;          // longest vocabulary key in bytes
     // BPE
-    const uint64_t* pair;  uint32_t pair_log2;
+    const uint32_t* pair;  uint32_t pair_log2;     // buckets of SPL_PAIR_WORDS words
+    const uint32_t* bpair;         // [65536] dense: rank of the pair (byte b0, byte b1) at [b0 << 8 | b1], SPL_RANK_NONE if none
     uint32_t byte_sym[256];        // symbol of each single byte
+    // independent segments (spl_segment.h)
+    const uint32_t* seg_irr;       // [2048] words
+    const uint32_t* seg_h2;  uint32_t seg_h2_log2;   // hashed bitmap, 2^seg_h2_log2 bits
+    const uint32_t* char_tok;      // [65536] merge-loop result of the UTF-8 bytes of code point c if that is ONE id, else SPL_RANK_NONE
     // decode: id -> bytes
     const uint8_t*  dec_bytes;
     const uint32_t* dec_off;       // [n_dec + 1]

@@ -42,28 +42,35 @@ __device__ __forceinline__ uint32_t g_next_bit(const uint32_t* __restrict__ w, u
     }
 }
 
-// one bucket of the pair table: SPL_PAIR_WAYS entries = one 32-byte sector
-struct PairBucket { ulonglong2 lo, hi; };
-__device__ __forceinline__ PairBucket pair_bucket_load(const uint64_t* __restrict__ tab, uint32_t b) {
-    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(tab + (size_t)b * SPL_PAIR_WAYS);
+// one bucket of the pair table: four tags + four values = one 32-byte sector, read with ONE 256-bit load
+// (LDG.E.256 -- sm_100 and later)
+struct PairBucket { uint4 tag, val; };
+__device__ __forceinline__ PairBucket pair_bucket_load(const uint32_t* __restrict__ tab, uint32_t b) {
+    const uint32_t* p = tab + (size_t)b * SPL_PAIR_WORDS;
+    unsigned long long a, c, d, e;
+    asm("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(c), "=l"(d), "=l"(e) : "l"(p));
     PairBucket r;
-    r.lo = __ldg(p); r.hi = __ldg(p + 1);
+    r.tag = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)c, (uint32_t)(c >> 32));
+    r.val = make_uint4((uint32_t)d, (uint32_t)(d >> 32), (uint32_t)e, (uint32_t)(e >> 32));
     return r;
 }
+// the key as the bucket holds it
+struct PairKey { uint32_t tag, hi; };
+__device__ __forceinline__ PairKey pair_key(uint32_t l, uint32_t r) { return PairKey{spl_pair_tag(l, r), spl_pair_hi(l)}; }
 // 0: key absent (bucket not full), 1: found (out set), 2: bucket full, go on with the next one
-__device__ __forceinline__ int pair_bucket_match(const PairBucket& k, uint64_t key, uint32_t& out) {
-    const uint32_t symmask = (1u << SPL_SYM_BITS) - 1;
-    if ((k.lo.x >> SPL_SYM_BITS) == key) { out = (uint32_t)k.lo.x & symmask; return 1; }
-    if ((k.lo.y >> SPL_SYM_BITS) == key) { out = (uint32_t)k.lo.y & symmask; return 1; }
-    if ((k.hi.x >> SPL_SYM_BITS) == key) { out = (uint32_t)k.hi.x & symmask; return 1; }
-    if ((k.hi.y >> SPL_SYM_BITS) == key) { out = (uint32_t)k.hi.y & symmask; return 1; }
-    return k.hi.y == SPL_PAIR_EMPTY ? 0 : 2;
+__device__ __forceinline__ int pair_bucket_match(const PairBucket& k, const PairKey key, uint32_t& out) {
+    const bool m0 = k.tag.x == key.tag && (k.val.x & ~SPL_SYM_MASK) == key.hi;
+    const bool m1 = k.tag.y == key.tag && (k.val.y & ~SPL_SYM_MASK) == key.hi;
+    const bool m2 = k.tag.z == key.tag && (k.val.z & ~SPL_SYM_MASK) == key.hi;
+    const bool m3 = k.tag.w == key.tag && (k.val.w & ~SPL_SYM_MASK) == key.hi;
+    if (m0 | m1 | m2 | m3) { out = (m0 ? k.val.x : m1 ? k.val.y : m2 ? k.val.z : k.val.w) & SPL_SYM_MASK; return 1; }
+    return k.val.w == SPL_PAIR_EMPTY ? 0 : 2;
 }
 
-__device__ __forceinline__ uint32_t pair_lookup(const uint64_t* __restrict__ tab, uint32_t log2, uint32_t l, uint32_t r) {
-    const uint64_t key = spl_pair_key(l, r);
+__device__ __forceinline__ uint32_t pair_lookup(const uint32_t* __restrict__ tab, uint32_t log2, uint32_t l, uint32_t r) {
+    const PairKey key = pair_key(l, r);
     const uint32_t mask = (1u << log2) - 1;
-    uint32_t b = spl_pair_hash(key, log2), out = SPL_RANK_NONE;
+    uint32_t b = spl_pair_hash(l, r, log2), out = SPL_RANK_NONE;
     for (;;) {
         PairBucket k = pair_bucket_load(tab, b);
         int m = pair_bucket_match(k, key, out);
@@ -121,16 +128,16 @@ __device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
     return v;
 }
 
-// three independent pair probes issued back to back (the ranks a merge window needs per candidate, k_bpe)
-__device__ __forceinline__ void pair_lookup3(const uint64_t* __restrict__ tab, uint32_t log2,
+// three independent pair probes issued back to back (the ranks a merge window needs per candidate, k_bpe_long)
+__device__ __forceinline__ void pair_lookup3(const uint32_t* __restrict__ tab, uint32_t log2,
                                              bool va, uint32_t la, uint32_t ra, bool vb, uint32_t lb, uint32_t rb,
                                              bool vc, uint32_t lc, uint32_t rc,
                                              uint32_t& outa, uint32_t& outb, uint32_t& outc) {
     const uint32_t mask = (1u << log2) - 1;
-    const uint64_t ka = spl_pair_key(la, ra), kb = spl_pair_key(lb, rb), kc = spl_pair_key(lc, rc);
-    uint32_t ba = spl_pair_hash(ka, log2), bb = spl_pair_hash(kb, log2), bc = spl_pair_hash(kc, log2);
+    const PairKey ka = pair_key(la, ra), kb = pair_key(lb, rb), kc = pair_key(lc, rc);
+    uint32_t ba = spl_pair_hash(la, ra, log2), bb = spl_pair_hash(lb, rb, log2), bc = spl_pair_hash(lc, rc, log2);
     PairBucket xa, xb, xc;
-    xa.lo = xa.hi = make_ulonglong2(SPL_PAIR_EMPTY, SPL_PAIR_EMPTY);
+    xa.tag = xa.val = make_uint4(SPL_PAIR_EMPTY, SPL_PAIR_EMPTY, SPL_PAIR_EMPTY, SPL_PAIR_EMPTY);
     xb = xa; xc = xa;
     if (va) xa = pair_bucket_load(tab, ba);
     if (vb) xb = pair_bucket_load(tab, bb);
@@ -145,14 +152,14 @@ __device__ __forceinline__ void pair_lookup3(const uint64_t* __restrict__ tab, u
 }
 
 // two independent pair probes issued back to back (the two re-ranks after a merge)
-__device__ __forceinline__ void pair_lookup2(const uint64_t* __restrict__ tab, uint32_t log2,
+__device__ __forceinline__ void pair_lookup2(const uint32_t* __restrict__ tab, uint32_t log2,
                                              bool va, uint32_t la, uint32_t ra, bool vb, uint32_t lb, uint32_t rb,
                                              uint32_t& outa, uint32_t& outb) {
     const uint32_t mask = (1u << log2) - 1;
-    const uint64_t ka = spl_pair_key(la, ra), kb = spl_pair_key(lb, rb);
-    uint32_t ba = spl_pair_hash(ka, log2), bb = spl_pair_hash(kb, log2);
+    const PairKey ka = pair_key(la, ra), kb = pair_key(lb, rb);
+    uint32_t ba = spl_pair_hash(la, ra, log2), bb = spl_pair_hash(lb, rb, log2);
     PairBucket xa, xb;
-    xa.lo = xa.hi = make_ulonglong2(SPL_PAIR_EMPTY, SPL_PAIR_EMPTY);
+    xa.tag = xa.val = make_uint4(SPL_PAIR_EMPTY, SPL_PAIR_EMPTY, SPL_PAIR_EMPTY, SPL_PAIR_EMPTY);
     xb = xa;
     if (va) xa = pair_bucket_load(tab, ba);
     if (vb) xb = pair_bucket_load(tab, bb);

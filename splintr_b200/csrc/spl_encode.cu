@@ -12,7 +12,7 @@
 // No block waits for another block inside a kernel; the miss lists decouple the rare, latency-bound merge loop from
 // the streaming probe so that both run at full occupancy.  Integer / byte work; no tensor cores.
 #include "spl_device.cuh"
-#include "spl_fast_dev.cuh"
+#include "spl_segment.h"
 #include "spl_bpe_bits.h"
 
 // ------------------------------------------------------------------------------------------
@@ -82,23 +82,19 @@ __device__ uint32_t lookupL_warp_g(const SplTables* T, const uint8_t* __restrict
     }
 }
 
-__device__ __forceinline__ uint64_t ml_entry(uint32_t gpos, uint32_t len, uint32_t j) {
-    uint32_t l = len < SPL_ML_LEN_SAT ? len : SPL_ML_LEN_SAT;
-    return (uint64_t)gpos | ((uint64_t)l << 32) | ((uint64_t)j << 52);
+__device__ __forceinline__ uint64_t ml_entry(uint32_t gpos, uint32_t len) {
+    return (uint64_t)gpos | ((uint64_t)(len & SPL_ML_LEN_MASK) << 32);
 }
 
 // ------------------------------------------------------------------------------------------
 // probe_tile: the whole-piece probe of one 4 KiB tile whose text and piece-start bits are staged in shared memory.
 // Called by all threads of the block (barriers inside); threads beyond SPL_THREADS only take part in the barriers.
-//   k_probe         stages one tile from global memory (text + the piece-start bitmap another kernel wrote)
-//   k_pretok_probe  (spl_kernels.cu) computes the piece starts of two tiles itself and stages both from registers:
-//                   DEFER = true, because the piece starts beyond its own words are not in global memory yet
+// k_probe stages the tile from global memory (text + the piece-start bitmap the pre-tokenizer wrote).
 // ------------------------------------------------------------------------------------------
 #define PB_WORDS (SPL_PROBE_WIN / 32u + 1u)          // piece-start words staged: bits 0 .. SPL_PROBE_WIN + 31
 #define PB_BITS  (PB_WORDS * 32u)
 #define PROBE_WARPS (SPL_THREADS / 32)
 
-template <bool DEFER>
 __device__ __forceinline__ void probe_tile(const SplWork& w, SplProbeScratch& sm, const uint32_t* text, const uint32_t* pb,
                                            const uint32_t tile) {
     const SplTables* T = w.T;
@@ -138,8 +134,7 @@ __device__ __forceinline__ void probe_tile(const SplWork& w, SplProbeScratch& sm
     if (tid == 0) {
         uint32_t e = sm_next_bit(pb, SPL_TILE < avail ? SPL_TILE : avail, PB_BITS);
         if (P && e >= PB_BITS) {                                   // the last piece leaves the staged bits
-            if (DEFER) e = SPL_RANK_NONE;                          // its end is some other block's business: see k_probe_rest
-            else e = g_next_bit(w.pstart, tile0 + PB_BITS, N + 1) - tile0;
+            e = g_next_bit(w.pstart, tile0 + PB_BITS, N + 1) - tile0;
         }
         sm.last_end = e;
         sm.plist[P] = (uint16_t)(e >= PB_BITS ? 0xFFFFu : e);      // 0xFFFF: see last_end
@@ -197,13 +192,7 @@ __device__ __forceinline__ void probe_tile(const SplWork& w, SplProbeScratch& sm
             if (e == 0xFFFFu) e = sm.last_end;
             const uint32_t len = e - s, gpos = tile0 + s;
             uint32_t val = SPL_PV_NONE;
-            if (DEFER && e == SPL_RANK_NONE) {
-                // the end of this piece (the tile's last, longer than the staged bits) is not known yet: k_probe_rest
-                // looks it up once every piece start is in global memory and files the piece in its length class
-                const uint32_t di = atomicAdd(&w.counters[SPL_CTR_DEFER], 1u);
-                w.defer_list[di] = (uint64_t)gpos | ((uint64_t)j << 32);
-                val = SPL_PV_NONE - 1u;                            // placeholder (overwritten by k_probe_rest)
-            } else if (w.with_special && ((sm.spw[s >> 5] >> (s & 31)) & 1u)) {
+            if (w.with_special && ((sm.spw[s >> 5] >> (s & 31)) & 1u)) {
                 val = special_id_g(T, w.text + gpos, len);
             } else if (len == 1) {
                 uint32_t sy = T->byte_sym[sm_byte(text, s)];
@@ -247,7 +236,7 @@ __device__ __forceinline__ void probe_tile(const SplWork& w, SplProbeScratch& sm
                 b0 = __shfl_sync(FULL, b0, leader);
                 if (cls == c + 1) {
                     const uint32_t midx = w.ml_base[c] + b0 + __popc(bal & lt_mask);
-                    w.mlist[midx] = ml_entry(mpos, mlen, j);
+                    w.mlist[midx] = ml_entry(mpos, mlen);
                     w.pv[pvbase + j] = SPL_PV_MISS | midx;
                 }
             }
@@ -267,118 +256,15 @@ __device__ __forceinline__ void probe_tile(const SplWork& w, SplProbeScratch& sm
         for (uint32_t i = lane; i < n_short; i += 32) {
             uint32_t j = sm.mloc[jlo + i], s = sm.plist[j], e = sm.plist[j + 1], midx = w.ml_base[0] + g_short + i;
             if (e == 0xFFFFu) e = sm.last_end;
-            w.mlist[midx] = ml_entry(tile0 + s, e - s, j);
+            w.mlist[midx] = ml_entry(tile0 + s, e - s);
             w.pv[pvbase + j] = SPL_PV_MISS | midx;
         }
         for (uint32_t i = lane; i < n_warp; i += 32) {
             uint32_t j = sm.mloc[jhi - 1 - i], s = sm.plist[j], e = sm.plist[j + 1], midx = w.ml_base[1] + g_warp + i;
             if (e == 0xFFFFu) e = sm.last_end;
-            w.mlist[midx] = ml_entry(tile0 + s, e - s, j);
+            w.mlist[midx] = ml_entry(tile0 + s, e - s);
             w.pv[pvbase + j] = SPL_PV_MISS | midx;
         }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// k_pretok_probe: the bit-parallel pre-tokenizer (k_pretok_fast, spl_kernels.cu: same three phases) and the probe of
-// the two tiles it has just decided, in one kernel.  The 32 text bytes every thread classified are still in its
-// registers and so is its word of piece starts: both go to shared memory directly, the text is not read a second
-// time and the probe does not wait for a bitmap round trip through global memory.  Blocks in the (integer-pipe bound)
-// classification phases and blocks in the (L1-wavefront bound) probe phase share an SM.
-// The probe needs the piece starts of SPL_PROBE_HALO + 32 bits beyond its tile: the first FUSE_EXT halo words, which
-// this block computes anyway; they are trusted under the same rule as the payload (no carry from outside the window).
-// A block that cannot decide its words appends its tile to the fallback list exactly like k_pretok_fast and probes
-// nothing; k_pretok_fb and k_probe_rest finish those tiles.
-// ------------------------------------------------------------------------------------------
-#define FUSE_EXT 5u                                   // halo words whose piece starts the probe of the second tile reads
-#define FUSE_TILES (SPL_FAST_PAYLOAD * 32u / SPL_TILE)
-
-struct FusedProbeSmem {
-    uint32_t text[(SPL_FAST_PAYLOAD + FUSE_EXT) * 8u + 8u];     // payload + ext words (+ slack for the unaligned key loads)
-    uint32_t pb[SPL_FAST_PAYLOAD + FUSE_EXT + 1u];
-    SplProbeScratch ps;
-};
-union FusedSmem {
-    FastSmem fast;                                    // phases A-C
-    FusedProbeSmem probe;                             // afterwards
-};
-
-__global__ void __launch_bounds__(SPL_FAST_THREADS, 4) k_pretok_probe(SplWork w) {
-    __shared__ FusedSmem sm;
-    const int k = threadIdx.x;
-    const int gw0 = (int)(blockIdx.x * SPL_FAST_PAYLOAD) - (int)SPL_FAST_HALO;
-    const int gw = gw0 + k;
-    const uint32_t N = w.N;
-    const SplTables* T = w.T;
-    const uint32_t last_word = N >> 5;                        // the word that holds the sentinel bit N
-
-    // ---- phase A: classify my word ------------------------------------------------------------------
-    SplFastWord fw;
-#pragma unroll
-    for (int q = 0; q <= FM_BAD; ++q) fw.m[q] = 0;
-    uint32_t hw = 0, sw = 0;
-    uint32_t xw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (gw >= 0 && (uint32_t)gw <= last_word) {
-        const uint32_t base = (uint32_t)gw * 32u;
-        hw = __ldg(w.hard + gw);
-        if (w.with_special) sw = __ldg(w.spec + gw);
-        if (base < N) {
-            const uint4* p4 = reinterpret_cast<const uint4*>(w.text + base);
-            uint4 a = __ldg(p4);
-            uint4 b = (base + 16u < ((N + 15u) & ~15u)) ? __ldg(p4 + 1) : make_uint4(0, 0, 0, 0);
-            xw[0] = a.x; xw[1] = a.y; xw[2] = a.z; xw[3] = a.w; xw[4] = b.x; xw[5] = b.y; xw[6] = b.z; xw[7] = b.w;
-            FastGText t{w.text};
-            fw = spl_fast_classify(t, xw, base, N, T->ucd_stage1, T->ucd_stage2, w.pattern);
-        }
-    }
-#pragma unroll
-    for (int q = 0; q <= FM_BAD; ++q) sm.fast.m[q][k] = fw.m[q];
-    sm.fast.hardw[k] = hw; sm.fast.specw[k] = sw;
-    __syncthreads();
-
-    // ---- phase B: local masks, fills, summary ------------------------------------------------------------
-    FastMasks M{&sm.fast, gw0, N};
-    SplFastLocal loc;
-    uint32_t s = spl_fast_local(M, k, SPL_FAST_THREADS, w.pattern, loc);
-    sm.fast.sum[k] = s;
-    sm.fast.m[FM_A2][k] = loc.A2; sm.fast.m[FM_A3][k] = loc.A3;
-    __syncthreads();
-
-    // ---- phase C: carries, piece starts --------------------------------------------------------------------
-    bool structural = false, unknown = false;
-    uint32_t start = spl_fast_final(M, loc, k, SPL_FAST_THREADS, w.pattern, w.with_special, structural, unknown);
-    const bool payload = k >= (int)SPL_FAST_HALO && k < (int)(SPL_FAST_HALO + SPL_FAST_PAYLOAD);
-    const bool staged = k >= (int)SPL_FAST_HALO && k < (int)(SPL_FAST_HALO + SPL_FAST_PAYLOAD + FUSE_EXT);
-    int flag = ((s & FS_BAD) != 0) || structural || (staged && unknown);
-    flag = __syncthreads_or(flag);                 // (also: nobody reads sm.fast any more)
-    if (flag) {
-        if (k == 0) {
-            uint32_t idx = atomicAdd(&w.counters[SPL_CTR_FB], 1u);
-            w.fb_list[idx] = blockIdx.x;
-        }
-        return;
-    }
-    if ((uint32_t)gw == last_word) start |= 1u << (N & 31u);
-    if (payload && (uint32_t)gw <= last_word) w.pstart[gw] = start;
-
-    // ---- stage text and piece starts for the probe, from registers ----------------------------------------
-    if (staged) {
-        const uint32_t pk = (uint32_t)k - SPL_FAST_HALO;
-        uint4* dst = reinterpret_cast<uint4*>(sm.probe.text + pk * 8u);
-        dst[0] = make_uint4(xw[0], xw[1], xw[2], xw[3]);
-        dst[1] = make_uint4(xw[4], xw[5], xw[6], xw[7]);
-        sm.probe.pb[pk] = ((uint32_t)gw <= last_word) ? start : 0u;
-    }
-    if (k < 8) sm.probe.text[(SPL_FAST_PAYLOAD + FUSE_EXT) * 8u + k] = 0u;
-    if (k == 8) sm.probe.pb[SPL_FAST_PAYLOAD + FUSE_EXT] = 0u;
-    __syncthreads();
-#pragma unroll 1
-    for (uint32_t sub = 0; sub < FUSE_TILES; ++sub) {
-        const uint32_t tile = blockIdx.x * FUSE_TILES + sub;
-        if (tile >= w.n_tiles) break;
-        if (sub) __syncthreads();                  // the scratch of the previous tile is free
-        if (w.with_special && k < (int)(SPL_TILE / 32)) sm.probe.ps.spw[k] = __ldg(w.spec + tile * (SPL_TILE / 32u) + k);
-        probe_tile<true>(w, sm.probe.ps, sm.probe.text + sub * (SPL_TILE / 4u), sm.probe.pb + sub * (SPL_TILE / 32u), tile);
     }
 }
 
@@ -405,35 +291,7 @@ __device__ __forceinline__ void probe_stage(const SplWork& w, ProbeSmem& sm, con
 __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
     __shared__ ProbeSmem sm;
     probe_stage(w, sm, blockIdx.x);
-    probe_tile<false>(w, sm.ps, sm.text, sm.pb, blockIdx.x);
-}
-
-// After k_pretok_probe + k_pretok_fb: (1) the tiles the bit-parallel pre-tokenizer handed to the sequential rules are
-// probed here, now that their piece starts exist; (2) every deferred piece (see probe_tile) gets its end, its length
-// class and its miss-list entry.
-__global__ void __launch_bounds__(SPL_THREADS) k_probe_rest(SplWork w) {
-    __shared__ ProbeSmem sm;
-    const uint32_t n_fb = w.counters[SPL_CTR_FB];
-    for (uint32_t i = blockIdx.x; i < n_fb; i += gridDim.x) {
-#pragma unroll 1
-        for (uint32_t sub = 0; sub < SPL_FAST_PAYLOAD * 32u / SPL_TILE; ++sub) {
-            const uint32_t tile = w.fb_list[i] * (SPL_FAST_PAYLOAD * 32u / SPL_TILE) + sub;
-            if (tile >= w.n_tiles) break;
-            __syncthreads();
-            probe_stage(w, sm, tile);
-            probe_tile<false>(w, sm.ps, sm.text, sm.pb, tile);
-        }
-    }
-    const uint32_t n_def = w.counters[SPL_CTR_DEFER];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_def; i += gridDim.x * blockDim.x) {
-        const uint64_t d = w.defer_list[i];
-        const uint32_t gpos = (uint32_t)d, j = (uint32_t)(d >> 32);
-        const uint32_t len = g_next_bit(w.pstart, gpos + 1, w.N + 1) - gpos;     // > SPL_PROBE_HALO: k_bpe tries the whole piece
-        const uint32_t c = spl_len_class(len);
-        const uint32_t midx = w.ml_base[c] + atomicAdd(&w.counters[SPL_CTR_CLS + c], 1u);
-        w.mlist[midx] = ml_entry(gpos, len, j);
-        w.pv[(gpos / SPL_TILE) * SPL_TILE + j] = SPL_PV_MISS | midx;
-    }
+    probe_tile(w, sm.ps, sm.text, sm.pb, blockIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -490,7 +348,7 @@ __device__ uint32_t lookupL_serial_g(const SplTables* T, const uint8_t* __restri
 }
 
 __device__ __forceinline__ void bpe_finish(const SplWork& w, uint64_t* slot, uint32_t gpos, uint32_t cnt) {
-    *slot = (uint64_t)gpos | ((uint64_t)cnt << 32);
+    *slot = (uint64_t)gpos | ((uint64_t)cnt << 32) | SPL_ML_DONE;
     if (cnt != 1u) {
         atomicAdd(&w.tinfo[gpos / SPL_TILE].extra, (int32_t)cnt - 1);
         atomicAdd(&w.chunk_cnt[gpos / (SPL_TILE * SPL_CHUNK_TILES)], (int32_t)cnt - 1);
@@ -516,8 +374,9 @@ __device__ uint32_t bpe_seq(uint32_t* reg, const bool valid, const SplTables* T,
     uint32_t* A = reg;                                             // symbol:21 | next:11
     uint32_t* R = reg + 1024;                                      // rank:21 | own position:11  (the scan key)
     uint16_t* P = reinterpret_cast<uint16_t*>(reg + 2048);         // prev
-    const uint64_t* __restrict__ ptab = T->pair;
-    const uint32_t plog = T->pair_log2, pmask = (1u << plog) - 1u;
+    const uint32_t* __restrict__ ptab = T->pair;
+    const uint32_t plog = T->pair_log2;
+    const uint32_t* __restrict__ bpair = T->bpair;
 #define IDX(e) ((((e) >> LG) << 5) + (p << LG) + ((e) & (G - 1u)))
     bool act = valid;
     {
@@ -533,42 +392,23 @@ __device__ uint32_t bpe_seq(uint32_t* reg, const bool valid, const SplTables* T,
     const bool whole = valid && !act;
     const uint32_t rows = act ? (n + G - 1u - g) >> LG : 0u;      // parts of this lane: e = g + it * G, at word it * 32 + lane
     const uint32_t rows4 = (rows + 3u) & ~3u;                      // the scan runs four rows at a time
-    // ---- every byte becomes a part ------------------------------------------------------------------
-    // (two passes, each unrolled, so that the loads of several parts are in flight together)
+    // ---- every byte becomes a part; its first rank comes from the dense byte x byte table (no hashing) ----------
 #pragma unroll 4
     for (uint32_t it = 0; it < rows; ++it) A[it * 32u + lane] = __ldg(tx + g + (it << LG));
+    for (uint32_t it = rows; it < rows4; ++it) R[it * 32u + lane] = BG_RANK_NONE << 11;
+    __syncwarp();
+#pragma unroll 4
+    for (uint32_t it = 0; it < rows; ++it) {
+        const uint32_t e = g + (it << LG);
+        const uint32_t r = e + 1 < n ? __ldg(bpair + ((A[it * 32u + lane] << 8) | A[IDX(e + 1)])) : SPL_RANK_NONE;
+        R[it * 32u + lane] = ((r & BG_RANK_NONE) << 11) | e;
+        P[it * 32u + lane] = (uint16_t)(e ? e - 1 : BG_LINK_NONE);
+    }
+    __syncwarp();
 #pragma unroll 4
     for (uint32_t it = 0; it < rows; ++it) {
         const uint32_t e = g + (it << LG);
         A[it * 32u + lane] = (T->byte_sym[A[it * 32u + lane]] << 11) | (e + 1 < n ? e + 1 : BG_LINK_NONE);
-    }
-    for (uint32_t it = rows; it < rows4; ++it) R[it * 32u + lane] = BG_RANK_NONE << 11;
-    __syncwarp();
-    // ---- ranks of the adjacent pairs, two independent probes in flight per lane ----------------------
-    for (uint32_t it = 0; it < rows; it += 2) {
-        PairBucket bk[2];
-        uint64_t key[2];
-        uint32_t bb[2];
-#pragma unroll
-        for (uint32_t q = 0; q < 2; ++q) {
-            const uint32_t e = g + (it + q) * G;
-            if (e + 1 < n) {
-                key[q] = spl_pair_key(A[(it + q) * 32u + lane] >> 11, A[IDX(e + 1)] >> 11);
-                bb[q] = spl_pair_hash(key[q], plog);
-                bk[q] = pair_bucket_load(ptab, bb[q]);
-            }
-        }
-#pragma unroll
-        for (uint32_t q = 0; q < 2; ++q) {
-            const uint32_t e = g + (it + q) * G;
-            if (e < n) {
-                uint32_t r = SPL_RANK_NONE;
-                if (e + 1 < n)
-                    while (pair_bucket_match(bk[q], key[q], r) == 2) { bb[q] = (bb[q] + 1) & pmask; bk[q] = pair_bucket_load(ptab, bb[q]); }
-                R[(it + q) * 32u + lane] = ((r & BG_RANK_NONE) << 11) | e;
-                P[(it + q) * 32u + lane] = (uint16_t)(e ? e - 1 : BG_LINK_NONE);
-            }
-        }
     }
     __syncwarp();
     // ---- merge loop --------------------------------------------------------------------------------------
@@ -635,8 +475,9 @@ __device__ uint32_t bpe_group(uint32_t* reg, const bool valid, const SplTables* 
     uint16_t* WL = reinterpret_cast<uint16_t*>(reg + 3u * BG_ARR); // worklist of the round: every m-pair of the warp (<= 512)
     uint32_t* LW = reg + 3u * BG_ARR + 256u;                       // per lane: part count of its piece | B << 16
     uint32_t* TH = LW + 32u;                                       // per group (at its first lane): theta
-    const uint64_t* __restrict__ ptab = T->pair;
-    const uint32_t plog = T->pair_log2, pmask = (1u << plog) - 1u;
+    const uint32_t* __restrict__ ptab = T->pair;
+    const uint32_t plog = T->pair_log2;
+    const uint32_t* __restrict__ bpair = T->bpair;
     // part e of the group that starts at lane gs: one pad word per 32 parts, so lanes that walk their blocks in step hit 32 banks
 #define ADR(gs, e) ((gs) * 33u + (e) + ((e) >> 5))
 #define AD(e) ADR(gsh, e)
@@ -658,35 +499,20 @@ __device__ uint32_t bpe_group(uint32_t* reg, const bool valid, const SplTables* 
     uint32_t B = max(2u, (L + G - 1u) >> LG);                      // parts per lane: lane g owns [g * B, g * B + B)
     {
         const uint32_t e0 = g * B, nv = e0 < L ? min(B, L - e0) : 0u;
-        // ---- every byte becomes a part (the lanes of the group read consecutive bytes)
+        // ---- every byte becomes a part (the lanes of the group read consecutive bytes); its first rank comes from
+        // the dense byte x byte table (no hashing)
 #pragma unroll 4
-        for (uint32_t i = g; i < L; i += G) S[AD(i)] = T->byte_sym[__ldg(tx + i)];
+        for (uint32_t i = g; i < L; i += G) S[AD(i)] = __ldg(tx + i);
         __syncwarp();
-        // ---- ranks of the adjacent pairs, two independent probes in flight per lane
-        for (uint32_t j = 0; j < nv; j += 2) {
-            PairBucket bk[2];
-            uint64_t key[2];
-            uint32_t bb[2];
-#pragma unroll
-            for (uint32_t q = 0; q < 2; ++q) {
-                const uint32_t e = e0 + j + q;
-                if (j + q < nv && e + 1 < L) {
-                    key[q] = spl_pair_key(S[AD(e)], S[AD(e + 1)]);
-                    bb[q] = spl_pair_hash(key[q], plog);
-                    bk[q] = pair_bucket_load(ptab, bb[q]);
-                }
-            }
-#pragma unroll
-            for (uint32_t q = 0; q < 2; ++q) {
-                const uint32_t e = e0 + j + q;
-                if (j + q < nv) {
-                    uint32_t r = SPL_RANK_NONE;
-                    if (e + 1 < L)
-                        while (pair_bucket_match(bk[q], key[q], r) == 2) { bb[q] = (bb[q] + 1) & pmask; bk[q] = pair_bucket_load(ptab, bb[q]); }
-                    K[AD(e)] = r & NONE;
-                }
-            }
+#pragma unroll 4
+        for (uint32_t j = 0; j < nv; ++j) {
+            const uint32_t e = e0 + j;
+            const uint32_t r = e + 1 < L ? __ldg(bpair + ((S[AD(e)] << 8) | S[AD(e + 1)])) : SPL_RANK_NONE;
+            K[AD(e)] = r & NONE;
         }
+        __syncwarp();
+#pragma unroll 4
+        for (uint32_t i = g; i < L; i += G) S[AD(i)] = T->byte_sym[S[AD(i)]];
         __syncwarp();
     }
     // ---- merge rounds ------------------------------------------------------------------------------------
@@ -822,6 +648,161 @@ __device__ uint32_t bpe_group(uint32_t* reg, const bool valid, const SplTables* 
     return c;
 }
 
+// ------------------------------------------------------------------------------------------
+// k_bpe: the segment walker.  ONE LANE PER PIECE, whatever its length.
+//
+// A lane walks its piece character by character and cuts it into independent segments (spl_segment.h: no vocabulary
+// key can lie across a safe boundary, so the merge loop of bpe.rs:83-194 runs per segment and the id lists
+// concatenate).  A segment that is one 2- or 3-byte character is ONE table load (char_tok: what the merge loop makes
+// of that character); any other segment of up to SPL_SEG_MAX bytes goes through the merge loop right here, in the
+// lane's own two rows of shared memory:
+//     S[i] = symbol of the part that starts at byte i          K[i] = rank of (part at i, next part) << 5 | i
+// Which bytes still start a part is a 32-bit mask in a register, so the neighbours of a part are two bit scans and the
+// reference's linked list (bpe.rs:42-54) needs no memory.  The minimum over K is the lowest rank at the leftmost
+// position -- exactly the pair bpe.rs:121-138 selects; it is found with 16-byte loads (rows are 36 words apart: 16-byte
+// aligned, and the eight lanes of a quarter warp cover all 32 banks).  The first rank of every part comes from the
+// dense byte x byte table (one 4-byte load, no hashing); the two re-ranks after a merge (bpe.rs:146-166) are two
+// 256-bit bucket loads in flight together.
+// The lanes of a warp alternate between two phases in step: (A) walk until the lane holds a segment for the merge
+// loop or its piece is done; (B) all lanes that hold a segment run the merge loop side by side.
+// A piece with a segment beyond SPL_SEG_MAX bytes (long runs of ASCII letters or punctuation) is left to k_bpe_long.
+// CJK text: 97 % of the character boundaries of cfg5 are safe and 93 % of its segments are single characters; its longest
+// segment is 15 bytes (tools/seg_stats.py).
+// ------------------------------------------------------------------------------------------
+#define WK_STRIDE 36u                                  // words between the rows of two lanes
+#define WK_WORDS  (2u * 32u * WK_STRIDE)               // per warp: 32 K rows, 32 S rows
+#define WK_NONE   (BG_RANK_NONE << 5)
+#define WK_SMEM_BYTES ((SPL_BPE_THREADS / 32) * WK_WORDS * 4)
+
+// four text bytes from byte index gi on (little endian); never reads beyond the 16-byte padded end of the text
+__device__ __forceinline__ uint32_t text_load4(const uint8_t* __restrict__ text, uint32_t gi, uint32_t n_up) {
+    const uint32_t a0 = gi & ~3u;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(text + a0);
+    const uint32_t a = __ldg(wp), b = (a0 + 4u < n_up) ? __ldg(wp + 1) : 0u;
+    return __funnelshift_r(a, b, (gi & 3u) * 8u);
+}
+
+struct WalkReader {
+    const uint8_t* __restrict__ p; uint32_t g0, n_up;                  // piece start, its global index, padded text end
+    __device__ __forceinline__ uint32_t load4(uint32_t i) const { return text_load4(p - g0, g0 + i, n_up); }
+};
+
+__device__ __forceinline__ void walker_task(const SplWork& w, const SplTables* __restrict__ T, uint32_t* __restrict__ Krow,
+                                            uint32_t* __restrict__ Srow, uint64_t* slot, const bool valid) {
+    const uint8_t* __restrict__ text = w.text;
+    const uint32_t n_up = (w.N + 15u) & ~15u;
+    const uint32_t* __restrict__ ptab = T->pair;
+    const uint32_t plog = T->pair_log2;
+    const uint32_t* __restrict__ bpair = T->bpair;
+    const uint32_t* __restrict__ irr = T->seg_irr;
+    const uint32_t* __restrict__ h2 = T->seg_h2;
+    const uint32_t h2log = T->seg_h2_log2;
+    const uint32_t* __restrict__ ctok = T->char_tok;
+
+    uint64_t e = valid ? *slot : SPL_ML_DONE;
+    const bool todo = !(e & SPL_ML_DONE);
+    const uint32_t gpos = (uint32_t)e, len = todo ? (uint32_t)(e >> 32) & SPL_ML_LEN_MASK : 0u;
+    uint32_t* __restrict__ out = w.pool + gpos;
+    const WalkReader rd{text + gpos, gpos, n_up};
+    uint32_t pos = 0, cnt = 0;
+    bool bail = false, taint = false;
+
+    for (;;) {
+        // ---- phase A: walk to the next segment that needs the merge loop -------------------------------------
+        uint32_t seg0 = 0, n = 0;
+        while (pos < len && !bail) {
+            uint32_t a_first, la_first, w4;
+            const uint32_t end = spl_segment_end(rd, pos, len, taint, irr, h2, h2log, a_first, la_first, w4);
+            const uint32_t sl = end - pos;
+            if (sl > SPL_SEG_MAX) { bail = true; break; }
+            if (sl == 1u) {
+                const uint32_t sy = T->byte_sym[w4 & 0xFFu];
+                if (sy < SPL_UNK_BASE) out[cnt++] = sy;               // unknown byte: no id (bpe.rs:73-75, 187-191)
+                pos = end;
+                continue;
+            }
+            if (sl == la_first && sl <= 3u) {                         // one 2- or 3-byte character
+                const uint32_t id = __ldg(ctok + spl_u8_cp23(a_first, sl));
+                if (id != SPL_RANK_NONE) { out[cnt++] = id; pos = end; continue; }
+            }
+            seg0 = pos; n = sl; pos = end;
+            break;
+        }
+        if (!__any_sync(FULL, n != 0u)) break;
+        if (n == 0u) continue;
+
+        // ---- phase B: the merge loop over the segment [seg0, seg0 + n) ------------------------------------------
+        {
+            uint32_t prevb = 0;
+            for (uint32_t i = 0; i < n; i += 4u) {
+                uint32_t w4 = text_load4(text, gpos + seg0 + i, n_up);
+#pragma unroll
+                for (uint32_t q = 0; q < 4u; ++q) {
+                    const uint32_t b = w4 & 0xFFu;
+                    w4 >>= 8;
+                    if (i + q < n) {
+                        Srow[i + q] = T->byte_sym[b];
+                        if (i + q) Krow[i + q - 1u] = ((__ldg(bpair + ((prevb << 8) | b)) & BG_RANK_NONE) << 5) | (i + q - 1u);
+                        prevb = b;
+                    }
+                }
+            }
+            Krow[n - 1u] = WK_NONE | (n - 1u);
+            for (uint32_t i = n; i < ((n + 3u) & ~3u); ++i) Krow[i] = 0xFFFFFFFFu;
+        }
+        uint32_t live = n >= 32u ? 0xFFFFFFFFu : (1u << n) - 1u;
+        const uint32_t n4 = (n + 3u) >> 2;
+        for (;;) {
+            uint32_t key = 0xFFFFFFFFu;
+            const uint4* k4 = reinterpret_cast<const uint4*>(Krow);
+            for (uint32_t it = 0; it < n4; ++it) {
+                const uint4 v = k4[it];
+                key = min(min(key, v.x), min(v.y, min(v.z, v.w)));
+            }
+            const uint32_t r = key >> 5;
+            if (r == BG_RANK_NONE) break;
+            const uint32_t p = key & 31u;                                   // the pair (part at p, next part): p <= 30
+            const uint32_t upper = live & ~((2u << p) - 1u);
+            const uint32_t j = (uint32_t)__ffs(upper) - 1u;                 // the part being absorbed
+            const uint32_t upper2 = upper & (upper - 1u);
+            const uint32_t lower = live & ((1u << p) - 1u);
+            const bool has_k = upper2 != 0u, has_h = lower != 0u;
+            const uint32_t k = has_k ? (uint32_t)__ffs(upper2) - 1u : 0u, h = has_h ? 31u - (uint32_t)__clz(lower) : 0u;
+            const uint32_t symk = Srow[k], symh = Srow[h];
+            live &= ~(1u << j);
+            Srow[p] = r;                                                    // merged id == its rank
+            Krow[j] = WK_NONE | j;
+            uint32_t ra, rb;
+            pair_lookup2(ptab, plog, has_k, r, symk, has_h, symh, r, ra, rb);
+            Krow[p] = ((ra & BG_RANK_NONE) << 5) | p;
+            if (has_h) Krow[h] = ((rb & BG_RANK_NONE) << 5) | h;
+        }
+        for (uint32_t m = live; m; m &= m - 1u) {
+            const uint32_t sy = Srow[(uint32_t)__ffs(m) - 1u];
+            if (sy < SPL_UNK_BASE) out[cnt++] = sy;                         // unknown bytes produce no id (bpe.rs:187-191)
+        }
+    }
+    if (todo && !bail) bpe_finish(w, slot, gpos, cnt);
+}
+
+__global__ void __launch_bounds__(SPL_BPE_THREADS, 6) k_bpe(SplWork w) {
+    extern __shared__ __align__(16) uint32_t bpe_smem[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t gwarp = blockIdx.x * (SPL_BPE_THREADS / 32) + warp, nwarps = gridDim.x * (SPL_BPE_THREADS / 32);
+    uint32_t* Krow = bpe_smem + warp * WK_WORDS + lane * WK_STRIDE;
+    uint32_t* Srow = Krow + 32u * WK_STRIDE;
+    const SplTables* T = w.T;
+    // the longest pieces first, so that the tail of the kernel is short work
+    for (int c = SPL_NCLS - 1; c >= 0; --c) {
+        const uint32_t n = w.counters[SPL_CTR_CLS + c];
+        const uint32_t tasks = (n + 31u) >> 5;
+        for (uint32_t t = gwarp; t < tasks; t += nwarps) {
+            const uint32_t pi = t * 32u + lane;
+            walker_task(w, T, Krow, Srow, &w.mlist[w.ml_base[c] + (pi < n ? pi : 0u)], pi < n);
+        }
+    }
+}
+
 template <uint32_t LG, bool WINDOWED>
 __device__ void bpe_class(const SplWork& w, uint32_t c, uint32_t* reg, uint32_t gwarp, uint32_t nwarps) {
     const uint32_t n = w.counters[SPL_CTR_CLS + c];
@@ -834,10 +815,12 @@ __device__ void bpe_class(const SplWork& w, uint32_t c, uint32_t* reg, uint32_t 
     const uint32_t tasks = (n + ppw - 1) / ppw;
     for (uint32_t t = gwarp; t < tasks; t += nwarps) {
         const uint32_t pi = t * ppw + (lane >> LG);
-        const bool valid = (lane >> LG) < ppw && pi < n;
+        bool valid = (lane >> LG) < ppw && pi < n;
         uint64_t* slot = &w.mlist[w.ml_base[c] + (valid ? pi : 0u)];
         const uint64_t e = *slot;
-        const uint32_t gpos = (uint32_t)e, len = (uint32_t)(e >> 32) & SPL_ML_LEN_SAT;
+        valid = valid && !(e & SPL_ML_DONE);                          // the segment walker (k_bpe) has settled this piece
+        if (!__any_sync(FULL, valid)) continue;
+        const uint32_t gpos = (uint32_t)e, len = (uint32_t)(e >> 32) & SPL_ML_LEN_MASK;
         uint32_t cnt;
         if constexpr (WINDOWED) cnt = bpe_group<LG>(reg, valid, w.T, w.text + gpos, len, w.pool + gpos);
         else cnt = bpe_seq<LG>(reg, valid, w.T, w.text + gpos, len, w.pool + gpos);
@@ -971,25 +954,10 @@ __device__ void chunk_scan_block(const SplWork& w, uint32_t* smem) {
     }
 }
 
-// k_bpe_long: the classes from win_cls up by windowed rounds (13.6 KiB of shared memory per warp), then the huge class.
-// k_bpe: the classes below win_cls, one merge per step (10 KiB per warp: five blocks per SM -- those pieces wait on
-// dependent table probes, so resident warps are what counts).
+// k_bpe_long: what the segment walker left (pieces with a segment beyond SPL_SEG_MAX bytes).  Class 2 (33..64 bytes):
+// one merge per step by two lanes per piece; the classes from win_cls up: windowed rounds (13.6 KiB of shared memory
+// per warp); then the huge class.
 #define BPE_SEQ_WORDS 2560u                            // A[1024] + R[1024] + P[1024 x u16]
-#define BPE_SEQ_SMEM_BYTES ((SPL_BPE_THREADS / 32) * BPE_SEQ_WORDS * 4)
-__global__ void __launch_bounds__(SPL_BPE_THREADS, 5) k_bpe(SplWork w, const uint32_t win_cls) {
-    extern __shared__ __align__(16) uint32_t bpe_smem[];
-    const uint32_t warp = threadIdx.x >> 5;
-    const uint32_t gwarp = blockIdx.x * (SPL_BPE_THREADS / 32) + warp, nwarps = gridDim.x * (SPL_BPE_THREADS / 32);
-    uint32_t* reg = bpe_smem + warp * BPE_SEQ_WORDS;
-    // the longest pieces first, so that the tail of the kernel is short work
-    if (win_cls > 5u) bpe_class<4, false>(w, 5, reg, gwarp, nwarps);
-    if (win_cls > 4u) bpe_class<3, false>(w, 4, reg, gwarp, nwarps);
-    if (win_cls > 3u) bpe_class<2, false>(w, 3, reg, gwarp, nwarps);
-    if (win_cls > 2u) bpe_class<1, false>(w, 2, reg, gwarp, nwarps);
-    bpe_class<0, false>(w, 1, reg, gwarp, nwarps);
-    bpe_class<0, false>(w, 0, reg, gwarp, nwarps);
-}
-
 __global__ void __launch_bounds__(SPL_BPE_THREADS, 4) k_bpe_long(SplWork w, const uint32_t win_cls) {
     extern __shared__ __align__(16) uint32_t bpe_smem[];
     __shared__ uint32_t s_bcast, s_off;
@@ -997,11 +965,12 @@ __global__ void __launch_bounds__(SPL_BPE_THREADS, 4) k_bpe_long(SplWork w, cons
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     const uint32_t gwarp = blockIdx.x * (SPL_BPE_THREADS / 32) + warp, nwarps = gridDim.x * (SPL_BPE_THREADS / 32);
     uint32_t* reg = bpe_smem + warp * BG_WORDS;
+    // the longest pieces first, so that the tail of the kernel is short work
     bpe_class<5, true>(w, 6, reg, gwarp, nwarps);
-    if (win_cls <= 5u) bpe_class<4, true>(w, 5, reg, gwarp, nwarps);
-    if (win_cls <= 4u) bpe_class<3, true>(w, 4, reg, gwarp, nwarps);
-    if (win_cls <= 3u) bpe_class<2, true>(w, 3, reg, gwarp, nwarps);
-    if (win_cls <= 2u) bpe_class<1, true>(w, 2, reg, gwarp, nwarps);
+    if (win_cls <= 5u) bpe_class<4, true>(w, 5, reg, gwarp, nwarps); else bpe_class<4, false>(w, 5, reg, gwarp, nwarps);
+    if (win_cls <= 4u) bpe_class<3, true>(w, 4, reg, gwarp, nwarps); else bpe_class<3, false>(w, 4, reg, gwarp, nwarps);
+    if (win_cls <= 3u) bpe_class<2, true>(w, 3, reg, gwarp, nwarps); else bpe_class<2, false>(w, 3, reg, gwarp, nwarps);
+    if (win_cls <= 2u) bpe_class<1, true>(w, 2, reg, gwarp, nwarps); else bpe_class<1, false>(w, 2, reg, gwarp, nwarps);
     // ---- huge class: whole block, global scratch ----------------------------------------------------
     {
         const uint32_t n = w.counters[SPL_CTR_CLS + SPL_NCLS - 1];
@@ -1011,6 +980,7 @@ __global__ void __launch_bounds__(SPL_BPE_THREADS, 4) k_bpe_long(SplWork w, cons
             for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
                 uint64_t* slot = &w.mlist[w.ml_base[SPL_NCLS - 1] + i];
                 uint64_t e = *slot;
+                if (e & SPL_ML_DONE) continue;                 // the segment walker has settled this piece (block-uniform)
                 uint32_t gpos = (uint32_t)e;
                 if (tid == 0) {
                     uint32_t ge = g_next_bit(w.pstart, gpos + 1, w.N + 1);
@@ -1066,7 +1036,7 @@ __device__ __forceinline__ uint32_t emit_count(const SplWork& w, uint32_t v, boo
     if (!valid) return 0u;
     if (v < SPL_PV_MISS) return 1u;
     if (v == SPL_PV_NONE) return 0u;
-    return (uint32_t)(w.mlist[v & ~SPL_PV_MISS] >> 32);
+    return (uint32_t)(w.mlist[v & ~SPL_PV_MISS] >> 32) & SPL_ML_LEN_MASK;
 }
 
 __global__ void __launch_bounds__(SPL_THREADS, 8) k_emit(SplWork w) {
@@ -1163,7 +1133,7 @@ __global__ void __launch_bounds__(SPL_THREADS, 8) k_emit(SplWork w) {
                     if (x < SPL_PV_MISS) out[pos++] = x;
                     else if (x != SPL_PV_NONE) {
                         const uint64_t e = w.mlist[x & ~SPL_PV_MISS];
-                        const uint32_t gp = (uint32_t)e, c = (uint32_t)(e >> 32);
+                        const uint32_t gp = (uint32_t)e, c = (uint32_t)(e >> 32) & SPL_ML_LEN_MASK;
                         if (c <= EM_INLINE) {
                             for (uint32_t r = 0; r < c; ++r) out[pos + r] = w.pool[gp + r];
                         } else {
@@ -1209,30 +1179,18 @@ __global__ void __launch_bounds__(SPL_THREADS, 8) k_emit(SplWork w) {
 // ------------------------------------------------------------------------------------------
 void spl_encode_init() {
     cudaFuncSetAttribute(k_bpe_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BPE_SMEM_BYTES);
-    cudaFuncSetAttribute(k_bpe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BPE_SEQ_SMEM_BYTES);
+    cudaFuncSetAttribute(k_bpe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WK_SMEM_BYTES);
     cudaFuncSetAttribute(k_probe, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
-    cudaFuncSetAttribute(k_probe_rest, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
-    cudaFuncSetAttribute(k_pretok_probe, cudaFuncAttributePreferredSharedMemoryCarveout, 75);
     cudaFuncSetAttribute(k_emit, cudaFuncAttributePreferredSharedMemoryCarveout, 75);
     cudaGetLastError();
 }
 
-void spl_launch_pretok_probe(const SplWork& w, cudaStream_t stream) {
-    k_pretok_probe<<<w.n_fast_tiles, SPL_FAST_THREADS, 0, stream>>>(w);
-}
-
-void spl_launch_encode_stage(const SplWork& w, int num_sms, cudaStream_t stream, SplMarkFn mark, void* ctx, bool probed) {
-    if (probed) {
-        // k_pretok_probe has probed every tile the bit-parallel pre-tokenizer decided; the rest + deferred pieces here
-        k_probe_rest<<<(uint32_t)num_sms * 2u, SPL_THREADS, 0, stream>>>(w);
-        mark(ctx, "k_probe_rest");
-    } else {
-        k_probe<<<w.n_tiles, SPL_THREADS, 0, stream>>>(w);
-        mark(ctx, "k_probe");
-    }
+void spl_launch_encode_stage(const SplWork& w, int num_sms, cudaStream_t stream, SplMarkFn mark, void* ctx) {
+    k_probe<<<w.n_tiles, SPL_THREADS, 0, stream>>>(w);
+    mark(ctx, "k_probe");
     // first length class merged by windowed rounds (measured crossover; SPL_BPE_WIN_CLS overrides it for experiments)
     static const uint32_t win_cls = [] { const char* e = getenv("SPL_BPE_WIN_CLS"); return e ? (uint32_t)atoi(e) : SPL_BPE_WIN_CLS; }();
-    k_bpe<<<(uint32_t)num_sms * 5u, SPL_BPE_THREADS, BPE_SEQ_SMEM_BYTES, stream>>>(w, win_cls);
+    k_bpe<<<(uint32_t)num_sms * 6u, SPL_BPE_THREADS, WK_SMEM_BYTES, stream>>>(w);
     mark(ctx, "k_bpe");
     k_bpe_long<<<(uint32_t)num_sms * 4u, SPL_BPE_THREADS, BPE_SMEM_BYTES, stream>>>(w, win_cls);   // + the chunk scan, by its last block
     mark(ctx, "k_bpe_long");

@@ -1,5 +1,6 @@
 // Host-side table construction; see spl_host.h.
 #include "spl_host.h"
+#include "spl_segment.h"
 #include <algorithm>
 #include <cstring>
 
@@ -128,16 +129,38 @@ uint64_t spl_host_hashL(const uint8_t* p, uint32_t len) {
 }
 
 uint32_t spl_host_lookup_pair(const SplHostTables& t, uint32_t l, uint32_t r) {
-    uint64_t key = spl_pair_key(l, r);
+    const uint32_t tag = spl_pair_tag(l, r), hi = spl_pair_hi(l);
     uint32_t mask = (1u << t.pair_log2) - 1;
-    uint32_t b = spl_pair_hash(key, t.pair_log2);
+    uint32_t b = spl_pair_hash(l, r, t.pair_log2);
     for (;;) {
-        const uint64_t* e = &t.pair[(size_t)b * SPL_PAIR_WAYS];
+        const uint32_t* e = &t.pair[(size_t)b * SPL_PAIR_WORDS];
         for (int k = 0; k < SPL_PAIR_WAYS; ++k)
-            if (e[k] != SPL_PAIR_EMPTY && (e[k] >> SPL_SYM_BITS) == key) return (uint32_t)(e[k] & ((1u << SPL_SYM_BITS) - 1));
-        if (e[SPL_PAIR_WAYS - 1] == SPL_PAIR_EMPTY) return SPL_RANK_NONE;
+            if (e[k] == tag && (e[SPL_PAIR_WAYS + k] & ~SPL_SYM_MASK) == hi) return e[SPL_PAIR_WAYS + k] & SPL_SYM_MASK;
+        if (e[SPL_PAIR_WORDS - 1] == SPL_PAIR_EMPTY) return SPL_RANK_NONE;
         b = (b + 1) & mask;
     }
+}
+
+// The merge loop of bpe.rs:83-194 over the bytes p[0, n) WITHOUT the whole-piece probe (the id list of a segment).
+void spl_host_merge_loop(const SplHostTables& t, const uint8_t* p, uint32_t n, std::vector<uint32_t>& out) {
+    std::vector<uint32_t> sym(n), rnk(n, SPL_RANK_NONE);
+    std::vector<uint8_t> live(n, 1);
+    for (uint32_t i = 0; i < n; ++i) sym[i] = t.byte_sym[p[i]];
+    for (uint32_t i = 0; i + 1 < n; ++i) rnk[i] = spl_host_lookup_pair(t, sym[i], sym[i + 1]);
+    for (;;) {
+        uint32_t best = SPL_RANK_NONE, bi = 0;
+        for (uint32_t i = 0; i < n; ++i) if (rnk[i] < best) { best = rnk[i]; bi = i; }
+        if (best == SPL_RANK_NONE) break;
+        uint32_t j = bi + 1; while (!live[j]) ++j;
+        sym[bi] = best; live[j] = 0; rnk[j] = SPL_RANK_NONE;
+        uint32_t k = j + 1; while (k < n && !live[k]) ++k;
+        rnk[bi] = (k < n) ? spl_host_lookup_pair(t, best, sym[k]) : SPL_RANK_NONE;
+        if (bi > 0) {
+            uint32_t h = bi - 1; while (!live[h]) --h;
+            rnk[h] = spl_host_lookup_pair(t, sym[h], best);
+        }
+    }
+    for (uint32_t i = 0; i < n; ++i) if (live[i] && sym[i] < SPL_UNK_BASE) out.push_back(sym[i]);
 }
 
 uint32_t spl_host_lookup_piece(const SplHostTables& t, const uint8_t* p, uint32_t len) {
@@ -380,7 +403,8 @@ bool spl_build_tables(SplHostTables& t, const uint8_t* vocab, size_t vocab_len, 
 
     // ---- pair table: every split of every key into two symbols ------------------------------
     {
-        std::vector<uint64_t> ents;
+        struct Ent { uint32_t l, r, m; };
+        std::vector<Ent> ents;
         ents.reserve(t.encoder.size() * 3);
         std::string a, b;
         for (auto& kv : t.encoder) {
@@ -402,29 +426,85 @@ bool spl_build_tables(SplHostTables& t, const uint8_t* vocab, size_t vocab_len, 
                     if (it == t.encoder.end()) continue;
                     rs = it->second;
                 }
-                ents.push_back(spl_pair_entry(ls, rs, kv.second));
+                ents.push_back(Ent{ls, rs, kv.second});
             }
         }
         t.n_pairs = ents.size();
         t.pair_log2 = log2_for(ents.size()) - 1;          // buckets of four at load <= 0.25: a probe rarely leaves its home bucket
-        t.pair.assign(((size_t)1 << t.pair_log2) * SPL_PAIR_WAYS, SPL_PAIR_EMPTY);
+        t.pair.assign(((size_t)1 << t.pair_log2) * SPL_PAIR_WORDS, SPL_PAIR_EMPTY);
         uint32_t mask = (1u << t.pair_log2) - 1;
         // low merged rank first: the pairs the merge loop asks for most sit in their home bucket
-        std::sort(ents.begin(), ents.end(), [](uint64_t a, uint64_t b) {
-            uint64_t ma = a & ((1u << SPL_SYM_BITS) - 1), mb = b & ((1u << SPL_SYM_BITS) - 1);
-            return ma != mb ? ma < mb : a < b;
+        std::sort(ents.begin(), ents.end(), [](const Ent& x, const Ent& y) {
+            return x.m != y.m ? x.m < y.m : (x.l != y.l ? x.l < y.l : x.r < y.r);
         });
         t.pair_displaced = 0;
-        for (uint64_t e : ents) {
-            uint32_t b = spl_pair_hash(e >> SPL_SYM_BITS, t.pair_log2);
+        for (const Ent& e : ents) {
+            uint32_t bk = spl_pair_hash(e.l, e.r, t.pair_log2);
             bool home = true;
-            for (;; b = (b + 1) & mask, home = false) {
-                uint64_t* s = &t.pair[(size_t)b * SPL_PAIR_WAYS];
+            for (;; bk = (bk + 1) & mask, home = false) {
+                uint32_t* s = &t.pair[(size_t)bk * SPL_PAIR_WORDS];
                 int k = 0;
-                while (k < SPL_PAIR_WAYS && s[k] != SPL_PAIR_EMPTY) ++k;
-                if (k < SPL_PAIR_WAYS) { s[k] = e; break; }
+                while (k < SPL_PAIR_WAYS && s[SPL_PAIR_WAYS + k] != SPL_PAIR_EMPTY) ++k;
+                if (k < SPL_PAIR_WAYS) { s[k] = spl_pair_tag(e.l, e.r); s[SPL_PAIR_WAYS + k] = e.m | spl_pair_hi(e.l); break; }
             }
             if (!home) ++t.pair_displaced;
+        }
+        // dense copy of the byte x byte corner: the first rank of every part of every piece is one of these
+        t.bpair.assign(65536, SPL_RANK_NONE);
+        for (uint32_t b0 = 0; b0 < 256; ++b0)
+            for (uint32_t b1 = 0; b1 < 256; ++b1)
+                t.bpair[(b0 << 8) | b1] = spl_host_lookup_pair(t, t.byte_sym[b0], t.byte_sym[b1]);
+    }
+
+    // ---- independent segments (spl_segment.h): which character boundaries can no key cross --------------------
+    {
+        t.seg_irr.assign(2048, 0u);
+        std::vector<std::pair<uint32_t, uint32_t>> regular;        // (A, B) packed
+        for (auto& kv : t.encoder) {
+            const uint8_t* k = (const uint8_t*)kv.first.data();
+            const uint32_t n = (uint32_t)kv.first.size();
+            auto word_at = [&](uint32_t i) { uint32_t w = 0; for (uint32_t q = 0; q < 4 && i + q < n; ++q) w |= (uint32_t)k[i + q] << (8 * q); return w; };
+            for (uint32_t q = 0; q + 1 < n; ++q) {
+                if ((k[q + 1] & 0xC0u) == 0x80u) continue;         // never the first byte of a character of the text
+                uint32_t pa = 0, pb = 0;
+                int32_t p = (int32_t)q;
+                while (p >= 0 && (k[p] & 0xC0u) == 0x80u) --p;
+                const uint32_t la = p >= 0 ? spl_u8_char(word_at((uint32_t)p), q + 1 - (uint32_t)p, pa) : 0u;
+                const bool left_ok = la != 0 && (uint32_t)p + la == q + 1;
+                const uint32_t lb = spl_u8_char(word_at(q + 1), n - (q + 1), pb);
+                if (left_ok && lb) {
+                    if (la > 1 || lb > 1) regular.emplace_back(pa, pb);
+                } else {
+                    const uint32_t ci = ((uint32_t)k[q] << 8) | k[q + 1];
+                    t.seg_irr[ci >> 5] |= 1u << (ci & 31);
+                }
+            }
+        }
+        std::sort(regular.begin(), regular.end());
+        regular.erase(std::unique(regular.begin(), regular.end()), regular.end());
+        t.seg_pairs = regular.size();
+        uint32_t lg = 16;
+        while (lg < 26 && ((size_t)1 << lg) < regular.size() * 64) ++lg;       // fill <= 1/64: that many safe boundaries are missed
+        t.seg_h2_log2 = lg;
+        t.seg_h2.assign((size_t)1 << (lg - 5), 0u);
+        for (auto& ab : regular) {
+            const uint32_t hb = spl_seg_hash(ab.first, ab.second, lg);
+            t.seg_h2[hb >> 5] |= 1u << (hb & 31);
+        }
+        // what the merge loop makes of a single 2- or 3-byte character
+        t.char_tok.assign(65536, SPL_RANK_NONE);
+        std::vector<uint32_t> ids;
+        for (uint32_t cp = 0x80; cp < 0x10000; ++cp) {
+            uint8_t u[3];
+            uint32_t L;
+            if (cp < 0x800) { u[0] = (uint8_t)(0xC0 | (cp >> 6)); u[1] = (uint8_t)(0x80 | (cp & 0x3F)); L = 2; }
+            else { u[0] = (uint8_t)(0xE0 | (cp >> 12)); u[1] = (uint8_t)(0x80 | ((cp >> 6) & 0x3F)); u[2] = (uint8_t)(0x80 | (cp & 0x3F)); L = 3; }
+            ids.clear();
+            spl_host_merge_loop(t, u, L, ids);
+            // one id, and none of the bytes dropped as unknown (bpe.rs:187-191 drops them one by one: keep that to the loop)
+            bool known = true;
+            for (uint32_t q = 0; q < L; ++q) known &= t.byte_sym[u[q]] < SPL_UNK_BASE;
+            if (ids.size() == 1 && known) t.char_tok[cp] = ids[0];
         }
     }
 

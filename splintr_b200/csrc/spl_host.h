@@ -25,7 +25,9 @@ struct SplHostTables {
     std::vector<uint8_t>  tok_bytes;
     std::vector<uint32_t> tok_off;
     uint32_t n_ids = 0, max_key_len = 0;
-    std::vector<uint64_t> pair; uint32_t pair_log2 = 0; size_t n_pairs = 0;
+    std::vector<uint32_t> pair; uint32_t pair_log2 = 0; size_t n_pairs = 0;      // buckets of SPL_PAIR_WORDS words
+    std::vector<uint32_t> bpair;                                                  // [65536] dense byte x byte corner of it
+    std::vector<uint32_t> seg_irr, seg_h2, char_tok;  uint32_t seg_h2_log2 = 16; size_t seg_pairs = 0;   // spl_segment.h
     size_t t8_displaced = 0, pair_displaced = 0;         // keys that are not in their home bucket
     uint32_t byte_sym[256];
     // decode (tokenizer.rs:877-897): id -> bytes for every vocabulary id (byte-level keys translated back to raw
@@ -51,3 +53,5 @@ bool spl_build_tables(SplHostTables& t, const uint8_t* vocab, size_t vocab_len, 
 uint32_t spl_host_lookup_piece(const SplHostTables& t, const uint8_t* p, uint32_t len);   // SPL_RANK_NONE if absent
 uint32_t spl_host_lookup_pair(const SplHostTables& t, uint32_t l, uint32_t r);
 uint64_t spl_host_hashL(const uint8_t* p, uint32_t len);
+// merge loop of bpe.rs:83-194 without the whole-piece probe (ids appended to out)
+void spl_host_merge_loop(const SplHostTables& t, const uint8_t* p, uint32_t n, std::vector<uint32_t>& out);

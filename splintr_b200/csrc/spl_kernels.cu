@@ -273,7 +273,6 @@ int spl_launch_encode(const SplWork& w, int num_sms, cudaStream_t stream, SplKer
     MarkCtx mc{prof, stream, 0};
     if (prof) { prof->n = 0; cudaEventRecord(prof->ev[0], stream); }
     auto mark = [&](const char* name) { mark_cb(&mc, name); };
-    bool probed = false;
     {
         uint32_t n = w.n_docs + 1;
         k_mark_docs<<<(n + 255) / 256, 256, 0, stream>>>(w);
@@ -290,13 +289,6 @@ int spl_launch_encode(const SplWork& w, int num_sms, cudaStream_t stream, SplKer
     } else if (w.N && w.pattern == SPL_PAT_MISTRAL_V3) {
         k_pretok<<<(w.N + SPL_TILE - 1) / SPL_TILE, SPL_THREADS, 0, stream>>>(w);
         mark("k_pretok");
-    } else if (w.N && w.fused) {
-        spl_launch_pretok_probe(w, stream);
-        mark("k_pretok_probe");
-        uint32_t cap = (uint32_t)num_sms * 4;
-        k_pretok_fb<<<w.n_fast_tiles < cap ? w.n_fast_tiles : cap, SPL_THREADS, 0, stream>>>(w);
-        mark("k_pretok_fb");
-        probed = true;
     } else if (w.N) {
         k_pretok_fast<<<w.n_fast_tiles, SPL_FAST_THREADS, 0, stream>>>(w);
         mark("k_pretok_fast");
@@ -304,6 +296,6 @@ int spl_launch_encode(const SplWork& w, int num_sms, cudaStream_t stream, SplKer
         k_pretok_fb<<<w.n_fast_tiles < cap ? w.n_fast_tiles : cap, SPL_THREADS, 0, stream>>>(w);
         mark("k_pretok_fb");
     }
-    spl_launch_encode_stage(w, num_sms, stream, mark_cb, &mc, probed);
+    spl_launch_encode_stage(w, num_sms, stream, mark_cb, &mc);
     return mc.launches;
 }

@@ -37,9 +37,10 @@ __host__ __device__ inline uint32_t spl_class_log2group(uint32_t c) { return c <
 // values of SplWork::pv (one per piece, in text order)
 #define SPL_PV_MISS  0x80000000u      // | index of the piece's entry in `mlist`
 #define SPL_PV_NONE  0xFFFFFFFFu      // the piece produces no id (byte unknown to the vocabulary)
-// miss-list entry before k_bpe:  gpos:32 | len:20 (saturating) | piece index in its tile:12
-// miss-list entry after  k_bpe:  gpos:32 | id count:32         (ids at pool[gpos ..])
-#define SPL_ML_LEN_SAT 0xFFFFFu
+// miss-list entry before the merge kernels:  gpos:32 | len:31
+// miss-list entry after:                      gpos:32 | id count:31 | SPL_ML_DONE    (ids at pool[gpos ..])
+#define SPL_ML_LEN_MASK 0x7FFFFFFFu
+#define SPL_ML_DONE (1ull << 63)
 
 // one record per tile, so that k_emit learns everything about its tile (and its chunk) from one line
 struct SplTileInfo {
@@ -70,8 +71,6 @@ struct SplWork {
     uint32_t        ml_base[SPL_NCLS + 1];   // class c owns mlist[ml_base[c] .. ml_base[c+1])
     uint32_t*       counters;         // [SPL_CTR_WORDS]: see SPL_CTR_*
     uint32_t*       fb_list;          // [n_fast_tiles] fast-path tiles handed to the sequential rules
-    uint64_t*       defer_list;       // [n_tiles] fused front end: pieces whose end lies beyond the staged bits (gpos | piece index << 32)
-    bool            fused;            // front end = k_pretok_probe (pre-tokenizer + probe in one kernel)
     uint32_t        n_fast_tiles;
     uint32_t*       huge_pool;        // scratch for pieces that outgrow shared memory
     uint32_t        huge_pool_words;
@@ -87,7 +86,7 @@ struct SplWork {
 };
 
 // SplWork::counters
-enum : uint32_t { SPL_CTR_ERR = 1, SPL_CTR_HUGE_POOL = 2, SPL_CTR_FB = 3, SPL_CTR_DEFER = 5,
+enum : uint32_t { SPL_CTR_ERR = 1, SPL_CTR_HUGE_POOL = 2, SPL_CTR_FB = 3,
                   SPL_CTR_CLS = 8,            // [8 .. 8 + SPL_NCLS): entries in the miss list of each class
                   SPL_CTR_TICKET = 16,        // blocks of k_bpe_long that are done (the last one scans the chunk totals)
                   SPL_CTR_WORDS = 32 };
@@ -166,9 +165,7 @@ void spl_launch_decode_emit(const SplDecLaunch& L, cudaStream_t stream);    // k
 // spl_encode.cu: the encode stage behind the pre-tokenizer (k_probe, k_bpe, k_tile_scan, k_emit)
 typedef void (*SplMarkFn)(void* ctx, const char* name);
 void spl_encode_init();
-// probed: the front end was k_pretok_probe, which has already probed the tiles it decided
-void spl_launch_encode_stage(const SplWork& w, int num_sms, cudaStream_t stream, SplMarkFn mark, void* ctx, bool probed);
-void spl_launch_pretok_probe(const SplWork& w, cudaStream_t stream);   // k_pretok_probe (bit-parallel pre-tokenizer + probe)
+void spl_launch_encode_stage(const SplWork& w, int num_sms, cudaStream_t stream, SplMarkFn mark, void* ctx);
 
 // per-tile scratch of the whole-piece probe (spl_encode.cu: probe_tile)
 struct SplProbeScratch {

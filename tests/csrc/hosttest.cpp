@@ -74,27 +74,48 @@ int ht_scan_chunked(int pattern, const uint8_t* text, uint32_t n, uint32_t chunk
 // (pair table keyed by symbol ids, leftmost minimum, in-place part bitmap).
 #include "../../splintr_b200/csrc/spl_host.h"
 
-static void ht_bpe_piece(const SplHostTables& T, const uint8_t* p, uint32_t n, std::vector<uint32_t>& out) {
+#include "../../splintr_b200/csrc/spl_segment.h"
+
+struct HostPieceReader {
+    const uint8_t* p; uint32_t n;
+    uint32_t load4(uint32_t i) const { uint32_t v = 0; for (uint32_t q = 0; q < 4 && i + q < n; ++q) v |= (uint32_t)p[i + q] << (8 * q); return v; }
+};
+
+static uint64_t ht_seg_stats[4];     // segments, single-character segments, pieces left to the long path, safe boundaries
+
+// The device path for one piece (k_probe + k_bpe's segment walker + k_bpe_long for what the walker leaves):
+// whole-piece probe, then the independent segments of spl_segment.h -- a single 2- or 3-byte character through
+// char_tok, any other segment through the merge loop -- and the whole piece through the merge loop if a segment
+// outgrows SPL_SEG_MAX.
+static void ht_bpe_piece(const SplHostTables& T, const uint8_t* p, uint32_t n, std::vector<uint32_t>& out, bool segments = true) {
     uint32_t whole = spl_host_lookup_piece(T, p, n);
     if (whole != SPL_RANK_NONE) { out.push_back(whole); return; }
-    std::vector<uint32_t> sym(n), rnk(n, SPL_RANK_NONE);
-    std::vector<uint8_t> live(n, 1);
-    for (uint32_t i = 0; i < n; ++i) sym[i] = T.byte_sym[p[i]];
-    for (uint32_t i = 0; i + 1 < n; ++i) rnk[i] = spl_host_lookup_pair(T, sym[i], sym[i + 1]);
-    for (;;) {
-        uint32_t best = SPL_RANK_NONE, bi = 0;
-        for (uint32_t i = 0; i < n; ++i) if (rnk[i] < best) { best = rnk[i]; bi = i; }
-        if (best == SPL_RANK_NONE) break;
-        uint32_t j = bi + 1; while (!live[j]) ++j;
-        sym[bi] = best; live[j] = 0; rnk[j] = SPL_RANK_NONE;
-        uint32_t k = j + 1; while (k < n && !live[k]) ++k;
-        rnk[bi] = (k < n) ? spl_host_lookup_pair(T, best, sym[k]) : SPL_RANK_NONE;
-        if (bi > 0) {
-            uint32_t h = bi - 1; while (!live[h]) --h;
-            rnk[h] = spl_host_lookup_pair(T, sym[h], best);
+    if (n == 1) { if (T.byte_sym[p[0]] < SPL_UNK_BASE) out.push_back(T.byte_sym[p[0]]); return; }
+    if (!segments) { spl_host_merge_loop(T, p, n, out); return; }
+    std::vector<uint32_t> tmp;
+    HostPieceReader rd{p, n};
+    bool taint = false, bail = false;
+    uint32_t pos = 0;
+    while (pos < n) {
+        uint32_t a_first, la_first, w4;
+        const uint32_t end = spl_segment_end(rd, pos, n, taint, T.seg_irr.data(), T.seg_h2.data(), T.seg_h2_log2, a_first, la_first, w4);
+        const uint32_t sl = end - pos;
+        if (sl > SPL_SEG_MAX) { bail = true; break; }
+        ++ht_seg_stats[0];
+        if (end < n) ++ht_seg_stats[3];
+        if (sl == 1) {
+            const uint32_t sy = T.byte_sym[w4 & 0xFF];
+            if (sy < SPL_UNK_BASE) tmp.push_back(sy);
+        } else if (sl == la_first && sl <= 3 && T.char_tok[spl_u8_cp23(a_first, sl)] != SPL_RANK_NONE) {
+            tmp.push_back(T.char_tok[spl_u8_cp23(a_first, sl)]);
+            ++ht_seg_stats[1];
+        } else {
+            spl_host_merge_loop(T, p + pos, sl, tmp);
         }
+        pos = end;
     }
-    for (uint32_t i = 0; i < n; ++i) if (live[i] && sym[i] < SPL_UNK_BASE) out.push_back(sym[i]);
+    if (bail) { ++ht_seg_stats[2]; spl_host_merge_loop(T, p, n, out); }
+    else out.insert(out.end(), tmp.begin(), tmp.end());
 }
 
 extern "C" {
@@ -114,6 +135,21 @@ void ht_stats(void* h, uint64_t* out) {
     out[0] = t->encoder.size(); out[1] = t->n_pairs; out[2] = t->t8_log2; out[3] = t->t16_log2;
     out[4] = t->tl_log2; out[5] = t->pair_log2; out[6] = t->max_key_len; out[7] = t->specials_unambiguous;
     out[8] = t->t8_displaced; out[9] = t->pair_displaced;
+    out[10] = t->seg_pairs; out[11] = t->seg_h2_log2;
+    uint64_t irr = 0; for (uint32_t w : t->seg_irr) irr += __builtin_popcount(w);
+    out[12] = irr;
+    uint64_t ct = 0; for (uint32_t v : t->char_tok) ct += v != SPL_RANK_NONE;
+    out[13] = ct;
+}
+void ht_seg_counters(uint64_t* out, int reset) { for (int i = 0; i < 4; ++i) { out[i] = ht_seg_stats[i]; if (reset) ht_seg_stats[i] = 0; } }
+
+// one piece (no pre-tokenizer): segments != 0 -> the device path, 0 -> whole-piece probe + the plain merge loop
+long ht_encode_piece(void* h, const uint8_t* p, uint32_t n, int segments, uint32_t* ids, size_t cap) {
+    std::vector<uint32_t> out;
+    ht_bpe_piece(*(SplHostTables*)h, p, n, out, segments != 0);
+    if (out.size() > cap) return -2;
+    memcpy(ids, out.data(), out.size() * 4);
+    return (long)out.size();
 }
 
 // encode one segment (no special handling); returns token count or -1

@@ -9,7 +9,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = [os.path.join(ROOT, "tests", "csrc", "hosttest.cpp"), os.path.join(ROOT, "splintr_b200", "csrc", "spl_host.cpp")]
-DEPS = SRC + [os.path.join(ROOT, "splintr_b200", "csrc", f) for f in ("spl_pretok.h", "spl_pretok_fast.h", "spl_sentencepiece.h", "spl_ingest.h", "spl_bpe_bits.h", "spl_common.h", "spl_host.h", "unicode_tables.inc")]
+DEPS = SRC + [os.path.join(ROOT, "splintr_b200", "csrc", f) for f in ("spl_pretok.h", "spl_pretok_fast.h", "spl_sentencepiece.h", "spl_ingest.h", "spl_bpe_bits.h", "spl_segment.h", "spl_common.h", "spl_host.h", "unicode_tables.inc")]
 LIB = os.path.join(ROOT, "tests", "csrc", "libhosttest.so")
 _lib = None
 
@@ -38,6 +38,9 @@ def load():
     lib.ht_stats.argtypes = [vp, vp]
     lib.ht_encode.restype = ctypes.c_long
     lib.ht_encode.argtypes = [vp, ctypes.c_char_p, ctypes.c_uint32, vp, ctypes.c_size_t]
+    lib.ht_encode_piece.restype = ctypes.c_long
+    lib.ht_encode_piece.argtypes = [vp, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_int, vp, ctypes.c_size_t]
+    lib.ht_seg_counters.argtypes = [vp, ctypes.c_int]
     lib.ht_jsonl.restype = ctypes.c_int
     lib.ht_jsonl.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, vp, vp, vp]
     lib.ht_set_fast_ext.argtypes = [ctypes.c_int]
@@ -49,6 +52,13 @@ def load():
     lib.ht_bpe_window_m.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, vp]
     _lib = lib
     return lib
+
+
+def seg_counters(reset: bool = True):
+    """(segments, single-character segments, pieces left to the long path, safe boundaries) since the last reset."""
+    out = np.zeros(4, dtype=np.uint64)
+    load().ht_seg_counters(out.ctypes.data, 1 if reset else 0)
+    return [int(x) for x in out]
 
 
 def bpe_window_m(ranks, G: int, B: int):
@@ -167,10 +177,19 @@ class HostTables:
             raise ValueError(err.value.decode())
 
     def stats(self):
-        out = np.zeros(10, dtype=np.uint64)
+        out = np.zeros(14, dtype=np.uint64)
         load().ht_stats(self.h, out.ctypes.data)
         return dict(zip(["n_keys", "n_pairs", "t8_log2", "t16_log2", "tl_log2", "pair_log2", "max_key_len", "unambiguous",
-                         "t8_displaced", "pair_displaced"], out.tolist()))
+                         "t8_displaced", "pair_displaced", "seg_pairs", "seg_h2_log2", "seg_irr_bits", "char_tok_entries"],
+                        out.tolist()))
+
+    def encode_piece(self, piece: bytes, segments: bool = True):
+        """One piece through the device path's piece encoder (segments=True: whole-piece probe + segment walker;
+        False: whole-piece probe + the plain merge loop of bpe.rs:83-194)."""
+        ids = np.zeros(len(piece) + 1, dtype=np.uint32)
+        n = load().ht_encode_piece(self.h, piece, len(piece), 1 if segments else 0, ids.ctypes.data, len(ids))
+        assert n >= 0, n
+        return ids[:n].tolist()
 
     def encode(self, data: bytes):
         ids = np.zeros(len(data) + 1, dtype=np.uint32)

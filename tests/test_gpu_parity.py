@@ -144,12 +144,14 @@ def test_cfg3_mixed_o200k(toks):
 
 
 def test_cfg4_long_docs_llama3(toks):
-    d, o = synth.cfg4(vocab_bytes("llama3"), 24, 1_000_000.0)
+    """BASELINE.json configs[3] on the 1 % document sample BASELINE.md allows: 100 docs of ~1 MB (100 MB)."""
+    d, o = synth.cfg4(vocab_bytes("llama3"), 100, 1_000_000.0)
     _check_packed(toks("llama3"), c_oracle("llama3"), d, o)
 
 
-def test_cfg5_cjk_deepseek(toks):
-    d, o = synth.cfg5(b"", 30_000)
+def test_cfg5_cjk_deepseek_full_size(toks):
+    """BASELINE.json configs[4] at full size: 100 000 CJK-heavy docs (~150 MB)."""
+    d, o = synth.cfg5(b"", 100_000)
     _check_packed(toks("deepseek_v3"), c_oracle("deepseek_v3"), d, o)
 
 
@@ -171,6 +173,26 @@ def test_merge_rounds_long_pieces(toks, name, monkeypatch):
     assert t.encode_batch(texts) == o.encode_batch(texts)
     docs = ["\n".join(texts[i:i + 20]) for i in range(0, len(texts), 20)]     # many long pieces per warp task
     assert t.encode_batch(docs) == o.encode_batch(docs)
+
+
+@pytest.mark.parametrize("name", VOCABS)
+def test_segment_walker_multiscript(toks, name):
+    """k_bpe, the segment walker (spl_segment.h): multi-script text -- CJK, kana, Hangul, Cyrillic, Hebrew, Arabic, Thai,
+    Devanagari, emoji, accented Latin -- in pieces of every length class, pieces the walker has to leave to k_bpe_long
+    (a segment beyond 32 bytes next to CJK), and keys glued together; against the C oracle."""
+    from test_segments_host import random_piece, CJK_COMMON, CJK_RARE, HANGUL
+    rng = random.Random(2024)
+    texts = [" ".join(random_piece(rng, 14).decode() for _ in range(rng.randint(1, 12))) for _ in range(4000)]
+    texts += ["".join(rng.choice(CJK_COMMON) for _ in range(k)) for k in (1, 2, 5, 10, 11, 12, 21, 22, 43, 85, 170, 171, 341, 342, 400, 1200, 5000)]
+    texts += ["".join(rng.choice(CJK_RARE + HANGUL + CJK_COMMON) for _ in range(rng.randint(1, 200))) for _ in range(400)]
+    # letters longer than a segment in the middle of a CJK run: one piece under O200K (Lo + Ll), the walker leaves it
+    texts += ["".join(rng.choice(CJK_COMMON) for _ in range(rng.randint(1, 30))) + "".join(rng.choice("abcdefgh") for _ in range(rng.randint(30, 200))) +
+              "".join(rng.choice(CJK_COMMON) for _ in range(rng.randint(0, 30))) for _ in range(300)]
+    texts = [t for t in texts if "\u180e" not in t]
+    t, o = toks(name), c_oracle(name)
+    assert t.encode_batch(texts) == o.encode_batch(texts)
+    doc = "\n".join(texts[:1500])
+    assert t.encode(doc) == o.encode_batch([doc])[0]
 
 
 def test_device_resident_entry_point(toks):
@@ -430,31 +452,6 @@ def test_sentencepiece_pipelined_small_chunks(toks, monkeypatch):
     texts[3] = ""; texts[17] = " " * 50_000; texts[18] = ""; texts[-1] = ""
     assert t.encode_batch(texts) == o.encode_batch(texts)
     assert t.pcre2().encode("a  b") == o.encode("a  b")           # clones keep the mode
-
-
-def test_fused_front_end_is_bit_exact(monkeypatch):
-    """SPL_FUSED=1 selects k_pretok_probe (pre-tokenizer + probe in one kernel, deferred list for pieces that leave the
-    staged bits, k_probe_rest for the tiles the bit-parallel path declines) -- not the default (no faster),
-    but kept working: fuzz, long pieces across tile ends, specials, cfg3 / cfg4 samples against the C oracle."""
-    from splintr_b200 import Tokenizer
-    monkeypatch.setenv("SPL_FUSED", "1")
-    toks_f = {n: Tokenizer.from_pretrained(n, devices=[0]) for n in ("cl100k_base", "o200k_base", "llama3")}
-    monkeypatch.delenv("SPL_FUSED")
-    rng = random.Random(321)
-    texts = [t for t in (random_text(rng, 80) for _ in range(3000)) if "᠎" not in t]
-    texts += ["a" * k for k in (4000, 4096, 4097, 8100, 8192, 8193, 8350, 20000)] + [" " * 9000, "x" * 8000 + " " + "y" * 300, "=" * 8400]
-    texts += ["".join(rng.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(rng.randint(100, 900))) + " " for _ in range(200)]
-    for name, t in toks_f.items():
-        o = c_oracle(name)
-        assert t.encode_batch(texts) == o.encode_batch(texts), name
-        assert t.launches_per_call() == 7
-    sp = "<|endoftext|>"
-    st = [x[:40] + sp + x[40:] for x in texts[:300]]
-    assert toks_f["cl100k_base"].encode_batch_with_special(st) == c_oracle("cl100k_base").encode_batch(st, with_special=True)
-    d, off = synth.cfg3(vocab_bytes("o200k_base"), 8000)
-    _check_packed(toks_f["o200k_base"], c_oracle("o200k_base"), d, off)
-    d, off = synth.cfg4(vocab_bytes("llama3"), 6, 1_000_000.0)
-    _check_packed(toks_f["llama3"], c_oracle("llama3"), d, off)
 
 
 # ---- JSON Lines ingestion on the device (SURVEY section 8f, N4) ---------------------------------------------

@@ -1,0 +1,17 @@
+#!/bin/bash
+# Round-2 evidence: GPU tests, per-config kernel times, ncu --set full of the merge kernels on cfg4 / cfg5.
+# Usage: bash tools/gpu_r2a.sh <tag> [pytest -k expression]
+TAG=${1:-r02a}
+K=${2:-}
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build(); g.smoke()" > gpurun_out/smoke_${TAG}.log 2>&1; tail -2 gpurun_out/smoke_${TAG}.log
+if [ -n "$K" ]; then
+  timeout 1500 python -m pytest tests -m gpu -x -q -k "$K" > gpurun_out/pytest_gpu_${TAG}.log 2>&1
+else
+  timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_${TAG}.log 2>&1
+fi
+tail -15 gpurun_out/pytest_gpu_${TAG}.log
+timeout 600 python tools/gpu_cfgs.py > gpurun_out/cfgs_${TAG}.txt 2>&1
+tail -8 gpurun_out/cfgs_${TAG}.txt
+bash tools/gpu_ncu_bpe.sh ${TAG}
+ls -la gpurun_out | tail -8
