@@ -110,13 +110,29 @@ void spl_result_free(spl_result* r);
  * d_ids must hold ids_capacity >= n_bytes entries (worst case: one id per byte; for a SentencePiece-mode
  * handle n_bytes + 2 * (number of spaces) <= 3 * n_bytes, because a space becomes the three bytes of U+2581).
  * Work is enqueued on `cuda_stream` (a cudaStream_t, NULL = legacy default stream).
- * If n_tokens_out is non-NULL the call synchronises the stream and stores the id count;
- * otherwise it returns after enqueueing (d_out_offsets[n_docs] holds the count). */
+ * If n_tokens_out is non-NULL the call synchronises the stream, checks the device-side error flags (invalid
+ * offsets -> SPL_ERR_INVALID_ARG; scratch for pieces beyond 1 KiB exhausted -> the pool is enlarged and the pass
+ * repeated) and stores the id count; otherwise it returns SPL_OK after enqueueing (d_out_offsets[n_docs] holds the
+ * count once the stream has run) and the flags are the caller's to collect: see spl_device_status. */
 int spl_encode_batch_device(spl_tokenizer* tok, int dev_index,
                             const uint8_t* d_bytes, size_t n_bytes,
                             const uint64_t* d_offsets, size_t n_docs, uint32_t flags,
                             uint32_t* d_ids, size_t ids_capacity, uint64_t* d_out_offsets,
                             void* cuda_stream, uint64_t* n_tokens_out);
+
+/* Error flags of the LAST pass enqueued on device `dev_index` by spl_encode_batch_device with n_tokens_out == NULL:
+ * synchronises `cuda_stream` and stores the flags.  0 = the pass is good.  With SPL_STATUS_BAD_OFFSETS no kernel used
+ * the offsets as indices and the output buffers hold nothing; with SPL_STATUS_SCRATCH_EXHAUSTED pieces beyond 1 KiB
+ * produced no ids (call again with n_tokens_out != NULL, which enlarges the pool and repeats the pass). */
+#define SPL_STATUS_BAD_OFFSETS        1u
+#define SPL_STATUS_SCRATCH_EXHAUSTED  2u
+int spl_device_status(spl_tokenizer* tok, int dev_index, void* cuda_stream, uint32_t* flags_out);
+
+/* Diagnostics: the 32 device counters of the last pass on device `dev_index` (synchronises `cuda_stream`):
+ * [1] error flags, [4] tiles the bit-parallel pre-tokenizer handed to the sequential rules, [5] long pieces that repeated
+ * an earlier one (their merge loop was skipped), [6] tiles that went through the refining pass of the probe,
+ * [8 .. 15] pieces filed for the merge loop by length class. */
+int spl_debug_counters(spl_tokenizer* tok, int dev_index, void* cuda_stream, uint32_t* out32);
 
 /* ---- decode (the step on the other side of the path) ------------------------------
  * Replaces, for batches, Tokenizer::decode_bytes / decode_batch (src/core/tokenizer.rs:877-897, 945-958;

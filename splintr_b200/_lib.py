@@ -40,11 +40,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a into splintr_b200/libsplintr_b200.so."""
     if not force and not needs_build():
         return LIB_PATH
+    tmp = f"{LIB_PATH}.{os.getpid()}.tmp"                   # ranks / test workers may get here together: build aside, rename
     cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+        ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    os.replace(tmp, LIB_PATH)
     if verbose:
         print(proc.stderr)
     return LIB_PATH
@@ -110,7 +114,7 @@ EXPORTS = ["spl_create", "spl_destroy", "spl_last_error", "spl_encode_batch", "s
            "spl_result_free", "spl_encode_batch_device", "spl_launches_per_call", "spl_alloc_pinned",
            "spl_free_pinned", "spl_version", "spl_set_profiling", "spl_last_kernel_times",
            "spl_decode_batch", "spl_decode_batch_device", "spl_result_bytes", "spl_result_n_bytes",
-           "spl_ingest_jsonl_device", "spl_encode_jsonl"]
+           "spl_ingest_jsonl_device", "spl_encode_jsonl", "spl_device_status", "spl_debug_counters"]
 
 SPL_OK, SPL_ERR_INVALID_ARG, SPL_ERR_VOCAB, SPL_ERR_CUDA, SPL_ERR_OOM, SPL_ERR_UNSUPPORTED, SPL_ERR_NO_DEVICE = \
     0, -1, -2, -3, -4, -5, -6

@@ -57,7 +57,7 @@ struct DevCtx {
     void* table_blob = nullptr;
     SplTables* d_tables = nullptr;
     DevBuf text, doc_off, ids, out_off;          // spl_encode_batch: the shard's buffers
-    DevBuf zero, tstate, pv, pool, mlist, fbl, huge;
+    DevBuf zero, tstate, pv, pool, mlist, fbl, huge, dupof;
     DevBuf dec_ids, dec_off, dec_ws, dec_out, dec_out_off;       // spl_decode_batch   // per-pass workspace (zero: everything that starts cleared)
     DevBuf jl_tiles, jl_lines;                                   // spl_ingest_jsonl_device: tile counts, per-line arrays
     DevBuf jl_text, jl_off, jl_out_off[2];                       // spl_encode_jsonl: ingested text + offsets, output offsets (alternating)
@@ -75,6 +75,7 @@ struct PinnedBuf { void* p; size_t cap; };
 struct spl_tokenizer {
     bool profiling = false;
     bool trace = false;                     // SPL_TRACE=1: per-chunk timeline of spl_encode_batch on stderr
+    bool dedup = true;                      // SPL_NO_DEDUP=1: every long piece goes through the merge loop, repeated or not
     int trace_chunk = -1;                   // SPL_TRACE_CHUNK=k: with SPL_TRACE, per-kernel times of the k-th chunk
     uint64_t chunk_bytes = 0;               // pipeline chunk size of spl_encode_batch (0 = automatic)
     SplHostTables host;
@@ -163,7 +164,7 @@ int upload_tables(spl_tokenizer* tk, DevCtx& dc) {
 
 void destroy_ctx(DevCtx& dc) {
     cudaSetDevice(dc.device);
-    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.ids, &dc.out_off, &dc.dec_ids, &dc.dec_off, &dc.dec_ws, &dc.dec_out, &dc.dec_out_off, &dc.jl_tiles, &dc.jl_lines, &dc.jl_text, &dc.jl_off, &dc.jl_out_off[0], &dc.jl_out_off[1], &dc.run_tot, &dc.sp_zero, &dc.sp_tiles, &dc.sp_text, &dc.sp_doc, &dc.zero, &dc.tstate, &dc.pv, &dc.pool, &dc.mlist, &dc.fbl, &dc.huge})
+    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.ids, &dc.out_off, &dc.dec_ids, &dc.dec_off, &dc.dec_ws, &dc.dec_out, &dc.dec_out_off, &dc.jl_tiles, &dc.jl_lines, &dc.jl_text, &dc.jl_off, &dc.jl_out_off[0], &dc.jl_out_off[1], &dc.run_tot, &dc.sp_zero, &dc.sp_tiles, &dc.sp_text, &dc.sp_doc, &dc.zero, &dc.tstate, &dc.pv, &dc.pool, &dc.mlist, &dc.fbl, &dc.huge, &dc.dupof})
         b->release();
     if (dc.table_blob) cudaFree(dc.table_blob);
     for (auto& e : dc.ev) if (e) cudaEventDestroy(e);
@@ -178,13 +179,18 @@ void destroy_ctx(DevCtx& dc) {
 // limits of one device shard: 32-bit positions inside the kernels
 const uint64_t kMaxShardBytes = 0xFFFFFFFFull - 4ull * SPL_WIN;
 
-// layout of the zero-initialised region: counters | chunk_cnt | tinfo | hard | pstart | spec
-struct ZeroLayout { size_t words, n_tiles, off_chunk, off_extra, off_hard, off_pstart, off_spec, total; };
-ZeroLayout zero_layout(uint64_t N, bool with_special) {
+// layout of the zero-initialised region: counters | duplicate table | chunk_cnt | tinfo | hard | pstart | spec
+struct ZeroLayout { size_t words, n_tiles, dd_slots, off_dd, off_chunk, off_extra, off_hard, off_pstart, off_spec, total; };
+ZeroLayout zero_layout(uint64_t N, bool with_special, bool dedup) {
     ZeroLayout z;
     z.words = (size_t)((N + SPL_WIN) / 32 + 16);
     z.n_tiles = (size_t)(N / SPL_TILE) + 1;
-    z.off_chunk = 256;
+    // duplicate table: one slot per 64 bytes of text, 4 Ki .. 256 Ki slots (at most 2 MiB to clear per pass); when it
+    // fills up, further pieces simply go through the merge loop
+    z.dd_slots = 0;
+    if (dedup) { z.dd_slots = 4096; while (z.dd_slots < ((size_t)1 << 18) && z.dd_slots < N / 64) z.dd_slots <<= 1; }
+    z.off_dd = 256;
+    z.off_chunk = z.off_dd + z.dd_slots * 8;
     z.off_extra = align_up(z.off_chunk + (z.n_tiles / SPL_CHUNK_TILES + 2) * 4, 256);
     z.off_hard = align_up(z.off_extra + (z.n_tiles + 2) * sizeof(SplTileInfo), 256);
     z.off_pstart = align_up(z.off_hard + z.words * 4, 256);
@@ -208,7 +214,7 @@ int reserve_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
         tk->err = "one device pass is limited to 4 GiB of text";
         return SPL_ERR_UNSUPPORTED;
     }
-    const ZeroLayout z = zero_layout(N, with_special);
+    const ZeroLayout z = zero_layout(N, with_special, tk->dedup);
     const MissLayout m = miss_layout(N);
     int rc;
     if ((rc = dc.zero.ensure(z.total, tk->err))) return rc;
@@ -216,6 +222,7 @@ int reserve_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
     if ((rc = dc.pv.ensure(z.n_tiles * SPL_TILE * 4, tk->err))) return rc;
     if ((rc = dc.pool.ensure((size_t)(N + 64) * 4, tk->err))) return rc;
     if ((rc = dc.mlist.ensure((size_t)m.base[SPL_NCLS] * 8, tk->err))) return rc;
+    if (tk->dedup && (rc = dc.dupof.ensure((size_t)(m.base[SPL_NCLS] - m.base[2] + 16) * 4, tk->err))) return rc;
     uint32_t n_fast_tiles = (uint32_t)((N + SPL_FAST_PAYLOAD * 32u - 1) / (SPL_FAST_PAYLOAD * 32u));
     if ((rc = dc.fbl.ensure((size_t)(n_fast_tiles + 1) * 4, tk->err))) return rc;
     if (dc.huge_words == 0) dc.huge_words = (size_t)16 << 20;             // 64 MiB of scratch
@@ -229,7 +236,7 @@ int prepare_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
                  cudaStream_t st, SplWork& w) {
     int rc = reserve_work(tk, dc, N, n_docs, with_special);
     if (rc) return rc;
-    const ZeroLayout z = zero_layout(N, with_special);
+    const ZeroLayout z = zero_layout(N, with_special, tk->dedup);
     const MissLayout m = miss_layout(N);
     uint32_t n_fast_tiles = (uint32_t)((N + SPL_FAST_PAYLOAD * 32u - 1) / (SPL_FAST_PAYLOAD * 32u));
     CUDA_TRY(cudaMemsetAsync(dc.zero.p, 0, z.total, st), tk->err);
@@ -251,8 +258,11 @@ int prepare_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
     for (uint32_t c = 0; c <= SPL_NCLS; ++c) w.ml_base[c] = m.base[c];
     w.fb_list = (uint32_t*)dc.fbl.p;
     w.n_fast_tiles = n_fast_tiles;
+    w.dd_tab = tk->dedup ? (unsigned long long*)(zb + z.off_dd) : nullptr;
+    w.dd_mask = tk->dedup ? (uint32_t)z.dd_slots - 1u : 0u;
+    w.dup_of = (uint32_t*)dc.dupof.p;
     w.huge_pool = (uint32_t*)dc.huge.p;
-    w.huge_pool_words = (uint32_t)std::min<size_t>(dc.huge_words, 0xFFFFFFFFu);
+    w.huge_pool_words = dc.huge_words;
     w.T = dc.d_tables;
     w.pattern = tk->host.pattern;
     w.with_special = with_special;
@@ -460,6 +470,7 @@ int spl_create(const uint8_t* vocab, size_t vocab_len, int pattern_id, uint32_t 
     if (!tk) return SPL_ERR_OOM;
     if (const char* tr = getenv("SPL_TRACE")) tk->trace = tr[0] == '1';
     if (const char* tc = getenv("SPL_TRACE_CHUNK")) tk->trace_chunk = atoi(tc);
+    if (const char* nd = getenv("SPL_NO_DEDUP")) tk->dedup = nd[0] == '0';
     if (const char* cb = getenv("SPL_CHUNK_BYTES")) tk->chunk_bytes = strtoull(cb, nullptr, 10);
     uint32_t hflags = ((flags & SPL_CREATE_BYTE_LEVEL) ? SPL_FLAG_BYTE_LEVEL : 0) |
                       ((flags & SPL_CREATE_SENTENCEPIECE) ? SPL_FLAG_SENTENCEPIECE : 0);
@@ -515,9 +526,9 @@ const char* spl_last_error(const spl_tokenizer* tk) { return tk ? tk->err.c_str(
 int spl_launches_per_call(const spl_tokenizer* tk, uint32_t flags) {
     if (!tk) return 0;
     bool ws = (flags & SPL_ENCODE_WITH_SPECIAL) && !tk->host.sp_id.empty();
-    if (is_sentencepiece(tk)) return 11 + (ws ? 1 : 0);                // mark (T), 4 x scan, sp_emit, mark (T'), probe, bpe, bpe_long (+ chunk scan), emit
+    if (is_sentencepiece(tk)) return 12 + (ws ? 1 : 0);                // mark (T), 4 x scan, sp_emit, mark (T'), probe, bpe, bpe_long, bpe_fin (+ chunk scan), emit
     int pre = tk->host.pattern == SPL_PAT_MISTRAL_V3 ? 1 : 2;          // sequential rules | bit-parallel + fallback
-    return 5 + pre + (ws ? 1 : 0);                                     // mark_docs, probe, bpe, bpe_long (+ chunk scan), emit
+    return 6 + pre + (ws ? 1 : 0);                                     // mark_docs, probe, bpe, bpe_long, bpe_fin (+ chunk scan), emit
 }
 
 int spl_set_profiling(spl_tokenizer* tk, int enable) {
@@ -587,13 +598,41 @@ int spl_encode_batch_device(spl_tokenizer* tk, int dev_index, const uint8_t* d_b
         CUDA_TRY(cudaStreamSynchronize(st), tk->err);
         if (h_counters[1] & SPL_DEVERR_OFFSETS) { tk->err = "document offsets are not a non-decreasing sequence from 0 to n_bytes"; return SPL_ERR_INVALID_ARG; }
         if (h_counters[1] & SPL_DEVERR_HUGE_POOL) {
-            if (attempt >= 6) { tk->err = "scratch pool for very long pieces exhausted"; return SPL_ERR_OOM; }
-            dc.huge_words = std::max<size_t>(dc.huge_words * 4, (size_t)h_counters[2] + 1024);
+            if (attempt >= 3) { tk->err = "scratch pool for very long pieces exhausted"; return SPL_ERR_OOM; }
+            const uint64_t need = (uint64_t)h_counters[2] | ((uint64_t)h_counters[3] << 32);      // what this pass asked for in all
+            dc.huge_words = std::max<size_t>(dc.huge_words * 2, (size_t)need + 1024);
             continue;
         }
         *n_tokens_out = total;
         return SPL_OK;
     }
+}
+
+int spl_device_status(spl_tokenizer* tk, int dev_index, void* cuda_stream, uint32_t* flags_out) {
+    if (!tk || !flags_out || dev_index < 0 || (size_t)dev_index >= tk->devs.size()) return SPL_ERR_INVALID_ARG;
+    DeviceGuard guard;
+    DevCtx& dc = tk->devs[dev_index];
+    CUDA_TRY(cudaSetDevice(dc.device), tk->err);
+    *flags_out = 0;
+    if (!dc.zero.p) return SPL_OK;                                // no pass yet
+    uint32_t h = 0;
+    static_assert(SPL_DEVERR_OFFSETS == SPL_STATUS_BAD_OFFSETS && SPL_DEVERR_HUGE_POOL == SPL_STATUS_SCRATCH_EXHAUSTED, "flag values");
+    CUDA_TRY(cudaMemcpyAsync(&h, (const uint32_t*)dc.zero.p + SPL_CTR_ERR, 4, cudaMemcpyDeviceToHost, (cudaStream_t)cuda_stream), tk->err);
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)cuda_stream), tk->err);
+    *flags_out = h;
+    return SPL_OK;
+}
+
+int spl_debug_counters(spl_tokenizer* tk, int dev_index, void* cuda_stream, uint32_t* out32) {
+    if (!tk || !out32 || dev_index < 0 || (size_t)dev_index >= tk->devs.size()) return SPL_ERR_INVALID_ARG;
+    DeviceGuard guard;
+    DevCtx& dc = tk->devs[dev_index];
+    CUDA_TRY(cudaSetDevice(dc.device), tk->err);
+    memset(out32, 0, SPL_CTR_WORDS * 4);
+    if (!dc.zero.p) return SPL_OK;
+    CUDA_TRY(cudaMemcpyAsync(out32, dc.zero.p, SPL_CTR_WORDS * 4, cudaMemcpyDeviceToHost, (cudaStream_t)cuda_stream), tk->err);
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)cuda_stream), tk->err);
+    return SPL_OK;
 }
 
 // One pipeline stage of spl_encode_batch: a contiguous range of documents of one device.
@@ -741,6 +780,7 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
         memset(&r->stats, 0, sizeof(r->stats));
         bool retry = false;
         int err_code = SPL_OK;
+        std::vector<uint64_t> huge_need(G, 0);   // words of huge-piece scratch the chunks of each device asked for (max)
         uint64_t total = 0;                 // ids of the chunks drained so far
         size_t next_out = 0;                // chunks are drained in document order
 
@@ -751,7 +791,8 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
             const uint32_t errbits = (uint32_t)c.meta[1];
             if (errbits & SPL_DEVERR_OFFSETS) { tk->err = "invalid document offsets"; return SPL_ERR_INVALID_ARG; }
             if (errbits & SPL_DEVERR_HUGE_POOL) {
-                dc.huge_words = std::max<size_t>(dc.huge_words * 4, (size_t)(c.meta[1] >> 32) + 1024);
+                // remember the largest request of any chunk of this device; the pool is resized ONCE before the retry
+                huge_need[c.g] = std::max<uint64_t>(huge_need[c.g], (uint64_t)c.meta[2]);
                 retry = true;
                 return SPL_OK;
             }
@@ -841,7 +882,7 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
                 // the chunk's id count and error flags arrive in mapped host memory (written by k_emit): no copy on the
                 // kernel stream, which would queue behind the previous chunk's ids on the device-to-host engine
                 CUDA_TRY(cudaEventRecord(ev_done, dc.stream), tk->err);
-                r->stats.d2h_bytes += 16;
+                r->stats.d2h_bytes += 24;
                 return SPL_OK;
             };
             err_code = enqueue();
@@ -903,9 +944,10 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
         }
         h_synced = h_ms();
         if (retry) {
-            if (attempt >= 6) { tk->err = "scratch pool for very long pieces exhausted"; return fail(SPL_ERR_OOM); }
+            if (attempt >= 3) { tk->err = "scratch pool for very long pieces exhausted"; return fail(SPL_ERR_OOM); }
             for (size_t g = 0; g < G; ++g) {
                 cudaSetDevice(tk->devs[g].device);
+                if (huge_need[g]) tk->devs[g].huge_words = std::max<size_t>(tk->devs[g].huge_words * 2, (size_t)huge_need[g] + 1024);
                 if ((rc = reserve_work(tk, tk->devs[g], ids_bound(tk, max_nb[g]), max_nd[g], with_special))) return fail(rc);
             }
             continue;
@@ -1110,11 +1152,19 @@ int spl_encode_jsonl(spl_tokenizer* tk, const uint8_t* bytes, size_t n_bytes, co
     PinnedBuf meta_buf = take_pinned(tk, (C + 1) * 32);
     spl_ingest_stats tot;
     memset(&tot, 0, sizeof(tot));
+    static thread_local int jsonl_depth = 0;
     auto fail = [&](int code) {
         cudaStreamSynchronize(dc.s_in); cudaStreamSynchronize(dc.stream); cudaStreamSynchronize(dc.s_out);
         cudaGetLastError();
         give_pinned(tk, r->off_buf); give_pinned(tk, r->ids_buf); give_pinned(tk, meta_buf);
         delete r;
+        if (code == SPL_ERR_OOM + 1000) {                      // huge-piece scratch was too small and has been enlarged
+            if (jsonl_depth >= 3) return (int)SPL_ERR_OOM;
+            ++jsonl_depth;
+            const int rc2 = spl_encode_jsonl(tk, bytes, n_bytes, field, flags, out, ingest_stats);
+            --jsonl_depth;
+            return rc2;
+        }
         return code;
     };
     if (!r->off_buf.p || !meta_buf.p) { tk->err = "pinned host allocation failed"; return fail(SPL_ERR_OOM); }
@@ -1163,7 +1213,11 @@ int spl_encode_jsonl(spl_tokenizer* tk, const uint8_t* bytes, size_t n_bytes, co
     auto drain = [&](size_t k) -> int {
         JChunk& c = chunks[k];
         const uint32_t errbits = (uint32_t)c.meta[1];
-        if (errbits & SPL_DEVERR_HUGE_POOL) { tk->err = "scratch pool for very long pieces exhausted (spl_encode_jsonl does not retry)"; return SPL_ERR_OOM; }
+        if (errbits & SPL_DEVERR_HUGE_POOL) {              // grow the pool and run the whole call again (see the end of the function)
+            dc.huge_words = std::max<size_t>(dc.huge_words * 2, (size_t)c.meta[2] + 1024);
+            tk->err = "scratch pool for very long pieces exhausted";
+            return SPL_ERR_OOM + 1000;
+        }
         if (errbits) { tk->err = "device error flags set by the encode kernels"; return SPL_ERR_CUDA; }
         c.n_tokens = c.meta[0];
         c.tok_base = total;

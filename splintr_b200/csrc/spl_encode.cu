@@ -95,21 +95,15 @@ __device__ __forceinline__ uint64_t ml_entry(uint32_t gpos, uint32_t len) {
 #define PB_BITS  (PB_WORDS * 32u)
 #define PROBE_WARPS (SPL_THREADS / 32)
 
-__device__ __forceinline__ void probe_tile(const SplWork& w, SplProbeScratch& sm, const uint32_t* text, const uint32_t* pb,
-                                           const uint32_t tile) {
-    const SplTables* T = w.T;
+// Piece list of a tile: sm.plist[0 .. P) = window positions of the piece starts in pb (bits below SPL_TILE), in order,
+// sm.plist[P] = end of the last piece (0xFFFF: beyond the staged bits, see sm.last_end).  All threads of the block call
+// this (two barriers inside).  publish: record P for k_emit and add it to the chunk total.
+__device__ __forceinline__ uint32_t build_piece_list(const SplWork& w, SplProbeScratch& sm, const uint32_t* pb, const uint32_t tile,
+                                                     const bool publish) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const bool worker = tid < SPL_THREADS;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t N = w.N;
-    const uint32_t tile0 = tile * SPL_TILE;
-    const SplKey8* __restrict__ t8 = T->t8;
-    const uint32_t t8_log2 = T->t8_log2;
-
-    // (sm.spw, the special-span bits of the tile, is filled by the caller together with text and pb)
-    // ---- piece list: positions of the piece starts of this tile, in order ------------------
+    const uint32_t N = w.N, tile0 = tile * SPL_TILE;
     const uint32_t avail = N - tile0;                          // text bytes from tile0 on
-    uint32_t my = worker ? (pb[tid >> 1] >> ((tid & 1u) * 16u)) & 0xFFFFu : 0u;
+    uint32_t my = (pb[tid >> 1] >> ((tid & 1u) * 16u)) & 0xFFFFu;
     if (tid * 16u + 16u > avail) my &= (tid * 16u >= avail) ? 0u : ((1u << (avail - tid * 16u)) - 1u);   // sentinel bit at N
     uint32_t cnt = __popc(my), incl = cnt;
 #pragma unroll
@@ -117,7 +111,7 @@ __device__ __forceinline__ void probe_tile(const SplWork& w, SplProbeScratch& sm
         uint32_t t = __shfl_up_sync(FULL, incl, o);
         if (lane >= (uint32_t)o) incl += t;
     }
-    if (lane == 31 && worker) sm.wtot[warp] = incl;
+    if (lane == 31) sm.wtot[warp] = incl;
     __syncthreads();
     uint32_t base = incl - cnt, P = 0;
 #pragma unroll
@@ -138,10 +132,27 @@ __device__ __forceinline__ void probe_tile(const SplWork& w, SplProbeScratch& sm
         }
         sm.last_end = e;
         sm.plist[P] = (uint16_t)(e >= PB_BITS ? 0xFFFFu : e);      // 0xFFFF: see last_end
-        w.tinfo[tile].np = P;
-        if (P) atomicAdd(&w.chunk_cnt[tile / SPL_CHUNK_TILES], (int32_t)P);
+        if (publish) {
+            w.tinfo[tile].np = P;
+            if (P) atomicAdd(&w.chunk_cnt[tile / SPL_CHUNK_TILES], (int32_t)P);
+        }
     }
     __syncthreads();
+    return P;
+}
+
+__device__ __forceinline__ void probe_tile(const SplWork& w, SplProbeScratch& sm, const uint32_t* text, const uint32_t* pb,
+                                           const uint32_t tile) {
+    const SplTables* T = w.T;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t N = w.N;
+    const uint32_t tile0 = tile * SPL_TILE;
+    const SplKey8* __restrict__ t8 = T->t8;
+    const uint32_t t8_log2 = T->t8_log2;
+
+    // (sm.spw, the special-span bits of the tile, is filled by the caller together with text and pb)
+    const uint32_t P = build_piece_list(w, sm, pb, tile, true);
 
     // From here on every warp works alone on its own range of pieces [jlo, jhi): no block barrier, a warp with
     // slow pieces does not hold the others back.
@@ -268,30 +279,218 @@ __device__ __forceinline__ void probe_tile(const SplWork& w, SplProbeScratch& sm
     }
 }
 
-struct ProbeSmem {
-    uint32_t text[SPL_PROBE_WIN / 4 + 4];     // staged bytes (+ slack for the unaligned 8-byte key loads)
-    uint32_t pb[PB_WORDS];                    // piece-start bits
-    SplProbeScratch ps;
+// ------------------------------------------------------------------------------------------
+// probe_tile_refine: the probe of a tile with many multi-byte characters (CJK text).  On such text most pieces miss the
+// whole-piece probe and would go through the merge loop as they are -- 24 bytes on average, 20 merges each.  Instead
+// every missed piece is cut at its safe boundaries (spl_segment.h: no vocabulary key can lie across one, so the merge
+// loop runs per segment and the id lists concatenate); the segments become pieces of their own:
+//   pass 1   whole-piece probe of every piece (results by start position in val_at, misses marked in mstw)
+//   pass R   one thread per missed piece walks its characters and marks the safe boundaries inside the tile in segw
+//   pass 2   piece list over the old and the new starts; a segment that is one 2- or 3-byte character is ONE table
+//            load (char_tok: what the merge loop makes of that character), any other segment is filed in the miss
+//            list of its length class with SPL_ML_SEG; the piece-start bitmap in global memory gets the new bits
+//            (k_emit counts pieces with it)
+// Only boundaries inside the tile are looked for (the tile that owns a piece owns its segments; what lies beyond
+// stays one segment), and a piece that is a candidate for the long-key probe of the merge kernels (longer than the
+// probe halo, not longer than the longest key) is left whole.
+// ------------------------------------------------------------------------------------------
+#define PV_MISSMARK 0xFFFFFFFEu
+
+struct SmemPieceReader {
+    const uint32_t* text; uint32_t s;
+    __device__ __forceinline__ uint32_t load4(uint32_t i) const {
+        const uint32_t q = s + i, wi = q >> 2;
+        return __funnelshift_r(text[wi], text[wi + 1], (q & 3u) * 8u);
+    }
 };
 
-// stage one tile (text window + piece-start bits) from global memory
+// whole-piece probe of the piece [s, s + len) of the staged window; returns its pv value or PV_MISSMARK
+__device__ __forceinline__ uint32_t probe_whole(const SplWork& w, const SplTables* T, const SplProbeScratch& sm,
+                                                const uint32_t* text, uint32_t s, uint32_t len, uint32_t gpos) {
+    if (w.with_special && ((sm.spw[s >> 5] >> (s & 31)) & 1u)) return special_id_g(T, w.text + gpos, len);
+    if (len == 1) {
+        const uint32_t sy = T->byte_sym[sm_byte(text, s)];
+        return sy < SPL_UNK_BASE ? sy : SPL_PV_NONE;                // unknown byte: no id (bpe.rs:73-75)
+    }
+    uint32_t id = SPL_RANK_NONE;
+    if (len <= 8) {
+        uint64_t k0 = sm_load8(text, s);
+        if (len < 8) k0 &= (1ull << (8 * len)) - 1;
+        id = lookup8(T->t8, T->t8_log2, k0, len);
+    } else if (len <= 16) {
+        uint64_t k0 = sm_load8(text, s), k1 = sm_load8(text, s + 8);
+        if (len < 16) k1 &= (1ull << (8 * (len - 8))) - 1;
+        id = lookup16(T->t16, T->t16_log2, k0, k1, len);
+    } else if (len <= SPL_PROBE_HALO && len <= T->max_key_len) {
+        id = lookupL_thread(T, text, s, len);
+    }
+    return id != SPL_RANK_NONE ? id : PV_MISSMARK;
+}
+
+__device__ __forceinline__ void probe_tile_refine(const SplWork& w, SplProbeScratch& sm, const uint32_t* text, uint32_t* pb,
+                                                  const uint32_t tile) {
+    const SplTables* T = w.T;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t tile0 = tile * SPL_TILE, pvbase = tile * SPL_TILE;
+    uint32_t* val_at = reinterpret_cast<uint32_t*>(sm.slow);           // [SPL_TILE] (slow + mloc: unused on this path)
+    static_assert(sizeof(sm.slow) + sizeof(sm.mloc) >= SPL_TILE * 4u && offsetof(SplProbeScratch, mloc) == offsetof(SplProbeScratch, slow) + sizeof(sm.slow), "val_at");
+    if (tid < SPL_TILE / 32) { sm.segw[tid] = 0u; sm.mstw[tid] = 0u; }
+    if (tid == 0) atomicAdd(&w.counters[SPL_CTR_REFINED], 1u);
+    const uint32_t P1 = build_piece_list(w, sm, pb, tile, false);
+
+    // ---- pass 1 + pass R: one thread per piece ------------------------------------------------------------
+    for (uint32_t j = tid; j < P1; j += SPL_THREADS) {
+        const uint32_t s = sm.plist[j];
+        uint32_t e = sm.plist[j + 1];
+        if (e == 0xFFFFu) e = sm.last_end;
+        const uint32_t len = e - s;
+        const uint32_t v = probe_whole(w, T, sm, text, s, len, tile0 + s);
+        val_at[s] = v;
+        if (v != PV_MISSMARK) continue;
+        if (len > SPL_PROBE_HALO && len <= T->max_key_len) continue;      // the merge kernels still owe it the long-key probe: stays whole
+        atomicOr(&sm.mstw[s >> 5], 1u << (s & 31u));
+        const SmemPieceReader rd{text, s};
+        // characters are read from the staged window: only boundaries below the tile end are looked for, and the
+        // character that starts there lies inside the halo
+        spl_safe_boundaries(rd, len, SPL_TILE - s, T->seg_irr, T->seg_h2, T->seg_h2_log2,
+                            [&](uint32_t pos) { const uint32_t q = s + pos; atomicOr(&sm.segw[q >> 5], 1u << (q & 31u)); });
+    }
+    __syncthreads();
+
+    // ---- pass 2: the new piece list ----------------------------------------------------------------------------
+    if (tid < SPL_TILE / 32) {
+        const uint32_t nw = sm.segw[tid];
+        if (nw) { pb[tid] |= nw; w.pstart[(tile0 >> 5) + tid] = pb[tid]; }     // only this block writes the words of its tile
+    }
+    __syncthreads();
+    const uint32_t P = build_piece_list(w, sm, pb, tile, true);
+    int32_t dropped = 0;
+    for (uint32_t j0 = 0; j0 < P; j0 += SPL_THREADS) {
+        const uint32_t j = j0 + tid;
+        uint32_t cls = 0, gpos = 0, len = 0;                     // cls: 0 settled, else 1 + length class of the miss
+        bool seg = false;
+        if (j < P) {
+            const uint32_t s = sm.plist[j];
+            uint32_t e = sm.plist[j + 1];
+            if (e == 0xFFFFu) e = sm.last_end;
+            len = e - s; gpos = tile0 + s;
+            seg = ((sm.segw[s >> 5] | sm.mstw[s >> 5]) >> (s & 31u)) & 1u;
+            uint32_t val;
+            if (!seg) {
+                val = val_at[s];
+            } else if (len == 1) {
+                const uint32_t sy = T->byte_sym[sm_byte(text, s)];
+                val = sy < SPL_UNK_BASE ? sy : SPL_PV_NONE;
+            } else {
+                val = PV_MISSMARK;
+                if (len <= 3) {                                   // one 2- or 3-byte character?
+                    const SmemPieceReader rd{text, s};
+                    uint32_t packed = 0;
+                    if (spl_u8_char(rd.load4(0), len, packed) == len) {
+                        const uint32_t id = __ldg(T->char_tok + spl_u8_cp23(packed, len));
+                        if (id != SPL_RANK_NONE) val = id;
+                    }
+                }
+            }
+            if (val == PV_MISSMARK) cls = 1u + spl_len_class(len);
+            else {
+                w.pv[pvbase + j] = val;
+                if (val == SPL_PV_NONE) ++dropped;
+            }
+        }
+        // misses: one atomic per warp and class
+        if (__any_sync(FULL, cls != 0u)) {
+            for (uint32_t c = 0; c < SPL_NCLS; ++c) {
+                const uint32_t bal = __ballot_sync(FULL, cls == c + 1u);
+                if (!bal) continue;
+                const uint32_t leader = __ffs(bal) - 1;
+                uint32_t b0 = 0;
+                if (lane == leader) b0 = atomicAdd(&w.counters[SPL_CTR_CLS + c], (uint32_t)__popc(bal));
+                b0 = __shfl_sync(FULL, b0, leader);
+                if (cls == c + 1u) {
+                    const uint32_t midx = w.ml_base[c] + b0 + __popc(bal & lt_mask);
+                    w.mlist[midx] = ml_entry(gpos, len) | (seg ? SPL_ML_SEG : 0ull);
+                    w.pv[pvbase + j] = SPL_PV_MISS | midx;
+                }
+            }
+        }
+    }
+    dropped = __reduce_add_sync(FULL, dropped);
+    if (lane == 0 && dropped) { atomicAdd(&w.tinfo[tile].extra, -dropped); atomicAdd(&w.chunk_cnt[tile / SPL_CHUNK_TILES], -dropped); }
+}
+
+struct __align__(16) ProbeSmem {
+    uint32_t text[SPL_PROBE_WIN / 4 + 4];     // staged bytes (+ slack for the unaligned 8-byte key loads)
+    uint32_t pb[PB_WORDS + 3];                // piece-start bits (a multiple of 16 bytes: bulk copies move 16-byte units)
+    SplProbeScratch ps;
+    unsigned long long mbar;                  // arrival barrier of the bulk copies
+};
+#define PROBE_TEXT_BYTES (SPL_PROBE_WIN + 16u)
+#define PROBE_PB_BYTES   ((PB_WORDS + 3u) / 4u * 16u)
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Stage one tile (text window + piece-start bits) from global memory.
+// BULK: two 1-D bulk copies (cp.async.bulk -> SASS UBLKCP, the TMA engine of sm_90+/sm_100) issued by one thread and
+// awaited on an mbarrier -- no registers, no LDG/STS pairs in the 256 threads; else 16-byte loads through registers.
+// Counts the bytes >= 0x80 of the tile into sm.ps.n_hi.
+template <bool BULK>
 __device__ __forceinline__ void probe_stage(const SplWork& w, ProbeSmem& sm, const uint32_t tile) {
     const uint32_t tid = threadIdx.x, tile0 = tile * SPL_TILE, Nup = (w.N + 15u) & ~15u;
-    for (uint32_t v = tid; v < SPL_PROBE_WIN / 16 + 1; v += SPL_THREADS) {
-        uint32_t g = tile0 + v * 16;
-        uint4 x = make_uint4(0, 0, 0, 0);
-        if (g < Nup) x = __ldg(reinterpret_cast<const uint4*>(w.text + g));
-        reinterpret_cast<uint4*>(sm.text)[v] = x;
+    if (tid == 0) sm.ps.n_hi = 0u;
+    if (BULK) {
+        const uint32_t tb = min(PROBE_TEXT_BYTES, Nup - tile0);                  // bytes of the window that exist (16-byte units)
+        const uint32_t bar = smem_addr(&sm.mbar);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(tb + PROBE_PB_BYTES) : "memory");
+            if (tb) asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 :: "r"(smem_addr(sm.text)), "l"(w.text + tile0), "r"(tb), "r"(bar) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_addr(sm.pb)), "l"(w.pstart + (tile0 >> 5)), "r"(PROBE_PB_BYTES), "r"(bar) : "memory");
+        }
+        for (uint32_t v = tb / 16u + tid; v < PROBE_TEXT_BYTES / 16u; v += SPL_THREADS)       // beyond the end of the text: zeros
+            reinterpret_cast<uint4*>(sm.text)[v] = make_uint4(0, 0, 0, 0);
+        if (w.with_special && tid < SPL_TILE / 32) sm.ps.spw[tid] = __ldg(w.spec + (tile0 >> 5) + tid);
+        __syncthreads();                                                          // the barrier is initialised for everybody
+        uint32_t ok, spins = 0;
+        do {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok) : "r"(bar) : "memory");
+            if (!ok && ++spins > (1u << 24)) __trap();                            // a copy that never lands must not hang the device
+        } while (!ok);
+        const uint4 x = reinterpret_cast<const uint4*>(sm.text)[tid];            // the tile proper: 256 x 16 bytes
+        const uint32_t hi = __popc(x.x & 0x80808080u) + __popc(x.y & 0x80808080u) + __popc(x.z & 0x80808080u) + __popc(x.w & 0x80808080u);
+        const uint32_t tot = __reduce_add_sync(FULL, hi);
+        if ((tid & 31u) == 0 && tot) atomicAdd(&sm.ps.n_hi, tot);
+    } else {
+        uint32_t hi = 0;
+        for (uint32_t v = tid; v < PROBE_TEXT_BYTES / 16u; v += SPL_THREADS) {
+            uint32_t g = tile0 + v * 16;
+            uint4 x = make_uint4(0, 0, 0, 0);
+            if (g < Nup) x = __ldg(reinterpret_cast<const uint4*>(w.text + g));
+            reinterpret_cast<uint4*>(sm.text)[v] = x;
+            if (v < SPL_TILE / 16u) hi += __popc(x.x & 0x80808080u) + __popc(x.y & 0x80808080u) + __popc(x.z & 0x80808080u) + __popc(x.w & 0x80808080u);
+        }
+        for (uint32_t v = tid; v < PB_WORDS; v += SPL_THREADS) sm.pb[v] = __ldg(w.pstart + (tile0 >> 5) + v);
+        if (w.with_special && tid < SPL_TILE / 32) sm.ps.spw[tid] = __ldg(w.spec + (tile0 >> 5) + tid);
+        const uint32_t tot = __reduce_add_sync(FULL, hi);
+        __syncthreads();                                                          // n_hi is zero for everybody
+        if ((tid & 31u) == 0 && tot) atomicAdd(&sm.ps.n_hi, tot);
     }
-    for (uint32_t v = tid; v < PB_WORDS; v += SPL_THREADS) sm.pb[v] = __ldg(w.pstart + (tile0 >> 5) + v);
-    if (w.with_special && tid < SPL_TILE / 32) sm.ps.spw[tid] = __ldg(w.spec + (tile0 >> 5) + tid);
     __syncthreads();
 }
 
+// a tile goes through the refining pass when more than 1/16 of its bytes belong to multi-byte characters
+template <bool BULK>
 __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
     __shared__ ProbeSmem sm;
-    probe_stage(w, sm, blockIdx.x);
-    probe_tile(w, sm.ps, sm.text, sm.pb, blockIdx.x);
+    SPL_RETURN_IF_BAD_OFFSETS(w);
+    probe_stage<BULK>(w, sm, blockIdx.x);
+    if (sm.ps.n_hi * 16u > SPL_TILE) probe_tile_refine(w, sm.ps, sm.text, sm.pb, blockIdx.x);
+    else probe_tile(w, sm.ps, sm.text, sm.pb, blockIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -367,7 +566,7 @@ __device__ __forceinline__ void bpe_finish(const SplWork& w, uint64_t* slot, uin
 // All 32 lanes call this (valid: the group has a piece).  Returns the id count in lane g == 0; ids go to out[0 ..] in order.
 #define BG_LINK_NONE 0x7FFu
 template <uint32_t LG>
-__device__ uint32_t bpe_seq(uint32_t* reg, const bool valid, const SplTables* T,
+__device__ uint32_t bpe_seq(uint32_t* reg, const bool valid, const bool allow_whole, const SplTables* T,
                             const uint8_t* __restrict__ tx, const uint32_t n, uint32_t* __restrict__ out) {
     constexpr uint32_t G = 1u << LG;
     const uint32_t lane = threadIdx.x & 31u, p = lane >> LG, g = lane & (G - 1u);
@@ -381,7 +580,7 @@ __device__ uint32_t bpe_seq(uint32_t* reg, const bool valid, const SplTables* T,
     bool act = valid;
     {
         // whole-piece probe of pieces beyond the probe halo (k_probe has already tried the shorter ones)
-        const bool tryw = act && n > SPL_PROBE_HALO && n <= T->max_key_len;
+        const bool tryw = act && allow_whole && n > SPL_PROBE_HALO && n <= T->max_key_len;
         if (__any_sync(FULL, tryw)) {
             uint32_t id = SPL_RANK_NONE;
             if (tryw && g == 0) id = lookupL_serial_g(T, tx, n);
@@ -464,7 +663,7 @@ __device__ uint32_t bpe_seq(uint32_t* reg, const bool valid, const SplTables* T,
 // All 32 lanes call this; lane = p * G + g works on piece p of the warp's task (valid: the piece exists), G = 1 << LG.
 // Returns the id count in every lane of the group; ids go to out[0 ..] in order.
 template <uint32_t LG>
-__device__ uint32_t bpe_group(uint32_t* reg, const bool valid, const SplTables* T,
+__device__ uint32_t bpe_group(uint32_t* reg, const bool valid, const bool allow_whole, const SplTables* T,
                               const uint8_t* __restrict__ tx, const uint32_t n, uint32_t* __restrict__ out) {
     constexpr uint32_t G = 1u << LG;
     constexpr uint32_t NONE = BG_RANK_NONE;
@@ -486,7 +685,7 @@ __device__ uint32_t bpe_group(uint32_t* reg, const bool valid, const SplTables* 
     bool act = valid;
     {
         // whole-piece probe of pieces beyond the probe halo (k_probe has already tried the shorter ones)
-        const bool tryw = act && n > SPL_PROBE_HALO && n <= T->max_key_len;
+        const bool tryw = act && allow_whole && n > SPL_PROBE_HALO && n <= T->max_key_len;
         if (__any_sync(FULL, tryw)) {
             uint32_t id = SPL_RANK_NONE;
             if (tryw && g == 0) id = lookupL_serial_g(T, tx, n);
@@ -649,25 +848,17 @@ __device__ uint32_t bpe_group(uint32_t* reg, const bool valid, const SplTables* 
 }
 
 // ------------------------------------------------------------------------------------------
-// k_bpe: the segment walker.  ONE LANE PER PIECE, whatever its length.
+// k_bpe: the merge loop for pieces and segments of up to SPL_SEG_MAX (32) bytes.  ONE LANE PER PIECE.
 //
-// A lane walks its piece character by character and cuts it into independent segments (spl_segment.h: no vocabulary
-// key can lie across a safe boundary, so the merge loop of bpe.rs:83-194 runs per segment and the id lists
-// concatenate).  A segment that is one 2- or 3-byte character is ONE table load (char_tok: what the merge loop makes
-// of that character); any other segment of up to SPL_SEG_MAX bytes goes through the merge loop right here, in the
-// lane's own two rows of shared memory:
+// The whole state of a piece lives in the lane's own two rows of shared memory and one register:
 //     S[i] = symbol of the part that starts at byte i          K[i] = rank of (part at i, next part) << 5 | i
-// Which bytes still start a part is a 32-bit mask in a register, so the neighbours of a part are two bit scans and the
-// reference's linked list (bpe.rs:42-54) needs no memory.  The minimum over K is the lowest rank at the leftmost
-// position -- exactly the pair bpe.rs:121-138 selects; it is found with 16-byte loads (rows are 36 words apart: 16-byte
-// aligned, and the eight lanes of a quarter warp cover all 32 banks).  The first rank of every part comes from the
-// dense byte x byte table (one 4-byte load, no hashing); the two re-ranks after a merge (bpe.rs:146-166) are two
-// 256-bit bucket loads in flight together.
-// The lanes of a warp alternate between two phases in step: (A) walk until the lane holds a segment for the merge
-// loop or its piece is done; (B) all lanes that hold a segment run the merge loop side by side.
-// A piece with a segment beyond SPL_SEG_MAX bytes (long runs of ASCII letters or punctuation) is left to k_bpe_long.
-// CJK text: 97 % of the character boundaries of cfg5 are safe and 93 % of its segments are single characters; its longest
-// segment is 15 bytes (tools/seg_stats.py).
+//     live = bit i set while a part starts at byte i
+// so the neighbours of a part are two bit scans and the reference's linked list (bpe.rs:42-54) needs no memory.
+// The minimum over K is the lowest rank at the leftmost position -- exactly the pair bpe.rs:121-138 selects; it is
+// found with 16-byte loads (rows are 36 words apart: 16-byte aligned, and the eight lanes of a quarter warp cover all 32
+// banks).  The first rank of every part comes from the dense byte x byte table (one 4-byte load, no hashing); the two
+// re-ranks after a merge (bpe.rs:146-166) are two 256-bit bucket loads in flight together.
+// The whole-piece probe is k_probe's business; CJK text arrives here already cut into segments (probe_tile_refine).
 // ------------------------------------------------------------------------------------------
 #define WK_STRIDE 36u                                  // words between the rows of two lanes
 #define WK_WORDS  (2u * 32u * WK_STRIDE)               // per warp: 32 K rows, 32 S rows
@@ -682,125 +873,160 @@ __device__ __forceinline__ uint32_t text_load4(const uint8_t* __restrict__ text,
     return __funnelshift_r(a, b, (gi & 3u) * 8u);
 }
 
-struct WalkReader {
-    const uint8_t* __restrict__ p; uint32_t g0, n_up;                  // piece start, its global index, padded text end
-    __device__ __forceinline__ uint32_t load4(uint32_t i) const { return text_load4(p - g0, g0 + i, n_up); }
-};
-
-__device__ __forceinline__ void walker_task(const SplWork& w, const SplTables* __restrict__ T, uint32_t* __restrict__ Krow,
-                                            uint32_t* __restrict__ Srow, uint64_t* slot, const bool valid) {
-    const uint8_t* __restrict__ text = w.text;
-    const uint32_t n_up = (w.N + 15u) & ~15u;
+// merge loop over the n <= 32 bytes from text[gpos] on; ids to out[0 ..] in order; returns their number
+__device__ __forceinline__ uint32_t bpe_lane(const SplTables* __restrict__ T, const uint8_t* __restrict__ text, const uint32_t n_up,
+                                             uint32_t* __restrict__ Krow, uint32_t* __restrict__ Srow,
+                                             const uint32_t gpos, const uint32_t n, uint32_t* __restrict__ out) {
     const uint32_t* __restrict__ ptab = T->pair;
     const uint32_t plog = T->pair_log2;
     const uint32_t* __restrict__ bpair = T->bpair;
-    const uint32_t* __restrict__ irr = T->seg_irr;
-    const uint32_t* __restrict__ h2 = T->seg_h2;
-    const uint32_t h2log = T->seg_h2_log2;
-    const uint32_t* __restrict__ ctok = T->char_tok;
-
-    uint64_t e = valid ? *slot : SPL_ML_DONE;
-    const bool todo = !(e & SPL_ML_DONE);
-    const uint32_t gpos = (uint32_t)e, len = todo ? (uint32_t)(e >> 32) & SPL_ML_LEN_MASK : 0u;
-    uint32_t* __restrict__ out = w.pool + gpos;
-    const WalkReader rd{text + gpos, gpos, n_up};
-    uint32_t pos = 0, cnt = 0;
-    bool bail = false, taint = false;
-
-    for (;;) {
-        // ---- phase A: walk to the next segment that needs the merge loop -------------------------------------
-        uint32_t seg0 = 0, n = 0;
-        while (pos < len && !bail) {
-            uint32_t a_first, la_first, w4;
-            const uint32_t end = spl_segment_end(rd, pos, len, taint, irr, h2, h2log, a_first, la_first, w4);
-            const uint32_t sl = end - pos;
-            if (sl > SPL_SEG_MAX) { bail = true; break; }
-            if (sl == 1u) {
-                const uint32_t sy = T->byte_sym[w4 & 0xFFu];
-                if (sy < SPL_UNK_BASE) out[cnt++] = sy;               // unknown byte: no id (bpe.rs:73-75, 187-191)
-                pos = end;
-                continue;
-            }
-            if (sl == la_first && sl <= 3u) {                         // one 2- or 3-byte character
-                const uint32_t id = __ldg(ctok + spl_u8_cp23(a_first, sl));
-                if (id != SPL_RANK_NONE) { out[cnt++] = id; pos = end; continue; }
-            }
-            seg0 = pos; n = sl; pos = end;
-            break;
-        }
-        if (!__any_sync(FULL, n != 0u)) break;
-        if (n == 0u) continue;
-
-        // ---- phase B: the merge loop over the segment [seg0, seg0 + n) ------------------------------------------
-        {
-            uint32_t prevb = 0;
-            for (uint32_t i = 0; i < n; i += 4u) {
-                uint32_t w4 = text_load4(text, gpos + seg0 + i, n_up);
+    {
+        uint32_t prevb = 0;
+        for (uint32_t i = 0; i < n; i += 4u) {
+            uint32_t w4 = text_load4(text, gpos + i, n_up);
 #pragma unroll
-                for (uint32_t q = 0; q < 4u; ++q) {
-                    const uint32_t b = w4 & 0xFFu;
-                    w4 >>= 8;
-                    if (i + q < n) {
-                        Srow[i + q] = T->byte_sym[b];
-                        if (i + q) Krow[i + q - 1u] = ((__ldg(bpair + ((prevb << 8) | b)) & BG_RANK_NONE) << 5) | (i + q - 1u);
-                        prevb = b;
-                    }
+            for (uint32_t q = 0; q < 4u; ++q) {
+                const uint32_t b = w4 & 0xFFu;
+                w4 >>= 8;
+                if (i + q < n) {
+                    Srow[i + q] = T->byte_sym[b];
+                    if (i + q) Krow[i + q - 1u] = ((__ldg(bpair + ((prevb << 8) | b)) & BG_RANK_NONE) << 5) | (i + q - 1u);
+                    prevb = b;
                 }
             }
-            Krow[n - 1u] = WK_NONE | (n - 1u);
-            for (uint32_t i = n; i < ((n + 3u) & ~3u); ++i) Krow[i] = 0xFFFFFFFFu;
         }
-        uint32_t live = n >= 32u ? 0xFFFFFFFFu : (1u << n) - 1u;
-        const uint32_t n4 = (n + 3u) >> 2;
-        for (;;) {
-            uint32_t key = 0xFFFFFFFFu;
-            const uint4* k4 = reinterpret_cast<const uint4*>(Krow);
-            for (uint32_t it = 0; it < n4; ++it) {
-                const uint4 v = k4[it];
-                key = min(min(key, v.x), min(v.y, min(v.z, v.w)));
-            }
-            const uint32_t r = key >> 5;
-            if (r == BG_RANK_NONE) break;
-            const uint32_t p = key & 31u;                                   // the pair (part at p, next part): p <= 30
-            const uint32_t upper = live & ~((2u << p) - 1u);
-            const uint32_t j = (uint32_t)__ffs(upper) - 1u;                 // the part being absorbed
-            const uint32_t upper2 = upper & (upper - 1u);
-            const uint32_t lower = live & ((1u << p) - 1u);
-            const bool has_k = upper2 != 0u, has_h = lower != 0u;
-            const uint32_t k = has_k ? (uint32_t)__ffs(upper2) - 1u : 0u, h = has_h ? 31u - (uint32_t)__clz(lower) : 0u;
-            const uint32_t symk = Srow[k], symh = Srow[h];
-            live &= ~(1u << j);
-            Srow[p] = r;                                                    // merged id == its rank
-            Krow[j] = WK_NONE | j;
-            uint32_t ra, rb;
-            pair_lookup2(ptab, plog, has_k, r, symk, has_h, symh, r, ra, rb);
-            Krow[p] = ((ra & BG_RANK_NONE) << 5) | p;
-            if (has_h) Krow[h] = ((rb & BG_RANK_NONE) << 5) | h;
-        }
-        for (uint32_t m = live; m; m &= m - 1u) {
-            const uint32_t sy = Srow[(uint32_t)__ffs(m) - 1u];
-            if (sy < SPL_UNK_BASE) out[cnt++] = sy;                         // unknown bytes produce no id (bpe.rs:187-191)
-        }
+        if (n) Krow[n - 1u] = WK_NONE | (n - 1u);
+        for (uint32_t i = n; i < ((n + 3u) & ~3u); ++i) Krow[i] = 0xFFFFFFFFu;
     }
-    if (todo && !bail) bpe_finish(w, slot, gpos, cnt);
+    uint32_t live = n >= 32u ? 0xFFFFFFFFu : (1u << n) - 1u;
+    const uint32_t n4 = (n + 3u) >> 2;
+    for (;;) {
+        uint32_t key = 0xFFFFFFFFu;
+        const uint4* k4 = reinterpret_cast<const uint4*>(Krow);
+        for (uint32_t it = 0; it < n4; ++it) {
+            const uint4 v = k4[it];
+            key = min(min(key, v.x), min(v.y, min(v.z, v.w)));
+        }
+        const uint32_t r = key >> 5;
+        if (r >= BG_RANK_NONE) break;                                   // (also n == 0: key is all ones)
+        const uint32_t p = key & 31u;                                   // the pair (part at p, next part): p <= 30
+        const uint32_t upper = live & ~((2u << p) - 1u);
+        const uint32_t j = (uint32_t)__ffs(upper) - 1u;                 // the part being absorbed
+        const uint32_t upper2 = upper & (upper - 1u);
+        const uint32_t lower = live & ((1u << p) - 1u);
+        const bool has_k = upper2 != 0u, has_h = lower != 0u;
+        const uint32_t k = has_k ? (uint32_t)__ffs(upper2) - 1u : 0u, h = has_h ? 31u - (uint32_t)__clz(lower) : 0u;
+        const uint32_t symk = Srow[k], symh = Srow[h];
+        live &= ~(1u << j);
+        Srow[p] = r;                                                    // merged id == its rank
+        Krow[j] = WK_NONE | j;
+        uint32_t ra, rb;
+        pair_lookup2(ptab, plog, has_k, r, symk, has_h, symh, r, ra, rb);
+        Krow[p] = ((ra & BG_RANK_NONE) << 5) | p;
+        if (has_h) Krow[h] = ((rb & BG_RANK_NONE) << 5) | h;
+    }
+    uint32_t cnt = 0;
+    for (uint32_t m = live; m; m &= m - 1u) {
+        const uint32_t sy = Srow[(uint32_t)__ffs(m) - 1u];
+        if (sy < SPL_UNK_BASE) out[cnt++] = sy;                         // unknown bytes produce no id (bpe.rs:187-191)
+    }
+    return cnt;
 }
 
 __global__ void __launch_bounds__(SPL_BPE_THREADS, 6) k_bpe(SplWork w) {
     extern __shared__ __align__(16) uint32_t bpe_smem[];
+    SPL_RETURN_IF_BAD_OFFSETS(w);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t gwarp = blockIdx.x * (SPL_BPE_THREADS / 32) + warp, nwarps = gridDim.x * (SPL_BPE_THREADS / 32);
     uint32_t* Krow = bpe_smem + warp * WK_WORDS + lane * WK_STRIDE;
     uint32_t* Srow = Krow + 32u * WK_STRIDE;
     const SplTables* T = w.T;
-    // the longest pieces first, so that the tail of the kernel is short work
-    for (int c = SPL_NCLS - 1; c >= 0; --c) {
+    const uint32_t n_up = (w.N + 15u) & ~15u;
+    // the longer pieces first, so that the tail of the kernel is short work
+    for (int c = 1; c >= 0; --c) {
         const uint32_t n = w.counters[SPL_CTR_CLS + c];
-        const uint32_t tasks = (n + 31u) >> 5;
+        // few pieces: spread them over all warps of the grid (a warp's time is its slowest lane's)
+        uint32_t per = 32u;
+        while (per > 1u && (size_t)n * 2u <= (size_t)nwarps * per) per >>= 1;
+        const uint32_t tasks = (n + per - 1u) / per;
         for (uint32_t t = gwarp; t < tasks; t += nwarps) {
-            const uint32_t pi = t * 32u + lane;
-            walker_task(w, T, Krow, Srow, &w.mlist[w.ml_base[c] + (pi < n ? pi : 0u)], pi < n);
+            const uint32_t pi = t * per + lane;
+            if (lane < per && pi < n) {
+                uint64_t* slot = &w.mlist[w.ml_base[c] + pi];
+                const uint64_t e = *slot;
+                const uint32_t gpos = (uint32_t)e, len = (uint32_t)(e >> 32) & SPL_ML_LEN_MASK;
+                const uint32_t cnt = bpe_lane(T, w.text, n_up, Krow, Srow, gpos, len, w.pool + gpos);
+                bpe_finish(w, slot, gpos, cnt);
+            }
         }
     }
+}
+
+// 64-bit hash of the len bytes at text[gpos] by the G = 2^LG lanes of a group (every lane gets it)
+template <uint32_t LG>
+__device__ __forceinline__ uint64_t group_hash(const uint8_t* __restrict__ text, uint32_t n_up, uint32_t gpos, uint32_t len) {
+    constexpr uint32_t G = 1u << LG;
+    const uint32_t g = threadIdx.x & (G - 1u);
+    uint64_t sum = 0;
+    for (uint32_t i = g * 4u; i < len; i += G * 4u) {
+        uint32_t w4 = text_load4(text, gpos + i, n_up);
+        if (len - i < 4u) w4 &= (1u << (8u * (len - i))) - 1u;
+        sum += spl_mix64((uint64_t)w4 + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1u));
+    }
+#pragma unroll
+    for (uint32_t o = G >> 1; o; o >>= 1) {
+        const uint32_t lo = __shfl_xor_sync(FULL, (uint32_t)sum, o), hi = __shfl_xor_sync(FULL, (uint32_t)(sum >> 32), o);
+        sum += (uint64_t)lo | ((uint64_t)hi << 32);
+    }
+    return spl_hashL_final(sum, len);
+}
+
+// Duplicate detection for the pieces of a warp task (all 32 lanes call this; valid: the lane's group has a piece).
+// Returns true in every lane of a group whose piece has the same bytes as an EARLIER entry of the miss list: that
+// entry's ids will do (k_bpe_fin copies the result), the merge loop is skipped.  Exact: equal hash tags only nominate
+// a candidate, the bytes (and the piece length) are compared.
+template <uint32_t LG>
+__device__ __forceinline__ bool dedup_check(const SplWork& w, const bool valid, const uint32_t midx, uint64_t* slot,
+                                            const uint32_t gpos, const uint32_t len) {
+    constexpr uint32_t G = 1u << LG;
+    const uint32_t lane = threadIdx.x & 31u, g = lane & (G - 1u), gsh = lane & ~(G - 1u);
+    const uint32_t n_up = (w.N + 15u) & ~15u;
+    const uint64_t hv = group_hash<LG>(w.text, n_up, valid ? gpos : 0u, valid ? len : 0u);
+    uint32_t cand = SPL_RANK_NONE;                                    // miss-list index of the entry that may hold the same bytes
+    if (valid && g == 0) {
+        const uint32_t tag = (uint32_t)(hv >> 32) | 1u;
+        uint32_t idx = (uint32_t)hv & w.dd_mask;
+        for (uint32_t probe = 0; probe < 4u; ++probe, idx = (idx + 1u) & w.dd_mask) {
+            unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&w.dd_tab[idx]);
+            if (cur == 0ull) cur = atomicCAS(&w.dd_tab[idx], 0ull, ((unsigned long long)tag << 32) | (midx + 1u));
+            if (cur == 0ull) break;                                   // inserted: this entry stands for its bytes
+            if ((uint32_t)(cur >> 32) == tag) { cand = (uint32_t)cur - 1u; break; }
+        }
+    }
+    cand = __shfl_sync(FULL, cand, gsh);
+    const bool check = valid && cand != SPL_RANK_NONE && cand != midx;
+    if (!__any_sync(FULL, check)) return false;
+    bool same = check;
+    uint32_t rpos = 0;
+    if (check) {
+        rpos = (uint32_t)w.mlist[cand];                               // (the low word of an entry is its position, before and after)
+        for (uint32_t i = g * 4u; i < len && same; i += G * 4u) {
+            uint32_t a = text_load4(w.text, gpos + i, n_up), b = text_load4(w.text, rpos + i, n_up);
+            if (len - i < 4u) { const uint32_t m = (1u << (8u * (len - i))) - 1u; a &= m; b &= m; }
+            same = a == b;
+        }
+        if (g == 0 && same) same = g_next_bit(w.pstart, rpos + 1u, w.N + 1u) == rpos + len;     // the same length, too
+    }
+    // every lane of the group must agree
+    uint32_t bad = __ballot_sync(FULL, check && !same);
+    const uint32_t gmask = (G >= 32u ? FULL : ((1u << G) - 1u) << gsh);
+    const bool dup = check && !(bad & gmask);
+    if (dup && g == 0) {
+        w.dup_of[midx - w.ml_base[2]] = cand;
+        *slot = (uint64_t)gpos | ((uint64_t)len << 32) | SPL_ML_DUP;
+        atomicAdd(&w.counters[SPL_CTR_DUP], 1u);
+    }
+    return dup;
 }
 
 template <uint32_t LG, bool WINDOWED>
@@ -816,14 +1042,16 @@ __device__ void bpe_class(const SplWork& w, uint32_t c, uint32_t* reg, uint32_t 
     for (uint32_t t = gwarp; t < tasks; t += nwarps) {
         const uint32_t pi = t * ppw + (lane >> LG);
         bool valid = (lane >> LG) < ppw && pi < n;
-        uint64_t* slot = &w.mlist[w.ml_base[c] + (valid ? pi : 0u)];
+        const uint32_t midx = w.ml_base[c] + (valid ? pi : 0u);
+        uint64_t* slot = &w.mlist[midx];
         const uint64_t e = *slot;
-        valid = valid && !(e & SPL_ML_DONE);                          // the segment walker (k_bpe) has settled this piece
-        if (!__any_sync(FULL, valid)) continue;
         const uint32_t gpos = (uint32_t)e, len = (uint32_t)(e >> 32) & SPL_ML_LEN_MASK;
+        if (w.dd_tab) valid = valid && !dedup_check<LG>(w, valid, midx, slot, gpos, len);
+        if (!__any_sync(FULL, valid)) continue;
         uint32_t cnt;
-        if constexpr (WINDOWED) cnt = bpe_group<LG>(reg, valid, w.T, w.text + gpos, len, w.pool + gpos);
-        else cnt = bpe_seq<LG>(reg, valid, w.T, w.text + gpos, len, w.pool + gpos);
+        const bool allow_whole = !(e & SPL_ML_SEG);                   // a segment of a piece is not a piece: no whole-piece probe
+        if constexpr (WINDOWED) cnt = bpe_group<LG>(reg, valid, allow_whole, w.T, w.text + gpos, len, w.pool + gpos);
+        else cnt = bpe_seq<LG>(reg, valid, allow_whole, w.T, w.text + gpos, len, w.pool + gpos);
         if (valid && (lane & ((1u << LG) - 1u)) == 0) bpe_finish(w, slot, gpos, cnt);
         __syncwarp();
     }
@@ -832,15 +1060,15 @@ __device__ void bpe_class(const SplWork& w, uint32_t c, uint32_t* reg, uint32_t 
 // The whole block merges one piece that does not fit shared memory: text bytes tx[0, len) in global memory; the
 // sym / rnk / next / prev arrays live in the scratch pool.  Returns (to every thread) the number of ids, written in
 // order to out[0 ..].
-__device__ uint32_t bpe_piece_block(uint64_t* red, uint32_t* s_bcast, const SplTables* T, const uint8_t* __restrict__ tx, uint32_t len,
-                                    uint32_t* scratch, uint32_t* __restrict__ out) {
+__device__ uint32_t bpe_piece_block(uint64_t* red, uint32_t* s_bcast, const SplTables* T, const bool allow_whole,
+                                    const uint8_t* __restrict__ tx, uint32_t len, uint32_t* scratch, uint32_t* __restrict__ out) {
     const uint32_t tid = threadIdx.x;
     uint32_t* sym = scratch;
     uint32_t* rnk = scratch + len;
     uint32_t* nxt = scratch + 2 * (size_t)len;
     uint32_t* prv = scratch + 3 * (size_t)len;
 
-    if (len <= T->max_key_len) {                     // only for vocabularies with very long keys
+    if (allow_whole && len <= T->max_key_len) {      // only for vocabularies with very long keys
         if (tid < 32) {
             uint32_t id = lookupL_warp_g(T, tx, len);
             if (tid == 0) *s_bcast = id;
@@ -960,7 +1188,9 @@ __device__ void chunk_scan_block(const SplWork& w, uint32_t* smem) {
 #define BPE_SEQ_WORDS 2560u                            // A[1024] + R[1024] + P[1024 x u16]
 __global__ void __launch_bounds__(SPL_BPE_THREADS, 4) k_bpe_long(SplWork w, const uint32_t win_cls) {
     extern __shared__ __align__(16) uint32_t bpe_smem[];
-    __shared__ uint32_t s_bcast, s_off;
+    __shared__ uint32_t s_bcast;
+    __shared__ uint64_t s_off;
+    SPL_RETURN_IF_BAD_OFFSETS(w);
     const SplTables* T = w.T;
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     const uint32_t gwarp = blockIdx.x * (SPL_BPE_THREADS / 32) + warp, nwarps = gridDim.x * (SPL_BPE_THREADS / 32);
@@ -980,35 +1210,65 @@ __global__ void __launch_bounds__(SPL_BPE_THREADS, 4) k_bpe_long(SplWork w, cons
             for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
                 uint64_t* slot = &w.mlist[w.ml_base[SPL_NCLS - 1] + i];
                 uint64_t e = *slot;
-                if (e & SPL_ML_DONE) continue;                 // the segment walker has settled this piece (block-uniform)
                 uint32_t gpos = (uint32_t)e;
                 if (tid == 0) {
                     uint32_t ge = g_next_bit(w.pstart, gpos + 1, w.N + 1);
-                    uint32_t need = 4u * (ge - gpos);
-                    uint32_t off = atomicAdd(&w.counters[SPL_CTR_HUGE_POOL], need);
-                    if ((uint64_t)off + need > w.huge_pool_words) { atomicOr(&w.counters[SPL_CTR_ERR], SPL_DEVERR_HUGE_POOL); off = SPL_RANK_NONE; }
+                    const unsigned long long need = 4ull * (ge - gpos);
+                    unsigned long long off = atomicAdd(reinterpret_cast<unsigned long long*>(&w.counters[SPL_CTR_HUGE_POOL]), need);
+                    if (off + need > w.huge_pool_words) { atomicOr(&w.counters[SPL_CTR_ERR], SPL_DEVERR_HUGE_POOL); off = ~0ull; }
                     s_off = off; s_bcast = ge - gpos;
                 }
                 __syncthreads();
-                const uint32_t off = s_off, len = s_bcast;
+                const uint64_t off = s_off;
+                const uint32_t len = s_bcast;
                 __syncthreads();
                 uint32_t c = 0;
-                if (off != SPL_RANK_NONE) c = bpe_piece_block(red, &s_bcast, T, w.text + gpos, len, w.huge_pool + off, w.pool + gpos);
+                if (off != ~0ull) c = bpe_piece_block(red, &s_bcast, T, !(e & SPL_ML_SEG), w.text + gpos, len, w.huge_pool + off, w.pool + gpos);
                 if (tid == 0) bpe_finish(w, slot, gpos, c);
                 __syncthreads();
             }
         }
     }
-    // ---- the block that finishes last (k_bpe ran before this kernel) scans the chunk totals for k_emit --------------
+}
+
+// k_bpe_fin: (1) an entry that was found to repeat an earlier one (dedup_check) takes over that entry's result: its
+// ids are read from the earlier piece's place in the pool, only the id count is added to the entry's own tile;
+// (2) the block that finishes last scans the chunk totals for k_emit.
+#define FIN_SMEM_WORDS (CS_TILE + CS_TILE / 32u + 4u * SPL_BPE_THREADS + 4u)
+__global__ void __launch_bounds__(SPL_BPE_THREADS) k_bpe_fin(SplWork w) {
+    __shared__ __align__(16) uint32_t fin_smem[FIN_SMEM_WORDS];
+    __shared__ uint32_t s_last;
+    SPL_RETURN_IF_BAD_OFFSETS(w);
+    const uint32_t tid = threadIdx.x;
+    if (w.dd_tab && w.counters[SPL_CTR_DUP]) {
+        const uint32_t lo = w.ml_base[2], hi = w.ml_base[SPL_NCLS - 1];           // the classes dedup_check looks at
+        for (uint32_t c = 2; c < SPL_NCLS - 1; ++c) {
+            const uint32_t n = w.counters[SPL_CTR_CLS + c];
+            for (uint32_t i = blockIdx.x * SPL_BPE_THREADS + tid; i < n; i += gridDim.x * SPL_BPE_THREADS) {
+                const uint32_t midx = w.ml_base[c] + i;
+                const uint64_t e = w.mlist[midx];
+                if (!(e & SPL_ML_DUP)) continue;
+                const uint32_t rep = w.dup_of[midx - lo];
+                if (rep < lo || rep >= hi) continue;                            // (cannot happen)
+                const uint64_t re = w.mlist[rep];
+                const uint32_t cnt = (uint32_t)(re >> 32) & SPL_ML_LEN_MASK, gpos = (uint32_t)e;
+                w.mlist[midx] = (uint64_t)(uint32_t)re | ((uint64_t)cnt << 32) | SPL_ML_DONE;
+                if (cnt != 1u) {
+                    atomicAdd(&w.tinfo[gpos / SPL_TILE].extra, (int32_t)cnt - 1);
+                    atomicAdd(&w.chunk_cnt[gpos / (SPL_TILE * SPL_CHUNK_TILES)], (int32_t)cnt - 1);
+                }
+            }
+        }
+    }
     __syncthreads();
     if (tid == 0) {
         __threadfence();
-        s_bcast = atomicAdd(&w.counters[SPL_CTR_TICKET], 1u) == gridDim.x - 1u;
+        s_last = atomicAdd(&w.counters[SPL_CTR_TICKET], 1u) == gridDim.x - 1u;
     }
     __syncthreads();
-    if (s_bcast) {
+    if (s_last) {
         __threadfence();
-        chunk_scan_block(w, bpe_smem);
+        chunk_scan_block(w, fin_smem);
     }
 }
 
@@ -1041,6 +1301,10 @@ __device__ __forceinline__ uint32_t emit_count(const SplWork& w, uint32_t v, boo
 
 __global__ void __launch_bounds__(SPL_THREADS, 8) k_emit(SplWork w) {
     __shared__ EmitSmem sm;
+    if (w.counters[SPL_CTR_ERR] & SPL_DEVERR_OFFSETS) {            // rejected offsets: nothing was computed; deliver the flag
+        if (blockIdx.x == 0 && threadIdx.x == 0 && w.host_meta) { w.host_meta[0] = 0; w.host_meta[2] = 0; w.host_meta[1] = w.counters[SPL_CTR_ERR]; }
+        return;
+    }
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t tile = blockIdx.x, tile0 = tile * SPL_TILE;
     const uint32_t* __restrict__ pv = w.pv + tile0;
@@ -1168,7 +1432,8 @@ __global__ void __launch_bounds__(SPL_THREADS, 8) k_emit(SplWork w) {
             if (w.tok_total_out) *w.tok_total_out = base + prefix + rel;
             if (w.host_meta) {                                 // the call's summary, straight to the host (no copy on this stream)
                 w.host_meta[0] = prefix + rel;
-                w.host_meta[1] = (uint64_t)w.counters[SPL_CTR_ERR] | ((uint64_t)w.counters[SPL_CTR_HUGE_POOL] << 32);
+                w.host_meta[2] = *reinterpret_cast<const uint64_t*>(&w.counters[SPL_CTR_HUGE_POOL]);
+                w.host_meta[1] = w.counters[SPL_CTR_ERR];
             }
         }
     }
@@ -1180,20 +1445,26 @@ __global__ void __launch_bounds__(SPL_THREADS, 8) k_emit(SplWork w) {
 void spl_encode_init() {
     cudaFuncSetAttribute(k_bpe_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BPE_SMEM_BYTES);
     cudaFuncSetAttribute(k_bpe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WK_SMEM_BYTES);
-    cudaFuncSetAttribute(k_probe, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
+    cudaFuncSetAttribute(k_probe<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
+    cudaFuncSetAttribute(k_probe<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
     cudaFuncSetAttribute(k_emit, cudaFuncAttributePreferredSharedMemoryCarveout, 75);
     cudaGetLastError();
 }
 
 void spl_launch_encode_stage(const SplWork& w, int num_sms, cudaStream_t stream, SplMarkFn mark, void* ctx) {
-    k_probe<<<w.n_tiles, SPL_THREADS, 0, stream>>>(w);
+    // staging by bulk copy (TMA engine) or through registers: SPL_PROBE_BULK=0 selects the latter (A/B measurements)
+    static const bool bulk = [] { const char* e = getenv("SPL_PROBE_BULK"); return !e || e[0] != '0'; }();
+    if (bulk) k_probe<true><<<w.n_tiles, SPL_THREADS, 0, stream>>>(w);
+    else k_probe<false><<<w.n_tiles, SPL_THREADS, 0, stream>>>(w);
     mark(ctx, "k_probe");
     // first length class merged by windowed rounds (measured crossover; SPL_BPE_WIN_CLS overrides it for experiments)
     static const uint32_t win_cls = [] { const char* e = getenv("SPL_BPE_WIN_CLS"); return e ? (uint32_t)atoi(e) : SPL_BPE_WIN_CLS; }();
     k_bpe<<<(uint32_t)num_sms * 6u, SPL_BPE_THREADS, WK_SMEM_BYTES, stream>>>(w);
     mark(ctx, "k_bpe");
-    k_bpe_long<<<(uint32_t)num_sms * 4u, SPL_BPE_THREADS, BPE_SMEM_BYTES, stream>>>(w, win_cls);   // + the chunk scan, by its last block
+    k_bpe_long<<<(uint32_t)num_sms * 4u, SPL_BPE_THREADS, BPE_SMEM_BYTES, stream>>>(w, win_cls);
     mark(ctx, "k_bpe_long");
+    k_bpe_fin<<<(uint32_t)num_sms, SPL_BPE_THREADS, 0, stream>>>(w);                                // duplicates + the chunk scan, by its last block
+    mark(ctx, "k_bpe_fin");
     k_emit<<<w.n_tiles, SPL_THREADS, 0, stream>>>(w);
     mark(ctx, "k_emit");
 }

@@ -38,6 +38,7 @@ __global__ void k_mark_docs(SplWork w) {
 // k_mark_specials: every occurrence of a special string that lies inside one document
 // ------------------------------------------------------------------------------------------
 __global__ void k_mark_specials(SplWork w) {
+    SPL_RETURN_IF_BAD_OFFSETS(w);
     const SplTables* T = w.T;
     uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < w.N; i += stride) {
@@ -160,6 +161,7 @@ __device__ void pretok_tile(const SplWork& w, PretokSmem& sm, uint32_t tile0, bo
 
 __global__ void __launch_bounds__(SPL_THREADS) k_pretok(SplWork w) {
     __shared__ PretokSmem sm;
+    SPL_RETURN_IF_BAD_OFFSETS(w);
     pretok_tile(w, sm, blockIdx.x * SPL_TILE, false);
 }
 
@@ -170,6 +172,7 @@ __global__ void __launch_bounds__(SPL_THREADS) k_pretok(SplWork w) {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SPL_FAST_THREADS) k_pretok_fast(SplWork w) {
     __shared__ FastSmem sm;
+    SPL_RETURN_IF_BAD_OFFSETS(w);
     const int k = threadIdx.x;
     const int gw0 = (int)(blockIdx.x * SPL_FAST_PAYLOAD) - (int)SPL_FAST_HALO;
     const int gw = gw0 + k;
@@ -231,6 +234,7 @@ __global__ void __launch_bounds__(SPL_FAST_THREADS) k_pretok_fast(SplWork w) {
 // tiles the fast path declined: the sequential rules, two SPL_TILE tiles per fast tile
 __global__ void __launch_bounds__(SPL_THREADS) k_pretok_fb(SplWork w) {
     __shared__ PretokSmem sm;
+    SPL_RETURN_IF_BAD_OFFSETS(w);
     const uint32_t n = w.counters[SPL_CTR_FB];
     for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
         const uint32_t t0 = w.fb_list[i] * (SPL_FAST_PAYLOAD * 32u);

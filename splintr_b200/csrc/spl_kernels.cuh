@@ -39,8 +39,12 @@ __host__ __device__ inline uint32_t spl_class_log2group(uint32_t c) { return c <
 #define SPL_PV_NONE  0xFFFFFFFFu      // the piece produces no id (byte unknown to the vocabulary)
 // miss-list entry before the merge kernels:  gpos:32 | len:31
 // miss-list entry after:                      gpos:32 | id count:31 | SPL_ML_DONE    (ids at pool[gpos ..])
-#define SPL_ML_LEN_MASK 0x7FFFFFFFu
+// SPL_ML_SEG: the entry is a SEGMENT of a piece (spl_segment.h): the whole-piece probe does not apply to it
+// SPL_ML_DUP: same bytes as an earlier entry (dup_of[] names it): k_bpe_fin copies that entry's result
+#define SPL_ML_LEN_MASK 0x1FFFFFFFu
 #define SPL_ML_DONE (1ull << 63)
+#define SPL_ML_SEG  (1ull << 62)
+#define SPL_ML_DUP  (1ull << 61)
 
 // one record per tile, so that k_emit learns everything about its tile (and its chunk) from one line
 struct SplTileInfo {
@@ -72,11 +76,16 @@ struct SplWork {
     uint32_t*       counters;         // [SPL_CTR_WORDS]: see SPL_CTR_*
     uint32_t*       fb_list;          // [n_fast_tiles] fast-path tiles handed to the sequential rules
     uint32_t        n_fast_tiles;
+    // duplicate long pieces (the merge loop runs once per distinct byte string, like the reference's chunk cache,
+    // tokenizer.rs:667-724): open-addressing table hash tag:32 | miss-list index + 1, zero-initialised; dd_tab == nullptr: off
+    unsigned long long* dd_tab;
+    uint32_t        dd_mask;          // slots - 1
+    uint32_t*       dup_of;           // [entries of the classes >= 2] miss-list index of the entry with the same bytes
     uint32_t*       huge_pool;        // scratch for pieces that outgrow shared memory
-    uint32_t        huge_pool_words;
+    uint64_t        huge_pool_words;
     uint32_t*       ids;              // [>= N]
     uint64_t*       out_off;          // [n_docs+1]
-    uint64_t*       host_meta;        // optional, mapped pinned host memory: [0] id count, [1] error flags | huge-pool need << 32
+    uint64_t*       host_meta;        // optional, mapped pinned host memory: [0] id count, [1] error flags, [2] words of huge-piece scratch the pass asked for
     const uint64_t* tok_base_in;      // optional: ids of the shard's earlier chunks, added to out_off (not to the id positions)
     uint64_t*       tok_total_out;    // optional: receives *tok_base_in + this pass's id count
     const SplTables* T;               // device copy of the tables
@@ -86,12 +95,17 @@ struct SplWork {
 };
 
 // SplWork::counters
-enum : uint32_t { SPL_CTR_ERR = 1, SPL_CTR_HUGE_POOL = 2, SPL_CTR_FB = 3,
+enum : uint32_t { SPL_CTR_ERR = 1, SPL_CTR_HUGE_POOL = 2 /* 64 bit: words 2 and 3 */, SPL_CTR_FB = 4,
+                  SPL_CTR_DUP = 5,            // long pieces that were duplicates of an earlier one
+                  SPL_CTR_REFINED = 6,        // tiles that went through k_probe's refining pass
                   SPL_CTR_CLS = 8,            // [8 .. 8 + SPL_NCLS): entries in the miss list of each class
-                  SPL_CTR_TICKET = 16,        // blocks of k_bpe_long that are done (the last one scans the chunk totals)
+                  SPL_CTR_TICKET = 16,        // blocks of k_bpe_fin that are done (the last one scans the chunk totals)
                   SPL_CTR_WORDS = 32 };
 
 enum : uint32_t { SPL_DEVERR_OFFSETS = 1u, SPL_DEVERR_HUGE_POOL = 2u };
+// Every kernel behind k_mark_docs starts with this: document offsets that k_mark_docs rejected must never be used as
+// indices (the host reports SPL_ERR_INVALID_ARG from the flag; k_emit still delivers it)
+#define SPL_RETURN_IF_BAD_OFFSETS(w) do { if ((w).counters[SPL_CTR_ERR] & SPL_DEVERR_OFFSETS) return; } while (0)
 
 // optional per-kernel device timing: ev[i] is recorded before kernel i, ev[n] after the last
 #define SPL_PROF_MAX 16
@@ -175,4 +189,7 @@ struct SplProbeScratch {
     uint16_t mloc[SPL_TILE];                  // missed pieces: class 0 from the bottom of the warp's range, class 1 from its top
     uint32_t wtot[SPL_THREADS / 32];
     uint32_t last_end;                        // window position of the end of the tile's last piece
+    uint32_t segw[SPL_TILE / 32];             // refining pass: safe boundaries found inside missed pieces (new piece starts)
+    uint32_t mstw[SPL_TILE / 32];             // refining pass: starts of the pieces the whole-piece probe missed
+    uint32_t n_hi;                            // bytes >= 0x80 in the tile (decides whether the tile is refined)
 };

@@ -65,7 +65,7 @@ SPL_HD bool spl_boundary_safe(const uint32_t* irr, const uint32_t* h2, uint32_t 
     return !((h2[hb >> 5] >> (hb & 31u)) & 1u);
 }
 
-#define SPL_SEG_MAX 32u            // the per-lane merge loop holds a segment of up to this many bytes
+#define SPL_SEG_MAX 32u            // the per-lane merge loop (k_bpe) holds a piece or segment of up to this many bytes
 
 // code point of a well-formed 2- or 3-byte character (index into the single-character table)
 SPL_HD uint32_t spl_u8_cp23(uint32_t packed, uint32_t L) {
@@ -79,22 +79,20 @@ SPL_HD uint32_t spl_u8_cp23(uint32_t packed, uint32_t L) {
 #define SPL_CTZ32(x) ((uint32_t)__builtin_ctz(x))
 #endif
 
-// The segment of a piece that starts at byte `pos` (a character boundary): returns its end, the first safe boundary
-// after pos or `len`.  Gives up -- returns more than pos + SPL_SEG_MAX -- as soon as the segment outgrows the per-lane
-// merge loop.  rd.load4(i) = the four bytes from piece-relative index i on, little endian (bytes beyond len are never
-// interpreted).  `taint` is sticky per piece: once a byte sequence is not UTF-8 nothing after it is declared safe.
-// first_packed / first_len: the character at pos (length 0 if malformed); first_w4 = rd.load4(pos).
-template <class Reader>
-SPL_HD uint32_t spl_segment_end(const Reader& rd, uint32_t pos, uint32_t len, bool& taint,
-                                const uint32_t* irr, const uint32_t* h2, uint32_t h2_log2,
-                                uint32_t& first_packed, uint32_t& first_len, uint32_t& first_w4) {
+// Every safe boundary of the piece [0, len) at a position below `limit`: f(pos) is called, in increasing order, for
+// each byte position pos (0 < pos < min(len, limit)) where a segment ends and the next one starts.
+// rd.load4(i) = the four bytes from piece-relative index i on, little endian (bytes at or beyond len are never
+// interpreted).  Once a byte sequence is not UTF-8 nothing after it is declared safe.
+template <class Reader, class F>
+SPL_HD void spl_safe_boundaries(const Reader& rd, uint32_t len, uint32_t limit,
+                                const uint32_t* irr, const uint32_t* h2, uint32_t h2_log2, F f) {
+    if (limit > len) limit = len;
     uint32_t a = 0;
-    const uint32_t w4 = rd.load4(pos);
-    uint32_t la = spl_u8_char(w4, len - pos, a);
-    first_packed = a; first_len = la; first_w4 = w4;
-    if (la == 0u) { taint = true; la = 1u; a = w4 & 0xFFu; }
-    uint32_t end = pos + la;
-    while (end < len) {
+    uint32_t w4 = rd.load4(0);
+    uint32_t la = spl_u8_char(w4, len, a);
+    if (la == 0u) return;
+    uint32_t end = la;
+    while (end < limit) {
         const uint32_t wb = rd.load4(end);
         if (la == 1u) {
             // ASCII | ASCII is never asked: skip over the run four bytes at a time
@@ -104,17 +102,14 @@ SPL_HD uint32_t spl_segment_end(const Reader& rd, uint32_t pos, uint32_t len, bo
             if (na) {
                 end += na;
                 a = (wb >> (8u * (na - 1u))) & 0xFFu;
-                if (end - pos > SPL_SEG_MAX) break;
                 continue;
             }
         }
         uint32_t b = 0;
         const uint32_t lb = spl_u8_char(wb, len - end, b);
-        if (lb == 0u) taint = true;
-        if (!taint && spl_boundary_safe(irr, h2, h2_log2, a, la, b)) break;
-        la = lb ? lb : 1u; a = lb ? b : (wb & 0xFFu);
-        end += la;
-        if (end - pos > SPL_SEG_MAX) break;
+        if (lb == 0u) return;
+        if (spl_boundary_safe(irr, h2, h2_log2, a, la, b)) f(end);
+        la = lb; a = b;
+        end += lb;
     }
-    return end;
 }

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import base64
 import ctypes
+import threading
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -96,6 +97,9 @@ class Tokenizer:
     def _init(self, data: bytes, pattern: str, special_tokens: Dict[str, int], byte_level: bool,
               sentencepiece: bool, devices: Optional[Sequence[int]] = None) -> None:
         self._handle = None
+        # one call in flight per handle (include/splintr_b200.h): ctypes releases the GIL around the C call, the reference's
+        # binding never does (no allow_threads in bindings.rs), so threads that share a Tokenizer are serialised here
+        self._lock = threading.RLock()
         if not isinstance(pattern, str):
             raise TypeError("pattern must be str")
         if sentencepiece:
@@ -111,6 +115,8 @@ class Tokenizer:
         for k, v in special_tokens.items():
             if not isinstance(k, str) or not isinstance(v, int):
                 raise TypeError("special_tokens must map str -> int")
+            if not 0 <= v <= 0xFFFFFFFF:                     # u32 in the reference (PyO3 raises OverflowError)
+                raise OverflowError("special token id out of range for u32")
         self._vocab_data = bytes(data)
         self._pattern = pattern
         self._special_tokens = dict(special_tokens)
@@ -231,23 +237,31 @@ class Tokenizer:
         n_docs = offsets.shape[0] - 1
         if n_docs < 0:
             raise ValueError("offsets must have n_docs + 1 entries")
+        n_avail = None
         if isinstance(data, (bytes, bytearray)):
             keep = bytes(data)
+            n_avail = len(keep)
             ptr = ctypes.cast(ctypes.c_char_p(keep), ctypes.c_void_p)
         elif isinstance(data, np.ndarray):
             keep = np.ascontiguousarray(data, dtype=np.uint8)
+            n_avail = int(keep.size)
             ptr = ctypes.c_void_p(keep.ctypes.data)
         elif isinstance(data, int):
             keep = None
             ptr = ctypes.c_void_p(data)
         else:
             raise TypeError("data must be bytes, bytearray, numpy uint8 array or an address")
+        if int(offsets[0]) != 0:
+            raise ValueError("offsets must start at 0")
+        if n_avail is not None and int(offsets[-1]) > n_avail:
+            raise ValueError("offsets[-1] exceeds the length of data")
         res = ctypes.c_void_p()
-        rc = lib.spl_encode_batch(self._handle, ptr, ctypes.c_void_p(offsets.ctypes.data), n_docs,
-                                  _lib.SPL_ENCODE_WITH_SPECIAL if with_special else 0, ctypes.byref(res))
+        with self._lock:
+            rc = lib.spl_encode_batch(self._handle, ptr, ctypes.c_void_p(offsets.ctypes.data), n_docs,
+                                      _lib.SPL_ENCODE_WITH_SPECIAL if with_special else 0, ctypes.byref(res))
+            msg = _lib.last_error(self._handle) if rc != _lib.SPL_OK else ""
         del keep
         if rc != _lib.SPL_OK:
-            msg = _lib.last_error(self._handle)
             if rc in (_lib.SPL_ERR_INVALID_ARG, _lib.SPL_ERR_UNSUPPORTED):
                 raise ValueError(msg)
             raise RuntimeError(f"splintr_b200: {msg} (code {rc})")
@@ -273,7 +287,8 @@ class Tokenizer:
         storage is 16-byte aligned and padded to a multiple of 16, `d_offsets` = CUDA int64
         tensor [n_docs+1] (non-negative, so bit-identical to the ABI's uint64).  Work is enqueued
         on torch's current stream.  Returns (ids int32[capacity], out_offsets int64[n_docs+1],
-        n_tokens or None when sync=False); ids[:n_tokens] are valid."""
+        n_tokens or None when sync=False); ids[:n_tokens] are valid.  With sync=False nothing has been checked yet:
+        call device_status() once the stream has run (0 = good)."""
         import torch
         lib = _lib.load()
         n_bytes = int(d_bytes.numel())
@@ -287,18 +302,44 @@ class Tokenizer:
             out_offsets = torch.empty(n_docs + 1, dtype=torch.int64, device=d_bytes.device)
         n_tok = ctypes.c_uint64(0)
         stream = torch.cuda.current_stream(d_bytes.device).cuda_stream
-        rc = lib.spl_encode_batch_device(self._handle, dev_index, ctypes.c_void_p(d_bytes.data_ptr()), n_bytes,
-                                         ctypes.c_void_p(d_offsets.data_ptr()), n_docs,
-                                         _lib.SPL_ENCODE_WITH_SPECIAL if with_special else 0,
-                                         ctypes.c_void_p(ids_out.data_ptr()), int(ids_out.numel()),
-                                         ctypes.c_void_p(out_offsets.data_ptr()), ctypes.c_void_p(stream),
-                                         ctypes.byref(n_tok) if sync else None)
+        with self._lock:
+            rc = lib.spl_encode_batch_device(self._handle, dev_index, ctypes.c_void_p(d_bytes.data_ptr()), n_bytes,
+                                             ctypes.c_void_p(d_offsets.data_ptr()), n_docs,
+                                             _lib.SPL_ENCODE_WITH_SPECIAL if with_special else 0,
+                                             ctypes.c_void_p(ids_out.data_ptr()), int(ids_out.numel()),
+                                             ctypes.c_void_p(out_offsets.data_ptr()), ctypes.c_void_p(stream),
+                                             ctypes.byref(n_tok) if sync else None)
+            msg = _lib.last_error(self._handle) if rc != _lib.SPL_OK else ""
         if rc != _lib.SPL_OK:
-            msg = _lib.last_error(self._handle)
             if rc in (_lib.SPL_ERR_INVALID_ARG, _lib.SPL_ERR_UNSUPPORTED):
                 raise ValueError(msg)
             raise RuntimeError(f"splintr_b200: {msg} (code {rc})")
         return ids_out, out_offsets, (int(n_tok.value) if sync else None)
+
+    def device_status(self, dev_index: int = 0) -> int:
+        """spl_device_status: error flags of the last encode_device(sync=False) pass on that device (synchronises
+        torch's current stream).  0 = good, 1 = the document offsets were rejected, 2 = scratch for pieces beyond
+        1 KiB exhausted (run the call again with sync=True)."""
+        import torch
+        flags = ctypes.c_uint32(0)
+        with self._lock:
+            stream = torch.cuda.current_stream().cuda_stream
+            rc = _lib.load().spl_device_status(self._handle, dev_index, ctypes.c_void_p(stream), ctypes.byref(flags))
+        if rc != _lib.SPL_OK:
+            raise RuntimeError(f"splintr_b200: spl_device_status failed (code {rc})")
+        return int(flags.value)
+
+    def debug_counters(self, dev_index: int = 0) -> Dict[str, int]:
+        """spl_debug_counters: what the last device pass did (duplicates skipped, tiles refined, misses per length class)."""
+        import torch
+        out = (ctypes.c_uint32 * 32)()
+        with self._lock:
+            stream = torch.cuda.current_stream().cuda_stream
+            rc = _lib.load().spl_debug_counters(self._handle, dev_index, ctypes.c_void_p(stream), out)
+        if rc != _lib.SPL_OK:
+            raise RuntimeError(f"splintr_b200: spl_debug_counters failed (code {rc})")
+        return {"error_flags": out[1], "fallback_tiles": out[4], "duplicates": out[5], "refined_tiles": out[6],
+                "misses_by_class": [out[8 + c] for c in range(8)]}
 
     # -- ingestion (SURVEY 8f N4): JSON Lines -> packed text + offsets on the device ---------------
     def ingest_jsonl_device(self, d_jsonl, field: str = "text", dev_index: int = 0):
@@ -316,11 +357,12 @@ class Tokenizer:
         offs = torch.empty(n_lines_max, dtype=torch.int64, device=d_jsonl.device)
         st = _lib.SplIngestStats()
         stream = torch.cuda.current_stream(d_jsonl.device).cuda_stream
-        rc = lib.spl_ingest_jsonl_device(self._handle, dev_index, ctypes.c_void_p(d_jsonl.data_ptr()), n, field.encode("utf-8"),
-                                         ctypes.c_void_p(text.data_ptr()), n, ctypes.c_void_p(offs.data_ptr()), n_lines_max,
-                                         ctypes.c_void_p(stream), ctypes.byref(st))
+        with self._lock:
+            rc = lib.spl_ingest_jsonl_device(self._handle, dev_index, ctypes.c_void_p(d_jsonl.data_ptr()), n, field.encode("utf-8"),
+                                             ctypes.c_void_p(text.data_ptr()), n, ctypes.c_void_p(offs.data_ptr()), n_lines_max,
+                                             ctypes.c_void_p(stream), ctypes.byref(st))
+            msg = _lib.last_error(self._handle) if rc != _lib.SPL_OK else ""
         if rc != _lib.SPL_OK:
-            msg = _lib.last_error(self._handle)
             if rc in (_lib.SPL_ERR_INVALID_ARG, _lib.SPL_ERR_UNSUPPORTED):
                 raise ValueError(msg)
             raise RuntimeError(f"splintr_b200: {msg} (code {rc})")
@@ -346,11 +388,12 @@ class Tokenizer:
             ptr = ctypes.c_void_p(keep.ctypes.data)
         res = ctypes.c_void_p()
         ist = _lib.SplIngestStats()
-        rc = lib.spl_encode_jsonl(self._handle, ptr, n, field.encode("utf-8"),
-                                  _lib.SPL_ENCODE_WITH_SPECIAL if with_special else 0, ctypes.byref(res), ctypes.byref(ist))
+        with self._lock:
+            rc = lib.spl_encode_jsonl(self._handle, ptr, n, field.encode("utf-8"),
+                                      _lib.SPL_ENCODE_WITH_SPECIAL if with_special else 0, ctypes.byref(res), ctypes.byref(ist))
+            msg = _lib.last_error(self._handle) if rc != _lib.SPL_OK else ""
         del keep
         if rc != _lib.SPL_OK:
-            msg = _lib.last_error(self._handle)
             if rc in (_lib.SPL_ERR_INVALID_ARG, _lib.SPL_ERR_UNSUPPORTED):
                 raise ValueError(msg)
             raise RuntimeError(f"splintr_b200: {msg} (code {rc})")
@@ -480,10 +523,11 @@ class Tokenizer:
         if int(offsets[-1]) != ids.shape[0]:
             raise ValueError("offsets[-1] must equal the number of ids")
         res = ctypes.c_void_p()
-        rc = lib.spl_decode_batch(self._handle, ctypes.c_void_p(ids.ctypes.data), ctypes.c_void_p(offsets.ctypes.data),
-                                  n_docs, ctypes.byref(res))
+        with self._lock:
+            rc = lib.spl_decode_batch(self._handle, ctypes.c_void_p(ids.ctypes.data), ctypes.c_void_p(offsets.ctypes.data),
+                                      n_docs, ctypes.byref(res))
+            msg = _lib.last_error(self._handle) if rc != _lib.SPL_OK else ""
         if rc != _lib.SPL_OK:
-            msg = _lib.last_error(self._handle)
             if rc in (_lib.SPL_ERR_INVALID_ARG, _lib.SPL_ERR_UNSUPPORTED):
                 raise ValueError(msg)
             raise RuntimeError(f"splintr_b200: {msg} (code {rc})")
@@ -517,16 +561,18 @@ class Tokenizer:
         for _ in range(2):
             out = torch.empty(cap, dtype=torch.uint8, device=d_tok_offsets.device)
             nb = ctypes.c_uint64(0)
-            rc = lib.spl_decode_batch_device(self._handle, dev_index, ctypes.c_void_p(d_ids.data_ptr()), n_tok,
-                                             ctypes.c_void_p(d_tok_offsets.data_ptr()), n_docs,
-                                             ctypes.c_void_p(out.data_ptr()), cap, ctypes.c_void_p(out_off.data_ptr()),
-                                             ctypes.c_void_p(stream), ctypes.byref(nb))
+            with self._lock:
+                rc = lib.spl_decode_batch_device(self._handle, dev_index, ctypes.c_void_p(d_ids.data_ptr()), n_tok,
+                                                 ctypes.c_void_p(d_tok_offsets.data_ptr()), n_docs,
+                                                 ctypes.c_void_p(out.data_ptr()), cap, ctypes.c_void_p(out_off.data_ptr()),
+                                                 ctypes.c_void_p(stream), ctypes.byref(nb))
+                msg = _lib.last_error(self._handle) if rc != _lib.SPL_OK else ""
             if rc == _lib.SPL_OK:
                 return out[:int(nb.value)], out_off
             if rc == _lib.SPL_ERR_INVALID_ARG and int(nb.value) > cap:
                 cap = int(nb.value)
                 continue
-            raise RuntimeError(f"splintr_b200: {_lib.last_error(self._handle)} (code {rc})")
+            raise RuntimeError(f"splintr_b200: {msg} (code {rc})")
         raise RuntimeError("splintr_b200: decode capacity retry failed")
 
     def _decode_many(self, token_lists, errors: str) -> List[str]:

@@ -81,41 +81,42 @@ struct HostPieceReader {
     uint32_t load4(uint32_t i) const { uint32_t v = 0; for (uint32_t q = 0; q < 4 && i + q < n; ++q) v |= (uint32_t)p[i + q] << (8 * q); return v; }
 };
 
-static uint64_t ht_seg_stats[4];     // segments, single-character segments, pieces left to the long path, safe boundaries
+static uint64_t ht_seg_stats[4];     // segments, single-character segments, segments beyond SPL_SEG_MAX, safe boundaries
 
-// The device path for one piece (k_probe + k_bpe's segment walker + k_bpe_long for what the walker leaves):
-// whole-piece probe, then the independent segments of spl_segment.h -- a single 2- or 3-byte character through
-// char_tok, any other segment through the merge loop -- and the whole piece through the merge loop if a segment
-// outgrows SPL_SEG_MAX.
+// The device path for one piece: whole-piece probe (k_probe); on a miss the piece falls apart at its safe boundaries
+// (spl_segment.h, k_probe's refining pass) -- a segment that is a single 2- or 3-byte character goes through char_tok,
+// any other segment through the merge loop (k_bpe up to SPL_SEG_MAX bytes, k_bpe_long beyond).
+// tile_limit: boundaries at or beyond this byte of the piece are not looked for (the device only refines inside the
+// tile that owns the piece).
+static uint32_t ht_tile_limit = 0xFFFFFFFFu;
 static void ht_bpe_piece(const SplHostTables& T, const uint8_t* p, uint32_t n, std::vector<uint32_t>& out, bool segments = true) {
     uint32_t whole = spl_host_lookup_piece(T, p, n);
     if (whole != SPL_RANK_NONE) { out.push_back(whole); return; }
     if (n == 1) { if (T.byte_sym[p[0]] < SPL_UNK_BASE) out.push_back(T.byte_sym[p[0]]); return; }
     if (!segments) { spl_host_merge_loop(T, p, n, out); return; }
-    std::vector<uint32_t> tmp;
     HostPieceReader rd{p, n};
-    bool taint = false, bail = false;
+    std::vector<uint32_t> cuts;
+    spl_safe_boundaries(rd, n, ht_tile_limit, T.seg_irr.data(), T.seg_h2.data(), T.seg_h2_log2, [&](uint32_t pos) { cuts.push_back(pos); });
+    cuts.push_back(n);
     uint32_t pos = 0;
-    while (pos < n) {
-        uint32_t a_first, la_first, w4;
-        const uint32_t end = spl_segment_end(rd, pos, n, taint, T.seg_irr.data(), T.seg_h2.data(), T.seg_h2_log2, a_first, la_first, w4);
+    for (uint32_t end : cuts) {
         const uint32_t sl = end - pos;
-        if (sl > SPL_SEG_MAX) { bail = true; break; }
         ++ht_seg_stats[0];
         if (end < n) ++ht_seg_stats[3];
+        if (sl > SPL_SEG_MAX) ++ht_seg_stats[2];
+        uint32_t packed = 0;
+        const uint32_t la = spl_u8_char(rd.load4(pos), sl, packed);
         if (sl == 1) {
-            const uint32_t sy = T.byte_sym[w4 & 0xFF];
-            if (sy < SPL_UNK_BASE) tmp.push_back(sy);
-        } else if (sl == la_first && sl <= 3 && T.char_tok[spl_u8_cp23(a_first, sl)] != SPL_RANK_NONE) {
-            tmp.push_back(T.char_tok[spl_u8_cp23(a_first, sl)]);
+            const uint32_t sy = T.byte_sym[p[pos]];
+            if (sy < SPL_UNK_BASE) out.push_back(sy);
+        } else if (la == sl && sl <= 3 && T.char_tok[spl_u8_cp23(packed, sl)] != SPL_RANK_NONE) {
+            out.push_back(T.char_tok[spl_u8_cp23(packed, sl)]);
             ++ht_seg_stats[1];
         } else {
-            spl_host_merge_loop(T, p + pos, sl, tmp);
+            spl_host_merge_loop(T, p + pos, sl, out);
         }
         pos = end;
     }
-    if (bail) { ++ht_seg_stats[2]; spl_host_merge_loop(T, p, n, out); }
-    else out.insert(out.end(), tmp.begin(), tmp.end());
 }
 
 extern "C" {
@@ -141,6 +142,7 @@ void ht_stats(void* h, uint64_t* out) {
     uint64_t ct = 0; for (uint32_t v : t->char_tok) ct += v != SPL_RANK_NONE;
     out[13] = ct;
 }
+void ht_set_tile_limit(uint32_t l) { ht_tile_limit = l; }
 void ht_seg_counters(uint64_t* out, int reset) { for (int i = 0; i < 4; ++i) { out[i] = ht_seg_stats[i]; if (reset) ht_seg_stats[i] = 0; } }
 
 // one piece (no pre-tokenizer): segments != 0 -> the device path, 0 -> whole-piece probe + the plain merge loop

@@ -41,6 +41,7 @@ def load():
     lib.ht_encode_piece.restype = ctypes.c_long
     lib.ht_encode_piece.argtypes = [vp, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_int, vp, ctypes.c_size_t]
     lib.ht_seg_counters.argtypes = [vp, ctypes.c_int]
+    lib.ht_set_tile_limit.argtypes = [ctypes.c_uint32]
     lib.ht_jsonl.restype = ctypes.c_int
     lib.ht_jsonl.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, vp, vp, vp]
     lib.ht_set_fast_ext.argtypes = [ctypes.c_int]
@@ -54,8 +55,13 @@ def load():
     return lib
 
 
+def set_tile_limit(limit: int = 0xFFFFFFFF):
+    """boundaries at or beyond this byte of a piece are not looked for (the device refines a piece only inside its tile)"""
+    load().ht_set_tile_limit(limit)
+
+
 def seg_counters(reset: bool = True):
-    """(segments, single-character segments, pieces left to the long path, safe boundaries) since the last reset."""
+    """(segments, single-character segments, segments beyond SPL_SEG_MAX, safe boundaries) since the last reset."""
     out = np.zeros(4, dtype=np.uint64)
     load().ht_seg_counters(out.ctypes.data, 1 if reset else 0)
     return [int(x) for x in out]

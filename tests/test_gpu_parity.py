@@ -254,6 +254,78 @@ def test_custom_vocab_with_unknown_bytes(toks):
         assert t.encode(s) == o.encode(s), s
 
 
+def test_huge_piece_scratch_grows_once_per_attempt(monkeypatch):
+    """Pieces beyond 1 KiB that the segment walker leaves alone take global scratch (4 words per byte).  Several
+    pipeline chunks that each outgrow the 64 MiB pool must make the call resize it ONCE and succeed (it used to
+    quadruple per failing chunk and run out of memory); spl_encode_jsonl retries the same way."""
+    import base64, json
+    from splintr_b200 import Tokenizer, CL100K_BASE_PATTERN
+    vb = b"".join(base64.b64encode(bytes([b])) + b" " + str(b).encode() + b"\n" for b in range(256))   # bytes only: no merges
+    monkeypatch.setenv("SPL_CHUNK_BYTES", "6000000")
+    t = Tokenizer.from_bytes(vb, CL100K_BASE_PATTERN)
+    monkeypatch.delenv("SPL_CHUNK_BYTES")
+    piece = "#" * 2000 + " "
+    docs = [piece * 300 for _ in range(40)]                      # 24 MB, ~12 000 pieces of 2 000 bytes, ~4 chunks
+    got = t.encode_batch(docs)
+    want = list((piece * 300).encode())
+    assert all(g == want for g in got)
+    jl = "".join(json.dumps({"text": d}) + "\n" for d in docs).encode()
+    ids, off = t.encode_jsonl(jl)
+    assert len(off) == len(docs) + 1 and ids.tolist() == want * len(docs)
+
+
+def test_threads_share_a_tokenizer(toks):
+    """The reference's binding holds the GIL for a whole call, so threads may share a Tokenizer; here a per-object lock
+    serialises them (one call in flight per handle)."""
+    import threading
+    tok, o = toks("cl100k_base"), c_oracle("cl100k_base")
+    d, off = synth.cfg2(vocab_bytes("cl100k_base"), 2000)
+    texts = synth.unpack_texts(d, off)
+    want = o.encode_batch(texts)
+    out, errs = {}, []
+
+    def work(k):
+        try:
+            for r in range(6):
+                lo = (k * 37 + r * 101) % 1500
+                out[(k, r)] = (lo, tok.encode_batch(texts[lo:lo + 300]), tok.decode_batch(want[lo:lo + 20]))
+        except Exception as e:                                   # noqa: BLE001
+            errs.append(e)
+    th = [threading.Thread(target=work, args=(k,)) for k in range(6)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errs, errs
+    for (k, r), (lo, ids, dec) in out.items():
+        assert ids == want[lo:lo + 300] and dec == texts[lo:lo + 20]
+
+
+def test_device_entry_async_status(toks):
+    """sync=False: nothing is checked in the call; spl_device_status delivers the flags, and rejected offsets are never
+    used as indices by the kernels behind k_mark_docs."""
+    import torch
+    tok = toks("cl100k_base")
+    d, o = synth.cfg2(vocab_bytes("cl100k_base"), 300)
+    n = len(d)
+    buf = torch.zeros(n + ((-n) % 16), dtype=torch.uint8, device="cuda")
+    buf[:n].copy_(torch.from_numpy(d))
+    good = torch.from_numpy(o.astype(np.int64)).cuda()
+    ids, out, _ = tok.encode_device(buf[:n], good, sync=False)
+    assert tok.device_status() == 0
+    want_ids, want_off = c_oracle("cl100k_base").encode_packed(d, o)
+    assert np.array_equal(out.cpu().numpy().astype(np.uint64), want_off)
+    bad = good.clone()
+    bad[5] = 10 ** 12                                            # far outside the text
+    bad[9] = bad[8] - 3                                          # decreasing
+    tok.encode_device(buf[:n], bad, sync=False)
+    assert tok.device_status() & 1
+    with pytest.raises(ValueError):
+        tok.encode_device(buf[:n], bad, sync=True)
+    ids2, out2, nt = tok.encode_device(buf[:n], good)            # the handle is still usable
+    assert nt == len(want_ids) and tok.device_status() == 0
+
+
 def test_pipelined_host_call_many_chunks(toks, monkeypatch):
     """spl_encode_batch cuts a shard into pipeline chunks (H2D / kernels / D2H overlapped); force tiny chunks so
     one call runs through dozens of them, with empty and large documents on the chunk boundaries."""
@@ -319,8 +391,9 @@ def test_cfg3_large_host_call_equals_parts(toks):
 # ---- decode on the device ---------------------------------------------------------
 @pytest.mark.parametrize("name", VOCABS + SP_VOCABS)
 def test_decode_batch_matches_host_decode(toks, name):
-    """spl_decode_batch against the host table lookup (mirror of tokenizer.rs:877-897) on ordinary ids, special
-    ids, ids outside the vocabulary (skipped) and, for the byte-level vocabulary, the untranslatable keys."""
+    """spl_decode_batch against the ORACLE's decode_bytes (oracle/py_oracle.py, restating tokenizer.rs:877-897) on
+    ordinary ids, special ids, ids outside the vocabulary (skipped) and, for the byte-level vocabulary, the
+    untranslatable keys (ids 0-2 of deepseek_v3)."""
     t = toks(name)
     rng = random.Random(99)
     vs = t.vocab_size
@@ -332,9 +405,11 @@ def test_decode_batch_matches_host_decode(toks, name):
     ids = np.array([x for l in lists for x in l], dtype=np.uint32)
     data, boff = t.decode_packed(ids, off)
     raw = data.tobytes()
+    o = py_oracle(name)                                          # decode_bytes of the reference, tokenizer.rs:877-897
     for i, l in enumerate(lists):
-        assert raw[int(boff[i]):int(boff[i + 1])] == t.decode_bytes(l), (name, i)
-    assert t.decode_batch_lossy(lists[:50]) == [t.decode_lossy(l) for l in lists[:50]]
+        assert raw[int(boff[i]):int(boff[i + 1])] == o.decode_bytes(l), (name, i)
+        assert t.decode_bytes(l) == o.decode_bytes(l)            # the host-side single-list decode, same oracle
+    assert t.decode_batch_lossy(lists[:50]) == [o.decode_lossy(l) for l in lists[:50]]
 
 
 def test_decode_roundtrip_cfg2_full_and_device_entry(toks):

@@ -65,8 +65,11 @@ def test_segmented_piece_equals_whole_merge_loop(tables):
     hostlib.seg_counters()
     for i in range(60000):
         piece = random_piece(rng, 14 if i % 4 else 60)
+        if i % 16 == 5:
+            hostlib.set_tile_limit(rng.randint(1, len(piece)))       # the piece leaves its tile here: no cuts beyond
         assert t.encode_piece(piece, True) == t.encode_piece(piece, False), (name, piece)
-    segs, single, bailed, safe = hostlib.seg_counters()
+        hostlib.set_tile_limit()
+    segs, single, beyond, safe = hostlib.seg_counters()
     assert safe > 0 and single > 0, "the filters never declared a boundary safe: the test exercised nothing"
 
 
@@ -133,6 +136,6 @@ def test_cjk_falls_apart(tables):
         k = rng.randint(4, 40)
         nchars += k
         t.encode_piece("".join(rng.choice(CJK_COMMON) for _ in range(k)).encode(), True)
-    segs, single, bailed, safe = hostlib.seg_counters()
-    assert bailed == 0
+    segs, single, beyond, safe = hostlib.seg_counters()
+    assert beyond == 0
     assert single > 0.5 * nchars, (name, segs, single, nchars)

@@ -40,4 +40,5 @@ for name in (sys.argv[1:] or list(CFG)):
             best = (ms, kt)
     ntok = int(out[-1].item())
     print(f"{name} {vocab}: {n/1e6:.1f} MB, {len(off)-1} docs, {ntok} ids ({n/max(ntok,1):.2f} B/id): best {best[0]:.3f} ms = {n/best[0]/1e6:.1f} GB/s")
-    print("   ", {k: round(v * 1000, 1) for k, v in best[1].items()}, flush=True)
+    print("   ", {k: round(v * 1000, 1) for k, v in best[1].items()})
+    print("   ", tok.debug_counters(), flush=True)
