@@ -180,8 +180,8 @@ void destroy_ctx(DevCtx& dc) {
 const uint64_t kMaxShardBytes = 0xFFFFFFFFull - 4ull * SPL_WIN;
 
 // layout of the zero-initialised region: counters | duplicate table | chunk_cnt | tinfo | hard | pstart | spec
-struct ZeroLayout { size_t words, n_tiles, dd_slots, off_dd, off_chunk, off_extra, off_hard, off_pstart, off_spec, total; };
-ZeroLayout zero_layout(uint64_t N, bool with_special, bool dedup) {
+struct ZeroLayout { size_t words, n_tiles, dd_slots, off_dd, off_chunk, off_extra, off_hard, off_pstart, off_spec, off_cand, total; };
+ZeroLayout zero_layout(uint64_t N, bool with_special, bool dedup, bool ambiguous = false) {
     ZeroLayout z;
     z.words = (size_t)((N + SPL_WIN) / 32 + 16);
     z.n_tiles = (size_t)(N / SPL_TILE) + 1;
@@ -195,7 +195,8 @@ ZeroLayout zero_layout(uint64_t N, bool with_special, bool dedup) {
     z.off_hard = align_up(z.off_extra + (z.n_tiles + 2) * sizeof(SplTileInfo), 256);
     z.off_pstart = align_up(z.off_hard + z.words * 4, 256);
     z.off_spec = align_up(z.off_pstart + z.words * 4, 256);
-    z.total = with_special ? align_up(z.off_spec + z.words * 4, 256) : z.off_spec;
+    z.off_cand = with_special ? align_up(z.off_spec + z.words * 4, 256) : z.off_spec;
+    z.total = (with_special && ambiguous) ? align_up(z.off_cand + z.words * 4, 256) : z.off_cand;
     return z;
 }
 
@@ -214,7 +215,7 @@ int reserve_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
         tk->err = "one device pass is limited to 4 GiB of text";
         return SPL_ERR_UNSUPPORTED;
     }
-    const ZeroLayout z = zero_layout(N, with_special, tk->dedup);
+    const ZeroLayout z = zero_layout(N, with_special, tk->dedup, !tk->host.specials_unambiguous);
     const MissLayout m = miss_layout(N);
     int rc;
     if ((rc = dc.zero.ensure(z.total, tk->err))) return rc;
@@ -236,7 +237,7 @@ int prepare_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
                  cudaStream_t st, SplWork& w) {
     int rc = reserve_work(tk, dc, N, n_docs, with_special);
     if (rc) return rc;
-    const ZeroLayout z = zero_layout(N, with_special, tk->dedup);
+    const ZeroLayout z = zero_layout(N, with_special, tk->dedup, !tk->host.specials_unambiguous);
     const MissLayout m = miss_layout(N);
     uint32_t n_fast_tiles = (uint32_t)((N + SPL_FAST_PAYLOAD * 32u - 1) / (SPL_FAST_PAYLOAD * 32u));
     CUDA_TRY(cudaMemsetAsync(dc.zero.p, 0, z.total, st), tk->err);
@@ -250,6 +251,7 @@ int prepare_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
     w.hard = (uint32_t*)(zb + z.off_hard);
     w.pstart = (uint32_t*)(zb + z.off_pstart);
     w.spec = with_special ? (uint32_t*)(zb + z.off_spec) : nullptr;
+    w.cand = (with_special && !tk->host.specials_unambiguous) ? (uint32_t*)(zb + z.off_cand) : nullptr;
     w.bitmap_words = z.words;
     w.chunk_state = (uint64_t*)dc.tstate.p;
     w.pv = (uint32_t*)dc.pv.p;
@@ -270,11 +272,9 @@ int prepare_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
 }
 
 int check_special_support(spl_tokenizer* tk, uint32_t flags, bool& with_special) {
+    // any set is served: where strings can contain or overlap one another the matches are those of aho-corasick's
+    // Standard non-overlapping find_iter (spl_special.h, k_resolve_specials)
     with_special = (flags & SPL_ENCODE_WITH_SPECIAL) && !tk->host.sp_id.empty();
-    if (with_special && !tk->host.specials_unambiguous) {
-        tk->err = "special-token set is ambiguous (one string contains or overlaps another); not supported on device";
-        return SPL_ERR_UNSUPPORTED;
-    }
     return SPL_OK;
 }
 
@@ -316,10 +316,12 @@ int enqueue_encode(spl_tokenizer* tk, DevCtx& dc, cudaStream_t st, const EncodeA
     const size_t off_tinfo = 256, off_hard = align_up(off_tinfo + (n_tiles + 2) * sizeof(SplTileInfo), 256);
     const size_t bm = align_up(words * 4, 256);
     const size_t off_spec = off_hard + bm, off_w0 = off_spec + (with_special ? bm : 0), off_a = off_w0 + bm, off_rs = off_a + bm;
-    if ((rc = dc.sp_zero.ensure(off_rs + bm, tk->err))) return rc;
+    const bool amb = with_special && !tk->host.specials_unambiguous;
+    const size_t off_cand = off_rs + bm, sp_total = off_cand + (amb ? bm : 0);
+    if ((rc = dc.sp_zero.ensure(sp_total, tk->err))) return rc;
     if ((rc = dc.sp_tiles.ensure((2 * n_tiles + 2) * 4, tk->err))) return rc;
     if ((rc = dc.sp_doc.ensure((a.n_docs + 1) * 8, tk->err))) return rc;
-    CUDA_TRY(cudaMemsetAsync(dc.sp_zero.p, 0, off_rs + bm, st), tk->err);
+    CUDA_TRY(cudaMemsetAsync(dc.sp_zero.p, 0, sp_total, st), tk->err);
     uint8_t* zb = (uint8_t*)dc.sp_zero.p;
     SplWork v;
     memset(&v, 0, sizeof(v));
@@ -328,6 +330,7 @@ int enqueue_encode(spl_tokenizer* tk, DevCtx& dc, cudaStream_t st, const EncodeA
     v.counters = (uint32_t*)zb; v.tinfo = (SplTileInfo*)(zb + off_tinfo);
     v.hard = (uint32_t*)(zb + off_hard); v.pstart = v.hard;            // the sentinel bit N is a hard bit as well
     v.spec = with_special ? (uint32_t*)(zb + off_spec) : nullptr;
+    v.cand = amb ? (uint32_t*)(zb + off_cand) : nullptr;
     v.T = dc.d_tables; v.pattern = tk->host.pattern; v.with_special = with_special;
     launches += spl_launch_mark(v, dc.num_sms, st);
     SplSpWork s;
@@ -526,9 +529,11 @@ const char* spl_last_error(const spl_tokenizer* tk) { return tk ? tk->err.c_str(
 int spl_launches_per_call(const spl_tokenizer* tk, uint32_t flags) {
     if (!tk) return 0;
     bool ws = (flags & SPL_ENCODE_WITH_SPECIAL) && !tk->host.sp_id.empty();
-    if (is_sentencepiece(tk)) return 12 + (ws ? 1 : 0);                // mark (T), 4 x scan, sp_emit, mark (T'), probe, bpe, bpe_long, bpe_fin (+ chunk scan), emit
+    int extra = 0;
+    if (ws && !tk->host.specials_unambiguous) ws = false, ++extra;      // + k_resolve_specials
+    if (is_sentencepiece(tk)) return 12 + (ws ? 1 : 0) + 2 * extra;                // mark (T), 4 x scan, sp_emit, mark (T'), probe, bpe, bpe_long, bpe_fin (+ chunk scan), emit
     int pre = tk->host.pattern == SPL_PAT_MISTRAL_V3 ? 1 : 2;          // sequential rules | bit-parallel + fallback
-    return 6 + pre + (ws ? 1 : 0);                                     // mark_docs, probe, bpe, bpe_long, bpe_fin (+ chunk scan), emit
+    return 6 + pre + (ws ? 1 : 0) + 2 * extra;                         // mark_docs, probe, bpe, bpe_long, bpe_fin (+ chunk scan), emit
 }
 
 int spl_set_profiling(spl_tokenizer* tk, int enable) {

@@ -11,6 +11,7 @@
 //
 // No block waits for another block inside a kernel; the miss lists decouple the rare, latency-bound merge loop from
 // the streaming probe so that both run at full occupancy.  Integer / byte work; no tensor cores.
+#include <algorithm>
 #include "spl_device.cuh"
 #include "spl_segment.h"
 #include "spl_bpe_bits.h"
@@ -1046,7 +1047,10 @@ __device__ void bpe_class(const SplWork& w, uint32_t c, uint32_t* reg, uint32_t 
         uint64_t* slot = &w.mlist[midx];
         const uint64_t e = *slot;
         const uint32_t gpos = (uint32_t)e, len = (uint32_t)(e >> 32) & SPL_ML_LEN_MASK;
-        if (w.dd_tab) valid = valid && !dedup_check<LG>(w, valid, midx, slot, gpos, len);
+        if (w.dd_tab) {                                               // (all 32 lanes: the check shuffles and votes)
+            const bool dup = dedup_check<LG>(w, valid, midx, slot, gpos, len);
+            valid = valid && !dup;
+        }
         if (!__any_sync(FULL, valid)) continue;
         uint32_t cnt;
         const bool allow_whole = !(e & SPL_ML_SEG);                   // a segment of a piece is not a piece: no whole-piece probe
@@ -1459,11 +1463,16 @@ void spl_launch_encode_stage(const SplWork& w, int num_sms, cudaStream_t stream,
     mark(ctx, "k_probe");
     // first length class merged by windowed rounds (measured crossover; SPL_BPE_WIN_CLS overrides it for experiments)
     static const uint32_t win_cls = [] { const char* e = getenv("SPL_BPE_WIN_CLS"); return e ? (uint32_t)atoi(e) : SPL_BPE_WIN_CLS; }();
-    k_bpe<<<(uint32_t)num_sms * 6u, SPL_BPE_THREADS, WK_SMEM_BYTES, stream>>>(w);
+    // persistent grids, but no larger than the text can feed: a small batch must not pay for launching (and draining)
+    // hundreds of idle blocks
+    const uint32_t g_bpe = std::min<uint32_t>((uint32_t)num_sms * 6u, std::max<uint32_t>(1u, w.N / 2048u));
+    const uint32_t g_long = std::min<uint32_t>((uint32_t)num_sms * 4u, std::max<uint32_t>(1u, w.N / 4096u));
+    const uint32_t g_fin = std::min<uint32_t>((uint32_t)num_sms, std::max<uint32_t>(1u, w.n_tiles / 8u));
+    k_bpe<<<g_bpe, SPL_BPE_THREADS, WK_SMEM_BYTES, stream>>>(w);
     mark(ctx, "k_bpe");
-    k_bpe_long<<<(uint32_t)num_sms * 4u, SPL_BPE_THREADS, BPE_SMEM_BYTES, stream>>>(w, win_cls);
+    k_bpe_long<<<g_long, SPL_BPE_THREADS, BPE_SMEM_BYTES, stream>>>(w, win_cls);
     mark(ctx, "k_bpe_long");
-    k_bpe_fin<<<(uint32_t)num_sms, SPL_BPE_THREADS, 0, stream>>>(w);                                // duplicates + the chunk scan, by its last block
+    k_bpe_fin<<<g_fin, SPL_BPE_THREADS, 0, stream>>>(w);                                            // duplicates + the chunk scan, by its last block
     mark(ctx, "k_bpe_fin");
     k_emit<<<w.n_tiles, SPL_THREADS, 0, stream>>>(w);
     mark(ctx, "k_emit");

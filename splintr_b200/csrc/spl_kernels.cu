@@ -9,10 +9,14 @@
 //
 // The second half (whole-piece probe, merge loop, ordered id output) is spl_encode.cu.
 // Integer / byte work, bounded by instruction issue and HBM traffic; no tensor cores.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include "spl_device.cuh"
 #include "spl_pretok.h"
 #include "spl_pretok_fast.h"
 #include "spl_fast_dev.cuh"
+#include "spl_special.h"
 
 // ------------------------------------------------------------------------------------------
 // k_mark_docs
@@ -35,8 +39,17 @@ __global__ void k_mark_docs(SplWork w) {
 }
 
 // ------------------------------------------------------------------------------------------
-// k_mark_specials: every occurrence of a special string that lies inside one document
+// k_mark_specials: every occurrence of a special string that lies inside one document.
+// Sets where no string contains or overlaps another (all bundled ones): every occurrence is a match, marked right here.
+// Other sets (w.cand != nullptr): occurrences compete (spl_special.h); this pass only records where one STARTS, and
+// k_resolve_specials walks every document from candidate to candidate.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mark_special_span(const SplWork& w, uint32_t i, uint32_t e) {
+    atomicOr(&w.hard[i >> 5], 1u << (i & 31));
+    atomicOr(&w.hard[e >> 5], 1u << (e & 31));
+    for (uint32_t j = i; j < e; ++j) atomicOr(&w.spec[j >> 5], 1u << (j & 31));
+}
+
 __global__ void k_mark_specials(SplWork w) {
     SPL_RETURN_IF_BAD_OFFSETS(w);
     const SplTables* T = w.T;
@@ -52,11 +65,30 @@ __global__ void k_mark_specials(SplWork w) {
                 if (w.text[i + j] != T->sp_bytes[o + j]) { eq = false; break; }
             if (!eq) continue;
             if (g_next_bit(w.hard, i + 1, i + len) < i + len) continue;     // would span two documents
-            atomicOr(&w.hard[i >> 5], 1u << (i & 31));
-            atomicOr(&w.hard[(i + len) >> 5], 1u << ((i + len) & 31));
-            for (uint32_t j = i; j < i + len; ++j) atomicOr(&w.spec[j >> 5], 1u << (j & 31));
+            if (w.cand) { atomicOr(&w.cand[i >> 5], 1u << (i & 31)); break; }
+            mark_special_span(w, i, i + len);
             break;
         }
+    }
+}
+
+struct GlobalByteText { const uint8_t* __restrict__ p; __device__ __forceinline__ uint8_t byte(uint32_t i) const { return __ldg(p + i); } };
+struct GlobalCand {
+    const uint32_t* __restrict__ bits;
+    __device__ __forceinline__ uint32_t next(uint32_t from, uint32_t lim) const { return g_next_bit(bits, from, lim); }
+};
+
+// one thread per document: the matches aho-corasick's Standard non-overlapping find_iter reports (tokenizer.rs:851)
+__global__ void k_resolve_specials(SplWork w) {
+    SPL_RETURN_IF_BAD_OFFSETS(w);
+    const SplTables* T = w.T;
+    const SplSpecialSet S{T->sp_bytes, T->sp_off, T->n_special};
+    const GlobalByteText t{w.text};
+    const GlobalCand c{w.cand};
+    for (uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; d < w.n_docs; d += gridDim.x * blockDim.x) {
+        const uint32_t d0 = (uint32_t)(w.doc_off[d] - w.off_base), d1 = (uint32_t)(w.doc_off[d + 1] - w.off_base);
+        if (g_next_bit(w.cand, d0, d1) >= d1) continue;
+        spl_special_walk(t, c, S, d0, d1, [&](uint32_t s, uint32_t e, uint32_t) { mark_special_span(w, s, e); });
     }
 }
 
@@ -260,6 +292,12 @@ void mark_cb(void* p, const char* name) {
     ++c->launches;
     SplKernelProfile* prof = c->prof;
     if (prof && prof->n < SPL_PROF_MAX) { prof->name[prof->n] = name; ++prof->n; cudaEventRecord(prof->ev[prof->n], c->stream); }
+    // SPL_SYNC_EACH=1 (debugging): wait for every kernel and name the one that faults
+    static const bool sync_each = [] { const char* e = getenv("SPL_SYNC_EACH"); return e && e[0] == '1'; }();
+    if (sync_each) {
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) fprintf(stderr, "[spl] kernel %s: %s\n", name, cudaGetErrorString(e));
+    }
 }
 }  // namespace
 
@@ -270,7 +308,9 @@ int spl_launch_mark(const SplWork& w, int num_sms, cudaStream_t stream) {
     uint32_t blocks = (w.N + 255) / 256;
     uint32_t cap = (uint32_t)num_sms * 16;
     k_mark_specials<<<blocks < cap ? blocks : cap, 256, 0, stream>>>(w);
-    return 2;
+    if (!w.cand) return 2;
+    k_resolve_specials<<<std::min<uint32_t>((w.n_docs + 127u) / 128u, cap), 128, 0, stream>>>(w);
+    return 3;
 }
 
 int spl_launch_encode(const SplWork& w, int num_sms, cudaStream_t stream, SplKernelProfile* prof) {
@@ -287,6 +327,10 @@ int spl_launch_encode(const SplWork& w, int num_sms, cudaStream_t stream, SplKer
         uint32_t cap = (uint32_t)num_sms * 16;
         k_mark_specials<<<blocks < cap ? blocks : cap, 256, 0, stream>>>(w);
         mark("k_mark_specials");
+        if (w.cand) {
+            k_resolve_specials<<<std::min<uint32_t>((w.n_docs + 127u) / 128u, cap), 128, 0, stream>>>(w);
+            mark("k_resolve_specials");
+        }
     }
     if (w.pretok_done) {
         // SentencePiece mode: k_sp_emit has written the piece starts of the transformed text

@@ -64,6 +64,7 @@ struct SplWork {
     uint32_t        n_tiles;     // N / SPL_TILE + 1
     uint32_t*       hard;        // bitmap words: segment boundaries (doc starts, special-span edges, N)
     uint32_t*       spec;        // bitmap words: bytes inside special-token spans (with_special only)
+    uint32_t*       cand;        // bitmap words: starts of special-string occurrences; only for sets whose strings can overlap (spl_special.h), else nullptr
     uint32_t*       pstart;      // bitmap words: piece starts (incl. sentinel bit N)
     size_t          bitmap_words;
     SplTileInfo*    tinfo;            // [n_tiles+1] per-tile record (zero-initialised)

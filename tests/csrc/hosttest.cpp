@@ -462,3 +462,31 @@ extern "C" int ht_bpe_window_m(const uint32_t* K, uint32_t n_pairs, uint32_t G, 
     for (uint32_t g = 0; g < G; ++g) m_out[g] = spl_window_peaks(m[g], fPK[g], cin[g], cin2[g], B);
     return passes;
 }
+
+// ---------------------------------------------------------------------------------------
+// Special-token matches for arbitrary (overlapping) sets: spl_special.h, the walker k_resolve_specials runs per document.
+#include "../../splintr_b200/csrc/spl_special.h"
+
+struct HostByteText { const uint8_t* p; uint8_t byte(uint32_t i) const { return p[i]; } };
+struct HostCand {
+    const std::vector<uint8_t>* c;
+    uint32_t next(uint32_t from, uint32_t lim) const { while (from < lim && !(*c)[from]) ++from; return from < lim ? from : lim; }
+};
+
+// strs: n strings concatenated with offsets off[n + 1]; out: triples (start, end, k); returns the number of matches
+extern "C" long ht_special_walk(const uint8_t* text, uint32_t n_text, const uint8_t* strs, const uint32_t* off, uint32_t n,
+                                uint32_t* out, size_t cap) {
+    SplSpecialSet S{strs, off, n};
+    HostByteText t{text};
+    std::vector<uint8_t> cand(n_text + 1, 0);
+    for (uint32_t i = 0; i < n_text; ++i)                       // the parallel pass: where does any special string occur?
+        for (uint32_t k = 0; k < n; ++k)
+            if (spl_special_match(t, S, k, i, n_text)) { cand[i] = 1; break; }
+    HostCand c{&cand};
+    size_t m = 0;
+    spl_special_walk(t, c, S, 0, n_text, [&](uint32_t s, uint32_t e, uint32_t k) {
+        if (m + 3 <= cap) { out[m] = s; out[m + 1] = e; out[m + 2] = k; }
+        m += 3;
+    });
+    return (long)(m / 3);
+}

@@ -9,7 +9,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = [os.path.join(ROOT, "tests", "csrc", "hosttest.cpp"), os.path.join(ROOT, "splintr_b200", "csrc", "spl_host.cpp")]
-DEPS = SRC + [os.path.join(ROOT, "splintr_b200", "csrc", f) for f in ("spl_pretok.h", "spl_pretok_fast.h", "spl_sentencepiece.h", "spl_ingest.h", "spl_bpe_bits.h", "spl_segment.h", "spl_common.h", "spl_host.h", "unicode_tables.inc")]
+DEPS = SRC + [os.path.join(ROOT, "splintr_b200", "csrc", f) for f in ("spl_pretok.h", "spl_pretok_fast.h", "spl_sentencepiece.h", "spl_ingest.h", "spl_bpe_bits.h", "spl_segment.h", "spl_special.h", "spl_common.h", "spl_host.h", "unicode_tables.inc")]
 LIB = os.path.join(ROOT, "tests", "csrc", "libhosttest.so")
 _lib = None
 
@@ -42,6 +42,8 @@ def load():
     lib.ht_encode_piece.argtypes = [vp, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_int, vp, ctypes.c_size_t]
     lib.ht_seg_counters.argtypes = [vp, ctypes.c_int]
     lib.ht_set_tile_limit.argtypes = [ctypes.c_uint32]
+    lib.ht_special_walk.restype = ctypes.c_long
+    lib.ht_special_walk.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, vp, ctypes.c_uint32, vp, ctypes.c_size_t]
     lib.ht_jsonl.restype = ctypes.c_int
     lib.ht_jsonl.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, vp, vp, vp]
     lib.ht_set_fast_ext.argtypes = [ctypes.c_int]
@@ -53,6 +55,16 @@ def load():
     lib.ht_bpe_window_m.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, vp]
     _lib = lib
     return lib
+
+
+def special_walk(text: bytes, specials):
+    """spl_special.h over one document: [(start, end, index into specials)] as aho-corasick's Standard non-overlapping
+    find_iter reports them."""
+    strs = b"".join(specials)
+    off = np.cumsum([0] + [len(x) for x in specials]).astype(np.uint32)
+    out = np.zeros(3 * (len(text) + 1), dtype=np.uint32)
+    n = load().ht_special_walk(text, len(text), strs, off.ctypes.data, len(specials), out.ctypes.data, len(out))
+    return [(int(out[3 * i]), int(out[3 * i + 1]), int(out[3 * i + 2])) for i in range(n)]
 
 
 def set_tile_limit(limit: int = 0xFFFFFFFF):

@@ -95,6 +95,36 @@ def test_special_tokens(toks, name):
     assert t.decode(t.encode_with_special("a" + sp[0] + "b")) == "a" + sp[0] + "b"
 
 
+def test_special_tokens_user_sets_that_overlap():
+    """Tokenizer(vocab, pattern, special_tokens) takes ANY dict (bindings.rs:70-83; the Aho-Corasick automaton of
+    tokenizer.rs:429-434 is built from it).  Strings that contain or overlap one another: the matches are those of
+    MatchKind::Standard non-overlapping find_iter -- earliest end first, ties to the longest (k_resolve_specials,
+    spl_special.h) -- checked against the oracle, through the batch call and in SentencePiece mode."""
+    from splintr_b200 import Tokenizer, presets as P
+    from oracle.py_oracle import OracleTokenizer
+    rng = random.Random(5)
+    sets = [{"<a>": 200001, "<a><b>": 200002, "<b>": 200003, "b><": 200004},
+            {"<|end|>": 200001, "<|endoftext|>": 200002, "|><|": 200003, "<|": 200004},
+            {"aa": 200001, "aaa": 200002, "ab": 200003}]
+    for name in ("cl100k_base", "mistral_v2"):
+        p = P.PRESETS[name]
+        vb = P.load_vocab_bytes(p.vocab_file)
+        for sp in sets:
+            if p.sentencepiece:
+                t = Tokenizer.from_bytes_sentencepiece(vb, p.pattern, sp)
+            else:
+                t = Tokenizer.from_bytes(vb, p.pattern, sp)
+            o = OracleTokenizer.from_bytes(vb, p.pattern, sp, p.byte_level, p.sentencepiece)
+            alpha = "".join(sp) + " xy\n"
+            texts = ["", "<a><b>", "x<a><b><a>", "aaaaa aaaa aaa aa a"] + list(sp)
+            texts += ["".join(rng.choice(alpha) for _ in range(rng.randint(0, 80))) for _ in range(400)]
+            texts += [" ".join(rng.choice(list(sp) + ["hello", "world", "<", "|", ">"]) for _ in range(rng.randint(1, 30))) for _ in range(200)]
+            got = t.encode_batch_with_special(texts)
+            for x, g in zip(texts, got):
+                assert g == o.encode_with_special(x), (name, sp, x)
+            assert t.encode_batch(texts[:50]) == [o.encode(x) for x in texts[:50]]
+
+
 @pytest.mark.parametrize("name", ["cl100k_base", "o200k_base"])
 def test_batch_equals_individual_and_roundtrip(toks, name):
     """tests/cl100k.rs:191-214 and python/tests/test_cl100k.py:545-570 (700-text batch)."""
