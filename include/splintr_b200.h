@@ -130,7 +130,8 @@ int spl_device_status(spl_tokenizer* tok, int dev_index, void* cuda_stream, uint
 
 /* Diagnostics: the 32 device counters of the last pass on device `dev_index` (synchronises `cuda_stream`):
  * [1] error flags, [4] tiles the bit-parallel pre-tokenizer handed to the sequential rules, [5] long pieces that repeated
- * an earlier one (their merge loop was skipped), [6] tiles that went through the refining pass of the probe,
+ * an earlier one (their merge loop was skipped), [6] tiles that went through the refining pass of the probe, [7] single
+ * characters of two or three ids that the probe settled from its table,
  * [8 .. 15] pieces filed for the merge loop by length class. */
 int spl_debug_counters(spl_tokenizer* tok, int dev_index, void* cuda_stream, uint32_t* out32);
 

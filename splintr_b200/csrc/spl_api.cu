@@ -121,6 +121,7 @@ int upload_tables(spl_tokenizer* tk, DevCtx& dc) {
     size_t i_irr = add(h.seg_irr.data(), h.seg_irr.size() * 4);
     size_t i_h2 = add(h.seg_h2.data(), h.seg_h2.size() * 4);
     size_t i_ctok = add(h.char_tok.data(), h.char_tok.size() * 4);
+    size_t i_cids = add(h.char_ids.data(), h.char_ids.size() * 4);
     size_t i_decb = add(h.dec_bytes.data(), h.dec_bytes.size());
     size_t i_deco = add(h.dec_off.data(), h.dec_off.size() * 4);
     size_t i_spb = add(h.sp_bytes.data(), h.sp_bytes.size());
@@ -147,6 +148,7 @@ int upload_tables(spl_tokenizer* tk, DevCtx& dc) {
     t.seg_irr = (const uint32_t*)(base + parts[i_irr].off);
     t.seg_h2 = (const uint32_t*)(base + parts[i_h2].off); t.seg_h2_log2 = h.seg_h2_log2;
     t.char_tok = (const uint32_t*)(base + parts[i_ctok].off);
+    t.char_ids = (const uint32_t*)(base + parts[i_cids].off);
     memcpy(t.byte_sym, h.byte_sym, sizeof(t.byte_sym));
     t.dec_bytes = base + parts[i_decb].off;
     t.dec_off = (const uint32_t*)(base + parts[i_deco].off);

@@ -132,7 +132,8 @@ struct SplTables {
     // independent segments (spl_segment.h)
     const uint32_t* seg_irr;       // [2048] words
     const uint32_t* seg_h2;  uint32_t seg_h2_log2;   // hashed bitmap, 2^seg_h2_log2 bits
-    const uint32_t* char_tok;      // [65536] merge-loop result of the UTF-8 bytes of code point c if that is ONE id, else SPL_RANK_NONE
+    const uint32_t* char_tok;      // [65536] what the merge loop makes of the UTF-8 bytes of code point c (SPL_CHAR_* in spl_segment.h)
+    const uint32_t* char_ids;      // the id lists of the characters that are two or three ids
     // decode: id -> bytes
     const uint8_t*  dec_bytes;
     const uint32_t* dec_off;       // [n_dec + 1]

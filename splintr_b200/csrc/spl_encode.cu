@@ -366,17 +366,23 @@ __device__ __forceinline__ void probe_tile_refine(const SplWork& w, SplProbeScra
     }
     __syncthreads();
     const uint32_t P = build_piece_list(w, sm, pb, tile, true);
-    int32_t dropped = 0;
+    // 2a: settle what can be settled; count the misses of the block per length class (shared counters: the global
+    // class counters are ONE address each for the whole grid -- one atomic per warp was 48 per tile and the kernel's
+    // whole cost on CJK text).  "Class" SPL_NCLS: characters that are two or three ids (char_tok): settled here too,
+    // but more than one id needs a miss-list entry and room in the pool.
+    uint32_t* s_cnt = sm.cls_cnt;                                     // [SPL_NCLS + 1] block counts, then global bases
+    if (tid <= SPL_NCLS) s_cnt[tid] = 0u;
+    __syncthreads();
+    int32_t extra = 0;                                                // ids minus pieces of what this thread settles
     for (uint32_t j0 = 0; j0 < P; j0 += SPL_THREADS) {
         const uint32_t j = j0 + tid;
-        uint32_t cls = 0, gpos = 0, len = 0;                     // cls: 0 settled, else 1 + length class of the miss
-        bool seg = false;
+        uint32_t cls = 0, s = 0;                                      // cls: 0 settled, else 1 + class of the entry to file
         if (j < P) {
-            const uint32_t s = sm.plist[j];
+            s = sm.plist[j];
             uint32_t e = sm.plist[j + 1];
             if (e == 0xFFFFu) e = sm.last_end;
-            len = e - s; gpos = tile0 + s;
-            seg = ((sm.segw[s >> 5] | sm.mstw[s >> 5]) >> (s & 31u)) & 1u;
+            const uint32_t len = e - s;
+            const bool seg = ((sm.segw[s >> 5] | sm.mstw[s >> 5]) >> (s & 31u)) & 1u;
             uint32_t val;
             if (!seg) {
                 val = val_at[s];
@@ -385,40 +391,77 @@ __device__ __forceinline__ void probe_tile_refine(const SplWork& w, SplProbeScra
                 val = sy < SPL_UNK_BASE ? sy : SPL_PV_NONE;
             } else {
                 val = PV_MISSMARK;
-                if (len <= 3) {                                   // one 2- or 3-byte character?
+                if (len <= 3) {                                       // one 2- or 3-byte character?
                     const SmemPieceReader rd{text, s};
                     uint32_t packed = 0;
                     if (spl_u8_char(rd.load4(0), len, packed) == len) {
-                        const uint32_t id = __ldg(T->char_tok + spl_u8_cp23(packed, len));
-                        if (id != SPL_RANK_NONE) val = id;
+                        const uint32_t ct = __ldg(T->char_tok + spl_u8_cp23(packed, len));
+                        if (ct != SPL_RANK_NONE) {
+                            if ((ct >> SPL_CHAR_COUNT_SHIFT) == 0u) val = ct;             // one id
+                            else cls = 1u + SPL_NCLS;                                     // two or three: 2b writes them
+                        }
                     }
                 }
             }
-            if (val == PV_MISSMARK) cls = 1u + spl_len_class(len);
-            else {
-                w.pv[pvbase + j] = val;
-                if (val == SPL_PV_NONE) ++dropped;
+            if (cls == 0u) {
+                if (val == PV_MISSMARK) cls = 1u + spl_len_class(len);
+                else {
+                    w.pv[pvbase + j] = val;
+                    if (val == SPL_PV_NONE) --extra;
+                    val_at[s] = 0xFFFFFFFFu;                          // settled (2b files what is not)
+                }
             }
         }
-        // misses: one atomic per warp and class
         if (__any_sync(FULL, cls != 0u)) {
-            for (uint32_t c = 0; c < SPL_NCLS; ++c) {
+            for (uint32_t c = 0; c <= SPL_NCLS; ++c) {
                 const uint32_t bal = __ballot_sync(FULL, cls == c + 1u);
                 if (!bal) continue;
                 const uint32_t leader = __ffs(bal) - 1;
                 uint32_t b0 = 0;
-                if (lane == leader) b0 = atomicAdd(&w.counters[SPL_CTR_CLS + c], (uint32_t)__popc(bal));
+                if (lane == leader) b0 = atomicAdd(&s_cnt[c], (uint32_t)__popc(bal));
                 b0 = __shfl_sync(FULL, b0, leader);
-                if (cls == c + 1u) {
-                    const uint32_t midx = w.ml_base[c] + b0 + __popc(bal & lt_mask);
-                    w.mlist[midx] = ml_entry(gpos, len) | (seg ? SPL_ML_SEG : 0ull);
-                    w.pv[pvbase + j] = SPL_PV_MISS | midx;
-                }
+                if (cls == c + 1u) val_at[s] = (c << 16) | (b0 + __popc(bal & lt_mask));       // class | index within the block
             }
         }
     }
-    dropped = __reduce_add_sync(FULL, dropped);
-    if (lane == 0 && dropped) { atomicAdd(&w.tinfo[tile].extra, -dropped); atomicAdd(&w.chunk_cnt[tile / SPL_CHUNK_TILES], -dropped); }
+    __syncthreads();
+    if (tid <= SPL_NCLS) {
+        const uint32_t nb = s_cnt[tid];
+        s_cnt[tid] = nb ? atomicAdd(&w.counters[tid < SPL_NCLS ? SPL_CTR_CLS + tid : SPL_CTR_FINAL], nb) : 0u;
+    }
+    __syncthreads();
+    // 2b: file the entries
+    for (uint32_t j = tid; j < P; j += SPL_THREADS) {
+        const uint32_t s = sm.plist[j];
+        const uint32_t code = val_at[s];
+        if (code == 0xFFFFFFFFu) continue;
+        uint32_t e = sm.plist[j + 1];
+        if (e == 0xFFFFu) e = sm.last_end;
+        const uint32_t c = code >> 16, gpos = tile0 + s;
+        if (c < SPL_NCLS) {
+            const bool seg = ((sm.segw[s >> 5] | sm.mstw[s >> 5]) >> (s & 31u)) & 1u;
+            const uint32_t midx = w.ml_base[c] + s_cnt[c] + (code & 0xFFFFu);
+            w.mlist[midx] = ml_entry(gpos, e - s) | (seg ? SPL_ML_SEG : 0ull);
+            w.pv[pvbase + j] = SPL_PV_MISS | midx;
+        } else {
+            // a character of two or three ids: ids to the pool, a settled entry from the top of class 0's region down
+            // (pending and settled entries of the region are disjoint pieces of two bytes or more: they fit together)
+            const SmemPieceReader rd{text, s};
+            uint32_t packed = 0;
+            const uint32_t len = e - s;
+            spl_u8_char(rd.load4(0), len, packed);
+            const uint32_t ct = __ldg(T->char_tok + spl_u8_cp23(packed, len));
+            const uint32_t n_ids = (ct >> SPL_CHAR_COUNT_SHIFT) + 1u;
+            const uint32_t* __restrict__ src = T->char_ids + (ct & SPL_CHAR_VALUE_MASK);
+            for (uint32_t q = 0; q < n_ids; ++q) w.pool[gpos + q] = __ldg(src + q);
+            const uint32_t midx = w.ml_base[1] - 1u - (s_cnt[SPL_NCLS] + (code & 0xFFFFu));
+            w.mlist[midx] = (uint64_t)gpos | ((uint64_t)n_ids << 32) | SPL_ML_DONE | SPL_ML_SEG;
+            w.pv[pvbase + j] = SPL_PV_MISS | midx;
+            extra += (int32_t)n_ids - 1;
+        }
+    }
+    extra = __reduce_add_sync(FULL, extra);
+    if (lane == 0 && extra) { atomicAdd(&w.tinfo[tile].extra, extra); atomicAdd(&w.chunk_cnt[tile / SPL_CHUNK_TILES], extra); }
 }
 
 struct __align__(16) ProbeSmem {
@@ -545,6 +588,24 @@ __device__ uint32_t lookupL_serial_g(const SplTables* T, const uint8_t* __restri
         }
         h = (h + 1) & mask;
     }
+}
+
+// The same for the pieces of a whole warp (ALL 32 lanes call this; has: the lane has a finished piece).  Pieces of one
+// warp task are neighbours in the text, so their id-count corrections go to the same tile and the same chunk: lanes
+// with the same tile add up first and ONE atomic goes out -- with millions of short segments (CJK text) per-piece
+// atomics on a few hundred chunk counters were the whole cost of the kernel.
+__device__ __forceinline__ void bpe_finish_warp(const SplWork& w, const bool has, uint64_t* slot, uint32_t gpos, uint32_t cnt) {
+    const uint32_t lane = threadIdx.x & 31u;
+    if (has) *slot = (uint64_t)gpos | ((uint64_t)cnt << 32) | SPL_ML_DONE;
+    const int32_t delta = has ? (int32_t)cnt - 1 : 0;
+    const uint32_t tile = has ? gpos / SPL_TILE : 0xFFFFFFFFu;
+    const uint32_t peers = __match_any_sync(FULL, tile);
+    const int32_t tsum = __reduce_add_sync(peers, delta);
+    if (has && lane == (uint32_t)__ffs(peers) - 1u && tsum) atomicAdd(&w.tinfo[tile].extra, tsum);
+    const uint32_t chunk = has ? tile / SPL_CHUNK_TILES : 0xFFFFFFFFu;
+    const uint32_t cpeers = __match_any_sync(FULL, chunk);
+    const int32_t csum = __reduce_add_sync(cpeers, delta);
+    if (has && lane == (uint32_t)__ffs(cpeers) - 1u && csum) atomicAdd(&w.chunk_cnt[chunk], csum);
 }
 
 __device__ __forceinline__ void bpe_finish(const SplWork& w, uint64_t* slot, uint32_t gpos, uint32_t cnt) {
@@ -952,13 +1013,15 @@ __global__ void __launch_bounds__(SPL_BPE_THREADS, 6) k_bpe(SplWork w) {
         const uint32_t tasks = (n + per - 1u) / per;
         for (uint32_t t = gwarp; t < tasks; t += nwarps) {
             const uint32_t pi = t * per + lane;
-            if (lane < per && pi < n) {
-                uint64_t* slot = &w.mlist[w.ml_base[c] + pi];
+            const bool has = lane < per && pi < n;
+            uint64_t* slot = &w.mlist[w.ml_base[c] + (has ? pi : 0u)];
+            uint32_t gpos = 0, cnt = 0;
+            if (has) {
                 const uint64_t e = *slot;
-                const uint32_t gpos = (uint32_t)e, len = (uint32_t)(e >> 32) & SPL_ML_LEN_MASK;
-                const uint32_t cnt = bpe_lane(T, w.text, n_up, Krow, Srow, gpos, len, w.pool + gpos);
-                bpe_finish(w, slot, gpos, cnt);
+                gpos = (uint32_t)e;
+                cnt = bpe_lane(T, w.text, n_up, Krow, Srow, gpos, (uint32_t)(e >> 32) & SPL_ML_LEN_MASK, w.pool + gpos);
             }
+            bpe_finish_warp(w, has, slot, gpos, cnt);
         }
     }
 }
@@ -1056,7 +1119,7 @@ __device__ void bpe_class(const SplWork& w, uint32_t c, uint32_t* reg, uint32_t 
         const bool allow_whole = !(e & SPL_ML_SEG);                   // a segment of a piece is not a piece: no whole-piece probe
         if constexpr (WINDOWED) cnt = bpe_group<LG>(reg, valid, allow_whole, w.T, w.text + gpos, len, w.pool + gpos);
         else cnt = bpe_seq<LG>(reg, valid, allow_whole, w.T, w.text + gpos, len, w.pool + gpos);
-        if (valid && (lane & ((1u << LG) - 1u)) == 0) bpe_finish(w, slot, gpos, cnt);
+        bpe_finish_warp(w, valid && (lane & ((1u << LG) - 1u)) == 0, slot, gpos, cnt);
         __syncwarp();
     }
 }
@@ -1248,19 +1311,26 @@ __global__ void __launch_bounds__(SPL_BPE_THREADS) k_bpe_fin(SplWork w) {
         const uint32_t lo = w.ml_base[2], hi = w.ml_base[SPL_NCLS - 1];           // the classes dedup_check looks at
         for (uint32_t c = 2; c < SPL_NCLS - 1; ++c) {
             const uint32_t n = w.counters[SPL_CTR_CLS + c];
-            for (uint32_t i = blockIdx.x * SPL_BPE_THREADS + tid; i < n; i += gridDim.x * SPL_BPE_THREADS) {
-                const uint32_t midx = w.ml_base[c] + i;
+            const uint32_t n_round = (n + SPL_BPE_THREADS - 1u) / SPL_BPE_THREADS * SPL_BPE_THREADS;     // whole warps enter the vote
+            for (uint32_t i = blockIdx.x * SPL_BPE_THREADS + tid; i < n_round; i += gridDim.x * SPL_BPE_THREADS) {
+                const uint32_t midx = w.ml_base[c] + (i < n ? i : 0u);
                 const uint64_t e = w.mlist[midx];
-                if (!(e & SPL_ML_DUP)) continue;
-                const uint32_t rep = w.dup_of[midx - lo];
-                if (rep < lo || rep >= hi) continue;                            // (cannot happen)
+                bool dup = i < n && (e & SPL_ML_DUP);
+                uint32_t rep = dup ? w.dup_of[midx - lo] : lo;
+                if (rep < lo || rep >= hi) { dup = false; rep = lo; }            // (cannot happen)
                 const uint64_t re = w.mlist[rep];
                 const uint32_t cnt = (uint32_t)(re >> 32) & SPL_ML_LEN_MASK, gpos = (uint32_t)e;
-                w.mlist[midx] = (uint64_t)(uint32_t)re | ((uint64_t)cnt << 32) | SPL_ML_DONE;
-                if (cnt != 1u) {
-                    atomicAdd(&w.tinfo[gpos / SPL_TILE].extra, (int32_t)cnt - 1);
-                    atomicAdd(&w.chunk_cnt[gpos / (SPL_TILE * SPL_CHUNK_TILES)], (int32_t)cnt - 1);
-                }
+                // the ids stay where the earlier piece put them; only the count is added to this piece's own tile
+                if (dup) w.mlist[midx] = (uint64_t)(uint32_t)re | ((uint64_t)cnt << 32) | SPL_ML_DONE;
+                const int32_t delta = dup ? (int32_t)cnt - 1 : 0;
+                const uint32_t tile = dup ? gpos / SPL_TILE : 0xFFFFFFFFu;
+                const uint32_t peers = __match_any_sync(FULL, tile);
+                const int32_t tsum = __reduce_add_sync(peers, delta);
+                if (dup && (tid & 31u) == (uint32_t)__ffs(peers) - 1u && tsum) atomicAdd(&w.tinfo[tile].extra, tsum);
+                const uint32_t chunk = dup ? tile / SPL_CHUNK_TILES : 0xFFFFFFFFu;
+                const uint32_t cpeers = __match_any_sync(FULL, chunk);
+                const int32_t csum = __reduce_add_sync(cpeers, delta);
+                if (dup && (tid & 31u) == (uint32_t)__ffs(cpeers) - 1u && csum) atomicAdd(&w.chunk_cnt[chunk], csum);
             }
         }
     }

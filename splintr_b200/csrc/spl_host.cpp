@@ -491,21 +491,28 @@ bool spl_build_tables(SplHostTables& t, const uint8_t* vocab, size_t vocab_len, 
             const uint32_t hb = spl_seg_hash(ab.first, ab.second, lg);
             t.seg_h2[hb >> 5] |= 1u << (hb & 31);
         }
-        // what the merge loop makes of a single 2- or 3-byte character
+        // what the merge loop makes of a single 2- or 3-byte character: one id in place, two or three ids in char_ids
+        // (SPL_CHAR_* in spl_segment.h); characters with a byte the vocabulary does not know stay with the merge loop
         t.char_tok.assign(65536, SPL_RANK_NONE);
+        t.char_ids.clear();
         std::vector<uint32_t> ids;
         for (uint32_t cp = 0x80; cp < 0x10000; ++cp) {
             uint8_t u[3];
             uint32_t L;
             if (cp < 0x800) { u[0] = (uint8_t)(0xC0 | (cp >> 6)); u[1] = (uint8_t)(0x80 | (cp & 0x3F)); L = 2; }
             else { u[0] = (uint8_t)(0xE0 | (cp >> 12)); u[1] = (uint8_t)(0x80 | ((cp >> 6) & 0x3F)); u[2] = (uint8_t)(0x80 | (cp & 0x3F)); L = 3; }
-            ids.clear();
-            spl_host_merge_loop(t, u, L, ids);
-            // one id, and none of the bytes dropped as unknown (bpe.rs:187-191 drops them one by one: keep that to the loop)
             bool known = true;
             for (uint32_t q = 0; q < L; ++q) known &= t.byte_sym[u[q]] < SPL_UNK_BASE;
-            if (ids.size() == 1 && known) t.char_tok[cp] = ids[0];
+            if (!known) continue;                 // bpe.rs:187-191 drops unknown bytes one by one: leave that to the loop
+            ids.clear();
+            spl_host_merge_loop(t, u, L, ids);
+            if (ids.size() == 1) t.char_tok[cp] = ids[0];
+            else if (ids.size() == L || ids.size() == 2) {
+                t.char_tok[cp] = ((uint32_t)(ids.size() - 1) << SPL_CHAR_COUNT_SHIFT) | (uint32_t)t.char_ids.size();
+                t.char_ids.insert(t.char_ids.end(), ids.begin(), ids.end());
+            }
         }
+        t.char_ids.resize(t.char_ids.size() + 4, 0);
     }
 
     // ---- special tokens -----------------------------------------------------------------------

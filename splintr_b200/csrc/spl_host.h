@@ -27,7 +27,7 @@ struct SplHostTables {
     uint32_t n_ids = 0, max_key_len = 0;
     std::vector<uint32_t> pair; uint32_t pair_log2 = 0; size_t n_pairs = 0;      // buckets of SPL_PAIR_WORDS words
     std::vector<uint32_t> bpair;                                                  // [65536] dense byte x byte corner of it
-    std::vector<uint32_t> seg_irr, seg_h2, char_tok;  uint32_t seg_h2_log2 = 16; size_t seg_pairs = 0;   // spl_segment.h
+    std::vector<uint32_t> seg_irr, seg_h2, char_tok, char_ids;  uint32_t seg_h2_log2 = 16; size_t seg_pairs = 0;   // spl_segment.h
     size_t t8_displaced = 0, pair_displaced = 0;         // keys that are not in their home bucket
     uint32_t byte_sym[256];
     // decode (tokenizer.rs:877-897): id -> bytes for every vocabulary id (byte-level keys translated back to raw

@@ -99,6 +99,7 @@ struct SplWork {
 enum : uint32_t { SPL_CTR_ERR = 1, SPL_CTR_HUGE_POOL = 2 /* 64 bit: words 2 and 3 */, SPL_CTR_FB = 4,
                   SPL_CTR_DUP = 5,            // long pieces that were duplicates of an earlier one
                   SPL_CTR_REFINED = 6,        // tiles that went through k_probe's refining pass
+                  SPL_CTR_FINAL = 7,          // entries k_probe filed already settled (characters of two or three ids): from the top of class 0's region down
                   SPL_CTR_CLS = 8,            // [8 .. 8 + SPL_NCLS): entries in the miss list of each class
                   SPL_CTR_TICKET = 16,        // blocks of k_bpe_fin that are done (the last one scans the chunk totals)
                   SPL_CTR_WORDS = 32 };
@@ -193,4 +194,5 @@ struct SplProbeScratch {
     uint32_t segw[SPL_TILE / 32];             // refining pass: safe boundaries found inside missed pieces (new piece starts)
     uint32_t mstw[SPL_TILE / 32];             // refining pass: starts of the pieces the whole-piece probe missed
     uint32_t n_hi;                            // bytes >= 0x80 in the tile (decides whether the tile is refined)
+    uint32_t cls_cnt[SPL_NCLS + 1];           // refining pass: misses of the block per length class (+ settled multi-id characters), then list bases
 };

@@ -67,6 +67,11 @@ SPL_HD bool spl_boundary_safe(const uint32_t* irr, const uint32_t* h2, uint32_t 
 
 #define SPL_SEG_MAX 32u            // the per-lane merge loop (k_bpe) holds a piece or segment of up to this many bytes
 
+// char_tok[code point]: SPL_RANK_NONE = ask the merge loop; else bits 30-31 = id count - 1; one id: the id itself in the
+// low bits; two or three ids: index of the first one in char_ids
+#define SPL_CHAR_COUNT_SHIFT 30u
+#define SPL_CHAR_VALUE_MASK  0x3FFFFFFFu
+
 // code point of a well-formed 2- or 3-byte character (index into the single-character table)
 SPL_HD uint32_t spl_u8_cp23(uint32_t packed, uint32_t L) {
     const uint32_t b0 = packed & 0xFFu, b1 = (packed >> 8) & 0x3Fu, b2 = (packed >> 16) & 0x3Fu;

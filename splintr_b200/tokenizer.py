@@ -338,7 +338,7 @@ class Tokenizer:
             rc = _lib.load().spl_debug_counters(self._handle, dev_index, ctypes.c_void_p(stream), out)
         if rc != _lib.SPL_OK:
             raise RuntimeError(f"splintr_b200: spl_debug_counters failed (code {rc})")
-        return {"error_flags": out[1], "fallback_tiles": out[4], "duplicates": out[5], "refined_tiles": out[6],
+        return {"error_flags": out[1], "fallback_tiles": out[4], "duplicates": out[5], "refined_tiles": out[6], "settled_multi_id_chars": out[7],
                 "misses_by_class": [out[8 + c] for c in range(8)]}
 
     # -- ingestion: JSON Lines -> packed text + offsets on the device ---------------

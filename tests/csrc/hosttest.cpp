@@ -110,7 +110,9 @@ static void ht_bpe_piece(const SplHostTables& T, const uint8_t* p, uint32_t n, s
             const uint32_t sy = T.byte_sym[p[pos]];
             if (sy < SPL_UNK_BASE) out.push_back(sy);
         } else if (la == sl && sl <= 3 && T.char_tok[spl_u8_cp23(packed, sl)] != SPL_RANK_NONE) {
-            out.push_back(T.char_tok[spl_u8_cp23(packed, sl)]);
+            const uint32_t v = T.char_tok[spl_u8_cp23(packed, sl)], cnt = (v >> SPL_CHAR_COUNT_SHIFT) + 1;
+            if (cnt == 1) out.push_back(v & SPL_CHAR_VALUE_MASK);
+            else for (uint32_t q = 0; q < cnt; ++q) out.push_back(T.char_ids[(v & SPL_CHAR_VALUE_MASK) + q]);
             ++ht_seg_stats[1];
         } else {
             spl_host_merge_loop(T, p + pos, sl, out);

@@ -26,7 +26,7 @@ for k in sorted(hist):
     h = hist[k]
     print(f"== {k}: {sum(h.values())} instructions")
     print("   " + ", ".join(f"{op} {n}" for op, n in h.most_common(14)))
-    seen = collections.Counter(x.split(" ", 1)[1].split(" ")[0] for x in feat[k])
+    seen = collections.Counter(re.sub(r"^@!?U?P\d+ ", "", x.split(" ", 1)[1]).split(" ")[0] for x in feat[k])
     print("   features: " + (", ".join(f"{op} x{n}" for op, n in seen.items()) or "-"))
     for x in feat[k][:12]:
         print("      " + x)
