@@ -100,7 +100,7 @@ __device__ __forceinline__ uint64_t ml_entry(uint32_t gpos, uint32_t len) {
 // sm.plist[P] = end of the last piece (0xFFFF: beyond the staged bits, see sm.last_end).  All threads of the block call
 // this (two barriers inside).  publish: record P for k_emit and add it to the chunk total.
 __device__ __forceinline__ uint32_t build_piece_list(const SplWork& w, SplProbeScratch& sm, const uint32_t* pb, const uint32_t tile,
-                                                     const bool publish) {
+                                                     const bool publish, const uint32_t my_hi = 0u, uint32_t* n_hi = nullptr) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t N = w.N, tile0 = tile * SPL_TILE;
     const uint32_t avail = N - tile0;                          // text bytes from tile0 on
@@ -113,14 +113,20 @@ __device__ __forceinline__ uint32_t build_piece_list(const SplWork& w, SplProbeS
         if (lane >= (uint32_t)o) incl += t;
     }
     if (lane == 31) sm.wtot[warp] = incl;
+    if (n_hi) {                                                // (block-uniform) bytes >= 0x80 of the tile, summed alongside
+        const uint32_t h = __reduce_add_sync(FULL, my_hi);
+        if (lane == 0) sm.whi[warp] = h;
+    }
     __syncthreads();
-    uint32_t base = incl - cnt, P = 0;
+    uint32_t base = incl - cnt, P = 0, H = 0;
 #pragma unroll
     for (uint32_t q = 0; q < PROBE_WARPS; ++q) {
         uint32_t t = sm.wtot[q];
         base += (q < warp) ? t : 0u;
         P += t;
+        if (n_hi) H += sm.whi[q];
     }
+    if (n_hi) *n_hi = H;
     while (my) {
         uint32_t b = __ffs(my) - 1;
         my &= my - 1;
@@ -143,7 +149,7 @@ __device__ __forceinline__ uint32_t build_piece_list(const SplWork& w, SplProbeS
 }
 
 __device__ __forceinline__ void probe_tile(const SplWork& w, SplProbeScratch& sm, const uint32_t* text, const uint32_t* pb,
-                                           const uint32_t tile) {
+                                           const uint32_t tile, const uint32_t P) {
     const SplTables* T = w.T;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -152,9 +158,11 @@ __device__ __forceinline__ void probe_tile(const SplWork& w, SplProbeScratch& sm
     const SplKey8* __restrict__ t8 = T->t8;
     const uint32_t t8_log2 = T->t8_log2;
 
-    // (sm.spw, the special-span bits of the tile, is filled by the caller together with text and pb)
-    const uint32_t P = build_piece_list(w, sm, pb, tile, true);
-
+    // (sm.spw, the special-span bits of the tile, is filled by the caller together with text and pb; so is the piece list)
+    if (tid == 0) {
+        w.tinfo[tile].np = P;
+        if (P) atomicAdd(&w.chunk_cnt[tile / SPL_CHUNK_TILES], (int32_t)P);
+    }
     // From here on every warp works alone on its own range of pieces [jlo, jhi): no block barrier, a warp with
     // slow pieces does not hold the others back.
     const uint32_t per = (((P + PROBE_WARPS - 1) / PROBE_WARPS) + 31u) & ~31u;
@@ -329,7 +337,7 @@ __device__ __forceinline__ uint32_t probe_whole(const SplWork& w, const SplTable
 }
 
 __device__ __forceinline__ void probe_tile_refine(const SplWork& w, SplProbeScratch& sm, const uint32_t* text, uint32_t* pb,
-                                                  const uint32_t tile) {
+                                                  const uint32_t tile, const uint32_t P1) {
     const SplTables* T = w.T;
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -338,7 +346,7 @@ __device__ __forceinline__ void probe_tile_refine(const SplWork& w, SplProbeScra
     static_assert(sizeof(sm.slow) + sizeof(sm.mloc) >= SPL_TILE * 4u && offsetof(SplProbeScratch, mloc) == offsetof(SplProbeScratch, slow) + sizeof(sm.slow), "val_at");
     if (tid < SPL_TILE / 32) { sm.segw[tid] = 0u; sm.mstw[tid] = 0u; }
     if (tid == 0) atomicAdd(&w.counters[SPL_CTR_REFINED], 1u);
-    const uint32_t P1 = build_piece_list(w, sm, pb, tile, false);
+    __syncthreads();
 
     // ---- pass 1 + pass R: one thread per piece ------------------------------------------------------------
     for (uint32_t j = tid; j < P1; j += SPL_THREADS) {
@@ -351,11 +359,50 @@ __device__ __forceinline__ void probe_tile_refine(const SplWork& w, SplProbeScra
         if (v != PV_MISSMARK) continue;
         if (len > SPL_PROBE_HALO && len <= T->max_key_len) continue;      // the merge kernels still owe it the long-key probe: stays whole
         atomicOr(&sm.mstw[s >> 5], 1u << (s & 31u));
-        const SmemPieceReader rd{text, s};
-        // characters are read from the staged window: only boundaries below the tile end are looked for, and the
-        // character that starts there lies inside the halo
-        spl_safe_boundaries(rd, len, SPL_TILE - s, T->seg_irr, T->seg_h2, T->seg_h2_log2,
-                            [&](uint32_t pos) { const uint32_t q = s + pos; atomicOr(&sm.segw[q >> 5], 1u << (q & 31u)); });
+    }
+    __syncthreads();
+
+    // ---- pass R: safe boundaries inside the missed pieces, one thread per 16 BYTES of the tile (a thread per piece
+    // walked its characters one dependent table load after the other while the block waited for the longest piece)
+    // R1: which bytes belong to a missed piece?  Word k: a piece start switches membership on (missed) or off.
+    if (tid < SPL_TILE / 32) {
+        const uint32_t S = pb[tid], M = sm.mstw[tid];
+        const bool has = S != 0u;
+        const uint32_t last = has ? (M >> (31u - (uint32_t)__clz(S))) & 1u : 0u;           // membership behind the word's last start
+        const uint32_t hmask = __ballot_sync(FULL, has), lmask = __ballot_sync(FULL, last != 0u);
+        if (lane == 0) sm.wtot[tid >> 5] = hmask ? (2u | ((lmask >> (31u - (uint32_t)__clz(hmask))) & 1u)) : 0u;
+        const uint32_t below = hmask & lt_mask;
+        uint32_t carry = below ? (lmask >> (31u - (uint32_t)__clz(below))) & 1u : 2u;         // 2: ask the warps in front
+        // (the four warps of this branch meet at a named barrier: the other four are not here)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (carry == 2u) {
+            carry = 0u;                                            // a piece that started in an earlier tile is not ours
+            for (int q = (int)(tid >> 5) - 1; q >= 0; --q)
+                if (sm.wtot[q]) { carry = sm.wtot[q] & 1u; break; }
+        }
+        uint32_t mask = 0, pos = 0, cur = carry;
+        for (uint32_t m = S; m; m &= m - 1u) {
+            const uint32_t b = (uint32_t)__ffs(m) - 1u;
+            if (cur) mask |= ((1u << b) - 1u) & ~((1u << pos) - 1u);
+            cur = (M >> b) & 1u; pos = b;
+        }
+        if (cur) mask |= ~((1u << pos) - 1u);
+        sm.inmw[tid] = mask;
+    }
+    __syncthreads();
+    // R2: my 16 bytes
+    {
+        const uint32_t sh = (tid & 1u) * 16u;
+        const uint32_t in16 = (sm.inmw[tid >> 1] >> sh) & 0xFFFFu, st16 = (pb[tid >> 1] >> sh) & 0xFFFFu;
+        const SmemPieceReader rd{text, 0u};
+        const uint32_t avail_tile = w.N - tile0;                    // text bytes from the tile start on
+        uint32_t found = 0;
+        for (uint32_t m = in16 & ~st16; m; m &= m - 1u) {
+            const uint32_t bq = (uint32_t)__ffs(m) - 1u, q = tid * 16u + bq;
+            if ((sm_byte(text, q) & 0xC0u) == 0x80u) continue;     // a continuation byte starts no character
+            if (spl_boundary_safe_at(rd, q, 0u, min(4u, avail_tile - q), T->seg_irr, T->seg_h2, T->seg_h2_log2)) found |= 1u << bq;
+        }
+        if (found) atomicOr(&sm.segw[tid >> 1], found << sh);
     }
     __syncthreads();
 
@@ -478,11 +525,11 @@ __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)
 // Stage one tile (text window + piece-start bits) from global memory.
 // BULK: two 1-D bulk copies (cp.async.bulk -> SASS UBLKCP, the TMA engine of sm_90+/sm_100) issued by one thread and
 // awaited on an mbarrier -- no registers, no LDG/STS pairs in the 256 threads; else 16-byte loads through registers.
-// Counts the bytes >= 0x80 of the tile into sm.ps.n_hi.
+// Returns the number of bytes >= 0x80 among the thread's 16 bytes of the tile.
 template <bool BULK>
-__device__ __forceinline__ void probe_stage(const SplWork& w, ProbeSmem& sm, const uint32_t tile) {
+__device__ __forceinline__ uint32_t probe_stage(const SplWork& w, ProbeSmem& sm, const uint32_t tile) {
     const uint32_t tid = threadIdx.x, tile0 = tile * SPL_TILE, Nup = (w.N + 15u) & ~15u;
-    if (tid == 0) sm.ps.n_hi = 0u;
+    uint32_t hi = 0;
     if (BULK) {
         const uint32_t tb = min(PROBE_TEXT_BYTES, Nup - tile0);                  // bytes of the window that exist (16-byte units)
         const uint32_t bar = smem_addr(&sm.mbar);
@@ -506,11 +553,8 @@ __device__ __forceinline__ void probe_stage(const SplWork& w, ProbeSmem& sm, con
             if (!ok && ++spins > (1u << 24)) __trap();                            // a copy that never lands must not hang the device
         } while (!ok);
         const uint4 x = reinterpret_cast<const uint4*>(sm.text)[tid];            // the tile proper: 256 x 16 bytes
-        const uint32_t hi = __popc(x.x & 0x80808080u) + __popc(x.y & 0x80808080u) + __popc(x.z & 0x80808080u) + __popc(x.w & 0x80808080u);
-        const uint32_t tot = __reduce_add_sync(FULL, hi);
-        if ((tid & 31u) == 0 && tot) atomicAdd(&sm.ps.n_hi, tot);
+        hi = __popc(x.x & 0x80808080u) + __popc(x.y & 0x80808080u) + __popc(x.z & 0x80808080u) + __popc(x.w & 0x80808080u);
     } else {
-        uint32_t hi = 0;
         for (uint32_t v = tid; v < PROBE_TEXT_BYTES / 16u; v += SPL_THREADS) {
             uint32_t g = tile0 + v * 16;
             uint4 x = make_uint4(0, 0, 0, 0);
@@ -520,11 +564,9 @@ __device__ __forceinline__ void probe_stage(const SplWork& w, ProbeSmem& sm, con
         }
         for (uint32_t v = tid; v < PB_WORDS; v += SPL_THREADS) sm.pb[v] = __ldg(w.pstart + (tile0 >> 5) + v);
         if (w.with_special && tid < SPL_TILE / 32) sm.ps.spw[tid] = __ldg(w.spec + (tile0 >> 5) + tid);
-        const uint32_t tot = __reduce_add_sync(FULL, hi);
-        __syncthreads();                                                          // n_hi is zero for everybody
-        if ((tid & 31u) == 0 && tot) atomicAdd(&sm.ps.n_hi, tot);
+        __syncthreads();
     }
-    __syncthreads();
+    return hi;
 }
 
 // a tile goes through the refining pass when more than 1/16 of its bytes belong to multi-byte characters
@@ -532,9 +574,11 @@ template <bool BULK>
 __global__ void __launch_bounds__(SPL_THREADS) k_probe(SplWork w) {
     __shared__ ProbeSmem sm;
     SPL_RETURN_IF_BAD_OFFSETS(w);
-    probe_stage<BULK>(w, sm, blockIdx.x);
-    if (sm.ps.n_hi * 16u > SPL_TILE) probe_tile_refine(w, sm.ps, sm.text, sm.pb, blockIdx.x);
-    else probe_tile(w, sm.ps, sm.text, sm.pb, blockIdx.x);
+    const uint32_t my_hi = probe_stage<BULK>(w, sm, blockIdx.x);
+    uint32_t n_hi = 0;
+    const uint32_t P = build_piece_list(w, sm.ps, sm.pb, blockIdx.x, false, my_hi, &n_hi);
+    if (n_hi * 16u > SPL_TILE) probe_tile_refine(w, sm.ps, sm.text, sm.pb, blockIdx.x, P);
+    else probe_tile(w, sm.ps, sm.text, sm.pb, blockIdx.x, P);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1311,26 +1355,21 @@ __global__ void __launch_bounds__(SPL_BPE_THREADS) k_bpe_fin(SplWork w) {
         const uint32_t lo = w.ml_base[2], hi = w.ml_base[SPL_NCLS - 1];           // the classes dedup_check looks at
         for (uint32_t c = 2; c < SPL_NCLS - 1; ++c) {
             const uint32_t n = w.counters[SPL_CTR_CLS + c];
-            const uint32_t n_round = (n + SPL_BPE_THREADS - 1u) / SPL_BPE_THREADS * SPL_BPE_THREADS;     // whole warps enter the vote
-            for (uint32_t i = blockIdx.x * SPL_BPE_THREADS + tid; i < n_round; i += gridDim.x * SPL_BPE_THREADS) {
-                const uint32_t midx = w.ml_base[c] + (i < n ? i : 0u);
+            for (uint32_t i = blockIdx.x * SPL_BPE_THREADS + tid; i < n; i += gridDim.x * SPL_BPE_THREADS) {
+                const uint32_t midx = w.ml_base[c] + i;
                 const uint64_t e = w.mlist[midx];
-                bool dup = i < n && (e & SPL_ML_DUP);
-                uint32_t rep = dup ? w.dup_of[midx - lo] : lo;
-                if (rep < lo || rep >= hi) { dup = false; rep = lo; }            // (cannot happen)
+                if (!(e & SPL_ML_DUP)) continue;
+                const uint32_t rep = w.dup_of[midx - lo];
+                if (rep < lo || rep >= hi) continue;                            // (cannot happen)
                 const uint64_t re = w.mlist[rep];
                 const uint32_t cnt = (uint32_t)(re >> 32) & SPL_ML_LEN_MASK, gpos = (uint32_t)e;
                 // the ids stay where the earlier piece put them; only the count is added to this piece's own tile
-                if (dup) w.mlist[midx] = (uint64_t)(uint32_t)re | ((uint64_t)cnt << 32) | SPL_ML_DONE;
-                const int32_t delta = dup ? (int32_t)cnt - 1 : 0;
-                const uint32_t tile = dup ? gpos / SPL_TILE : 0xFFFFFFFFu;
-                const uint32_t peers = __match_any_sync(FULL, tile);
-                const int32_t tsum = __reduce_add_sync(peers, delta);
-                if (dup && (tid & 31u) == (uint32_t)__ffs(peers) - 1u && tsum) atomicAdd(&w.tinfo[tile].extra, tsum);
-                const uint32_t chunk = dup ? tile / SPL_CHUNK_TILES : 0xFFFFFFFFu;
-                const uint32_t cpeers = __match_any_sync(FULL, chunk);
-                const int32_t csum = __reduce_add_sync(cpeers, delta);
-                if (dup && (tid & 31u) == (uint32_t)__ffs(cpeers) - 1u && csum) atomicAdd(&w.chunk_cnt[chunk], csum);
+                // (repeats are scattered over the text: nothing to aggregate, unlike bpe_finish_warp)
+                w.mlist[midx] = (uint64_t)(uint32_t)re | ((uint64_t)cnt << 32) | SPL_ML_DONE;
+                if (cnt != 1u) {
+                    atomicAdd(&w.tinfo[gpos / SPL_TILE].extra, (int32_t)cnt - 1);
+                    atomicAdd(&w.chunk_cnt[gpos / (SPL_TILE * SPL_CHUNK_TILES)], (int32_t)cnt - 1);
+                }
             }
         }
     }

@@ -193,6 +193,7 @@ struct SplProbeScratch {
     uint32_t last_end;                        // window position of the end of the tile's last piece
     uint32_t segw[SPL_TILE / 32];             // refining pass: safe boundaries found inside missed pieces (new piece starts)
     uint32_t mstw[SPL_TILE / 32];             // refining pass: starts of the pieces the whole-piece probe missed
-    uint32_t n_hi;                            // bytes >= 0x80 in the tile (decides whether the tile is refined)
+    uint32_t inmw[SPL_TILE / 32];             // refining pass: bytes that belong to those pieces
+    uint32_t whi[SPL_THREADS / 32];           // bytes >= 0x80 of the tile per warp (decides whether the tile is refined)
     uint32_t cls_cnt[SPL_NCLS + 1];           // refining pass: misses of the block per length class (+ settled multi-id characters), then list bases
 };

@@ -84,37 +84,38 @@ SPL_HD uint32_t spl_u8_cp23(uint32_t packed, uint32_t L) {
 #define SPL_CTZ32(x) ((uint32_t)__builtin_ctz(x))
 #endif
 
+// Is the boundary in front of byte q safe?  Position-local: B = the character that starts at q, A = the character
+// that ends at q - 1, both decoded right here (the proof above needs nothing else -- in particular not that the bytes
+// further left or right are UTF-8).  rd.load4(i) = the four bytes from index i on, little endian; indices from `lo` on
+// are readable, bytes in front of `lo` count as absent, `avail` = readable bytes from q on.
+template <class Reader>
+SPL_HD bool spl_boundary_safe_at(const Reader& rd, uint32_t q, uint32_t lo, uint32_t avail,
+                                 const uint32_t* irr, const uint32_t* h2, uint32_t h2_log2) {
+    uint32_t b = 0;
+    const uint32_t lb = spl_u8_char(rd.load4(q), avail, b);
+    if (lb == 0u || q <= lo) return false;
+    const uint32_t back = q - lo;                                       // bytes in front of q that exist
+    const uint32_t wa = back >= 4u ? rd.load4(q - 4u) : rd.load4(lo) << (8u * (4u - back));   // bytes q-4 .. q-1; absent ones 0
+    const uint32_t c1 = wa >> 24, c2 = (wa >> 16) & 0xFFu, c3 = (wa >> 8) & 0xFFu, c4 = wa & 0xFFu;
+    uint32_t a, la;
+    if (c1 < 0x80u) { a = c1; la = 1u; }
+    else if ((c1 & 0xC0u) != 0x80u) return false;                      // a lead byte right in front of q
+    else if ((c2 & 0xC0u) != 0x80u) { if (spl_u8_len(c2) != 2u || back < 2u) return false; a = c2 | (c1 << 8); la = 2u; }
+    else if ((c3 & 0xC0u) != 0x80u) { if (spl_u8_len(c3) != 3u || back < 3u) return false; a = c3 | (c2 << 8) | (c1 << 16); la = 3u; }
+    else if ((c4 & 0xC0u) != 0x80u) { if (spl_u8_len(c4) != 4u || back < 4u) return false; a = wa; la = 4u; }
+    else return false;
+    if (la == 1u && lb == 1u) return false;                            // ASCII | ASCII is never asked
+    return spl_boundary_safe(irr, h2, h2_log2, a, la, b);
+}
+
 // Every safe boundary of the piece [0, len) at a position below `limit`: f(pos) is called, in increasing order, for
-// each byte position pos (0 < pos < min(len, limit)) where a segment ends and the next one starts.
-// rd.load4(i) = the four bytes from piece-relative index i on, little endian (bytes at or beyond len are never
-// interpreted).  Once a byte sequence is not UTF-8 nothing after it is declared safe.
+// each byte position pos (0 < pos < min(len, limit)) in front of which spl_boundary_safe_at holds.
 template <class Reader, class F>
 SPL_HD void spl_safe_boundaries(const Reader& rd, uint32_t len, uint32_t limit,
                                 const uint32_t* irr, const uint32_t* h2, uint32_t h2_log2, F f) {
     if (limit > len) limit = len;
-    uint32_t a = 0;
-    uint32_t w4 = rd.load4(0);
-    uint32_t la = spl_u8_char(w4, len, a);
-    if (la == 0u) return;
-    uint32_t end = la;
-    while (end < limit) {
-        const uint32_t wb = rd.load4(end);
-        if (la == 1u) {
-            // ASCII | ASCII is never asked: skip over the run four bytes at a time
-            const uint32_t hi = wb & 0x80808080u;
-            uint32_t na = hi ? SPL_CTZ32(hi) >> 3 : 4u;
-            if (na > len - end) na = len - end;
-            if (na) {
-                end += na;
-                a = (wb >> (8u * (na - 1u))) & 0xFFu;
-                continue;
-            }
-        }
-        uint32_t b = 0;
-        const uint32_t lb = spl_u8_char(wb, len - end, b);
-        if (lb == 0u) return;
-        if (spl_boundary_safe(irr, h2, h2_log2, a, la, b)) f(end);
-        la = lb; a = b;
-        end += lb;
+    for (uint32_t q = 1; q < limit; ++q) {
+        if ((rd.load4(q) & 0xC0u) == 0x80u) continue;                  // a continuation byte starts no character
+        if (spl_boundary_safe_at(rd, q, 0u, len - q, irr, h2, h2_log2)) f(q);
     }
 }
