@@ -75,6 +75,7 @@ struct PinnedBuf { void* p; size_t cap; };
 struct spl_tokenizer {
     bool profiling = false;
     bool trace = false;                     // SPL_TRACE=1: per-chunk timeline of spl_encode_batch on stderr
+    bool charref = true;                    // SPL_NO_CHARREF=1: characters of two or three ids get miss-list entries (the path for passes beyond ~1.7 GB)
     bool dedup = true;                      // SPL_NO_DEDUP=1: every long piece goes through the merge loop, repeated or not
     int trace_chunk = -1;                   // SPL_TRACE_CHUNK=k: with SPL_TRACE, per-kernel times of the k-th chunk
     uint64_t chunk_bytes = 0;               // pipeline chunk size of spl_encode_batch (0 = automatic)
@@ -270,6 +271,7 @@ int prepare_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
     w.T = dc.d_tables;
     w.pattern = tk->host.pattern;
     w.with_special = with_special;
+    w.charref = tk->charref && m.base[SPL_NCLS] < 0x40000000u;     // SPL_PV_CHARREF needs miss-list indices below 2^30
     return SPL_OK;
 }
 
@@ -476,6 +478,7 @@ int spl_create(const uint8_t* vocab, size_t vocab_len, int pattern_id, uint32_t 
     if (const char* tr = getenv("SPL_TRACE")) tk->trace = tr[0] == '1';
     if (const char* tc = getenv("SPL_TRACE_CHUNK")) tk->trace_chunk = atoi(tc);
     if (const char* nd = getenv("SPL_NO_DEDUP")) tk->dedup = nd[0] == '0';
+    if (const char* nc = getenv("SPL_NO_CHARREF")) tk->charref = nc[0] == '0';
     if (const char* cb = getenv("SPL_CHUNK_BYTES")) tk->chunk_bytes = strtoull(cb, nullptr, 10);
     uint32_t hflags = ((flags & SPL_CREATE_BYTE_LEVEL) ? SPL_FLAG_BYTE_LEVEL : 0) |
                       ((flags & SPL_CREATE_SENTENCEPIECE) ? SPL_FLAG_SENTENCEPIECE : 0);

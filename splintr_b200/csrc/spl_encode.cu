@@ -444,8 +444,12 @@ __device__ __forceinline__ void probe_tile_refine(const SplWork& w, SplProbeScra
                     if (spl_u8_char(rd.load4(0), len, packed) == len) {
                         const uint32_t ct = __ldg(T->char_tok + spl_u8_cp23(packed, len));
                         if (ct != SPL_RANK_NONE) {
-                            if ((ct >> SPL_CHAR_COUNT_SHIFT) == 0u) val = ct;             // one id
-                            else cls = 1u + SPL_NCLS;                                     // two or three: 2b writes them
+                            const uint32_t more = ct >> SPL_CHAR_COUNT_SHIFT;             // ids - 1
+                            if (more == 0u) val = ct;                                     // one id
+                            else if (w.charref) {                                         // two or three: k_emit reads them from the table
+                                val = SPL_PV_CHARREF | (more << 28) | (ct & SPL_CHAR_VALUE_MASK);
+                                extra += (int32_t)more;
+                            } else cls = 1u + SPL_NCLS;                                   // ... or 2b writes them to the pool
                         }
                     }
                 }
@@ -1409,6 +1413,7 @@ __device__ __forceinline__ uint32_t emit_count(const SplWork& w, uint32_t v, boo
     if (!valid) return 0u;
     if (v < SPL_PV_MISS) return 1u;
     if (v == SPL_PV_NONE) return 0u;
+    if (w.charref && SPL_PV_IS_CHARREF(v)) return ((v >> 28) & 3u) + 1u;
     return (uint32_t)(w.mlist[v & ~SPL_PV_MISS] >> 32) & SPL_ML_LEN_MASK;
 }
 
@@ -1508,7 +1513,12 @@ __global__ void __launch_bounds__(SPL_THREADS, 8) k_emit(SplWork w) {
                 if (j4 + q < P) {
                     const uint32_t x = vv[q];
                     if (x < SPL_PV_MISS) out[pos++] = x;
-                    else if (x != SPL_PV_NONE) {
+                    else if (w.charref && SPL_PV_IS_CHARREF(x)) {
+                        const uint32_t* __restrict__ src = w.T->char_ids + (x & 0x0FFFFFFFu);
+                        const uint32_t c = ((x >> 28) & 3u) + 1u;
+                        for (uint32_t r = 0; r < c; ++r) out[pos + r] = __ldg(src + r);
+                        pos += c;
+                    } else if (x != SPL_PV_NONE) {
                         const uint64_t e = w.mlist[x & ~SPL_PV_MISS];
                         const uint32_t gp = (uint32_t)e, c = (uint32_t)(e >> 32) & SPL_ML_LEN_MASK;
                         if (c <= EM_INLINE) {

@@ -37,6 +37,10 @@ __host__ __device__ inline uint32_t spl_class_log2group(uint32_t c) { return c <
 // values of SplWork::pv (one per piece, in text order)
 #define SPL_PV_MISS  0x80000000u      // | index of the piece's entry in `mlist`
 #define SPL_PV_NONE  0xFFFFFFFFu      // the piece produces no id (byte unknown to the vocabulary)
+// a single character of two or three ids (SplWork::charref): 0xC0000000 | (ids - 1) << 28 | index of the first id in
+// SplTables::char_ids.  Top nibble C..E; needs miss-list indices below 2^30 (the host checks) -- F is NONE / internal.
+#define SPL_PV_CHARREF 0xC0000000u
+#define SPL_PV_IS_CHARREF(v) ((v) >= 0xC0000000u && (v) < 0xF0000000u)
 // miss-list entry before the merge kernels:  gpos:32 | len:31
 // miss-list entry after:                      gpos:32 | id count:31 | SPL_ML_DONE    (ids at pool[gpos ..])
 // SPL_ML_SEG: the entry is a SEGMENT of a piece (spl_segment.h): the whole-piece probe does not apply to it
@@ -92,6 +96,7 @@ struct SplWork {
     const SplTables* T;               // device copy of the tables
     int             pattern;
     bool            with_special;
+    bool            charref;          // pv may hold SPL_PV_CHARREF values (else such characters get a settled miss-list entry)
     bool            pretok_done;      // pstart / spec are already filled in (SentencePiece mode: written by k_sp_emit)
 };
 

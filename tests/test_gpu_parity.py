@@ -225,6 +225,28 @@ def test_segment_walker_multiscript(toks, name):
     assert t.encode(doc) == o.encode_batch([doc])[0]
 
 
+def test_multi_id_characters_through_the_miss_list(monkeypatch):
+    """Characters that are two or three ids are settled by k_probe's table: as SPL_PV_CHARREF values in pv, or -- in
+    passes too large for that encoding, forced here with SPL_NO_CHARREF=1 -- as settled miss-list entries with their ids
+    in the pool.  Both against the C oracle; SPL_NO_DEDUP=1 as well (every long piece through the merge loop)."""
+    from splintr_b200 import Tokenizer
+    from test_segments_host import CJK_COMMON, CJK_RARE, HANGUL, KANA
+    rng = random.Random(9)
+    texts = ["".join(rng.choice(CJK_RARE + HANGUL + KANA + CJK_COMMON + "，。 a") for _ in range(rng.randint(1, 4000))) for _ in range(60)]
+    texts += ["".join(rng.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(rng.randint(40, 600))) + " " for _ in range(40)] * 3
+    for env in ("SPL_NO_CHARREF", "SPL_NO_DEDUP"):
+        monkeypatch.setenv(env, "1")
+        for name in ("deepseek_v3", "cl100k_base"):
+            t = Tokenizer.from_pretrained(name, devices=[0])
+            assert t.encode_batch(texts) == c_oracle(name).encode_batch(texts), (env, name)
+            c = t.debug_counters()
+            if env == "SPL_NO_CHARREF":
+                assert c["settled_multi_id_chars"] > 0
+            else:
+                assert c["duplicates"] == 0
+        monkeypatch.delenv(env)
+
+
 def test_device_resident_entry_point(toks):
     import torch
     tok = toks("cl100k_base")
