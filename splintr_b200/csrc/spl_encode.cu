@@ -394,12 +394,25 @@ __device__ __forceinline__ void probe_tile_refine(const SplWork& w, SplProbeScra
     {
         const uint32_t sh = (tid & 1u) * 16u;
         const uint32_t in16 = (sm.inmw[tid >> 1] >> sh) & 0xFFFFu, st16 = (pb[tid >> 1] >> sh) & 0xFFFFu;
+        uint32_t cand = in16 & ~st16;
+        if (cand) {
+            // only bytes that start a character: not 10xxxxxx (four bytes per word -> four mask bits)
+            const uint4 x = reinterpret_cast<const uint4*>(text)[tid];
+            const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+            uint32_t lead = 0;
+#pragma unroll
+            for (uint32_t k = 0; k < 4u; ++k) {
+                const uint32_t t = (xs[k] & 0xC0C0C0C0u) ^ 0x80808080u;          // a byte of t is zero iff the text byte is a continuation byte
+                const uint32_t y = ((t | (t << 1)) >> 7) & 0x01010101u;
+                lead |= ((y & 1u) | ((y >> 7) & 2u) | ((y >> 14) & 4u) | ((y >> 21) & 8u)) << (4u * k);
+            }
+            cand &= lead;
+        }
         const SmemPieceReader rd{text, 0u};
         const uint32_t avail_tile = w.N - tile0;                    // text bytes from the tile start on
         uint32_t found = 0;
-        for (uint32_t m = in16 & ~st16; m; m &= m - 1u) {
+        for (uint32_t m = cand; m; m &= m - 1u) {
             const uint32_t bq = (uint32_t)__ffs(m) - 1u, q = tid * 16u + bq;
-            if ((sm_byte(text, q) & 0xC0u) == 0x80u) continue;     // a continuation byte starts no character
             if (spl_boundary_safe_at(rd, q, 0u, min(4u, avail_tile - q), T->seg_irr, T->seg_h2, T->seg_h2_log2)) found |= 1u << bq;
         }
         if (found) atomicOr(&sm.segw[tid >> 1], found << sh);
@@ -463,8 +476,10 @@ __device__ __forceinline__ void probe_tile_refine(const SplWork& w, SplProbeScra
                 }
             }
         }
-        if (__any_sync(FULL, cls != 0u)) {
-            for (uint32_t c = 0; c <= SPL_NCLS; ++c) {
+        const uint32_t anyb = __ballot_sync(FULL, cls != 0u);
+        if (anyb) {
+            const uint32_t cmax = __ballot_sync(FULL, cls > 1u) ? SPL_NCLS : 0u;          // usually only the shortest class is there
+            for (uint32_t c = 0; c <= cmax; ++c) {
                 const uint32_t bal = __ballot_sync(FULL, cls == c + 1u);
                 if (!bal) continue;
                 const uint32_t leader = __ffs(bal) - 1;
