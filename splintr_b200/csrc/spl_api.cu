@@ -655,6 +655,8 @@ struct Chunk {
     size_t ev;                  // first of its 4 timing events in DevCtx::pipe_ev (copied in*, kernels start, kernels end,
                                 // ids copied out*; * = trace only); its 2 ordering events are sync_ev[ev / 2 ..] (in, done)
     size_t slot;                // index of the chunk within its device's shard (running-total slot)
+    size_t doc_slot;            // first entry of the chunk in the device's doc_off / out_off buffers
+    bool first, last;           // first / last chunk of its device
     volatile uint64_t* meta;    // pinned, mapped: [0] id count, [1] error flags | huge-pool need << 32
     uint64_t* d_meta;           // the same memory as the device sees it
     uint64_t n_tokens;
@@ -677,51 +679,60 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
     int rc = check_special_support(tk, flags, with_special);
     if (rc) return rc;
 
-    // ---- shard documents over devices by cumulative bytes, then cut every shard into pipeline chunks ----
+    // ---- documents -> pipeline chunks -> devices ----------------------------------------------------------------
+    // One device: its shard is the whole batch, cut into chunks.  Several devices: the chunks of the WHOLE batch, in
+    // document order, go to the devices round robin.  (Contiguous shards per device serialised the devices: the ids of
+    // device g + 1 belong behind ALL ids of device g in the result, so its copy-out could only start once device g
+    // had finished -- measured 44 GB/s on two GPUs where one gives 36.  With interleaved chunks the position of a chunk's
+    // ids is known as soon as the chunk in front of it -- on the neighbouring device -- has been counted, and all
+    // devices copy in and out at the same time.)
     const size_t G = tk->devs.size();
+    const bool rr = G > 1;
     std::vector<size_t> dlo(G + 1, 0);
-    for (size_t g = 1; g < G; ++g) {
-        uint64_t target = N / G * g;
-        size_t d = std::lower_bound(offsets, offsets + n_docs + 1, target) - offsets;
-        dlo[g] = std::max(std::min(d, n_docs), dlo[g - 1]);
-    }
-    dlo[G] = n_docs;
+    for (size_t g = 1; g <= G; ++g) dlo[g] = n_docs;               // (one device: [0, n_docs); round robin: not used)
     std::vector<Chunk> chunks;
-    std::vector<size_t> text_need(G, 0), max_nb(G, 0), max_nd(G, 0);
-    for (size_t g = 0; g < G; ++g) {
-        const uint64_t s0 = offsets[dlo[g]], s1 = offsets[dlo[g + 1]], nb = s1 - s0;
-        uint64_t target = tk->chunk_bytes ? tk->chunk_bytes : std::min<uint64_t>(std::max<uint64_t>(nb / 8, 4u << 20), 256u << 20);
+    std::vector<size_t> text_need(G, 0), max_nb(G, 0), max_nd(G, 0), ids_need(G, 0), doc_need(G, 0), n_chunks(G, 0);
+    {
+        const uint64_t per_dev = N / G;
+        uint64_t target = tk->chunk_bytes ? tk->chunk_bytes : std::min<uint64_t>(std::max<uint64_t>(per_dev / 8, 4u << 20), 256u << 20);
         target = std::min<uint64_t>(target, kMaxShardBytes / (is_sentencepiece(tk) ? 6 : 2));
         // the pipeline fills with the first chunk's copy-in and drains with the last chunk's copy-out: ramp the chunk
         // size up at the start and down at the end (quarter, half, full ... full, half, quarter) unless it was pinned
-        const bool ramp = !tk->chunk_bytes && nb >= 4 * target;
-        size_t d = dlo[g], toff = 0, k = 0;
+        const bool ramp = !tk->chunk_bytes && per_dev >= 4 * target;
+        size_t d = 0, k = 0;
         do {
             Chunk c;
             memset(&c, 0, sizeof(c));
+            const size_t g = rr ? k % G : 0;
             c.g = (int)g; c.d0 = d; c.b0 = offsets[d];
             uint64_t want = target;
-            const uint64_t rem = s1 - c.b0;
+            const uint64_t rem = N - c.b0;
             if (ramp) {
-                if (k == 0) want = target / 4; else if (k == 1) want = target / 2;
-                if (rem <= target / 4 + target / 8) want = rem;                      // last: about a quarter
-                else if (rem <= target) want = rem - target / 4;                     // second to last
+                if (k < G) want = target / 4; else if (k < 2 * G) want = target / 2;            // every device starts small
+                if (rem <= (target / 4 + target / 8) * G) want = std::max<uint64_t>(rem / G, 1);  // the last round: about a quarter each
+                else if (rem <= target * G) want = std::max<uint64_t>((rem - target / 4 * G) / G, 1);
             }
-            ++k;
-            size_t e = std::upper_bound(offsets + d, offsets + dlo[g + 1] + 1, c.b0 + want) - offsets;   // first doc end beyond the target
-            e = std::min(std::max(e, d + 1), dlo[g + 1]);
-            if (!ramp && rem <= target + target / 4) e = dlo[g + 1];                                      // no runt at the end
-            if (ramp && rem <= want + want / 8) e = dlo[g + 1];
-            if (d == dlo[g + 1]) e = d;                                                                    // shard without documents
+            size_t e = std::upper_bound(offsets + d, offsets + n_docs + 1, c.b0 + want) - offsets;   // first doc end beyond the target
+            e = std::min(std::max(e, d + 1), n_docs);
+            if (!rr) {
+                if (!ramp && rem <= target + target / 4) e = n_docs;                              // no runt at the end
+                if (ramp && rem <= want + want / 8) e = n_docs;
+            } else if (rem <= want + want / 8) e = n_docs;
+            if (d == n_docs) e = d;                                                                // batch without documents
             c.d1 = e; c.b1 = offsets[e];
-            c.text_off = toff; c.ids_off = (size_t)ids_bound(tk, c.b0 - s0);
-            toff += align_up((size_t)(c.b1 - c.b0) + 16, 16);
+            c.text_off = text_need[g]; c.ids_off = ids_need[g]; c.doc_slot = doc_need[g]; c.slot = n_chunks[g]++;
+            c.first = c.slot == 0;
+            text_need[g] += align_up((size_t)(c.b1 - c.b0) + 16, 16);
+            ids_need[g] += (size_t)ids_bound(tk, c.b1 - c.b0) + (rr ? 16 : 0);
+            doc_need[g] += (c.d1 - c.d0) + (rr ? 1 : 0);
             max_nb[g] = std::max<size_t>(max_nb[g], (size_t)(c.b1 - c.b0));
             max_nd[g] = std::max<size_t>(max_nd[g], c.d1 - c.d0);
             chunks.push_back(c);
-            d = e;
-        } while (d < dlo[g + 1]);
-        text_need[g] = toff + 64;
+            d = e; ++k;
+        } while (d < n_docs);
+        for (size_t g = 0; g < G; ++g) { text_need[g] += 64; ids_need[g] += 16; doc_need[g] += 1; }
+        std::vector<int> seen(G, 0);
+        for (size_t i = chunks.size(); i-- > 0;) { chunks[i].last = !seen[chunks[i].g]; seen[chunks[i].g] = 1; }
     }
     const size_t C = chunks.size();
     h_plan = h_ms();
@@ -734,14 +745,21 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
     r->ids_buf = PinnedBuf{nullptr, 0};
     r->off_buf = take_pinned(tk, (n_docs + 1) * 8);
     PinnedBuf meta_buf = take_pinned(tk, C * 32);
+    std::vector<PinnedBuf> stage_off(G, PinnedBuf{nullptr, 0});      // round robin: every device's chunk-relative output offsets
     auto fail = [&](int code) {
         for (auto& dc : tk->devs) { cudaSetDevice(dc.device); cudaStreamSynchronize(dc.s_in); cudaStreamSynchronize(dc.stream); cudaStreamSynchronize(dc.s_out); }
         cudaGetLastError();
         give_pinned(tk, r->off_buf); give_pinned(tk, r->ids_buf); give_pinned(tk, meta_buf);
+        for (auto& b : stage_off) give_pinned(tk, b);
         delete r;
         return code;
     };
     if (!r->off_buf.p || !meta_buf.p) { tk->err = "pinned host allocation failed"; return fail(SPL_ERR_OOM); }
+    if (rr)
+        for (size_t g = 0; g < G; ++g) {
+            stage_off[g] = take_pinned(tk, (doc_need[g] + 1) * 8);
+            if (!stage_off[g].p) { tk->err = "pinned host allocation failed"; return fail(SPL_ERR_OOM); }
+        }
     uint64_t* res_off = (uint64_t*)r->off_buf.p;
     {
         void* d_meta_base = nullptr;
@@ -757,13 +775,11 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
         DevCtx& dc = tk->devs[g];
         auto reserve = [&]() -> int {
             CUDA_TRY(cudaSetDevice(dc.device), tk->err);
-            const size_t nd = dlo[g + 1] - dlo[g];
-            const uint64_t nb = offsets[dlo[g + 1]] - offsets[dlo[g]];
             int rc2;
             if ((rc2 = dc.text.ensure(text_need[g], tk->err))) return rc2;
-            if ((rc2 = dc.doc_off.ensure((nd + 1) * 8, tk->err))) return rc2;
-            if ((rc2 = dc.ids.ensure((ids_bound(tk, nb) + 16) * 4, tk->err))) return rc2;
-            if ((rc2 = dc.out_off.ensure((nd + 1) * 8, tk->err))) return rc2;
+            if ((rc2 = dc.doc_off.ensure((doc_need[g] + 1) * 8, tk->err))) return rc2;
+            if ((rc2 = dc.ids.ensure((ids_need[g] + 16) * 4, tk->err))) return rc2;
+            if ((rc2 = dc.out_off.ensure((doc_need[g] + 1) * 8, tk->err))) return rc2;
             if ((rc2 = reserve_work(tk, dc, ids_bound(tk, max_nb[g]), max_nd[g], with_special))) return rc2;
             size_t n_ev = 0, n_slot = 0;
             for (auto& c : chunks) if (c.g == (int)g) { c.ev = n_ev; n_ev += 4; c.slot = n_slot++; }
@@ -831,13 +847,15 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
             r->stats.d2h_bytes += c.n_tokens * 4;
             if (tk->trace) cudaEventRecord(dc.pipe_ev[c.ev + 3], dc.s_out);
             const size_t g = (size_t)c.g;
-            if (c.d1 == dlo[g + 1]) {
-                // last chunk of the shard: the per-document offsets of the whole shard in one copy.  They are
-                // shard-relative (every chunk's k_emit adds the ids of the chunks before it, kept on the device); one
-                // small copy per chunk would cost the copy engine more than it moves.
-                const size_t n_off = dlo[g + 1] - dlo[g] + (g + 1 == G ? 1 : 0);
+            if (c.last) {
+                // last chunk of the device: the per-document offsets of all its chunks in one copy (one small copy per
+                // chunk would cost the copy engine more than it moves).  One device: they are batch-relative (every
+                // chunk's k_emit adds the ids of the chunks before it, kept on the device) and go straight to the result.
+                // Round robin: chunk-relative, staged, and put in place with the chunk's base once everything has arrived.
+                const size_t n_off = rr ? doc_need[g] : n_docs + 1;
+                void* dst = rr ? stage_off[g].p : (void*)res_off;
                 if (n_off)
-                    CUDA_TRY(cudaMemcpyAsync(res_off + dlo[g], dc.out_off.p, n_off * 8, cudaMemcpyDeviceToHost, dc.s_out), tk->err);
+                    CUDA_TRY(cudaMemcpyAsync(dst, dc.out_off.p, n_off * 8, cudaMemcpyDeviceToHost, dc.s_out), tk->err);
                 r->stats.d2h_bytes += n_off * 8;
             }
             return SPL_OK;
@@ -850,21 +868,24 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
                 CUDA_TRY(cudaSetDevice(dc.device), tk->err);
                 const size_t nd = c.d1 - c.d0, g = (size_t)c.g;
                 const uint64_t nb = c.b1 - c.b0;
-                const bool first = c.d0 == dlo[g], last = c.d1 == dlo[g + 1];
+                const bool first = c.first;
                 cudaEvent_t ev_in = dc.sync_ev[c.ev / 2], ev_done = dc.sync_ev[c.ev / 2 + 1];
                 cudaEvent_t ev_k0 = dc.pipe_ev[c.ev + 1], ev_k1 = dc.pipe_ev[c.ev + 2];
                 uint64_t* run_tot = (uint64_t*)dc.run_tot.p;
-                if (first) {
-                    CUDA_TRY(cudaEventRecord(dc.ev[0], dc.s_in), tk->err);
-                    // the document offsets of the whole shard go in with one copy, ahead of the text
-                    const size_t nds = dlo[g + 1] - dlo[g];
-                    CUDA_TRY(cudaMemcpyAsync(dc.doc_off.p, offsets + dlo[g], (nds + 1) * 8, cudaMemcpyHostToDevice, dc.s_in), tk->err);
+                if (first) CUDA_TRY(cudaEventRecord(dc.ev[0], dc.s_in), tk->err);
+                if (first && !rr) {
+                    // the document offsets of the whole batch go in with one copy, ahead of the text
+                    CUDA_TRY(cudaMemcpyAsync(dc.doc_off.p, offsets, (n_docs + 1) * 8, cudaMemcpyHostToDevice, dc.s_in), tk->err);
                     CUDA_TRY(cudaMemsetAsync(run_tot, 0, 8, dc.s_in), tk->err);
-                    r->stats.h2d_bytes += (nds + 1) * 8;
+                    r->stats.h2d_bytes += (n_docs + 1) * 8;
                 }
                 // stage in: text to its aligned slot
                 uint8_t* d_text = (uint8_t*)dc.text.p + c.text_off;
-                uint64_t* d_doc = (uint64_t*)dc.doc_off.p + (c.d0 - dlo[g]);
+                uint64_t* d_doc = (uint64_t*)dc.doc_off.p + c.doc_slot;
+                if (rr) {                                          // round robin: the chunk's own slice of the document offsets
+                    CUDA_TRY(cudaMemcpyAsync(d_doc, offsets + c.d0, (nd + 1) * 8, cudaMemcpyHostToDevice, dc.s_in), tk->err);
+                    r->stats.h2d_bytes += (nd + 1) * 8;
+                }
                 if (nb) CUDA_TRY(cudaMemcpyAsync(d_text, bytes + c.b0, nb, cudaMemcpyHostToDevice, dc.s_in), tk->err);
                 if (tk->trace) CUDA_TRY(cudaEventRecord(dc.pipe_ev[c.ev], dc.s_in), tk->err);
                 CUDA_TRY(cudaEventRecord(ev_in, dc.s_in), tk->err);
@@ -874,9 +895,9 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
                 CUDA_TRY(cudaEventRecord(ev_k0, dc.stream), tk->err);
                 SplWork w;
                 int rc2;
-                uint64_t* d_out = (uint64_t*)dc.out_off.p + (c.d0 - dlo[g]);
+                uint64_t* d_out = (uint64_t*)dc.out_off.p + c.doc_slot;
                 EncodeArgs ea{d_text, nb, d_doc, c.b0, nd, (uint32_t*)dc.ids.p + c.ids_off, ids_bound(tk, nb), d_out, c.d_meta,
-                              run_tot + c.slot, run_tot + c.slot + 1};
+                              rr ? nullptr : run_tot + c.slot, rr ? nullptr : run_tot + c.slot + 1};
                 SplKernelProfile* prof = nullptr;
                 if (tk->trace && (int)c.slot == tk->trace_chunk) {        // SPL_TRACE_CHUNK=k: per-kernel times of chunk k
                     if (!dc.prof_ready) {
@@ -966,12 +987,13 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
             r->ids_buf = take_pinned(tk, 64);
             if (!r->ids_buf.p) { tk->err = "pinned host allocation failed"; return fail(SPL_ERR_OOM); }
         }
-        // the per-document offsets came back shard-relative: shards after the first are rebased (all copies have completed)
-        for (size_t g = 1; g < G; ++g) {
-            uint64_t sbase = 0;
-            for (auto& c : chunks) if (c.g == (int)g && c.d0 == dlo[g]) sbase = c.tok_base;
-            if (sbase) for (size_t d = dlo[g]; d < dlo[g + 1]; ++d) res_off[d] += sbase;
-        }
+        // round robin: the per-document offsets came back chunk-relative, per device: every chunk's slice gets the chunk's
+        // position in the result (all copies have completed)
+        if (rr)
+            for (auto& c : chunks) {
+                const uint64_t* src = (const uint64_t*)stage_off[c.g].p + c.doc_slot;
+                for (size_t d = c.d0; d < c.d1; ++d) res_off[d] = src[d - c.d0] + c.tok_base;
+            }
         res_off[n_docs] = total;
         r->n_tokens = total;
         r->stats.n_docs = n_docs; r->stats.n_bytes = N; r->stats.n_tokens = total;
@@ -980,6 +1002,7 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
         break;
     }
     give_pinned(tk, meta_buf);
+    for (auto& b : stage_off) give_pinned(tk, b);
     *out = r;
     if (tk->trace)
         fprintf(stderr, "[spl trace] host ms: plan %.3f  reserved %.3f  enqueued %.3f  drained %.3f  synced %.3f  end %.3f  (%zu chunks)\n",

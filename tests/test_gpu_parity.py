@@ -293,6 +293,33 @@ def test_multi_device_handle_matches_single(toks):
     assert np.array_equal(ids1, ids2) and np.array_equal(off1, off2)
 
 
+def test_multi_device_handle_round_robin(toks, monkeypatch):
+    """One handle over several devices: the chunks of the batch go to the devices round robin and come back in document
+    order (spl_api.cu).  The same GPU listed three times drives exactly that code on a one-GPU box: default chunking,
+    dozens of small chunks, empty documents on chunk boundaries, a document larger than a chunk, special tokens."""
+    from splintr_b200 import Tokenizer
+    o = c_oracle("cl100k_base")
+    d, off = synth.cfg2(vocab_bytes("cl100k_base"), 6000)
+    t3 = Tokenizer.from_pretrained("cl100k_base", devices=[0, 0, 0])
+    ids, out = _check_packed(t3, o, d, off)
+    ids1, out1 = toks("cl100k_base").encode_packed(d, off)
+    assert np.array_equal(ids, ids1) and np.array_equal(out, out1)
+    monkeypatch.setenv("SPL_CHUNK_BYTES", "30000")
+    t2 = Tokenizer.from_pretrained("cl100k_base", devices=[0, 0])
+    monkeypatch.delenv("SPL_CHUNK_BYTES")
+    _check_packed(t2, o, d, off)
+    texts = synth.unpack_texts(d, off)[:500]
+    texts[0] = ""; texts[7] = ""; texts[8] = ""; texts[30] = "y" * 100_000; texts[31] = ""; texts[-1] = ""
+    assert t2.encode_batch(texts) == o.encode_batch(texts)
+    assert t2.encode_batch(["", "", ""]) == [[], [], []]
+    assert t2.encode_batch([]) == []
+    sp = "<|endoftext|>"
+    texts2 = [tx[:40] + sp + tx[40:] for tx in texts[:200]]
+    po = py_oracle("cl100k_base")
+    assert t2.encode_batch_with_special(texts2) == [po.encode_with_special(x) for x in texts2]
+    assert t2.decode_batch(t2.encode_batch(texts[100:120])) == texts[100:120]
+
+
 def test_custom_vocab_with_unknown_bytes(toks):
     """bpe.rs:73-75,187-191: bytes that are not in the vocabulary are silently dropped."""
     import base64
