@@ -940,6 +940,7 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
         float kmax = 0, tmax = 0;
         for (size_t g = 0; g < G; ++g) {
             DevCtx& dc = tk->devs[g];
+            if (!n_chunks[g]) continue;                        // round robin over few chunks: this device had nothing to do
             cudaSetDevice(dc.device);
             cudaEventRecord(dc.ev[3], dc.s_out);
             cudaError_t e = cudaStreamSynchronize(dc.s_out);

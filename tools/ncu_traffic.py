@@ -26,7 +26,7 @@ def main():
         hdr, units = rows[0], rows[1]
         ik, ir, iw, it = (hdr.index(x) for x in ("Kernel Name", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum"))
         for r in rows[2:]:
-            name = r[ik].split("(")[0].split("<")[0]
+            name = r[ik].split("(")[0].split("<")[0].replace("void ", "").strip()
             rd = float(r[ir].replace(",", "")) * UNIT[units[ir]]
             wr = float(r[iw].replace(",", "")) * UNIT[units[iw]]
             ms = float(r[it].replace(",", "")) * TUNIT[units[it]]
