@@ -309,7 +309,7 @@ def test_multi_device_handle_round_robin(toks, monkeypatch):
     monkeypatch.delenv("SPL_CHUNK_BYTES")
     _check_packed(t2, o, d, off)
     texts = synth.unpack_texts(d, off)[:500]
-    texts[0] = ""; texts[7] = ""; texts[8] = ""; texts[30] = "y" * 100_000; texts[31] = ""; texts[-1] = ""
+    texts[0] = ""; texts[7] = ""; texts[8] = ""; texts[30] = "y" * 20_000; texts[31] = ""; texts[-1] = ""
     assert t2.encode_batch(texts) == o.encode_batch(texts)
     assert t2.encode_batch(["", "", ""]) == [[], [], []]
     assert t2.encode_batch([]) == []
