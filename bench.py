@@ -459,7 +459,8 @@ def strong_scaling(cx, keep3):
         ctypes.memmove(h_ptr + r * n1, data.ctypes.data, n1)
         h_off[r * nd1:(r + 1) * nd1] = offsets[:-1] + np.uint64(r * n1)
     h_off[nd] = n
-    tok = Tokenizer.from_pretrained(CONFIGS["cfg3"]["vocab"], devices=list(range(cx.world)))
+    n_dev = getattr(cx, "strong_devices", cx.world)
+    tok = Tokenizer.from_pretrained(CONFIGS["cfg3"]["vocab"], devices=list(range(n_dev)))
     times, ok, n_tok, stats = [], True, 0, None
     for it in range(3):
         res = ctypes.c_void_p()
@@ -489,9 +490,9 @@ def strong_scaling(cx, keep3):
     lib.spl_free_pinned(h_ptr)
     lib.spl_free_pinned(h_off_ptr)
     best = min(times)
-    return {"value": n / best / 1e9, "unit": UNIT, "scaling": "strong", "n_gpus": cx.world, "batch_bytes": n, "batch_docs": nd,
+    return {"value": n / best / 1e9, "unit": UNIT, "scaling": "strong", "n_gpus": n_dev, "batch_bytes": n, "batch_docs": nd,
             "ms_per_call": best * 1e3, "ids_match_single_device": bool(ok), **(stats or {}),
-            "what": f"one spl_encode_batch call, one handle over devices 0..{cx.world - 1} (single process), pinned host in, ids + "
+            "what": f"one spl_encode_batch call, one handle over devices 0..{n_dev - 1} (single process), pinned host in, ids + "
                     f"offsets in host memory out; batch = the cfg3 shard tiled {reps}x; best of 2 after 1 warm-up, host wall clock"}
 
 
@@ -550,6 +551,7 @@ def main():
     ap.add_argument("--docs", type=int, default=None, help="documents per rank of the headline config (default: the named size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--only-headline", action="store_true", help="skip the configs / strong / python_api blocks (profiling runs)")
+    ap.add_argument("--only-strong", action="store_true", help="single process: just the strong-scaling arm over --gpus devices")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -599,6 +601,13 @@ def main():
         barrier()
     cx.lib = _lib.load()
     cx.flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+
+    if args.only_strong:                                     # development aid: python bench.py --gpus N --only-strong (no torchrun)
+        cx.strong_devices = args.gpus
+        cx.no_cpu = True
+        _, keep3 = measure(cx, "cfg3", 2, 3, 0.0, None)
+        print(json.dumps({"strong": strong_scaling(cx, keep3)}), flush=True)
+        return
 
     traffic_table = None
     try:

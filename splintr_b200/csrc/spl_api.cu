@@ -441,7 +441,16 @@ PinnedBuf take_pinned(spl_tokenizer* tk, size_t bytes) {
 void give_pinned(spl_tokenizer* tk, PinnedBuf b) {
     if (!b.p) return;
     std::lock_guard<std::mutex> g(tk->pool_mu);
-    if (tk->pinned_pool.size() >= 8) { cudaFreeHost(b.p); return; }
+    // keep what one call of a multi-device handle takes (result ids + offsets, chunk records, one staging buffer per
+    // device): a pool that evicts makes the next call pin gigabytes again (cudaHostAlloc of 2.5 GB: ~1 s)
+    if (tk->pinned_pool.size() >= 8 + 2 * tk->devs.size()) {
+        size_t small = 0;
+        for (size_t i = 1; i < tk->pinned_pool.size(); ++i) if (tk->pinned_pool[i].cap < tk->pinned_pool[small].cap) small = i;
+        if (tk->pinned_pool[small].cap >= b.cap) { cudaFreeHost(b.p); return; }
+        cudaFreeHost(tk->pinned_pool[small].p);
+        tk->pinned_pool[small] = b;
+        return;
+    }
     tk->pinned_pool.push_back(b);
 }
 
