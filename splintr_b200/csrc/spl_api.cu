@@ -64,6 +64,11 @@ struct DevCtx {
     DevBuf run_tot;                                              // spl_encode_batch: cumulative id count after each pipeline chunk
     DevBuf sp_zero, sp_tiles, sp_text, sp_doc;                   // SentencePiece mode: bitmaps over T, tile counts, T', offsets in T'
     size_t huge_words = 0;
+    // the kernels of one pipeline chunk as ONE graph launch (spl_encode_batch): [with_special]
+    struct GraphCache {
+        cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+        cudaGraphNode_t mnode = nullptr; std::vector<cudaGraphNode_t> knodes; std::vector<const void*> funcs;
+    } gc[2];
     SplKernelProfile prof;
     bool prof_ready = false;
 };
@@ -75,6 +80,7 @@ struct PinnedBuf { void* p; size_t cap; };
 struct spl_tokenizer {
     bool profiling = false;
     bool trace = false;                     // SPL_TRACE=1: per-chunk timeline of spl_encode_batch on stderr
+    bool use_graph = true;                  // SPL_GRAPH=0: plain launches in spl_encode_batch as well
     bool charref = true;                    // SPL_NO_CHARREF=1: characters of two or three ids get miss-list entries (the path for passes beyond ~1.7 GB)
     bool dedup = true;                      // SPL_NO_DEDUP=1: every long piece goes through the merge loop, repeated or not
     int trace_chunk = -1;                   // SPL_TRACE_CHUNK=k: with SPL_TRACE, per-kernel times of the k-th chunk
@@ -169,6 +175,7 @@ void destroy_ctx(DevCtx& dc) {
     cudaSetDevice(dc.device);
     for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.ids, &dc.out_off, &dc.dec_ids, &dc.dec_off, &dc.dec_ws, &dc.dec_out, &dc.dec_out_off, &dc.jl_tiles, &dc.jl_lines, &dc.jl_text, &dc.jl_off, &dc.jl_out_off[0], &dc.jl_out_off[1], &dc.run_tot, &dc.sp_zero, &dc.sp_tiles, &dc.sp_text, &dc.sp_doc, &dc.zero, &dc.tstate, &dc.pv, &dc.pool, &dc.mlist, &dc.fbl, &dc.huge, &dc.dupof})
         b->release();
+    for (auto& g : dc.gc) { if (g.exec) cudaGraphExecDestroy(g.exec); if (g.graph) cudaGraphDestroy(g.graph); }
     if (dc.table_blob) cudaFree(dc.table_blob);
     for (auto& e : dc.ev) if (e) cudaEventDestroy(e);
     if (dc.prof_ready) for (auto& e : dc.prof.ev) cudaEventDestroy(e);
@@ -237,13 +244,14 @@ int reserve_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, boo
 // Prepare the internal workspace of `dc` for N bytes / n_docs documents and fill `w`
 // (text / doc_off / ids / out_off are set by the caller).  Enqueues the zero-fill.
 int prepare_work(spl_tokenizer* tk, DevCtx& dc, uint64_t N, uint64_t n_docs, bool with_special,
-                 cudaStream_t st, SplWork& w) {
+                 cudaStream_t st, SplWork& w, size_t* zero_bytes = nullptr) {
     int rc = reserve_work(tk, dc, N, n_docs, with_special);
     if (rc) return rc;
     const ZeroLayout z = zero_layout(N, with_special, tk->dedup, !tk->host.specials_unambiguous);
     const MissLayout m = miss_layout(N);
     uint32_t n_fast_tiles = (uint32_t)((N + SPL_FAST_PAYLOAD * 32u - 1) / (SPL_FAST_PAYLOAD * 32u));
-    CUDA_TRY(cudaMemsetAsync(dc.zero.p, 0, z.total, st), tk->err);
+    if (zero_bytes) *zero_bytes = z.total;                       // the caller clears the region itself (graph memset node)
+    else CUDA_TRY(cudaMemsetAsync(dc.zero.p, 0, z.total, st), tk->err);
     uint8_t* zb = (uint8_t*)dc.zero.p;
     w.N = (uint32_t)N;
     w.n_docs = (uint32_t)n_docs;
@@ -369,6 +377,61 @@ int enqueue_encode(spl_tokenizer* tk, DevCtx& dc, cudaStream_t st, const EncodeA
     return SPL_OK;
 }
 
+// The same pass as ONE graph launch: a memset node and the kernels of spl_describe_encode in a chain.  The executable
+// graph is built once per device and flag set; every chunk only rewrites the node parameters (pointers, sizes, grids).
+// Under saturating host-to-device traffic a kernel launch takes 25-45 us to reach the device: one launch per chunk
+// instead of nine brings the first ids of a call out earlier and shortens its tail.
+int enqueue_encode_graph(spl_tokenizer* tk, DevCtx& dc, cudaStream_t st, const EncodeArgs& a, bool with_special,
+                         SplWork& w, int& launches) {
+    int rc;
+    memset(&w, 0, sizeof(w));
+    size_t zero_bytes = 0;
+    if ((rc = prepare_work(tk, dc, a.N, a.n_docs, with_special, st, w, &zero_bytes))) return rc;
+    w.text = a.text; w.doc_off = a.doc_off; w.off_base = a.off_base;
+    w.ids = a.ids; w.out_off = a.out_off; w.host_meta = a.host_meta;
+    w.tok_base_in = a.tok_base_in; w.tok_total_out = a.tok_total_out;
+    SplLaunchDesc d[SPL_MAX_LAUNCHES];
+    const int n = spl_describe_encode(w, dc.num_sms, d);
+    DevCtx::GraphCache& g = dc.gc[with_special ? 1 : 0];
+    cudaMemsetParams mp;
+    memset(&mp, 0, sizeof(mp));
+    mp.dst = dc.zero.p; mp.value = 0; mp.elementSize = 4; mp.width = zero_bytes / 4; mp.height = 1; mp.pitch = zero_bytes;
+    uint32_t u32s[SPL_MAX_LAUNCHES];
+    void* args[SPL_MAX_LAUNCHES][2];
+    cudaKernelNodeParams kp[SPL_MAX_LAUNCHES];
+    for (int i = 0; i < n; ++i) {
+        u32s[i] = d[i].u32;
+        args[i][0] = &w; args[i][1] = &u32s[i];
+        memset(&kp[i], 0, sizeof(kp[i]));
+        kp[i].func = const_cast<void*>(d[i].func);
+        kp[i].gridDim = dim3(d[i].grid); kp[i].blockDim = dim3(d[i].block);
+        kp[i].sharedMemBytes = (unsigned)d[i].smem;
+        kp[i].kernelParams = args[i];
+    }
+    bool same = g.exec && (int)g.funcs.size() == n;
+    for (int i = 0; same && i < n; ++i) same = g.funcs[i] == d[i].func;
+    if (!same) {
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        if (g.graph) { cudaGraphDestroy(g.graph); g.graph = nullptr; }
+        g.knodes.assign(n, nullptr); g.funcs.assign(n, nullptr);
+        CUDA_TRY(cudaGraphCreate(&g.graph, 0), tk->err);
+        CUDA_TRY(cudaGraphAddMemsetNode(&g.mnode, g.graph, nullptr, 0, &mp), tk->err);
+        cudaGraphNode_t prev = g.mnode;
+        for (int i = 0; i < n; ++i) {
+            CUDA_TRY(cudaGraphAddKernelNode(&g.knodes[i], g.graph, &prev, 1, &kp[i]), tk->err);
+            prev = g.knodes[i];
+            g.funcs[i] = d[i].func;
+        }
+        CUDA_TRY(cudaGraphInstantiate(&g.exec, g.graph, 0), tk->err);
+    } else {
+        CUDA_TRY(cudaGraphExecMemsetNodeSetParams(g.exec, g.mnode, &mp), tk->err);
+        for (int i = 0; i < n; ++i) CUDA_TRY(cudaGraphExecKernelNodeSetParams(g.exec, g.knodes[i], &kp[i]), tk->err);
+    }
+    CUDA_TRY(cudaGraphLaunch(g.exec, st), tk->err);
+    launches += n;
+    return SPL_OK;
+}
+
 struct JlOut { uint8_t* text; size_t text_cap; uint64_t* off; size_t off_cap; };
 
 // JSON Lines -> packed text + offsets for one device pass on `st` (two synchronisations).  `outputs(n_lines, o)` is
@@ -488,6 +551,7 @@ int spl_create(const uint8_t* vocab, size_t vocab_len, int pattern_id, uint32_t 
     if (const char* tc = getenv("SPL_TRACE_CHUNK")) tk->trace_chunk = atoi(tc);
     if (const char* nd = getenv("SPL_NO_DEDUP")) tk->dedup = nd[0] == '0';
     if (const char* nc = getenv("SPL_NO_CHARREF")) tk->charref = nc[0] == '0';
+    if (const char* gr = getenv("SPL_GRAPH")) tk->use_graph = gr[0] != '0';
     if (const char* cb = getenv("SPL_CHUNK_BYTES")) tk->chunk_bytes = strtoull(cb, nullptr, 10);
     uint32_t hflags = ((flags & SPL_CREATE_BYTE_LEVEL) ? SPL_FLAG_BYTE_LEVEL : 0) |
                       ((flags & SPL_CREATE_SENTENCEPIECE) ? SPL_FLAG_SENTENCEPIECE : 0);
@@ -916,7 +980,9 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
                     }
                     prof = &dc.prof;
                 }
-                if ((rc2 = enqueue_encode(tk, dc, dc.stream, ea, with_special, prof, w, launches))) return rc2;
+                if (tk->use_graph && !prof && !is_sentencepiece(tk)) rc2 = enqueue_encode_graph(tk, dc, dc.stream, ea, with_special, w, launches);
+                else rc2 = enqueue_encode(tk, dc, dc.stream, ea, with_special, prof, w, launches);
+                if (rc2) return rc2;
                 CUDA_TRY(cudaGetLastError(), tk->err);
                 CUDA_TRY(cudaEventRecord(ev_k1, dc.stream), tk->err);
                 // the chunk's id count and error flags arrive in mapped host memory (written by k_emit): no copy on the

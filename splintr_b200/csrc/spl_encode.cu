@@ -1589,12 +1589,9 @@ void spl_encode_init() {
     cudaGetLastError();
 }
 
-void spl_launch_encode_stage(const SplWork& w, int num_sms, cudaStream_t stream, SplMarkFn mark, void* ctx) {
+int spl_describe_encode_stage(const SplWork& w, int num_sms, SplLaunchDesc* out) {
     // staging by bulk copy (TMA engine) or through registers: SPL_PROBE_BULK=0 selects the latter (A/B measurements)
     static const bool bulk = [] { const char* e = getenv("SPL_PROBE_BULK"); return !e || e[0] != '0'; }();
-    if (bulk) k_probe<true><<<w.n_tiles, SPL_THREADS, 0, stream>>>(w);
-    else k_probe<false><<<w.n_tiles, SPL_THREADS, 0, stream>>>(w);
-    mark(ctx, "k_probe");
     // first length class merged by windowed rounds (measured crossover; SPL_BPE_WIN_CLS overrides it for experiments)
     static const uint32_t win_cls = [] { const char* e = getenv("SPL_BPE_WIN_CLS"); return e ? (uint32_t)atoi(e) : SPL_BPE_WIN_CLS; }();
     // persistent grids, but no larger than the text can feed: a small batch must not pay for launching (and draining)
@@ -1602,12 +1599,11 @@ void spl_launch_encode_stage(const SplWork& w, int num_sms, cudaStream_t stream,
     const uint32_t g_bpe = std::min<uint32_t>((uint32_t)num_sms * 6u, std::max<uint32_t>(1u, w.N / 2048u));
     const uint32_t g_long = std::min<uint32_t>((uint32_t)num_sms * 4u, std::max<uint32_t>(1u, w.N / 4096u));
     const uint32_t g_fin = std::min<uint32_t>((uint32_t)num_sms, std::max<uint32_t>(1u, w.n_tiles / 8u));
-    k_bpe<<<g_bpe, SPL_BPE_THREADS, WK_SMEM_BYTES, stream>>>(w);
-    mark(ctx, "k_bpe");
-    k_bpe_long<<<g_long, SPL_BPE_THREADS, BPE_SMEM_BYTES, stream>>>(w, win_cls);
-    mark(ctx, "k_bpe_long");
-    k_bpe_fin<<<g_fin, SPL_BPE_THREADS, 0, stream>>>(w);                                            // duplicates + the chunk scan, by its last block
-    mark(ctx, "k_bpe_fin");
-    k_emit<<<w.n_tiles, SPL_THREADS, 0, stream>>>(w);
-    mark(ctx, "k_emit");
+    int n = 0;
+    out[n++] = SplLaunchDesc{bulk ? (const void*)k_probe<true> : (const void*)k_probe<false>, "k_probe", w.n_tiles, SPL_THREADS, 0, false, 0};
+    out[n++] = SplLaunchDesc{(const void*)k_bpe, "k_bpe", g_bpe, SPL_BPE_THREADS, WK_SMEM_BYTES, false, 0};
+    out[n++] = SplLaunchDesc{(const void*)k_bpe_long, "k_bpe_long", g_long, SPL_BPE_THREADS, BPE_SMEM_BYTES, true, win_cls};
+    out[n++] = SplLaunchDesc{(const void*)k_bpe_fin, "k_bpe_fin", g_fin, SPL_BPE_THREADS, 0, false, 0};      // duplicates + the chunk scan, by its last block
+    out[n++] = SplLaunchDesc{(const void*)k_emit, "k_emit", w.n_tiles, SPL_THREADS, 0, false, 0};
+    return n;
 }

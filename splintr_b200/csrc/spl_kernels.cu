@@ -286,64 +286,65 @@ void spl_kernels_init() {
 }
 
 namespace {
-struct MarkCtx { SplKernelProfile* prof; cudaStream_t stream; int launches; };
-void mark_cb(void* p, const char* name) {
-    MarkCtx* c = static_cast<MarkCtx*>(p);
-    ++c->launches;
-    SplKernelProfile* prof = c->prof;
-    if (prof && prof->n < SPL_PROF_MAX) { prof->name[prof->n] = name; ++prof->n; cudaEventRecord(prof->ev[prof->n], c->stream); }
+void launch_desc(const SplLaunchDesc& d, const SplWork& w, cudaStream_t stream) {
+    SplWork wc = w;
+    uint32_t u = d.u32;
+    void* args[2] = {&wc, &u};
+    cudaLaunchKernel(d.func, dim3(d.grid), dim3(d.block), args, d.smem, stream);
+}
+void sync_each(cudaStream_t stream, const char* name) {
     // SPL_SYNC_EACH=1 (debugging): wait for every kernel and name the one that faults
-    static const bool sync_each = [] { const char* e = getenv("SPL_SYNC_EACH"); return e && e[0] == '1'; }();
-    if (sync_each) {
-        cudaError_t e = cudaStreamSynchronize(c->stream);
-        if (e != cudaSuccess) fprintf(stderr, "[spl] kernel %s: %s\n", name, cudaGetErrorString(e));
-    }
+    static const bool on = [] { const char* e = getenv("SPL_SYNC_EACH"); return e && e[0] == '1'; }();
+    if (!on) return;
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) fprintf(stderr, "[spl] kernel %s: %s\n", name, cudaGetErrorString(e));
 }
 }  // namespace
 
-int spl_launch_mark(const SplWork& w, int num_sms, cudaStream_t stream) {
-    uint32_t n = w.n_docs + 1;
-    k_mark_docs<<<(n + 255) / 256, 256, 0, stream>>>(w);
-    if (!(w.with_special && w.N)) return 1;
-    uint32_t blocks = (w.N + 255) / 256;
-    uint32_t cap = (uint32_t)num_sms * 16;
-    k_mark_specials<<<blocks < cap ? blocks : cap, 256, 0, stream>>>(w);
-    if (!w.cand) return 2;
-    k_resolve_specials<<<std::min<uint32_t>((w.n_docs + 127u) / 128u, cap), 128, 0, stream>>>(w);
-    return 3;
+static int describe_mark(const SplWork& w, int num_sms, SplLaunchDesc* out) {
+    int n = 0;
+    out[n++] = SplLaunchDesc{(const void*)k_mark_docs, "k_mark_docs", (w.n_docs + 1 + 255) / 256, 256, 0, false, 0};
+    if (w.with_special && w.N && !w.pretok_done) {
+        const uint32_t blocks = (w.N + 255) / 256, cap = (uint32_t)num_sms * 16;
+        out[n++] = SplLaunchDesc{(const void*)k_mark_specials, "k_mark_specials", blocks < cap ? blocks : cap, 256, 0, false, 0};
+        if (w.cand)
+            out[n++] = SplLaunchDesc{(const void*)k_resolve_specials, "k_resolve_specials", std::min<uint32_t>((w.n_docs + 127u) / 128u, cap), 128, 0, false, 0};
+    }
+    return n;
 }
 
-int spl_launch_encode(const SplWork& w, int num_sms, cudaStream_t stream, SplKernelProfile* prof) {
-    MarkCtx mc{prof, stream, 0};
-    if (prof) { prof->n = 0; cudaEventRecord(prof->ev[0], stream); }
-    auto mark = [&](const char* name) { mark_cb(&mc, name); };
-    {
-        uint32_t n = w.n_docs + 1;
-        k_mark_docs<<<(n + 255) / 256, 256, 0, stream>>>(w);
-        mark("k_mark_docs");
-    }
-    if (w.with_special && w.N && !w.pretok_done) {
-        uint32_t blocks = (w.N + 255) / 256;
-        uint32_t cap = (uint32_t)num_sms * 16;
-        k_mark_specials<<<blocks < cap ? blocks : cap, 256, 0, stream>>>(w);
-        mark("k_mark_specials");
-        if (w.cand) {
-            k_resolve_specials<<<std::min<uint32_t>((w.n_docs + 127u) / 128u, cap), 128, 0, stream>>>(w);
-            mark("k_resolve_specials");
-        }
-    }
+int spl_launch_mark(const SplWork& w, int num_sms, cudaStream_t stream) {
+    SplLaunchDesc d[4];
+    SplWork v = w;
+    v.pretok_done = false;
+    const int n = describe_mark(v, num_sms, d);
+    for (int i = 0; i < n; ++i) { launch_desc(d[i], w, stream); sync_each(stream, d[i].name); }
+    return n;
+}
+
+int spl_describe_encode(const SplWork& w, int num_sms, SplLaunchDesc* out) {
+    int n = describe_mark(w, num_sms, out);
     if (w.pretok_done) {
         // SentencePiece mode: k_sp_emit has written the piece starts of the transformed text
     } else if (w.N && w.pattern == SPL_PAT_MISTRAL_V3) {
-        k_pretok<<<(w.N + SPL_TILE - 1) / SPL_TILE, SPL_THREADS, 0, stream>>>(w);
-        mark("k_pretok");
+        out[n++] = SplLaunchDesc{(const void*)k_pretok, "k_pretok", (w.N + SPL_TILE - 1) / SPL_TILE, SPL_THREADS, 0, false, 0};
     } else if (w.N) {
-        k_pretok_fast<<<w.n_fast_tiles, SPL_FAST_THREADS, 0, stream>>>(w);
-        mark("k_pretok_fast");
-        uint32_t cap = (uint32_t)num_sms * 4;
-        k_pretok_fb<<<w.n_fast_tiles < cap ? w.n_fast_tiles : cap, SPL_THREADS, 0, stream>>>(w);
-        mark("k_pretok_fb");
+        const uint32_t cap = (uint32_t)num_sms * 4;
+        out[n++] = SplLaunchDesc{(const void*)k_pretok_fast, "k_pretok_fast", w.n_fast_tiles, SPL_FAST_THREADS, 0, false, 0};
+        out[n++] = SplLaunchDesc{(const void*)k_pretok_fb, "k_pretok_fb", w.n_fast_tiles < cap ? w.n_fast_tiles : cap, SPL_THREADS, 0, false, 0};
     }
-    spl_launch_encode_stage(w, num_sms, stream, mark_cb, &mc);
-    return mc.launches;
+    n += spl_describe_encode_stage(w, num_sms, out + n);
+    return n;
+}
+
+int spl_launch_encode(const SplWork& w, int num_sms, cudaStream_t stream, SplKernelProfile* prof) {
+    SplLaunchDesc d[SPL_MAX_LAUNCHES];
+    const int n = spl_describe_encode(w, num_sms, d);
+    if (prof) { prof->n = 0; cudaEventRecord(prof->ev[0], stream); }
+    for (int i = 0; i < n; ++i) {
+        launch_desc(d[i], w, stream);
+        if (prof && prof->n < SPL_PROF_MAX) { prof->name[prof->n] = d[i].name; ++prof->n; cudaEventRecord(prof->ev[prof->n], stream); }
+        sync_each(stream, d[i].name);
+    }
+    return n;
 }

@@ -122,6 +122,18 @@ struct SplKernelProfile {
     int n;
 };
 
+// One kernel launch of the encode path, described instead of performed: the same list feeds plain launches
+// (spl_launch_encode) and the nodes of a CUDA graph (spl_api.cu: one graph launch per pipeline chunk).
+// Every kernel takes the SplWork by value; k_bpe_long a second u32 argument.
+#define SPL_MAX_LAUNCHES 16
+struct SplLaunchDesc {
+    const void* func; const char* name;
+    unsigned grid, block; size_t smem;
+    bool has_u32; uint32_t u32;
+};
+int spl_describe_encode(const SplWork& w, int num_sms, SplLaunchDesc* out);      // returns the number of launches
+int spl_describe_encode_stage(const SplWork& w, int num_sms, SplLaunchDesc* out);
+
 // Enqueue the whole encode path on `stream`.  Returns the number of kernels launched.
 int spl_launch_encode(const SplWork& w, int num_sms, cudaStream_t stream, SplKernelProfile* prof = nullptr);
 
@@ -184,9 +196,7 @@ void spl_launch_decode_count(const SplDecLaunch& L, cudaStream_t stream);   // k
 void spl_launch_decode_emit(const SplDecLaunch& L, cudaStream_t stream);    // k_dec_emit (no-op on the device if capacity is too small)
 
 // spl_encode.cu: the encode stage behind the pre-tokenizer (k_probe, k_bpe, k_tile_scan, k_emit)
-typedef void (*SplMarkFn)(void* ctx, const char* name);
 void spl_encode_init();
-void spl_launch_encode_stage(const SplWork& w, int num_sms, cudaStream_t stream, SplMarkFn mark, void* ctx);
 
 // per-tile scratch of the whole-piece probe (spl_encode.cu: probe_tile)
 struct SplProbeScratch {
