@@ -85,6 +85,8 @@ struct spl_tokenizer {
     bool dedup = true;                      // SPL_NO_DEDUP=1: every long piece goes through the merge loop, repeated or not
     int trace_chunk = -1;                   // SPL_TRACE_CHUNK=k: with SPL_TRACE, per-kernel times of the k-th chunk
     uint64_t chunk_bytes = 0;               // pipeline chunk size of spl_encode_batch (0 = automatic)
+    uint64_t chunks_per_dev = 8;            // automatic chunk size = shard / this (SPL_CHUNKS_PER_DEV)
+    std::vector<uint64_t> ramp_div{4, 2};   // the first pipeline chunks of a device are target / 4, target / 2 (SPL_RAMP="8,4,2" to experiment)
     SplHostTables host;
     std::vector<DevCtx> devs;
     std::string err;
@@ -553,6 +555,11 @@ int spl_create(const uint8_t* vocab, size_t vocab_len, int pattern_id, uint32_t 
     if (const char* nc = getenv("SPL_NO_CHARREF")) tk->charref = nc[0] == '0';
     if (const char* gr = getenv("SPL_GRAPH")) tk->use_graph = gr[0] != '0';
     if (const char* cb = getenv("SPL_CHUNK_BYTES")) tk->chunk_bytes = strtoull(cb, nullptr, 10);
+    if (const char* rp = getenv("SPL_RAMP")) {
+        tk->ramp_div.clear();
+        for (const char* p = rp; *p;) { char* e; uint64_t v = strtoull(p, &e, 10); if (e == p) break; if (v) tk->ramp_div.push_back(v); p = *e ? e + 1 : e; }
+    }
+    if (const char* ch = getenv("SPL_CHUNKS_PER_DEV")) tk->chunks_per_dev = std::max<uint64_t>(strtoull(ch, nullptr, 10), 1);
     uint32_t hflags = ((flags & SPL_CREATE_BYTE_LEVEL) ? SPL_FLAG_BYTE_LEVEL : 0) |
                       ((flags & SPL_CREATE_SENTENCEPIECE) ? SPL_FLAG_SENTENCEPIECE : 0);
     if (!spl_build_tables(tk->host, vocab, vocab_len, pattern_id, hflags, special_strs, special_ids, n_special)) {
@@ -767,7 +774,7 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
     std::vector<size_t> text_need(G, 0), max_nb(G, 0), max_nd(G, 0), ids_need(G, 0), doc_need(G, 0), n_chunks(G, 0);
     {
         const uint64_t per_dev = N / G;
-        uint64_t target = tk->chunk_bytes ? tk->chunk_bytes : std::min<uint64_t>(std::max<uint64_t>(per_dev / 8, 4u << 20), 256u << 20);
+        uint64_t target = tk->chunk_bytes ? tk->chunk_bytes : std::min<uint64_t>(std::max<uint64_t>(per_dev / tk->chunks_per_dev, 4u << 20), 256u << 20);
         target = std::min<uint64_t>(target, kMaxShardBytes / (is_sentencepiece(tk) ? 6 : 2));
         // the pipeline fills with the first chunk's copy-in and drains with the last chunk's copy-out: ramp the chunk
         // size up at the start and down at the end (quarter, half, full ... full, half, quarter) unless it was pinned
@@ -781,9 +788,13 @@ int spl_encode_batch(spl_tokenizer* tk, const uint8_t* bytes, const uint64_t* of
             uint64_t want = target;
             const uint64_t rem = N - c.b0;
             if (ramp) {
-                if (k < G) want = target / 4; else if (k < 2 * G) want = target / 2;            // every device starts small
-                if (rem <= (target / 4 + target / 8) * G) want = std::max<uint64_t>(rem / G, 1);  // the last round: about a quarter each
-                else if (rem <= target * G) want = std::max<uint64_t>((rem - target / 4 * G) / G, 1);
+                // every device starts small (target / ramp_div[round]) ...
+                const size_t round = k / G;
+                if (round < tk->ramp_div.size()) want = std::max<uint64_t>(target / tk->ramp_div[round], 1);
+                // ... and ends small: the last rounds mirror the first ones
+                const uint64_t last_div = tk->ramp_div.empty() ? 1 : tk->ramp_div[0];
+                if (rem <= (target / last_div + target / (2 * last_div)) * G) want = std::max<uint64_t>(rem / G, 1);
+                else if (rem <= target * G) want = std::max<uint64_t>((rem - target / last_div * G) / G, 1);
             }
             size_t e = std::upper_bound(offsets + d, offsets + n_docs + 1, c.b0 + want) - offsets;   // first doc end beyond the target
             e = std::min(std::max(e, d + 1), n_docs);
