@@ -404,7 +404,8 @@ def measure(cx, cfg: str, steps: int, warmup: int, cpu_budget: float, traffic_ta
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_stats["h2d"], "d2h_bytes_per_step": e2e_stats["d2h"],
                    "ms_per_step": float(e2e_s.item()) / steps * 1e3, "device_ms_per_step": e2e_stats["dev_ms"],
                    "timing": "host wall clock around spl_encode_batch, barrier + synchronize both sides, max over ranks"},
-           "ids_match_cpu_baseline": parity, "launches_per_call": e2e_stats["launches"], "generate_s": round(t_gen, 2)}
+           "ids_match_cpu_baseline": parity, "launches_per_step": tok.launches_per_call(False),
+           "launches_per_call": e2e_stats["launches"], "generate_s": round(t_gen, 2)}
     keep = Ctx()
     keep.data, keep.offsets, keep.tok, keep.d_ids, keep.d_out, keep.n_tok = data, offsets, tok, d_ids, d_out, n_tok
     return out, keep
@@ -663,7 +664,8 @@ def main():
                            "tokens_per_gpu": head["tokens_per_gpu"]},
                 "roofline": head["roofline"], "cpu_baseline": head["cpu_baseline"],
                 "e2e": e2e,
-                "gpu_launches": args.steps * head["launches_per_call"], "clocks": clocks,
+                "gpu_launches": args.steps * head["launches_per_step"], "gpu_launches_e2e": args.steps * head["launches_per_call"],
+                "clocks": clocks,
                 "ids_match_cpu_baseline": head["ids_match_cpu_baseline"],
                 "configs": configs or None, "strong": strong, "python_api": py_api, "small_batch": small}
         print(json.dumps(line), flush=True)
