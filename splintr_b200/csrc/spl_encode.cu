@@ -1405,21 +1405,34 @@ __global__ void __launch_bounds__(SPL_BPE_THREADS) k_bpe_fin(SplWork w) {
 }
 
 // ------------------------------------------------------------------------------------------
-// k_emit: one tile per block: pv[] (+ pool[] for merged pieces) -> ids in document order, output offsets.
-// Four pieces per thread and round (one 16-byte load of pv), so a warp owns 128 consecutive pieces.
+// k_emit: one tile per block: pv[] (+ pool[] for merged pieces, char_ids[] for characters of several ids) -> ids in
+// document order, output offsets.  Four pieces per thread and round (one 16-byte load of pv), so a warp owns 128
+// consecutive pieces.
+//
+// The ids of a tile are assembled in shared memory and leave in whole 128-byte lines.  (A thread that stores its own
+// four-odd ids straight to global memory makes every warp store touch ~20 sectors for 32 words, one partial-sector
+// write per id at the L2: 29 M sector operations per 100 MB of cfg2.  Measured, that was NOT what bounds the kernel:
+// cfg2 / cfg3 / cfg4 are unchanged (80 / 102 / 107 us against 80 / 103 / 104 us at 64 MB), cfg5 -- two ids per
+// piece -- gains 6 % (272 against 288 us).  The kernel waits on its barriers and on the pv -> mlist -> pool chain and
+// issues 415 instructions per warp and tile.  k_emit_direct below is the other version, kept for the A/B measurement:
+// SPL_EMIT_STAGE=0.)
 // ------------------------------------------------------------------------------------------
 #define EM_ROUNDS (SPL_TILE / (SPL_THREADS * 4))     // 4 rounds cover the 4096 pieces a tile can have
 #define EM_WARPS (SPL_THREADS / 32)
 #define EM_INLINE 8u                                 // ids of a merged piece copied by its own thread up to this many
 #define EM_BIGCAP (SPL_TILE / (EM_INLINE + 1u) + 1u) // pieces of a tile that can have more ids than that
+#define EM_STAGE 3072u                               // ids assembled at a time (a tile with more takes several phases)
 
 struct EmitSmem {
-    __align__(16) uint32_t spos[SPL_TILE + 4];       // ids of the warp's round before piece j (see wtot)
+    // ids of the warp's round before piece j.  16 bits: every piece but the tile's last one ends inside the tile, so
+    // the ids in front of any piece of the tile are at most SPL_TILE
+    __align__(16) uint16_t spos[SPL_TILE + 8];
+    uint32_t stage[EM_STAGE];
     uint32_t pbw[SPL_TILE / 32];
     uint32_t wpre[SPL_TILE / 32];
     uint32_t wtot[EM_ROUNDS * EM_WARPS];             // ids of each (round, warp)
     uint32_t wexc[EM_ROUNDS * EM_WARPS];             // ids of the tile before each (round, warp)
-    uint32_t bigpos[EM_BIGCAP], biggp[EM_BIGCAP], bigcnt[EM_BIGCAP];
+    uint16_t bigj[EM_BIGCAP];                        // pieces with more than EM_INLINE ids
     uint32_t n_big;
     uint64_t prefix;
 };
@@ -1432,8 +1445,194 @@ __device__ __forceinline__ uint32_t emit_count(const SplWork& w, uint32_t v, boo
     return (uint32_t)(w.mlist[v & ~SPL_PV_MISS] >> 32) & SPL_ML_LEN_MASK;
 }
 
+// ids [lo, lo + EM_STAGE) of the tile into sm.stage.  CHECK = false: the tile has at most EM_STAGE ids (lo == 0).
+template <bool CHECK>
+__device__ __forceinline__ void emit_stage(const SplWork& w, EmitSmem& sm, const uint32_t* __restrict__ pv, const uint4 v_first,
+                                           const uint32_t P, const uint32_t rounds, const uint32_t my_excl, const uint32_t lo) {
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    auto put = [&](uint32_t pos, uint32_t x) {
+        const uint32_t r = pos - lo;
+        if (!CHECK || r < EM_STAGE) sm.stage[r] = x;
+    };
+    for (uint32_t k = 0; k < rounds; ++k) {
+        const uint32_t j4 = (k * SPL_THREADS + tid) * 4u;
+        const uint32_t base_k = __shfl_sync(FULL, my_excl, k * EM_WARPS + warp);
+        if (j4 >= P) continue;
+        uint32_t pos = sm.spos[j4] + base_k;
+        if (CHECK && lo != 0u && pos >= lo + EM_STAGE) continue;  // all beyond the phase (phase 0 visits every piece: bigj)
+        uint4 v = v_first;
+        if (k > 0 || tid >= 128) v = __ldg(reinterpret_cast<const uint4*>(pv + j4));
+        const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (uint32_t q = 0; q < 4; ++q) {
+            if (j4 + q >= P) break;
+            const uint32_t x = vv[q];
+            if (x < SPL_PV_MISS) put(pos++, x);
+            else if (w.charref && SPL_PV_IS_CHARREF(x)) {
+                const uint32_t* __restrict__ src = w.T->char_ids + (x & 0x0FFFFFFFu);
+                const uint32_t c = ((x >> 28) & 3u) + 1u;
+                for (uint32_t r = 0; r < c; ++r) put(pos + r, __ldg(src + r));
+                pos += c;
+            } else if (x != SPL_PV_NONE) {
+                const uint64_t e = w.mlist[x & ~SPL_PV_MISS];
+                const uint32_t gp = (uint32_t)e, c = (uint32_t)(e >> 32) & SPL_ML_LEN_MASK;
+                if (c <= EM_INLINE) {
+                    for (uint32_t r = 0; r < c; ++r) put(pos + r, w.pool[gp + r]);
+                } else if (lo == 0) {
+                    sm.bigj[atomicAdd(&sm.n_big, 1u)] = (uint16_t)(j4 + q);      // by a warp, after the barrier
+                }
+                pos += c;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(SPL_THREADS, 8) k_emit(SplWork w) {
     __shared__ EmitSmem sm;
+    if (w.counters[SPL_CTR_ERR] & SPL_DEVERR_OFFSETS) {            // rejected offsets: nothing was computed; deliver the flag
+        if (blockIdx.x == 0 && threadIdx.x == 0 && w.host_meta) { w.host_meta[0] = 0; w.host_meta[2] = 0; w.host_meta[1] = w.counters[SPL_CTR_ERR]; }
+        return;
+    }
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t tile = blockIdx.x, tile0 = tile * SPL_TILE;
+    const uint32_t* __restrict__ pv = w.pv + tile0;
+
+    // everything the block needs to know comes from one round of independent loads
+    const uint4 ti = __ldg(reinterpret_cast<const uint4*>(w.tinfo + tile));          // {np, extra, first_doc, -}
+    const uint32_t d1 = __ldg(&w.tinfo[tile + 1].first_doc);
+    uint4 v_first = make_uint4(SPL_PV_NONE, SPL_PV_NONE, SPL_PV_NONE, SPL_PV_NONE);
+    if (tid < 128) v_first = __ldg(reinterpret_cast<const uint4*>(pv + tid * 4u));   // the first 512 pieces: every ordinary tile has them
+    const uint32_t pbw_mine = tid < SPL_TILE / 32 ? __ldg(w.pstart + (tile0 >> 5) + tid) : 0u;
+    if (warp == EM_WARPS - 1) {
+        // ids before this tile: the chunk's prefix plus the tiles of the chunk in front of this one
+        const uint32_t t = (tile & ~(SPL_CHUNK_TILES - 1u)) + lane;
+        uint32_t c = 0;
+        if (t < tile) { const uint4 x = __ldg(reinterpret_cast<const uint4*>(w.tinfo + t)); c = x.x + x.y; }
+        c = __reduce_add_sync(FULL, c);
+        if (lane == 0) sm.prefix = w.chunk_state[tile / SPL_CHUNK_TILES] + c;
+    }
+    const uint32_t P = ti.x, d0 = ti.z;
+    const uint32_t rounds = (P + SPL_THREADS * 4 - 1) / (SPL_THREADS * 4);
+    if (tid == 0) sm.n_big = 0;
+    if (tid < SPL_TILE / 32) sm.pbw[tid] = pbw_mine;
+
+    // ---- pass 1: id count of every piece, warp-level prefixes ---------------------------------------
+    for (uint32_t k = 0; k < rounds; ++k) {
+        const uint32_t j4 = (k * SPL_THREADS + tid) * 4u;
+        if ((k * SPL_THREADS + warp * 32u) * 4u >= P) {            // the whole warp is past the last piece (warp-uniform)
+            if (lane == 31) sm.wtot[k * EM_WARPS + warp] = 0u;
+            continue;
+        }
+        uint4 v = v_first;
+        if ((k > 0 || tid >= 128) && j4 < P) v = __ldg(reinterpret_cast<const uint4*>(pv + j4));
+        const uint32_t c0 = emit_count(w, v.x, j4 < P), c1 = emit_count(w, v.y, j4 + 1 < P),
+                       c2 = emit_count(w, v.z, j4 + 2 < P), c3 = emit_count(w, v.w, j4 + 3 < P);
+        const uint32_t c = c0 + c1 + c2 + c3;
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= (uint32_t)o) incl += t;
+        }
+        const uint32_t ex = incl - c, e1 = ex + c0, e2 = e1 + c1, e3 = e2 + c2;
+        // (an entry behind the tile's last piece -- the one piece whose count is not bounded by the tile -- may be
+        // truncated: it is never read)
+        *reinterpret_cast<uint2*>(&sm.spos[j4]) = make_uint2((ex & 0xFFFFu) | (e1 << 16), (e2 & 0xFFFFu) | (e3 << 16));
+        if (lane == 31) sm.wtot[k * EM_WARPS + warp] = incl;
+    }
+    __syncthreads();
+    // every warp turns the (<= 32) warp totals into exclusive offsets for itself: no serial scan, no second barrier
+    uint32_t my_tot = lane < rounds * EM_WARPS ? sm.wtot[lane] : 0u, my_incl = my_tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(FULL, my_incl, o);
+        if (lane >= (uint32_t)o) my_incl += t;
+    }
+    const uint32_t my_excl = my_incl - my_tot;                   // lane l: ids before (round, warp) pair l
+    const uint32_t tile_total = __shfl_sync(FULL, my_incl, 31);
+    if (d1 > d0) {                                               // for the document offsets at the end (after the next barrier)
+        if (warp == 0) sm.wexc[lane] = my_excl;
+        if (warp == 1) {
+            // word prefixes of the piece bits (document start -> piece index)
+            uint32_t loc[4], run = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { loc[q] = __popc(sm.pbw[lane * 4 + q]); run += loc[q]; }
+            uint32_t incl = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= (uint32_t)o) incl += t;
+            }
+            uint32_t b = incl - run;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { sm.wpre[lane * 4 + q] = b; b += loc[q]; }
+        }
+    }
+
+    // ---- pass 2: ids to their place in the staging buffer, then out in whole lines ------------------------
+    const uint64_t prefix = sm.prefix;
+    uint32_t* __restrict__ out = w.ids + prefix;
+    for (uint32_t lo = 0; lo < tile_total; lo += EM_STAGE) {     // (block-uniform; one phase unless the tile is dense in ids)
+        if (tile_total <= EM_STAGE) emit_stage<false>(w, sm, pv, v_first, P, rounds, my_excl, 0u);
+        else emit_stage<true>(w, sm, pv, v_first, P, rounds, my_excl, lo);
+        __syncthreads();
+        const uint32_t nb = sm.n_big;
+        if (nb) {                                                // one warp per long piece: pool -> staging buffer
+            for (uint32_t b = warp; b < nb; b += EM_WARPS) {
+                const uint32_t j = sm.bigj[b];
+                const uint32_t pos = sm.spos[j] + __shfl_sync(FULL, my_excl, (j / (SPL_THREADS * 4u)) * EM_WARPS + ((j / 128u) & (EM_WARPS - 1u)));
+                const uint64_t e = w.mlist[__ldg(pv + j) & ~SPL_PV_MISS];
+                const uint32_t gp = (uint32_t)e, c = (uint32_t)(e >> 32) & SPL_ML_LEN_MASK;
+                // the part of [pos, pos + c) inside this phase
+                const uint32_t q0 = pos < lo ? lo - pos : 0u;
+                const uint32_t q1 = pos + c > lo + EM_STAGE ? (lo + EM_STAGE > pos ? lo + EM_STAGE - pos : 0u) : c;
+                for (uint32_t q = q0 + lane; q < q1; q += 32) sm.stage[pos + q - lo] = w.pool[gp + q];
+            }
+            __syncthreads();
+        }
+        const uint32_t n = tile_total - lo < EM_STAGE ? tile_total - lo : EM_STAGE;
+        for (uint32_t i = tid; i < n; i += SPL_THREADS) out[lo + i] = sm.stage[i];
+        if (lo + EM_STAGE < tile_total) __syncthreads();         // the buffer is refilled
+    }
+    if (tile_total == 0u) __syncthreads();                       // wexc / wpre for the document offsets
+
+    // ---- output offset of every document that starts in this tile ----------------------------------------
+    for (uint32_t d = d0 + tid; d < d1; d += SPL_THREADS) {
+        const uint32_t x = (uint32_t)(w.doc_off[d] - w.off_base - tile0);
+        const uint32_t pi = sm.wpre[x >> 5] + __popc(sm.pbw[x >> 5] & ((1u << (x & 31)) - 1u));
+        const uint32_t rel = pi >= P ? tile_total : sm.spos[pi] + sm.wexc[(pi / (SPL_THREADS * 4u)) * EM_WARPS + ((pi / 128u) & (EM_WARPS - 1u))];
+        // pipelined host call: the ids of the shard's earlier chunks (kept on the device, so that the host gets
+        // shard-relative offsets in one copy at the end instead of one small copy and a rebase per chunk)
+        const uint64_t base = w.tok_base_in ? *w.tok_base_in : 0ull;
+        w.out_off[d] = base + prefix + rel;
+        if (d == w.n_docs) {
+            if (w.tok_total_out) *w.tok_total_out = base + prefix + rel;
+            if (w.host_meta) {                                 // the call's summary, straight to the host (no copy on this stream)
+                w.host_meta[0] = prefix + rel;
+                w.host_meta[2] = *reinterpret_cast<const uint64_t*>(&w.counters[SPL_CTR_HUGE_POOL]);
+                w.host_meta[1] = w.counters[SPL_CTR_ERR];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_emit_direct: the same with every thread storing its ids straight to global memory (SPL_EMIT_STAGE=0).
+// ------------------------------------------------------------------------------------------
+
+struct EmitDirectSmem {
+    __align__(16) uint32_t spos[SPL_TILE + 4];       // ids of the warp's round before piece j (see wtot)
+    uint32_t pbw[SPL_TILE / 32];
+    uint32_t wpre[SPL_TILE / 32];
+    uint32_t wtot[EM_ROUNDS * EM_WARPS];             // ids of each (round, warp)
+    uint32_t wexc[EM_ROUNDS * EM_WARPS];             // ids of the tile before each (round, warp)
+    uint32_t bigpos[EM_BIGCAP], biggp[EM_BIGCAP], bigcnt[EM_BIGCAP];
+    uint32_t n_big;
+    uint64_t prefix;
+};
+
+__global__ void __launch_bounds__(SPL_THREADS, 8) k_emit_direct(SplWork w) {
+    __shared__ EmitDirectSmem sm;
     if (w.counters[SPL_CTR_ERR] & SPL_DEVERR_OFFSETS) {            // rejected offsets: nothing was computed; deliver the flag
         if (blockIdx.x == 0 && threadIdx.x == 0 && w.host_meta) { w.host_meta[0] = 0; w.host_meta[2] = 0; w.host_meta[1] = w.counters[SPL_CTR_ERR]; }
         return;
@@ -1586,6 +1785,7 @@ void spl_encode_init() {
     cudaFuncSetAttribute(k_probe<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
     cudaFuncSetAttribute(k_probe<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
     cudaFuncSetAttribute(k_emit, cudaFuncAttributePreferredSharedMemoryCarveout, 75);
+    cudaFuncSetAttribute(k_emit_direct, cudaFuncAttributePreferredSharedMemoryCarveout, 75);
     cudaGetLastError();
 }
 
@@ -1594,6 +1794,8 @@ int spl_describe_encode_stage(const SplWork& w, int num_sms, SplLaunchDesc* out)
     static const bool bulk = [] { const char* e = getenv("SPL_PROBE_BULK"); return !e || e[0] != '0'; }();
     // first length class merged by windowed rounds (measured crossover; SPL_BPE_WIN_CLS overrides it for experiments)
     static const uint32_t win_cls = [] { const char* e = getenv("SPL_BPE_WIN_CLS"); return e ? (uint32_t)atoi(e) : SPL_BPE_WIN_CLS; }();
+    // ids assembled in shared memory and written in whole lines, or stored by the thread that has them (A/B)
+    static const bool emit_stage_on = [] { const char* e = getenv("SPL_EMIT_STAGE"); return !e || e[0] != '0'; }();
     // persistent grids, but no larger than the text can feed: a small batch must not pay for launching (and draining)
     // hundreds of idle blocks
     const uint32_t g_bpe = std::min<uint32_t>((uint32_t)num_sms * 6u, std::max<uint32_t>(1u, w.N / 2048u));
@@ -1604,6 +1806,6 @@ int spl_describe_encode_stage(const SplWork& w, int num_sms, SplLaunchDesc* out)
     out[n++] = SplLaunchDesc{(const void*)k_bpe, "k_bpe", g_bpe, SPL_BPE_THREADS, WK_SMEM_BYTES, false, 0};
     out[n++] = SplLaunchDesc{(const void*)k_bpe_long, "k_bpe_long", g_long, SPL_BPE_THREADS, BPE_SMEM_BYTES, true, win_cls};
     out[n++] = SplLaunchDesc{(const void*)k_bpe_fin, "k_bpe_fin", g_fin, SPL_BPE_THREADS, 0, false, 0};      // duplicates + the chunk scan, by its last block
-    out[n++] = SplLaunchDesc{(const void*)k_emit, "k_emit", w.n_tiles, SPL_THREADS, 0, false, 0};
+    out[n++] = SplLaunchDesc{emit_stage_on ? (const void*)k_emit : (const void*)k_emit_direct, "k_emit", w.n_tiles, SPL_THREADS, 0, false, 0};
     return n;
 }

@@ -79,6 +79,26 @@ def test_edge_cases(toks, name):
     assert t.encode_batch(rag) == o.encode_batch(rag)
 
 
+@pytest.mark.parametrize("name", ["cl100k_base", "deepseek_v3"])
+def test_tiles_dense_in_ids(toks, name, monkeypatch):
+    """k_emit assembles a tile's ids in a 3 072-entry buffer: tiles with more ids than that (one id per byte: rare
+    characters that fall apart into byte tokens, alternating one-byte pieces) take several phases, and a long piece
+    may lie across the phase boundary.  Both output paths (SPL_EMIT_STAGE=0: per-thread stores) must agree."""
+    rng = random.Random(99)
+    rare = "龘靐齉爨灪麤鱻饕鼗黻黼黽鼇鼈鼉鼊"
+    texts = ["".join(rng.choice(rare) for _ in range(6000)),                       # 18 000 bytes, mostly 1 id per byte
+             "".join(rng.choice("!?;:") + rng.choice("\n\t") for _ in range(9000)),
+             "".join(rng.choice(rare) for _ in range(900)) + "q" * 700 + "".join(rng.choice(rare) for _ in range(2000)),
+             "".join(chr(rng.randrange(0x80, 0x250)) for _ in range(5000)),
+             " ".join("".join(rng.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(rng.randint(40, 400))) + rng.choice(rare) * 50 for _ in range(120))]
+    want = c_oracle(name).encode_batch(texts)
+    assert toks(name).encode_batch(texts) == want
+    assert max(len(w) / len(t.encode()) for w, t in zip(want, texts)) > 0.8, "no tile of this test is dense in ids"
+    from splintr_b200 import Tokenizer
+    monkeypatch.setenv("SPL_EMIT_STAGE", "0")
+    assert Tokenizer.from_pretrained(name, devices=[0]).encode_batch(texts) == want
+
+
 @pytest.mark.parametrize("name", VOCABS)
 def test_special_tokens(toks, name):
     t, po = toks(name), py_oracle(name)

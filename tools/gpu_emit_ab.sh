@@ -1,0 +1,8 @@
+#!/bin/bash
+# k_emit: ids assembled in shared memory (default) against per-thread stores (SPL_EMIT_STAGE=0).  Usage: bash tools/gpu_emit_ab.sh <tag> "<pytest -k>"
+TAG=${1:-x}; K=${2:-dense}
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build(); g.smoke()" > gpurun_out/smoke_${TAG}.log 2>&1; tail -1 gpurun_out/smoke_${TAG}.log
+timeout 1200 python -m pytest tests -m gpu -x -q -k "$K" > gpurun_out/pytest_gpu_${TAG}.log 2>&1; tail -3 gpurun_out/pytest_gpu_${TAG}.log
+timeout 600 python tools/gpu_cfgs.py > gpurun_out/cfgs_${TAG}.txt 2>&1; cut -c1-300 gpurun_out/cfgs_${TAG}.txt
+SPL_EMIT_STAGE=0 timeout 600 python tools/gpu_cfgs.py > gpurun_out/cfgs_${TAG}_direct.txt 2>&1; cut -c1-300 gpurun_out/cfgs_${TAG}_direct.txt
