@@ -185,6 +185,32 @@ int spl_ingest_jsonl_device(spl_tokenizer* tok, int dev_index, const uint8_t* d_
 int spl_encode_jsonl(spl_tokenizer* tok, const uint8_t* bytes, size_t n_bytes, const char* field, uint32_t flags,
                      spl_result** out, spl_ingest_stats* ingest_stats);
 
+/* ---- ingestion, Parquet: one string column of a Parquet file -> packed text + offsets ---
+ * Replaces the loop a splintr user runs in front of Tokenizer.encode_batch,
+ *     texts = pyarrow.parquet.read_table(path, columns=[column])[column].to_pylist()
+ * and the packing of `texts`.  `bytes` = the whole file in HOST memory: the footer and the page headers are read on the
+ * host (a few hundred bytes per page), the column chunks go to the device as they lie in the file, and pages are
+ * decompressed (snappy) and decoded (PLAIN, dictionary, V1 / V2 data pages, definition levels) there.  `column` =
+ * the leaf's name or dotted path ("text", "meta.body").  One document per row; a null at any level is an EMPTY document.
+ * Supported: BYTE_ARRAY (string / binary) columns that are not repeated; UNCOMPRESSED and SNAPPY.  Anything else the
+ * format allows (other codecs, DELTA_* encodings, lists, encryption) is refused with SPL_ERR_UNSUPPORTED and a message
+ * that names what to rewrite; a damaged file gives SPL_ERR_INVALID_ARG.
+ *
+ * spl_ingest_parquet: outputs in device memory of the caller (d_text_out 16-byte aligned and 16 bytes longer than the
+ * text if it is to be fed to spl_encode_batch_device; d_offsets_out: rows + 1 entries).  The sizes are not known in
+ * advance (a dictionary page can expand): with too small a capacity -- or NULL outputs -- nothing is written, the needed
+ * sizes are in *stats (n_docs rows, n_text_bytes) and SPL_ERR_INVALID_ARG is returned (NULL outputs: SPL_OK).  The
+ * column must fit one device pass (4 GiB of text).  stats: n_lines = n_docs = rows. */
+int spl_ingest_parquet(spl_tokenizer* tok, int dev_index, const uint8_t* bytes, size_t n_bytes, const char* column,
+                       uint8_t* d_text_out, size_t text_capacity, uint64_t* d_offsets_out, size_t offsets_capacity,
+                       void* cuda_stream, spl_ingest_stats* stats);
+
+/* spl_encode_batch for one string column of a Parquet file held in host memory: runs of row groups (about 1 GiB of
+ * column data each) are ingested and encoded on the handle's first device, their ids copied out.  The result is the
+ * object spl_encode_batch returns (one document per row). */
+int spl_encode_parquet(spl_tokenizer* tok, const uint8_t* bytes, size_t n_bytes, const char* column, uint32_t flags,
+                       spl_result** out, spl_ingest_stats* ingest_stats);
+
 /* number of kernels one spl_encode_batch_device call launches for these flags */
 int spl_launches_per_call(const spl_tokenizer* tok, uint32_t flags);
 

@@ -13,8 +13,8 @@ from typing import List, Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libsplintr_b200.so")
-SOURCES = ["spl_api.cu", "spl_kernels.cu", "spl_encode.cu", "spl_decode.cu", "spl_sentencepiece.cu", "spl_ingest.cu", "spl_host.cpp"]
-HEADERS = ["spl_common.h", "spl_segment.h", "spl_pretok.h", "spl_pretok_fast.h", "spl_sentencepiece.h", "spl_ingest.h", "spl_host.h", "spl_kernels.cuh", "spl_device.cuh", "spl_fast_dev.cuh", "spl_bpe_bits.h", "unicode_tables.inc",
+SOURCES = ["spl_api.cu", "spl_kernels.cu", "spl_encode.cu", "spl_decode.cu", "spl_sentencepiece.cu", "spl_ingest.cu", "spl_parquet.cu", "spl_parquet_meta.cpp", "spl_host.cpp"]
+HEADERS = ["spl_common.h", "spl_segment.h", "spl_pretok.h", "spl_pretok_fast.h", "spl_sentencepiece.h", "spl_ingest.h", "spl_parquet.h", "spl_parquet_meta.h", "spl_special.h", "spl_host.h", "spl_kernels.cuh", "spl_device.cuh", "spl_fast_dev.cuh", "spl_bpe_bits.h", "unicode_tables.inc",
            os.path.join("..", "..", "include", "splintr_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -114,7 +114,7 @@ EXPORTS = ["spl_create", "spl_destroy", "spl_last_error", "spl_encode_batch", "s
            "spl_result_free", "spl_encode_batch_device", "spl_launches_per_call", "spl_alloc_pinned",
            "spl_free_pinned", "spl_version", "spl_set_profiling", "spl_last_kernel_times",
            "spl_decode_batch", "spl_decode_batch_device", "spl_result_bytes", "spl_result_n_bytes",
-           "spl_ingest_jsonl_device", "spl_encode_jsonl", "spl_device_status", "spl_debug_counters"]
+           "spl_ingest_jsonl_device", "spl_encode_jsonl", "spl_ingest_parquet", "spl_encode_parquet", "spl_device_status", "spl_debug_counters"]
 
 SPL_OK, SPL_ERR_INVALID_ARG, SPL_ERR_VOCAB, SPL_ERR_CUDA, SPL_ERR_OOM, SPL_ERR_UNSUPPORTED, SPL_ERR_NO_DEVICE = \
     0, -1, -2, -3, -4, -5, -6
@@ -177,6 +177,12 @@ def load() -> ctypes.CDLL:
     lib.spl_encode_jsonl.restype = ctypes.c_int
     lib.spl_encode_jsonl.argtypes = [vp, u8p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_uint32, ctypes.POINTER(vp),
                                      ctypes.POINTER(SplIngestStats)]
+    lib.spl_ingest_parquet.restype = ctypes.c_int
+    lib.spl_ingest_parquet.argtypes = [vp, ctypes.c_int, u8p, ctypes.c_size_t, ctypes.c_char_p, u8p, ctypes.c_size_t,
+                                       u64p, ctypes.c_size_t, vp, ctypes.POINTER(SplIngestStats)]
+    lib.spl_encode_parquet.restype = ctypes.c_int
+    lib.spl_encode_parquet.argtypes = [vp, u8p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_uint32, ctypes.POINTER(vp),
+                                       ctypes.POINTER(SplIngestStats)]
     lib.spl_launches_per_call.restype = ctypes.c_int
     lib.spl_launches_per_call.argtypes = [vp, ctypes.c_uint32]
     lib.spl_set_profiling.restype = ctypes.c_int

@@ -14,6 +14,7 @@
 #include "../../include/splintr_b200.h"
 #include "spl_host.h"
 #include "spl_kernels.cuh"
+#include "spl_parquet_meta.h"
 #include "unicode_tables.inc"
 
 namespace {
@@ -62,6 +63,7 @@ struct DevCtx {
     DevBuf jl_tiles, jl_lines;                                   // spl_ingest_jsonl_device: tile counts, per-line arrays
     DevBuf jl_text, jl_off, jl_out_off[2];                       // spl_encode_jsonl: ingested text + offsets, output offsets (alternating)
     DevBuf run_tot;                                              // spl_encode_batch: cumulative id count after each pipeline chunk
+    DevBuf pq_stage, pq_scratch, pq_pages, pq_rows, pq_dict, pq_small;   // Parquet ingestion: staged column chunks, decompressed pages, page descriptors, spans, block sums + counters
     DevBuf sp_zero, sp_tiles, sp_text, sp_doc;                   // SentencePiece mode: bitmaps over T, tile counts, T', offsets in T'
     size_t huge_words = 0;
     // the kernels of one pipeline chunk as ONE graph launch (spl_encode_batch): [with_special]
@@ -1429,6 +1431,248 @@ int spl_encode_jsonl(spl_tokenizer* tk, const uint8_t* bytes, size_t n_bytes, co
     r->stats.n_docs = docs; r->stats.n_bytes = n_bytes; r->stats.n_tokens = total;
     r->stats.total_ms = t; r->stats.n_devices = 1; r->stats.n_launches = launches;
     if (ingest_stats) *ingest_stats = tot;
+    give_pinned(tk, meta_buf);
+    *out = r;
+    return SPL_OK;
+}
+
+// ---- ingestion (row N4): Parquet string column -> packed text + offsets -----------------------------------------
+
+}  // extern "C"
+
+namespace {
+
+struct PqOut { uint8_t* text; size_t text_cap; uint64_t* off; size_t off_cap; };
+
+// One batch (a run of row groups) of the planned column on `st`: column chunks host -> device as they lie in the file,
+// pages -> row spans -> offsets (one synchronisation: the text size), `outputs(text_bytes, o)` names the buffers, rows ->
+// packed text.  The batch's offsets start at 0.
+template <class OutFn>
+int ingest_parquet_batch(spl_tokenizer* tk, DevCtx& dc, cudaStream_t st, const uint8_t* file, const SplPqPlan& plan,
+                         const SplPqBatch& b, OutFn outputs, uint64_t& text_bytes, int& launches, uint64_t& h2d) {
+    int rc;
+    const size_t n_pages = b.page1 - b.page0;
+    const uint32_t n_blocks = (uint32_t)std::max<uint64_t>(1, (b.n_rows + 2047) / 2048);
+    if ((rc = dc.pq_stage.ensure((size_t)b.stage_bytes + 64, tk->err))) return rc;
+    if ((rc = dc.pq_scratch.ensure((size_t)b.scratch_bytes + 64, tk->err))) return rc;
+    if ((rc = dc.pq_pages.ensure((n_pages + 1) * sizeof(SplPqPage), tk->err))) return rc;
+    if ((rc = dc.pq_rows.ensure((size_t)(b.n_rows + 2) * 12 + 64, tk->err))) return rc;
+    if ((rc = dc.pq_dict.ensure((size_t)(b.dict_entries + 2) * 12 + 64, tk->err))) return rc;
+    if ((rc = dc.pq_small.ensure(256 + ((size_t)n_blocks + 2) * 8, tk->err))) return rc;
+    if ((rc = dc.jl_off.ensure((size_t)(b.n_rows + 2) * 8, tk->err))) return rc;
+    SplPqWork w;
+    memset(&w, 0, sizeof(w));
+    w.file = (const uint8_t*)dc.pq_stage.p; w.scratch = (uint8_t*)dc.pq_scratch.p;
+    w.pages = (const SplPqPage*)dc.pq_pages.p;
+    w.row_off = (uint64_t*)dc.pq_rows.p; w.row_len = (uint32_t*)((uint8_t*)dc.pq_rows.p + align_up((size_t)(b.n_rows + 1) * 8, 16));
+    w.dict_off = (uint64_t*)dc.pq_dict.p; w.dict_len = (uint32_t*)((uint8_t*)dc.pq_dict.p + align_up((size_t)(b.dict_entries + 1) * 8, 16));
+    w.n_rows = b.n_rows; w.n_blocks = n_blocks;
+    w.counters = (uint32_t*)dc.pq_small.p; w.bsum = (unsigned long long*)((uint8_t*)dc.pq_small.p + 256);
+    w.out_off = (uint64_t*)dc.jl_off.p;
+    CUDA_TRY(cudaMemsetAsync(dc.pq_small.p, 0, 256, st), tk->err);
+    for (size_t k = b.range0; k < b.range1; ++k) {
+        const SplPqRange& r = plan.ranges[k];
+        CUDA_TRY(cudaMemcpyAsync((uint8_t*)dc.pq_stage.p + r.stage_off, file + r.file_off, (size_t)r.len, cudaMemcpyHostToDevice, st), tk->err);
+        h2d += r.len;
+    }
+    bool has_dict = false;
+    for (size_t k = b.page0; k < b.page1; ++k) has_dict |= plan.pages[k].kind == SPL_PQ_DICT;
+    if (n_pages) CUDA_TRY(cudaMemcpyAsync(dc.pq_pages.p, plan.pages.data() + b.page0, n_pages * sizeof(SplPqPage), cudaMemcpyHostToDevice, st), tk->err);
+    launches += spl_launch_pq_spans(w, 0, (uint32_t)n_pages, has_dict, st);
+    if (n_pages == 0) CUDA_TRY(cudaMemsetAsync(dc.jl_off.p, 0, 8, st), tk->err);            // no rows: offsets = {0}
+    CUDA_TRY(cudaGetLastError(), tk->err);
+    uint32_t h_ctr[8];
+    CUDA_TRY(cudaMemcpyAsync(h_ctr, w.counters, sizeof(h_ctr), cudaMemcpyDeviceToHost, st), tk->err);
+    CUDA_TRY(cudaStreamSynchronize(st), tk->err);
+    if (h_ctr[SPL_PQCTR_ERR]) {
+        const uint32_t e = h_ctr[SPL_PQCTR_ERR];
+        tk->err = std::string("parquet: damaged page (") + ((e & SPL_PQ_ERR_SNAPPY) ? "snappy stream " : "") + ((e & SPL_PQ_ERR_LEVELS) ? "definition levels " : "") +
+                  ((e & SPL_PQ_ERR_VALUES) ? "values " : "") + ((e & SPL_PQ_ERR_DICT_INDEX) ? "dictionary index " : "") + "do not decode)";
+        return SPL_ERR_INVALID_ARG;
+    }
+    memcpy(&text_bytes, &h_ctr[SPL_PQCTR_TEXT], 8);
+    PqOut o{nullptr, 0, nullptr, 0};
+    if ((rc = outputs(text_bytes, o))) return rc;
+    if (o.off && o.off != (uint64_t*)dc.jl_off.p)
+        CUDA_TRY(cudaMemcpyAsync(o.off, dc.jl_off.p, (size_t)(b.n_rows + 1) * 8, cudaMemcpyDeviceToDevice, st), tk->err);
+    if (o.text) {
+        w.out_text = o.text;
+        launches += spl_launch_pq_copy(w, text_bytes, st);
+        CUDA_TRY(cudaGetLastError(), tk->err);
+    }
+    return SPL_OK;
+}
+
+int plan_parquet(spl_tokenizer* tk, const uint8_t* bytes, size_t n_bytes, const char* column, uint64_t batch_bytes, SplPqPlan& plan) {
+    if (!spl_pq_plan(bytes, n_bytes, column, batch_bytes, plan)) {
+        tk->err = plan.err;
+        return plan.unsupported ? SPL_ERR_UNSUPPORTED : SPL_ERR_INVALID_ARG;
+    }
+    return SPL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int spl_ingest_parquet(spl_tokenizer* tk, int dev_index, const uint8_t* bytes, size_t n_bytes, const char* column,
+                       uint8_t* d_text_out, size_t text_capacity, uint64_t* d_offsets_out, size_t offsets_capacity,
+                       void* cuda_stream, spl_ingest_stats* stats) {
+    if (!tk) return SPL_ERR_INVALID_ARG;
+    if (dev_index < 0 || (size_t)dev_index >= tk->devs.size() || !stats || !column || !column[0] || (n_bytes && !bytes)) {
+        tk->err = "invalid argument (null pointer, empty column name, or device index out of range)";
+        return SPL_ERR_INVALID_ARG;
+    }
+    memset(stats, 0, sizeof(*stats));
+    SplPqPlan plan;
+    int rc = plan_parquet(tk, bytes, n_bytes, column, ~0ull, plan);          // one batch, whatever its size
+    if (rc) return rc;
+    if (plan.batches.size() > 1) { tk->err = "parquet: the column does not fit one device pass (spl_encode_parquet works batch by batch)"; return SPL_ERR_UNSUPPORTED; }
+    DeviceGuard guard;
+    DevCtx& dc = tk->devs[dev_index];
+    CUDA_TRY(cudaSetDevice(dc.device), tk->err);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    stats->n_lines = stats->n_docs = plan.n_rows;
+    SplPqBatch empty;
+    memset(&empty, 0, sizeof(empty));
+    const SplPqBatch& b = plan.batches.empty() ? empty : plan.batches[0];
+    uint64_t text_bytes = 0, h2d = 0;
+    int launches = 0;
+    bool small = false;
+    rc = ingest_parquet_batch(tk, dc, st, bytes, plan, b, [&](uint64_t tb, PqOut& o) {
+        stats->n_text_bytes = tb;
+        small = (d_text_out && tb > text_capacity) || (d_offsets_out && plan.n_rows + 1 > offsets_capacity);
+        if (!small) o = PqOut{d_text_out, text_capacity, d_offsets_out, offsets_capacity};
+        return SPL_OK;
+    }, text_bytes, launches, h2d);
+    if (rc) return rc;
+    stats->n_launches = launches;
+    CUDA_TRY(cudaStreamSynchronize(st), tk->err);
+    if (small) { tk->err = "output capacity too small (the needed sizes are in the stats)"; return SPL_ERR_INVALID_ARG; }
+    return SPL_OK;
+}
+
+// File bytes in host memory -> ids in host memory: spl_encode_batch for one string column of a Parquet file, one
+// document per row.  Batch by batch (runs of row groups): column chunks in, pages decoded and rows packed on the
+// device, encoded there, ids and offsets out.  One device (the handle's first).
+int spl_encode_parquet(spl_tokenizer* tk, const uint8_t* bytes, size_t n_bytes, const char* column, uint32_t flags,
+                       spl_result** out, spl_ingest_stats* ingest_stats) {
+    if (!tk || !out) return SPL_ERR_INVALID_ARG;
+    *out = nullptr;
+    if ((n_bytes && !bytes) || !column || !column[0]) { tk->err = "invalid argument (null bytes or empty column name)"; return SPL_ERR_INVALID_ARG; }
+    bool with_special;
+    int rc = check_special_support(tk, flags, with_special);
+    if (rc) return rc;
+    SplPqPlan plan;
+    const uint64_t batch_target = tk->chunk_bytes ? tk->chunk_bytes : (1ull << 30) / (is_sentencepiece(tk) ? 3 : 1);
+    if ((rc = plan_parquet(tk, bytes, n_bytes, column, batch_target, plan))) return rc;
+
+    DeviceGuard guard;
+    DevCtx& dc = tk->devs[0];
+    CUDA_TRY(cudaSetDevice(dc.device), tk->err);
+    spl_result* r = new (std::nothrow) spl_result();
+    if (!r) return SPL_ERR_OOM;
+    memset(&r->stats, 0, sizeof(r->stats));
+    r->owner = tk; r->n_docs = 0; r->n_tokens = 0;
+    r->ids_buf = PinnedBuf{nullptr, 0};
+    r->off_buf = take_pinned(tk, (size_t)(plan.n_rows + 2) * 8);
+    PinnedBuf meta_buf = take_pinned(tk, 64);
+    static thread_local int pq_depth = 0;
+    auto fail = [&](int code) {
+        cudaStreamSynchronize(dc.stream);
+        cudaGetLastError();
+        give_pinned(tk, r->off_buf); give_pinned(tk, r->ids_buf); give_pinned(tk, meta_buf);
+        delete r;
+        if (code == SPL_ERR_OOM + 1000) {                      // huge-piece scratch was too small and has been enlarged
+            if (pq_depth >= 3) return (int)SPL_ERR_OOM;
+            ++pq_depth;
+            const int rc2 = spl_encode_parquet(tk, bytes, n_bytes, column, flags, out, ingest_stats);
+            --pq_depth;
+            return rc2;
+        }
+        return code;
+    };
+    if (!r->off_buf.p || !meta_buf.p) { tk->err = "pinned host allocation failed"; return fail(SPL_ERR_OOM); }
+    void* d_meta = nullptr;
+    if (cudaHostGetDevicePointer(&d_meta, meta_buf.p, 0) != cudaSuccess) { cudaGetLastError(); tk->err = "pinned host memory is not mapped"; return fail(SPL_ERR_CUDA); }
+    volatile uint64_t* meta = (volatile uint64_t*)meta_buf.p;
+    uint64_t* res_off = (uint64_t*)r->off_buf.p;
+    uint64_t total = 0, docs = 0, text_total = 0, h2d = 0;
+    int launches = 0;
+    auto run = [&]() -> int {
+        int rc2;
+        if ((rc2 = dc.run_tot.ensure(16, tk->err))) return rc2;
+        uint64_t* run_tot = (uint64_t*)dc.run_tot.p;
+        CUDA_TRY(cudaEventRecord(dc.ev[0], dc.stream), tk->err);
+        for (const SplPqBatch& b : plan.batches) {
+            uint64_t tb = 0;
+            rc2 = ingest_parquet_batch(tk, dc, dc.stream, bytes, plan, b, [&](uint64_t text_bytes, PqOut& o) {
+                if (text_bytes > kMaxShardBytes / (is_sentencepiece(tk) ? 3 : 1)) {
+                    tk->err = "parquet: a batch of row groups expands to more text than one device pass takes (dictionary-encoded column): write smaller row groups";
+                    return (int)SPL_ERR_UNSUPPORTED;
+                }
+                int e = dc.jl_text.ensure((size_t)text_bytes + 64, tk->err);
+                o = PqOut{(uint8_t*)dc.jl_text.p, dc.jl_text.cap, (uint64_t*)dc.jl_off.p, (size_t)b.n_rows + 1};
+                return e;
+            }, tb, launches, h2d);
+            if (rc2) return rc2;
+            text_total += tb;
+            if (tb == 0) {                                         // rows, but no text: every document of the batch is empty
+                for (uint64_t i = 0; i <= b.n_rows; ++i) res_off[docs + i] = total;
+                docs += b.n_rows;
+                continue;
+            }
+            const uint64_t cap = ids_bound(tk, tb);
+            if ((rc2 = dc.ids.ensure((size_t)(cap + 16) * 4, tk->err))) return rc2;
+            if ((rc2 = dc.jl_out_off[0].ensure((size_t)(b.n_rows + 2) * 8, tk->err))) return rc2;
+            CUDA_TRY(cudaMemcpyAsync(run_tot, &total, 8, cudaMemcpyHostToDevice, dc.stream), tk->err);   // ids of the batches in front
+            SplWork w;
+            EncodeArgs ea{(const uint8_t*)dc.jl_text.p, tb, (const uint64_t*)dc.jl_off.p, 0, b.n_rows,
+                          (uint32_t*)dc.ids.p, cap, (uint64_t*)dc.jl_out_off[0].p, (uint64_t*)d_meta, run_tot, run_tot + 1};
+            meta[0] = meta[1] = meta[2] = 0;
+            if ((rc2 = enqueue_encode(tk, dc, dc.stream, ea, with_special, nullptr, w, launches))) return rc2;
+            CUDA_TRY(cudaGetLastError(), tk->err);
+            CUDA_TRY(cudaStreamSynchronize(dc.stream), tk->err);
+            const uint32_t errbits = (uint32_t)meta[1];
+            if (errbits & SPL_DEVERR_HUGE_POOL) {
+                dc.huge_words = std::max<size_t>(dc.huge_words * 2, (size_t)meta[2] + 1024);
+                tk->err = "scratch pool for very long pieces exhausted";
+                return SPL_ERR_OOM + 1000;
+            }
+            if (errbits) { tk->err = "device error flags set by the encode kernels"; return SPL_ERR_CUDA; }
+            const uint64_t n_tok = meta[0];
+            if ((total + n_tok + 16) * 4 > r->ids_buf.cap) {
+                uint64_t est = plan.batches.size() > 1 ? (uint64_t)((double)(total + n_tok) * 1.25 * (double)plan.n_rows / (double)std::max<uint64_t>(docs + b.n_rows, 1)) : 0;
+                PinnedBuf nb = take_pinned(tk, (size_t)(std::max<uint64_t>(est, total + n_tok) + 16) * 4);
+                if (!nb.p) { tk->err = "pinned host allocation failed"; return SPL_ERR_OOM; }
+                if (r->ids_buf.p) { memcpy(nb.p, r->ids_buf.p, (size_t)total * 4); give_pinned(tk, r->ids_buf); }
+                r->ids_buf = nb;
+            }
+            if (n_tok) CUDA_TRY(cudaMemcpyAsync((uint32_t*)r->ids_buf.p + total, dc.ids.p, (size_t)n_tok * 4, cudaMemcpyDeviceToHost, dc.stream), tk->err);
+            CUDA_TRY(cudaMemcpyAsync(res_off + docs, dc.jl_out_off[0].p, (size_t)(b.n_rows + 1) * 8, cudaMemcpyDeviceToHost, dc.stream), tk->err);
+            CUDA_TRY(cudaStreamSynchronize(dc.stream), tk->err);
+            r->stats.d2h_bytes += n_tok * 4 + (b.n_rows + 1) * 8 + 24;
+            total += n_tok; docs += b.n_rows;
+        }
+        CUDA_TRY(cudaEventRecord(dc.ev[3], dc.stream), tk->err);
+        CUDA_TRY(cudaStreamSynchronize(dc.stream), tk->err);
+        return SPL_OK;
+    };
+    if ((rc = run())) return fail(rc);
+    if (!r->ids_buf.p) {
+        r->ids_buf = take_pinned(tk, 64);
+        if (!r->ids_buf.p) { tk->err = "pinned host allocation failed"; return fail(SPL_ERR_OOM); }
+    }
+    res_off[docs] = total;
+    float t = 0;
+    cudaEventElapsedTime(&t, dc.ev[0], dc.ev[3]);
+    r->n_docs = (size_t)docs; r->n_tokens = (size_t)total;
+    r->stats.n_docs = docs; r->stats.n_bytes = text_total; r->stats.n_tokens = total; r->stats.h2d_bytes = h2d;
+    r->stats.total_ms = t; r->stats.n_devices = 1; r->stats.n_launches = launches;
+    if (ingest_stats) {
+        memset(ingest_stats, 0, sizeof(*ingest_stats));
+        ingest_stats->n_lines = ingest_stats->n_docs = docs; ingest_stats->n_text_bytes = text_total; ingest_stats->n_launches = launches;
+    }
     give_pinned(tk, meta_buf);
     *out = r;
     return SPL_OK;

@@ -182,6 +182,26 @@ struct SplJlWork {
 int spl_launch_jsonl_count(const SplJlWork& w, cudaStream_t stream);     // k_jl_count, k_jl_scan
 int spl_launch_jsonl_extract(const SplJlWork& w, cudaStream_t stream);   // k_jl_lines, k_jl_parse, k_jl_scan2, k_jl_emit
 
+// spl_parquet.cu: the pages of one Parquet string column -> packed text + offsets (row N4; formats: spl_parquet.h)
+#define SPL_PQCTR_ERR 0                // SPL_PQ_ERR_* bits
+#define SPL_PQCTR_TEXT 2               // (64-bit) bytes of packed text
+struct SplPqPage;
+struct SplPqWork {
+    const uint8_t* file;               // staged file bytes (the column chunks of the batch), padded by 16 bytes
+    uint8_t* scratch;                  // decompressed pages, padded by 16 bytes
+    const SplPqPage* pages;
+    uint64_t* row_off; uint32_t* row_len;      // [n_rows] span of every row
+    uint64_t* dict_off; uint32_t* dict_len;    // [dict entries of the batch]
+    uint64_t n_rows;
+    uint32_t n_blocks;                 // max(1, ceil(n_rows / 2048))
+    unsigned long long* bsum;          // [n_blocks + 1]
+    uint32_t* counters;                // SPL_PQCTR_* (zero-initialised, 8 words)
+    uint8_t* out_text;                 // packed text (known size: counters[SPL_PQCTR_TEXT] after spl_launch_pq_spans)
+    uint64_t* out_off;                 // [n_rows + 1]
+};
+int spl_launch_pq_spans(const SplPqWork& w, uint32_t first_page, uint32_t n_pages, bool has_dict, cudaStream_t stream);
+int spl_launch_pq_copy(const SplPqWork& w, uint64_t text_bytes, cudaStream_t stream);
+
 // spl_decode.cu: ids -> bytes (row N2)
 #define SPL_DEC_TILE 2048u            // ids per tile
 struct SplDecLaunch {

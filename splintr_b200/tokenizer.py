@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import base64
 import ctypes
+import os
 import threading
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
@@ -369,28 +370,28 @@ class Tokenizer:
         stats = {f: getattr(st, f) for f, _ in _lib.SplIngestStats._fields_}
         return text[:int(st.n_text_bytes)], offs[:int(st.n_docs) + 1], stats
 
-    def encode_jsonl(self, data, field: str = "text", with_special: bool = False, return_stats: bool = False):
-        """spl_encode_jsonl: the bytes of a JSON Lines file (bytes / bytearray / numpy uint8 / integer host address
-        with `nbytes=` folded into a (address, nbytes) tuple) -> (ids uint32, offsets uint64): chunks of the raw file
-        are copied to the device, member extraction + unescaping and the encode run there, ids come back --
-        the `[json.loads(l)[field] for l in f]` loop and the packing of its result never run on the host."""
-        lib = _lib.load()
+    @staticmethod
+    def _host_bytes(data):
+        """bytes / bytearray / numpy uint8 / (address, nbytes) / a path -> (object to keep alive, void pointer, size)"""
         if isinstance(data, tuple):
-            keep, (addr, n) = None, data
-            ptr = ctypes.c_void_p(addr)
-        elif isinstance(data, (bytes, bytearray)):
+            addr, n = data
+            return None, ctypes.c_void_p(addr), int(n)
+        if isinstance(data, (str, os.PathLike)):
+            data = np.fromfile(data, dtype=np.uint8)
+        if isinstance(data, (bytes, bytearray)):
             keep = bytes(data)
-            n = len(keep)
-            ptr = ctypes.cast(ctypes.c_char_p(keep), ctypes.c_void_p)
-        else:
-            keep = np.ascontiguousarray(data, dtype=np.uint8)
-            n = int(keep.shape[0])
-            ptr = ctypes.c_void_p(keep.ctypes.data)
+            return keep, ctypes.cast(ctypes.c_char_p(keep), ctypes.c_void_p), len(keep)
+        keep = np.ascontiguousarray(data, dtype=np.uint8)
+        return keep, ctypes.c_void_p(keep.ctypes.data), int(keep.shape[0])
+
+    def _encode_file(self, fn_name: str, data, member: str, with_special: bool, return_stats: bool):
+        lib = _lib.load()
+        keep, ptr, n = self._host_bytes(data)
         res = ctypes.c_void_p()
         ist = _lib.SplIngestStats()
         with self._lock:
-            rc = lib.spl_encode_jsonl(self._handle, ptr, n, field.encode("utf-8"),
-                                      _lib.SPL_ENCODE_WITH_SPECIAL if with_special else 0, ctypes.byref(res), ctypes.byref(ist))
+            rc = getattr(lib, fn_name)(self._handle, ptr, n, member.encode("utf-8"),
+                                       _lib.SPL_ENCODE_WITH_SPECIAL if with_special else 0, ctypes.byref(res), ctypes.byref(ist))
             msg = _lib.last_error(self._handle) if rc != _lib.SPL_OK else ""
         del keep
         if rc != _lib.SPL_OK:
@@ -413,6 +414,91 @@ class Tokenizer:
             return ids, out_off
         finally:
             lib.spl_result_free(res)
+
+    def encode_jsonl(self, data, field: str = "text", with_special: bool = False, return_stats: bool = False):
+        """spl_encode_jsonl: the bytes of a JSON Lines file (bytes / bytearray / numpy uint8 / a path / integer host
+        address folded into a (address, nbytes) tuple) -> (ids uint32, offsets uint64): chunks of the raw file
+        are copied to the device, member extraction + unescaping and the encode run there, ids come back --
+        the `[json.loads(l)[field] for l in f]` loop and the packing of its result never run on the host."""
+        return self._encode_file("spl_encode_jsonl", data, field, with_special, return_stats)
+
+    def encode_parquet(self, data, column: str = "text", with_special: bool = False, return_stats: bool = False):
+        """spl_encode_parquet: a Parquet file (bytes / numpy uint8 / a path / (address, nbytes)) -> (ids uint32,
+        offsets uint64), one document per row of the string column `column` ("text", or a dotted path into structs);
+        a null row is an empty document.  The host only reads the footer and the page headers; the column chunks go
+        to the device as they lie in the file and are decompressed (snappy) and decoded there -- the
+        `pq.read_table(path)[column].to_pylist()` in front of encode_batch never runs.  ValueError for what the
+        reader does not take (other codecs, DELTA encodings, list columns), with what to rewrite."""
+        return self._encode_file("spl_encode_parquet", data, column, with_special, return_stats)
+
+    def ingest_parquet(self, data, column: str = "text", dev_index: int = 0):
+        """spl_ingest_parquet: the same decoding without the encode -> (text uint8 CUDA tensor -- a view of a 16-byte
+        padded buffer, ready for encode_device --, offsets int64[rows + 1] CUDA tensor, stats dict)."""
+        import torch
+        lib = _lib.load()
+        keep, ptr, n = self._host_bytes(data)
+        dev = torch.device("cuda", self._devices[dev_index] if self._devices else torch.cuda.current_device())
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        st = _lib.SplIngestStats()
+
+        def call(text, offs):
+            with self._lock:
+                rc = lib.spl_ingest_parquet(self._handle, dev_index, ptr, n, column.encode("utf-8"),
+                                            ctypes.c_void_p(text.data_ptr()) if text is not None else None, int(text.numel()) - 32 if text is not None else 0,
+                                            ctypes.c_void_p(offs.data_ptr()) if offs is not None else None, int(offs.numel()) if offs is not None else 0,
+                                            ctypes.c_void_p(stream), ctypes.byref(st))
+                msg = _lib.last_error(self._handle) if rc != _lib.SPL_OK else ""
+            return rc, msg
+
+        rc, msg = call(None, None)                       # sizes first (a dictionary-encoded column can expand)
+        text = offs = None
+        if rc == _lib.SPL_OK:
+            nt, nr = int(st.n_text_bytes), int(st.n_docs)
+            text = torch.empty(nt + ((-nt) % 16) + 32, dtype=torch.uint8, device=dev)
+            offs = torch.empty(nr + 1, dtype=torch.int64, device=dev)
+            rc, msg = call(text, offs)
+        del keep
+        if rc != _lib.SPL_OK:
+            if rc in (_lib.SPL_ERR_INVALID_ARG, _lib.SPL_ERR_UNSUPPORTED):
+                raise ValueError(msg)
+            raise RuntimeError(f"splintr_b200: {msg} (code {rc})")
+        stats = {f: getattr(st, f) for f, _ in _lib.SplIngestStats._fields_}
+        return text[:int(st.n_text_bytes)], offs, stats
+
+    def encode_arrow(self, column, with_special: bool = False):
+        """An Arrow string column (pyarrow StringArray / LargeStringArray / ChunkedArray of them) -> (ids uint32,
+        offsets uint64), one document per element, a null an empty document.  An Arrow string array IS the packed
+        layout of spl_encode_batch -- one data buffer + offsets -- so nothing is copied or packed on the host beyond
+        widening 32-bit offsets: the data buffer goes to the device as it is (encode_batch_packed)."""
+        import pyarrow as pa
+        chunks = column.chunks if isinstance(column, pa.ChunkedArray) else [column]
+        ids_parts, off_parts, base = [], [np.zeros(1, dtype=np.uint64)], 0
+        for a in chunks:
+            if pa.types.is_string(a.type) or pa.types.is_binary(a.type):
+                odt = np.int32
+            elif pa.types.is_large_string(a.type) or pa.types.is_large_binary(a.type):
+                odt = np.int64
+            else:
+                raise TypeError(f"encode_arrow needs a string column, got {a.type}")
+            if len(a) == 0:
+                continue
+            bufs = a.buffers()
+            o = np.frombuffer(bufs[1], dtype=odt)[a.offset:a.offset + len(a) + 1].astype(np.uint64)
+            if a.null_count:                                       # a null slot may hold any bytes: make it empty
+                lens = np.diff(o)
+                lens[~np.asarray(a.is_valid())] = 0
+                if int(lens.sum()) != int(o[-1] - o[0]):          # some null slot was not empty: repack those bytes out
+                    a = pa.array(["" if v is None else v for v in a.to_pylist()], type=a.type)
+                    bufs = a.buffers()
+                    o = np.frombuffer(bufs[1], dtype=odt)[:len(a) + 1].astype(np.uint64)
+            lo, hi = int(o[0]), int(o[-1])
+            data = np.frombuffer(bufs[2], dtype=np.uint8)[lo:hi] if bufs[2] is not None else np.zeros(0, dtype=np.uint8)
+            ids, off = self.encode_packed(data, o - np.uint64(lo), with_special)
+            ids_parts.append(ids)
+            off_parts.append(off[1:] + np.uint64(base))
+            base += int(off[-1])
+        ids = np.concatenate(ids_parts) if ids_parts else np.zeros(0, dtype=np.uint32)
+        return ids, np.concatenate(off_parts)
 
     def set_profiling(self, enable: bool = True) -> None:
         _lib.load().spl_set_profiling(self._handle, int(enable))

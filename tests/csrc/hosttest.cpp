@@ -424,6 +424,47 @@ extern "C" int ht_jsonl(const uint8_t* text, uint32_t n, const char* field, uint
     return 0;
 }
 
+// ---- Parquet ingestion (row N4): the host plan (spl_parquet_meta.cpp) and the page decoder of spl_parquet.h with a
+// lane group of one, batch by batch, as spl_api.cu drives the device.  Returns the row count, or -1 (malformed: err),
+// -2 (unsupported: err), -3 (a page raised error bits: info[0]), -4 (capacities).  info[1] = batches, info[2] = pages.
+#include "../../splintr_b200/csrc/spl_parquet_meta.h"
+extern "C" long ht_parquet(const uint8_t* file, size_t n, const char* column, uint64_t batch_bytes,
+                           uint8_t* out_text, size_t text_cap, uint64_t* out_off, size_t off_cap,
+                           char* err, size_t err_cap, uint64_t* info) {
+    SplPqPlan plan;
+    info[0] = info[1] = info[2] = 0;
+    if (!spl_pq_plan(file, n, column, batch_bytes, plan)) {
+        snprintf(err, err_cap, "%s", plan.err.c_str());
+        return plan.unsupported ? -2 : -1;
+    }
+    info[1] = plan.batches.size(); info[2] = plan.pages.size();
+    if (plan.n_rows + 1 > off_cap) return -4;
+    uint64_t rows = 0, bytes = 0;
+    for (const SplPqBatch& b : plan.batches) {
+        std::vector<uint8_t> stage(b.stage_bytes + 16, 0), scratch(b.scratch_bytes + 16, 0);
+        for (size_t k = b.range0; k < b.range1; ++k) memcpy(stage.data() + plan.ranges[k].stage_off, file + plan.ranges[k].file_off, plan.ranges[k].len);
+        std::vector<uint64_t> row_off(b.n_rows + 1), dict_off(b.dict_entries + 1);
+        std::vector<uint32_t> row_len(b.n_rows + 1), dict_len(b.dict_entries + 1);
+        SplPqSpans R{row_off.data(), row_len.data()}, D{dict_off.data(), dict_len.data()};
+        SplPqOneLane g;
+        uint32_t e = 0;
+        for (int pass = 0; pass < 2; ++pass)
+            for (size_t k = b.page0; k < b.page1; ++k)
+                if ((plan.pages[k].kind == SPL_PQ_DICT) == (pass == 0)) e |= spl_pq_decode_page(g, plan.pages[k], stage.data(), scratch.data(), R, D);
+        if (e) { info[0] = e; return -3; }
+        for (uint64_t r = 0; r < b.n_rows; ++r) {
+            out_off[rows + r] = bytes;
+            if (bytes + row_len[r] > text_cap) return -4;
+            const uint8_t* src = (row_off[r] & SPL_PQ_IN_SCRATCH) ? scratch.data() + (row_off[r] & ~SPL_PQ_IN_SCRATCH) : stage.data() + row_off[r];
+            memcpy(out_text + bytes, src, row_len[r]);
+            bytes += row_len[r];
+        }
+        rows += b.n_rows;
+    }
+    out_off[rows] = bytes;
+    return (long)rows;
+}
+
 // ---- windowed merge rounds (spl_bpe_bits.h): the m masks of one group of G lanes, B parts per lane ----------------
 // K[0 .. n_pairs): rank of every pair (0x1FFFFF = none).  Builds the lanes' LT / RT masks the way bpe_group does, then
 // runs the kernel's boundary-bit iteration (the shuffles become array reads) and the peak step.  m_out[g] = lane g's mask.

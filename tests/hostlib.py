@@ -8,8 +8,9 @@ import subprocess
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SRC = [os.path.join(ROOT, "tests", "csrc", "hosttest.cpp"), os.path.join(ROOT, "splintr_b200", "csrc", "spl_host.cpp")]
-DEPS = SRC + [os.path.join(ROOT, "splintr_b200", "csrc", f) for f in ("spl_pretok.h", "spl_pretok_fast.h", "spl_sentencepiece.h", "spl_ingest.h", "spl_bpe_bits.h", "spl_segment.h", "spl_special.h", "spl_common.h", "spl_host.h", "unicode_tables.inc")]
+SRC = [os.path.join(ROOT, "tests", "csrc", "hosttest.cpp"), os.path.join(ROOT, "splintr_b200", "csrc", "spl_host.cpp"),
+       os.path.join(ROOT, "splintr_b200", "csrc", "spl_parquet_meta.cpp")]
+DEPS = SRC + [os.path.join(ROOT, "splintr_b200", "csrc", f) for f in ("spl_pretok.h", "spl_pretok_fast.h", "spl_sentencepiece.h", "spl_ingest.h", "spl_bpe_bits.h", "spl_segment.h", "spl_special.h", "spl_parquet.h", "spl_parquet_meta.h", "spl_common.h", "spl_host.h", "unicode_tables.inc")]
 LIB = os.path.join(ROOT, "tests", "csrc", "libhosttest.so")
 _lib = None
 
@@ -46,6 +47,9 @@ def load():
     lib.ht_special_walk.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, vp, ctypes.c_uint32, vp, ctypes.c_size_t]
     lib.ht_jsonl.restype = ctypes.c_int
     lib.ht_jsonl.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, vp, vp, vp]
+    lib.ht_parquet.restype = ctypes.c_long
+    lib.ht_parquet.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_uint64, vp, ctypes.c_size_t, vp, ctypes.c_size_t,
+                               ctypes.c_char_p, ctypes.c_size_t, vp]
     lib.ht_set_fast_ext.argtypes = [ctypes.c_int]
     lib.ht_sp_transform.restype = ctypes.c_long
     lib.ht_sp_transform.argtypes = [ctypes.c_char_p, ctypes.c_uint32, vp, vp, vp, vp, vp]
@@ -100,6 +104,30 @@ def jsonl(data: bytes, field: str = "text"):
     raw = out[:int(cnt[1])].tobytes()
     o = off[:nd + 1].tolist()
     return [raw[o[i]:o[i + 1]] for i in range(nd)], int(cnt[2]), int(cnt[3])
+
+
+class ParquetError(Exception):
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+def parquet(data: bytes, column: str = "text", batch_bytes: int = 0, text_cap: int = 0, max_rows: int = 0):
+    """spl_parquet_meta.cpp + the page decoder of spl_parquet.h over a whole Parquet file -> (list of row bytes, info).
+    text_cap / max_rows: capacities of the output (defaults are generous guesses; dictionary pages can expand)."""
+    n = len(data)
+    text_cap = text_cap or max(64 * n, 1 << 20)
+    max_rows = max_rows or max(8 * n, 1 << 16)
+    out = np.zeros(text_cap + 16, dtype=np.uint8)
+    off = np.zeros(max_rows + 2, dtype=np.uint64)
+    info = np.zeros(4, dtype=np.uint64)
+    err = ctypes.create_string_buffer(512)
+    rc = load().ht_parquet(data, n, column.encode(), batch_bytes, out.ctypes.data, text_cap, off.ctypes.data, max_rows + 1, err, 512, info.ctypes.data)
+    if rc < 0:
+        raise ParquetError(rc, err.value.decode() or f"page error bits {int(info[0])}")
+    o = off[:rc + 1].tolist()
+    raw = out[:o[-1]].tobytes()
+    return [raw[o[i]:o[i + 1]] for i in range(rc)], {"batches": int(info[1]), "pages": int(info[2])}
 
 
 def sp_transform(data: bytes, hard=None, spec=None):

@@ -708,3 +708,148 @@ def test_ingest_jsonl_cfg2_roundtrip(toks):
     ids, ioff = tok.encode_jsonl(data)
     want_ids, want_off = tok.encode_packed(d, o)
     assert np.array_equal(ids, want_ids) and np.array_equal(ioff, want_off)
+
+
+# ---- row N4, Parquet / Arrow: the column's pages are decompressed and decoded on the device ----------------------------
+
+def _pq_bytes(table, **kw):
+    import io
+    import pyarrow.parquet as pq
+    buf = io.BytesIO()
+    pq.write_table(table, buf, **kw)
+    return buf.getvalue()
+
+
+def test_ingest_parquet_matches_pyarrow(toks):
+    """Every page kind the reader takes (tests/test_parquet_host.py runs the same decoder on the CPU): device output
+    == pyarrow's column, a null row an empty document; encode_parquet == encode_batch of that column."""
+    import pyarrow as pa
+    from test_parquet_host import OPTS, make_texts, expect
+    tok = toks("cl100k_base")
+    for i, opt in enumerate(OPTS):
+        rng = random.Random(40 + i)
+        for n, nulls, repeat in ((0, 0.0, False), (1, 0.0, False), (4000, 0.15, i % 2 == 0), (9000, 0.0, i % 2 == 1)):
+            texts = make_texts(rng, n, nulls, repeat)
+            data = _pq_bytes(pa.table({"id": pa.array(range(n)), "text": pa.array(texts, pa.string())}), **opt)
+            want = expect(texts)
+            text, offs, st = tok.ingest_parquet(data, "text")
+            raw, o = text.cpu().numpy().tobytes(), offs.cpu().tolist()
+            assert st["n_docs"] == n and o[0] == 0 and len(o) == n + 1
+            assert [raw[o[k]:o[k + 1]] for k in range(n)] == want, (opt, n, nulls, repeat)
+            ids, ioff = tok.encode_parquet(data, "text")
+            flat, io_ = ids.tolist(), ioff.tolist()
+            assert [flat[io_[k]:io_[k + 1]] for k in range(n)] == tok.encode_batch([w.decode() for w in want]), (opt, n)
+    # a string inside nullable structs, by dotted path
+    rng = random.Random(3)
+    vals = [None if rng.random() < 0.1 else {"body": None if rng.random() < 0.2 else "doc %d é" % k} for k in range(3000)]
+    t = pa.table({"meta": pa.array(vals, pa.struct([("body", pa.string())]))})
+    text, offs, _ = tok.ingest_parquet(_pq_bytes(t), "meta.body")
+    raw, o = text.cpu().numpy().tobytes(), offs.cpu().tolist()
+    assert [raw[o[k]:o[k + 1]] for k in range(3000)] == [b"" if (v is None or v["body"] is None) else v["body"].encode() for v in vals]
+
+
+def test_encode_parquet_cfg2_row_groups_and_batches(toks, monkeypatch):
+    """cfg2 (100 000 documents) as a snappy Parquet file of 13 row groups: ingested text == the packed batch byte for
+    byte, ids == the ids of the packed batch; the same through many small batches (SPL_CHUNK_BYTES), in SentencePiece
+    mode, and with special tokens."""
+    import pyarrow as pa
+    from splintr_b200 import Tokenizer
+    tok = toks("cl100k_base")
+    d, o = synth.cfg2(vocab_bytes("cl100k_base"), 100_000)
+    texts = synth.unpack_texts(d, o)
+    table = pa.table({"id": pa.array(range(len(texts))), "text": pa.array(texts, pa.string())})
+    want_ids, want_off = tok.encode_packed(d, o)
+    for kw in (dict(compression="snappy", row_group_size=8000), dict(compression="none", use_dictionary=False, data_page_version="2.0")):
+        data = _pq_bytes(table, **kw)
+        text, offs, st = tok.ingest_parquet(data, "text")
+        assert np.array_equal(text.cpu().numpy(), d) and np.array_equal(offs.cpu().numpy().astype(np.uint64), o)
+        ids, ioff, st = tok.encode_parquet(data, "text", return_stats=True)
+        assert np.array_equal(ids, want_ids) and np.array_equal(ioff, want_off)
+        assert st["n_docs"] == 100_000 and st["h2d_bytes"] < len(data)
+    data = _pq_bytes(table.slice(0, 30_000), compression="snappy", row_group_size=1500)
+    sub = texts[:30_000]
+    sub[7] = "<|endoftext|> and <|fim_prefix|>" + sub[7]
+    data_s = _pq_bytes(pa.table({"text": pa.array(sub)}), compression="snappy", row_group_size=1500)
+    monkeypatch.setenv("SPL_CHUNK_BYTES", "2000000")
+    t1 = Tokenizer.from_pretrained("cl100k_base", devices=[0])
+    t2 = Tokenizer.from_pretrained("mistral_v2", devices=[0])
+    monkeypatch.delenv("SPL_CHUNK_BYTES")
+    for t in (t1, t2):
+        ids, ioff = t.encode_parquet(data, "text")
+        w_ids, w_off = t.encode_batch_packed(texts[:30_000])
+        assert np.array_equal(ids, w_ids) and np.array_equal(ioff, w_off)
+    ids, ioff = t1.encode_parquet(data_s, "text", with_special=True)
+    w_ids, w_off = t1.encode_batch_packed(sub, with_special=True)
+    assert np.array_equal(ids, w_ids) and np.array_equal(ioff, w_off)
+    assert 100257 in ids.tolist()[:int(ioff[8])]
+
+
+def test_parquet_refusals_and_damaged_pages(toks):
+    """What the reader does not take is refused with a message (ValueError), never guessed at; a page whose bytes do not
+    decode is reported by the device (error bits -> ValueError), never read out of bounds."""
+    import io
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    tok = toks("cl100k_base")
+    table = pa.table({"text": pa.array(["a", "b"]), "n": pa.array([1, 2]), "l": pa.array([["x"], ["y", "z"]])})
+    for column, kw, pat in (("body", {}, "no column named"), ("n", {}, "BYTE_ARRAY"), ("l.list.element", {}, "repeated"),
+                            ("text", dict(compression="zstd"), "snappy"),
+                            ("text", dict(use_dictionary=False, column_encoding={"text": "DELTA_BYTE_ARRAY"}), "DELTA")):
+        with pytest.raises(ValueError, match=pat):
+            tok.encode_parquet(_pq_bytes(table, **kw), column)
+    with pytest.raises(ValueError, match="not a Parquet file"):
+        tok.encode_parquet(b"hello world, this is not parquet", "text")
+    rng = random.Random(8)
+    texts = ["".join(rng.choice("abcdefgh ") for _ in range(rng.randint(0, 300))) for _ in range(3000)]
+    good = _pq_bytes(pa.table({"text": pa.array(texts)}), compression="snappy", use_dictionary=False, data_page_size=20000)
+    col = pq.ParquetFile(io.BytesIO(good)).metadata.row_group(0).column(0)
+    lo, hi = col.data_page_offset + 40, col.data_page_offset + col.total_compressed_size
+    outcomes = {"ok": 0, "err": 0}
+    for k in range(12):
+        b = bytearray(good)
+        for _ in range(3):
+            b[rng.randrange(lo, hi)] ^= 1 << rng.randrange(8)
+        try:
+            ids, off = tok.encode_parquet(bytes(b), "text")
+            assert len(off) == 3001
+            outcomes["ok"] += 1
+        except ValueError as e:
+            assert "parquet" in str(e)
+            outcomes["err"] += 1
+    assert outcomes["err"] > 0
+    ids, off = tok.encode_parquet(good, "text")                      # the handle is fine afterwards
+    assert [ids[off[k]:off[k + 1]].tolist() for k in range(50)] == tok.encode_batch(texts[:50])
+
+
+def test_encode_arrow_string_columns(toks):
+    """An Arrow string array is the packed layout already: data buffer + offsets go in as they are (nulls, slices,
+    chunked arrays, 64-bit offsets)."""
+    import pyarrow as pa
+    tok = toks("o200k_base")
+    rng = random.Random(21)
+    texts = [None if rng.random() < 0.1 else random_text(rng, 60) for _ in range(5000)]
+    texts = [t if (t is None or "᠎" not in t) else "x" for t in texts]
+    want = tok.encode_batch([t or "" for t in texts])
+
+    def check(col, exp):
+        ids, off = tok.encode_arrow(col)
+        flat, o = ids.tolist(), off.tolist()
+        assert len(o) == len(exp) + 1 and o[0] == 0
+        assert [flat[o[k]:o[k + 1]] for k in range(len(exp))] == exp
+
+    a = pa.array(texts, pa.string())
+    check(a, want)
+    check(a.slice(1234, 2000), want[1234:3234])
+    check(pa.array(texts, pa.large_string()), want)
+    check(pa.chunked_array([a.slice(0, 100), a.slice(100, 0), a.slice(100, 4900)]), want)
+    check(pa.array([], pa.string()), [])
+    # a null slot that holds bytes (legal in Arrow): must still be an empty document
+    import numpy as _np
+    data = pa.py_buffer(b"helloJUNKworld")
+    offs = pa.py_buffer(_np.array([0, 5, 9, 14], dtype=_np.int32).tobytes())
+    valid = pa.py_buffer(bytes([0b101]))
+    odd = pa.Array.from_buffers(pa.string(), 3, [valid, offs, data])
+    assert odd.to_pylist() == ["hello", None, "world"]
+    check(odd, tok.encode_batch(["hello", "", "world"]))
+    with pytest.raises(TypeError):
+        tok.encode_arrow(pa.array([1, 2, 3]))

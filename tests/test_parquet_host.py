@@ -1,0 +1,148 @@
+"""Parquet ingestion (row N4), CPU side: the footer / page-header reader (splintr_b200/csrc/spl_parquet_meta.cpp) and
+the page decoder the device runs (spl_parquet.h: snappy, RLE / bit-packed hybrid, PLAIN and dictionary pages, V1 / V2
+data pages), compiled for the host, against pyarrow on files pyarrow wrote.  What is replaced is the user's loop in
+front of Tokenizer.encode_batch (/root/reference/python/splintr/__init__.py documents encode_batch over a list):
+    texts = pyarrow.parquet.read_table(path, columns=[column])[column].to_pylist()
+with a null row read as an empty document."""
+import io
+import random
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.parquet as pq
+import pytest
+
+import hostlib
+
+WORDS = ["the", "of", "tokenizer", "Parquet", "naïve", "日本語", "数据", "🙂", "snappy", "x" * 70, "", " ", "\n", "a\tb"]
+
+
+def make_texts(rng, n, null_rate=0.0, repeat=False, big=False):
+    pool = [" ".join(rng.choice(WORDS) for _ in range(rng.randint(0, 30))) for _ in range(40)] if repeat else None
+    out = []
+    for _ in range(n):
+        if rng.random() < null_rate:
+            out.append(None)
+        elif repeat:
+            out.append(rng.choice(pool))
+        else:
+            k = rng.randint(0, 400 if not big else 20000)
+            out.append("".join(rng.choice(WORDS) + rng.choice(" .,\n") for _ in range(k // 6)))
+    return out
+
+
+def write(table, **kw):
+    buf = io.BytesIO()
+    pq.write_table(table, buf, **kw)
+    return buf.getvalue()
+
+
+def expect(texts):
+    return [b"" if t is None else (t if isinstance(t, bytes) else t.encode()) for t in texts]
+
+
+OPTS = [dict(compression="none", use_dictionary=False),
+        dict(compression="snappy", use_dictionary=False),
+        dict(compression="none", use_dictionary=True),
+        dict(compression="snappy", use_dictionary=True),
+        dict(compression="snappy", use_dictionary=True, data_page_version="2.0"),
+        dict(compression="none", use_dictionary=False, data_page_version="2.0"),
+        dict(compression="snappy", use_dictionary=False, data_page_version="2.0", data_page_size=2000),
+        dict(compression="snappy", use_dictionary=True, data_page_size=1500, row_group_size=700),
+        dict(compression="snappy", use_dictionary=True, dictionary_pagesize_limit=3000, data_page_size=4000),   # falls back to PLAIN mid-chunk
+        dict(compression="none", use_dictionary=True, dictionary_pagesize_limit=3000, data_page_size=4000, data_page_version="2.0")]
+
+
+@pytest.mark.parametrize("opt", range(len(OPTS)))
+@pytest.mark.parametrize("nulls", [0.0, 0.2])
+def test_text_column_matches_pyarrow(opt, nulls):
+    rng = random.Random(100 * opt + int(nulls * 10))
+    for n, repeat in ((0, False), (1, False), (3000, False), (5000, True)):
+        texts = make_texts(rng, n, nulls, repeat)
+        table = pa.table({"id": pa.array(range(n), pa.int64()), "text": pa.array(texts, pa.string()), "tail": pa.array([1.5] * n)})
+        data = write(table, **OPTS[opt])
+        want = expect(pq.read_table(io.BytesIO(data), columns=["text"])["text"].to_pylist())
+        got, info = hostlib.parquet(data, "text")
+        assert got == want, (OPTS[opt], nulls, n, repeat)
+        got2, info2 = hostlib.parquet(data, "text", batch_bytes=1)          # one batch per row group
+        assert got2 == want
+        assert info2["batches"] >= info["batches"]
+
+
+def test_required_large_string_binary_and_nested_columns():
+    rng = random.Random(5)
+    texts = [t for t in make_texts(rng, 2000, 0.0)]
+    req = pa.field("text", pa.string(), nullable=False)
+    t1 = pa.table([pa.array(texts, pa.string())], schema=pa.schema([req]))
+    assert hostlib.parquet(write(t1, compression="snappy"), "text")[0] == expect(texts)
+    t2 = pa.table({"text": pa.array(texts, pa.large_string())})
+    assert hostlib.parquet(write(t2), "text")[0] == expect(texts)
+    blobs = [bytes(rng.randrange(256) for _ in range(rng.randint(0, 300))) for _ in range(500)]
+    t3 = pa.table({"blob": pa.array(blobs, pa.binary())})
+    assert hostlib.parquet(write(t3, compression="snappy", use_dictionary=False), "blob")[0] == blobs
+    # a string inside (nullable) structs: definition levels up to 3, a null at any level is an empty document
+    inner = [None if rng.random() < 0.1 else {"body": (None if rng.random() < 0.2 else rng.choice(texts)), "n": 1} for _ in range(3000)]
+    outer = [None if rng.random() < 0.1 else {"doc": x} for x in inner]
+    t4 = pa.table({"meta": pa.array(outer, pa.struct([("doc", pa.struct([("body", pa.string()), ("n", pa.int32())]))])), "k": pa.array(range(3000))})
+    want = [b"" if (o is None or o["doc"] is None or o["doc"]["body"] is None) else o["doc"]["body"].encode() for o in outer]
+    for kw in (dict(compression="snappy"), dict(compression="none", use_dictionary=False, data_page_version="2.0")):
+        assert hostlib.parquet(write(t4, **kw), "meta.doc.body")[0] == want
+
+
+def test_large_pages_and_long_documents():
+    rng = random.Random(9)
+    texts = make_texts(rng, 300, 0.05, big=True)
+    table = pa.table({"text": pa.array(texts, pa.string())})
+    for kw in (dict(compression="snappy", use_dictionary=False), dict(compression="snappy"), dict(compression="none")):
+        data = write(table, **kw)
+        assert hostlib.parquet(data, "text")[0] == expect(texts)
+    # highly repetitive text: long snappy copies, copies that overlap their own output
+    rep = ["ab" * 5000, "x" * 70000, "", "abc" * 3 + "z" * 100, ("0123456789" * 7 + "\n") * 900]
+    data = write(pa.table({"text": pa.array(rep)}), compression="snappy", use_dictionary=False)
+    assert hostlib.parquet(data, "text")[0] == expect(rep)
+
+
+def test_refusals_say_what_to_do():
+    table = pa.table({"text": pa.array(["a", "b"]), "n": pa.array([1, 2]), "l": pa.array([["x"], ["y", "z"]])})
+    data = write(table)
+    with pytest.raises(hostlib.ParquetError, match="no column named") as e:
+        hostlib.parquet(data, "body")
+    assert e.value.code == -1
+    with pytest.raises(hostlib.ParquetError, match="BYTE_ARRAY") as e:
+        hostlib.parquet(data, "n")
+    assert e.value.code == -2
+    with pytest.raises(hostlib.ParquetError, match="repeated") as e:
+        hostlib.parquet(data, "l.list.element")
+    assert e.value.code == -2
+    for codec in ("zstd", "gzip"):
+        with pytest.raises(hostlib.ParquetError, match="not supported.*snappy") as e:
+            hostlib.parquet(write(table, compression=codec), "text")
+        assert e.value.code == -2
+    with pytest.raises(hostlib.ParquetError, match="DELTA") as e:
+        hostlib.parquet(write(table, use_dictionary=False, column_encoding={"text": "DELTA_BYTE_ARRAY"}), "text")
+    assert e.value.code == -2
+
+
+def test_damaged_files_never_crash():
+    """Truncations and flipped bytes anywhere in the file: an error or (when the damage hits no structure this column
+    needs, or only text bytes) some result -- never a crash or an out-of-bounds read (run under the sanitizer build too)."""
+    rng = random.Random(17)
+    texts = make_texts(rng, 400, 0.1)
+    good = write(pa.table({"text": pa.array(texts)}), compression="snappy", data_page_size=3000)
+    assert hostlib.parquet(good, "text")[0] == expect(texts)
+    outcomes = {"ok": 0, "err": 0}
+    for i in range(400):
+        b = bytearray(good)
+        if i % 4 == 0:
+            b = b[:rng.randrange(len(b))]
+            if len(b) >= 4 and rng.random() < 0.5:
+                b[-4:] = b"PAR1"
+        else:
+            for _ in range(rng.randint(1, 4)):
+                b[rng.randrange(len(b))] = rng.randrange(256)
+        try:
+            hostlib.parquet(bytes(b), "text", text_cap=1 << 22, max_rows=1 << 16)
+            outcomes["ok"] += 1
+        except hostlib.ParquetError:
+            outcomes["err"] += 1
+    assert outcomes["err"] > 50
