@@ -1475,10 +1475,10 @@ int ingest_parquet_batch(spl_tokenizer* tk, DevCtx& dc, cudaStream_t st, const u
         CUDA_TRY(cudaMemcpyAsync((uint8_t*)dc.pq_stage.p + r.stage_off, file + r.file_off, (size_t)r.len, cudaMemcpyHostToDevice, st), tk->err);
         h2d += r.len;
     }
-    bool has_dict = false;
-    for (size_t k = b.page0; k < b.page1; ++k) has_dict |= plan.pages[k].kind == SPL_PQ_DICT;
+    bool has_dict = false, has_snappy = false;
+    for (size_t k = b.page0; k < b.page1; ++k) { has_dict |= plan.pages[k].kind == SPL_PQ_DICT; has_snappy |= plan.pages[k].codec == SPL_PQ_CODEC_SNAPPY; }
     if (n_pages) CUDA_TRY(cudaMemcpyAsync(dc.pq_pages.p, plan.pages.data() + b.page0, n_pages * sizeof(SplPqPage), cudaMemcpyHostToDevice, st), tk->err);
-    launches += spl_launch_pq_spans(w, 0, (uint32_t)n_pages, has_dict, st);
+    launches += spl_launch_pq_spans(w, 0, (uint32_t)n_pages, has_dict, has_snappy, st);
     if (n_pages == 0) CUDA_TRY(cudaMemsetAsync(dc.jl_off.p, 0, 8, st), tk->err);            // no rows: offsets = {0}
     CUDA_TRY(cudaGetLastError(), tk->err);
     uint32_t h_ctr[8];

@@ -199,7 +199,7 @@ struct SplPqWork {
     uint8_t* out_text;                 // packed text (known size: counters[SPL_PQCTR_TEXT] after spl_launch_pq_spans)
     uint64_t* out_off;                 // [n_rows + 1]
 };
-int spl_launch_pq_spans(const SplPqWork& w, uint32_t first_page, uint32_t n_pages, bool has_dict, cudaStream_t stream);
+int spl_launch_pq_spans(const SplPqWork& w, uint32_t first_page, uint32_t n_pages, bool has_dict, bool has_snappy, cudaStream_t stream);
 int spl_launch_pq_copy(const SplPqWork& w, uint64_t text_bytes, cudaStream_t stream);
 
 // spl_decode.cu: ids -> bytes (row N2)

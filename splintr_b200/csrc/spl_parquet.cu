@@ -2,8 +2,9 @@
 // document offsets, the input format of spl_encode_batch_device.  Formats and per-page decoder: spl_parquet.h; footer
 // and page headers are read on the host (spl_parquet_meta.cpp).
 //
-//   k_pq_pages    one warp per page: snappy (lane 0's element stream is every lane's: all lanes parse, all lanes copy),
-//                 definition levels, PLAIN lengths or dictionary indices -> one (source offset, length) span per row;
+//   k_pq_pages    one warp per page: snappy (all lanes parse the element stream alike, all lanes copy; input slots and
+//                 a 64 KiB ring of output in shared memory, so an element touches no global memory), definition
+//                 levels, PLAIN lengths or dictionary indices -> one (source offset, length) span per row;
 //                 launched twice: dictionary pages, then data pages (which read the dictionary's spans)
 //   k_pq_bsum     row lengths summed per block of 2 048 rows        k_pq_bscan   exclusive prefix over the blocks
 //   k_pq_offsets  u64 document offsets (row r: bytes of the rows in front of it), total -> counters
@@ -11,6 +12,8 @@
 //                 the row that lies in the block's range with aligned 4-byte stores (funnel-shifted aligned loads)
 // Pages are the unit of parallelism of the first kernel (a 1 MiB page is one warp's work: ~0.1 ms uncompressed PLAIN,
 // a few ms of snappy); the copy is bounded by HBM traffic.
+#include <cstdlib>
+
 #include "spl_device.cuh"
 #include "spl_parquet.h"
 
@@ -19,19 +22,24 @@ namespace {
 struct WarpLanes {
     static constexpr uint32_t NL = 32;
     uint32_t lane;
+    uint8_t* win; uint8_t* inbuf;          // snappy: 64 KiB ring of output + two 4 KiB input slots in shared memory (or null)
     __device__ __forceinline__ void sync() const { __syncwarp(); }
 };
+#define PQ_RING_SMEM (SPL_SNAPPY_WIN + SPL_SNAPPY_INBUF)
 
 #define PQ_THREADS 256
 #define PQ_ROWS_PER_BLOCK 2048u
 #define PQ_COPY_BYTES 16384u
 
-__global__ void __launch_bounds__(128) k_pq_pages(SplPqWork w, const uint32_t first, const uint32_t count, const bool dict_pass) {
+// RING: one warp per block with 72 KiB of shared memory (three pages in flight per SM); else four warps per block
+template <bool RING>
+__global__ void __launch_bounds__(RING ? 32 : 128) k_pq_pages(SplPqWork w, const uint32_t first, const uint32_t count, const bool dict_pass) {
+    extern __shared__ __align__(16) uint8_t pq_smem[];
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= count) return;
     const SplPqPage pg = w.pages[first + warp];
     if ((pg.kind == SPL_PQ_DICT) != dict_pass) return;
-    WarpLanes g{threadIdx.x & 31u};
+    WarpLanes g{threadIdx.x & 31u, RING ? pq_smem : nullptr, RING ? pq_smem + SPL_SNAPPY_WIN : nullptr};
     const uint32_t err = spl_pq_decode_page(g, pg, w.file, w.scratch, SplPqSpans{w.row_off, w.row_len}, SplPqSpans{w.dict_off, w.dict_len});
     if (err && g.lane == 0) atomicOr(&w.counters[SPL_PQCTR_ERR], err);
 }
@@ -151,12 +159,19 @@ __global__ void __launch_bounds__(PQ_THREADS) k_pq_copy(SplPqWork w) {
 
 }  // namespace
 
-int spl_launch_pq_spans(const SplPqWork& w, uint32_t first_page, uint32_t n_pages, bool has_dict, cudaStream_t stream) {
+int spl_launch_pq_spans(const SplPqWork& w, uint32_t first_page, uint32_t n_pages, bool has_dict, bool has_snappy, cudaStream_t stream) {
     if (n_pages == 0) return 0;
-    const uint32_t blocks = (n_pages + 3) / 4;
+    // snappy out of shared memory (SPL_PQ_SNAPPY_RING=0: the plain decoder, every element through global memory -- A/B)
+    static const bool ring_on = [] { const char* e = getenv("SPL_PQ_SNAPPY_RING"); return !e || e[0] != '0'; }();
     int n = 0;
-    if (has_dict) { k_pq_pages<<<blocks, 128, 0, stream>>>(w, first_page, n_pages, true); ++n; }
-    k_pq_pages<<<blocks, 128, 0, stream>>>(w, first_page, n_pages, false); ++n;
+    for (int pass = has_dict ? 0 : 1; pass < 2; ++pass, ++n) {
+        if (has_snappy && ring_on) {
+            cudaFuncSetAttribute(k_pq_pages<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PQ_RING_SMEM);
+            k_pq_pages<true><<<n_pages, 32, PQ_RING_SMEM, stream>>>(w, first_page, n_pages, pass == 0);
+        } else {
+            k_pq_pages<false><<<(n_pages + 3) / 4, 128, 0, stream>>>(w, first_page, n_pages, pass == 0);
+        }
+    }
     k_pq_bsum<<<w.n_blocks, PQ_THREADS, 0, stream>>>(w);
     k_pq_bscan<<<1, 1024, 0, stream>>>(w);
     k_pq_offsets<<<w.n_blocks, PQ_THREADS, 0, stream>>>(w);

@@ -430,7 +430,7 @@ extern "C" int ht_jsonl(const uint8_t* text, uint32_t n, const char* field, uint
 #include "../../splintr_b200/csrc/spl_parquet_meta.h"
 extern "C" long ht_parquet(const uint8_t* file, size_t n, const char* column, uint64_t batch_bytes,
                            uint8_t* out_text, size_t text_cap, uint64_t* out_off, size_t off_cap,
-                           char* err, size_t err_cap, uint64_t* info) {
+                           char* err, size_t err_cap, uint64_t* info, int staged) {
     SplPqPlan plan;
     info[0] = info[1] = info[2] = 0;
     if (!spl_pq_plan(file, n, column, batch_bytes, plan)) {
@@ -447,6 +447,8 @@ extern "C" long ht_parquet(const uint8_t* file, size_t n, const char* column, ui
         std::vector<uint32_t> row_len(b.n_rows + 1), dict_len(b.dict_entries + 1);
         SplPqSpans R{row_off.data(), row_len.data()}, D{dict_off.data(), dict_len.data()};
         SplPqOneLane g;
+        std::vector<SplU128> win(SPL_SNAPPY_WIN / 16), inbuf(SPL_SNAPPY_INBUF / 16);
+        if (staged) { g.win = (uint8_t*)win.data(); g.inbuf = (uint8_t*)inbuf.data(); }   // the snappy decoder the device runs
         uint32_t e = 0;
         for (int pass = 0; pass < 2; ++pass)
             for (size_t k = b.page0; k < b.page1; ++k)
@@ -463,6 +465,18 @@ extern "C" long ht_parquet(const uint8_t* file, size_t n, const char* column, ui
     }
     out_off[rows] = bytes;
     return (long)rows;
+}
+
+// the two snappy decoders of spl_parquet.h on a raw stream (src and dst 16-byte aligned copies, padded); 1 = decoded
+extern "C" int ht_snappy(const uint8_t* src, uint32_t n, uint8_t* out, uint32_t cap, int staged) {
+    std::vector<SplU128> in((n + 31) / 16 + 1), dst((cap + 31) / 16 + 1), win(SPL_SNAPPY_WIN / 16), inbuf(SPL_SNAPPY_INBUF / 16);
+    uint8_t* s = (uint8_t*)in.data() + 5;                       // an odd start, as a page body has
+    memcpy(s, src, n);
+    SplPqOneLane g;
+    if (staged) { g.win = (uint8_t*)win.data(); g.inbuf = (uint8_t*)inbuf.data(); }
+    const bool ok = staged ? spl_snappy_decode_staged(g, s, n, (uint8_t*)dst.data(), cap) : spl_snappy_decode(g, s, n, (uint8_t*)dst.data(), cap);
+    if (ok) memcpy(out, dst.data(), cap);
+    return ok ? 1 : 0;
 }
 
 // ---- windowed merge rounds (spl_bpe_bits.h): the m masks of one group of G lanes, B parts per lane ----------------

@@ -49,7 +49,9 @@ def load():
     lib.ht_jsonl.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, vp, vp, vp]
     lib.ht_parquet.restype = ctypes.c_long
     lib.ht_parquet.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_uint64, vp, ctypes.c_size_t, vp, ctypes.c_size_t,
-                               ctypes.c_char_p, ctypes.c_size_t, vp]
+                               ctypes.c_char_p, ctypes.c_size_t, vp, ctypes.c_int]
+    lib.ht_snappy.restype = ctypes.c_int
+    lib.ht_snappy.argtypes = [ctypes.c_char_p, ctypes.c_uint32, vp, ctypes.c_uint32, ctypes.c_int]
     lib.ht_set_fast_ext.argtypes = [ctypes.c_int]
     lib.ht_sp_transform.restype = ctypes.c_long
     lib.ht_sp_transform.argtypes = [ctypes.c_char_p, ctypes.c_uint32, vp, vp, vp, vp, vp]
@@ -106,15 +108,23 @@ def jsonl(data: bytes, field: str = "text"):
     return [raw[o[i]:o[i + 1]] for i in range(nd)], int(cnt[2]), int(cnt[3])
 
 
+def snappy(stream: bytes, size: int, staged: bool):
+    """spl_parquet.h snappy decoders on a raw stream -> bytes, or None if the stream is refused"""
+    out = np.zeros(size + 16, dtype=np.uint8)
+    ok = load().ht_snappy(stream, len(stream), out.ctypes.data, size, int(staged))
+    return out[:size].tobytes() if ok else None
+
+
 class ParquetError(Exception):
     def __init__(self, code, msg):
         super().__init__(msg)
         self.code = code
 
 
-def parquet(data: bytes, column: str = "text", batch_bytes: int = 0, text_cap: int = 0, max_rows: int = 0):
+def parquet(data: bytes, column: str = "text", batch_bytes: int = 0, text_cap: int = 0, max_rows: int = 0, staged: bool = True):
     """spl_parquet_meta.cpp + the page decoder of spl_parquet.h over a whole Parquet file -> (list of row bytes, info).
-    text_cap / max_rows: capacities of the output (defaults are generous guesses; dictionary pages can expand)."""
+    text_cap / max_rows: capacities of the output (defaults are generous guesses; dictionary pages can expand).
+    staged: the snappy decoder that works out of a 64 KiB ring + input slots (the device's), else the plain one."""
     n = len(data)
     text_cap = text_cap or max(64 * n, 1 << 20)
     max_rows = max_rows or max(8 * n, 1 << 16)
@@ -122,7 +132,7 @@ def parquet(data: bytes, column: str = "text", batch_bytes: int = 0, text_cap: i
     off = np.zeros(max_rows + 2, dtype=np.uint64)
     info = np.zeros(4, dtype=np.uint64)
     err = ctypes.create_string_buffer(512)
-    rc = load().ht_parquet(data, n, column.encode(), batch_bytes, out.ctypes.data, text_cap, off.ctypes.data, max_rows + 1, err, 512, info.ctypes.data)
+    rc = load().ht_parquet(data, n, column.encode(), batch_bytes, out.ctypes.data, text_cap, off.ctypes.data, max_rows + 1, err, 512, info.ctypes.data, int(staged))
     if rc < 0:
         raise ParquetError(rc, err.value.decode() or f"page error bits {int(info[0])}")
     o = off[:rc + 1].tolist()

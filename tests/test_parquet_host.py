@@ -64,7 +64,7 @@ def test_text_column_matches_pyarrow(opt, nulls):
         want = expect(pq.read_table(io.BytesIO(data), columns=["text"])["text"].to_pylist())
         got, info = hostlib.parquet(data, "text")
         assert got == want, (OPTS[opt], nulls, n, repeat)
-        got2, info2 = hostlib.parquet(data, "text", batch_bytes=1)          # one batch per row group
+        got2, info2 = hostlib.parquet(data, "text", batch_bytes=1, staged=False)          # one batch per row group; the plain snappy decoder
         assert got2 == want
         assert info2["batches"] >= info["batches"]
 
@@ -100,6 +100,72 @@ def test_large_pages_and_long_documents():
     rep = ["ab" * 5000, "x" * 70000, "", "abc" * 3 + "z" * 100, ("0123456789" * 7 + "\n") * 900]
     data = write(pa.table({"text": pa.array(rep)}), compression="snappy", use_dictionary=False)
     assert hostlib.parquet(data, "text")[0] == expect(rep)
+    assert hostlib.parquet(data, "text", staged=False)[0] == expect(rep)
+    # incompressible rows (literals of several KiB: many input slots per element) between compressible ones, 3 MB page
+    blobs = [bytes(rng.randrange(256) for _ in range(rng.randint(3000, 9000))) if k % 3 else b"hello world " * rng.randint(1, 900) for k in range(400)]
+    data = write(pa.table({"b": pa.array(blobs, pa.binary())}), compression="snappy", use_dictionary=False, data_page_size=3 << 20)
+    assert hostlib.parquet(data, "b")[0] == blobs
+
+
+def _varint(v):
+    out = bytearray()
+    while v >= 0x80:
+        out.append((v & 0x7F) | 0x80)
+        v >>= 7
+    out.append(v)
+    return bytes(out)
+
+
+def test_snappy_streams_by_hand():
+    """Element forms a compressor rarely emits (standard snappy works in 64 KiB blocks): copies from 65 473 .. 65 535
+    bytes back (beyond what the decoder's ring serves), 4-byte offsets, literals with 1..4 length bytes, copies that
+    overlap their own output -- random streams built here element by element, both decoders against the construction."""
+    rng = random.Random(31)
+    for trial in range(60):
+        out = bytearray()
+        stream = bytearray()
+        n_el = rng.randint(1, 400)
+        for _ in range(n_el):
+            kind = rng.random()
+            if kind < 0.35 or len(out) == 0:
+                l = rng.choice([1, 5, 60, 61, 255, 256, 257, 4095, 4096, 4097, rng.randint(1, 70000), 65536 + rng.randint(0, 9)])
+                lit = bytes(rng.randrange(256) for _ in range(l)) if l < 5000 else rng.randbytes(l)
+                if l <= 60:
+                    stream.append((l - 1) << 2)
+                else:
+                    nb = 1 if l - 1 < 1 << 8 else 2 if l - 1 < 1 << 16 else 3 if l - 1 < 1 << 24 else 4
+                    if rng.random() < 0.2:
+                        nb = 4
+                    stream.append((59 + nb) << 2)
+                    stream += (l - 1).to_bytes(nb, "little")
+                stream += lit
+                out += lit
+            else:
+                l = rng.randint(1, 64)
+                off = rng.choice([1, 2, 3, 7, 63, 64, 65, rng.randint(1, 70000), 65472, 65473, 65500, 65535, 65536, 65537, 69000])
+                off = min(off, len(out))
+                form = rng.random()
+                if form < 0.4 and 4 <= l <= 11 and off < 2048:
+                    stream.append(1 | ((l - 4) << 2) | ((off >> 8) << 5))
+                    stream.append(off & 0xFF)
+                elif form < 0.8 and off < 65536:
+                    stream.append(2 | ((l - 1) << 2))
+                    stream += off.to_bytes(2, "little")
+                else:
+                    stream.append(3 | ((l - 1) << 2))
+                    stream += off.to_bytes(4, "little")
+                for i in range(l):
+                    out.append(out[len(out) - off])
+        full = _varint(len(out)) + bytes(stream)
+        for staged in (False, True):
+            assert hostlib.snappy(full, len(out), staged) == bytes(out), (trial, staged)
+        # damaged: wrong size, cut stream, offset beyond the output
+        assert hostlib.snappy(full, len(out) + 1, True) is None and hostlib.snappy(full, len(out) + 1, False) is None
+        if len(full) > 3:
+            cut = full[:rng.randrange(1, len(full))]
+            assert hostlib.snappy(cut, len(out), True) == hostlib.snappy(cut, len(out), False)
+    bad = _varint(10) + bytes([(5 - 1) << 2]) + b"hello" + bytes([2 | ((5 - 1) << 2)]) + (6).to_bytes(2, "little")
+    assert hostlib.snappy(bad, 10, True) is None and hostlib.snappy(bad, 10, False) is None
 
 
 def test_refusals_say_what_to_do():
@@ -141,7 +207,7 @@ def test_damaged_files_never_crash():
             for _ in range(rng.randint(1, 4)):
                 b[rng.randrange(len(b))] = rng.randrange(256)
         try:
-            hostlib.parquet(bytes(b), "text", text_cap=1 << 22, max_rows=1 << 16)
+            hostlib.parquet(bytes(b), "text", text_cap=1 << 22, max_rows=1 << 16, staged=bool(i & 1))
             outcomes["ok"] += 1
         except hostlib.ParquetError:
             outcomes["err"] += 1

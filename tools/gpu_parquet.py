@@ -26,6 +26,8 @@ def best(f, n=4):
 for name, kw in (("snappy, dictionary (pyarrow defaults)", dict(compression="snappy")),
                  ("snappy, PLAIN", dict(compression="snappy", use_dictionary=False)),
                  ("uncompressed, PLAIN", dict(compression="none", use_dictionary=False))):
+    if len(sys.argv) > 1 and sys.argv[1] not in name:
+        continue
     buf = io.BytesIO(); pq.write_table(table, buf, **kw); data = buf.getvalue()
     arr = np.frombuffer(data, dtype=np.uint8)
     t_dev, (ids, off, st) = best(lambda: tok.encode_parquet(arr, "text", return_stats=True))
@@ -38,3 +40,5 @@ for name, kw in (("snappy, dictionary (pyarrow defaults)", dict(compression="sna
     print(f"    encode_parquet (device pages)            {t_dev * 1e3:8.2f} ms = {len(d) / t_dev / 1e9:6.2f} GB/s of text   (device part {st['total_ms']:.2f} ms)")
     print(f"    pyarrow read_table + encode_arrow        {t_arrow * 1e3:8.2f} ms = {len(d) / t_arrow / 1e9:6.2f} GB/s   (read_table alone {t_read * 1e3:.2f} ms)")
     print(f"    pyarrow read + to_pylist + encode_packed {t_list * 1e3:8.2f} ms = {len(d) / t_list / 1e9:6.2f} GB/s")
+sys.stdout.flush()
+os._exit(0)          # (pyarrow's thread pool and the CUDA context do not agree on who goes first at interpreter exit)
