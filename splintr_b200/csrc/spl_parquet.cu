@@ -24,6 +24,8 @@ struct WarpLanes {
     uint32_t lane;
     uint8_t* win; uint8_t* inbuf;          // snappy: 64 KiB ring of output + two 4 KiB input slots in shared memory (or null)
     __device__ __forceinline__ void sync() const { __syncwarp(); }
+    __device__ __forceinline__ uint32_t shfl(uint32_t v, uint32_t src) const { return __shfl_sync(FULL, v, src); }
+    __device__ __forceinline__ uint32_t ballot(bool p) const { return __ballot_sync(FULL, p); }
 };
 #define PQ_RING_SMEM (SPL_SNAPPY_WIN + SPL_SNAPPY_INBUF)
 

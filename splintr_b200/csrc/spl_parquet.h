@@ -231,6 +231,177 @@ SPL_HD bool spl_snappy_decode_staged(const G& g, const uint8_t* src, uint32_t n,
     return op == cap;
 }
 
+// The warp version: elements are short on text (cfg2 through pyarrow's snappy: 485 000 elements per 2 MB page, 4.1
+// bytes each), and one element at a time leaves a warp waiting on its own instruction latencies (~530 cycles per
+// element, with or without shared memory).  Here the 32 lanes parse the next 32 INPUT bytes speculatively -- lane i
+// assumes an element starts at byte i --, the real chain of element starts is found by pointer doubling (5 shuffle
+// rounds), output positions by a warp scan, and the batch (~11 elements) is copied at once: short literals and copies
+// whose source lies in front of the batch by their own lanes, the few copies that read what the batch itself produces
+// one after the other, a long literal (always the batch's last element) by the whole warp.
+// G: 32 lanes with shfl(value, source lane) / ballot(predicate) / sync(), all called by every lane alike.
+template <class G>
+SPL_HD bool spl_snappy_decode_warp(const G& g, const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t cap) {
+    constexpr uint32_t M = SPL_SNAPPY_WIN - 1u;
+    constexpr uint32_t NEAR = SPL_SNAPPY_WIN - 4096u;          // offsets the ring serves while a batch (< 2.1 KiB without its long literal) is written
+    constexpr uint32_t SHORT = 32u;                            // literals up to this long are copied by their own lane
+    uint8_t* const win = g.win; uint8_t* const inbuf = g.inbuf;
+    const uint32_t lane = g.lane;
+    const uint32_t lead = (uint32_t)((uintptr_t)src & 15u);
+    const uint8_t* a0 = src - lead;
+    const uint32_t in_end = lead + n, in_end16 = (in_end + 15u) & ~15u;
+    uint32_t loaded = 0;
+    auto need = [&](uint32_t pos) {
+        const uint32_t want = (pos >> 12) + 2u;
+        if (loaded >= want) return;
+        while (loaded < want) {
+            const uint32_t c0 = loaded << 12;
+            if (c0 < in_end16) {
+                const uint32_t units = (in_end16 - c0 < 4096u ? in_end16 - c0 : 4096u) >> 4;
+                const SplU128* s4 = reinterpret_cast<const SplU128*>(a0 + c0);
+                SplU128* d4 = reinterpret_cast<SplU128*>(inbuf + ((loaded & 1u) << 12));
+                for (uint32_t k = lane; k < units; k += 32u) d4[k] = s4[k];
+            }
+            ++loaded;
+        }
+        g.sync();
+    };
+    auto in = [&](uint32_t pos) -> uint32_t { return inbuf[pos & (SPL_SNAPPY_INBUF - 1u)]; };
+    uint32_t ip = lead, op = 0, flushed = 0;
+    auto flush_to = [&](uint32_t limit16) {
+        const uint32_t units = (limit16 - flushed) >> 4;
+        SplU128* d4 = reinterpret_cast<SplU128*>(dst + flushed);
+        for (uint32_t k = lane; k < units; k += 32u) d4[k] = *reinterpret_cast<const SplU128*>(win + ((flushed + (k << 4)) & M));
+        flushed = limit16;
+    };
+    auto flush_all = [&](uint32_t limit) {
+        flush_to(limit & ~15u);
+        if (lane < (limit & 15u)) dst[flushed + lane] = win[(flushed + lane) & M];
+    };
+    need(ip);
+    uint32_t total_len = 0, shift = 0;
+    for (;;) {
+        if (ip >= in_end || shift > 28u) return false;
+        const uint32_t b = in(ip++);
+        total_len |= (b & 0x7Fu) << shift;
+        if (!(b & 0x80u)) break;
+        shift += 7u;
+    }
+    if (total_len != cap) return false;
+    while (ip < in_end) {
+        need(ip);
+        // ---- 1. what an element starting at byte ip + lane would be ----------------------------------------------
+        const uint32_t s = ip + lane;
+        const bool inside = s < in_end;
+        uint32_t hs = 1, pl = 0, l = 0, off = 0;
+        bool lit = false, bad = false;
+        if (inside) {
+            const uint32_t tag = in(s), t = tag & 3u, avail = in_end - s - 1u;
+            if (t == 0u) {
+                lit = true;
+                l = tag >> 2;
+                if (l >= 60u) {
+                    const uint32_t nb = l - 59u;
+                    hs = 1u + nb;
+                    if (nb > avail) bad = true;
+                    else {
+                        l = 0;
+                        for (uint32_t k = 0; k < nb; ++k) l |= in(s + 1u + k) << (8u * k);
+                        if (l == 0xFFFFFFFFu) bad = true;
+                    }
+                }
+                if (!bad) { l += 1u; pl = l; if (l > in_end - s - hs) bad = true; }
+            } else if (t == 1u) {
+                hs = 2;
+                if (avail < 1u) bad = true; else { l = ((tag >> 2) & 7u) + 4u; off = ((tag >> 5) << 8) | in(s + 1u); }
+            } else if (t == 2u) {
+                hs = 3;
+                if (avail < 2u) bad = true; else { l = (tag >> 2) + 1u; off = in(s + 1u) | (in(s + 2u) << 8); }
+            } else {
+                hs = 5;
+                if (avail < 4u) bad = true; else { l = (tag >> 2) + 1u; off = in(s + 1u) | (in(s + 2u) << 8) | (in(s + 3u) << 16) | (in(s + 4u) << 24); }
+            }
+        }
+        // ---- 2. the chain of element starts from lane 0 (pointer doubling) ----------------------------------------
+        uint32_t far = 32u;                                      // where one step from here lands (32: beyond the window)
+        if (inside && !bad) { const uint32_t st = pl > 64u ? 64u : hs + pl; far = lane + st > 32u ? 32u : lane + st; }
+        uint32_t reach = 1u << lane;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const uint32_t r2 = g.shfl(reach, far & 31u), f2 = g.shfl(far, far & 31u);
+            if (far < 32u) { reach |= r2; far = f2; }
+        }
+        const uint32_t starts = g.shfl(reach, 0u);
+        const bool mine = inside && ((starts >> lane) & 1u);
+        if (g.ballot(mine && bad)) return false;
+        // ---- 3. output positions (saturating scan: a literal can claim up to 4 GiB) --------------------------------
+        const uint32_t x = mine ? l : 0u;
+        uint32_t incl = x;
+#pragma unroll
+        for (uint32_t o = 1; o < 32u; o <<= 1) {
+            const uint32_t t = g.shfl(incl, (lane - o) & 31u);
+            if (lane >= o) incl = incl + t < incl ? 0xFFFFFFFFu : incl + t;
+        }
+        const uint32_t total = g.shfl(incl, 31u);
+        if (total > cap - op) return false;
+        const uint32_t oe = op + (incl - x);                     // where my element's output starts
+        const bool cp = mine && !lit;
+        if (g.ballot(cp && (off == 0u || off > oe))) return false;
+        // ---- 4. copies ------------------------------------------------------------------------------------------
+        if (mine && lit && pl <= SHORT)
+            for (uint32_t i = 0; i < pl; ++i) win[(oe + i) & M] = (uint8_t)in(s + hs + i);
+        const uint32_t srcb = oe - off, srce = srcb + (l < off ? l : off);
+        const bool indep = cp && srce <= op && off <= NEAR;      // reads nothing this batch writes
+        g.sync();
+        if (indep)
+            for (uint32_t i = 0; i < l; ++i) win[(oe + i) & M] = win[(srcb + (off >= l ? i : i % off)) & M];
+        g.sync();
+        uint32_t deps = g.ballot(cp && !indep);
+        while (deps) {                                           // in stream order, each by the whole warp
+#if defined(__CUDA_ARCH__)
+            const uint32_t e = __ffs(deps) - 1u;
+#else
+            const uint32_t e = (uint32_t)__builtin_ctz(deps);
+#endif
+            deps &= deps - 1u;
+            const uint32_t eo = g.shfl(oe, e), eoff = g.shfl(off, e), el = g.shfl(l, e);
+            if (eoff <= NEAR) {
+                for (uint32_t i = lane; i < el; i += 32u) win[(eo + i) & M] = win[(eo - eoff + (eoff >= el ? i : i % eoff)) & M];
+            } else {                                             // further back than the ring reaches: through dst
+                flush_all(eo);
+                g.sync();
+                const uint8_t* from = dst + (eo - eoff);
+                for (uint32_t i = lane; i < el; i += 32u) win[(eo + i) & M] = from[i];              // (eoff > el here)
+            }
+            g.sync();
+        }
+        // the last element of the chain: where the next batch starts; a long literal is copied by the whole warp
+#if defined(__CUDA_ARCH__)
+        const uint32_t last = 31u - (uint32_t)__clz((int)(starts & g.ballot(inside)));
+#else
+        const uint32_t last = 31u - (uint32_t)__builtin_clz(starts & g.ballot(inside));
+#endif
+        const uint32_t l_pos = g.shfl(s + hs, last), l_pl = g.shfl(pl, last), l_out = g.shfl(oe, last);
+        if (l_pl > SHORT) {
+            uint32_t pos = l_pos, o2 = l_out, left = l_pl;
+            while (left) {
+                need(pos);
+                const uint32_t seg = left < 4096u ? left : 4096u;
+                for (uint32_t i = lane; i < seg; i += 32u) win[(o2 + i) & M] = (uint8_t)in(pos + i);
+                pos += seg; o2 += seg; left -= seg;
+                g.sync();
+                if (o2 - flushed >= 4096u) flush_to(o2 & ~15u);
+            }
+        }
+        ip = l_pos + l_pl;
+        op += total;
+        if (op - flushed >= 4096u) flush_to(op & ~15u);
+        g.sync();
+    }
+    flush_all(op);
+    g.sync();
+    return op == cap;
+}
+
 // ---- RLE / bit-packed hybrid -----------------------------------------------------------------------------------
 struct SplPqHybrid {
     const uint8_t* p; const uint8_t* end;
@@ -310,7 +481,9 @@ SPL_HD uint32_t spl_pq_decode_page(const G& g, const SplPqPage& pg, const uint8_
     if (ok && pg.codec == SPL_PQ_CODEC_SNAPPY && (!v2 || pg.v2_compressed)) {
         uint8_t* d = scratch + pg.scratch;
         if (body_len == 0u) ok = true;                                   // (writers emit no stream for an empty body)
-        else ok = g.win ? spl_snappy_decode_staged(g, body, pg.comp_size - lvl, d, body_len) : spl_snappy_decode(g, body, pg.comp_size - lvl, d, body_len);
+        else if (!g.win) ok = spl_snappy_decode(g, body, pg.comp_size - lvl, d, body_len);
+        else if constexpr (G::NL == 32u) ok = spl_snappy_decode_warp(g, body, pg.comp_size - lvl, d, body_len);
+        else ok = spl_snappy_decode_staged(g, body, pg.comp_size - lvl, d, body_len);
         body = d; base = SPL_PQ_IN_SCRATCH | pg.scratch;
         if (!ok) err |= SPL_PQ_ERR_SNAPPY;
     } else if (ok && pg.comp_size != pg.uncomp_size) {

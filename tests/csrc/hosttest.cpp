@@ -424,6 +424,47 @@ extern "C" int ht_jsonl(const uint8_t* text, uint32_t n, const char* field, uint
     return 0;
 }
 
+// 32 host threads in lock step: the lane group of the warp-wide snappy decoder (shuffles and ballots through a slot
+// array and a barrier; a collective that not every lane reaches hangs the test, as it would hang the warp)
+#include <pthread.h>
+#include <thread>
+struct HostWarpShared {
+    pthread_barrier_t bar;
+    uint32_t slot[2][32];
+    HostWarpShared() { pthread_barrier_init(&bar, nullptr, 32); }
+    ~HostWarpShared() { pthread_barrier_destroy(&bar); }
+};
+struct HostWarp {
+    static constexpr uint32_t NL = 32;
+    uint32_t lane;
+    uint8_t* win; uint8_t* inbuf;
+    HostWarpShared* sh;
+    mutable uint32_t phase = 0;
+    void sync() const { pthread_barrier_wait(&sh->bar); }
+    uint32_t shfl(uint32_t v, uint32_t src) const {
+        uint32_t* b = sh->slot[phase++ & 1u];
+        __atomic_store_n(&b[lane], v, __ATOMIC_RELAXED);
+        pthread_barrier_wait(&sh->bar);
+        return __atomic_load_n(&b[src & 31u], __ATOMIC_RELAXED);
+    }
+    uint32_t ballot(bool p) const {
+        uint32_t* b = sh->slot[phase++ & 1u];
+        __atomic_store_n(&b[lane], p ? 1u : 0u, __ATOMIC_RELAXED);
+        pthread_barrier_wait(&sh->bar);
+        uint32_t r = 0;
+        for (uint32_t i = 0; i < 32; ++i) r |= __atomic_load_n(&b[i], __ATOMIC_RELAXED) << i;
+        return r;
+    }
+};
+template <class Fn>
+static void run_host_warp(uint8_t* win, uint8_t* inbuf, Fn fn) {
+    HostWarpShared sh;
+    std::vector<std::thread> th;
+    for (uint32_t lane = 0; lane < 32; ++lane)
+        th.emplace_back([&, lane] { HostWarp g{lane, win, inbuf, &sh}; fn(g); });
+    for (auto& t : th) t.join();
+}
+
 // ---- Parquet ingestion (row N4): the host plan (spl_parquet_meta.cpp) and the page decoder of spl_parquet.h with a
 // lane group of one, batch by batch, as spl_api.cu drives the device.  Returns the row count, or -1 (malformed: err),
 // -2 (unsupported: err), -3 (a page raised error bits: info[0]), -4 (capacities).  info[1] = batches, info[2] = pages.
@@ -451,8 +492,15 @@ extern "C" long ht_parquet(const uint8_t* file, size_t n, const char* column, ui
         if (staged) { g.win = (uint8_t*)win.data(); g.inbuf = (uint8_t*)inbuf.data(); }   // the snappy decoder the device runs
         uint32_t e = 0;
         for (int pass = 0; pass < 2; ++pass)
-            for (size_t k = b.page0; k < b.page1; ++k)
-                if ((plan.pages[k].kind == SPL_PQ_DICT) == (pass == 0)) e |= spl_pq_decode_page(g, plan.pages[k], stage.data(), scratch.data(), R, D);
+            for (size_t k = b.page0; k < b.page1; ++k) {
+                if ((plan.pages[k].kind == SPL_PQ_DICT) != (pass == 0)) continue;
+                if (staged == 2)                                    // 32 lanes, as the device runs it
+                    run_host_warp(g.win, g.inbuf, [&](const HostWarp& hw) {
+                        const uint32_t pe = spl_pq_decode_page(hw, plan.pages[k], stage.data(), scratch.data(), R, D);
+                        if (pe) __atomic_fetch_or(&e, pe, __ATOMIC_RELAXED);
+                    });
+                else e |= spl_pq_decode_page(g, plan.pages[k], stage.data(), scratch.data(), R, D);
+            }
         if (e) { info[0] = e; return -3; }
         for (uint64_t r = 0; r < b.n_rows; ++r) {
             out_off[rows + r] = bytes;
@@ -474,7 +522,15 @@ extern "C" int ht_snappy(const uint8_t* src, uint32_t n, uint8_t* out, uint32_t 
     memcpy(s, src, n);
     SplPqOneLane g;
     if (staged) { g.win = (uint8_t*)win.data(); g.inbuf = (uint8_t*)inbuf.data(); }
-    const bool ok = staged ? spl_snappy_decode_staged(g, s, n, (uint8_t*)dst.data(), cap) : spl_snappy_decode(g, s, n, (uint8_t*)dst.data(), cap);
+    bool ok;
+    if (staged == 2) {
+        uint32_t oks = 0;
+        run_host_warp((uint8_t*)win.data(), (uint8_t*)inbuf.data(), [&](const HostWarp& hw) {
+            if (spl_snappy_decode_warp(hw, s, n, (uint8_t*)dst.data(), cap)) __atomic_fetch_or(&oks, 1u << hw.lane, __ATOMIC_RELAXED);
+        });
+        if (oks != 0 && oks != 0xFFFFFFFFu) return -1;          // the lanes disagree
+        ok = oks != 0;
+    } else ok = staged ? spl_snappy_decode_staged(g, s, n, (uint8_t*)dst.data(), cap) : spl_snappy_decode(g, s, n, (uint8_t*)dst.data(), cap);
     if (ok) memcpy(out, dst.data(), cap);
     return ok ? 1 : 0;
 }

@@ -20,7 +20,7 @@ def load():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in DEPS):
-        cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", LIB] + SRC
+        cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", LIB] + SRC
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode:
             raise RuntimeError(p.stdout + p.stderr)
@@ -112,6 +112,7 @@ def snappy(stream: bytes, size: int, staged: bool):
     """spl_parquet.h snappy decoders on a raw stream -> bytes, or None if the stream is refused"""
     out = np.zeros(size + 16, dtype=np.uint8)
     ok = load().ht_snappy(stream, len(stream), out.ctypes.data, size, int(staged))
+    assert ok >= 0, "the lanes of the warp decoder disagree on the outcome"
     return out[:size].tobytes() if ok else None
 
 
@@ -124,7 +125,8 @@ class ParquetError(Exception):
 def parquet(data: bytes, column: str = "text", batch_bytes: int = 0, text_cap: int = 0, max_rows: int = 0, staged: bool = True):
     """spl_parquet_meta.cpp + the page decoder of spl_parquet.h over a whole Parquet file -> (list of row bytes, info).
     text_cap / max_rows: capacities of the output (defaults are generous guesses; dictionary pages can expand).
-    staged: the snappy decoder that works out of a 64 KiB ring + input slots (the device's), else the plain one."""
+    staged: True / 1 the one-lane snappy decoder that works out of a 64 KiB ring + input slots, False / 0 the plain
+    one, 2 the warp-wide decoder the device runs (32 host threads in lock step: slow, keep the files small)."""
     n = len(data)
     text_cap = text_cap or max(64 * n, 1 << 20)
     max_rows = max_rows or max(8 * n, 1 << 16)

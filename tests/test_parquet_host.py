@@ -157,15 +157,48 @@ def test_snappy_streams_by_hand():
                 for i in range(l):
                     out.append(out[len(out) - off])
         full = _varint(len(out)) + bytes(stream)
-        for staged in (False, True):
+        for staged in (False, True) + ((2,) if len(full) < 40000 or trial % 10 == 0 else ()):
             assert hostlib.snappy(full, len(out), staged) == bytes(out), (trial, staged)
         # damaged: wrong size, cut stream, offset beyond the output
         assert hostlib.snappy(full, len(out) + 1, True) is None and hostlib.snappy(full, len(out) + 1, False) is None
         if len(full) > 3:
             cut = full[:rng.randrange(1, len(full))]
             assert hostlib.snappy(cut, len(out), True) == hostlib.snappy(cut, len(out), False)
+            if len(cut) < 20000:
+                assert hostlib.snappy(cut, len(out), 2) is None
     bad = _varint(10) + bytes([(5 - 1) << 2]) + b"hello" + bytes([2 | ((5 - 1) << 2)]) + (6).to_bytes(2, "little")
-    assert hostlib.snappy(bad, 10, True) is None and hostlib.snappy(bad, 10, False) is None
+    assert hostlib.snappy(bad, 10, True) is None and hostlib.snappy(bad, 10, False) is None and hostlib.snappy(bad, 10, 2) is None
+
+
+def test_warp_wide_decoder_on_written_files():
+    """the 32-lane snappy decoder (what the device runs), emulated by 32 threads in lock step, on pages pyarrow wrote:
+    text (short elements), repetitive text (overlapping copies), incompressible rows (long literals), dictionary pages"""
+    rng = random.Random(23)
+    texts = make_texts(rng, 700, 0.1)
+    rep = ["ab" * 3000, "x" * 9000, "", "abc" * 3 + "z" * 100, ("0123456789" * 7 + "\n") * 200] * 3
+    blobs = [bytes(rng.randrange(256) for _ in range(rng.randint(3000, 9000))) if k % 3 else b"hello world " * rng.randint(1, 300) for k in range(40)]
+    cases = [(pa.array(texts, pa.string()), dict(compression="snappy", use_dictionary=False)),
+             (pa.array(texts, pa.string()), dict(compression="snappy", data_page_version="2.0", data_page_size=20000)),
+             (pa.array(make_texts(rng, 2000, 0.2, repeat=True), pa.string()), dict(compression="snappy")),
+             (pa.array(rep, pa.string()), dict(compression="snappy", use_dictionary=False)),
+             (pa.array(blobs, pa.binary()), dict(compression="snappy", use_dictionary=False))]
+    for col, kw in cases:
+        data = write(pa.table({"text": col}), **kw)
+        want = expect(col.to_pylist())
+        assert hostlib.parquet(data, "text", staged=2)[0] == want, kw
+    # damaged pages: same verdict as the plain decoder (an error, or the same rows)
+    good = write(pa.table({"text": pa.array(texts[:200])}), compression="snappy", use_dictionary=False)
+    for k in range(25):
+        b = bytearray(good)
+        for _ in range(3):
+            b[rng.randrange(60, len(b) - 300)] ^= 1 << rng.randrange(8)
+        res = []
+        for staged in (0, 2):
+            try:
+                res.append(hostlib.parquet(bytes(b), "text", text_cap=1 << 21, max_rows=1 << 12, staged=staged)[0])
+            except hostlib.ParquetError as e:
+                res.append(e.code)
+        assert res[0] == res[1], k
 
 
 def test_refusals_say_what_to_do():

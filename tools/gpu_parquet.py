@@ -25,6 +25,7 @@ def best(f, n=4):
 
 for name, kw in (("snappy, dictionary (pyarrow defaults)", dict(compression="snappy")),
                  ("snappy, PLAIN", dict(compression="snappy", use_dictionary=False)),
+                 ("snappy, PLAIN, 64 KiB pages", dict(compression="snappy", use_dictionary=False, data_page_size=65536)),
                  ("uncompressed, PLAIN", dict(compression="none", use_dictionary=False))):
     if len(sys.argv) > 1 and sys.argv[1] not in name:
         continue
