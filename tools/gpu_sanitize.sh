@@ -37,6 +37,26 @@ tok = Tokenizer.from_pretrained("cl100k_base", devices=[0])
 ids, off = tok.encode_jsonl(join_lines(lines))
 assert len(off) == len(want) + 1
 print("jsonl", len(want), len(ids), flush=True)
+# Parquet ingestion (row N4): snappy (warp-wide decoder), dictionary pages, V2 pages, nulls
+import io, pyarrow as pa, pyarrow.parquet as pq
+ptexts = [None if rng.random() < 0.1 else t for t in texts[:250]] * 3
+for kw in (dict(compression="snappy"), dict(compression="snappy", use_dictionary=False, data_page_version="2.0", data_page_size=4000), dict(compression="none")):
+    buf = io.BytesIO(); pq.write_table(pa.table({"text": pa.array(ptexts, pa.string())}), buf, **kw)
+    ids, off = tok.encode_parquet(buf.getvalue(), "text")
+    flat, o = ids.tolist(), off.tolist()
+    assert [flat[o[k]:o[k + 1]] for k in range(len(ptexts))] == tok.encode_batch([t or "" for t in ptexts])
+print("parquet", len(ptexts), flush=True)
+# tiles dense in ids (k_emit in several phases) and user special-token sets that overlap (candidate walk)
+rare = "\u9f98\u9750\u9f49\u7228\u706a\u9ea4\u9c7b\u9955"
+dense = ["".join(rng.choice(rare) for _ in range(4000)), "".join(rng.choice("!?;:") + rng.choice("\n\t") for _ in range(6000)),
+         "".join(chr(rng.randrange(0x80, 0x250)) for _ in range(4000))]
+a = tok.encode_batch(dense)
+pc = P.PRESETS["cl100k_base"]
+sp = {"<a>": 200001, "<a><b>": 200002, "<b>": 200003, "b><": 200004}
+tok2 = Tokenizer.from_bytes(P.load_vocab_bytes(pc.vocab_file), pc.pattern, sp)
+alpha = "".join(sp) + " xy\n"
+b = tok2.encode_batch_with_special(["", "<a><b>", "x<a><b><a>"] + ["".join(rng.choice(alpha) for _ in range(rng.randint(0, 80))) for _ in range(200)])
+print("dense", sum(len(x) for x in a), "overlapping specials", sum(len(x) for x in b), flush=True)
 PY
 for tool in memcheck racecheck; do
   timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python /tmp/san_driver.py > gpurun_out/sanitizer_$tool.log 2>&1
