@@ -84,6 +84,7 @@ struct spl_tokenizer {
     bool trace = false;                     // SPL_TRACE=1: per-chunk timeline of spl_encode_batch on stderr
     bool use_graph = true;                  // SPL_GRAPH=0: plain launches in spl_encode_batch as well
     bool charref = true;                    // SPL_NO_CHARREF=1: characters of two or three ids get miss-list entries (the path for passes beyond ~1.7 GB)
+    bool bpe_overlap = true;                // SPL_BPE_OVERLAP=0: the graph of a pass is a plain chain (k_bpe_long behind k_bpe)
     bool dedup = true;                      // SPL_NO_DEDUP=1: every long piece goes through the merge loop, repeated or not
     int trace_chunk = -1;                   // SPL_TRACE_CHUNK=k: with SPL_TRACE, per-kernel times of the k-th chunk
     uint64_t chunk_bytes = 0;               // pipeline chunk size of spl_encode_batch (0 = automatic)
@@ -420,8 +421,23 @@ int enqueue_encode_graph(spl_tokenizer* tk, DevCtx& dc, cudaStream_t st, const E
         g.knodes.assign(n, nullptr); g.funcs.assign(n, nullptr);
         CUDA_TRY(cudaGraphCreate(&g.graph, 0), tk->err);
         CUDA_TRY(cudaGraphAddMemsetNode(&g.mnode, g.graph, nullptr, 0, &mp), tk->err);
+        // A chain, except that k_bpe_long runs beside k_bpe (their miss lists are disjoint, everything they share is
+        // atomic counters): on text with few long pieces k_bpe_long is a handful of warps walking long merge chains
+        // -- pure latency with the device idle.  Its node is created first: its blocks without work leave at once and
+        // k_bpe's fill the SMs next to the few that have some.  k_bpe_fin waits for both.
         cudaGraphNode_t prev = g.mnode;
         for (int i = 0; i < n; ++i) {
+            const bool fork = tk->bpe_overlap && i + 2 < n && !strcmp(d[i].name, "k_bpe") && !strcmp(d[i + 1].name, "k_bpe_long");
+            if (fork) {
+                CUDA_TRY(cudaGraphAddKernelNode(&g.knodes[i + 1], g.graph, &prev, 1, &kp[i + 1]), tk->err);
+                CUDA_TRY(cudaGraphAddKernelNode(&g.knodes[i], g.graph, &prev, 1, &kp[i]), tk->err);
+                cudaGraphNode_t both[2] = {g.knodes[i], g.knodes[i + 1]};
+                CUDA_TRY(cudaGraphAddKernelNode(&g.knodes[i + 2], g.graph, both, 2, &kp[i + 2]), tk->err);
+                g.funcs[i] = d[i].func; g.funcs[i + 1] = d[i + 1].func; g.funcs[i + 2] = d[i + 2].func;
+                prev = g.knodes[i + 2];
+                i += 2;
+                continue;
+            }
             CUDA_TRY(cudaGraphAddKernelNode(&g.knodes[i], g.graph, &prev, 1, &kp[i]), tk->err);
             prev = g.knodes[i];
             g.funcs[i] = d[i].func;
@@ -556,6 +572,7 @@ int spl_create(const uint8_t* vocab, size_t vocab_len, int pattern_id, uint32_t 
     if (const char* nd = getenv("SPL_NO_DEDUP")) tk->dedup = nd[0] == '0';
     if (const char* nc = getenv("SPL_NO_CHARREF")) tk->charref = nc[0] == '0';
     if (const char* gr = getenv("SPL_GRAPH")) tk->use_graph = gr[0] != '0';
+    if (const char* bo = getenv("SPL_BPE_OVERLAP")) tk->bpe_overlap = bo[0] != '0';
     if (const char* cb = getenv("SPL_CHUNK_BYTES")) tk->chunk_bytes = strtoull(cb, nullptr, 10);
     if (const char* rp = getenv("SPL_RAMP")) {
         tk->ramp_div.clear();
@@ -680,7 +697,10 @@ int spl_encode_batch_device(spl_tokenizer* tk, int dev_index, const uint8_t* d_b
         }
         int launches = 0;
         EncodeArgs ea{d_bytes, n_bytes, d_offsets, 0, n_docs, d_ids, ids_capacity, d_out_offsets, nullptr, nullptr, nullptr};
-        if ((rc = enqueue_encode(tk, dc, st, ea, with_special, prof, w, launches))) return rc;
+        // one graph launch (k_bpe_long beside k_bpe) unless per-kernel events are wanted
+        if (tk->use_graph && !prof && !is_sentencepiece(tk)) rc = enqueue_encode_graph(tk, dc, st, ea, with_special, w, launches);
+        else rc = enqueue_encode(tk, dc, st, ea, with_special, prof, w, launches);
+        if (rc) return rc;
         CUDA_TRY(cudaGetLastError(), tk->err);
         if (!n_tokens_out) return SPL_OK;
         uint32_t h_counters[4];

@@ -1303,6 +1303,7 @@ __device__ void chunk_scan_block(const SplWork& w, uint32_t* smem) {
                 const uint32_t ta = __shfl_sync(FULL, (uint32_t)incl, 31), tb = __shfl_sync(FULL, (uint32_t)(incl >> 32), 31);
                 carry += (uint64_t)ta | ((uint64_t)tb << 32);
             }
+            __syncwarp();                            // every lane has read *s_carry (the shuffles order that in practice; this says so)
             if (tid == 0) *s_carry = carry;
         }
         __syncthreads();

@@ -289,37 +289,36 @@ SPL_HD bool spl_snappy_decode_warp(const G& g, const uint8_t* src, uint32_t n, u
     if (total_len != cap) return false;
     while (ip < in_end) {
         need(ip);
-        // ---- 1. what an element starting at byte ip + lane would be ----------------------------------------------
+        // ---- 1. what an element starting at byte ip + lane would be (no branches: the lanes' tags differ) ---------
         const uint32_t s = ip + lane;
         const bool inside = s < in_end;
         uint32_t hs = 1, pl = 0, l = 0, off = 0;
         bool lit = false, bad = false;
-        if (inside) {
-            const uint32_t tag = in(s), t = tag & 3u, avail = in_end - s - 1u;
-            if (t == 0u) {
-                lit = true;
-                l = tag >> 2;
-                if (l >= 60u) {
-                    const uint32_t nb = l - 59u;
-                    hs = 1u + nb;
-                    if (nb > avail) bad = true;
-                    else {
-                        l = 0;
-                        for (uint32_t k = 0; k < nb; ++k) l |= in(s + 1u + k) << (8u * k);
-                        if (l == 0xFFFFFFFFu) bad = true;
-                    }
-                }
-                if (!bad) { l += 1u; pl = l; if (l > in_end - s - hs) bad = true; }
-            } else if (t == 1u) {
-                hs = 2;
-                if (avail < 1u) bad = true; else { l = ((tag >> 2) & 7u) + 4u; off = ((tag >> 5) << 8) | in(s + 1u); }
-            } else if (t == 2u) {
-                hs = 3;
-                if (avail < 2u) bad = true; else { l = (tag >> 2) + 1u; off = in(s + 1u) | (in(s + 2u) << 8); }
+        {
+            // the eight bytes from s on: two aligned words of the input slots
+            const uint32_t* in32 = reinterpret_cast<const uint32_t*>(inbuf);
+            const uint32_t wi = (s & (SPL_SNAPPY_INBUF - 1u)) >> 2, sh = (s & 3u) * 8u;
+            const uint32_t w0 = in32[wi], w1 = in32[(wi + 1u) & (SPL_SNAPPY_INBUF / 4u - 1u)], w2 = in32[(wi + 2u) & (SPL_SNAPPY_INBUF / 4u - 1u)];
+            const uint32_t lo = sh ? (w0 >> sh) | (w1 << (32u - sh)) : w0, hi = sh ? (w1 >> sh) | (w2 << (32u - sh)) : w1;
+            const uint32_t tag = lo & 0xFFu, t = tag & 3u, n6 = tag >> 2;
+            const uint32_t w = (lo >> 8) | (hi << 24);                   // the four bytes behind the tag
+            const uint32_t avail = inside ? in_end - s - 1u : 0u;
+            lit = t == 0u;
+            const uint32_t nb = lit ? (n6 >= 60u ? n6 - 59u : 0u) : (t == 1u ? 1u : (t == 2u ? 2u : 4u));   // bytes behind the tag that belong to the header
+            hs = 1u + nb;
+            const uint32_t field = nb >= 4u ? w : (w & ((1u << (8u * nb)) - 1u));
+            if (lit) {
+                l = nb ? field : n6;
+                bad = nb > avail || l == 0xFFFFFFFFu;
+                l += 1u;
+                pl = l;
+                bad = bad || l > in_end - s - hs;                        // (evaluated only where it matters: mine && bad)
             } else {
-                hs = 5;
-                if (avail < 4u) bad = true; else { l = (tag >> 2) + 1u; off = in(s + 1u) | (in(s + 2u) << 8) | (in(s + 3u) << 16) | (in(s + 4u) << 24); }
+                l = t == 1u ? ((n6 & 7u) + 4u) : n6 + 1u;
+                off = t == 1u ? (((tag >> 5) << 8) | field) : field;
+                bad = nb > avail;
             }
+            if (!inside) { bad = true; lit = false; pl = 0; l = 0; }
         }
         // ---- 2. the chain of element starts from lane 0 (pointer doubling) ----------------------------------------
         uint32_t far = 32u;                                      // where one step from here lands (32: beyond the window)
@@ -347,13 +346,22 @@ SPL_HD bool spl_snappy_decode_warp(const G& g, const uint8_t* src, uint32_t n, u
         const bool cp = mine && !lit;
         if (g.ballot(cp && (off == 0u || off > oe))) return false;
         // ---- 4. copies ------------------------------------------------------------------------------------------
-        if (mine && lit && pl <= SHORT)
-            for (uint32_t i = 0; i < pl; ++i) win[(oe + i) & M] = (uint8_t)in(s + hs + i);
+        if (mine && lit && pl <= SHORT) {
+            uint32_t ps = (s + hs) & (SPL_SNAPPY_INBUF - 1u), pd = oe & M;
+            for (uint32_t i = 0; i < pl; ++i) { win[pd] = inbuf[ps]; ps = (ps + 1u) & (SPL_SNAPPY_INBUF - 1u); pd = (pd + 1u) & M; }
+        }
         const uint32_t srcb = oe - off, srce = srcb + (l < off ? l : off);
         const bool indep = cp && srce <= op && off <= NEAR;      // reads nothing this batch writes
         g.sync();
-        if (indep)
-            for (uint32_t i = 0; i < l; ++i) win[(oe + i) & M] = win[(srcb + (off >= l ? i : i % off)) & M];
+        if (indep) {
+            uint32_t pd = oe & M;
+            if (off >= l) {
+                uint32_t ps = srcb & M;
+                for (uint32_t i = 0; i < l; ++i) { win[pd] = win[ps]; ps = (ps + 1u) & M; pd = (pd + 1u) & M; }
+            } else {                                             // the pattern of `off` bytes repeats
+                for (uint32_t i = 0, j = 0; i < l; ++i) { win[pd] = win[(srcb + j) & M]; pd = (pd + 1u) & M; if (++j == off) j = 0; }
+            }
+        }
         g.sync();
         uint32_t deps = g.ballot(cp && !indep);
         while (deps) {                                           // in stream order, each by the whole warp
