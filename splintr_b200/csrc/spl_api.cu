@@ -84,7 +84,8 @@ struct spl_tokenizer {
     bool trace = false;                     // SPL_TRACE=1: per-chunk timeline of spl_encode_batch on stderr
     bool use_graph = true;                  // SPL_GRAPH=0: plain launches in spl_encode_batch as well
     bool charref = true;                    // SPL_NO_CHARREF=1: characters of two or three ids get miss-list entries (the path for passes beyond ~1.7 GB)
-    bool bpe_overlap = true;                // SPL_BPE_OVERLAP=0: the graph of a pass is a plain chain (k_bpe_long behind k_bpe)
+    bool use_pdl = false;                   // SPL_PDL=1: programmatic edges between the kernel nodes of a pass's graph (measured: nothing on cfg2 / cfg3 / cfg5, -10 % on cfg4)
+    int bpe_overlap = 0;                    // SPL_BPE_OVERLAP: 0 the graph of a pass is a plain chain; 1: k_bpe_long beside k_bpe, its node first; 2: k_bpe's node first, on 4 blocks per SM so that one block of k_bpe_long fits beside them (measured: +-3 % either way)
     bool dedup = true;                      // SPL_NO_DEDUP=1: every long piece goes through the merge loop, repeated or not
     int trace_chunk = -1;                   // SPL_TRACE_CHUNK=k: with SPL_TRACE, per-kernel times of the k-th chunk
     uint64_t chunk_bytes = 0;               // pipeline chunk size of spl_encode_batch (0 = automatic)
@@ -421,16 +422,25 @@ int enqueue_encode_graph(spl_tokenizer* tk, DevCtx& dc, cudaStream_t st, const E
         g.knodes.assign(n, nullptr); g.funcs.assign(n, nullptr);
         CUDA_TRY(cudaGraphCreate(&g.graph, 0), tk->err);
         CUDA_TRY(cudaGraphAddMemsetNode(&g.mnode, g.graph, nullptr, 0, &mp), tk->err);
-        // A chain, except that k_bpe_long runs beside k_bpe (their miss lists are disjoint, everything they share is
-        // atomic counters): on text with few long pieces k_bpe_long is a handful of warps walking long merge chains
-        // -- pure latency with the device idle.  Its node is created first: its blocks without work leave at once and
-        // k_bpe's fill the SMs next to the few that have some.  k_bpe_fin waits for both.
+        // A chain.  (SPL_BPE_OVERLAP=1 / 2 puts k_bpe_long beside k_bpe -- their miss lists are disjoint, everything
+        // they share is atomic counters -- with k_bpe_fin waiting for both.  Both kernels size themselves for the whole
+        // device, so whichever node is dispatched first keeps the other out: cfg4 gains 3 % one way and loses 13 % the
+        // other, cfg5 the reverse; the chain is the default.)
         cudaGraphNode_t prev = g.mnode;
+        // kernel -> kernel edges are programmatic (SPL_PDL_ENTER in spl_kernels.cuh): the next kernel's blocks are
+        // scheduled into the tail of the one before
+        const bool pdl = tk->use_pdl && tk->bpe_overlap == 0;
         for (int i = 0; i < n; ++i) {
             const bool fork = tk->bpe_overlap && i + 2 < n && !strcmp(d[i].name, "k_bpe") && !strcmp(d[i + 1].name, "k_bpe_long");
             if (fork) {
-                CUDA_TRY(cudaGraphAddKernelNode(&g.knodes[i + 1], g.graph, &prev, 1, &kp[i + 1]), tk->err);
-                CUDA_TRY(cudaGraphAddKernelNode(&g.knodes[i], g.graph, &prev, 1, &kp[i]), tk->err);
+                if (tk->bpe_overlap == 2) {
+                    kp[i].gridDim = dim3(std::min<unsigned>(kp[i].gridDim.x, 4u * (unsigned)dc.num_sms));
+                    CUDA_TRY(cudaGraphAddKernelNode(&g.knodes[i], g.graph, &prev, 1, &kp[i]), tk->err);
+                    CUDA_TRY(cudaGraphAddKernelNode(&g.knodes[i + 1], g.graph, &prev, 1, &kp[i + 1]), tk->err);
+                } else {
+                    CUDA_TRY(cudaGraphAddKernelNode(&g.knodes[i + 1], g.graph, &prev, 1, &kp[i + 1]), tk->err);
+                    CUDA_TRY(cudaGraphAddKernelNode(&g.knodes[i], g.graph, &prev, 1, &kp[i]), tk->err);
+                }
                 cudaGraphNode_t both[2] = {g.knodes[i], g.knodes[i + 1]};
                 CUDA_TRY(cudaGraphAddKernelNode(&g.knodes[i + 2], g.graph, both, 2, &kp[i + 2]), tk->err);
                 g.funcs[i] = d[i].func; g.funcs[i + 1] = d[i + 1].func; g.funcs[i + 2] = d[i + 2].func;
@@ -438,14 +448,29 @@ int enqueue_encode_graph(spl_tokenizer* tk, DevCtx& dc, cudaStream_t st, const E
                 i += 2;
                 continue;
             }
-            CUDA_TRY(cudaGraphAddKernelNode(&g.knodes[i], g.graph, &prev, 1, &kp[i]), tk->err);
+            if (pdl && i > 0) {
+                CUDA_TRY(cudaGraphAddKernelNode(&g.knodes[i], g.graph, nullptr, 0, &kp[i]), tk->err);
+                cudaGraphEdgeData ed;
+                memset(&ed, 0, sizeof(ed));
+                ed.from_port = cudaGraphKernelNodePortProgrammatic; ed.type = cudaGraphDependencyTypeProgrammatic;
+                if (cudaGraphAddDependencies_v2(g.graph, &prev, &g.knodes[i], &ed, 1) != cudaSuccess) {
+                    cudaGetLastError();                          // (a driver without the edge type: ordinary edges from here on)
+                    tk->use_pdl = false;
+                    CUDA_TRY(cudaGraphAddDependencies(g.graph, &prev, &g.knodes[i], 1), tk->err);
+                }
+            } else {
+                CUDA_TRY(cudaGraphAddKernelNode(&g.knodes[i], g.graph, &prev, 1, &kp[i]), tk->err);
+            }
             prev = g.knodes[i];
             g.funcs[i] = d[i].func;
         }
         CUDA_TRY(cudaGraphInstantiate(&g.exec, g.graph, 0), tk->err);
     } else {
         CUDA_TRY(cudaGraphExecMemsetNodeSetParams(g.exec, g.mnode, &mp), tk->err);
-        for (int i = 0; i < n; ++i) CUDA_TRY(cudaGraphExecKernelNodeSetParams(g.exec, g.knodes[i], &kp[i]), tk->err);
+        for (int i = 0; i < n; ++i) {
+            if (tk->bpe_overlap == 2 && !strcmp(d[i].name, "k_bpe")) kp[i].gridDim = dim3(std::min<unsigned>(kp[i].gridDim.x, 4u * (unsigned)dc.num_sms));
+            CUDA_TRY(cudaGraphExecKernelNodeSetParams(g.exec, g.knodes[i], &kp[i]), tk->err);
+        }
     }
     CUDA_TRY(cudaGraphLaunch(g.exec, st), tk->err);
     launches += n;
@@ -572,7 +597,8 @@ int spl_create(const uint8_t* vocab, size_t vocab_len, int pattern_id, uint32_t 
     if (const char* nd = getenv("SPL_NO_DEDUP")) tk->dedup = nd[0] == '0';
     if (const char* nc = getenv("SPL_NO_CHARREF")) tk->charref = nc[0] == '0';
     if (const char* gr = getenv("SPL_GRAPH")) tk->use_graph = gr[0] != '0';
-    if (const char* bo = getenv("SPL_BPE_OVERLAP")) tk->bpe_overlap = bo[0] != '0';
+    if (const char* bo = getenv("SPL_BPE_OVERLAP")) tk->bpe_overlap = atoi(bo);
+    if (const char* pd = getenv("SPL_PDL")) tk->use_pdl = pd[0] != '0';
     if (const char* cb = getenv("SPL_CHUNK_BYTES")) tk->chunk_bytes = strtoull(cb, nullptr, 10);
     if (const char* rp = getenv("SPL_RAMP")) {
         tk->ramp_div.clear();

@@ -1490,6 +1490,7 @@ __device__ __forceinline__ void emit_stage(const SplWork& w, EmitSmem& sm, const
 
 __global__ void __launch_bounds__(SPL_THREADS, 8) k_emit(SplWork w) {
     __shared__ EmitSmem sm;
+    SPL_PDL_ENTER();
     if (w.counters[SPL_CTR_ERR] & SPL_DEVERR_OFFSETS) {            // rejected offsets: nothing was computed; deliver the flag
         if (blockIdx.x == 0 && threadIdx.x == 0 && w.host_meta) { w.host_meta[0] = 0; w.host_meta[2] = 0; w.host_meta[1] = w.counters[SPL_CTR_ERR]; }
         return;
@@ -1634,6 +1635,7 @@ struct EmitDirectSmem {
 
 __global__ void __launch_bounds__(SPL_THREADS, 8) k_emit_direct(SplWork w) {
     __shared__ EmitDirectSmem sm;
+    SPL_PDL_ENTER();
     if (w.counters[SPL_CTR_ERR] & SPL_DEVERR_OFFSETS) {            // rejected offsets: nothing was computed; deliver the flag
         if (blockIdx.x == 0 && threadIdx.x == 0 && w.host_meta) { w.host_meta[0] = 0; w.host_meta[2] = 0; w.host_meta[1] = w.counters[SPL_CTR_ERR]; }
         return;

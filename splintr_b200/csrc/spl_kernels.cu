@@ -22,6 +22,7 @@
 // k_mark_docs
 // ------------------------------------------------------------------------------------------
 __global__ void k_mark_docs(SplWork w) {
+    SPL_PDL_ENTER();
     uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d > w.n_docs) return;
     uint64_t s = w.doc_off[d] - w.off_base;

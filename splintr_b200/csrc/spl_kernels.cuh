@@ -112,7 +112,19 @@ enum : uint32_t { SPL_CTR_ERR = 1, SPL_CTR_HUGE_POOL = 2 /* 64 bit: words 2 and 
 enum : uint32_t { SPL_DEVERR_OFFSETS = 1u, SPL_DEVERR_HUGE_POOL = 2u };
 // Every kernel behind k_mark_docs starts with this: document offsets that k_mark_docs rejected must never be used as
 // indices (the host reports SPL_ERR_INVALID_ARG from the flag; k_emit still delivers it)
-#define SPL_RETURN_IF_BAD_OFFSETS(w) do { if ((w).counters[SPL_CTR_ERR] & SPL_DEVERR_OFFSETS) return; } while (0)
+// Programmatic dependent launch: the kernels of a pass are the nodes of a graph whose edges are of type Programmatic
+// (spl_api.cu: enqueue_encode_graph).  A kernel first waits for the grid in front of it (all of its memory is visible
+// then), and at once lets the grid behind it be scheduled: that grid's blocks come in as this one's last blocks leave
+// and sit at their own wait -- the launch latency and the ramp of every kernel are hidden in the tail of the one
+// before.  Both instructions do nothing in a plain launch.  Off by default (SPL_PDL=1): inside a graph the gaps between
+// the kernels are already too small for this to show, and on cfg4 the early blocks of the kernels behind k_bpe_long take
+// resources from its tail (0.80 -> 0.89 ms).
+#if defined(__CUDA_ARCH__)
+#define SPL_PDL_ENTER() do { asm volatile("griddepcontrol.wait;" ::: "memory"); asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); } while (0)
+#else
+#define SPL_PDL_ENTER() do { } while (0)
+#endif
+#define SPL_RETURN_IF_BAD_OFFSETS(w) do { SPL_PDL_ENTER(); if ((w).counters[SPL_CTR_ERR] & SPL_DEVERR_OFFSETS) return; } while (0)
 
 // optional per-kernel device timing: ev[i] is recorded before kernel i, ev[n] after the last
 #define SPL_PROF_MAX 16
