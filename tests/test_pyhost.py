@@ -55,3 +55,32 @@ def test_ids_to_lists(ph):
     assert got == [flat[o[i]:o[i + 1]] for i in range(len(counts))]
     assert all(type(x) is int for row in got[:50] for x in row)
     assert ph.ids_to_lists(ids.ctypes.data, off.ctypes.data, 0) == []
+
+
+def test_ids_to_lists_shares_int_objects_and_leaves_gc_alone(ph):
+    """token ids below 2^21 come from a per-process table of int objects (made on first use); the result is
+    indistinguishable from fresh ints, the garbage collector is back on afterwards, and repeated calls agree"""
+    import gc
+    import sys
+    rng = np.random.default_rng(9)
+    ids = np.concatenate([rng.integers(0, 200_000, size=50_000), [0, 1, 255, 256, 257, 2 ** 21 - 1, 2 ** 21, 2 ** 21 + 1, 2 ** 32 - 1]]).astype(np.uint32)
+    off = np.array([0, 10, 10, 5000, len(ids)], dtype=np.uint64)
+    want = [ids.tolist()[int(off[i]):int(off[i + 1])] for i in range(4)]
+    assert gc.isenabled()
+    a = ph.ids_to_lists(ids.ctypes.data, off.ctypes.data, 4)
+    assert gc.isenabled()
+    b = ph.ids_to_lists(ids.ctypes.data, off.ctypes.data, 4)
+    assert a == want and b == want
+    assert all(type(x) is int for x in a[3][-9:])
+    a[0].append(7); a[2][0] = -1                                    # the lists are the caller's own
+    assert b == want
+    x = int(ids[20])
+    before = sys.getrefcount(b[2][10])
+    del a
+    assert sys.getrefcount(b[2][10]) <= before                       # references were counted: dropping lists releases them
+    gc.disable()
+    try:
+        ph.ids_to_lists(ids.ctypes.data, off.ctypes.data, 4)
+        assert not gc.isenabled()                                    # a collector the caller turned off stays off
+    finally:
+        gc.enable()
