@@ -229,7 +229,7 @@ class Tokenizer:
         ph.pack_copy(texts, data.ctypes.data)
         return data[:total], offsets
 
-    def encode_packed(self, data, offsets: np.ndarray, with_special: bool = False, return_stats: bool = False):
+    def encode_packed(self, data, offsets: np.ndarray, with_special: bool = False, return_stats: bool = False, _as_lists: bool = False):
         """Zero-copy surface: `data` = concatenated UTF-8 (bytes / bytearray / uint8 array /
         integer host address), `offsets` = uint64[n_docs+1].  Returns (ids uint32[n_tokens],
         out_offsets uint64[n_docs+1]) as numpy arrays."""
@@ -268,6 +268,10 @@ class Tokenizer:
             raise RuntimeError(f"splintr_b200: {msg} (code {rc})")
         try:
             n_tok = lib.spl_result_n_tokens(res)
+            if _as_lists:                              # list[list[int]] straight from the pinned result (no copy in between)
+                ph = _lib.pyhost()
+                if ph is not None:
+                    return ph.ids_to_lists(int(lib.spl_result_ids(res) or 0), int(lib.spl_result_offsets(res)), n_docs)
             ids = np.empty(n_tok, dtype=np.uint32)
             out_off = np.empty(n_docs + 1, dtype=np.uint64)
             if n_tok:
@@ -278,6 +282,9 @@ class Tokenizer:
                 lib.spl_result_stats(res, ctypes.byref(st))
                 stats = {f: getattr(st, f) for f, _ in _lib.SplStats._fields_}
                 return ids, out_off, stats
+            if _as_lists:
+                flat, o = ids.tolist(), out_off.tolist()
+                return [flat[o[i]:o[i + 1]] for i in range(n_docs)]
             return ids, out_off
         finally:
             lib.spl_result_free(res)
@@ -519,13 +526,8 @@ class Tokenizer:
         return self.encode_packed(data, offsets, with_special)
 
     def _encode_many(self, texts: Sequence[str], with_special: bool) -> List[List[int]]:
-        ids, off = self.encode_batch_packed(texts, with_special)
-        ph = _lib.pyhost()
-        if ph is not None:
-            return ph.ids_to_lists(ids.ctypes.data, off.ctypes.data, len(texts))
-        flat = ids.tolist()
-        o = off.tolist()
-        return [flat[o[i]:o[i + 1]] for i in range(len(texts))]
+        data, offsets = self._pack(texts)
+        return self.encode_packed(data, offsets, with_special, _as_lists=True)
 
     def encode(self, text: str) -> List[int]:
         """bindings.rs:254-256 -> tokenizer.rs:729-808 (special strings are plain text)."""
