@@ -5,7 +5,8 @@
 //   k_pq_pages    one warp per page: snappy (all lanes parse the element stream alike, all lanes copy; input slots and
 //                 a 64 KiB ring of output in shared memory, so an element touches no global memory), definition
 //                 levels, PLAIN lengths or dictionary indices -> one (source offset, length) span per row;
-//                 launched twice: dictionary pages, then data pages (which read the dictionary's spans)
+//                 launched twice: dictionary pages and PLAIN data pages, then the dictionary-encoded data pages (which
+//                 read the dictionary's spans)
 //   k_pq_bsum     row lengths summed per block of 2 048 rows        k_pq_bscan   exclusive prefix over the blocks
 //   k_pq_offsets  u64 document offsets (row r: bytes of the rows in front of it), total -> counters
 //   k_pq_copy     one block per 16 KiB of output text: finds its first row by bisection, a warp per row copies the part of
@@ -40,7 +41,7 @@ __global__ void __launch_bounds__(RING ? 32 : 128) k_pq_pages(SplPqWork w, const
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= count) return;
     const SplPqPage pg = w.pages[first + warp];
-    if ((pg.kind == SPL_PQ_DICT) != dict_pass) return;
+    if (spl_pq_first_pass(pg) != dict_pass) return;
     WarpLanes g{threadIdx.x & 31u, RING ? pq_smem : nullptr, RING ? pq_smem + SPL_SNAPPY_WIN : nullptr};
     const uint32_t err = spl_pq_decode_page(g, pg, w.file, w.scratch, SplPqSpans{w.row_off, w.row_len}, SplPqSpans{w.dict_off, w.dict_len});
     if (err && g.lane == 0) atomicOr(&w.counters[SPL_PQCTR_ERR], err);
@@ -166,7 +167,7 @@ int spl_launch_pq_spans(const SplPqWork& w, uint32_t first_page, uint32_t n_page
     // snappy out of shared memory (SPL_PQ_SNAPPY_RING=0: the plain decoder, every element through global memory -- A/B)
     static const bool ring_on = [] { const char* e = getenv("SPL_PQ_SNAPPY_RING"); return !e || e[0] != '0'; }();
     int n = 0;
-    for (int pass = has_dict ? 0 : 1; pass < 2; ++pass, ++n) {
+    for (int pass = 0; pass < (has_dict ? 2 : 1); ++pass, ++n) {            // without a dictionary page there is no second pass
         if (has_snappy && ring_on) {
             cudaFuncSetAttribute(k_pq_pages<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PQ_RING_SMEM);
             k_pq_pages<true><<<n_pages, 32, PQ_RING_SMEM, stream>>>(w, first_page, n_pages, pass == 0);

@@ -53,6 +53,10 @@ struct SplPqPage {
     uint8_t v2_compressed, pad_[3];
 };
 
+// Pages are decoded in two launches: dictionary pages and the data pages that need no dictionary (PLAIN) first, then
+// the dictionary-encoded data pages (they read the dictionary's spans).
+SPL_HD bool spl_pq_first_pass(const SplPqPage& pg) { return pg.kind == SPL_PQ_DICT || pg.encoding == SPL_PQ_ENC_PLAIN; }
+
 // A span of source bytes: what a row (or a dictionary entry) is.
 struct SplPqSpans { uint64_t* off; uint32_t* len; };
 

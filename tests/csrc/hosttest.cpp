@@ -493,7 +493,7 @@ extern "C" long ht_parquet(const uint8_t* file, size_t n, const char* column, ui
         uint32_t e = 0;
         for (int pass = 0; pass < 2; ++pass)
             for (size_t k = b.page0; k < b.page1; ++k) {
-                if ((plan.pages[k].kind == SPL_PQ_DICT) != (pass == 0)) continue;
+                if (spl_pq_first_pass(plan.pages[k]) != (pass == 0)) continue;
                 if (staged == 2)                                    // 32 lanes, as the device runs it
                     run_host_warp(g.win, g.inbuf, [&](const HostWarp& hw) {
                         const uint32_t pe = spl_pq_decode_page(hw, plan.pages[k], stage.data(), scratch.data(), R, D);
