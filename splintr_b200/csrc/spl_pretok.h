@@ -16,17 +16,7 @@
 
 struct SplChar { uint32_t cls; uint32_t len; };
 
-// the two-level table; spl_class_of_cp answers the CJK Unified Ideographs U+4E00..U+9FA5 (Lo in every Unicode version:
-// CLS_BOTH, tests/test_pretok_host.py holds the table to that) without the two dependent loads -- on Chinese text the
-// pre-tokenizer walks ten of them per 32-byte word, one after the other
-SPL_HD uint32_t spl_class_of_cp_table(uint32_t cp, const uint8_t* s1, const uint8_t* s2) {
-    uint32_t blk = s1[cp >> 8];
-    uint32_t v = s2[blk * 128u + ((cp & 255u) >> 1)];
-    return (cp & 1u) ? (v >> 4) : (v & 15u);
-}
-
 SPL_HD uint32_t spl_class_of_cp(uint32_t cp, const uint8_t* s1, const uint8_t* s2) {
-    if (cp - 0x4E00u <= 0x9FA5u - 0x4E00u) return CLS_BOTH;
     uint32_t blk = s1[cp >> 8];
     uint32_t v = s2[blk * 128u + ((cp & 255u) >> 1)];
     return (cp & 1u) ? (v >> 4) : (v & 15u);

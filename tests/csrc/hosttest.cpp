@@ -465,11 +465,6 @@ static void run_host_warp(uint8_t* win, uint8_t* inbuf, Fn fn) {
     for (auto& t : th) t.join();
 }
 
-// class of a code point: the table alone, and as the pre-tokenizer asks (with the CJK shortcut)
-extern "C" int ht_class_of_cp(uint32_t cp, int table_only) {
-    return (int)(table_only ? spl_class_of_cp_table(cp, spl_ucd_stage1, spl_ucd_stage2) : spl_class_of_cp(cp, spl_ucd_stage1, spl_ucd_stage2));
-}
-
 // ---- Parquet ingestion (row N4): the host plan (spl_parquet_meta.cpp) and the page decoder of spl_parquet.h with a
 // lane group of one, batch by batch, as spl_api.cu drives the device.  Returns the row count, or -1 (malformed: err),
 // -2 (unsupported: err), -3 (a page raised error bits: info[0]), -4 (capacities).  info[1] = batches, info[2] = pages.

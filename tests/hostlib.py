@@ -50,8 +50,6 @@ def load():
     lib.ht_parquet.restype = ctypes.c_long
     lib.ht_parquet.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_uint64, vp, ctypes.c_size_t, vp, ctypes.c_size_t,
                                ctypes.c_char_p, ctypes.c_size_t, vp, ctypes.c_int]
-    lib.ht_class_of_cp.restype = ctypes.c_int
-    lib.ht_class_of_cp.argtypes = [ctypes.c_uint32, ctypes.c_int]
     lib.ht_snappy.restype = ctypes.c_int
     lib.ht_snappy.argtypes = [ctypes.c_char_p, ctypes.c_uint32, vp, ctypes.c_uint32, ctypes.c_int]
     lib.ht_set_fast_ext.argtypes = [ctypes.c_int]

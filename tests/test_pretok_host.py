@@ -76,15 +76,3 @@ def test_kernel_work_split_multi_doc_small_window(name, pid):
         for tile, halo, chunk in ((32, 8, 4), (64, 16, 16), (16, 0, 16)):
             got = hostlib.scan_kernel_emul(pid, data, tile, halo, chunk, hard)
             assert got == sorted(set(want)), (name, docs, tile, halo, chunk)
-
-
-def test_cjk_shortcut_equals_the_class_table():
-    """spl_class_of_cp answers U+4E00..U+9FA5 without the table: every code point (all 0x110000 of them) must get the
-    class the two-level table holds -- and the oracle's regex module must agree that the range is \\p{Lo}."""
-    import regex
-    import hostlib
-    lib = hostlib.load()
-    bad = [cp for cp in range(0x110000) if lib.ht_class_of_cp(cp, 0) != lib.ht_class_of_cp(cp, 1)]
-    assert bad == [], [hex(c) for c in bad[:10]]
-    lo = regex.compile(r"\p{Lo}")
-    assert all(lo.fullmatch(chr(cp)) for cp in range(0x4E00, 0x9FA6))
