@@ -179,7 +179,8 @@ int upload_tables(spl_tokenizer* tk, DevCtx& dc) {
 
 void destroy_ctx(DevCtx& dc) {
     cudaSetDevice(dc.device);
-    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.ids, &dc.out_off, &dc.dec_ids, &dc.dec_off, &dc.dec_ws, &dc.dec_out, &dc.dec_out_off, &dc.jl_tiles, &dc.jl_lines, &dc.jl_text, &dc.jl_off, &dc.jl_out_off[0], &dc.jl_out_off[1], &dc.run_tot, &dc.sp_zero, &dc.sp_tiles, &dc.sp_text, &dc.sp_doc, &dc.zero, &dc.tstate, &dc.pv, &dc.pool, &dc.mlist, &dc.fbl, &dc.huge, &dc.dupof})
+    for (DevBuf* b : {&dc.text, &dc.doc_off, &dc.ids, &dc.out_off, &dc.dec_ids, &dc.dec_off, &dc.dec_ws, &dc.dec_out, &dc.dec_out_off, &dc.jl_tiles, &dc.jl_lines, &dc.jl_text, &dc.jl_off, &dc.jl_out_off[0], &dc.jl_out_off[1], &dc.run_tot, &dc.sp_zero, &dc.sp_tiles, &dc.sp_text, &dc.sp_doc, &dc.zero, &dc.tstate, &dc.pv, &dc.pool, &dc.mlist, &dc.fbl, &dc.huge, &dc.dupof,
+                       &dc.pq_stage, &dc.pq_scratch, &dc.pq_pages, &dc.pq_rows, &dc.pq_dict, &dc.pq_small})
         b->release();
     for (auto& g : dc.gc) { if (g.exec) cudaGraphExecDestroy(g.exec); if (g.graph) cudaGraphDestroy(g.graph); }
     if (dc.table_blob) cudaFree(dc.table_blob);
