@@ -1472,13 +1472,23 @@ __device__ __forceinline__ void emit_stage(const SplWork& w, EmitSmem& sm, const
             else if (w.charref && SPL_PV_IS_CHARREF(x)) {
                 const uint32_t* __restrict__ src = w.T->char_ids + (x & 0x0FFFFFFFu);
                 const uint32_t c = ((x >> 28) & 3u) + 1u;
-                for (uint32_t r = 0; r < c; ++r) put(pos + r, __ldg(src + r));
+                uint32_t t[4];                                   // all loads first: they are in flight together
+#pragma unroll
+                for (uint32_t r = 0; r < 4u; ++r) t[r] = r < c ? __ldg(src + r) : 0u;
+#pragma unroll
+                for (uint32_t r = 0; r < 4u; ++r) if (r < c) put(pos + r, t[r]);
                 pos += c;
             } else if (x != SPL_PV_NONE) {
                 const uint64_t e = w.mlist[x & ~SPL_PV_MISS];
                 const uint32_t gp = (uint32_t)e, c = (uint32_t)(e >> 32) & SPL_ML_LEN_MASK;
                 if (c <= EM_INLINE) {
-                    for (uint32_t r = 0; r < c; ++r) put(pos + r, w.pool[gp + r]);
+                    for (uint32_t r0 = 0; r0 < c; r0 += 4u) {       // four loads in flight, then their stores
+                        uint32_t t[4];
+#pragma unroll
+                        for (uint32_t r = 0; r < 4u; ++r) t[r] = r0 + r < c ? w.pool[gp + r0 + r] : 0u;
+#pragma unroll
+                        for (uint32_t r = 0; r < 4u; ++r) if (r0 + r < c) put(pos + r0 + r, t[r]);
+                    }
                 } else if (lo == 0) {
                     sm.bigj[atomicAdd(&sm.n_big, 1u)] = (uint16_t)(j4 + q);      // by a warp, after the barrier
                 }
